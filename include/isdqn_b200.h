@@ -1,0 +1,239 @@
+/*
+ * isdqn_b200.h — C-ABI of libisdqn_b200.so: the B200 (sm_100a) learner hot path of iS-DQN.
+ *
+ * The reference (theovincent/iS-DQN, package `slimdqn`) has no native boundary: the hot path sits behind a
+ * Python object API.  Every entry point below replaces the body of one reference method;
+ * the `replaces:` line cites it (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * stub a maintainer adds on the reference side, and the XLA-FFI wrapper shape for a JAX host.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller and borrowed for
+ *     the duration of the call; h_* are host pointers.  No entry point allocates device memory.
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless the function name ends in `_sync`.
+ *   - return value: 0 = ISDQN_OK, negative = ISDQN_E_* (see isdqn_strerror).  Nothing throws.
+ *   - data-dependent failures that the reference reports with exceptions (negative priority, target out of
+ *     range, ...) are reported through a caller-provided device status word `d_status` (bit mask ISDQN_ST_*),
+ *     OR-ed by the kernels; the host wrapper reads it when it needs the result anyway.
+ *   - thread-compatible: no global mutable state except the lazily dlopen'ed NCCL handle.
+ */
+#ifndef ISDQN_B200_H_
+#define ISDQN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISDQN_ABI_VERSION 1
+
+/* return codes */
+#define ISDQN_OK 0
+#define ISDQN_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, unsupported shape) */
+#define ISDQN_E_TOO_LARGE (-2)   /* request exceeds a documented kernel limit */
+#define ISDQN_E_CUDA (-3)        /* a CUDA runtime call failed; see isdqn_last_cuda_error() */
+#define ISDQN_E_UNSUPPORTED (-4) /* feature of the reference that is out of scope (batch_norm, impala) */
+#define ISDQN_E_NCCL (-5)        /* NCCL missing or a NCCL call failed */
+
+/* device status bits */
+#define ISDQN_ST_NEGATIVE_VALUE 1u   /* sum_tree.py:31 `assert (values >= 0.0).all()` would fire */
+#define ISDQN_ST_TARGET_RANGE 2u     /* sum_tree.py:74 ValueError: target outside [0, root) */
+#define ISDQN_ST_DESCENT_ASSERT 4u   /* sum_tree.py:82 `assert (targets < nodes[node]).all()` would fire */
+#define ISDQN_ST_EMPTY_TREE 8u       /* samplers.py:106 root == 0.0 */
+#define ISDQN_ST_INDEX_RANGE 16u      /* leaf index outside the heap (NumPy would raise IndexError / wrap) */
+#define ISDQN_ST_OP_TOO_LARGE 32u     /* an op of isdqn_sumtree_set_ops exceeds ISDQN_SUMTREE_OP_MAX */
+
+int isdqn_abi_version(void);
+const char* isdqn_strerror(int code);
+const char* isdqn_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------ sum tree
+ * Array heap of float64, `depth` levels, (1<<depth)-1 nodes, first leaf at (1<<(depth-1))-1
+ * (slimdqn/sample_collection/sum_tree.py:11-18). */
+
+/* replaces: SumTree.query  sum_tree.py:58-102.  Batched inverse-CDF descent, strict `<` go-left rule.
+ * d_out_index[i] = leaf index (int32).  Sets ISDQN_ST_TARGET_RANGE / ISDQN_ST_DESCENT_ASSERT. */
+int isdqn_sumtree_query(const double* d_nodes, int depth, const double* d_targets, int64_t n,
+                        int32_t* d_out_index, uint32_t* d_status, void* stream);
+
+/* replaces: SumTree.set  sum_tree.py:20-47.  De-duplicates (first occurrence wins), then applies
+ * delta = value - old_leaf to the leaf and every ancestor as a sequential left fold in ascending-leaf order
+ * (the np.add.at order), so the float64 node array is bit-identical to the reference's.
+ * *d_max_priority = max(*d_max_priority, max(values)) (sum_tree.py:32).  n <= ISDQN_SUMTREE_SET_MAX.
+ * If any value is negative/NaN nothing is modified and ISDQN_ST_NEGATIVE_VALUE is set. */
+#define ISDQN_SUMTREE_SET_MAX 8192
+int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_index, const double* d_value, int32_t n,
+                      double* d_max_priority, uint32_t* d_status, void* stream);
+
+/* A queue of `n_ops` sets applied strictly in order by one launch: op j covers entries
+ * [d_op_offset[j], d_op_offset[j+1]) of d_index/d_value, each op at most ISDQN_SUMTREE_OP_MAX entries.
+ * In this entry point only, a value -(1+j) means "the value leaf j holds when the op starts" (the swap-remove
+ * of samplers.py:99-102 without a device->host read).
+ * replaces: the per-transition SumTree.set calls of PrioritizedSamplingDistribution.add / .remove
+ * (samplers.py:67-74, 90-103), which the reference issues one NumPy call at a time. */
+#define ISDQN_SUMTREE_OP_MAX 1024
+int isdqn_sumtree_set_ops(double* d_nodes, int depth, const int32_t* d_op_offset, int32_t n_ops,
+                          const int32_t* d_index, const double* d_value, double* d_max_priority,
+                          uint32_t* d_status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ samplers
+ * d_rng: 6 x uint64 mirror of numpy's PCG64 state:
+ *   [0]=state low 64, [1]=state high 64, [2]=inc low, [3]=inc high, [4]=has_uint32, [5]=uinteger. */
+
+/* replaces: UniformSamplingDistribution.sample  samplers.py:39-49.
+ * Draws exactly what `Generator.integers(n_valid, size=size)` draws (PCG64 next32 stream + Lemire rejection),
+ * advances d_rng accordingly, d_out_index[i] = dense index, d_out_key[i] = d_index_to_key[index],
+ * d_out_slot[i] = key % capacity (may be NULL, as may d_out_key with d_index_to_key). size <= 1<<20. */
+int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t size, const int32_t* d_index_to_key,
+                         int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
+                         void* stream);
+
+/* replaces: PrioritizedSamplingDistribution.sample  samplers.py:105-116 (+ SumTree.query).
+ * targets = Generator.uniform(0.0, root, size) with root read on the device, then the descent of
+ * isdqn_sumtree_query.  d_out_target may be NULL.  Sets ISDQN_ST_EMPTY_TREE when root == 0. */
+int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size,
+                             const int32_t* d_index_to_key, int32_t capacity, int32_t* d_out_index,
+                             int32_t* d_out_key, int32_t* d_out_slot, double* d_out_target,
+                             uint32_t* d_status, void* stream);
+
+/* Scatter of host-accumulated patches into a device int32 table (index_to_key, element metadata):
+ * d_table[d_patch_index[i]*width + j] = d_patch_value[i*width + j].  Later patches win. */
+int isdqn_scatter_rows_i32(int32_t* d_table, int32_t width, const int32_t* d_patch_index,
+                           const int32_t* d_patch_value, int32_t n_patches, void* stream);
+int isdqn_scatter_rows_f64(double* d_table, const int32_t* d_patch_index, const double* d_patch_value,
+                           int32_t n_patches, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- gather
+ * Frame ring: `n_slots` frames of `frame_stride` bytes each (frame_stride % 16 == 0), slot `zero_slot` is all
+ * zeros and stands for the reference's zero padding (replay_buffer.py:131-147).  Element metadata is indexed by
+ * element slot = key % capacity: d_elem_frames[slot][2*stack] = ring slots of the `stack` state frames then the
+ * `stack` next_state frames; d_elem_action int64, d_elem_reward float64, d_elem_terminal uint8.
+ *
+ * replaces: ReplayBuffer.sample  replay_buffer.py:198-213 (itemgetter + unpack + np.stack) for the drawn slots.
+ * Outputs (batched on axis 0, layout = np.stack of ReplayElement fields):
+ *   d_out_state / d_out_next : [n][frame_elems][stack] of out_dtype, observation axis order preserved, stack last
+ *   d_out_action int64[n], d_out_reward float64[n], d_out_terminal uint8[n]   (any may be NULL) */
+#define ISDQN_OUT_RAW 0  /* same bytes as stored (bit-exact parity path) */
+#define ISDQN_OUT_F32 1  /* uint8 -> float32 x/255 (architectures/dqn.py:51), elem_size must be 1 */
+#define ISDQN_OUT_BF16 2 /* uint8 -> bfloat16(x/255), elem_size must be 1 */
+int isdqn_gather_stacks(const uint8_t* d_frames, int64_t frame_stride, int32_t frame_elems, int32_t elem_size,
+                        int32_t stack, const int32_t* d_elem_frames, const int64_t* d_elem_action,
+                        const double* d_elem_reward, const uint8_t* d_elem_terminal, const int32_t* d_slots,
+                        int32_t n, int32_t out_dtype, void* d_out_state, void* d_out_next,
+                        int64_t* d_out_action, double* d_out_reward, uint8_t* d_out_terminal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ learner
+ * Flat parameter vector: leaves packed in execution order, each leaf start aligned to 4 floats:
+ *   cnn: Conv_i.kernel (HWIO), Conv_i.bias, [LayerNorm_i.scale, LayerNorm_i.bias] for i=0..2, then the Dense
+ *        tail; fc: Dense tail only.  Dense kernels are (in, out) row-major; activations are NHWC.
+ * (slimdqn/networks/architectures/dqn.py:47-103; names are flax's auto-names.) */
+#define ISDQN_ARCH_CNN 0
+#define ISDQN_ARCH_FC 1
+#define ISDQN_MAX_FEATURES 8
+#define ISDQN_MAX_LEAVES 48
+
+typedef struct isdqn_net {
+  int32_t arch;        /* ISDQN_ARCH_* */
+  int32_t layer_norm;  /* 0/1 */
+  int32_t obs_h, obs_w, obs_c; /* cnn: (84,84,4); fc: obs_c = flattened observation size, h = w = 1 */
+  int32_t n_features;
+  int32_t features[ISDQN_MAX_FEATURES];
+  int32_t n_heads;     /* K = n_bellman_iterations (the net has 1+K heads) */
+  int32_t n_actions;   /* A */
+} isdqn_net;
+
+typedef struct isdqn_layout {
+  int32_t n_leaves;
+  int64_t offset[ISDQN_MAX_LEAVES]; /* in floats */
+  int64_t size[ISDQN_MAX_LEAVES];   /* in floats */
+  int64_t total;                    /* padded total, multiple of 4 */
+} isdqn_layout;
+
+int isdqn_net_layout(const isdqn_net* net, isdqn_layout* out);
+/* bytes of scratch the forward (n_rows images) / the training step (batch B) need */
+int64_t isdqn_forward_workspace_bytes(const isdqn_net* net, int32_t n_rows);
+int64_t isdqn_learn_workspace_bytes(const isdqn_net* net, int32_t batch);
+
+/* replaces: DQNNet.apply  architectures/dqn.py:47-103 (+ the reshape of isdqn.py:39-41, which is a view).
+ * d_input: cnn uint8 [n_rows][H][W][C] (normalised /255 inside) or, with input_is_float, float32 of the same
+ * shape (tests/utils.py feeds float32 in [0,1) which the reference also divides by 255); fc float32 [n_rows][D].
+ * d_q: float32 [n_rows][(1+K)*A]. */
+int isdqn_forward(const isdqn_net* net, const float* d_params, const void* d_input, int32_t input_is_float,
+                  int32_t n_rows, float* d_q, void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* replaces: the loss tail of iSDQN.loss_on_batch + compute_target  isdqn.py:97-109 and its gradient.
+ * d_q_all float32 [2B][(1+K)*A] (rows [0,B) = s, rows [B,2B) = s').  d_losses[k] = mean_b td^2 (k = 0..K-1);
+ * d_dq (may be NULL) float32 [B][(1+K)*A] = d(sum_k losses)/d q_all[:B], scaled with 1/batch_global.
+ * reward float64 -> float32, action int64, terminal uint8 (the dtypes rb.sample() yields). */
+int isdqn_heads_td_loss(const float* d_q_all, const int64_t* d_action, const double* d_reward,
+                        const uint8_t* d_terminal, float gamma_n, int32_t batch, int32_t batch_global,
+                        int32_t n_heads, int32_t n_actions, float* d_losses, float* d_dq, void* stream);
+
+/* replaces: optax.adam(lr, eps).update + optax.apply_updates  isdqn.py:46,85-86 (optax 0.2.4 semantics:
+ * eps outside the sqrt, bias correction with count+1).  *d_count is incremented on the device. */
+int isdqn_adam_step(float* d_params, const float* d_grads, float* d_mu, float* d_nu, int32_t* d_count, float lr,
+                    float b1, float b2, float eps, int64_t n, void* stream);
+
+/* Same update for a counter the caller already advanced (*d_count = t >= 1); used inside the fused step, where the
+ * loss kernel advances the counter so that the whole step stays one capturable launch sequence. */
+int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count,
+                            float lr, float b1, float b2, float eps, int64_t n, void* stream);
+
+/* replaces: iSDQN.shift_params  isdqn.py:111-125: kernel[:, :-A] = kernel[:, A:], bias[:-A] = bias[A:]. */
+int isdqn_shift_heads(float* d_kernel, float* d_bias, int32_t n_in, int32_t n_heads, int32_t n_actions,
+                      void* stream);
+
+typedef struct isdqn_batch {
+  const void* d_state;      /* cnn: uint8 [B][H][W][C]; fc: float32 [B][D] */
+  const void* d_next_state;
+  const int64_t* d_action;
+  const double* d_reward;
+  const uint8_t* d_terminal;
+} isdqn_batch;
+
+typedef struct isdqn_train {
+  float gamma_n;            /* gamma ** update_horizon */
+  float lr, b1, b2, eps;
+  int32_t batch;            /* rows on this device */
+  int32_t batch_global;     /* = batch unless data parallel */
+  float* d_params; float* d_grads; float* d_mu; float* d_nu; int32_t* d_count;
+  float* d_losses;          /* [K] per-head mean TD^2 of THIS step (local share under DP) */
+  void* d_workspace; int64_t workspace_bytes;
+  void* nccl_comm;          /* NULL, or the handle from isdqn_dp_init: gradients are all-reduced before Adam */
+} isdqn_train;
+
+/* replaces: iSDQN.loss_on_batch  isdqn.py:92-103 (forward on concat(s, s') + loss, no gradient). */
+int isdqn_loss_on_batch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* batch, float* d_q_all,
+                        void* stream);
+/* replaces: iSDQN.learn_on_batch  isdqn.py:82-90: forward, loss, backward, [allreduce], Adam — one call,
+ * graph-capturable (no host synchronisation, no allocation). */
+int isdqn_learn_on_batch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* batch, void* stream);
+/* backward only up to the gradient (used by parity tests and by the DP path) */
+int isdqn_grad_on_batch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* batch, void* stream);
+
+/* replaces: iSDQN.best_action  isdqn.py:127-135 for a given head index: argmax_a q[1+idx_network][a]. */
+int isdqn_best_action(const isdqn_net* net, const float* d_params, const void* d_state, int32_t input_is_float,
+                      int32_t idx_network, int32_t* d_action, void* d_workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------- CUDA graph helpers
+ * The step above is ~20 launches; at batch 32 it is launch-latency bound, so the host captures it once. */
+int isdqn_graph_begin(void* stream);
+int isdqn_graph_end(void* stream, void** out_graph_exec);
+int isdqn_graph_launch(void* graph_exec, void* stream);
+int isdqn_graph_destroy(void* graph_exec);
+
+/* -------------------------------------------------------------------------------------------- data parallel
+ * New functionality (the reference has no collective): gradient all-reduce over NVLink. NCCL is
+ * dlopen'ed on first use.  h_unique_id is the 128-byte ncclUniqueId produced on rank 0. */
+int isdqn_dp_unique_id(uint8_t* h_unique_id_128);
+int isdqn_dp_init(const uint8_t* h_unique_id_128, int32_t rank, int32_t world, void** out_comm);
+int isdqn_dp_allreduce_f32(void* comm, float* d_buf, int64_t n, void* stream);
+int isdqn_dp_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISDQN_B200_H_ */

@@ -1,0 +1,186 @@
+"""ctypes binding of libisdqn_b200.so (the C-ABI declared in include/isdqn_b200.h).
+
+There is no CPU fallback: if the library is missing or CUDA is unavailable the product raises
+`IsdqnNativeError` — loudly, at the first use of a device object.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libisdqn_b200.so")
+
+ABI_VERSION = 1
+MAX_FEATURES = 8
+MAX_LEAVES = 48
+SUMTREE_SET_MAX = 8192
+SUMTREE_OP_MAX = 1024
+
+ST_NEGATIVE_VALUE = 1
+ST_TARGET_RANGE = 2
+ST_DESCENT_ASSERT = 4
+ST_EMPTY_TREE = 8
+ST_INDEX_RANGE = 16
+ST_OP_TOO_LARGE = 32
+
+OUT_RAW, OUT_F32, OUT_BF16 = 0, 1, 2
+ARCH_CNN, ARCH_FC = 0, 1
+
+
+class IsdqnNativeError(RuntimeError):
+    pass
+
+
+class Net(C.Structure):
+    _fields_ = [
+        ("arch", C.c_int32),
+        ("layer_norm", C.c_int32),
+        ("obs_h", C.c_int32),
+        ("obs_w", C.c_int32),
+        ("obs_c", C.c_int32),
+        ("n_features", C.c_int32),
+        ("features", C.c_int32 * MAX_FEATURES),
+        ("n_heads", C.c_int32),
+        ("n_actions", C.c_int32),
+    ]
+
+
+class Layout(C.Structure):
+    _fields_ = [
+        ("n_leaves", C.c_int32),
+        ("offset", C.c_int64 * MAX_LEAVES),
+        ("size", C.c_int64 * MAX_LEAVES),
+        ("total", C.c_int64),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("d_state", C.c_void_p),
+        ("d_next_state", C.c_void_p),
+        ("d_action", C.c_void_p),
+        ("d_reward", C.c_void_p),
+        ("d_terminal", C.c_void_p),
+    ]
+
+
+class Train(C.Structure):
+    _fields_ = [
+        ("gamma_n", C.c_float),
+        ("lr", C.c_float),
+        ("b1", C.c_float),
+        ("b2", C.c_float),
+        ("eps", C.c_float),
+        ("batch", C.c_int32),
+        ("batch_global", C.c_int32),
+        ("d_params", C.c_void_p),
+        ("d_grads", C.c_void_p),
+        ("d_mu", C.c_void_p),
+        ("d_nu", C.c_void_p),
+        ("d_count", C.c_void_p),
+        ("d_losses", C.c_void_p),
+        ("d_workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+        ("nccl_comm", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_I32 = C.c_int32
+_I64 = C.c_int64
+_F = C.c_float
+
+# name -> (restype, argtypes); every symbol include/isdqn_b200.h declares
+PROTOTYPES = {
+    "isdqn_abi_version": (C.c_int, []),
+    "isdqn_strerror": (C.c_char_p, [C.c_int]),
+    "isdqn_last_cuda_error": (C.c_char_p, []),
+    "isdqn_sumtree_query": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P, _P]),
+    "isdqn_sumtree_set": (C.c_int, [_P, C.c_int, _P, _P, _I32, _P, _P, _P]),
+    "isdqn_sumtree_set_ops": (C.c_int, [_P, C.c_int, _P, _I32, _P, _P, _P, _P, _P]),
+    "isdqn_sample_uniform": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
+    "isdqn_sample_prioritized": (C.c_int, [_P, _P, C.c_int, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "isdqn_scatter_rows_i32": (C.c_int, [_P, _I32, _P, _P, _I32, _P]),
+    "isdqn_scatter_rows_f64": (C.c_int, [_P, _P, _P, _I32, _P]),
+    "isdqn_gather_stacks": (
+        C.c_int,
+        [_P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P],
+    ),
+    "isdqn_net_layout": (C.c_int, [C.POINTER(Net), C.POINTER(Layout)]),
+    "isdqn_forward_workspace_bytes": (_I64, [C.POINTER(Net), _I32]),
+    "isdqn_learn_workspace_bytes": (_I64, [C.POINTER(Net), _I32]),
+    "isdqn_forward": (C.c_int, [C.POINTER(Net), _P, _P, _I32, _I32, _P, _P, _I64, _P]),
+    "isdqn_heads_td_loss": (C.c_int, [_P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "isdqn_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
+    "isdqn_adam_step_nocount": (C.c_int, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
+    "isdqn_shift_heads": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+    "isdqn_loss_on_batch": (C.c_int, [C.POINTER(Net), C.POINTER(Train), C.POINTER(Batch), _P, _P]),
+    "isdqn_learn_on_batch": (C.c_int, [C.POINTER(Net), C.POINTER(Train), C.POINTER(Batch), _P]),
+    "isdqn_grad_on_batch": (C.c_int, [C.POINTER(Net), C.POINTER(Train), C.POINTER(Batch), _P]),
+    "isdqn_best_action": (C.c_int, [C.POINTER(Net), _P, _P, _I32, _I32, _P, _P, _I64, _P]),
+    "isdqn_graph_begin": (C.c_int, [_P]),
+    "isdqn_graph_end": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "isdqn_graph_launch": (C.c_int, [_P, _P]),
+    "isdqn_graph_destroy": (C.c_int, [_P]),
+    "isdqn_dp_unique_id": (C.c_int, [_P]),
+    "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),
+    "isdqn_dp_destroy": (C.c_int, [_P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library (no GPU needed for this) and binds every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IsdqnNativeError(
+            f"{LIB_PATH} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "isdqn_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise IsdqnNativeError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.isdqn_abi_version() != ABI_VERSION:
+        raise IsdqnNativeError(f"ABI mismatch: library {lib.isdqn_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == 0:
+        return
+    lib = load()
+    msg = lib.isdqn_strerror(rc).decode()
+    detail = lib.isdqn_last_cuda_error().decode() if rc in (-3, -5) else ""
+    raise IsdqnNativeError(f"{what or 'isdqn call'} failed: {msg} ({rc}) {detail}".strip())
+
+
+def require_cuda():
+    """Returns torch after making sure a CUDA device is usable; raises loudly otherwise."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise IsdqnNativeError("isdqn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    load()
+    return torch
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()

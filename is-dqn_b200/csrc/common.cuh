@@ -1,0 +1,78 @@
+// Shared device/host helpers for libisdqn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/isdqn_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libisdqn_b200 targets sm_100a (B200) only"
+#endif
+
+namespace isdqn {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_last_cuda_error(cudaError_t e, const char* where);
+
+#define ISDQN_CUDA_CHECK(expr)                              \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) {                                \
+      ::isdqn::set_last_cuda_error(_e, #expr);              \
+      return ISDQN_E_CUDA;                                  \
+    }                                                       \
+  } while (0)
+
+#define ISDQN_LAUNCH_CHECK() ISDQN_CUDA_CHECK(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Exclusive prefix sum of one int per thread over the whole CTA (THREADS <= 1024, multiple of 32).
+// warp_tot: 32 ints of shared memory, total: 1 int of shared memory.  Contains two __syncthreads().
+template <int THREADS>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int* total) {
+  // v: per-thread count; returns the exclusive prefix over the block; *total = block sum.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < THREADS / 32 ? warp_tot[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += y;
+    }
+    if (lane < THREADS / 32) warp_tot[lane] = winc - w;  // exclusive warp offsets
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  const int res = warp_tot[warp] + inc - v;
+  return res;
+}
+
+}  // namespace isdqn

@@ -1,0 +1,787 @@
+// fp32 learner kernels (CUDA-core FFMA, fp32 accumulate): the 1e-5 parity path of the iS-DQN learner.
+//
+//   conv_fwd_kernel    implicit GEMM (im2col gathered on the fly), one CTA covers ALL output channels of its
+//                      rows, so bias + LayerNorm-over-channels + ReLU (architectures/dqn.py:55-72) run in the
+//                      epilogue out of registers; also emits the normalised value and 1/std for the rows that
+//                      get a backward pass.
+//   conv_wgrad_kernel  dW[K][Cout] = im2col(X)^T dZ, split over the rows, deterministic partial sums.
+//   conv_dgrad_kernel  dX = dZ (*) W^T as a gather (no atomics), stride-s convs split into s*s parity classes so
+//                      only the taps that really hit an input pixel are multiplied.
+//   gemm_strided_kernel  Dense forward / wgrad / dgrad with arbitrary operand strides and split-K.
+//   dense_finalize_kernel, ln_relu_bwd_*_kernel, reduce_segments_kernel, heads_td_loss_kernel, adam_kernel.
+#pragma once
+#include "common.cuh"
+
+namespace isdqn {
+
+constexpr int kGemmThreads = 128;
+constexpr int kTM = 4;
+constexpr int kBK = 16;
+constexpr float kLnEps = 1e-6f;  // flax nn.LayerNorm default
+
+template <int BM, int BN, int TN>
+struct TileCfg {
+  static constexpr int LANES_N = BN / TN;
+  static constexpr int ROWS_T = kGemmThreads / LANES_N;
+  static_assert(ROWS_T * kTM == BM, "tile shape must use exactly 128 threads");
+  static_assert(TN % 4 == 0, "TN must be a multiple of 4");
+};
+
+template <int BM, int BN, int TN>
+__device__ __forceinline__ void tile_fma(const float (*As)[BM + 4], const float (*Bs)[BN + 4], float (&acc)[kTM][TN],
+                                         int ty, int tx) {
+#pragma unroll
+  for (int kk = 0; kk < kBK; ++kk) {
+    const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * kTM]);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    float b[TN];
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
+      b[j] = b4.x; b[j + 1] = b4.y; b[j + 2] = b4.z; b[j + 3] = b4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ input readers
+enum { IN_U8_255 = 0, IN_F32 = 1, IN_F32_255 = 2 };
+
+template <int KIND>
+__device__ __forceinline__ float read_in(const void* p, int64_t idx) {
+  if (KIND == IN_U8_255) return __fdiv_rn((float)reinterpret_cast<const uint8_t*>(p)[idx], 255.0f);
+  if (KIND == IN_F32_255) return __fdiv_rn(reinterpret_cast<const float*>(p)[idx], 255.0f);
+  return reinterpret_cast<const float*>(p)[idx];
+}
+
+struct ConvArgs {
+  const void* in0;  // images [0, n_img0)
+  const void* in1;  // images [n_img0, ...) (the s' half of concat(s, s'), isdqn.py:95); may be null
+  int n_img0;
+  int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x;
+  int M, K;  // M = n_img*OH*OW rows, K = ksz*ksz*Cin
+  const float* w;     // [K][Cout]  (HWIO flattened)
+  const float* bias;  // [Cout]
+  const float* ln_g;  // [Cout] or null
+  const float* ln_b;
+  int relu;
+  float* out;   // [M][Cout]
+  float* xhat;  // [m_train][Cout] or null
+  float* rstd;  // [m_train] or null
+  int m_train;
+};
+
+// ----------------------------------------------------------------------------------------------- conv fwd
+template <int BM, int BN, int TN, int KIND>
+__global__ void __launch_bounds__(kGemmThreads) conv_fwd_kernel(const ConvArgs a) {
+  typedef TileCfg<BM, BN, TN> Cfg;
+  __shared__ __align__(16) float As[kBK][BM + 4];
+  __shared__ __align__(16) float Bs[kBK][BN + 4];
+  __shared__ int ri_img[BM], ri_iy0[BM], ri_ix0[BM];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM;
+  const int tx = tid % Cfg::LANES_N, ty = tid / Cfg::LANES_N;
+
+  for (int r = tid; r < BM; r += kGemmThreads) {
+    const int m = m0 + r;
+    if (m < a.M) {
+      const int img = m / (a.OH * a.OW);
+      const int rem = m - img * (a.OH * a.OW);
+      const int oy = rem / a.OW, ox = rem - oy * a.OW;
+      ri_img[r] = img;
+      ri_iy0[r] = oy * a.stride - a.pad_y;
+      ri_ix0[r] = ox * a.stride - a.pad_x;
+    } else {
+      ri_img[r] = -1;
+      ri_iy0[r] = ri_ix0[r] = 0;
+    }
+  }
+  __syncthreads();
+
+  float acc[kTM][TN];
+#pragma unroll
+  for (int i = 0; i < kTM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int a_kk = tid % kBK, a_r0 = tid / kBK;
+  constexpr int A_ROWS_PER_PASS = kGemmThreads / kBK;
+  for (int k0 = 0; k0 < a.K; k0 += kBK) {
+    {  // A tile: im2col gather, k (= ky,kx,c with c fastest: contiguous in NHWC) fastest across lanes
+      const int k = k0 + a_kk;
+      const bool kvalid = k < a.K;
+      const int c = k % a.Cin;
+      const int t = k / a.Cin;
+      const int kx = t % a.ksz, ky = t / a.ksz;
+#pragma unroll
+      for (int r = a_r0; r < BM; r += A_ROWS_PER_PASS) {
+        float v = 0.f;
+        const int img = ri_img[r];
+        const int iy = ri_iy0[r] + ky, ix = ri_ix0[r] + kx;
+        if (kvalid && img >= 0 && (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W) {
+          const bool second = img >= a.n_img0;
+          const void* src = second ? a.in1 : a.in0;
+          const int li = second ? img - a.n_img0 : img;
+          v = read_in<KIND>(src, (((int64_t)li * a.H + iy) * a.W + ix) * a.Cin + c);
+        }
+        As[a_kk][r] = v;
+      }
+    }
+    for (int i = tid; i < kBK * BN; i += kGemmThreads) {  // B tile: weights, n fastest
+      const int nn = i % BN, kk = i / BN;
+      const int k = k0 + kk;
+      Bs[kk][nn] = (k < a.K && nn < a.Cout) ? __ldg(a.w + (int64_t)k * a.Cout + nn) : 0.f;
+    }
+    __syncthreads();
+    tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
+    __syncthreads();
+  }
+
+  // epilogue: bias -> LayerNorm over the channel axis -> ReLU, all out of registers
+  float bias[TN], g[TN], be[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = tx * TN + j;
+    const bool nv = n < a.Cout;
+    bias[j] = nv ? a.bias[n] : 0.f;
+    g[j] = (nv && a.ln_g) ? a.ln_g[n] : 0.f;
+    be[j] = (nv && a.ln_g) ? a.ln_b[n] : 0.f;
+  }
+  const float inv_c = 1.0f / (float)a.Cout;
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    const int m = m0 + ty * kTM + i;
+    float z[TN];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      z[j] = acc[i][j] + bias[j];
+      if (tx * TN + j < a.Cout) s += z[j];
+    }
+    float y[TN], xh[TN], r = 0.f;
+    if (a.ln_g) {
+#pragma unroll
+      for (int o = Cfg::LANES_N / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      float s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const float d = z[j] - mean;
+        if (tx * TN + j < a.Cout) s2 += d * d;
+      }
+#pragma unroll
+      for (int o = Cfg::LANES_N / 2; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      r = rsqrtf(s2 * inv_c + kLnEps);
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        xh[j] = (z[j] - mean) * r;
+        y[j] = xh[j] * g[j] + be[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) y[j] = z[j];
+    }
+    if (m < a.M) {
+      const bool save = a.xhat != nullptr && a.ln_g != nullptr && m < a.m_train;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int n = tx * TN + j;
+        if (n < a.Cout) {
+          a.out[(int64_t)m * a.Cout + n] = a.relu ? fmaxf(y[j], 0.f) : y[j];
+          if (save) a.xhat[(int64_t)m * a.Cout + n] = xh[j];
+        }
+      }
+      if (save && tx == 0) a.rstd[m] = r;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------- conv wgrad
+struct ConvWgradArgs {
+  const void* in;  // layer input for the rows with a backward pass: [n_img][H][W][Cin]
+  int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x;
+  int M, K;
+  const float* dz;  // [M][Cout]
+  float* part;      // [splits][K][Cout]
+  int rows_per_split;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kGemmThreads) conv_wgrad_kernel(const ConvWgradArgs a) {
+  constexpr int BM = 64, BN = 64, TN = 8;  // BM tiles the K (= ky,kx,c) axis of dW, BN its Cout axis
+  typedef TileCfg<BM, BN, TN> Cfg;
+  __shared__ __align__(16) float As[kBK][BM + 4];
+  __shared__ __align__(16) float Bs[kBK][BN + 4];
+  __shared__ int ri_img[kBK], ri_iy0[kBK], ri_ix0[kBK];
+  const int tid = threadIdx.x;
+  const int kc0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tx = tid % Cfg::LANES_N, ty = tid / Cfg::LANES_N;
+  const int m_begin = blockIdx.z * a.rows_per_split;
+  const int m_end = min(a.M, m_begin + a.rows_per_split);
+
+  // this thread always gathers the same column kc of the im2col matrix
+  const int a_mm = tid % BM, a_kk0 = tid / BM;
+  const int kc = kc0 + a_mm;
+  const bool kcvalid = kc < a.K;
+  const int c = kc % a.Cin;
+  const int t = kc / a.Cin;
+  const int kx = t % a.ksz, ky = t / a.ksz;
+  const int b_nn = tid % BN, b_kk0 = tid / BN;
+
+  float acc[kTM][TN];
+#pragma unroll
+  for (int i = 0; i < kTM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int mb = m_begin; mb < m_end; mb += kBK) {
+    if (tid < kBK) {
+      const int m = mb + tid;
+      if (m < m_end) {
+        const int img = m / (a.OH * a.OW);
+        const int rem = m - img * (a.OH * a.OW);
+        const int oy = rem / a.OW, ox = rem - oy * a.OW;
+        ri_img[tid] = img;
+        ri_iy0[tid] = oy * a.stride - a.pad_y;
+        ri_ix0[tid] = ox * a.stride - a.pad_x;
+      } else {
+        ri_img[tid] = -1;
+        ri_iy0[tid] = ri_ix0[tid] = 0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = a_kk0; kk < kBK; kk += kGemmThreads / BM) {
+      float v = 0.f;
+      const int img = ri_img[kk];
+      const int iy = ri_iy0[kk] + ky, ix = ri_ix0[kk] + kx;
+      if (kcvalid && img >= 0 && (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
+        v = read_in<KIND>(a.in, (((int64_t)img * a.H + iy) * a.W + ix) * a.Cin + c);
+      As[kk][a_mm] = v;
+    }
+#pragma unroll
+    for (int kk = b_kk0; kk < kBK; kk += kGemmThreads / BN) {
+      const int m = mb + kk;
+      const int n = n0 + b_nn;
+      Bs[kk][b_nn] = (m < m_end && n < a.Cout) ? a.dz[(int64_t)m * a.Cout + n] : 0.f;
+    }
+    __syncthreads();
+    tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
+    __syncthreads();
+  }
+  float* dst = a.part + (int64_t)blockIdx.z * a.K * a.Cout;
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    const int k = kc0 + ty * kTM + i;
+    if (k >= a.K) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < a.Cout) dst[(int64_t)k * a.Cout + n] = acc[i][j];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------- conv dgrad
+struct ConvDgradArgs {
+  int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x;
+  int n_img;
+  int taps;  // ceil(ksz / stride): taps per axis that can hit one input pixel
+  int Kd;    // taps*taps*Cout
+  const float* dz;  // [n_img*OH*OW][Cout]
+  const float* w;   // [ksz][ksz][Cin][Cout]
+  float* dx;        // [n_img*H*W][Cin]
+};
+
+__global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const ConvDgradArgs a) {
+  constexpr int BM = 64, BN = 64, TN = 8;
+  typedef TileCfg<BM, BN, TN> Cfg;
+  __shared__ __align__(16) float As[kBK][BM + 4];
+  __shared__ __align__(16) float Bs[kBK][BN + 4];
+  __shared__ int ri_img[BM], ri_oy[BM], ri_ox[BM], ri_pix[BM];
+  const int tid = threadIdx.x;
+  const int tx = tid % Cfg::LANES_N, ty = tid / Cfg::LANES_N;
+  const int s = a.stride;
+  // parity class of this CTA: input pixels with (iy + pad_y) % s == ry, (ix + pad_x) % s == rx
+  const int ry = blockIdx.z / s, rx = blockIdx.z % s;
+  const int iy_first = ((ry - a.pad_y) % s + s) % s, ix_first = ((rx - a.pad_x) % s + s) % s;
+  const int ny = iy_first < a.H ? (a.H - iy_first + s - 1) / s : 0;
+  const int nx = ix_first < a.W ? (a.W - ix_first + s - 1) / s : 0;
+  const int rows = a.n_img * ny * nx;
+  const int m0 = blockIdx.x * BM;
+  if (m0 >= rows) return;
+  const int n0 = blockIdx.y * BN;
+
+  for (int r = tid; r < BM; r += kGemmThreads) {
+    const int m = m0 + r;
+    if (m < rows) {
+      const int img = m / (ny * nx);
+      const int rem = m - img * (ny * nx);
+      const int iyc = rem / nx, ixc = rem - iyc * nx;
+      const int iy = iy_first + s * iyc, ix = ix_first + s * ixc;
+      ri_img[r] = img;
+      ri_oy[r] = (iy + a.pad_y - ry) / s;  // output row hit by tap ty_=0; tap ty_ hits oy - ty_
+      ri_ox[r] = (ix + a.pad_x - rx) / s;
+      ri_pix[r] = (img * a.H + iy) * a.W + ix;
+    } else {
+      ri_img[r] = -1;
+      ri_oy[r] = ri_ox[r] = ri_pix[r] = 0;
+    }
+  }
+  __syncthreads();
+
+  float acc[kTM][TN];
+#pragma unroll
+  for (int i = 0; i < kTM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int a_kk = tid % kBK, a_r0 = tid / kBK;
+  for (int k0 = 0; k0 < a.Kd; k0 += kBK) {
+    const int k = k0 + a_kk;
+    const int co = k % a.Cout;
+    const int t = k / a.Cout;
+    const int tx_ = t % a.taps, ty_ = t / a.taps;
+    const int ky = ry + s * ty_, kx = rx + s * tx_;
+    const bool tapvalid = k < a.Kd && ky < a.ksz && kx < a.ksz;
+#pragma unroll
+    for (int r = a_r0; r < BM; r += kGemmThreads / kBK) {
+      float v = 0.f;
+      const int img = ri_img[r];
+      const int oy = ri_oy[r] - ty_, ox = ri_ox[r] - tx_;
+      if (tapvalid && img >= 0 && (unsigned)oy < (unsigned)a.OH && (unsigned)ox < (unsigned)a.OW)
+        v = a.dz[(((int64_t)img * a.OH + oy) * a.OW + ox) * a.Cout + co];
+      As[a_kk][r] = v;
+    }
+#pragma unroll
+    for (int nn = a_r0; nn < BN; nn += kGemmThreads / kBK) {  // B tile: W[ky][kx][c][co], co (= k) fastest
+      const int cc = n0 + nn;
+      Bs[a_kk][nn] = (tapvalid && cc < a.Cin) ? __ldg(a.w + (((int64_t)ky * a.ksz + kx) * a.Cin + cc) * a.Cout + co) : 0.f;
+    }
+    __syncthreads();
+    tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    const int r = ty * kTM + i;
+    if (ri_img[r] < 0) continue;
+    float* dst = a.dx + (int64_t)ri_pix[r] * a.Cin;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int cc = n0 + tx * TN + j;
+      if (cc < a.Cin) dst[cc] = acc[i][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ strided GEMM
+struct GemmArgs {
+  const float* A; int64_t sam, sak;  // A(m,k) = A[m*sam + k*sak]
+  const float* B; int64_t sbk, sbn;  // B(k,n) = B[k*sbk + n*sbn]
+  float* C; int64_t ldc;             // split z writes C + z*split_stride
+  int64_t split_stride;
+  int M, N, K, k_per_split;
+  const float* bias;                 // optional (splits == 1): C = A B + bias[n]
+};
+
+template <bool A_KFAST, bool B_NFAST>
+__global__ void __launch_bounds__(kGemmThreads) gemm_strided_kernel(const GemmArgs g) {
+  constexpr int BM = 64, BN = 64, TN = 8;
+  typedef TileCfg<BM, BN, TN> Cfg;
+  __shared__ __align__(16) float As[kBK][BM + 4];
+  __shared__ __align__(16) float Bs[kBK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tx = tid % Cfg::LANES_N, ty = tid / Cfg::LANES_N;
+  const int k_begin = blockIdx.z * g.k_per_split;
+  const int k_end = min(g.K, k_begin + g.k_per_split);
+
+  float acc[kTM][TN];
+#pragma unroll
+  for (int i = 0; i < kTM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = k_begin; k0 < k_end; k0 += kBK) {
+#pragma unroll
+    for (int i = tid; i < BM * kBK; i += kGemmThreads) {
+      const int kk = A_KFAST ? i % kBK : i / BM;
+      const int mm = A_KFAST ? i / kBK : i % BM;
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < k_end) ? __ldg(g.A + (int64_t)m * g.sam + (int64_t)k * g.sak) : 0.f;
+    }
+#pragma unroll
+    for (int i = tid; i < BN * kBK; i += kGemmThreads) {
+      const int nn = B_NFAST ? i % BN : i / kBK;
+      const int kk = B_NFAST ? i / BN : i % kBK;
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < g.N && k < k_end) ? __ldg(g.B + (int64_t)k * g.sbk + (int64_t)n * g.sbn) : 0.f;
+    }
+    __syncthreads();
+    tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
+    __syncthreads();
+  }
+  float* C = g.C + (int64_t)blockIdx.z * g.split_stride;
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    const int m = m0 + ty * kTM + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < g.N) C[(int64_t)m * g.ldc + n] = acc[i][j] + (g.bias ? g.bias[n] : 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------- dense finalize (bias + LN + ReLU)
+constexpr int kRowThreads = 256;
+constexpr int kRowMaxPerThread = 8;  // dense widths up to 2048
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kRowThreads / 32; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+// out[r][n] = act( LN( sum_s part[s][r][n] + bias[n] ) ); one CTA per row
+__global__ void __launch_bounds__(kRowThreads)
+dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int rows, int N,
+                      const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                      int relu, float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
+                      int rows_train) {
+  __shared__ float red[kRowThreads / 32];
+  const int r = blockIdx.x;
+  float z[kRowMaxPerThread];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = threadIdx.x + j * kRowThreads;
+    z[j] = 0.f;
+    if (n < N) {
+      float v = 0.f;
+      for (int sp = 0; sp < splits; ++sp) v += part[(int64_t)sp * split_stride + (int64_t)r * N + n];
+      z[j] = v + bias[n];
+      s += z[j];
+    }
+  }
+  float rs = 0.f;
+  if (ln_g) {
+    const float mean = block_sum_256(s, red) / (float)N;
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = threadIdx.x + j * kRowThreads;
+      if (n < N) {
+        z[j] -= mean;
+        s2 += z[j] * z[j];
+      }
+    }
+    rs = rsqrtf(block_sum_256(s2, red) / (float)N + kLnEps);
+  }
+  const bool save = ln_g && xhat && r < rows_train;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = threadIdx.x + j * kRowThreads;
+    if (n < N) {
+      float y = z[j];
+      if (ln_g) {
+        const float xh = z[j] * rs;
+        if (save) xhat[(int64_t)r * N + n] = xh;
+        y = xh * ln_g[n] + ln_b[n];
+      }
+      out[(int64_t)r * N + n] = relu ? fmaxf(y, 0.f) : y;
+    }
+  }
+  if (save && threadIdx.x == 0) rstd[r] = rs;
+}
+
+// --------------------------------------------------------------------------------- LN + ReLU backward
+// In place: d (= dL/d out, post-ReLU) -> dz (= dL/d pre-LayerNorm conv/dense output).
+//   mask = out > 0 ; dy = d*mask ; g = dy*gamma ; dz = rstd * (g - mean(g) - xhat*mean(g*xhat))
+// Column partial sums per CTA (fixed order => deterministic): [0]=sum dz (dbias) [1]=sum dy*xhat (dgamma)
+// [2]=sum dy (dbeta).  Without LayerNorm: dz = dy, only [0] is meaningful.
+// Variant A: C <= 256, one warp per row.
+__global__ void __launch_bounds__(256)
+ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
+                        const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                        const float* __restrict__ act, int rows, int C, float* __restrict__ colpart) {
+  constexpr int MAXJ = 8;
+  __shared__ float sm[8][3][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float c0[MAXJ], c1[MAXJ], c2[MAXJ], gam[MAXJ], bet[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    c0[j] = c1[j] = c2[j] = 0.f;
+    const int n = lane + 32 * j;
+    gam[j] = (ln_g && n < C) ? ln_g[n] : 0.f;
+    bet[j] = (ln_g && n < C) ? ln_b[n] : 0.f;
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    float dy[MAXJ], xh[MAXJ];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int n = lane + 32 * j;
+      dy[j] = xh[j] = 0.f;
+      if (n < C) {
+        const int64_t idx = (int64_t)r * C + n;
+        const float dv = d[idx];
+        if (ln_g) {
+          xh[j] = xhat[idx];
+          dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;
+          const float g = dy[j] * gam[j];
+          sg += g;
+          sgx += g * xh[j];
+        } else {
+          dy[j] = act[idx] > 0.f ? dv : 0.f;
+        }
+      }
+    }
+    float rs = 0.f, mg = 0.f, mgx = 0.f;
+    if (ln_g) {
+      mg = warp_sum(sg) * inv_c;
+      mgx = warp_sum(sgx) * inv_c;
+      rs = rstd[r];
+    }
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int n = lane + 32 * j;
+      if (n < C) {
+        const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
+        d[(int64_t)r * C + n] = dz;
+        c0[j] += dz;
+        c1[j] += dy[j] * xh[j];
+        c2[j] += dy[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    sm[warp][0][lane + 32 * j] = c0[j];
+    sm[warp][1][lane + 32 * j] = c1[j];
+    sm[warp][2][lane + 32 * j] = c2[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    const int which = i / C, n = i - which * C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][which][n];
+    colpart[((int64_t)blockIdx.x * 3 + which) * C + n] = t;
+  }
+}
+
+// Variant B: any C <= 2048 (dense layers), one CTA walks its rows, thread t owns columns t, t+256, ...
+__global__ void __launch_bounds__(kRowThreads)
+ln_relu_bwd_block_kernel(float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
+                         const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                         const float* __restrict__ act, int rows, int C, float* __restrict__ colpart) {
+  __shared__ float red[kRowThreads / 32];
+  float c0[kRowMaxPerThread], c1[kRowMaxPerThread], c2[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    c0[j] = c1[j] = c2[j] = 0.f;
+    const int n = threadIdx.x + j * kRowThreads;
+    gam[j] = (ln_g && n < C) ? ln_g[n] : 0.f;
+    bet[j] = (ln_g && n < C) ? ln_b[n] : 0.f;
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    float dy[kRowMaxPerThread], xh[kRowMaxPerThread];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = threadIdx.x + j * kRowThreads;
+      dy[j] = xh[j] = 0.f;
+      if (n < C) {
+        const int64_t idx = (int64_t)r * C + n;
+        const float dv = d[idx];
+        if (ln_g) {
+          xh[j] = xhat[idx];
+          dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;
+          const float g = dy[j] * gam[j];
+          sg += g;
+          sgx += g * xh[j];
+        } else {
+          dy[j] = act[idx] > 0.f ? dv : 0.f;
+        }
+      }
+    }
+    float rs = 0.f, mg = 0.f, mgx = 0.f;
+    if (ln_g) {
+      mg = block_sum_256(sg, red) * inv_c;
+      mgx = block_sum_256(sgx, red) * inv_c;
+      rs = rstd[r];
+    }
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = threadIdx.x + j * kRowThreads;
+      if (n < C) {
+        const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
+        d[(int64_t)r * C + n] = dz;
+        c0[j] += dz;
+        c1[j] += dy[j] * xh[j];
+        c2[j] += dy[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = threadIdx.x + j * kRowThreads;
+    if (n < C) {
+      colpart[((int64_t)blockIdx.x * 3 + 0) * C + n] = c0[j];
+      colpart[((int64_t)blockIdx.x * 3 + 1) * C + n] = c1[j];
+      colpart[((int64_t)blockIdx.x * 3 + 2) * C + n] = c2[j];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- deterministic partial reduce
+constexpr int kMaxSegments = 40;
+struct Segment {
+  const float* src;  // partial p of element i at src[p*stride + i]
+  float* dst;
+  int64_t stride;
+  int n, parts;
+};
+struct SegmentList {
+  int count;
+  Segment s[kMaxSegments];
+};
+
+__global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
+  const Segment sg = list.s[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int p = 0; p < sg.parts; ++p) t += sg.src[(int64_t)p * sg.stride + i];
+    sg.dst[i] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------ K-head TD loss fwd + bwd
+// isdqn.py:97-109.  Single CTA, fixed reduction order.  Also: bumps the Adam step counter (so the following
+// adam_kernel of the same step reads count+1 with no race) and produces the bias gradient of the head layer.
+constexpr int kLossThreads = 256;
+constexpr int kMaxHeads = 64;
+
+__global__ void __launch_bounds__(kLossThreads)
+heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action,
+                     const double* __restrict__ reward, const uint8_t* __restrict__ terminal, float gamma_n, int B,
+                     int B_global, int K, int A, float* __restrict__ losses, float* __restrict__ dq,
+                     float* __restrict__ dbias, int32_t* count) {
+  __shared__ float red[kLossThreads / 32][kMaxHeads];
+  const int n_out = (1 + K) * A;
+  const int tid = threadIdx.x;
+  if (dq)
+    for (int i = tid; i < B * n_out; i += kLossThreads) dq[i] = 0.f;
+  __syncthreads();
+  float part[kMaxHeads];
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) part[k] = 0.f;
+  const float inv_b = 1.0f / (float)B_global;
+  for (int b = tid; b < B; b += kLossThreads) {
+    const int a = (int)action[b];
+    const float r = (float)reward[b];                       // f64 -> f32 at the jit boundary
+    const float coef = (float)(1 - (int)terminal[b]) * gamma_n;  // ((1 - d) * gamma^n) in fp32
+    const float* qs = q_all + (int64_t)b * n_out;           // Q(s, .)
+    const float* qn = q_all + (int64_t)(B + b) * n_out;     // Q(s', .)
+    for (int k = 0; k < K; ++k) {
+      float mx = qn[k * A];
+      for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[k * A + j]);
+      const float target = r + coef * mx;  // head k+1 regresses onto head k
+      const float td = qs[(k + 1) * A + a] - target;
+      part[k] += td * td;
+      if (dq) dq[(int64_t)b * n_out + (k + 1) * A + a] = 2.0f * td * inv_b;
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    const float v = warp_sum(part[k]);
+    if ((tid & 31) == 0) red[tid >> 5][k] = v;
+  }
+  __syncthreads();
+  if (tid < K) {
+    float t = 0.f;
+    for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][tid];
+    losses[tid] = t * inv_b;
+  }
+  if (dbias && dq) {
+    __syncthreads();
+    for (int n = tid; n < n_out; n += kLossThreads) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t += dq[(int64_t)b * n_out + n];
+      dbias[n] = t;
+    }
+  }
+  if (count && tid == 0) *count += 1;
+}
+
+// ------------------------------------------------------------------------------------------------- Adam
+// optax 0.2.4 scale_by_adam + scale(-lr): mu = b1 mu + (1-b1) g ; nu = b2 nu + (1-b2) g^2 ;
+// p -= lr * (mu / (1-b1^t)) / (sqrt(nu / (1-b2^t)) + eps) with t = *count (already incremented).
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
+            const int32_t* __restrict__ count, float lr, float b1, float b2, float eps, int64_t n4) {
+  const int t = *count;
+  const float c1 = (float)(1.0 - pow((double)b1, (double)t));
+  const float c2 = (float)(1.0 - pow((double)b2, (double)t));
+  const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(mu)[i];
+    float4 vv = reinterpret_cast<float4*>(nu)[i];
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+#define ISDQN_ADAM1(c)                                    \
+  mv.c = ob1 * gv.c + b1 * mv.c;                          \
+  vv.c = ob2 * (gv.c * gv.c) + b2 * vv.c;                 \
+  pv.c -= lr * ((mv.c / c1) / (sqrtf(vv.c / c2) + eps));
+    ISDQN_ADAM1(x) ISDQN_ADAM1(y) ISDQN_ADAM1(z) ISDQN_ADAM1(w)
+#undef ISDQN_ADAM1
+    reinterpret_cast<float4*>(mu)[i] = mv;
+    reinterpret_cast<float4*>(nu)[i] = vv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+}
+
+__global__ void count_inc_kernel(int32_t* count) { *count += 1; }
+
+// isdqn.py:111-125: one CTA per kernel row (+ one for the bias): row[j] = row[j + A] for j < K*A
+__global__ void __launch_bounds__(256) shift_heads_kernel(float* kernel, float* bias, int n_in, int K, int A) {
+  float* row = blockIdx.x < n_in ? kernel + (int64_t)blockIdx.x * (1 + K) * A : bias;
+  const int n = K * A;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * 256;
+    v[j] = i < n ? row[i + A] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * 256;
+    if (i < n) row[i] = v[j];
+  }
+}
+
+// isdqn.py:133-135: argmax over the actions of head 1+idx (first maximum, like jnp.argmax)
+__global__ void argmax_head_kernel(const float* __restrict__ q, int A, int head, int32_t* out) {
+  if (threadIdx.x == 0) {
+    const float* h = q + head * A;
+    int best = 0;
+    for (int a = 1; a < A; ++a)
+      if (h[a] > h[best]) best = a;
+    *out = best;
+  }
+}
+
+}  // namespace isdqn

@@ -1,0 +1,143 @@
+// Library plumbing: error strings, CUDA-graph helpers, NCCL (dlopen'ed) for the data-parallel mode.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace isdqn {
+static thread_local char g_last_error[512] = "";
+void set_last_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace isdqn
+
+using namespace isdqn;
+
+extern "C" int isdqn_abi_version(void) { return ISDQN_ABI_VERSION; }
+
+extern "C" const char* isdqn_strerror(int code) {
+  switch (code) {
+    case ISDQN_OK: return "ok";
+    case ISDQN_E_INVALID: return "invalid argument";
+    case ISDQN_E_TOO_LARGE: return "request exceeds a kernel limit";
+    case ISDQN_E_CUDA: return "CUDA runtime error";
+    case ISDQN_E_UNSUPPORTED: return "unsupported configuration";
+    case ISDQN_E_NCCL: return "NCCL error";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* isdqn_last_cuda_error(void) { return g_last_error; }
+
+// ------------------------------------------------------------------------------------------------- graphs
+extern "C" int isdqn_graph_begin(void* stream) {
+  ISDQN_CUDA_CHECK(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_graph_end(void* stream, void** out_graph_exec) {
+  if (!out_graph_exec) return ISDQN_E_INVALID;
+  cudaGraph_t graph = nullptr;
+  ISDQN_CUDA_CHECK(cudaStreamEndCapture(as_stream(stream), &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "cudaGraphInstantiate");
+    return ISDQN_E_CUDA;
+  }
+  *out_graph_exec = exec;
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_graph_launch(void* graph_exec, void* stream) {
+  if (!graph_exec) return ISDQN_E_INVALID;
+  ISDQN_CUDA_CHECK(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_graph_destroy(void* graph_exec) {
+  if (!graph_exec) return ISDQN_OK;
+  ISDQN_CUDA_CHECK(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+  return ISDQN_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- NCCL
+// Minimal, version-stable slice of nccl.h (ncclUniqueId is 128 bytes; enums as in NCCL 2.x).
+namespace {
+struct NcclUid {
+  char b[128];
+};
+struct NcclApi {
+  typedef NcclUid Uid;
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid /* ncclUniqueId by value */, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+  if (g_nccl.handle) return ISDQN_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    snprintf(g_last_error, sizeof(g_last_error), "dlopen(libnccl.so.2) failed: %s", dlerror());
+    return ISDQN_E_NCCL;
+  }
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    snprintf(g_last_error, sizeof(g_last_error), "libnccl is missing a required symbol");
+    return ISDQN_E_NCCL;
+  }
+  g_nccl.handle = h;
+  return ISDQN_OK;
+}
+
+int nccl_check(int rc, const char* where) {
+  if (rc == 0) return ISDQN_OK;
+  snprintf(g_last_error, sizeof(g_last_error), "%s: NCCL error %d (%s)", where, rc,
+           g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return ISDQN_E_NCCL;
+}
+}  // namespace
+
+extern "C" int isdqn_dp_unique_id(uint8_t* h_unique_id_128) {
+  if (!h_unique_id_128) return ISDQN_E_INVALID;
+  int rc = nccl_load();
+  if (rc) return rc;
+  return nccl_check(g_nccl.GetUniqueId(h_unique_id_128), "ncclGetUniqueId");
+}
+
+extern "C" int isdqn_dp_init(const uint8_t* h_unique_id_128, int32_t rank, int32_t world, void** out_comm) {
+  if (!h_unique_id_128 || !out_comm || world < 1 || rank < 0 || rank >= world) return ISDQN_E_INVALID;
+  int rc = nccl_load();
+  if (rc) return rc;
+  NcclApi::Uid uid;
+  memcpy(uid.b, h_unique_id_128, 128);
+  void* comm = nullptr;
+  rc = nccl_check(g_nccl.CommInitRank(&comm, world, uid, rank), "ncclCommInitRank");
+  if (rc) return rc;
+  *out_comm = comm;
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_dp_allreduce_f32(void* comm, float* d_buf, int64_t n, void* stream) {
+  if (!comm || !d_buf || n < 0) return ISDQN_E_INVALID;
+  if (!g_nccl.handle) return ISDQN_E_NCCL;
+  // ncclFloat32 = 7, ncclSum = 0
+  return nccl_check(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, 7, 0, comm, as_stream(stream)), "ncclAllReduce");
+}
+
+extern "C" int isdqn_dp_destroy(void* comm) {
+  if (!comm) return ISDQN_OK;
+  if (!g_nccl.handle) return ISDQN_E_NCCL;
+  return nccl_check(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}

@@ -1,0 +1,184 @@
+// Replay samplers on the device, bit-exact with numpy's Generator(PCG64) as used by
+// slimdqn/sample_collection/samplers.py:
+//   uniform      samplers.py:39-49    Generator.integers(n, size)  -> buffered 32-bit stream + Lemire rejection
+//   prioritized  samplers.py:105-116  Generator.uniform(0, root, size) + SumTree.query descent
+// Every thread jumps the 128-bit LCG straight to its own stream position (O(log) multiplies), so the draws are
+// produced in parallel yet are exactly the sequential ones; rejections are resolved with a block scan.
+#include "common.cuh"
+#include "pcg64.cuh"
+
+namespace isdqn {
+
+constexpr int kUniformThreads = 1024;
+
+__global__ void __launch_bounds__(kUniformThreads)
+sample_uniform_kernel(uint64_t* rng, uint32_t n_valid, int size, const int32_t* __restrict__ index_to_key,
+                      int capacity, int32_t* __restrict__ out_index, int32_t* __restrict__ out_key,
+                      int32_t* __restrict__ out_slot) {
+  __shared__ int warp_tot[32];
+  __shared__ int total_sh;
+  __shared__ unsigned long long consumed_final;
+  const int tid = threadIdx.x;
+  const PcgMirror m0 = pcg_load(rng);
+
+  auto emit = [&](int pos, int32_t index) {
+    if (out_index) out_index[pos] = index;
+    if (index_to_key) {
+      const int32_t key = index_to_key[index];
+      if (out_key) out_key[pos] = key;
+      if (out_slot) out_slot[pos] = key % capacity;
+    }
+  };
+
+  if (n_valid == 1u) {  // rng == 0: numpy fills with `off` and consumes no randomness
+    for (int i = tid; i < size; i += kUniformThreads) emit(i, 0);
+    return;
+  }
+  // Lemire: accept iff low32(v * n) >= (2^32 - n) % n   (the reference only evaluates the threshold when
+  // low32 < n, which is the same predicate because threshold < n)
+  const uint32_t threshold = (uint32_t)((0x100000000ull - n_valid) % n_valid);
+  int written = 0;
+  unsigned long long consumed = 0;  // 32-bit values consumed so far
+  while (written < size) {
+    const unsigned long long c = consumed + tid;
+    const uint32_t v = pcg_next32_at(m0, c);
+    const unsigned long long prod = (unsigned long long)v * n_valid;
+    const int accept = ((uint32_t)prod >= threshold) ? 1 : 0;
+    const int rank = block_exclusive_scan<kUniformThreads>(accept, warp_tot, &total_sh);
+    const int total = total_sh;
+    const int remaining = size - written;
+    if (accept && rank < remaining) {
+      emit(written + rank, (int32_t)(prod >> 32));
+      if (rank == remaining - 1) consumed_final = c + 1;
+    }
+    __syncthreads();
+    if (total >= remaining) {
+      consumed = consumed_final;
+      written = size;
+    } else {
+      consumed += kUniformThreads;
+      written += total;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) pcg_store(rng, pcg_after_next32(m0, consumed));
+}
+
+constexpr int kPrioThreads = 128;
+
+__global__ void __launch_bounds__(kPrioThreads)
+sample_prioritized_kernel(const uint64_t* __restrict__ rng, const double* __restrict__ nodes, int depth, int size,
+                          const int32_t* __restrict__ index_to_key, int capacity, int32_t* __restrict__ out_index,
+                          int32_t* __restrict__ out_key, int32_t* __restrict__ out_slot,
+                          double* __restrict__ out_target, uint32_t* status) {
+  const PcgMirror m0 = pcg_load(rng);
+  const double root = nodes[0];
+  const int first_leaf = (1 << (depth - 1)) - 1;
+  uint32_t st = 0;
+  if (root == 0.0) st |= ISDQN_ST_EMPTY_TREE;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x) {
+    // Generator.uniform: low + (high - low) * ((next64 >> 11) * 2^-53), one next64 per element
+    const uint64_t o = pcg_out64_at(m0.state, m0.inc, (uint64_t)i);
+    const double u = (double)(o >> 11) * (1.0 / 9007199254740992.0);
+    double t = __dadd_rn(0.0, __dmul_rn(root - 0.0, u));
+    if (out_target) out_target[i] = t;
+    if (!(t >= 0.0 && t < root)) st |= ISDQN_ST_TARGET_RANGE;
+    int node = 0;
+    for (int level = 0; level < depth - 1; ++level) {
+      const int left = 2 * node + 1;
+      const double ls = __ldg(nodes + left);
+      if (t < ls) {
+        node = left;
+      } else {
+        node = left + 1;
+        t = t - ls;
+        if (level + 1 < depth - 1 && !(t < __ldg(nodes + left + 1))) st |= ISDQN_ST_DESCENT_ASSERT;
+      }
+    }
+    const int32_t index = node - first_leaf;
+    if (out_index) out_index[i] = index;
+    if (index_to_key) {
+      const int32_t key = index_to_key[index];
+      if (out_key) out_key[i] = key;
+      if (out_slot) out_slot[i] = key % capacity;
+    }
+  }
+  if (st && status) atomicOr(status, st);
+}
+
+__global__ void pcg_advance64_kernel(uint64_t* rng, uint64_t steps) {
+  PcgMirror m = pcg_load(rng);
+  m.state = pcg_advance(m.state, m.inc, steps);
+  pcg_store(rng, m);
+}
+
+__global__ void scatter_rows_i32_kernel(int32_t* __restrict__ table, int width, const int32_t* __restrict__ pidx,
+                                        const int32_t* __restrict__ pval, int n) {
+  // rows in one patch list are distinct (the host keeps only the last write per row)
+  const int total = n * width;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int i = t / width, j = t - i * width;
+    table[(int64_t)pidx[i] * width + j] = pval[t];
+  }
+}
+
+__global__ void scatter_rows_f64_kernel(double* __restrict__ table, const int32_t* __restrict__ pidx,
+                                        const double* __restrict__ pval, int n) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) table[pidx[t]] = pval[t];
+}
+
+}  // namespace isdqn
+
+using namespace isdqn;
+
+extern "C" int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t size, const int32_t* d_index_to_key,
+                                    int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
+                                    void* stream) {
+  if (!d_rng || n_valid < 1 || size < 0 || (d_index_to_key && capacity < 1)) return ISDQN_E_INVALID;
+  if (size > (1 << 20)) return ISDQN_E_TOO_LARGE;
+  if (size == 0) return ISDQN_OK;
+  sample_uniform_kernel<<<1, kUniformThreads, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key,
+                                                                      capacity, d_out_index, d_out_key, d_out_slot);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size,
+                                        const int32_t* d_index_to_key, int32_t capacity, int32_t* d_out_index,
+                                        int32_t* d_out_key, int32_t* d_out_slot, double* d_out_target,
+                                        uint32_t* d_status, void* stream) {
+  if (!d_rng || !d_nodes || depth < 1 || depth > 31 || size < 0 || (d_index_to_key && capacity < 1))
+    return ISDQN_E_INVALID;
+  if (size == 0) return ISDQN_OK;
+  int grid = ceil_div(size, kPrioThreads);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  sample_prioritized_kernel<<<grid, kPrioThreads, 0, as_stream(stream)>>>(
+      d_rng, d_nodes, depth, size, d_index_to_key, capacity, d_out_index, d_out_key, d_out_slot, d_out_target, d_status);
+  ISDQN_LAUNCH_CHECK();
+  pcg_advance64_kernel<<<1, 1, 0, as_stream(stream)>>>(d_rng, (uint64_t)size);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_scatter_rows_i32(int32_t* d_table, int32_t width, const int32_t* d_patch_index,
+                                      const int32_t* d_patch_value, int32_t n_patches, void* stream) {
+  if (!d_table || !d_patch_index || !d_patch_value || width < 1 || n_patches < 0) return ISDQN_E_INVALID;
+  if (n_patches == 0) return ISDQN_OK;
+  const int total = n_patches * width;
+  int grid = ceil_div(total, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  scatter_rows_i32_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_table, width, d_patch_index, d_patch_value, n_patches);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_scatter_rows_f64(double* d_table, const int32_t* d_patch_index, const double* d_patch_value,
+                                      int32_t n_patches, void* stream) {
+  if (!d_table || !d_patch_index || !d_patch_value || n_patches < 0) return ISDQN_E_INVALID;
+  if (n_patches == 0) return ISDQN_OK;
+  int grid = ceil_div(n_patches, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  scatter_rows_f64_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_table, d_patch_index, d_patch_value, n_patches);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}

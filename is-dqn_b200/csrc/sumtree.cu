@@ -1,0 +1,311 @@
+// Sum-tree kernels (float64 array heap), bit-exact with slimdqn/sample_collection/sum_tree.py.
+//
+//   query  sum_tree.py:58-102   one thread walks QPT independent descents in lock step (QPT loads in flight per
+//                               thread); the top levels of the heap are staged in shared memory when a CTA has
+//                               enough queries to amortise the staging (throughput shapes).
+//   set    sum_tree.py:20-47    one CTA: bitonic sort of (leaf, position) in shared memory, first-duplicate-wins
+//                               compaction, delta = value - old leaf, then for every level the runs of equal
+//                               ancestors are folded sequentially in ascending-leaf order — exactly the order of
+//                               np.add.at — so the float64 heap stays bit-identical to the reference's.
+#include "common.cuh"
+
+namespace isdqn {
+
+// ------------------------------------------------------------------------------------------------- query
+constexpr int kQueryThreads = 256;
+constexpr int kQueryPerThread = 4;
+constexpr int kQueryMaxTopLevels = 12;  // 4095 nodes = 32 KB of shared memory
+
+template <int QPT>
+__global__ void __launch_bounds__(kQueryThreads)
+sumtree_query_kernel(const double* __restrict__ nodes, int depth, const double* __restrict__ targets, int64_t n,
+                     int32_t* __restrict__ out, uint32_t* status, int top_levels) {
+  extern __shared__ double top[];
+  const int n_top = top_levels > 0 ? (1 << top_levels) - 1 : 0;
+  for (int i = threadIdx.x; i < n_top; i += blockDim.x) top[i] = nodes[i];
+  if (n_top) __syncthreads();
+
+  const int first_leaf = (1 << (depth - 1)) - 1;
+  const double root = nodes[0];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  uint32_t st = 0;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * QPT) {
+    double t[QPT];
+    int node[QPT];
+    bool live[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t q = base + (int64_t)j * stride;
+      live[j] = q < n;
+      t[j] = live[j] ? targets[q] : 0.0;
+      node[j] = 0;
+      if (live[j] && !(t[j] >= 0.0 && t[j] < root)) st |= ISDQN_ST_TARGET_RANGE;
+    }
+    for (int level = 0; level < depth - 1; ++level) {
+      const bool child_in_top = (level + 1) < top_levels;
+      const bool child_internal = (level + 1) < (depth - 1);
+      double ls[QPT];
+#pragma unroll
+      for (int j = 0; j < QPT; ++j) {
+        const int left = 2 * node[j] + 1;
+        ls[j] = child_in_top ? top[left] : __ldg(nodes + left);
+      }
+#pragma unroll
+      for (int j = 0; j < QPT; ++j) {
+        const int left = 2 * node[j] + 1;
+        if (t[j] < ls[j]) {
+          node[j] = left;
+        } else {
+          node[j] = left + 1;
+          t[j] = t[j] - ls[j];
+          if (child_internal && live[j]) {
+            // sum_tree.py:82: the next iteration asserts target < nodes[node] (delta-propagated sums can
+            // violate it by one rounding); going left satisfies it by construction.
+            const double rs = child_in_top ? top[left + 1] : __ldg(nodes + left + 1);
+            if (!(t[j] < rs)) st |= ISDQN_ST_DESCENT_ASSERT;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t q = base + (int64_t)j * stride;
+      if (live[j]) out[q] = node[j] - first_leaf;
+    }
+  }
+  if (st && status) atomicOr(status, st);
+}
+
+// --------------------------------------------------------------------------------------------------- set
+struct SetSmem {
+  unsigned long long* keys;  // [MAXM]  (leaf << 32 | position), sorted ascending
+  int* uleaf;                // [MAXM]  unique leaves, ascending
+  double* udelta;            // [MAXM]
+  int* warp_tot;             // [32]
+  int* misc;                 // [4]: total, bad flag
+  double* red;               // [32]
+};
+
+// With TAGS a value -(1+j) stands for "the current value of leaf j" (read before this op modifies anything):
+// PrioritizedSamplingDistribution.remove moves the last leaf's priority into the hole (samplers.py:99-102)
+// and would otherwise need a device->host read per eviction.
+template <bool TAGS>
+__device__ __forceinline__ double resolve_value(double v, const double* nodes, int first_leaf, int n_leaves, int* bad) {
+  if (TAGS && v < 0.0) {
+    const int src = (int)(-v) - 1;
+    if (src < 0 || src >= n_leaves) {
+      *bad |= 2;
+      return 0.0;
+    }
+    return nodes[first_leaf + src];
+  }
+  return v;
+}
+
+// One `set` executed by the whole CTA.  Ends with a __syncthreads(), so it can be called back to back.
+template <int MAXM, int THREADS, bool TAGS>
+__device__ void sumtree_set_block(double* nodes, int depth, const int32_t* __restrict__ idx,
+                                  const double* __restrict__ val, int m, double* max_prio, uint32_t* status,
+                                  const SetSmem& sm) {
+  const int tid = threadIdx.x;
+  const int n_leaves = 1 << (depth - 1);
+  const int first_leaf = n_leaves - 1;
+
+  // (0) sum_tree.py:31 — nothing is modified when any value is negative (or NaN); indices must be leaves.
+  int bad = 0;
+  double vmax = 0.0;
+  for (int i = tid; i < m; i += THREADS) {
+    const double v = resolve_value<TAGS>(val[i], nodes, first_leaf, n_leaves, &bad);
+    const int l = idx[i];
+    if (!(v >= 0.0)) bad |= 1;
+    if (l < 0 || l >= n_leaves) bad |= 2;
+    vmax = fmax(vmax, v);
+  }
+  bad = __syncthreads_or(bad);
+  if (bad) {
+    // which of the two: recompute cheaply on one thread's worth of data is not possible; flag both classes
+    int mine = 0;
+    for (int i = tid; i < m; i += THREADS) {
+      int b2 = 0;
+      if (!(resolve_value<TAGS>(val[i], nodes, first_leaf, n_leaves, &b2) >= 0.0)) mine |= ISDQN_ST_NEGATIVE_VALUE;
+      if (b2 || idx[i] < 0 || idx[i] >= n_leaves) mine |= ISDQN_ST_INDEX_RANGE;
+    }
+    if (mine && status) atomicOr(status, (uint32_t)mine);
+    __syncthreads();
+    return;
+  }
+  // (1) sum_tree.py:32 — max_recorded_priority
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((tid & 31) == 0) sm.red[tid >> 5] = vmax;
+  __syncthreads();
+  if (tid == 0) {
+    double r = sm.red[0];
+    for (int w = 1; w < THREADS / 32; ++w) r = fmax(r, sm.red[w]);
+    if (max_prio) *max_prio = fmax(*max_prio, r);
+  }
+
+  // (2) sort (leaf, position) ascending: np.unique(node_indices, return_index=True) keeps the first position
+  int P = 1;
+  while (P < m) P <<= 1;
+  for (int i = tid; i < P; i += THREADS)
+    sm.keys[i] = i < m ? (((unsigned long long)(uint32_t)idx[i]) << 32) | (uint32_t)i : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = sm.keys[i], b = sm.keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            sm.keys[i] = b;
+            sm.keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // (3) compaction of first occurrences + delta against the OLD leaf value (sum_tree.py:34,39-40)
+  const int per = (P + THREADS - 1) / THREADS;
+  const int lo = tid * per;
+  int cnt = 0;
+  for (int i = lo; i < lo + per && i < m; ++i) {
+    const uint32_t leaf = (uint32_t)(sm.keys[i] >> 32);
+    cnt += (i == 0 || leaf != (uint32_t)(sm.keys[i - 1] >> 32)) ? 1 : 0;
+  }
+  int pos = block_exclusive_scan<THREADS>(cnt, sm.warp_tot, &sm.misc[0]);
+  const int u = sm.misc[0];
+  for (int i = lo; i < lo + per && i < m; ++i) {
+    const unsigned long long key = sm.keys[i];
+    const uint32_t leaf = (uint32_t)(key >> 32);
+    if (i == 0 || leaf != (uint32_t)(sm.keys[i - 1] >> 32)) {
+      sm.uleaf[pos] = (int)leaf;
+      int b2 = 0;
+      sm.udelta[pos] = resolve_value<TAGS>(val[(uint32_t)key], nodes, first_leaf, n_leaves, &b2) - nodes[first_leaf + (int)leaf];
+      ++pos;
+    }
+  }
+  __syncthreads();
+
+  // (4) sum_tree.py:41-47 — every level: np.add.at(nodes, ancestors, deltas) == sequential fold per run of
+  // equal ancestors, ascending-leaf order.  Levels touch disjoint nodes, runs are disjoint: no races.
+  const int tasks = u * depth;
+  for (int task = tid; task < tasks; task += THREADS) {
+    const int s = task / u;  // how many levels above the leaves
+    const int i = task - s * u;
+    const int node = ((first_leaf + sm.uleaf[i] + 1) >> s) - 1;
+    if (i > 0 && (((first_leaf + sm.uleaf[i - 1] + 1) >> s) - 1) == node) continue;  // not a run head
+    double acc = nodes[node];
+    int j = i;
+    do {
+      acc = __dadd_rn(acc, sm.udelta[j]);
+      ++j;
+    } while (j < u && (((first_leaf + sm.uleaf[j] + 1) >> s) - 1) == node);
+    nodes[node] = acc;
+  }
+  __syncthreads();
+}
+
+template <int MAXM, int THREADS>
+__device__ __forceinline__ SetSmem carve_set_smem(unsigned char* raw) {
+  SetSmem sm;
+  sm.keys = reinterpret_cast<unsigned long long*>(raw);
+  sm.udelta = reinterpret_cast<double*>(raw + sizeof(unsigned long long) * MAXM);
+  sm.red = reinterpret_cast<double*>(raw + 16 * MAXM);
+  sm.uleaf = reinterpret_cast<int*>(raw + 16 * MAXM + 32 * sizeof(double));
+  sm.warp_tot = sm.uleaf + MAXM;
+  sm.misc = sm.warp_tot + 32;
+  return sm;
+}
+template <int MAXM>
+constexpr size_t set_smem_bytes() {
+  return 16 * (size_t)MAXM + 32 * sizeof(double) + sizeof(int) * ((size_t)MAXM + 32 + 4);
+}
+
+template <int MAXM, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sumtree_set_kernel(double* nodes, int depth, const int32_t* __restrict__ idx, const double* __restrict__ val, int m,
+                   double* max_prio, uint32_t* status) {
+  extern __shared__ __align__(16) unsigned char set_raw[];
+  SetSmem sm = carve_set_smem<MAXM, THREADS>(set_raw);
+  sumtree_set_block<MAXM, THREADS, false>(nodes, depth, idx, val, m, max_prio, status, sm);
+}
+
+template <int MAXM, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_offset, int n_ops,
+                       const int32_t* __restrict__ idx, const double* __restrict__ val, double* max_prio,
+                       uint32_t* status) {
+  extern __shared__ __align__(16) unsigned char set_raw[];
+  SetSmem sm = carve_set_smem<MAXM, THREADS>(set_raw);
+  for (int op = 0; op < n_ops; ++op) {
+    const int b = op_offset[op], e = op_offset[op + 1];
+    if (e - b > MAXM || e < b) {
+      if (threadIdx.x == 0 && status) atomicOr(status, ISDQN_ST_OP_TOO_LARGE);
+      continue;
+    }
+    // sets are strictly ordered: op+1 reads the nodes op wrote (the trailing __syncthreads orders them)
+    sumtree_set_block<MAXM, THREADS, true>(nodes, depth, idx + b, val + b, e - b, max_prio, status, sm);
+  }
+}
+
+}  // namespace isdqn
+
+using namespace isdqn;
+
+extern "C" int isdqn_sumtree_query(const double* d_nodes, int depth, const double* d_targets, int64_t n,
+                                   int32_t* d_out_index, uint32_t* d_status, void* stream) {
+  if (!d_nodes || !d_targets || !d_out_index || depth < 1 || depth > 31 || n < 0) return ISDQN_E_INVALID;
+  if (n == 0) return ISDQN_OK;
+  const int64_t per_cta = (int64_t)kQueryThreads * kQueryPerThread;
+  int64_t grid = ceil_div<int64_t>(n, per_cta);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (grid > cap) grid = cap;
+  // staging pays once a CTA serves many queries: each query needs <= 12 of the staged nodes
+  int top_levels = 0;
+  if (n / grid >= 4096) top_levels = depth - 1 < kQueryMaxTopLevels ? depth - 1 : kQueryMaxTopLevels;
+  const size_t smem = top_levels > 0 ? sizeof(double) * ((1u << top_levels) - 1) : 0;
+  sumtree_query_kernel<kQueryPerThread><<<(unsigned)grid, kQueryThreads, smem, as_stream(stream)>>>(
+      d_nodes, depth, d_targets, n, d_out_index, d_status, top_levels);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_index, const double* d_value,
+                                 int32_t n, double* d_max_priority, uint32_t* d_status, void* stream) {
+  if (!d_nodes || !d_index || !d_value || depth < 1 || depth > 31 || n < 0) return ISDQN_E_INVALID;
+  if (n == 0) return ISDQN_OK;
+  if (n > ISDQN_SUMTREE_SET_MAX) return ISDQN_E_TOO_LARGE;
+  if (n <= 1024) {
+    sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), as_stream(stream)>>>(
+        d_nodes, depth, d_index, d_value, n, d_max_priority, d_status);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      ISDQN_CUDA_CHECK(cudaFuncSetAttribute(sumtree_set_kernel<ISDQN_SUMTREE_SET_MAX, 1024>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)set_smem_bytes<ISDQN_SUMTREE_SET_MAX>()));
+      attr_done = true;
+    }
+    sumtree_set_kernel<ISDQN_SUMTREE_SET_MAX, 1024>
+        <<<1, 1024, set_smem_bytes<ISDQN_SUMTREE_SET_MAX>(), as_stream(stream)>>>(d_nodes, depth, d_index, d_value, n,
+                                                                                  d_max_priority, d_status);
+  }
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_sumtree_set_ops(double* d_nodes, int depth, const int32_t* d_op_offset, int32_t n_ops,
+                                     const int32_t* d_index, const double* d_value, double* d_max_priority,
+                                     uint32_t* d_status, void* stream) {
+  if (!d_nodes || !d_op_offset || !d_index || !d_value || depth < 1 || depth > 31 || n_ops < 0)
+    return ISDQN_E_INVALID;
+  if (n_ops == 0) return ISDQN_OK;
+  sumtree_set_ops_kernel<ISDQN_SUMTREE_OP_MAX, 256><<<1, 256, set_smem_bytes<ISDQN_SUMTREE_OP_MAX>(), as_stream(stream)>>>(
+      d_nodes, depth, d_op_offset, n_ops, d_index, d_value, d_max_priority, d_status);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}

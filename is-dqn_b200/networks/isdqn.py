@@ -1,0 +1,378 @@
+"""iS-DQN agent on the device — drop-in for `slimdqn/networks/isdqn.py` (same constructor, attributes, methods).
+
+One shared torso, `(1 + K) * A` outputs reshaped to `(batch, 1 + K, A)`: head 0 is the frozen target, heads 1..K are
+online and head k regresses onto `r + gamma^n (1 - d) max_a Q_{k-1}(s')` (isdqn.py:34-43, 92-109).
+
+`learn_on_batch` is ONE native call (`isdqn_learn_on_batch`: forward on s and s', fused K-head TD loss fwd+bwd,
+backward, [NCCL all-reduce], Adam), captured once in a CUDA graph and replayed; params, Adam moments and the step
+counter stay in HBM as flat float32 vectors.  The reference's functional signature is kept — the returned pytrees
+are the (updated in place) inputs, i.e. the arguments are donated.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib
+from ..sample_collection.replay_buffer import ReplayElement
+from .architectures.dqn import DQNNet, ParamTree
+
+
+def _key_to_seed(key) -> np.random.SeedSequence:
+    return np.random.SeedSequence(np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8).tolist() or [0])
+
+
+class OptState(dict):
+    """`optax.adam` state: {"count": int32[1], "mu": ParamTree, "nu": ParamTree} (optax 0.2.4 ScaleByAdamState)."""
+
+
+class iSDQN:
+    def __init__(
+        self,
+        key,
+        observation_dim,
+        n_actions,
+        n_bellman_iterations: int,
+        features: list,
+        layer_norm: bool,
+        batch_norm: bool,
+        architecture_type: str,
+        learning_rate: float,
+        gamma: float,
+        update_horizon: int,
+        data_to_update: int,
+        target_update_frequency: int,
+        adam_eps: float = 1e-8,
+        use_cuda_graph: bool = True,
+    ):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._lib = _lib.load()
+        self.n_bellman_iterations = int(n_bellman_iterations)
+        self.n_actions = int(n_actions)
+        features = [int(f) for f in features]
+        self.last_idx_mlp = len(features) if architecture_type == "fc" else len(features) - 3
+        self.network = DQNNet(
+            features, architecture_type, (1 + self.n_bellman_iterations) * self.n_actions, layer_norm, batch_norm
+        )
+        self.network.configure(observation_dim, self.n_bellman_iterations, self.n_actions)
+
+        # 1 + self.n_bellman_iterations = [\bar{Q_0}, Q_1, ..., Q_K]
+        def apply(params, state):
+            q_values, batch_stats = self.network.apply(params, state, mutable=["batch_stats"])
+            return q_values.reshape((-1, 1 + self.n_bellman_iterations, self.n_actions)), batch_stats
+
+        self.network.apply_fn = apply
+        self.params = self.network.init(key)
+
+        # optax.adam(learning_rate, eps=adam_eps): b1=0.9, b2=0.999, eps_root=0 (isdqn.py:46)
+        self.learning_rate = float(learning_rate)
+        self.adam_eps = float(adam_eps)
+        self.adam_b1, self.adam_b2 = 0.9, 0.999
+        self.optimizer_state = OptState(
+            count=torch.zeros(1, dtype=torch.int32, device="cuda"),
+            mu=self.network.new_tree(),
+            nu=self.network.new_tree(),
+        )
+        self._grads = self.network.new_tree()
+
+        self.gamma = gamma
+        self.update_horizon = update_horizon
+        self.data_to_update = data_to_update
+        self.target_update_frequency = target_update_frequency
+        self._d_cumulated = torch.zeros(self.n_bellman_iterations, dtype=torch.float64, device="cuda")
+
+        self._use_graph = bool(use_cuda_graph)
+        self._ctx = {}  # batch size -> persistent buffers + captured graph
+        self._nccl_comm = None
+        self._dp_world = 1
+        self._side_stream = None
+
+    # ------------------------------------------------------------------------------------- loss bookkeeping
+    @property
+    def cumulated_losses(self) -> np.ndarray:
+        """Host view of the per-head loss sums (isdqn.py:53,62).  Accumulated on the device: reading it is the only
+        synchronisation, instead of one per update."""
+        return self._d_cumulated.cpu().numpy()
+
+    @cumulated_losses.setter
+    def cumulated_losses(self, value) -> None:
+        self._d_cumulated.copy_(self._torch.as_tensor(np.asarray(value, dtype=np.float64)))
+
+    # ----------------------------------------------------------------------------------------- data parallel
+    def enable_data_parallel(self, comm_handle: int, world_size: int) -> None:
+        """Large-batch data-parallel mode (new functionality): every rank runs the step on its
+        slice of the global batch; gradients are all-reduced over NCCL before the (replicated) Adam step."""
+        self._nccl_comm = comm_handle
+        self._dp_world = int(world_size)
+        self._ctx.clear()
+
+    # ------------------------------------------------------------------------------------------- step context
+    def _context(self, B: int):
+        ctx = self._ctx.get(B)
+        if ctx is not None:
+            return ctx
+        t = self._torch
+        net = self.network
+        ctx = {}
+        if net.architecture_type == "cnn":
+            shape, dt = (B,) + tuple(net.observation_dim), t.uint8
+        else:
+            shape, dt = (B,) + tuple(net.observation_dim), t.float32
+        ctx["state"] = t.zeros(shape, dtype=dt, device="cuda")
+        ctx["next_state"] = t.zeros(shape, dtype=dt, device="cuda")
+        ctx["action"] = t.zeros(B, dtype=t.int64, device="cuda")
+        ctx["reward"] = t.zeros(B, dtype=t.float64, device="cuda")
+        ctx["terminal"] = t.zeros(B, dtype=t.uint8, device="cuda")
+        ctx["losses"] = t.zeros(self.n_bellman_iterations, dtype=t.float32, device="cuda")
+        nbytes = self._lib.isdqn_learn_workspace_bytes(net._net, B)
+        if nbytes < 0:
+            raise _lib.IsdqnNativeError("isdqn_learn_workspace_bytes failed")
+        ctx["ws"] = t.empty(max(nbytes, 16), dtype=t.uint8, device="cuda")
+        # pinned staging for host batches (the reference's implicit device_put at the jit boundary)
+        ctx["h_state"] = t.zeros(shape, dtype=dt).pin_memory()
+        ctx["h_next_state"] = t.zeros(shape, dtype=dt).pin_memory()
+        ctx["h_action"] = t.zeros(B, dtype=t.int64).pin_memory()
+        ctx["h_reward"] = t.zeros(B, dtype=t.float64).pin_memory()
+        ctx["h_terminal"] = t.zeros(B, dtype=t.uint8).pin_memory()
+        batch = _lib.Batch(
+            ctx["state"].data_ptr(), ctx["next_state"].data_ptr(), ctx["action"].data_ptr(),
+            ctx["reward"].data_ptr(), ctx["terminal"].data_ptr(),
+        )
+        ctx["batch"] = batch
+        ctx["graph"] = None
+        ctx["graph_key"] = None
+        ctx["warm"] = 0
+        self._ctx[B] = ctx
+        return ctx
+
+    def batch_buffers(self, B: int) -> ReplayElement:
+        """The persistent device buffers the captured step reads: a replay buffer can gather straight into them
+        (`rb.sample_device(out=agent.batch_buffers(B))`)."""
+        c = self._context(B)
+        return ReplayElement(c["state"], c["action"], c["reward"], c["next_state"], c["terminal"])
+
+    def _train_struct(self, ctx, params: ParamTree, opt: OptState, B: int) -> "_lib.Train":
+        tr = _lib.Train()
+        tr.gamma_n = float(self.gamma**self.update_horizon)
+        tr.lr, tr.b1, tr.b2, tr.eps = self.learning_rate, self.adam_b1, self.adam_b2, self.adam_eps
+        tr.batch = B
+        tr.batch_global = B * self._dp_world
+        tr.d_params = params.flat.data_ptr()
+        tr.d_grads = self._grads.flat.data_ptr()
+        tr.d_mu = opt["mu"].flat.data_ptr() if opt is not None else None
+        tr.d_nu = opt["nu"].flat.data_ptr() if opt is not None else None
+        tr.d_count = opt["count"].data_ptr() if opt is not None else None
+        tr.d_losses = ctx["losses"].data_ptr()
+        tr.d_workspace = ctx["ws"].data_ptr()
+        tr.workspace_bytes = ctx["ws"].numel()
+        tr.nccl_comm = self._nccl_comm
+        return tr
+
+    def _load_batch(self, ctx, batch) -> int:
+        """Copies `batch` (host numpy, like `rb.sample()`; or CUDA tensors) into the persistent device buffers."""
+        t = self._torch
+        names = ("state", "action", "reward", "next_state", "terminal")
+        fields = (batch.state, batch.action, batch.reward, batch.next_state, batch.is_terminal)
+        for name, f in zip(names, fields):
+            dst = ctx[name]
+            if isinstance(f, t.Tensor):
+                if f.data_ptr() == dst.data_ptr():
+                    continue
+                dst.copy_(f.reshape(dst.shape) if f.dtype == dst.dtype else f.reshape(dst.shape).to(dst.dtype), non_blocking=True)
+            else:
+                h = ctx["h_" + name]
+                arr = np.asarray(f)
+                if name in ("state", "next_state") and self.network.architecture_type == "cnn" and arr.dtype != np.uint8:
+                    raise TypeError("cnn batches must be uint8 frames (float states: use loss_on_batch / apply)")
+                h.numpy()[...] = arr.reshape(h.shape)
+                dst.copy_(h, non_blocking=True)
+        return int(ctx["action"].shape[0])
+
+    # ------------------------------------------------------------------------------------------------ update
+    def update_online_params(self, step: int, replay_buffer):
+        if step % self.data_to_update == 0:
+            if hasattr(replay_buffer, "sample_device") and self.network.architecture_type == "cnn":
+                B = replay_buffer._batch_size
+                batch_samples = replay_buffer.sample_device(out=self.batch_buffers(B))
+            else:
+                batch_samples = replay_buffer.sample()
+
+            self.params, self.optimizer_state, losses = self.learn_on_batch(
+                self.params, self.optimizer_state, batch_samples
+            )
+            self._d_cumulated += losses
+
+    def update_target_params(self, step: int):
+        if step % self.target_update_frequency == 0:
+            # Window shift
+            self.params = self.shift_params(self.params)
+
+            cumulated = self.cumulated_losses
+            if self._dp_world > 1:
+                cumulated = cumulated  # per-rank share; callers all-reduce K floats when they log
+            logs = {
+                "loss": np.mean(cumulated) / (self.target_update_frequency / self.data_to_update),
+            }
+            for idx_network in range(min(self.n_bellman_iterations, 5)):
+                logs[f"networks/{idx_network}_loss"] = cumulated[idx_network] / (
+                    self.target_update_frequency / self.data_to_update
+                )
+            self._d_cumulated.zero_()
+
+            return True, logs
+
+        return False, {}
+
+    def learn_on_batch(self, params: ParamTree, optimizer_state: OptState, batch_samples):
+        """isdqn.py:82-90.  Returns (params, optimizer_state, losses[K] float32 CUDA tensor); params / optimizer
+        state are updated in place (donated) and returned."""
+        B = int(batch_samples.action.shape[0])
+        ctx = self._context(B)
+        self._load_batch(ctx, batch_samples)
+        cur = self._torch.cuda.current_stream()
+        side = None
+        if self._use_graph and cur.cuda_stream == 0:
+            # the legacy default stream cannot be captured: run the step on a side stream ordered after it
+            if self._side_stream is None:
+                self._side_stream = self._torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+        stream = side.cuda_stream if side is not None else cur.cuda_stream
+        try:
+            return self._learn_on_stream(ctx, params, optimizer_state, B, stream)
+        finally:
+            if side is not None:
+                cur.wait_stream(side)
+
+    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream):
+        key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
+               optimizer_state["count"].data_ptr(), stream)
+        if self._use_graph and ctx["graph"] is not None and ctx["graph_key"] == key:
+            _lib.check(self._lib.isdqn_graph_launch(ctx["graph"], stream), "isdqn_graph_launch")
+            return params, optimizer_state, ctx["losses"]
+        tr = self._train_struct(ctx, params, optimizer_state, B)
+        if self._use_graph and ctx["warm"] >= 1 and self._nccl_comm is None:
+            # capture this very step (it executes on replay, not during capture)
+            if ctx["graph"] is not None:
+                self._lib.isdqn_graph_destroy(ctx["graph"])
+                ctx["graph"] = None
+            _lib.check(self._lib.isdqn_graph_begin(stream), "isdqn_graph_begin")
+            rc = self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream)
+            exec_ = _lib.C.c_void_p()
+            rc2 = self._lib.isdqn_graph_end(stream, exec_)
+            _lib.check(rc, "isdqn_learn_on_batch (capture)")
+            _lib.check(rc2, "isdqn_graph_end")
+            ctx["graph"], ctx["graph_key"] = exec_, key
+            _lib.check(self._lib.isdqn_graph_launch(ctx["graph"], stream), "isdqn_graph_launch")
+        else:
+            _lib.check(self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream), "isdqn_learn_on_batch")
+            ctx["warm"] += 1
+        return params, optimizer_state, ctx["losses"]
+
+    def grad_on_batch(self, params: ParamTree, batch_samples):
+        """Gradient of the loss without the update: (grads ParamTree, losses[K]).  Used by parity tests / DP."""
+        B = int(batch_samples.action.shape[0])
+        ctx = self._context(B)
+        self._load_batch(ctx, batch_samples)
+        tr = self._train_struct(ctx, params, None, B)
+        _lib.check(self._lib.isdqn_grad_on_batch(self.network._net, tr, ctx["batch"], _lib.stream_ptr()), "isdqn_grad_on_batch")
+        return self._grads, ctx["losses"]
+
+    def loss_on_batch(self, params: ParamTree, samples):
+        """isdqn.py:92-103: (sum_k mean_b td^2, (per-head means (K,), batch_stats)).  Also leaves the (2B, 1+K, A)
+        Q-values of the call in `self.last_all_q_values`."""
+        t = self._torch
+        net = self.network
+        state, _, is_float = net.prepare_input(samples.state)
+        next_state, _, _ = net.prepare_input(samples.next_state)
+        B = int(state.shape[0])
+        if net.architecture_type == "cnn" and is_float:
+            # float states (tests/utils.py generator): forward through the float entry point, then the loss kernel
+            all_q, _ = net.apply_fn(params, t.cat((state, next_state)))
+            all_q = all_q.reshape(2 * B, -1).contiguous()
+            losses = t.empty(self.n_bellman_iterations, dtype=t.float32, device="cuda")
+            _lib.check(
+                self._lib.isdqn_heads_td_loss(
+                    all_q.data_ptr(), self._as_dev(samples.action, t.int64).data_ptr(),
+                    self._as_dev(samples.reward, t.float64).data_ptr(),
+                    self._as_dev(samples.is_terminal, t.uint8).data_ptr(), float(self.gamma**self.update_horizon), B, B,
+                    self.n_bellman_iterations, self.n_actions, losses.data_ptr(), None, _lib.stream_ptr(),
+                ),
+                "isdqn_heads_td_loss",
+            )
+        else:
+            ctx = self._context(B)
+            self._load_batch(ctx, ReplayElement(state, samples.action, samples.reward, next_state, samples.is_terminal))
+            tr = self._train_struct(ctx, params, None, B)
+            all_q = t.empty((2 * B, net.final_feature), dtype=t.float32, device="cuda")
+            _lib.check(
+                self._lib.isdqn_loss_on_batch(net._net, tr, ctx["batch"], all_q.data_ptr(), _lib.stream_ptr()),
+                "isdqn_loss_on_batch",
+            )
+            losses = ctx["losses"].clone()
+        self.last_all_q_values = all_q.reshape(2 * B, 1 + self.n_bellman_iterations, self.n_actions)
+        return losses.sum(), (losses, {})
+
+    def _as_dev(self, x, dtype):
+        t = self._torch
+        if isinstance(x, t.Tensor):
+            return x.to("cuda", dtype).contiguous()
+        return t.as_tensor(np.asarray(x)).to("cuda", dtype).contiguous()
+
+    def compute_target(self, sample, next_q_values):
+        """isdqn.py:105-109: r + (1 - d) * gamma^n * max_a next_q (fp32, evaluated as r + (((1-d) gamma^n) max))."""
+        t = self._torch
+        nq = next_q_values if isinstance(next_q_values, t.Tensor) else t.as_tensor(np.asarray(next_q_values))
+        nq = nq.to(t.float32)
+        r = t.as_tensor(np.asarray(sample.reward.cpu() if isinstance(sample.reward, t.Tensor) else sample.reward), dtype=t.float32).to(nq.device)
+        d = t.as_tensor(np.asarray(sample.is_terminal.cpu() if isinstance(sample.is_terminal, t.Tensor) else sample.is_terminal)).to(nq.device).to(t.int32)
+        coef = (1 - d).to(t.float32) * t.tensor(self.gamma**self.update_horizon, dtype=t.float32, device=nq.device)
+        return r + coef * nq.max(dim=-1).values
+
+    def shift_params(self, params: ParamTree) -> ParamTree:
+        """isdqn.py:111-125: \\bar{Q}_i <- Q_{i+1} on the last Dense layer only (Adam moments are not shifted)."""
+        mod = params["params"][f"Dense_{self.last_idx_mlp}"]
+        kernel, bias = mod["kernel"], mod["bias"]
+        _lib.check(
+            self._lib.isdqn_shift_heads(
+                kernel.data_ptr(), bias.data_ptr(), int(kernel.shape[0]), self.n_bellman_iterations, self.n_actions,
+                _lib.stream_ptr(),
+            ),
+            "isdqn_shift_heads",
+        )
+        return params
+
+    def best_action(self, params: ParamTree, state, key):
+        """isdqn.py:127-135: a uniformly drawn online head, then its greedy action.  Returns a 0-d int32 CUDA tensor
+        (`.item()` synchronises, like the reference's `.item()` in collect_single_sample).  The head draw uses
+        NumPy's stream seeded from `key` (JAX's threefry is not reproducible here)."""
+        t = self._torch
+        idx_network = int(np.random.default_rng(_key_to_seed(key)).integers(self.n_bellman_iterations))
+        return self.best_action_of_head(params, state, idx_network)
+
+    def best_action_of_head(self, params: ParamTree, state, idx_network: int):
+        t = self._torch
+        net = self.network
+        x, rows, is_float = net.prepare_input(state)
+        assert rows == 1
+        out = t.empty((), dtype=t.int32, device="cuda")
+        ws = net._workspace(1)
+        _lib.check(
+            self._lib.isdqn_best_action(
+                net._net, params.flat.data_ptr(), x.data_ptr(), is_float, int(idx_network), out.data_ptr(), ws.data_ptr(),
+                ws.numel(), _lib.stream_ptr(),
+            ),
+            "isdqn_best_action",
+        )
+        return out
+
+    def get_model(self):
+        """isdqn.py:137-138: `{"params": params}` with host numpy leaves (pickle-able, flax-shaped)."""
+        return {
+            "params": {
+                "params": {
+                    mod: {leaf: v.detach().cpu().numpy() for leaf, v in leaves.items()}
+                    for mod, leaves in self.params["params"].items()
+                }
+            }
+        }

@@ -1,0 +1,354 @@
+"""Replay buffer with a device-resident frame ring — drop-in for `slimdqn/sample_collection/replay_buffer.py`.
+
+Same API (`TransitionElement`, `ReplayElement`, `ReplayBuffer(...)`, `.add`, `.sample`, `.update`, `.add_count`,
+`._memory`, `._clipping`), different storage.  The reference keeps, per replay element, two stacked
+`(H, W, stack)` arrays in an OrderedDict (replay_buffer.py:88,128-149).  Here every observation frame is stored ONCE
+in a circular ring in HBM and an element is eight ring-slot references (zero padding = a slot that holds zeros);
+`sample()` is one sampling kernel plus one gather kernel (is-dqn_b200/csrc/{sampler,gather}.cu) whose output is
+byte-identical to `np.stack` over the reference's elements.
+
+Layout in HBM (capacity C elements, ring of R frame slots, frame of F bytes padded to a 16-byte stride):
+    frames        uint8  [R + 1][stride]     slot R is the all-zero frame
+    elem_frames   int32  [C][2*stack]        ring slots of state frames then next_state frames
+    elem_action   int64  [C]   elem_reward float64 [C]   elem_terminal uint8 [C]
+Element slot = key % C (keys are `add_count`, FIFO eviction keeps the live keys contiguous, replay_buffer.py:190-196).
+Frames are committed to the ring lazily, when the first element that references them is emitted, so the ring never
+holds frames of dropped (truncated) transitions; R = (1 + update_horizon) * C + stack + update_horizon + 2 is a
+proven upper bound of the live frames, overridable with `frame_capacity=`.
+
+The n-step accumulator (`accumulate`, replay_buffer.py:151-183) is host code, as in the reference; it emits frame
+references instead of copies.  Host -> device traffic is staged in pinned memory and flushed in bulk.
+"""
+from __future__ import annotations
+
+import collections
+import collections.abc
+import typing
+from typing import Any, Iterable, Optional
+
+import numpy as np
+import numpy.typing as npt
+
+from .. import _lib
+from . import ReplayItemID
+from .accumulator import Frame as _Frame
+from .accumulator import NStepAccumulator
+
+
+class TransitionElement(typing.NamedTuple):  # replay_buffer.py:18-23
+    observation: Optional[npt.NDArray[Any]]
+    action: int
+    reward: float
+    is_terminal: bool
+    episode_end: bool = False
+
+
+class ReplayElement(typing.NamedTuple):
+    """A single replay transition element, or a batch of them stacked on axis 0 (replay_buffer.py:26-33).
+
+    The reference's `pack`/`unpack` (snappy) exist for API compatibility and are identities: frames are stored
+    once in HBM, there is nothing to compress per element."""
+
+    state: Any
+    action: Any
+    reward: Any
+    next_state: Any
+    is_terminal: Any
+
+    def replace(self, **kw) -> "ReplayElement":
+        return self._replace(**kw)
+
+    def pack(self) -> "ReplayElement":
+        return self
+
+    def unpack(self) -> "ReplayElement":
+        return self
+
+
+class _MemoryView(collections.abc.Mapping):
+    """`rb._memory` as the reference exposes it: an ordered key -> ReplayElement mapping (live keys only)."""
+
+    def __init__(self, rb: "ReplayBuffer"):
+        self._rb = rb
+
+    def __len__(self):
+        return self._rb.add_count - self._rb._oldest_key
+
+    def __iter__(self):
+        return iter(range(self._rb._oldest_key, self._rb.add_count))
+
+    def __contains__(self, key):
+        return isinstance(key, (int, np.integer)) and self._rb._oldest_key <= key < self._rb.add_count
+
+    def __getitem__(self, key):
+        if key not in self:
+            raise KeyError(key)
+        b = self._rb._gather_keys(np.asarray([key], dtype=np.int64))
+        return ReplayElement(b.state[0], b.action[0].item(), b.reward[0].item(), b.next_state[0], bool(b.is_terminal[0]))
+
+
+class ReplayBuffer:
+    def __init__(
+        self,
+        sampling_distribution,
+        batch_size: int,
+        max_capacity: int,
+        stack_size: int = 4,
+        update_horizon: int = 1,
+        gamma: float = 0.99,
+        checkpoint_duration: int = 4,
+        compress: bool = True,
+        clipping: callable = None,
+        frame_capacity: Optional[int] = None,
+        staging_frames: int = 2048,
+    ):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._lib = _lib.load()
+        self._device = torch.device("cuda", torch.cuda.current_device())
+        self.add_count = 0
+        self._oldest_key = 0
+        self._max_capacity = max_capacity
+        self._compress = compress  # accepted for API compatibility; frames are stored once, uncompressed, in HBM
+        self._memory = _MemoryView(self)
+
+        self._sampling_distribution = sampling_distribution
+
+        self._checkpoint_duration = checkpoint_duration
+        self._batch_size = batch_size
+
+        self._stack_size = stack_size
+        self._update_horizon = update_horizon
+        self._gamma = gamma
+        self._clipping = clipping
+
+        self._accumulator = NStepAccumulator(stack_size, update_horizon, gamma, self._commit)
+        self._trajectory = self._accumulator.trajectory
+
+        # live elements: transiently max_capacity + 1 (replay_buffer.py:190-196 adds before it evicts)
+        self._slots = max_capacity + 1
+        self._frame_capacity = (
+            int(frame_capacity)
+            if frame_capacity is not None
+            else (1 + update_horizon) * (max_capacity + 1) + stack_size + update_horizon + 2
+        )
+        self._staging_frames = max(1, min(int(staging_frames), self._frame_capacity))
+        self._allocated = False
+        self._next_frame = 0        # frames committed so far (ids 0 .. _next_frame-1)
+        self._flushed_frames = 0    # ... of which already on the device
+        self._flushed_elems = 0     # elements whose metadata is already on the device
+        self._pending_event = None
+        self._action_dtype = None
+
+    # ------------------------------------------------------------------------------------------ allocation
+    def _allocate(self, observation: np.ndarray) -> None:
+        t = self._torch
+        obs = np.asarray(observation)
+        self._obs_shape = obs.shape
+        self._obs_dtype = obs.dtype
+        self._elem_size = obs.dtype.itemsize
+        if self._elem_size not in (1, 2, 4, 8):
+            raise _lib.IsdqnNativeError(f"unsupported observation dtype {obs.dtype}")
+        self._frame_elems = int(np.prod(obs.shape, dtype=np.int64)) if obs.shape else 1
+        self._frame_bytes = self._frame_elems * self._elem_size
+        self._frame_stride = (self._frame_bytes + 15) // 16 * 16
+        R, C, S = self._frame_capacity, self._slots, self._stack_size
+        self._zero_slot = R
+        self._d_frames = t.zeros((R + 1, self._frame_stride), dtype=t.uint8, device=self._device)
+        self._d_elem_frames = t.full((C, 2 * S), R, dtype=t.int32, device=self._device)
+        self._d_action = t.zeros(C, dtype=t.int64, device=self._device)
+        self._d_reward = t.zeros(C, dtype=t.float64, device=self._device)
+        self._d_terminal = t.zeros(C, dtype=t.uint8, device=self._device)
+        # pinned host mirrors / staging
+        self._h_stage = t.zeros((self._staging_frames, self._frame_stride), dtype=t.uint8).pin_memory()
+        self._h_stage_np = self._h_stage.numpy()
+        self._h_elem_frames = t.full((C, 2 * S), R, dtype=t.int32).pin_memory()
+        self._h_action = t.zeros(C, dtype=t.int64).pin_memory()
+        self._h_reward = t.zeros(C, dtype=t.float64).pin_memory()
+        self._h_terminal = t.zeros(C, dtype=t.uint8).pin_memory()
+        self._hn_elem_frames = self._h_elem_frames.numpy()
+        self._hn_action = self._h_action.numpy()
+        self._hn_reward = self._h_reward.numpy()
+        self._hn_terminal = self._h_terminal.numpy()
+        self._elem_min_frame = np.zeros(C, dtype=np.int64)  # smallest frame id an element references
+        self._allocated = True
+
+    # --------------------------------------------------------------------------------- host -> device flush
+    def _wait_pending(self) -> None:
+        if self._pending_event is not None:
+            self._pending_event.synchronize()
+            self._pending_event = None
+
+    def _copy_ring(self, dst, src, first: int, count: int, modulo: int) -> None:
+        """dst[(first + i) % modulo] = src[(first + i) % modulo] for i < count, as <= 2 contiguous copies."""
+        a = first % modulo
+        n1 = min(count, modulo - a)
+        dst[a : a + n1].copy_(src[a : a + n1], non_blocking=True)
+        if count > n1:
+            dst[: count - n1].copy_(src[: count - n1], non_blocking=True)
+
+    def _flush_frames(self) -> None:
+        n = self._next_frame - self._flushed_frames
+        if n == 0:
+            return
+        R, St = self._frame_capacity, self._staging_frames
+        done = 0
+        while done < n:  # staging index = id % St, ring index = id % R: copy maximal runs contiguous in both
+            fid = self._flushed_frames + done
+            run = min(n - done, St - fid % St, R - fid % R)
+            self._d_frames[fid % R : fid % R + run].copy_(self._h_stage[fid % St : fid % St + run], non_blocking=True)
+            done += run
+        self._flushed_frames = self._next_frame
+
+    def _flush(self) -> None:
+        """Pushes every pending frame and element record to the device (async, pinned source)."""
+        if not self._allocated:
+            return
+        dirty = self._next_frame > self._flushed_frames or self.add_count > self._flushed_elems
+        if not dirty:
+            return
+        self._flush_frames()
+        n = self.add_count - self._flushed_elems
+        if n > 0:
+            C = self._slots
+            first = self._flushed_elems
+            if n >= C:
+                first, n = 0, C
+            for dst, src in (
+                (self._d_elem_frames, self._h_elem_frames),
+                (self._d_action, self._h_action),
+                (self._d_reward, self._h_reward),
+                (self._d_terminal, self._h_terminal),
+            ):
+                self._copy_ring(dst, src, first, n, C)
+            self._flushed_elems = self.add_count
+        ev = self._torch.cuda.Event()
+        ev.record()
+        self._pending_event = ev
+
+    # -------------------------------------------------------------------------------------- frame commits
+    def _commit(self, fr: _Frame) -> int:
+        if fr.frame_id >= 0:
+            return fr.frame_id
+        self._wait_pending()  # an async flush may still be reading the pinned staging slots
+        live_from = self._elem_min_frame[self._oldest_key % self._slots] if self.add_count > self._oldest_key else self._next_frame
+        if self._next_frame - live_from >= self._frame_capacity:
+            raise _lib.IsdqnNativeError(
+                f"frame ring overflow: {self._frame_capacity} slots cannot hold the frames of the live elements; "
+                "pass a larger frame_capacity= to ReplayBuffer"
+            )
+        if self._next_frame - self._flushed_frames >= self._staging_frames:
+            self._wait_pending()
+            self._flush_frames()
+            ev = self._torch.cuda.Event()
+            ev.record()
+            ev.synchronize()  # the staging slots are about to be overwritten
+        obs = np.ascontiguousarray(fr.observation)
+        if obs.shape != self._obs_shape or obs.dtype != self._obs_dtype:
+            raise ValueError(f"observation {obs.shape}/{obs.dtype} differs from the first one {self._obs_shape}/{self._obs_dtype}")
+        fid = self._next_frame
+        self._h_stage_np[fid % self._staging_frames, : self._frame_bytes] = obs.reshape(-1).view(np.uint8)
+        fr.frame_id = fid
+        self._next_frame = fid + 1
+        return fid
+
+    def accumulate(self, transition: TransitionElement) -> Iterable[tuple]:
+        """Add a transition to the accumulator, maybe receive valid replay elements (replay_buffer.py:151-183).
+        Yields (frame refs, action, reward, is_terminal) records instead of materialised stacks."""
+        if not self._allocated:
+            self._allocate(transition.observation)
+        return self._accumulator.accumulate(
+            transition.observation, transition.action, transition.reward, transition.is_terminal, transition.episode_end
+        )
+
+    def add(self, transition: TransitionElement, **kwargs: Any) -> None:
+        """replay_buffer.py:185-196: key = add_count; sampler.add; FIFO eviction + sampler.remove."""
+        for refs, action, reward, is_terminal in self.accumulate(transition):
+            self._wait_pending()
+            if self._action_dtype is None:
+                self._action_dtype = np.asarray(action).dtype
+            key = ReplayItemID(self.add_count)
+            slot = key % self._slots
+            R = self._frame_capacity
+            valid = refs >= 0
+            self._hn_elem_frames[slot] = np.where(valid, refs % R, self._zero_slot)
+            self._elem_min_frame[slot] = refs[valid].min() if valid.any() else self._next_frame
+            self._hn_action[slot] = action
+            self._hn_reward[slot] = reward
+            self._hn_terminal[slot] = 1 if is_terminal else 0
+            self._sampling_distribution.add(key, **kwargs)
+            self.add_count += 1
+            if self.add_count > self._max_capacity:
+                oldest_key = self._oldest_key
+                self._oldest_key += 1
+                self._sampling_distribution.remove(oldest_key)
+
+    # --------------------------------------------------------------------------------------------- sampling
+    def _gather_slots_device(self, d_slots, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None):
+        """Runs the gather kernel for int32 CUDA element slots; returns CUDA tensors (no synchronisation).
+        `out`: preallocated CUDA tensors to gather into (e.g. the learner's persistent batch buffers)."""
+        t = self._torch
+        self._flush()
+        n = d_slots.numel()
+        S = self._stack_size
+        if out is not None:
+            state, action, reward, nxt, terminal = out
+        elif out_dtype == _lib.OUT_RAW:
+            shape = (n, self._frame_elems * S * self._elem_size)
+            state = t.empty(shape, dtype=t.uint8, device=self._device)
+            nxt = t.empty(shape, dtype=t.uint8, device=self._device)
+        else:
+            dt = t.float32 if out_dtype == _lib.OUT_F32 else t.bfloat16
+            state = t.empty((n,) + tuple(self._obs_shape) + (S,), dtype=dt, device=self._device)
+            nxt = t.empty_like(state)
+        if out is None:
+            action = t.empty(n, dtype=t.int64, device=self._device)
+            reward = t.empty(n, dtype=t.float64, device=self._device)
+            terminal = t.empty(n, dtype=t.uint8, device=self._device)
+        _lib.check(
+            self._lib.isdqn_gather_stacks(
+                self._d_frames.data_ptr(), self._frame_stride, self._frame_elems, self._elem_size, S,
+                self._d_elem_frames.data_ptr(), self._d_action.data_ptr(), self._d_reward.data_ptr(),
+                self._d_terminal.data_ptr(), d_slots.data_ptr(), n, out_dtype, state.data_ptr(), nxt.data_ptr(),
+                action.data_ptr(), reward.data_ptr(), terminal.data_ptr(), _lib.stream_ptr(),
+            ),
+            "isdqn_gather_stacks",
+        )
+        return ReplayElement(state, action, reward, nxt, terminal)
+
+    def _to_host(self, b: ReplayElement) -> ReplayElement:
+        n = b.action.numel()
+        shape = (n,) + tuple(self._obs_shape) + (self._stack_size,)
+        state = b.state.cpu().numpy().view(self._obs_dtype).reshape(shape)
+        nxt = b.next_state.cpu().numpy().view(self._obs_dtype).reshape(shape)
+        action = b.action.cpu().numpy().astype(self._action_dtype or np.int64, copy=False)
+        return ReplayElement(state, action, b.reward.cpu().numpy(), nxt, b.is_terminal.cpu().numpy().astype(np.bool_))
+
+    def _gather_keys(self, keys: np.ndarray) -> ReplayElement:
+        slots = (np.asarray(keys, dtype=np.int64) % self._slots).astype(np.int32)
+        d_slots = self._torch.from_numpy(slots).to(self._device)
+        return self._to_host(self._gather_slots_device(d_slots))
+
+    def sample_device(self, size=None, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None) -> ReplayElement:
+        """Device-resident `sample`: draw -> key -> slot -> gather without leaving the GPU.  For uint8 stack-4
+        frames the state tensors are (size, H, W, stack) uint8 (or f32/bf16 normalised with out_dtype)."""
+        assert self.add_count, ValueError("No samples in replay buffer!")
+        if size is None:
+            size = self._batch_size
+        _, _, d_slot = self._sampling_distribution.sample_device(size, self._slots)
+        b = self._gather_slots_device(d_slot, out_dtype, out)
+        if out is None and out_dtype == _lib.OUT_RAW and self._elem_size == 1:
+            shape = (size,) + tuple(self._obs_shape) + (self._stack_size,)
+            b = b._replace(state=b.state.view(shape), next_state=b.next_state.view(shape))
+        return b
+
+    def sample(self, size=None) -> ReplayElement:
+        """Sample a batch of elements from the replay buffer (replay_buffer.py:198-213); host numpy arrays."""
+        assert self.add_count, ValueError("No samples in replay buffer!")
+        if size is None:
+            size = self._batch_size
+        samples = self._sampling_distribution.sample(size)
+        return self._gather_keys(samples)
+
+    def update(self, keys, **kwargs: Any) -> None:  # replay_buffer.py:215-220
+        self._sampling_distribution.update(keys, **kwargs)
