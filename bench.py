@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — iS-DQN K=9 learner updates/s (+ replay samples/s) on B200.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20              # this repo (CUDA path)
+    python bench.py --impl reference --steps 20 --warmup 3         # the reference's CPU path (oracle port)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # N independent agents, one per GPU (weak scaling)
+
+A "step" is one learner update of BASELINE.json configs[1]: draw 32 transitions from the replay buffer (uniform,
+PCG64-exact), gather their 84x84x4 uint8 stacks out of the HBM frame ring, forward the K=9 Nature-CNN+LayerNorm
+network on s and s', iterated TD targets + loss, backward, Adam.
+
+  value  updates/s with every input resident in HBM (device sampler -> gather -> CUDA-graph learner step)
+  e2e    updates/s through the reference-facing call `agent.learn_on_batch(params, opt_state, host_batch)`:
+         pinned host batch -> H2D, step, D2H of the K losses — all inside the timed region
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FEATURES = [32, 64, 64, 512]
+K_HEADS, N_ACTIONS, BATCH = 9, 9, 32
+OBS = (84, 84, 4)
+LR, ADAM_EPS, GAMMA = 6.25e-5, 1.5e-4, 0.99  # launch_job/atari/launch.sh, experiments/atari/isdqn.py:46
+FLOP_PER_TRANSITION = 121_167_872
+
+
+def synthetic_stream(seed: int, n: int, chunk: int = 4096):
+    """Atari-shaped synthetic transitions: 90 % zero pixels, rewards in {-1,0,1}, geometric episodes."""
+    rng = np.random.default_rng(seed)
+    done = 0
+    while done < n:
+        m = min(chunk, n - done)
+        frames = rng.integers(0, 256, (m, 84, 84), dtype=np.uint8)
+        frames *= rng.random((m, 84, 84), dtype=np.float32) >= 0.9
+        actions = rng.integers(0, N_ACTIONS, m)
+        rewards = rng.integers(-1, 2, m).astype(np.float64)
+        terminal = rng.random(m) < 1e-3
+        for i in range(m):
+            yield frames[i], int(actions[i]), float(rewards[i]), bool(terminal[i])
+        done += m
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_steps(n_steps: int, warmup: int, capacity: int = 20_000, time_budget_s: float = 1e9):
+    """The reference's CPU learner path, restated (oracle port: JAX is not installable): ReplayOracle.sample(32) +
+    PyTorch-CPU learn_on_batch on all host cores.  Returns (updates/s, steps done, cores, sample description)."""
+    import torch
+
+    from oracle import learner_oracle as L
+    from oracle.replay_oracle import ReplayOracle
+    from oracle.samplers_oracle import UniformSamplingOracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rb = ReplayOracle(UniformSamplingOracle(0), BATCH, capacity, 4, 1, GAMMA)
+    for obs, a, r, d in synthetic_stream(0, capacity + 200):
+        rb.add(obs, a, r, d, d)
+    p = L.init_params(0, "cnn", OBS, FEATURES, (1 + K_HEADS) * N_ACTIONS, True, torch.float32)
+    mu, nu, count = L.zeros_like_params(p), L.zeros_like_params(p), 0
+
+    def step():
+        nonlocal count
+        b = rb.sample()
+        batch = tuple(torch.from_numpy(np.asarray(x)) for x in b)
+        count, losses, _, _, _ = L.learn_on_batch(p, mu, nu, count, batch, "cnn", True, K_HEADS, N_ACTIONS, GAMMA, 1, LR, ADAM_EPS)
+        return losses
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < n_steps and (time.perf_counter() - t0) < time_budget_s:
+        step()
+        done += 1
+    dt = time.perf_counter() - t0
+    desc = (f"{done} updates of batch {BATCH} (oracle port: numpy replay sample from a {capacity}-element buffer + "
+            f"torch-CPU fp32 learn_on_batch, {cores} threads)")
+    return done / dt, done, cores, desc, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    ups, done, cores, desc, dt = cpu_reference_steps(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "iS-DQN K=9 learner updates/sec", "value": ups, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(20_000),
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(capacity):
+    return {
+        "workload": "iS-DQN K=9 Nature-CNN+LayerNorm, Asterix-shaped synthetic uint8 84x84x4, batch 32, uniform replay "
+                    "(BASELINE.json configs[1])",
+        "batch": BATCH, "K": K_HEADS, "A": N_ACTIONS, "features": FEATURES, "replay_capacity": capacity,
+        "parallelism": "independent agents, one per GPU, no communication (SURVEY §8e mode 1)",
+        "l2": "inputs larger than L2: batches are drawn uniformly from the frame ring in HBM (7.06 GB at 1 M frames); "
+              "parameters/Adam state (65 MB) stay L2-resident between steps as in real training",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def kernel_work(name: str, P: int):
+    """Algorithmic work of one launch for the roofline: ('hbm', bytes) or ('tensor', flops)."""
+    B = BATCH
+    if name == "adam":
+        return "hbm", 28 * P
+    if name == "gather_stack4_u8":
+        return "hbm", 91_728 * B
+    if name == "dense_wgrad_gemm":
+        return "hbm", 4 * 7744 * 512 + 4 * B * (7744 + 512)  # dW written once + operands read once
+    if name == "dense_dgrad_gemm":
+        return "hbm", 4 * 7744 * 512 + 4 * B * (7744 + 512)
+    if name == "dense_fwd_gemm":
+        return "hbm", 4 * 7744 * 512 + 4 * 2 * B * (7744 + 512)
+    return None, 0
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from isdqn_b200 import _lib
+    from isdqn_b200.networks.isdqn import iSDQN
+    from isdqn_b200.sample_collection.replay_buffer import ReplayBuffer, ReplayElement, TransitionElement
+    from isdqn_b200.sample_collection.samplers import UniformSamplingDistribution
+
+    cap = args.capacity
+    rb = ReplayBuffer(UniformSamplingDistribution(rank), BATCH, cap, stack_size=4, update_horizon=1, gamma=GAMMA,
+                      clipping=lambda x: np.clip(x, -1, 1), frame_capacity=cap + cap // 8 + 64)
+    t_fill = time.perf_counter()
+    n_fill = cap + max(cap // 10, 64)
+    for obs, a, r, d in synthetic_stream(1000 + rank, n_fill):
+        rb.add(TransitionElement(obs, a, r, d, d))
+    t_fill = time.perf_counter() - t_fill
+    agent = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "cnn", LR, GAMMA, 1, 1, 8000, adam_eps=ADAM_EPS)
+    P = agent.network.n_params
+    stream = torch.cuda.Stream()
+    peaks = measured_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        step_no = [0]
+
+        def step():
+            step_no[0] += 1
+            agent.update_online_params(step_no[0], rb)
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            ev0.record()
+            for _ in range(args.steps):
+                step()
+            ev1.record()
+            barrier()
+        ms = ev0.elapsed_time(ev1)
+        # ---- e2e: host batch -> H2D -> step -> D2H of the losses, through the reference-facing call
+        pool = [rb.sample() for _ in range(8)]
+        h2d = sum(np.asarray(x).nbytes for x in pool[0])
+        for i in range(max(3, args.warmup // 2)):
+            agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])[2].cpu()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            _, _, losses = agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])
+            losses_host = losses.cpu()
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        d2h = losses_host.numel() * 4
+        # ---- replay throughput shape: 2048 batches of 32 per launch (sampler + gather only)
+        n_big = 2048 * BATCH
+        for _ in range(3):
+            rb.sample_device(n_big)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        r0.record()
+        for _ in range(reps):
+            rb.sample_device(n_big)
+        r1.record()
+        torch.cuda.synchronize()
+        ms_replay = r0.elapsed_time(r1) / reps
+        prof_replay = _lib.profile(lambda: rb.sample_device(n_big))
+        gather_ms = sum(t for n, t in prof_replay if n == "gather_stack4_u8")
+        # ---- per-kernel profile of one step (direct launches behind a spin kernel: no launch gaps)
+        agent._use_graph = False
+        prof = _lib.profile(lambda: agent.update_online_params(1, rb))
+        agent._use_graph = True
+    per_kernel = {}
+    for name, t in prof:
+        per_kernel.setdefault(name, [0, 0.0])
+        per_kernel[name][0] += 1
+        per_kernel[name][1] += t
+    launches = len(prof)
+    step_prof_ms = sum(t for _, t in prof)
+    dominant = max(per_kernel.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_count, dom_ms) = dominant
+    kind, work = kernel_work(dom_name, P)
+
+    t_max = torch.tensor([ms, ms_e2e, ms_replay], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_replay = (float(x) for x in t_max.cpu())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = world * args.steps / (ms / 1e3)
+    e2e = world * args.steps / (ms_e2e / 1e3)
+    roofline = None
+    if kind == "hbm":
+        ach = work * dom_count / (dom_ms / 1e3) / 1e9 / max(dom_count, 1) * 1.0
+        ach = (work / 1e9) / ((dom_ms / dom_count) / 1e3)
+        roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
+                    "share_of_step": dom_ms / step_prof_ms}
+    else:
+        roofline = {"kernel": dom_name, "bound": "tensor", "achieved": None, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                    "frac": None, "traffic": None, "peak_src": peaks["src"], "share_of_step": dom_ms / step_prof_ms}
+    gather_gbs = 91_728 * n_big / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else None
+    cpu = None
+    if world == 1 or True:
+        ups, done, cores, desc, _ = cpu_reference_steps(10**9, 2, time_budget_s=args.cpu_seconds)
+        cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc}
+    line = {
+        "metric": "iS-DQN K=9 learner updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cap),
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches * args.steps,
+        "gpu_launches_per_step": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "learner_tflops": world * args.steps * BATCH * FLOP_PER_TRANSITION / (ms / 1e3) / 1e12,
+        "replay": {"samples_per_s": world * n_big / (ms_replay / 1e3), "launch_samples": n_big,
+                   "gather_GBps": gather_gbs, "gather_frac_of_hbm": (gather_gbs / peaks["hbm_gbs"]) if gather_gbs else None,
+                   "kernels_ms": {n: t for n, t in prof_replay}},
+        "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 5)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
+        "fill": {"adds": n_fill, "seconds": t_fill},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--capacity", type=int, default=int(os.environ.get("ISDQN_BENCH_CAPACITY", 1_000_000)))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

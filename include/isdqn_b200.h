@@ -225,6 +225,14 @@ int isdqn_graph_end(void* stream, void** out_graph_exec);
 int isdqn_graph_launch(void* graph_exec, void* stream);
 int isdqn_graph_destroy(void* graph_exec);
 
+/* ------------------------------------------------------------------------------------------------- profiler
+ * Measurement support for bench.py (no counterpart in the reference): between begin and end every kernel launch
+ * of this library records a CUDA event on its stream; end returns (name, milliseconds) per launch. */
+int isdqn_profile_begin(void);
+int isdqn_profile_end(void* stream, int32_t max_entries, char* names, int32_t name_stride, float* ms);
+/* a ~micros busy-wait kernel: lets the host queue the following launches back to back (no launch gaps) */
+int isdqn_spin(void* stream, int32_t micros);
+
 /* -------------------------------------------------------------------------------------------- data parallel
  * New functionality (the reference has no collective): gradient all-reduce over NVLink. NCCL is
  * dlopen'ed on first use.  h_unique_id is the 128-byte ncclUniqueId produced on rank 0. */

@@ -124,6 +124,9 @@ PROTOTYPES = {
     "isdqn_graph_end": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "isdqn_graph_launch": (C.c_int, [_P, _P]),
     "isdqn_graph_destroy": (C.c_int, [_P]),
+    "isdqn_profile_begin": (C.c_int, []),
+    "isdqn_profile_end": (C.c_int, [_P, _I32, C.c_char_p, _I32, C.POINTER(C.c_float)]),
+    "isdqn_spin": (C.c_int, [_P, _I32]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),
@@ -164,6 +167,23 @@ def check(rc: int, what: str = "") -> None:
     msg = lib.isdqn_strerror(rc).decode()
     detail = lib.isdqn_last_cuda_error().decode() if rc in (-3, -5) else ""
     raise IsdqnNativeError(f"{what or 'isdqn call'} failed: {msg} ({rc}) {detail}".strip())
+
+
+def profile(fn, spin_us: int = 300):
+    """Runs fn() with the library's per-launch event marks on; returns [(kernel name, ms)] in launch order."""
+    lib = load()
+    stream = stream_ptr()
+    check(lib.isdqn_spin(stream, spin_us), "isdqn_spin")
+    check(lib.isdqn_profile_begin(), "isdqn_profile_begin")
+    try:
+        fn()
+    finally:
+        names = C.create_string_buffer(512 * 48)
+        ms = (C.c_float * 512)()
+        n = lib.isdqn_profile_end(stream, 512, names, 48, ms)
+    if n < 0:
+        check(n, "isdqn_profile_end")
+    return [(names.raw[i * 48 : (i + 1) * 48].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n)]
 
 
 def require_cuda():

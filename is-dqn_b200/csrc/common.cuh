@@ -28,6 +28,15 @@ void set_last_cuda_error(cudaError_t e, const char* where);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Optional per-kernel timing (isdqn_profile_begin/end): every launch site marks its name; a mark records a CUDA
+// event on the launching stream, so consecutive marks bracket one kernel.  Off (one predictable branch) by default.
+extern bool g_profile_on;
+void profile_mark(cudaStream_t s, const char* name);
+#define ISDQN_PROF(stream, name)                              \
+  do {                                                        \
+    if (::isdqn::g_profile_on) ::isdqn::profile_mark(stream, name); \
+  } while (0)
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
   return (a + b - 1) / b;

@@ -16,6 +16,7 @@ inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpre
 
 template <int KIND>
 int launch_conv_fwd_kind(const ConvArgs& a, cudaStream_t s) {
+  ISDQN_PROF(s, "conv_fwd");
   if (a.Cout <= 32) {
     conv_fwd_kernel<64, 32, 4, KIND><<<ceil_div(a.M, 64), kGemmThreads, 0, s>>>(a);
   } else if (a.Cout <= 64) {
@@ -39,7 +40,8 @@ int launch_conv_fwd(const ConvArgs& a, int kind, cudaStream_t s) {
   }
 }
 
-int launch_gemm(const GemmArgs& g, int splits, cudaStream_t s) {
+int launch_gemm(const GemmArgs& g, int splits, cudaStream_t s, const char* tag) {
+  ISDQN_PROF(s, tag);
   dim3 grid(ceil_div(g.M, 64), ceil_div(g.N, 64), splits);
   const bool a_kfast = g.sak == 1;
   const bool b_nfast = g.sbn == 1;
@@ -106,10 +108,11 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
         g.C = part + (int64_t)m_begin * L.out_dim; g.ldc = L.out_dim; g.split_stride = split_stride;
         g.M = m_count; g.N = L.out_dim; g.K = L.in_dim; g.k_per_split = kps;
         g.bias = direct ? params + L.b_off : nullptr;
-        int rc = launch_gemm(g, real_splits, s);
+        int rc = launch_gemm(g, real_splits, s, "dense_fwd_gemm");
         if (rc) return rc;
       }
       if (!direct) {
+        ISDQN_PROF(s, "dense_finalize");
         dense_finalize_kernel<<<rows, kRowThreads, 0, s>>>(
             part, real_splits, split_stride, rows, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu, out,
             rows_train > 0 ? wsp(ws, w.xhat[l]) : nullptr, rows_train > 0 ? wsp(ws, w.rstd[l]) : nullptr, rows_train);
@@ -128,6 +131,7 @@ int check_common(const isdqn_net* net, Plan* p) {
 
 int run_loss(const Plan& p, const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, const float* q_all,
              float* dq, float* dbias, int32_t* count, cudaStream_t s) {
+  ISDQN_PROF(s, "heads_td_loss");
   heads_td_loss_kernel<<<1, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n,
                                                   tr->batch, tr->batch_global, net->n_heads, net->n_actions,
                                                   tr->d_losses, dq, dbias, count);
@@ -160,7 +164,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       g.C = grads + L.w_off; g.ldc = L.out_dim; g.split_stride = 0;
       g.M = L.in_dim; g.N = L.out_dim; g.K = B; g.k_per_split = ceil_div(B, kBK) * kBK;
       g.bias = nullptr;
-      int rc = launch_gemm(g, 1, s);
+      int rc = launch_gemm(g, 1, s, "dense_wgrad_gemm");
       if (rc) return rc;
     } else {
       ConvWgradArgs a;
@@ -172,6 +176,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       a.rows_per_split = ceil_div(ceil_div(rows_l, splits), kBK) * kBK;
       const int real_splits = ceil_div(rows_l, a.rows_per_split);
       dim3 grid(ceil_div(L.in_dim, 64), ceil_div(L.out_dim, 64), real_splits);
+      ISDQN_PROF(s, "conv_wgrad");
       if (first) {
         if (in_kind == IN_U8_255) conv_wgrad_kernel<IN_U8_255><<<grid, kGemmThreads, 0, s>>>(a);
         else if (in_kind == IN_F32_255) conv_wgrad_kernel<IN_F32_255><<<grid, kGemmThreads, 0, s>>>(a);
@@ -203,7 +208,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       g.C = dprev; g.ldc = L.in_dim; g.split_stride = 0;
       g.M = B; g.N = L.in_dim; g.K = L.out_dim; g.k_per_split = ceil_div(L.out_dim, kBK) * kBK;
       g.bias = nullptr;
-      int rc = launch_gemm(g, 1, s);
+      int rc = launch_gemm(g, 1, s, "dense_dgrad_gemm");
       if (rc) return rc;
     } else {
       ConvDgradArgs a;
@@ -215,6 +220,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       a.dz = dz; a.w = params + L.w_off; a.dx = dprev;
       const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
       dim3 grid(ceil_div(rows_max, 64), ceil_div(L.Cin, 64), L.stride * L.stride);
+      ISDQN_PROF(s, "conv_dgrad");
       conv_dgrad_kernel<<<grid, kGemmThreads, 0, s>>>(a);
       ISDQN_LAUNCH_CHECK();
     }
@@ -222,6 +228,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       const int rows_p = B * P.pix;
       const float* g_ = P.has_ln ? params + P.g_off : nullptr;
       const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
+      ISDQN_PROF(s, "ln_relu_bwd");
       if (ln_bwd_use_warp(P.out_dim)) {
         ln_relu_bwd_warp_kernel<<<w.col_ctas[l - 1], 256, 0, s>>>(dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]),
                                                                   g_, b_, wsp(ws, w.act[l - 1]), rows_p, P.out_dim,
@@ -240,6 +247,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
     for (int i = 0; i < segs.count; ++i) max_n = segs.s[i].n > max_n ? segs.s[i].n : max_n;
     int gx = ceil_div(max_n, 256);
     if (gx > 64) gx = 64;
+    ISDQN_PROF(s, "reduce_segments");
     reduce_segments_kernel<<<dim3(gx, segs.count), 256, 0, s>>>(segs);
     ISDQN_LAUNCH_CHECK();
   }
@@ -276,6 +284,7 @@ int train_common(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch*
   if (rc) return rc;
   if (!update) return ISDQN_OK;
   if (tr->nccl_comm) {
+    ISDQN_PROF(s, "nccl_allreduce");
     rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, p.layout.total, stream);
     if (rc) return rc;
   }
@@ -351,6 +360,7 @@ extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, fl
   const int64_t n4 = n / 4;
   int64_t grid = ceil_div<int64_t>(n4, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  ISDQN_PROF(as_stream(stream), "adam");
   adam_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n4);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;

@@ -10,9 +10,68 @@ static thread_local char g_last_error[512] = "";
 void set_last_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+
+// ---------------------------------------------------------------------------------------------- profiler
+bool g_profile_on = false;
+namespace {
+constexpr int kMaxMarks = 512;
+cudaEvent_t g_marks[kMaxMarks];
+const char* g_mark_names[kMaxMarks];
+int g_n_marks = 0;
+}  // namespace
+void profile_mark(cudaStream_t s, const char* name) {
+  if (g_n_marks >= kMaxMarks) return;
+  if (!g_marks[g_n_marks]) cudaEventCreate(&g_marks[g_n_marks]);
+  cudaEventRecord(g_marks[g_n_marks], s);
+  g_mark_names[g_n_marks] = name;
+  ++g_n_marks;
+}
 }  // namespace isdqn
 
 using namespace isdqn;
+
+extern "C" int isdqn_profile_begin(void) {
+  g_n_marks = 0;
+  g_profile_on = true;
+  return ISDQN_OK;
+}
+
+// Closes the capture with a final mark on `stream`, synchronises, and writes up to `max_entries` (name, ms)
+// pairs: entry i is the time between mark i and mark i+1.  Returns the number of entries (or a negative error).
+extern "C" int isdqn_profile_end(void* stream, int32_t max_entries, char* names, int32_t name_stride, float* ms) {
+  if (!g_profile_on) return ISDQN_E_INVALID;
+  profile_mark(as_stream(stream), "end");
+  g_profile_on = false;
+  if (g_n_marks < 1) return 0;
+  ISDQN_CUDA_CHECK(cudaEventSynchronize(g_marks[g_n_marks - 1]));
+  int n = g_n_marks - 1;
+  if (n > max_entries) n = max_entries;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    ISDQN_CUDA_CHECK(cudaEventElapsedTime(&t, g_marks[i], g_marks[i + 1]));
+    if (ms) ms[i] = t;
+    if (names && name_stride > 0) {
+      strncpy(names + (size_t)i * name_stride, g_mark_names[i], name_stride - 1);
+      names[(size_t)i * name_stride + name_stride - 1] = 0;
+    }
+  }
+  return n;
+}
+
+// Keeps the GPU busy for ~`micros` so that the host can queue the launches that follow without gaps.
+namespace isdqn {
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+}  // namespace isdqn
+extern "C" int isdqn_spin(void* stream, int32_t micros) {
+  if (micros < 0 || micros > 100000) return ISDQN_E_INVALID;
+  spin_kernel<<<1, 1, 0, as_stream(stream)>>>((long long)micros * 1900);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
 
 extern "C" int isdqn_abi_version(void) { return ISDQN_ABI_VERSION; }
 

@@ -137,6 +137,7 @@ extern "C" int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t si
   if (!d_rng || n_valid < 1 || size < 0 || (d_index_to_key && capacity < 1)) return ISDQN_E_INVALID;
   if (size > (1 << 20)) return ISDQN_E_TOO_LARGE;
   if (size == 0) return ISDQN_OK;
+  ISDQN_PROF(as_stream(stream), "sample_uniform");
   sample_uniform_kernel<<<1, kUniformThreads, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key,
                                                                       capacity, d_out_index, d_out_key, d_out_slot);
   ISDQN_LAUNCH_CHECK();
@@ -152,9 +153,11 @@ extern "C" int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, 
   if (size == 0) return ISDQN_OK;
   int grid = ceil_div(size, kPrioThreads);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  ISDQN_PROF(as_stream(stream), "sample_prioritized");
   sample_prioritized_kernel<<<grid, kPrioThreads, 0, as_stream(stream)>>>(
       d_rng, d_nodes, depth, size, d_index_to_key, capacity, d_out_index, d_out_key, d_out_slot, d_out_target, d_status);
   ISDQN_LAUNCH_CHECK();
+  ISDQN_PROF(as_stream(stream), "pcg_advance");
   pcg_advance64_kernel<<<1, 1, 0, as_stream(stream)>>>(d_rng, (uint64_t)size);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;

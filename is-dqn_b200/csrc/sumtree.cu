@@ -268,6 +268,7 @@ extern "C" int isdqn_sumtree_query(const double* d_nodes, int depth, const doubl
   int top_levels = 0;
   if (n / grid >= 4096) top_levels = depth - 1 < kQueryMaxTopLevels ? depth - 1 : kQueryMaxTopLevels;
   const size_t smem = top_levels > 0 ? sizeof(double) * ((1u << top_levels) - 1) : 0;
+  ISDQN_PROF(as_stream(stream), "sumtree_query");
   sumtree_query_kernel<kQueryPerThread><<<(unsigned)grid, kQueryThreads, smem, as_stream(stream)>>>(
       d_nodes, depth, d_targets, n, d_out_index, d_status, top_levels);
   ISDQN_LAUNCH_CHECK();
@@ -279,6 +280,7 @@ extern "C" int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_in
   if (!d_nodes || !d_index || !d_value || depth < 1 || depth > 31 || n < 0) return ISDQN_E_INVALID;
   if (n == 0) return ISDQN_OK;
   if (n > ISDQN_SUMTREE_SET_MAX) return ISDQN_E_TOO_LARGE;
+  ISDQN_PROF(as_stream(stream), "sumtree_set");
   if (n <= 1024) {
     sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), as_stream(stream)>>>(
         d_nodes, depth, d_index, d_value, n, d_max_priority, d_status);
@@ -304,6 +306,7 @@ extern "C" int isdqn_sumtree_set_ops(double* d_nodes, int depth, const int32_t* 
   if (!d_nodes || !d_op_offset || !d_index || !d_value || depth < 1 || depth > 31 || n_ops < 0)
     return ISDQN_E_INVALID;
   if (n_ops == 0) return ISDQN_OK;
+  ISDQN_PROF(as_stream(stream), "sumtree_set_ops");
   sumtree_set_ops_kernel<ISDQN_SUMTREE_OP_MAX, 256><<<1, 256, set_smem_bytes<ISDQN_SUMTREE_OP_MAX>(), as_stream(stream)>>>(
       d_nodes, depth, d_op_offset, n_ops, d_index, d_value, d_max_priority, d_status);
   ISDQN_LAUNCH_CHECK();

@@ -291,11 +291,14 @@ class iSDQN:
             all_q, _ = net.apply_fn(params, t.cat((state, next_state)))
             all_q = all_q.reshape(2 * B, -1).contiguous()
             losses = t.empty(self.n_bellman_iterations, dtype=t.float32, device="cuda")
+            # named references: the buffers must outlive the (asynchronous) kernel in allocator order
+            d_action = self._as_dev(samples.action, t.int64)
+            d_reward = self._as_dev(samples.reward, t.float64)
+            d_terminal = self._as_dev(samples.is_terminal, t.uint8)
             _lib.check(
                 self._lib.isdqn_heads_td_loss(
-                    all_q.data_ptr(), self._as_dev(samples.action, t.int64).data_ptr(),
-                    self._as_dev(samples.reward, t.float64).data_ptr(),
-                    self._as_dev(samples.is_terminal, t.uint8).data_ptr(), float(self.gamma**self.update_horizon), B, B,
+                    all_q.data_ptr(), d_action.data_ptr(), d_reward.data_ptr(), d_terminal.data_ptr(),
+                    float(self.gamma**self.update_horizon), B, B,
                     self.n_bellman_iterations, self.n_actions, losses.data_ptr(), None, _lib.stream_ptr(),
                 ),
                 "isdqn_heads_td_loss",

@@ -108,8 +108,9 @@ def layer_norm_lastdim(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor,
     return (x - mean) * (torch.rsqrt(var + eps) * scale) + bias
 
 
-def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_heads_total: int, n_actions: int) -> torch.Tensor:
-    """DQNNet.__call__ + iSDQN.apply reshape.  x: (N,H,W,C) uint8/float for cnn, (N,D) for fc."""
+def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_heads_total: int, n_actions: int, taps=None) -> torch.Tensor:
+    """DQNNet.__call__ + iSDQN.apply reshape.  x: (N,H,W,C) uint8/float for cnn, (N,D) for fc.
+    `taps`: optional list that receives every pre-ReLU tensor (used by `relu_margin`)."""
     dtype = params["Dense_0"]["kernel"].dtype
     ln = 0
     d = 0
@@ -125,6 +126,8 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
             if layer_norm:
                 x = layer_norm_lastdim(x, params[f"LayerNorm_{ln}"]["scale"], params[f"LayerNorm_{ln}"]["bias"])
                 ln += 1
+            if taps is not None:
+                taps.append(x)
             x = torch.relu(x)
         x = x.reshape(x.shape[0], -1)
     else:
@@ -135,6 +138,8 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
         if layer_norm:
             x = layer_norm_lastdim(x, params[f"LayerNorm_{ln}"]["scale"], params[f"LayerNorm_{ln}"]["bias"])
             ln += 1
+        if taps is not None:
+            taps.append(x)
         x = torch.relu(x)
     last = params[f"Dense_{n_dense - 1}"]
     q = x @ last["kernel"] + last["bias"]
@@ -211,6 +216,18 @@ def shift_params(params: Params, last_idx_mlp: int, A: int) -> None:
 def best_action(params: Params, state, arch, layer_norm, K, A, idx_network: int) -> int:
     q = forward(params, state.unsqueeze(0), arch, layer_norm, 1 + K, A)[0]
     return int(torch.argmax(q[1 + idx_network]))
+
+
+def relu_margin(params: Params, state: torch.Tensor, arch: str, layer_norm: bool, n_heads_total: int, n_actions: int) -> float:
+    """min |pre-ReLU value| over every unit of the forward pass on `state`.  A unit closer to zero than the fp32
+    rounding of its pre-activation (~1e-6) can take the other ReLU branch in fp32 than in float64, which changes
+    the GRADIENT discontinuously (one flipped unit moved Conv_0.kernel's gradient by 7e-3 in a probe, identically
+    for torch-CPU fp32 and the CUDA path).  Parity tests therefore use batches whose margin is comfortably
+    larger than that rounding; Q-values/targets/losses are continuous and need no such care."""
+    taps: list = []
+    with torch.no_grad():
+        forward(params, state, arch, layer_norm, n_heads_total, n_actions, taps)
+    return min(float(t.abs().min()) for t in taps) if taps else float("inf")
 
 
 def make_batch(seed: int, B: int, obs_dim, A: int, arch: str, p_terminal: float = 0.2):
