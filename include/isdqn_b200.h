@@ -125,7 +125,7 @@ int isdqn_gather_stacks(const uint8_t* d_frames, int64_t frame_stride, int32_t f
                         int64_t* d_out_action, double* d_out_reward, uint8_t* d_out_terminal, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ learner
- * Flat parameter vector: leaves packed in execution order, each leaf start aligned to 4 floats:
+ * Flat parameter vector: leaves packed in execution order, each leaf start aligned to 8 floats:
  *   cnn: Conv_i.kernel (HWIO), Conv_i.bias, [LayerNorm_i.scale, LayerNorm_i.bias] for i=0..2, then the Dense
  *        tail; fc: Dense tail only.  Dense kernels are (in, out) row-major; activations are NHWC.
  * (slimdqn/networks/architectures/dqn.py:47-103; names are flax's auto-names.) */
@@ -148,7 +148,7 @@ typedef struct isdqn_layout {
   int32_t n_leaves;
   int64_t offset[ISDQN_MAX_LEAVES]; /* in floats */
   int64_t size[ISDQN_MAX_LEAVES];   /* in floats */
-  int64_t total;                    /* padded total, multiple of 4 */
+  int64_t total;                    /* padded total, multiple of 8 */
 } isdqn_layout;
 
 int isdqn_net_layout(const isdqn_net* net, isdqn_layout* out);
@@ -202,7 +202,20 @@ typedef struct isdqn_train {
   float* d_losses;          /* [K] per-head mean TD^2 of THIS step (local share under DP) */
   void* d_workspace; int64_t workspace_bytes;
   void* nccl_comm;          /* NULL, or the handle from isdqn_dp_init: gradients are all-reduced before Adam */
+  int32_t compute_dtype;    /* ISDQN_COMPUTE_F32 (CUDA-core fp32, 1e-5 parity) or ISDQN_COMPUTE_BF16 (tcgen05, 2e-2) */
+  void* d_workspace_tc; int64_t workspace_tc_bytes; /* bf16 path only: isdqn_learn_workspace_tc_bytes() */
 } isdqn_train;
+#define ISDQN_COMPUTE_F32 0
+#define ISDQN_COMPUTE_BF16 1
+/* bytes of bf16 scratch the tensor-core path needs (0 if the network is not eligible: cnn with 32/64/128/256
+ * channel convs and hidden Dense widths that are multiples of 64) */
+int64_t isdqn_learn_workspace_tc_bytes(const isdqn_net* net, int32_t batch);
+
+/* Building block / test entry of the tcgen05 tile engine: D[M][N] (fp32) = A B^T, bf16 operands.
+ *   a_mn_major = 0: A is [M][lda] (K contiguous); 1: A is [K][lda] (M contiguous); likewise B with N.
+ * splits > 1 writes the partial products of `splits` K ranges at d_c + z*M*N. lda, ldb, N multiples of 8. */
+int isdqn_tc_gemm_bf16(const void* d_a, int64_t lda, int32_t a_mn_major, const void* d_b, int64_t ldb, int32_t b_mn_major,
+                       float* d_c, int32_t M, int32_t N, int32_t K, int32_t splits, void* stream);
 
 /* replaces: iSDQN.loss_on_batch  isdqn.py:92-103 (forward on concat(s, s') + loss, no gradient). */
 int isdqn_loss_on_batch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* batch, float* d_q_all,

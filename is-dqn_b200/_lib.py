@@ -27,6 +27,7 @@ ST_OP_TOO_LARGE = 32
 
 OUT_RAW, OUT_F32, OUT_BF16 = 0, 1, 2
 ARCH_CNN, ARCH_FC = 0, 1
+COMPUTE_F32, COMPUTE_BF16 = 0, 1
 
 
 class IsdqnNativeError(RuntimeError):
@@ -84,6 +85,9 @@ class Train(C.Structure):
         ("d_workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
         ("nccl_comm", C.c_void_p),
+        ("compute_dtype", C.c_int32),
+        ("d_workspace_tc", C.c_void_p),
+        ("workspace_tc_bytes", C.c_int64),
     ]
 
 
@@ -111,6 +115,8 @@ PROTOTYPES = {
     "isdqn_net_layout": (C.c_int, [C.POINTER(Net), C.POINTER(Layout)]),
     "isdqn_forward_workspace_bytes": (_I64, [C.POINTER(Net), _I32]),
     "isdqn_learn_workspace_bytes": (_I64, [C.POINTER(Net), _I32]),
+    "isdqn_learn_workspace_tc_bytes": (_I64, [C.POINTER(Net), _I32]),
+    "isdqn_tc_gemm_bf16": (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I32, _I32, _I32, _I32, _P]),
     "isdqn_forward": (C.c_int, [C.POINTER(Net), _P, _P, _I32, _I32, _P, _P, _I64, _P]),
     "isdqn_heads_td_loss": (C.c_int, [_P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "isdqn_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),

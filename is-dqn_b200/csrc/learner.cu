@@ -10,6 +10,9 @@ extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, fl
                                        const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
                                        void* stream);
 
+int isdqn_tc_train_dispatch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update,
+                            float* q_out, void* stream);
+
 namespace {
 
 inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret_cast<float*>(ws) + off; }
@@ -256,6 +259,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
 
 int train_common(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update,
                  float* q_out, void* stream) {
+  if (tr && tr->compute_dtype == ISDQN_COMPUTE_BF16) return isdqn_tc_train_dispatch(net, tr, b, backward, update, q_out, stream);
   Plan p;
   int rc = check_common(net, &p);
   if (rc) return rc;

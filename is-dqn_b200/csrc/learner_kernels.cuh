@@ -10,6 +10,8 @@
 //   gemm_strided_kernel  Dense forward / wgrad / dgrad with arbitrary operand strides and split-K.
 //   dense_finalize_kernel, ln_relu_bwd_*_kernel, reduce_segments_kernel, heads_td_loss_kernel, adam_kernel.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace isdqn {
@@ -296,7 +298,7 @@ struct ConvDgradArgs {
   float* dx;        // [n_img*H*W][Cin]
 };
 
-__global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const ConvDgradArgs a) {
+static __global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const ConvDgradArgs a) {
   constexpr int BM = 64, BN = 64, TN = 8;
   typedef TileCfg<BM, BN, TN> Cfg;
   __shared__ __align__(16) float As[kBK][BM + 4];
@@ -454,11 +456,11 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 }
 
 // out[r][n] = act( LN( sum_s part[s][r][n] + bias[n] ) ); one CTA per row
-__global__ void __launch_bounds__(kRowThreads)
+static __global__ void __launch_bounds__(kRowThreads)
 dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int rows, int N,
                       const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                       int relu, float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
-                      int rows_train) {
+                      int rows_train, __nv_bfloat16* __restrict__ out16 = nullptr) {
   __shared__ float red[kRowThreads / 32];
   const int r = blockIdx.x;
   float z[kRowMaxPerThread];
@@ -499,7 +501,9 @@ dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_
         if (save) xhat[(int64_t)r * N + n] = xh;
         y = xh * ln_g[n] + ln_b[n];
       }
-      out[(int64_t)r * N + n] = relu ? fmaxf(y, 0.f) : y;
+      y = relu ? fmaxf(y, 0.f) : y;
+      out[(int64_t)r * N + n] = y;
+      if (out16) out16[(int64_t)r * N + n] = __float2bfloat16_rn(y);
     }
   }
   if (save && threadIdx.x == 0) rstd[r] = rs;
@@ -511,10 +515,11 @@ dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_
 // Column partial sums per CTA (fixed order => deterministic): [0]=sum dz (dbias) [1]=sum dy*xhat (dgamma)
 // [2]=sum dy (dbeta).  Without LayerNorm: dz = dy, only [0] is meaningful.
 // Variant A: C <= 256, one warp per row.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
                         const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                        const float* __restrict__ act, int rows, int C, float* __restrict__ colpart) {
+                        const float* __restrict__ act, int rows, int C, float* __restrict__ colpart,
+                        __nv_bfloat16* __restrict__ dz16 = nullptr, const __nv_bfloat16* __restrict__ act16 = nullptr) {
   constexpr int MAXJ = 8;
   __shared__ float sm[8][3][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -544,7 +549,8 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
           sg += g;
           sgx += g * xh[j];
         } else {
-          dy[j] = act[idx] > 0.f ? dv : 0.f;
+          const float a = act16 ? __bfloat162float(act16[idx]) : act[idx];
+          dy[j] = a > 0.f ? dv : 0.f;
         }
       }
     }
@@ -560,6 +566,7 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
       if (n < C) {
         const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
         d[(int64_t)r * C + n] = dz;
+        if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
         c0[j] += dz;
         c1[j] += dy[j] * xh[j];
         c2[j] += dy[j];
@@ -583,10 +590,11 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
 }
 
 // Variant B: any C <= 2048 (dense layers), one CTA walks its rows, thread t owns columns t, t+256, ...
-__global__ void __launch_bounds__(kRowThreads)
+static __global__ void __launch_bounds__(kRowThreads)
 ln_relu_bwd_block_kernel(float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
                          const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                         const float* __restrict__ act, int rows, int C, float* __restrict__ colpart) {
+                         const float* __restrict__ act, int rows, int C, float* __restrict__ colpart,
+                         __nv_bfloat16* __restrict__ dz16 = nullptr, const __nv_bfloat16* __restrict__ act16 = nullptr) {
   __shared__ float red[kRowThreads / 32];
   float c0[kRowMaxPerThread], c1[kRowMaxPerThread], c2[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
 #pragma unroll
@@ -614,7 +622,8 @@ ln_relu_bwd_block_kernel(float* __restrict__ d, const float* __restrict__ xhat, 
           sg += g;
           sgx += g * xh[j];
         } else {
-          dy[j] = act[idx] > 0.f ? dv : 0.f;
+          const float a = act16 ? __bfloat162float(act16[idx]) : act[idx];
+          dy[j] = a > 0.f ? dv : 0.f;
         }
       }
     }
@@ -630,6 +639,7 @@ ln_relu_bwd_block_kernel(float* __restrict__ d, const float* __restrict__ xhat, 
       if (n < C) {
         const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
         d[(int64_t)r * C + n] = dz;
+        if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
         c0[j] += dz;
         c1[j] += dy[j] * xh[j];
         c2[j] += dy[j];
@@ -660,7 +670,7 @@ struct SegmentList {
   Segment s[kMaxSegments];
 };
 
-__global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
+static __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
   const Segment sg = list.s[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
     float t = 0.f;
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList 
 constexpr int kLossThreads = 256;
 constexpr int kMaxHeads = 64;
 
-__global__ void __launch_bounds__(kLossThreads)
+static __global__ void __launch_bounds__(kLossThreads)
 heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action,
                      const double* __restrict__ reward, const uint8_t* __restrict__ terminal, float gamma_n, int B,
                      int B_global, int K, int A, float* __restrict__ losses, float* __restrict__ dq,
@@ -729,7 +739,7 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
 // ------------------------------------------------------------------------------------------------- Adam
 // optax 0.2.4 scale_by_adam + scale(-lr): mu = b1 mu + (1-b1) g ; nu = b2 nu + (1-b2) g^2 ;
 // p -= lr * (mu / (1-b1^t)) / (sqrt(nu / (1-b2^t)) + eps) with t = *count (already incremented).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
             const int32_t* __restrict__ count, float lr, float b1, float b2, float eps, int64_t n4) {
   const int t = *count;
@@ -753,10 +763,10 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
-__global__ void count_inc_kernel(int32_t* count) { *count += 1; }
+static __global__ void count_inc_kernel(int32_t* count) { *count += 1; }
 
 // isdqn.py:111-125: one CTA per kernel row (+ one for the bias): row[j] = row[j + A] for j < K*A
-__global__ void __launch_bounds__(256) shift_heads_kernel(float* kernel, float* bias, int n_in, int K, int A) {
+static __global__ void __launch_bounds__(256) shift_heads_kernel(float* kernel, float* bias, int n_in, int K, int A) {
   float* row = blockIdx.x < n_in ? kernel + (int64_t)blockIdx.x * (1 + K) * A : bias;
   const int n = K * A;
   float v[4];
@@ -774,7 +784,7 @@ __global__ void __launch_bounds__(256) shift_heads_kernel(float* kernel, float* 
 }
 
 // isdqn.py:133-135: argmax over the actions of head 1+idx (first maximum, like jnp.argmax)
-__global__ void argmax_head_kernel(const float* __restrict__ q, int A, int head, int32_t* out) {
+static __global__ void argmax_head_kernel(const float* __restrict__ q, int A, int head, int32_t* out) {
   if (threadIdx.x == 0) {
     const float* h = q + head * A;
     int best = 0;

@@ -44,12 +44,12 @@ static inline int build_plan(const isdqn_net* net, Plan* p) {
   isdqn_layout& lay = p->layout;
   lay.n_leaves = 0;
   int64_t off = 0;
-  auto leaf = [&](int64_t size) {
+  auto leaf = [&](int64_t size) {  // leaves start on 8-element boundaries: 16-byte aligned in fp32 AND in the bf16 shadow
     const int64_t o = off;
     lay.offset[lay.n_leaves] = o;
     lay.size[lay.n_leaves] = size;
     lay.n_leaves++;
-    off = align4(off + size);
+    off = (off + size + 7) & ~(int64_t)7;
     return o;
   };
   int start = 0;

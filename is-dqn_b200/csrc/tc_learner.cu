@@ -1,0 +1,422 @@
+// bf16 tensor-core learner path (tcgen05 / TMEM): the conv torso and the hidden Dense layers of
+// iSDQN.learn_on_batch (slimdqn/networks/isdqn.py:82-103, architectures/dqn.py:55-103) as implicit GEMMs on the
+// 5th-generation tensor cores; the tiny head layer, the K-head TD loss, LayerNorm backward, the deterministic
+// reductions and Adam stay on the fp32 kernels of learner_kernels.cuh.  Tolerance of this path: 2e-2 (north_star).
+#include "learner_kernels.cuh"
+#include "plan.cuh"
+#include "tc_problems.cuh"
+
+using namespace isdqn;
+using isdqn::tc::bf16;
+
+extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu,
+                                       const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
+                                       void* stream);
+
+namespace isdqn {
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(tc::pack_bf16(v.x, v.y), tc::pack_bf16(v.z, v.w));
+  }
+}
+
+}  // namespace isdqn
+
+namespace {
+
+inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret_cast<float*>(ws) + off; }
+
+template <class P>
+int launch_tc(const P& p, dim3 grid, cudaStream_t s, const char* tag) {
+  constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  ISDQN_PROF(s, tag);
+  tc::tc_gemm_kernel<P><<<grid, tc::kThreads, smem, s>>>(p);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
+// D[M][N] (fp32, + split partials) = A B^T with the four operand-major combinations
+template <bool A_MN, bool B_MN>
+int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C, int64_t ldc, int64_t split_stride, int M,
+                   int N, int K, int splits, cudaStream_t s, const char* tag) {
+  const int total_chunks = ceil_div(K, tc::kBK);
+  const int cps = ceil_div(total_chunks, splits);
+  const int real_splits = ceil_div(total_chunks, cps);
+  const int bn = pick_bn(N);
+  dim3 grid(ceil_div(M, tc::kBM), ceil_div(N, bn), real_splits);
+#define ISDQN_GEMM_TC(BN)                                                      \
+  {                                                                            \
+    tc::GemmTC<BN, A_MN, B_MN> p;                                              \
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;          \
+    p.split_stride = split_stride; p.M = M; p.N = N; p.K = K;                  \
+    p.chunks_per_split = cps;                                                  \
+    return launch_tc(p, grid, s, tag);                                         \
+  }
+  switch (bn) {
+    case 32: ISDQN_GEMM_TC(32)
+    case 64: ISDQN_GEMM_TC(64)
+    case 128: ISDQN_GEMM_TC(128)
+    default: ISDQN_GEMM_TC(256)
+  }
+#undef ISDQN_GEMM_TC
+}
+
+// ---------------------------------------------------------------------------------------------- workspace
+struct TcWorkspace {
+  int64_t act16[ISDQN_MAX_FEATURES + 1];  // byte offsets; bf16 [rows*pix][out_dim] for every non-final layer
+  int64_t dz16[2];                        // bf16 ping-pong [B*pix][out_dim]
+  int64_t shadow16;                       // bf16 copy of the flat parameter vector
+  int64_t total;                          // bytes
+};
+
+void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    const int64_t o = off;
+    off = (off + bytes + 255) & ~(int64_t)255;
+    return o;
+  };
+  int64_t max_d = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const Layer& L = p.L[l];
+    w->act16[l] = l + 1 < p.n_layers ? take((int64_t)rows * L.pix * L.out_dim * 2) : -1;
+    const int64_t d = (int64_t)B * L.pix * L.out_dim * 2;
+    if (d > max_d) max_d = d;
+  }
+  w->dz16[0] = take(max_d > 0 ? max_d : 16);
+  w->dz16[1] = take(max_d > 0 ? max_d : 16);
+  w->shadow16 = take(p.layout.total * 2);
+  w->total = off;
+}
+
+inline bf16* w16(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(ws) + off); }
+
+bool tc_eligible(const Plan& p, const isdqn_net* net) {
+  if (net->arch != ISDQN_ARCH_CNN || p.n_layers < 5) return false;
+  for (int l = 0; l + 1 < p.n_layers; ++l) {
+    const Layer& L = p.L[l];
+    if (L.type == 0) {
+      if (!(L.out_dim == 32 || L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256)) return false;
+    } else {
+      if (L.in_dim % 8 || L.out_dim % 64 || L.out_dim > kRowThreads * kRowMaxPerThread) return false;
+    }
+  }
+  return true;
+}
+
+template <bool U8>
+int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0, int rows, const bf16* w, const float* params,
+                       bf16* out, float* xhat, float* rstd, int m_train, cudaStream_t s) {
+#define ISDQN_CONV_FWD_TC(BN)                                                                          \
+  {                                                                                                    \
+    tc::ConvFwdTC<BN, U8> p;                                                                           \
+    p.in0 = in0; p.in1 = in1; p.n_img0 = n0;                                                           \
+    p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;                \
+    p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
+    p.M = rows * L.pix; p.K = L.in_dim; p.w = w;                                                       \
+    p.bias = params + L.b_off;                                                                         \
+    p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
+    p.ln_b = L.has_ln ? params + L.beta_off : nullptr;                                                 \
+    p.relu = L.relu; p.out = out; p.xhat = xhat; p.rstd = rstd; p.m_train = m_train;                   \
+    return launch_tc(p, dim3(ceil_div(p.M, tc::kBM), 1, 1), s, "tc_conv_fwd");                         \
+  }
+  switch (L.out_dim) {
+    case 32: ISDQN_CONV_FWD_TC(32)
+    case 64: ISDQN_CONV_FWD_TC(64)
+    case 128: ISDQN_CONV_FWD_TC(128)
+    case 256: ISDQN_CONV_FWD_TC(256)
+    default: return ISDQN_E_UNSUPPORTED;
+  }
+#undef ISDQN_CONV_FWD_TC
+}
+
+template <bool U8>
+int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* part, int rows, int splits, int* real_splits,
+                         cudaStream_t s) {
+  const int total_chunks = ceil_div(rows, tc::kBK);
+  const int cps = ceil_div(total_chunks, splits);
+  *real_splits = ceil_div(total_chunks, cps);
+#define ISDQN_CONV_WGRAD_TC(BN)                                                                        \
+  {                                                                                                    \
+    tc::ConvWgradTC<BN, U8> p;                                                                         \
+    p.in = in; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;     \
+    p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
+    p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
+    return launch_tc(p, dim3(ceil_div(L.in_dim, tc::kBM), 1, *real_splits), s, "tc_conv_wgrad");       \
+  }
+  switch (L.out_dim) {
+    case 32: ISDQN_CONV_WGRAD_TC(32)
+    case 64: ISDQN_CONV_WGRAD_TC(64)
+    case 128: ISDQN_CONV_WGRAD_TC(128)
+    case 256: ISDQN_CONV_WGRAD_TC(256)
+    default: return ISDQN_E_UNSUPPORTED;
+  }
+#undef ISDQN_CONV_WGRAD_TC
+}
+
+int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s) {
+  const int taps = ceil_div(L.ksz, L.stride);
+  const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
+  const int bn = pick_bn(L.Cin);
+  dim3 grid(ceil_div(rows_max, tc::kBM), ceil_div(L.Cin, bn), L.stride * L.stride);
+#define ISDQN_CONV_DGRAD_TC(BN)                                                                        \
+  {                                                                                                    \
+    tc::ConvDgradTC<BN> p;                                                                             \
+    p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;                \
+    p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.n_img = B;             \
+    p.taps = taps; p.Kd = taps * taps * L.out_dim; p.dz = dz; p.w = w; p.dx = dx;                      \
+    return launch_tc(p, grid, s, "tc_conv_dgrad");                                                     \
+  }
+  switch (bn) {
+    case 32: ISDQN_CONV_DGRAD_TC(32)
+    case 64: ISDQN_CONV_DGRAD_TC(64)
+    case 128: ISDQN_CONV_DGRAD_TC(128)
+    default: ISDQN_CONV_DGRAD_TC(256)
+  }
+#undef ISDQN_CONV_DGRAD_TC
+}
+
+int launch_simt_gemm(const GemmArgs& g, cudaStream_t s, const char* tag) {
+  dim3 grid(ceil_div(g.M, 64), ceil_div(g.N, 64), 1);
+  ISDQN_PROF(s, tag);
+  const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
+  if (a_kfast && b_nfast) gemm_strided_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g);
+  else if (a_kfast) gemm_strided_kernel<true, false><<<grid, kGemmThreads, 0, s>>>(g);
+  else if (b_nfast) gemm_strided_kernel<false, true><<<grid, kGemmThreads, 0, s>>>(g);
+  else gemm_strided_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update, float* q_out,
+             void* stream) {
+  Plan p;
+  if (!net) return ISDQN_E_INVALID;
+  if (net->n_heads > kMaxHeads) return ISDQN_E_TOO_LARGE;
+  int rc = build_plan(net, &p);
+  if (rc) return rc;
+  if (!tc_eligible(p, net)) return ISDQN_E_UNSUPPORTED;
+  if (!tr || !b || !tr->d_params || !tr->d_losses || !tr->d_workspace || !tr->d_workspace_tc || tr->batch < 1 ||
+      tr->batch_global < tr->batch)
+    return ISDQN_E_INVALID;
+  if (!b->d_state || !b->d_next_state || !b->d_action || !b->d_reward || !b->d_terminal) return ISDQN_E_INVALID;
+  if (backward && !tr->d_grads) return ISDQN_E_INVALID;
+  if (update && (!tr->d_mu || !tr->d_nu || !tr->d_count)) return ISDQN_E_INVALID;
+  const int B = tr->batch, rows = 2 * B;
+  Workspace w;
+  carve_workspace(p, rows, B, &w);
+  TcWorkspace t;
+  carve_tc(p, rows, B, &t);
+  if (w.total * (int64_t)sizeof(float) > tr->workspace_bytes || t.total > tr->workspace_tc_bytes) return ISDQN_E_INVALID;
+  cudaStream_t s = as_stream(stream);
+  void* ws = tr->d_workspace;
+  void* wt = tr->d_workspace_tc;
+  const float* params = tr->d_params;
+  float* grads = tr->d_grads;
+  const int nl = p.n_layers;
+
+  // bf16 shadow of the parameters (the fp32 master copy stays the truth; Adam updates it)
+  bf16* shadow = w16(wt, t.shadow16);
+  {
+    const int64_t n4 = p.layout.total / 4;
+    int64_t grid = ceil_div<int64_t>(n4, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    ISDQN_PROF(s, "cast_params_bf16");
+    cast_f32_bf16_kernel<<<(unsigned)grid, 256, 0, s>>>(params, shadow, n4);
+    ISDQN_LAUNCH_CHECK();
+  }
+  // ------------------------------------------------------------------------------------------ forward
+  const int rows_train = backward ? B : 0;
+  for (int l = 0; l < nl; ++l) {
+    const Layer& L = p.L[l];
+    const float* ln_g = L.has_ln ? params + L.g_off : nullptr;
+    const float* ln_b = L.has_ln ? params + L.beta_off : nullptr;
+    float* xhat = rows_train > 0 ? wsp(ws, w.xhat[l]) : nullptr;
+    float* rstd = rows_train > 0 ? wsp(ws, w.rstd[l]) : nullptr;
+    if (L.type == 0) {
+      if (l == 0)
+        rc = launch_conv_fwd_tc<true>(L, b->d_state, b->d_next_state, B, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
+                                      xhat, rstd, rows_train * L.pix, s);
+      else
+        rc = launch_conv_fwd_tc<false>(L, w16(wt, t.act16[l - 1]), nullptr, rows, rows, shadow + L.w_off, params,
+                                       w16(wt, t.act16[l]), xhat, rstd, rows_train * L.pix, s);
+      if (rc) return rc;
+    } else if (l + 1 < nl) {  // hidden Dense: split-K tensor-core GEMM -> partials -> bias + LN + ReLU
+      const int splits = dense_fwd_splits(rows, L.out_dim, L.in_dim);
+      const int64_t split_stride = (int64_t)rows * L.out_dim;
+      const int total_chunks = ceil_div(L.in_dim, tc::kBK);
+      const int cps = ceil_div(total_chunks, splits);
+      const int real_splits = ceil_div(total_chunks, cps);
+      rc = launch_gemm_tc<false, true>(w16(wt, t.act16[l - 1]), L.in_dim, shadow + L.w_off, L.out_dim, wsp(ws, w.fwd_part),
+                                       L.out_dim, split_stride, rows, L.out_dim, L.in_dim, splits, s, "tc_dense_fwd");
+      if (rc) return rc;
+      ISDQN_PROF(s, "dense_finalize");
+      dense_finalize_kernel<<<rows, kRowThreads, 0, s>>>(wsp(ws, w.fwd_part), real_splits, split_stride, rows, L.out_dim,
+                                                         params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]), xhat, rstd,
+                                                         rows_train, w16(wt, t.act16[l]));
+      ISDQN_LAUNCH_CHECK();
+    } else {  // head layer: fp32 (N = (1+K)A is tiny and not 16-byte aligned)
+      GemmArgs g;
+      g.A = wsp(ws, w.act[l - 1]); g.sam = L.in_dim; g.sak = 1;
+      g.B = params + L.w_off; g.sbk = L.out_dim; g.sbn = 1;
+      g.C = wsp(ws, w.act[l]); g.ldc = L.out_dim; g.split_stride = 0;
+      g.M = rows; g.N = L.out_dim; g.K = L.in_dim; g.k_per_split = ceil_div(L.in_dim, kBK) * kBK;
+      g.bias = params + L.b_off;
+      rc = launch_simt_gemm(g, s, "head_fwd_gemm");
+      if (rc) return rc;
+    }
+  }
+  const float* q_all = wsp(ws, w.act[nl - 1]);
+  const Layer& last = p.L[nl - 1];
+  ISDQN_PROF(s, "heads_td_loss");
+  heads_td_loss_kernel<<<1, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
+                                                  tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
+                                                  backward ? wsp(ws, w.dq) : nullptr, backward ? grads + last.b_off : nullptr,
+                                                  update ? tr->d_count : nullptr);
+  ISDQN_LAUNCH_CHECK();
+  if (q_out)
+    ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * (size_t)rows * p.n_out, cudaMemcpyDeviceToDevice, s));
+  if (!backward) return ISDQN_OK;
+
+  // ----------------------------------------------------------------------------------------- backward
+  SegmentList segs;
+  segs.count = 0;
+  auto add_seg = [&](const float* src, float* dst, int64_t stride, int n, int parts) {
+    Segment& sg = segs.s[segs.count++];
+    sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts;
+  };
+  float* dz32 = wsp(ws, w.dq);
+  for (int l = nl - 1; l >= 0; --l) {
+    const Layer& L = p.L[l];
+    const bf16* dz16 = w16(wt, t.dz16[l & 1]);
+    const int rows_l = B * L.pix;
+    // ---- weight gradient
+    if (l == nl - 1) {
+      GemmArgs g;
+      g.A = wsp(ws, w.act[l - 1]); g.sam = 1; g.sak = L.in_dim;
+      g.B = dz32; g.sbk = L.out_dim; g.sbn = 1;
+      g.C = grads + L.w_off; g.ldc = L.out_dim; g.split_stride = 0;
+      g.M = L.in_dim; g.N = L.out_dim; g.K = B; g.k_per_split = ceil_div(B, kBK) * kBK; g.bias = nullptr;
+      rc = launch_simt_gemm(g, s, "head_wgrad_gemm");
+    } else if (L.type == 1) {
+      rc = launch_gemm_tc<true, true>(w16(wt, t.act16[l - 1]), L.in_dim, dz16, L.out_dim, grads + L.w_off, L.out_dim, 0,
+                                      L.in_dim, L.out_dim, B, 1, s, "tc_dense_wgrad");
+    } else {
+      int real_splits = 1;
+      float* part = wsp(ws, w.wpart[l]);
+      if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, s);
+      else rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits[l], &real_splits, s);
+      add_seg(part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
+    }
+    if (rc) return rc;
+    if (L.relu) {
+      const float* cp = wsp(ws, w.colpart[l]);
+      const int64_t st = 3 * (int64_t)L.out_dim;
+      add_seg(cp, grads + L.b_off, st, L.out_dim, w.col_ctas[l]);
+      if (L.has_ln) {
+        add_seg(cp + L.out_dim, grads + L.g_off, st, L.out_dim, w.col_ctas[l]);
+        add_seg(cp + 2 * L.out_dim, grads + L.beta_off, st, L.out_dim, w.col_ctas[l]);
+      }
+    }
+    if (l == 0) break;
+    // ---- input gradient, then the previous layer's ReLU + LayerNorm backward (fp32), which also emits bf16 dz
+    const Layer& P = p.L[l - 1];
+    float* dprev = wsp(ws, w.dbuf[l & 1]);
+    if (l == nl - 1) {
+      GemmArgs g;
+      g.A = dz32; g.sam = L.out_dim; g.sak = 1;
+      g.B = params + L.w_off; g.sbk = 1; g.sbn = L.out_dim;
+      g.C = dprev; g.ldc = L.in_dim; g.split_stride = 0;
+      g.M = B; g.N = L.in_dim; g.K = L.out_dim; g.k_per_split = ceil_div(L.out_dim, kBK) * kBK; g.bias = nullptr;
+      rc = launch_simt_gemm(g, s, "head_dgrad_gemm");
+    } else if (L.type == 1) {
+      rc = launch_gemm_tc<false, false>(dz16, L.out_dim, shadow + L.w_off, L.out_dim, dprev, L.in_dim, 0, B, L.in_dim,
+                                        L.out_dim, 1, s, "tc_dense_dgrad");
+    } else {
+      rc = launch_conv_dgrad_tc(L, dz16, shadow + L.w_off, dprev, B, s);
+    }
+    if (rc) return rc;
+    {
+      const int rows_p = B * P.pix;
+      const float* g_ = P.has_ln ? params + P.g_off : nullptr;
+      const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
+      bf16* dz16_prev = w16(wt, t.dz16[(l - 1) & 1]);
+      // the ReLU mask of a layer without LayerNorm needs its post-activation output: fp32 for Dense, bf16 for conv
+      ISDQN_PROF(s, "ln_relu_bwd");
+      if (ln_bwd_use_warp(P.out_dim)) {
+        ln_relu_bwd_warp_kernel<<<w.col_ctas[l - 1], 256, 0, s>>>(dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
+                                                                  P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p,
+                                                                  P.out_dim, wsp(ws, w.colpart[l - 1]), dz16_prev,
+                                                                  P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr);
+      } else {
+        ln_relu_bwd_block_kernel<<<w.col_ctas[l - 1], kRowThreads, 0, s>>>(
+            dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p,
+            P.out_dim, wsp(ws, w.colpart[l - 1]), dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr);
+      }
+      ISDQN_LAUNCH_CHECK();
+    }
+    dz32 = dprev;
+  }
+  if (segs.count > 0) {
+    int max_n = 0;
+    for (int i = 0; i < segs.count; ++i) max_n = segs.s[i].n > max_n ? segs.s[i].n : max_n;
+    int gx = ceil_div(max_n, 256);
+    if (gx > 64) gx = 64;
+    ISDQN_PROF(s, "reduce_segments");
+    reduce_segments_kernel<<<dim3(gx, segs.count), 256, 0, s>>>(segs);
+    ISDQN_LAUNCH_CHECK();
+  }
+  if (!update) return ISDQN_OK;
+  if (tr->nccl_comm) {
+    ISDQN_PROF(s, "nccl_allreduce");
+    rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, p.layout.total, stream);
+    if (rc) return rc;
+  }
+  return isdqn_adam_step_nocount(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
+                                 p.layout.total, stream);
+}
+
+}  // namespace
+
+// Entry used by the learner dispatch in learner.cu
+int isdqn_tc_train_dispatch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update,
+                            float* q_out, void* stream) {
+  return tc_train(net, tr, b, backward, update, q_out, stream);
+}
+
+extern "C" int64_t isdqn_learn_workspace_tc_bytes(const isdqn_net* net, int32_t batch) {
+  Plan p;
+  if (build_plan(net, &p) || batch < 1) return -1;
+  if (!tc_eligible(p, net)) return 0;
+  TcWorkspace t;
+  carve_tc(p, 2 * batch, batch, &t);
+  return t.total;
+}
+
+// Test / building-block entry: D[M][N] (fp32) = A B^T on the tensor cores, bf16 operands.
+//   a_mn_major = 0: A is [M][lda] (K contiguous);  1: A is [K][lda] (M contiguous)
+//   b_mn_major = 0: B is [N][ldb] (K contiguous);  1: B is [K][ldb] (N contiguous)
+// splits > 1 writes `splits` partial products at d_c + z*M*N (the caller reduces them).
+extern "C" int isdqn_tc_gemm_bf16(const void* d_a, int64_t lda, int32_t a_mn_major, const void* d_b, int64_t ldb,
+                                  int32_t b_mn_major, float* d_c, int32_t M, int32_t N, int32_t K, int32_t splits,
+                                  void* stream) {
+  if (!d_a || !d_b || !d_c || M < 1 || N < 1 || K < 1 || splits < 1) return ISDQN_E_INVALID;
+  if ((lda % 8) || (ldb % 8) || (N % 8)) return ISDQN_E_INVALID;  // 16-byte cp.async granularity
+  const bf16* A = reinterpret_cast<const bf16*>(d_a);
+  const bf16* B = reinterpret_cast<const bf16*>(d_b);
+  cudaStream_t s = as_stream(stream);
+  const int64_t ss = (int64_t)M * N;
+  if (a_mn_major && b_mn_major) return launch_gemm_tc<true, true>(A, lda, B, ldb, d_c, N, ss, M, N, K, splits, s, "tc_gemm");
+  if (a_mn_major) return launch_gemm_tc<true, false>(A, lda, B, ldb, d_c, N, ss, M, N, K, splits, s, "tc_gemm");
+  if (b_mn_major) return launch_gemm_tc<false, true>(A, lda, B, ldb, d_c, N, ss, M, N, K, splits, s, "tc_gemm");
+  return launch_gemm_tc<false, false>(A, lda, B, ldb, d_c, N, ss, M, N, K, splits, s, "tc_gemm");
+}

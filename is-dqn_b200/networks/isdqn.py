@@ -43,6 +43,7 @@ class iSDQN:
         target_update_frequency: int,
         adam_eps: float = 1e-8,
         use_cuda_graph: bool = True,
+        compute_dtype: str = "float32",
     ):
         torch = _lib.require_cuda()
         self._torch = torch
@@ -82,6 +83,11 @@ class iSDQN:
         self._d_cumulated = torch.zeros(self.n_bellman_iterations, dtype=torch.float64, device="cuda")
 
         self._use_graph = bool(use_cuda_graph)
+        # "float32": CUDA-core FFMA path (1e-5 parity); "bfloat16": tcgen05 tensor-core path for the conv torso and
+        # the hidden Dense layers, fp32 accumulation / master weights / Adam (2e-2 parity, north_star)
+        if compute_dtype not in ("float32", "bfloat16"):
+            raise ValueError(f"compute_dtype must be 'float32' or 'bfloat16', got {compute_dtype!r}")
+        self.compute_dtype = compute_dtype
         self._ctx = {}  # batch size -> persistent buffers + captured graph
         self._nccl_comm = None
         self._dp_world = 1
@@ -128,6 +134,15 @@ class iSDQN:
         if nbytes < 0:
             raise _lib.IsdqnNativeError("isdqn_learn_workspace_bytes failed")
         ctx["ws"] = t.empty(max(nbytes, 16), dtype=t.uint8, device="cuda")
+        ctx["ws_tc"] = None
+        if self.compute_dtype == "bfloat16":
+            nb = self._lib.isdqn_learn_workspace_tc_bytes(net._net, B)
+            if nb <= 0:
+                raise _lib.IsdqnNativeError(
+                    "compute_dtype='bfloat16' needs a cnn with 32/64/128/256-channel convolutions and hidden Dense "
+                    "widths that are multiples of 64; use compute_dtype='float32' for this network"
+                )
+            ctx["ws_tc"] = t.empty(nb, dtype=t.uint8, device="cuda")
         # pinned staging for host batches (the reference's implicit device_put at the jit boundary)
         ctx["h_state"] = t.zeros(shape, dtype=dt).pin_memory()
         ctx["h_next_state"] = t.zeros(shape, dtype=dt).pin_memory()
@@ -166,6 +181,10 @@ class iSDQN:
         tr.d_workspace = ctx["ws"].data_ptr()
         tr.workspace_bytes = ctx["ws"].numel()
         tr.nccl_comm = self._nccl_comm
+        tr.compute_dtype = _lib.COMPUTE_BF16 if self.compute_dtype == "bfloat16" else _lib.COMPUTE_F32
+        if ctx["ws_tc"] is not None:
+            tr.d_workspace_tc = ctx["ws_tc"].data_ptr()
+            tr.workspace_tc_bytes = ctx["ws_tc"].numel()
         return tr
 
     def _load_batch(self, ctx, batch) -> int:
