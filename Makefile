@@ -4,7 +4,7 @@ PKG := is-dqn_b200
 SRCS := $(wildcard $(PKG)/csrc/*.cu)
 OBJS := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(SRCS))
 HDRS := $(wildcard $(PKG)/csrc/*.cuh) include/isdqn_b200.h
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+NVCCFLAGS := $(EXTRA) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
 LIB := $(PKG)/lib/libisdqn_b200.so
 
 all: $(LIB)

@@ -185,6 +185,18 @@ def kernel_work(name: str, P: int):
         return "hbm", 4 * 7744 * 512 + 4 * B * (7744 + 512)
     if name == "dense_fwd_gemm":
         return "hbm", 4 * 7744 * 512 + 4 * 2 * B * (7744 + 512)
+    if name == "cast_params_bf16":
+        return "hbm", 6 * P
+    if name == "tc_dense_wgrad":
+        return "hbm", 4 * 7744 * 512 + 2 * B * (7744 + 512)
+    if name in ("tc_dense_dgrad", "tc_dense_fwd"):
+        return "hbm", 2 * 7744 * 512 + 2 * 2 * B * (7744 + 512)
+    if name == "tc_conv_fwd":  # three launches: torso forward on 2B images
+        return "tensor", 2 * B * 24_076_288
+    if name == "tc_conv_wgrad":
+        return "tensor", B * 24_076_288
+    if name == "tc_conv_dgrad":
+        return "tensor", B * (24_076_288 - 2 * 441 * 256 * 32)
     return None, 0
 
 
@@ -210,7 +222,8 @@ def run_ours(args, rank, world, local_rank):
     for obs, a, r, d in synthetic_stream(1000 + rank, n_fill):
         rb.add(TransitionElement(obs, a, r, d, d))
     t_fill = time.perf_counter() - t_fill
-    agent = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "cnn", LR, GAMMA, 1, 1, 8000, adam_eps=ADAM_EPS)
+    agent = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "cnn", LR, GAMMA, 1, 1, 8000, adam_eps=ADAM_EPS,
+                  compute_dtype="bfloat16" if args.dtype == "bf16" else "float32")
     P = agent.network.n_params
     stream = torch.cuda.Stream()
     peaks = measured_peaks()
@@ -294,8 +307,12 @@ def run_ours(args, rank, world, local_rank):
     value = world * args.steps / (ms / 1e3)
     e2e = world * args.steps / (ms_e2e / 1e3)
     roofline = None
-    if kind == "hbm":
-        ach = work * dom_count / (dom_ms / 1e3) / 1e9 / max(dom_count, 1) * 1.0
+    if kind == "tensor":
+        ach = (work / 1e12) / (dom_ms / 1e3)  # `work` covers all launches of that name in one step
+        roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tflops_burst"], "traffic": None, "peak_src": peaks["src"],
+                    "share_of_step": dom_ms / step_prof_ms, "launches_per_step": dom_count}
+    elif kind == "hbm":
         ach = (work / 1e9) / ((dom_ms / dom_count) / 1e3)
         roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
@@ -311,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "iS-DQN K=9 learner updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(cap),
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -340,6 +357,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--capacity", type=int, default=int(os.environ.get("ISDQN_BENCH_CAPACITY", 1_000_000)))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"],
+                    help="bf16: tcgen05 tensor-core path (fp32 accumulate/master weights); f32: CUDA-core fp32 parity path")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -204,12 +204,18 @@ typedef struct isdqn_train {
   void* nccl_comm;          /* NULL, or the handle from isdqn_dp_init: gradients are all-reduced before Adam */
   int32_t compute_dtype;    /* ISDQN_COMPUTE_F32 (CUDA-core fp32, 1e-5 parity) or ISDQN_COMPUTE_BF16 (tcgen05, 2e-2) */
   void* d_workspace_tc; int64_t workspace_tc_bytes; /* bf16 path only: isdqn_learn_workspace_tc_bytes() */
+  void* d_params_bf16;      /* bf16 path only: bf16 shadow of d_params (layout.total elements).  Adam keeps it current;  */
+  int32_t refresh_shadow;   /* set to 1 to rebuild it from d_params at the start of the call (parameters were changed     */
+                            /* outside isdqn_learn_on_batch since the last call)                                          */
 } isdqn_train;
 #define ISDQN_COMPUTE_F32 0
 #define ISDQN_COMPUTE_BF16 1
 /* bytes of bf16 scratch the tensor-core path needs (0 if the network is not eligible: cnn with 32/64/128/256
  * channel convs and hidden Dense widths that are multiples of 64) */
 int64_t isdqn_learn_workspace_tc_bytes(const isdqn_net* net, int32_t batch);
+
+/* fp32 -> bf16 (round to nearest even) of n elements, n % 4 == 0: builds the parameter shadow */
+int isdqn_cast_f32_to_bf16(const float* d_src, void* d_dst_bf16, int64_t n, void* stream);
 
 /* Building block / test entry of the tcgen05 tile engine: D[M][N] (fp32) = A B^T, bf16 operands.
  *   a_mn_major = 0: A is [M][lda] (K contiguous); 1: A is [K][lda] (M contiguous); likewise B with N.

@@ -88,6 +88,8 @@ class Train(C.Structure):
         ("compute_dtype", C.c_int32),
         ("d_workspace_tc", C.c_void_p),
         ("workspace_tc_bytes", C.c_int64),
+        ("d_params_bf16", C.c_void_p),
+        ("refresh_shadow", C.c_int32),
     ]
 
 
@@ -116,6 +118,7 @@ PROTOTYPES = {
     "isdqn_forward_workspace_bytes": (_I64, [C.POINTER(Net), _I32]),
     "isdqn_learn_workspace_bytes": (_I64, [C.POINTER(Net), _I32]),
     "isdqn_learn_workspace_tc_bytes": (_I64, [C.POINTER(Net), _I32]),
+    "isdqn_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
     "isdqn_tc_gemm_bf16": (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I32, _I32, _I32, _I32, _P]),
     "isdqn_forward": (C.c_int, [C.POINTER(Net), _P, _P, _I32, _I32, _P, _P, _I64, _P]),
     "isdqn_heads_td_loss": (C.c_int, [_P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P, _P]),

@@ -92,6 +92,13 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
       const int splits = dense_fwd_splits(rows, L.out_dim, L.in_dim);
       const int kps = ceil_div(ceil_div(L.in_dim, splits), kBK) * kBK;
       const int real_splits = ceil_div(L.in_dim, kps);
+      if (!first && !L.has_ln && !L.relu && L.out_dim <= 128 && L.in_dim <= 8192) {  // the head layer
+        ISDQN_PROF(s, "head_fwd");
+        head_fwd_kernel<<<rows, 512, L.in_dim * sizeof(float), s>>>(wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
+                                                                  L.in_dim, L.out_dim, out);
+        ISDQN_LAUNCH_CHECK();
+        continue;
+      }
       const bool direct = real_splits == 1 && !L.has_ln && !L.relu;
       float* part = direct ? out : wsp(ws, w.fwd_part);
       const int64_t split_stride = (int64_t)rows * L.out_dim;
@@ -128,14 +135,14 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
 
 int check_common(const isdqn_net* net, Plan* p) {
   if (!net) return ISDQN_E_INVALID;
-  if (net->n_heads > kMaxHeads) return ISDQN_E_TOO_LARGE;
+  if (net->n_heads > kMaxHeads || net->n_actions > kMaxActions) return ISDQN_E_TOO_LARGE;
   return build_plan(net, p);
 }
 
 int run_loss(const Plan& p, const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, const float* q_all,
              float* dq, float* dbias, int32_t* count, cudaStream_t s) {
   ISDQN_PROF(s, "heads_td_loss");
-  heads_td_loss_kernel<<<1, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n,
+  heads_td_loss_kernel<<<net->n_heads, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n,
                                                   tr->batch, tr->batch_global, net->n_heads, net->n_actions,
                                                   tr->d_losses, dq, dbias, count);
   ISDQN_LAUNCH_CHECK();
@@ -347,27 +354,34 @@ extern "C" int isdqn_heads_td_loss(const float* d_q_all, const int64_t* d_action
   if (!d_q_all || !d_action || !d_reward || !d_terminal || !d_losses || batch < 1 || batch_global < batch ||
       n_heads < 1 || n_actions < 1)
     return ISDQN_E_INVALID;
-  if (n_heads > kMaxHeads) return ISDQN_E_TOO_LARGE;
-  heads_td_loss_kernel<<<1, kLossThreads, 0, as_stream(stream)>>>(d_q_all, d_action, d_reward, d_terminal, gamma_n, batch,
+  if (n_heads > kMaxHeads || n_actions > kMaxActions) return ISDQN_E_TOO_LARGE;
+  heads_td_loss_kernel<<<n_heads, kLossThreads, 0, as_stream(stream)>>>(d_q_all, d_action, d_reward, d_terminal, gamma_n, batch,
                                                                   batch_global, n_heads, n_actions, d_losses, d_dq,
                                                                   nullptr, nullptr);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
 
-// Adam over the flat vector; *d_count must already hold the step number t >= 1.
-extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu,
-                                       const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
-                                       void* stream) {
+// Adam over the flat vector; *d_count must already hold the step number t >= 1.  `shadow` (optional): bf16 copy of
+// the updated parameters, written in the same pass.
+int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
+                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream) {
   if (!d_params || !d_grads || !d_mu || !d_nu || !d_count || n < 0 || (n & 3)) return ISDQN_E_INVALID;
   if (n == 0) return ISDQN_OK;
   const int64_t n4 = n / 4;
   int64_t grid = ceil_div<int64_t>(n4, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   ISDQN_PROF(as_stream(stream), "adam");
-  adam_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n4);
+  adam_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n4,
+                                                             reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
+}
+
+extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu,
+                                       const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
+                                       void* stream) {
+  return isdqn_adam_launch(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n, nullptr, stream);
 }
 
 extern "C" int isdqn_adam_step(float* d_params, const float* d_grads, float* d_mu, float* d_nu, int32_t* d_count,

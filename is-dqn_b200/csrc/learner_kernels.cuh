@@ -670,70 +670,122 @@ struct SegmentList {
   Segment s[kMaxSegments];
 };
 
+// One CTA sums a tile of 32 elements: its 8 warps take the partials p = w, w+8, ... (32 independent loads in
+// flight per warp), then the 8 warp sums are combined in a fixed order => deterministic, and short segments
+// with many partials (LayerNorm/bias column sums: 32-64 elements x ~200 partials) are no longer one serial chain.
 static __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
+  __shared__ float sm[8][33];
   const Segment sg = list.s[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_tiles = (sg.n + 31) / 32;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int i = tile * 32 + lane;
     float t = 0.f;
-    for (int p = 0; p < sg.parts; ++p) t += sg.src[(int64_t)p * sg.stride + i];
-    sg.dst[i] = t;
+    if (i < sg.n)
+      for (int p = w; p < sg.parts; p += 8) t += sg.src[(int64_t)p * sg.stride + i];
+    sm[w][lane] = t;
+    __syncthreads();
+    if (w == 0 && i < sg.n) {
+      float tot = sm[0][lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) tot += sm[k][lane];
+      sg.dst[i] = tot;
+    }
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------ K-head TD loss fwd + bwd
-// isdqn.py:97-109.  Single CTA, fixed reduction order.  Also: bumps the Adam step counter (so the following
-// adam_kernel of the same step reads count+1 with no race) and produces the bias gradient of the head layer.
+// isdqn.py:97-109.  One CTA per online head k+1 (regressing onto head k), fixed reduction order => deterministic.
+// CTA 0 also bumps the Adam step counter (so the adam_kernel of the same step reads count+1 with no race); every
+// CTA produces its head's slice of d(loss)/dq and of the head layer's bias gradient.
 constexpr int kLossThreads = 256;
 constexpr int kMaxHeads = 64;
+constexpr int kMaxActions = 32;
 
 static __global__ void __launch_bounds__(kLossThreads)
 heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action,
                      const double* __restrict__ reward, const uint8_t* __restrict__ terminal, float gamma_n, int B,
                      int B_global, int K, int A, float* __restrict__ losses, float* __restrict__ dq,
                      float* __restrict__ dbias, int32_t* count) {
-  __shared__ float red[kLossThreads / 32][kMaxHeads];
+  __shared__ float red[kLossThreads / 32];
+  __shared__ float dbw[kLossThreads / 32][kMaxActions];
+  const int k = blockIdx.x;
   const int n_out = (1 + K) * A;
-  const int tid = threadIdx.x;
-  if (dq)
-    for (int i = tid; i < B * n_out; i += kLossThreads) dq[i] = 0.f;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (dq) {  // d(loss)/dq is zero except at (b, head k+1, a_b); head 0 receives no gradient at all
+    for (int i = tid; i < B * A; i += kLossThreads) {
+      const int b = i / A, a = i - b * A;
+      dq[(int64_t)b * n_out + (k + 1) * A + a] = 0.f;
+      if (k == 0) dq[(int64_t)b * n_out + a] = 0.f;
+    }
+  }
+  if (tid < kMaxActions)
+    for (int w = 0; w < kLossThreads / 32; ++w) dbw[w][tid] = 0.f;
   __syncthreads();
-  float part[kMaxHeads];
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) part[k] = 0.f;
   const float inv_b = 1.0f / (float)B_global;
-  for (int b = tid; b < B; b += kLossThreads) {
-    const int a = (int)action[b];
-    const float r = (float)reward[b];                       // f64 -> f32 at the jit boundary
-    const float coef = (float)(1 - (int)terminal[b]) * gamma_n;  // ((1 - d) * gamma^n) in fp32
-    const float* qs = q_all + (int64_t)b * n_out;           // Q(s, .)
-    const float* qn = q_all + (int64_t)(B + b) * n_out;     // Q(s', .)
-    for (int k = 0; k < K; ++k) {
-      float mx = qn[k * A];
-      for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[k * A + j]);
-      const float target = r + coef * mx;  // head k+1 regresses onto head k
-      const float td = qs[(k + 1) * A + a] - target;
-      part[k] += td * td;
-      if (dq) dq[(int64_t)b * n_out + (k + 1) * A + a] = 2.0f * td * inv_b;
+  float part = 0.f;
+  for (int b0 = 0; b0 < B; b0 += kLossThreads) {
+    const int b = b0 + tid;
+    float val = 0.f;
+    int a = -1;
+    if (b < B) {
+      a = (int)action[b];
+      const float r = (float)reward[b];                             // f64 -> f32 at the jit boundary
+      const float coef = (float)(1 - (int)terminal[b]) * gamma_n;   // ((1 - d) * gamma^n) in fp32
+      const float* qn = q_all + (int64_t)(B + b) * n_out + k * A;   // Q_k(s', .)
+      float mx = qn[0];
+      for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
+      const float target = r + coef * mx;
+      const float td = q_all[(int64_t)b * n_out + (k + 1) * A + a] - target;
+      part += td * td;
+      val = 2.0f * td * inv_b;
+      if (dq) dq[(int64_t)b * n_out + (k + 1) * A + a] = val;
+    }
+    if (dbias) {
+      for (int j = 0; j < A; ++j) {
+        const float sj = warp_sum(a == j ? val : 0.f);
+        if (lane == 0) dbw[warp][j] += sj;
+      }
     }
   }
-  for (int k = 0; k < K; ++k) {
-    const float v = warp_sum(part[k]);
-    if ((tid & 31) == 0) red[tid >> 5][k] = v;
-  }
+  part = warp_sum(part);
+  if (lane == 0) red[warp] = part;
   __syncthreads();
-  if (tid < K) {
+  if (tid == 0) {
     float t = 0.f;
-    for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][tid];
-    losses[tid] = t * inv_b;
+    for (int w = 0; w < kLossThreads / 32; ++w) t += red[w];
+    losses[k] = t * inv_b;
   }
-  if (dbias && dq) {
-    __syncthreads();
-    for (int n = tid; n < n_out; n += kLossThreads) {
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) t += dq[(int64_t)b * n_out + n];
-      dbias[n] = t;
-    }
+  if (dbias && tid < A) {
+    float t = 0.f;
+    for (int w = 0; w < kLossThreads / 32; ++w) t += dbw[w][tid];
+    dbias[(k + 1) * A + tid] = t;
+    if (k == 0) dbias[tid] = 0.f;
   }
-  if (count && tid == 0) *count += 1;
+  if (count && k == 0 && tid == 0) *count += 1;
+}
+
+// Head layer forward (tiny: N = (1+K)A <= 128 columns): one CTA per row, 4 k-groups x 128 columns.
+static __global__ void __launch_bounds__(512)
+head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int K, int N,
+                float* __restrict__ out) {
+  extern __shared__ float xs[];  // [K]
+  __shared__ float part[4][128];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < K; k += 512) xs[k] = x[(int64_t)r * K + k];
+  __syncthreads();
+  const int n = tid & 127, g = tid >> 7;
+  float acc = 0.f;
+  if (n < N) {
+    const int kq = (K + 3) / 4;
+    const int k_end = min(K, (g + 1) * kq);
+#pragma unroll 8
+    for (int k = g * kq; k < k_end; ++k) acc = fmaf(xs[k], __ldg(w + (int64_t)k * N + n), acc);
+  }
+  part[g][n] = acc;
+  __syncthreads();
+  if (g == 0 && n < N) out[(int64_t)r * N + n] = ((part[0][n] + part[1][n]) + (part[2][n] + part[3][n])) + bias[n];
 }
 
 // ------------------------------------------------------------------------------------------------- Adam
@@ -741,7 +793,8 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
 // p -= lr * (mu / (1-b1^t)) / (sqrt(nu / (1-b2^t)) + eps) with t = *count (already incremented).
 static __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
-            const int32_t* __restrict__ count, float lr, float b1, float b2, float eps, int64_t n4) {
+            const int32_t* __restrict__ count, float lr, float b1, float b2, float eps, int64_t n4,
+            __nv_bfloat16* __restrict__ shadow) {
   const int t = *count;
   const float c1 = (float)(1.0 - pow((double)b1, (double)t));
   const float c2 = (float)(1.0 - pow((double)b2, (double)t));
@@ -760,6 +813,10 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     reinterpret_cast<float4*>(mu)[i] = mv;
     reinterpret_cast<float4*>(nu)[i] = vv;
     reinterpret_cast<float4*>(p)[i] = pv;
+    if (shadow) {  // bf16 copy of the updated parameters for the tensor-core path of the next step
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
   }
 }
 

@@ -9,8 +9,8 @@
 
 namespace isdqn {
 
-constexpr int kUniformThreads = 1024;
-
+// THREADS candidates are examined per round; a batch of 32 uses the 128-thread instantiation (one short scan)
+template <int kUniformThreads>
 __global__ void __launch_bounds__(kUniformThreads)
 sample_uniform_kernel(uint64_t* rng, uint32_t n_valid, int size, const int32_t* __restrict__ index_to_key,
                       int capacity, int32_t* __restrict__ out_index, int32_t* __restrict__ out_key,
@@ -138,8 +138,12 @@ extern "C" int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t si
   if (size > (1 << 20)) return ISDQN_E_TOO_LARGE;
   if (size == 0) return ISDQN_OK;
   ISDQN_PROF(as_stream(stream), "sample_uniform");
-  sample_uniform_kernel<<<1, kUniformThreads, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key,
-                                                                      capacity, d_out_index, d_out_key, d_out_slot);
+  if (size <= 96)
+    sample_uniform_kernel<128><<<1, 128, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key, capacity,
+                                                                 d_out_index, d_out_key, d_out_slot);
+  else
+    sample_uniform_kernel<1024><<<1, 1024, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key, capacity,
+                                                                   d_out_index, d_out_key, d_out_slot);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

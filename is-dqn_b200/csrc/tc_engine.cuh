@@ -139,7 +139,8 @@ constexpr size_t smem_bytes() {
 
 // P (the problem) provides:
 //   static constexpr int BN, STAGES; static constexpr bool A_MN, B_MN;
-//   struct Ctx;  __device__ void init(Ctx&, int m0, int n0, int tid) const;
+//   static constexpr int EXTRA_BYTES (shared scratch for lookup tables);
+//   struct Ctx;  __device__ void init(Ctx&, uint8_t* extra, int m0, int n0, int tid) const;   (a __syncthreads follows)
 //   __device__ void k_range(int split, int& kc_begin, int& kc_end) const;      (in units of 64-element chunks)
 //   __device__ void load_a(const Ctx&, uint32_t stage_smem, int kc, int tid) const;   load_b(...)
 //   __device__ void epilogue(const Ctx&, uint32_t tmem_lane_base, bool has_acc, int m0, int n0, int tid, int split) const;
@@ -173,8 +174,10 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const P p) {
   tcgen05_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
 
+  __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
   typename P::Ctx ctx;
-  p.init(ctx, m0, n0, tid);
+  p.init(ctx, extra_sm, m0, n0, tid);
+  __syncthreads();
   int kc_begin, kc_end;
   p.k_range(split, kc_begin, kc_end);
   const int nk = kc_end - kc_begin;

@@ -9,9 +9,8 @@
 using namespace isdqn;
 using isdqn::tc::bf16;
 
-extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu,
-                                       const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
-                                       void* stream);
+int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
+                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream);
 
 namespace isdqn {
 
@@ -43,6 +42,12 @@ int launch_tc(const P& p, dim3 grid, cudaStream_t s, const char* tag) {
 }
 
 int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+// widest N tile that still gives the grid about one CTA per SM (batch-32 shapes are latency bound: parallelism first)
+int pick_bn_parallel(int n, int other_ctas) {
+  int bn = pick_bn(n);
+  while (bn > 32 && other_ctas * ceil_div(n, bn) < 120) bn >>= 1;
+  return bn;
+}
 
 // D[M][N] (fp32, + split partials) = A B^T with the four operand-major combinations
 template <bool A_MN, bool B_MN>
@@ -51,7 +56,7 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
   const int total_chunks = ceil_div(K, tc::kBK);
   const int cps = ceil_div(total_chunks, splits);
   const int real_splits = ceil_div(total_chunks, cps);
-  const int bn = pick_bn(N);
+  const int bn = pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
   dim3 grid(ceil_div(M, tc::kBM), ceil_div(N, bn), real_splits);
 #define ISDQN_GEMM_TC(BN)                                                      \
   {                                                                            \
@@ -74,7 +79,6 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
 struct TcWorkspace {
   int64_t act16[ISDQN_MAX_FEATURES + 1];  // byte offsets; bf16 [rows*pix][out_dim] for every non-final layer
   int64_t dz16[2];                        // bf16 ping-pong [B*pix][out_dim]
-  int64_t shadow16;                       // bf16 copy of the flat parameter vector
   int64_t total;                          // bytes
 };
 
@@ -94,7 +98,6 @@ void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
   }
   w->dz16[0] = take(max_d > 0 ? max_d : 16);
   w->dz16[1] = take(max_d > 0 ? max_d : 16);
-  w->shadow16 = take(p.layout.total * 2);
   w->total = off;
 }
 
@@ -102,10 +105,13 @@ inline bf16* w16(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret
 
 bool tc_eligible(const Plan& p, const isdqn_net* net) {
   if (net->arch != ISDQN_ARCH_CNN || p.n_layers < 5) return false;
+  if (net->obs_c != 4) return false;  // the uint8 gather of the first conv packs two 4-channel taps per 16-byte chunk
   for (int l = 0; l + 1 < p.n_layers; ++l) {
     const Layer& L = p.L[l];
     if (L.type == 0) {
       if (!(L.out_dim == 32 || L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256)) return false;
+      const int taps = ceil_div(L.ksz, L.stride);
+      if (L.in_dim > 8 * tc::kMaxChunks - 64 || taps * taps * L.out_dim > 8 * tc::kMaxChunks - 64) return false;
     } else {
       if (L.in_dim % 8 || L.out_dim % 64 || L.out_dim > kRowThreads * kRowMaxPerThread) return false;
     }
@@ -201,11 +207,11 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
              void* stream) {
   Plan p;
   if (!net) return ISDQN_E_INVALID;
-  if (net->n_heads > kMaxHeads) return ISDQN_E_TOO_LARGE;
+  if (net->n_heads > kMaxHeads || net->n_actions > kMaxActions) return ISDQN_E_TOO_LARGE;
   int rc = build_plan(net, &p);
   if (rc) return rc;
   if (!tc_eligible(p, net)) return ISDQN_E_UNSUPPORTED;
-  if (!tr || !b || !tr->d_params || !tr->d_losses || !tr->d_workspace || !tr->d_workspace_tc || tr->batch < 1 ||
+  if (!tr || !b || !tr->d_params || !tr->d_losses || !tr->d_workspace || !tr->d_workspace_tc || !tr->d_params_bf16 || tr->batch < 1 ||
       tr->batch_global < tr->batch)
     return ISDQN_E_INVALID;
   if (!b->d_state || !b->d_next_state || !b->d_action || !b->d_reward || !b->d_terminal) return ISDQN_E_INVALID;
@@ -225,8 +231,8 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   const int nl = p.n_layers;
 
   // bf16 shadow of the parameters (the fp32 master copy stays the truth; Adam updates it)
-  bf16* shadow = w16(wt, t.shadow16);
-  {
+  bf16* shadow = reinterpret_cast<bf16*>(tr->d_params_bf16);
+  if (tr->refresh_shadow) {
     const int64_t n4 = p.layout.total / 4;
     int64_t grid = ceil_div<int64_t>(n4, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
@@ -264,7 +270,12 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
                                                          params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]), xhat, rstd,
                                                          rows_train, w16(wt, t.act16[l]));
       ISDQN_LAUNCH_CHECK();
-    } else {  // head layer: fp32 (N = (1+K)A is tiny and not 16-byte aligned)
+    } else if (L.out_dim <= 128 && L.in_dim <= 8192) {  // head layer: fp32 (N = (1+K)A is tiny, not 16-byte aligned)
+      ISDQN_PROF(s, "head_fwd");
+      head_fwd_kernel<<<rows, 512, L.in_dim * sizeof(float), s>>>(wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
+                                                                L.in_dim, L.out_dim, wsp(ws, w.act[l]));
+      ISDQN_LAUNCH_CHECK();
+    } else {
       GemmArgs g;
       g.A = wsp(ws, w.act[l - 1]); g.sam = L.in_dim; g.sak = 1;
       g.B = params + L.w_off; g.sbk = L.out_dim; g.sbn = 1;
@@ -278,7 +289,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   const float* q_all = wsp(ws, w.act[nl - 1]);
   const Layer& last = p.L[nl - 1];
   ISDQN_PROF(s, "heads_td_loss");
-  heads_td_loss_kernel<<<1, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
+  heads_td_loss_kernel<<<net->n_heads, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
                                                   tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
                                                   backward ? wsp(ws, w.dq) : nullptr, backward ? grads + last.b_off : nullptr,
                                                   update ? tr->d_count : nullptr);
@@ -381,8 +392,8 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, p.layout.total, stream);
     if (rc) return rc;
   }
-  return isdqn_adam_step_nocount(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
-                                 p.layout.total, stream);
+  return isdqn_adam_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
+                           p.layout.total, shadow, stream);
 }
 
 }  // namespace
@@ -400,6 +411,18 @@ extern "C" int64_t isdqn_learn_workspace_tc_bytes(const isdqn_net* net, int32_t 
   TcWorkspace t;
   carve_tc(p, 2 * batch, batch, &t);
   return t.total;
+}
+
+extern "C" int isdqn_cast_f32_to_bf16(const float* d_src, void* d_dst_bf16, int64_t n, void* stream) {
+  if (!d_src || !d_dst_bf16 || n < 0 || (n & 3)) return ISDQN_E_INVALID;
+  if (n == 0) return ISDQN_OK;
+  const int64_t n4 = n / 4;
+  int64_t grid = ceil_div<int64_t>(n4, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  ISDQN_PROF(as_stream(stream), "cast_params_bf16");
+  cast_f32_bf16_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(d_src, reinterpret_cast<bf16*>(d_dst_bf16), n4);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
 }
 
 // Test / building-block entry: D[M][N] (fp32) = A B^T on the tensor cores, bf16 operands.

@@ -55,12 +55,16 @@ class _LeafDict(dict):
     """Module dict whose item assignment writes INTO the flat-vector view instead of rebinding it, so
     `params["params"]["Dense_1"]["bias"] = new_value` (tests/test_isdqn.py:102) reaches the kernels."""
 
+    owner = None  # the ParamTree whose flat vector the views alias
+
     def __setitem__(self, key, value):
         if key in self:
             import torch
 
             view = dict.__getitem__(self, key)
             view.copy_(torch.as_tensor(np.asarray(value.cpu() if hasattr(value, "cpu") else value), dtype=view.dtype).reshape(view.shape))
+            if self.owner is not None:
+                self.owner.shadow_dirty = True
         else:
             dict.__setitem__(self, key, value)
 
@@ -70,6 +74,14 @@ class ParamTree(dict):
 
     flat = None
     specs = None
+    # bf16 copy of `flat` for the tensor-core path (allocated on first use).  Adam keeps it current inside the captured
+    # step; anything that writes parameters outside of it (item assignment, shift_params, or in-place torch ops on the
+    # views — call mark_dirty() after those) makes the next step rebuild it.
+    shadow = None
+    shadow_dirty = True
+
+    def mark_dirty(self) -> None:
+        self.shadow_dirty = True
 
     def leaves(self):
         for mod, leaf, _ in self.specs:
@@ -82,6 +94,7 @@ def build_tree(flat, specs, offsets) -> ParamTree:
     for (mod, leaf, shape), off in zip(specs, offsets):
         n = int(np.prod(shape))
         d = inner.setdefault(mod, _LeafDict())
+        d.owner = tree
         dict.__setitem__(d, leaf, flat[off : off + n].view(shape))
     tree["params"] = inner
     tree.flat = flat

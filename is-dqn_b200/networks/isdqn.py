@@ -166,7 +166,21 @@ class iSDQN:
         c = self._context(B)
         return ReplayElement(c["state"], c["action"], c["reward"], c["next_state"], c["terminal"])
 
-    def _train_struct(self, ctx, params: ParamTree, opt: OptState, B: int) -> "_lib.Train":
+    def _ensure_shadow(self, params: ParamTree) -> None:
+        if params.shadow is None:
+            params.shadow = self._torch.empty(params.flat.numel(), dtype=self._torch.bfloat16, device="cuda")
+            params.shadow_dirty = True
+
+    def _refresh_shadow(self, params: ParamTree, stream) -> None:
+        """bf16 shadow <- fp32 parameters (needed after the parameters were written outside the captured step)."""
+        self._ensure_shadow(params)
+        _lib.check(
+            self._lib.isdqn_cast_f32_to_bf16(params.flat.data_ptr(), params.shadow.data_ptr(), params.flat.numel(), stream),
+            "isdqn_cast_f32_to_bf16",
+        )
+        params.shadow_dirty = False
+
+    def _train_struct(self, ctx, params: ParamTree, opt: OptState, B: int, refresh_shadow: bool = True) -> "_lib.Train":
         tr = _lib.Train()
         tr.gamma_n = float(self.gamma**self.update_horizon)
         tr.lr, tr.b1, tr.b2, tr.eps = self.learning_rate, self.adam_b1, self.adam_b2, self.adam_eps
@@ -183,8 +197,14 @@ class iSDQN:
         tr.nccl_comm = self._nccl_comm
         tr.compute_dtype = _lib.COMPUTE_BF16 if self.compute_dtype == "bfloat16" else _lib.COMPUTE_F32
         if ctx["ws_tc"] is not None:
+            self._ensure_shadow(params)
             tr.d_workspace_tc = ctx["ws_tc"].data_ptr()
             tr.workspace_tc_bytes = ctx["ws_tc"].numel()
+            tr.d_params_bf16 = params.shadow.data_ptr()
+            # direct launches always rebuild the shadow (5 us); the captured graph relies on Adam keeping it current
+            tr.refresh_shadow = 1 if refresh_shadow else 0
+            if refresh_shadow:
+                params.shadow_dirty = False
         return tr
 
     def _load_batch(self, ctx, batch) -> int:
@@ -267,6 +287,8 @@ class iSDQN:
         key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
                optimizer_state["count"].data_ptr(), stream)
         if self._use_graph and ctx["graph"] is not None and ctx["graph_key"] == key:
+            if ctx["ws_tc"] is not None and params.shadow_dirty:
+                self._refresh_shadow(params, stream)
             _lib.check(self._lib.isdqn_graph_launch(ctx["graph"], stream), "isdqn_graph_launch")
             return params, optimizer_state, ctx["losses"]
         tr = self._train_struct(ctx, params, optimizer_state, B)
@@ -275,6 +297,9 @@ class iSDQN:
             if ctx["graph"] is not None:
                 self._lib.isdqn_graph_destroy(ctx["graph"])
                 ctx["graph"] = None
+            if ctx["ws_tc"] is not None:
+                self._refresh_shadow(params, stream)  # outside the capture
+                tr.refresh_shadow = 0
             _lib.check(self._lib.isdqn_graph_begin(stream), "isdqn_graph_begin")
             rc = self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream)
             exec_ = _lib.C.c_void_p()
@@ -362,6 +387,7 @@ class iSDQN:
             ),
             "isdqn_shift_heads",
         )
+        params.shadow_dirty = True
         return params
 
     def best_action(self, params: ParamTree, state, key):
