@@ -349,6 +349,111 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_dp(args, rank, world, local_rank):
+    """BASELINE configs[4]: large-batch (default 4096, CNN x2) data-parallel learner; strong scaling over N GPUs."""
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from isdqn_b200 import _lib
+    from isdqn_b200.distributed import init_data_parallel, shard_bounds
+    from isdqn_b200.networks.isdqn import iSDQN
+    from isdqn_b200.sample_collection.replay_buffer import ReplayBuffer, TransitionElement
+    from isdqn_b200.sample_collection.samplers import UniformSamplingDistribution
+
+    Bg = args.batch or 4096
+    width = args.width or 2
+    feats = [f * width for f in FEATURES]
+    lo, hi = shard_bounds(Bg, rank, world)
+    Bl = hi - lo
+    cap = min(args.capacity, 200_000)
+    rb = ReplayBuffer(UniformSamplingDistribution(0), Bg, cap, stack_size=4, update_horizon=1, gamma=GAMMA,
+                      frame_capacity=cap + cap // 8 + 64)  # replicated storage, same seed => same draws on every rank
+    for obs, a, r, d in synthetic_stream(1000, cap + 64):
+        rb.add(TransitionElement(obs, a, r, d, d))
+    agent = iSDQN(0, OBS, N_ACTIONS, K_HEADS, feats, True, False, "cnn", LR, GAMMA, 1, 1, 8000, adam_eps=ADAM_EPS,
+                  compute_dtype="bfloat16" if args.dtype == "bf16" else "float32")
+    if world > 1:
+        init_data_parallel(agent)
+    stream = torch.cuda.Stream()
+    peaks = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        bufs = agent.batch_buffers(Bl)
+
+        def step():
+            _, _, d_slot = rb._sampling_distribution.sample_device(Bg, rb._slots)
+            batch = rb._gather_slots_device(d_slot[lo:hi].contiguous(), out=bufs)
+            agent.learn_on_batch(agent.params, agent.optimizer_state, batch)
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            ev0.record()
+            for _ in range(args.steps):
+                step()
+            ev1.record()
+            barrier()
+        ms = ev0.elapsed_time(ev1)
+        agent._use_graph = False
+        prof = _lib.profile(step)
+    per_kernel = {}
+    for name, t in prof:
+        per_kernel.setdefault(name, [0, 0.0])
+        per_kernel[name][0] += 1
+        per_kernel[name][1] += t
+    t_max = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms = float(t_max.item())
+    if rank == 0:
+        # FLOPs per transition scale with width^2 for every layer but the first conv (x width) and the head (x width)
+        P = agent.network.n_params
+        flops = Bg * flops_per_transition(feats)
+        torso = sum(v[1] for k, v in per_kernel.items() if k in ("tc_conv_fwd", "conv_fwd"))
+        torso_flops = 2 * Bl * torso_fwd_flops(feats)
+        line = {
+            "metric": "iS-DQN K=9 learner updates/sec (data parallel)", "value": args.steps / (ms / 1e3), "unit": "updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"large-batch iS-DQN K=9 data parallel, global batch {Bg}, CNN width x{width} "
+                                   "(BASELINE.json configs[4])", "global_batch": Bg, "features": feats, "params": P,
+                       "parallelism": f"dp{world}: NCCL all-reduce of the {4 * P / 1e6:.1f} MB fp32 gradient"},
+            "clocks": clk.summary(),
+            "transitions_per_s": Bg * args.steps / (ms / 1e3),
+            "learner_tflops": flops * args.steps / (ms / 1e3) / 1e12,
+            "torso_fwd": {"ms": torso, "tflops": torso_flops / (torso / 1e3) / 1e12 if torso > 0 else None,
+                          "frac_of_bf16_peak": (torso_flops / (torso / 1e3) / 1e12 / peaks["tflops_sustained"]) if torso > 0 else None},
+            "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def torso_fwd_flops(feats):
+    """2 * MACs of the three convs for one image (SAME padding: 84 -> 21 -> 11 -> 11)."""
+    return 2 * (441 * 256 * feats[0] + 121 * 16 * feats[0] * feats[1] + 121 * 9 * feats[1] * feats[2])
+
+
+def flops_per_transition(feats):
+    """fwd on 2 images + wgrad + dgrad (no dgrad for the first conv), SURVEY §8(d) accounting."""
+    c0, c1, c2 = 441 * 256 * feats[0], 121 * 16 * feats[0] * feats[1], 121 * 9 * feats[1] * feats[2]
+    d0, d1 = 121 * feats[2] * feats[3], feats[3] * (1 + K_HEADS) * N_ACTIONS
+    fwd = 2 * (c0 + c1 + c2 + d0 + d1)
+    return 2 * fwd + fwd + (fwd - 2 * c0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -357,6 +462,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--capacity", type=int, default=int(os.environ.get("ISDQN_BENCH_CAPACITY", 1_000_000)))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--mode", default="agents", choices=["agents", "dp"],
+                    help="agents: one independent agent per GPU (weak scaling, BASELINE configs[1]/[3]); dp: ONE learner, "
+                         "global batch split over the GPUs, NCCL gradient all-reduce (strong scaling, configs[4])")
+    ap.add_argument("--batch", type=int, default=None, help="dp mode: global batch (default 4096)")
+    ap.add_argument("--width", type=int, default=None, choices=[1, 2, 4], help="dp mode: CNN width multiplier (default 2)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"],
                     help="bf16: tcgen05 tensor-core path (fp32 accumulate/master weights); f32: CUDA-core fp32 parity path")
     args = ap.parse_args()
@@ -365,6 +475,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.mode == "dp":
+        if args.warmup < 3:
+            args.warmup = 3
+        run_dp(args, rank, world, local_rank)
     else:
         if args.warmup < 3:
             args.warmup = 3
