@@ -1,6 +1,7 @@
 // tcgen05 tile engine: D[128 x BN] (fp32, in TMEM) += A[128 x K] * B[BN x K]^T with bf16 operands staged in shared
-// memory by the CTA's own threads (implicit-GEMM gathers), one elected thread issuing tcgen05.mma, the epilogue
-// reading the accumulator back with tcgen05.ld — thread t owns output row t, so row-wise LayerNorm is thread-local.
+// memory by producer warps (implicit-GEMM gathers), one elected thread issuing tcgen05.mma, epilogue warps reading
+// the accumulator back with tcgen05.ld — thread t owns output row t, so row-wise LayerNorm is thread-local.
+// Persistent and warp-specialised: see tc_gemm_kernel below.
 //
 // Shared-memory operand layout: the canonical NO-SWIZZLE ("interleave") UMMA layout of 8x16-byte core matrices,
 // which — unlike the 128B-swizzle atoms TMA produces — accepts any extent that is a multiple of 8 and is cheap to
@@ -18,7 +19,7 @@
 namespace isdqn {
 namespace tc {
 
-constexpr int kThreads = 128;   // 4 warps: all of them load and run the epilogue, thread 0 also issues the MMAs
+constexpr int kThreads = 128;   // rows of a tile = threads of the epilogue = lanes of the accumulator
 constexpr int kBM = 128;        // UMMA_M (cta_group::1): accumulator row i lives in TMEM lane i
 constexpr int kBK = 64;         // reduction elements per pipeline stage (4 MMAs of K=16)
 constexpr int kABytes = kBM * kBK * 2;
@@ -97,14 +98,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ---- UMMA ----------------------------------------------------------------------------------------------------
-// shared-memory matrix descriptor, no swizzle, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor, version 1 (Blackwell); layout_type 0 = no swizzle, 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 0) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
+}
+// Descriptor of the q-th K=16 slice of one 64-deep stage.
+//   swizzled (128B):  K-major : rows of 128 B (64 k), 8-row atoms of 1 KB, SBO = 1 KB; a K slice is 32 B inside the row
+//                     MN-major: K-rows of 128 B (64 mn), 8-row atoms, SBO = 1 KB (next 8 k-rows), LBO = 8 KB (next 64 mn);
+//                               a K slice is two atoms = 2 KB
+//   no swizzle     :  8x16-byte core matrices, LBO = 128 B along K, SBO = 1 KB along M/N; a K slice is 256 B
+template <bool MN_MAJOR, bool SWIZZLED>
+__device__ __forceinline__ uint64_t stage_desc(uint32_t stage_addr, int q) {
+  if (!SWIZZLED) return make_smem_desc(stage_addr + q * 256, 128, 1024, 0);
+  if (MN_MAJOR) return make_smem_desc(stage_addr + q * 2048, 8192, 1024, 2);
+  return make_smem_desc(stage_addr + q * 32, 16, 1024, 2);
 }
 // instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M = 128
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
@@ -128,41 +142,86 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-// stage addressing helpers (bytes)
-__device__ __forceinline__ uint32_t kmajor_off(int row, int chunk) { return (uint32_t)((row >> 3) * 1024 + chunk * 128 + (row & 7) * 16); }
-__device__ __forceinline__ uint32_t mnmajor_off(int krow, int chunk) { return (uint32_t)(chunk * 1024 + (krow >> 3) * 128 + (krow & 7) * 16); }
+// stage addressing helpers (bytes): (row, 16-byte chunk of K) for K-major, (K-row, 16-byte chunk of MN) for MN-major
+template <bool SWIZZLED>
+__device__ __forceinline__ uint32_t kmajor_off(int row, int chunk) {
+  if (SWIZZLED) return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+  return (uint32_t)((row >> 3) * 1024 + chunk * 128 + (row & 7) * 16);
+}
+template <bool SWIZZLED>
+__device__ __forceinline__ uint32_t mnmajor_off(int krow, int chunk) {
+  if (SWIZZLED) return (uint32_t)((chunk >> 3) * 8192 + (krow >> 3) * 1024 + (krow & 7) * 128 + (((chunk & 7) ^ (krow & 7)) << 4));
+  return (uint32_t)(chunk * 1024 + (krow >> 3) * 128 + (krow & 7) * 16);
+}
 
 template <int BN, int STAGES>
 constexpr size_t smem_bytes() {
   return (size_t)STAGES * (kABytes + (size_t)BN * kBK * 2) + 1024;  // + alignment slack
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+constexpr int kEpilogueWarps = 4;  // warps 0..3: warp w may only touch TMEM lanes 32w..32w+31
+constexpr int kMmaWarp = 4;        // warp 4: lane 0 issues every tcgen05.mma
+constexpr int kFirstProducerWarp = 5;
+
+// Persistent, warp-specialised kernel.  Tiles (x fastest, then y, then z) are dealt round-robin to the CTAs; inside
+// a CTA three roles run concurrently and meet only through mbarriers:
+//   producers  gather the operands of k-chunk j into stage j % STAGES (cp.async / LDG+convert), keep STAGES-1 chunks
+//              in flight, and arrive on full[s] once their part of a chunk has landed and is fenced to the async proxy;
+//   MMA warp   waits full[s], issues 4 x tcgen05.mma (K = 16 each) into accumulator a = tile & 1, tcgen05.commit ->
+//              empty[s]; after the last chunk of a tile commit -> tmem_full[a];
+//   epilogue   waits tmem_full[a], reads the accumulator with tcgen05.ld (thread t owns row t), runs the problem's
+//              epilogue, arrives on tmem_empty[a] — so the gather of tile i+1 overlaps the epilogue of tile i.
+//
 // P (the problem) provides:
-//   static constexpr int BN, STAGES; static constexpr bool A_MN, B_MN;
-//   static constexpr int EXTRA_BYTES (shared scratch for lookup tables);
-//   struct Ctx;  __device__ void init(Ctx&, uint8_t* extra, int m0, int n0, int tid) const;   (a __syncthreads follows)
-//   __device__ void k_range(int split, int& kc_begin, int& kc_end) const;      (in units of 64-element chunks)
-//   __device__ void load_a(const Ctx&, uint32_t stage_smem, int kc, int tid) const;   load_b(...)
-//   __device__ void epilogue(const Ctx&, uint32_t tmem_lane_base, bool has_acc, int m0, int n0, int tid, int split) const;
+//   static constexpr int BN, STAGES, PRODUCER_WARPS, EXTRA_BYTES; static constexpr bool A_MN, B_MN, CHUNK_SYNC;
+//   (the A stage is always 128B-swizzled; the B stage is swizzled when BN >= 64, core-matrix layout for BN == 32)
+//   struct PCtx, ECtx;
+//   __device__ void init_cta(uint8_t* extra, int ptid) const;                  (producers only; a producer barrier follows)
+//   __device__ void tile_producer(PCtx&, uint8_t* extra, int m0, int n0, int z, int ptid, int tile_iter) const;
+//   __device__ void chunk_producer(PCtx&, uint8_t* extra, int kc, int ptid, int chunk_iter) const;   (if CHUNK_SYNC)
+//   __device__ void tile_epilogue(ECtx&, int m0, int n0, int z, int etid) const;
+//   __device__ void k_range(int z, int& kc_begin, int& kc_end) const;          (64-element chunks, never empty)
+//   __device__ void load_a(const PCtx&, uint32_t stage_smem, int kc, int ptid) const;   load_b(...)
+//   __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int z, int etid) const;
 template <class P>
-__global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const P p) {
+__global__ void __launch_bounds__(32 * (kFirstProducerWarp + P::PRODUCER_WARPS), (P::BN <= 64 ? 2 : 1))
+tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   constexpr int BN = P::BN, STAGES = P::STAGES;
   constexpr int B_BYTES = BN * kBK * 2;
-  constexpr uint32_t TMEM_COLS = tmem_cols_for(BN);
+  constexpr int PT = 32 * P::PRODUCER_WARPS;
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * BN);
+  static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
   extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_sh;
+  __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * kABytes;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, split = blockIdx.z;
+  const int n_tiles = tiles_x * tiles_y * tiles_z;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
-    mbar_init(&done_bar, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], PT);
+      mbar_init(&empty_bar[s], 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 32 * kEpilogueWarps);
+    }
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -174,53 +233,86 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const P p) {
   tcgen05_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
 
-  __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
-  typename P::Ctx ctx;
-  p.init(ctx, extra_sm, m0, n0, tid);
-  __syncthreads();
-  int kc_begin, kc_end;
-  p.k_range(split, kc_begin, kc_end);
-  const int nk = kc_end - kc_begin;
-  constexpr uint32_t idesc = make_idesc(BN, P::A_MN, P::B_MN);
-
-#pragma unroll
-  for (int i = 0; i < STAGES - 1; ++i) {
-    if (i < nk) {
-      p.load_a(ctx, sA + i * kABytes, kc_begin + i, tid);
-      p.load_b(ctx, sB + i * B_BYTES, kc_begin + i, tid);
-    }
-    cp_async_commit();
-  }
-  for (int i = 0; i < nk; ++i) {
-    const int pf = i + STAGES - 1;  // chunk to prefetch now
-    if (pf < nk) {
-      const int ps = pf % STAGES;
-      if (pf >= STAGES) mbar_wait(&empty_bar[ps], (uint32_t)((pf / STAGES - 1) & 1));  // MMAs of chunk pf-STAGES done
-      p.load_a(ctx, sA + ps * kABytes, kc_begin + pf, tid);
-      p.load_b(ctx, sB + ps * B_BYTES, kc_begin + pf, tid);
-    }
-    cp_async_commit();
-    cp_async_wait<STAGES - 1>();  // this thread's part of chunk i has landed
-    fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
-      tcgen05_fence_after();
-      const int s = i % STAGES;
-#pragma unroll
-      for (int j = 0; j < kBK / 16; ++j) {
-        const uint64_t adesc = make_smem_desc(sA + s * kABytes + j * 256, 128, 1024);
-        const uint64_t bdesc = make_smem_desc(sB + s * B_BYTES + j * 256, 128, 1024);
-        umma_bf16(tmem_d, adesc, bdesc, idesc, (i | j) != 0 ? 1u : 0u);
+  if (warp >= kFirstProducerWarp) {
+    // ------------------------------------------------------------------------------------------ producers
+    const int ptid = tid - 32 * kFirstProducerWarp;
+    p.init_cta(extra_sm, ptid);
+    named_bar_sync(1, PT);
+    typename P::PCtx ctx;
+    int j = 0;  // chunk counter of this CTA (stage = j % STAGES)
+    int ti = 0;
+    constexpr int D = STAGES - 1;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
+      const int m0 = tx * kBM, n0 = ty * BN;
+      p.tile_producer(ctx, extra_sm, m0, n0, tz, ptid, ti);  // may publish per-row info in shared memory (parity ti & 1)
+      named_bar_sync(1, PT);
+      int kb, ke;
+      p.k_range(tz, kb, ke);
+      for (int kc = kb; kc < ke; ++kc, ++j) {
+        const int s = j % STAGES;
+        if (P::CHUNK_SYNC) {  // per-chunk row info (weight gradient: the reduction rows change every chunk)
+          p.chunk_producer(ctx, extra_sm, kc, ptid, j);
+          named_bar_sync(1, PT);
+        }
+        mbar_wait(&empty_bar[s], (uint32_t)(((j / STAGES) & 1) ^ 1));  // stage free (first lap: passes)
+        p.load_a(ctx, sA + s * kABytes, kc, ptid);
+        p.load_b(ctx, sB + s * B_BYTES, kc, ptid);
+        cp_async_commit();
+        if (j >= D) {  // chunk j-D of this thread has landed: publish it
+          cp_async_wait<D>();
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(j - D) % STAGES]);
+        }
       }
-      umma_commit(&empty_bar[s]);
-      if (i == nk - 1) umma_commit(&done_bar);
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int q = (j > D ? j - D : 0); q < j; ++q) mbar_arrive(&full_bar[q % STAGES]);
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, P::A_MN, P::B_MN);
+      int j = 0, ti = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        const int tz = t / (tiles_x * tiles_y);
+        int kb, ke;
+        p.k_range(tz, kb, ke);
+        const int a = ti & 1;
+        mbar_wait(&tmem_empty_bar[a], (uint32_t)((((ti >> 1) & 1)) ^ 1));  // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_d + a * BN;
+        for (int kc = kb; kc < ke; ++kc, ++j) {
+          const int s = j % STAGES;
+          mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+          tcgen05_fence_after();
+#pragma unroll
+          for (int q = 0; q < kBK / 16; ++q) {
+            const uint64_t adesc = stage_desc<P::A_MN, true>(sA + s * kABytes, q);
+            const uint64_t bdesc = stage_desc<P::B_MN, (BN >= 64)>(sB + s * B_BYTES, q);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kc > kb || q > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[a]);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------------------------------- epilogue
+    typename P::ECtx ectx;
+    int ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
+      const int m0 = tx * kBM, n0 = ty * BN;
+      const int a = ti & 1;
+      p.tile_epilogue(ectx, m0, n0, tz, tid);
+      mbar_wait(&tmem_full_bar[a], (uint32_t)((ti >> 1) & 1));
+      tcgen05_fence_after();
+      p.epilogue(ectx, tmem_d + a * BN + ((uint32_t)(warp * 32) << 16), m0, n0, tz, tid);
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[a]);
     }
   }
-  if (nk > 0) {
-    mbar_wait(&done_bar, 0);
-    tcgen05_fence_after();
-  }
-  p.epilogue(ctx, tmem_d + ((uint32_t)(warp * 32) << 16), nk > 0, m0, n0, tid, split);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);

@@ -27,16 +27,26 @@ namespace {
 
 inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret_cast<float*>(ws) + off; }
 
+// Persistent launch: the tiles (x fastest) are dealt round-robin to min(#tiles, SMs x resident CTAs) CTAs.
 template <class P>
-int launch_tc(const P& p, dim3 grid, cudaStream_t s, const char* tag) {
+int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag) {
   constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
-  static bool configured = false;
-  if (!configured) {
+  constexpr int threads = 32 * (tc::kFirstProducerWarp + P::PRODUCER_WARPS);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    int occ = 0;
+    ISDQN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_gemm_kernel<P>, threads, smem));
+    const int by_tmem = 512 / tc::tmem_cols_for(2 * P::BN);  // every resident CTA owns two accumulators in TMEM
+    if (occ > by_tmem) occ = by_tmem;
+    ctas_per_sm = occ < 1 ? 1 : occ;
   }
+  const int64_t n_tiles = (int64_t)tiles_x * tiles_y * tiles_z;
+  if (n_tiles < 1 || n_tiles > 0x7fffffff) return ISDQN_E_INVALID;
+  const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   ISDQN_PROF(s, tag);
-  tc::tc_gemm_kernel<P><<<grid, tc::kThreads, smem, s>>>(p);
+  tc::tc_gemm_kernel<P><<<grid, threads, smem, s>>>(p, tiles_x, tiles_y, tiles_z);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -57,14 +67,13 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
   const int cps = ceil_div(total_chunks, splits);
   const int real_splits = ceil_div(total_chunks, cps);
   const int bn = pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
-  dim3 grid(ceil_div(M, tc::kBM), ceil_div(N, bn), real_splits);
 #define ISDQN_GEMM_TC(BN)                                                      \
   {                                                                            \
     tc::GemmTC<BN, A_MN, B_MN> p;                                              \
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;          \
     p.split_stride = split_stride; p.M = M; p.N = N; p.K = K;                  \
     p.chunks_per_split = cps;                                                  \
-    return launch_tc(p, grid, s, tag);                                         \
+    return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag); \
   }
   switch (bn) {
     case 32: ISDQN_GEMM_TC(32)
@@ -111,7 +120,9 @@ bool tc_eligible(const Plan& p, const isdqn_net* net) {
     if (L.type == 0) {
       if (!(L.out_dim == 32 || L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256)) return false;
       const int taps = ceil_div(L.ksz, L.stride);
-      if (L.in_dim > 8 * tc::kMaxChunks - 64 || taps * taps * L.out_dim > 8 * tc::kMaxChunks - 64) return false;
+      // chunk tables: whole K axis for the weight gradient, (parity classes x tap chunks) for the input gradient
+      if (ceil_div(L.in_dim, tc::kBM) * 16 > tc::kMaxChunks) return false;
+      if (l > 0 && L.stride * L.stride * ceil_div(taps * taps * L.out_dim, tc::kBK) * 8 > tc::kMaxChunks) return false;  // (no input gradient for the first layer)
     } else {
       if (L.in_dim % 8 || L.out_dim % 64 || L.out_dim > kRowThreads * kRowMaxPerThread) return false;
     }
@@ -133,7 +144,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
     p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
     p.ln_b = L.has_ln ? params + L.beta_off : nullptr;                                                 \
     p.relu = L.relu; p.out = out; p.xhat = xhat; p.rstd = rstd; p.m_train = m_train;                   \
-    return launch_tc(p, dim3(ceil_div(p.M, tc::kBM), 1, 1), s, "tc_conv_fwd");                         \
+    return launch_tc(p, ceil_div(p.M, tc::kBM), 1, 1, s, "tc_conv_fwd");                               \
   }
   switch (L.out_dim) {
     case 32: ISDQN_CONV_FWD_TC(32)
@@ -157,7 +168,7 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
     p.in = in; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;     \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
     p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
-    return launch_tc(p, dim3(ceil_div(L.in_dim, tc::kBM), 1, *real_splits), s, "tc_conv_wgrad");       \
+    return launch_tc(p, ceil_div(L.in_dim, tc::kBM), 1, *real_splits, s, "tc_conv_wgrad");             \
   }
   switch (L.out_dim) {
     case 32: ISDQN_CONV_WGRAD_TC(32)
@@ -173,14 +184,13 @@ int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* d
   const int taps = ceil_div(L.ksz, L.stride);
   const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
   const int bn = pick_bn(L.Cin);
-  dim3 grid(ceil_div(rows_max, tc::kBM), ceil_div(L.Cin, bn), L.stride * L.stride);
 #define ISDQN_CONV_DGRAD_TC(BN)                                                                        \
   {                                                                                                    \
     tc::ConvDgradTC<BN> p;                                                                             \
     p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;                \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.n_img = B;             \
     p.taps = taps; p.Kd = taps * taps * L.out_dim; p.dz = dz; p.w = w; p.dx = dx;                      \
-    return launch_tc(p, grid, s, "tc_conv_dgrad");                                                     \
+    return launch_tc(p, ceil_div(rows_max, tc::kBM), ceil_div(L.Cin, BN), L.stride * L.stride, s, "tc_conv_dgrad"); \
   }
   switch (bn) {
     case 32: ISDQN_CONV_DGRAD_TC(32)

@@ -2,9 +2,17 @@
 // operand gathers (im2col forward, transposed-data weight gradient, tap-gathered input gradient, plain matrices) and
 // epilogues (fused bias + LayerNorm + ReLU, plain fp32 store).  bf16 operands, fp32 accumulation in TMEM.
 //
-// Gathers never divide: every CTA first builds, in shared memory, one table entry per 16-byte chunk of its
-// reduction axis (offset of the chunk relative to the row's anchor pixel + the tap coordinates for the bounds
-// test); the per-chunk work of a loader is then one LDS, two compares and one cp.async.
+// Gather design (what ncu asked for):
+//  * coalesced: 8 consecutive lanes fetch the 8 16-byte chunks of ONE 128-byte row (one cache line per 8 lanes instead
+//    of one per lane) and write them into a 128B-swizzled UMMA stage, where those 8 chunks land in 8 different bank
+//    groups — the same trick TMA + SWIZZLE_128B plays, done by hand because the rows are gathered (im2col);
+//  * no per-element arithmetic: the producers build, once per CTA, a table with one entry per 16-byte chunk of the
+//    reduction axis (offset relative to the row's anchor pixel + tap coordinates for the bounds test), and publish
+//    the per-row anchors of each tile (or chunk) in shared memory; a gather task is then 2 LDS + 2 compares + 1 cp.async;
+//  * uint8 frames (first conv): the 8-byte loads of all tasks of a thread are issued back to back, then converted
+//    (x/255 -> bf16) and stored — the asm memory clobbers of the stores would otherwise serialise them.
+// Addresses are formed as base + (anchor + offset) with a SIGNED element offset: out-of-range pointers are never
+// materialised (nvcc 12.9 -O3 was observed to drop conditional stores into a context that held such pointers).
 #pragma once
 #include "tc_engine.cuh"
 
@@ -13,62 +21,64 @@ namespace tc {
 
 typedef __nv_bfloat16 bf16;
 
-constexpr int kMaxChunks = 512;  // 16-byte chunks of a reduction axis (K <= 4096 elements)
+constexpr int kMaxChunks = 512;  // table entries: 16-byte chunks of a reduction axis (x stride-parity classes)
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// x/255 (architectures/dqn.py:51) for a packed uint8 pair -> packed bf16 pair
+// x/255 (architectures/dqn.py:51) for a uint8 pair -> packed bf16 pair
 __device__ __forceinline__ uint32_t norm_pair_bf16(uint32_t b0, uint32_t b1) {
   return pack_bf16(__fmul_rn((float)b0, 1.0f / 255.0f), __fmul_rn((float)b1, 1.0f / 255.0f));
 }
 
 struct ChunkEntry {
   int off;  // element offset of the chunk relative to the row's anchor
-  int yx;   // (dy << 16) | dx : tap coordinates (or -1: chunk is past the end of the reduction axis)
+  int yx;   // (dy << 16) | dx : tap coordinates (or -1: no such chunk)
 };
+struct __align__(16) RowInfo {
+  int64_t anchor;  // element offset of the row's anchor relative to its base pointer (can be negative)
+  int y0;          // anchor coordinates; y0 = kInvalidRow for rows past the end
+  short x0;
+  short second;    // 1: the row's image lives in the second input pointer (the s' half of concat(s, s'))
+};
+constexpr int kInvalidRow = -(1 << 28);
+constexpr int kRowInfoBytes = 2 * kBM * (int)sizeof(RowInfo);  // double buffered (tile / chunk parity)
 
 // ------------------------------------------------------------------------------------------- generic loaders
-// K-major operand from a row-major matrix [rows][ld] (reduction index contiguous): thread t fills row t.
+// K-major operand from a row-major matrix [rows][ld] (reduction index contiguous); 8 lanes = one 128-byte row.
+template <int ROWS, int PT, bool SW>
 __device__ __forceinline__ void load_rows_kmajor(const bf16* __restrict__ src, int64_t ld, int row0, int n_rows_valid,
-                                                 int k0, int k_end, uint32_t stage, int tid, int rows_in_tile) {
-  for (int r = tid; r < rows_in_tile; r += kThreads) {
-    const int row = row0 + r;
-    const bool rv = row < n_rows_valid;
-    const bf16* base = src + (int64_t)(rv ? row : 0) * ld;
+                                                 int k0, int k_end, uint32_t stage, int ptid) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int k = k0 + 8 * c;
-      const bool v = rv && k < k_end;
-      cp_async16(stage + kmajor_off(r, c), base + (v ? k : 0), v);
-    }
+  for (int t = ptid; t < ROWS * 8; t += PT) {
+    const int c = t & 7, r = t >> 3;
+    const int row = row0 + r, k = k0 + 8 * c;
+    const bool v = row < n_rows_valid && k < k_end;
+    cp_async16(stage + kmajor_off<SW>(r, c), src + (v ? (int64_t)row * ld + k : 0), v);
   }
 }
 // MN-major operand from a row-major matrix [k rows][ld] (row = reduction index, MN contiguous): 64 k-rows per stage
+template <int MN_CHUNKS, int PT, bool SW>
 __device__ __forceinline__ void load_rows_mnmajor(const bf16* __restrict__ src, int64_t ld, int k0, int k_end, int mn0,
-                                                  int mn_end, uint32_t stage, int tid, int mn_chunks) {
-  for (int idx = tid; idx < 64 * mn_chunks; idx += kThreads) {
-    const int kk = idx & 63, c = idx >> 6;
+                                                  int mn_end, uint32_t stage, int ptid) {
+#pragma unroll
+  for (int t = ptid; t < 64 * MN_CHUNKS; t += PT) {
+    const int c = t % MN_CHUNKS, kk = t / MN_CHUNKS;
     const int k = k0 + kk, mn = mn0 + 8 * c;
     const bool v = k < k_end && mn < mn_end;
-    cp_async16(stage + mnmajor_off(kk, c), src + (v ? (int64_t)k * ld + mn : 0), v);
+    cp_async16(stage + mnmajor_off<SW>(kk, c), src + (v ? (int64_t)k * ld + mn : 0), v);
   }
 }
 
 // plain fp32 store of the accumulator tile: thread t owns row t
 template <int BN>
-__device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, bool has_acc, float* __restrict__ dst, int64_t ld,
-                                               bool row_valid, int n0, int n_end) {
+__device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, float* __restrict__ dst, bool row_valid, int n0,
+                                               int n_end) {
 #pragma unroll 1
   for (int cb = 0; cb < BN / 32; ++cb) {
     float v[32];
-    if (has_acc) {
-      tmem_ld32(tmem_lane_base + cb * 32, v);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.f;
-    }
+    tmem_ld32(tmem_lane_base + cb * 32, v);
     if (row_valid) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -83,49 +93,56 @@ __device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, bool has
       }
     }
   }
-  (void)ld;
 }
 
 // --------------------------------------------------------------------------------------- plain GEMM (+ split-K)
 // D[M][N] = sum_k A(m,k) B(n,k); A: K-major [M][lda] or MN-major [K][lda]; B likewise.  fp32 output (partials).
 template <int BN_, bool A_MN_, bool B_MN_>
 struct GemmTC {
-  static constexpr int BN = BN_, STAGES = 3, EXTRA_BYTES = 0;
-  static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
+  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4, EXTRA_BYTES = 0;
+  static constexpr int PT = 32 * PRODUCER_WARPS;
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, B_SW = BN_ >= 64;
   const bf16* A; int64_t lda;
   const bf16* B; int64_t ldb;
   float* C; int64_t ldc; int64_t split_stride;
   int M, N, K, chunks_per_split;
-  struct Ctx {};
-  __device__ void init(Ctx&, uint8_t*, int, int, int) const {}
+  struct PCtx {
+    int m0, n0;
+  };
+  struct ECtx {};
+  __device__ void init_cta(uint8_t*, int) const {}
+  __device__ void tile_producer(PCtx& c, uint8_t*, int m0, int n0, int, int, int) const {
+    c.m0 = m0;
+    c.n0 = n0;
+  }
+  __device__ void chunk_producer(PCtx&, uint8_t*, int, int, int) const {}
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
   __device__ void k_range(int split, int& b, int& e) const {
     const int total = (K + kBK - 1) / kBK;
     b = split * chunks_per_split;
     e = min(total, b + chunks_per_split);
-    if (e < b) e = b;
   }
-  __device__ void load_a(const Ctx&, uint32_t stage, int kc, int tid) const {
-    const int m0 = blockIdx.x * kBM;
-    if (A_MN) load_rows_mnmajor(A, lda, kc * kBK, K, m0, M, stage, tid, kBM / 8);
-    else load_rows_kmajor(A, lda, m0, M, kc * kBK, K, stage, tid, kBM);
+  __device__ void load_a(const PCtx& c, uint32_t stage, int kc, int ptid) const {
+    if (A_MN) load_rows_mnmajor<kBM / 8, PT, true>(A, lda, kc * kBK, K, c.m0, M, stage, ptid);
+    else load_rows_kmajor<kBM, PT, true>(A, lda, c.m0, M, kc * kBK, K, stage, ptid);
   }
-  __device__ void load_b(const Ctx&, uint32_t stage, int kc, int tid) const {
-    const int n0 = blockIdx.y * BN;
-    if (B_MN) load_rows_mnmajor(B, ldb, kc * kBK, K, n0, N, stage, tid, BN / 8);
-    else load_rows_kmajor(B, ldb, n0, N, kc * kBK, K, stage, tid, BN);
+  __device__ void load_b(const PCtx& c, uint32_t stage, int kc, int ptid) const {
+    if (B_MN) load_rows_mnmajor<BN / 8, PT, B_SW>(B, ldb, kc * kBK, K, c.n0, N, stage, ptid);
+    else load_rows_kmajor<BN, PT, B_SW>(B, ldb, c.n0, N, kc * kBK, K, stage, ptid);
   }
-  __device__ void epilogue(const Ctx&, uint32_t tmem_lane_base, bool has_acc, int m0, int n0, int tid, int split) const {
-    const int m = m0 + tid;
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
+    const int m = m0 + etid;
     float* dst = C + (int64_t)split * split_stride + (int64_t)(m < M ? m : 0) * ldc;
-    store_rows_f32<BN>(tmem_lane_base, has_acc, dst, ldc, m < M, n0, N);
+    store_rows_f32<BN>(tmem_lane_base, dst, m < M, n0, N);
   }
 };
 
 // im2col chunk table shared by the conv forward and weight-gradient problems.
 // bf16 input (Cin % 8 == 0): chunk = 8 channels of one tap.   uint8 input with Cin == 4: chunk = 2 taps (kx, kx+1).
 // entry.off = ((ky*W + kx)*Cin + c0) elements, entry.yx = (ky << 16) | kx.
-__device__ __forceinline__ void build_im2col_table(ChunkEntry* tab, int n_chunks, int K, int Cin, int ksz, int W, int tid) {
-  for (int ch = tid; ch < n_chunks; ch += kThreads) {
+__device__ __forceinline__ void build_im2col_table(ChunkEntry* tab, int n_chunks, int K, int Cin, int ksz, int W, int ptid,
+                                                   int pt) {
+  for (int ch = ptid; ch < n_chunks; ch += pt) {
     const int k = 8 * ch;
     ChunkEntry e;
     if (k < K) {
@@ -142,26 +159,60 @@ __device__ __forceinline__ void build_im2col_table(ChunkEntry* tab, int n_chunks
   }
 }
 
-// one 16-byte chunk of an im2col row: `anchor` = ELEMENT offset of input element (iy0, ix0, 0) of the row's image
-// relative to `base` (may be negative: it is only added to the pointer after the bounds test)
-template <bool IN_U8>
-__device__ __forceinline__ void gather_im2col_chunk(uint32_t dst, const uint8_t* base, int64_t anchor, bool row_valid, int iy0,
-                                                    int ix0, const ChunkEntry e, int H, int W, int Cin, const void* any_valid_ptr) {
-  const int ky = e.yx >> 16, kx = e.yx & 0xffff;
-  const int iy = iy0 + ky, ix = ix0 + kx;
-  const bool rowok = row_valid && e.yx >= 0 && (unsigned)iy < (unsigned)H;
-  if (!IN_U8) {
-    const bool v = rowok && (unsigned)ix < (unsigned)W;
-    cp_async16(dst, v ? base + (anchor + e.off) * 2 : reinterpret_cast<const uint8_t*>(any_valid_ptr), v);
-  } else {
-    // Cin == 4: two adjacent taps of 4 uint8 channels each (kx even, ksz even: both in the same kernel row)
-    const bool v0 = rowok && (unsigned)ix < (unsigned)W, v1 = rowok && (unsigned)(ix + 1) < (unsigned)W;
-    const uint32_t p0 = v0 ? *reinterpret_cast<const uint32_t*>(base + (anchor + e.off)) : 0u;
-    const uint32_t p1 = v1 ? *reinterpret_cast<const uint32_t*>(base + (anchor + e.off + 4)) : 0u;
-    st_shared_v4(dst, norm_pair_bf16(p0 & 0xff, (p0 >> 8) & 0xff), norm_pair_bf16((p0 >> 16) & 0xff, p0 >> 24),
-                 norm_pair_bf16(p1 & 0xff, (p1 >> 8) & 0xff), norm_pair_bf16((p1 >> 16) & 0xff, p1 >> 24));
+// anchor of output pixel m of a conv: input element (oy*stride - pad_y, ox*stride - pad_x, 0) of its image
+__device__ __forceinline__ RowInfo conv_row_info(int m, int M, int OH, int OW, int H, int W, int Cin, int stride, int pad_y,
+                                                 int pad_x, int n_img0) {
+  RowInfo ri;
+  int64_t anchor = 0;
+  int y0 = kInvalidRow, x0 = 0, second = 0;
+  if (m < M) {
+    const int img = m / (OH * OW);
+    const int rem = m - img * (OH * OW);
+    const int oy = rem / OW, ox = rem - oy * OW;
+    int64_t li = img;
+    if (img >= n_img0) {
+      second = 1;
+      li = img - n_img0;
+    }
+    y0 = oy * stride - pad_y;
+    x0 = ox * stride - pad_x;
+    anchor = ((li * H + y0) * W + x0) * (int64_t)Cin;
   }
-  (void)Cin;
+  ri.anchor = anchor;
+  ri.y0 = y0;
+  ri.x0 = (short)x0;
+  ri.second = (short)second;
+  return ri;
+}
+
+// bf16 gather task: one 16-byte chunk (8 channels of one tap) of one im2col row
+__device__ __forceinline__ void gather_chunk_bf16(uint32_t dst, const void* in0, const void* in1, const RowInfo ri,
+                                                  const ChunkEntry e, int H, int W) {
+  const int iy = ri.y0 + (e.yx >> 16), ix = ri.x0 + (e.yx & 0xffff);
+  const bool v = e.yx >= 0 && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+  const bf16* base = reinterpret_cast<const bf16*>(ri.second ? in1 : in0);
+  cp_async16(dst, v ? base + (ri.anchor + e.off) : reinterpret_cast<const bf16*>(in0), v);
+}
+
+// uint8 gather task, phase 1: fetch the 8 bytes (2 taps x 4 channels); phase 2 converts and stores.
+__device__ __forceinline__ uint2 fetch_chunk_u8(const void* in0, const void* in1, const RowInfo ri, const ChunkEntry e, int H,
+                                                int W) {
+  const int iy = ri.y0 + (e.yx >> 16), ix = ri.x0 + (e.yx & 0xffff);
+  const bool rowok = e.yx >= 0 && (unsigned)iy < (unsigned)H;
+  const bool v0 = rowok && (unsigned)ix < (unsigned)W, v1 = rowok && (unsigned)(ix + 1) < (unsigned)W;
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(ri.second ? in1 : in0) + (ri.anchor + e.off);
+  uint2 r = make_uint2(0u, 0u);
+  if (v0 && v1 && ((reinterpret_cast<uintptr_t>(p) & 7) == 0)) {
+    r = __ldg(reinterpret_cast<const uint2*>(p));
+  } else {
+    if (v0) r.x = __ldg(reinterpret_cast<const uint32_t*>(p));
+    if (v1) r.y = __ldg(reinterpret_cast<const uint32_t*>(p + 4));
+  }
+  return r;
+}
+__device__ __forceinline__ void store_chunk_u8(uint32_t dst, const uint2 p) {
+  st_shared_v4(dst, norm_pair_bf16(p.x & 0xff, (p.x >> 8) & 0xff), norm_pair_bf16((p.x >> 16) & 0xff, p.x >> 24),
+               norm_pair_bf16(p.y & 0xff, (p.y >> 8) & 0xff), norm_pair_bf16((p.y >> 16) & 0xff, p.y >> 24));
 }
 
 // ------------------------------------------------------------------------------------------------ conv forward
@@ -169,62 +220,59 @@ __device__ __forceinline__ void gather_im2col_chunk(uint32_t dst, const uint8_t*
 // IN_U8 requires Cin == 4 (the stacked Atari frames); bf16 input requires Cin % 8 == 0.
 template <int BN_, bool IN_U8_>
 struct ConvFwdTC {
-  static constexpr int BN = BN_, STAGES = 3, EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry);
-  static constexpr bool A_MN = false, B_MN = true;
+  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = IN_U8_ ? 8 : 4;
+  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT;
+  static constexpr int EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry) + kRowInfoBytes;
+  static constexpr bool A_MN = false, B_MN = true, CHUNK_SYNC = false, B_SW = BN_ >= 64;
   const void* in0; const void* in1; int n_img0;
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, M, K;
   const bf16* w;  // [K][Cout]
   const float* bias; const float* ln_g; const float* ln_b; int relu;
   bf16* out; float* xhat; float* rstd; int m_train;
-  struct Ctx {
-    const uint8_t* base;  // the half of concat(s, s') this row's image lives in
-    int64_t anchor;       // element offset of input element (iy0, ix0, 0) of this row's image (can be negative)
-    int iy0, ix0;
-    bool valid;
+  struct PCtx {
     const ChunkEntry* tab;
+    const RowInfo* rows;
   };
-  __device__ void init(Ctx& c, uint8_t* extra, int m0, int, int tid) const {
-    ChunkEntry* tab = reinterpret_cast<ChunkEntry*>(extra);
-    build_im2col_table(tab, ((K + kBK - 1) / kBK) * 8, K, Cin, ksz, W, tid);  // padded to whole stages
-    c.tab = tab;
-    const int m = m0 + tid;
-    // (plain locals, assigned to the context once at the end: conditional stores into the by-reference context were
-    //  observed to be dropped by nvcc 12.9 at -O3)
-    const bool valid = m < M;
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(in0);
-    int64_t anchor = 0;
-    int iy0 = 0, ix0 = 0;
-    if (valid) {
-      const int img = m / (OH * OW);
-      const int rem = m - img * (OH * OW);
-      const int oy = rem / OW, ox = rem - oy * OW;
-      int64_t li = img;
-      if (img >= n_img0) {
-        base = reinterpret_cast<const uint8_t*>(in1);
-        li = img - n_img0;
-      }
-      iy0 = oy * stride - pad_y;
-      ix0 = ox * stride - pad_x;
-      anchor = ((li * H + iy0) * W + ix0) * (int64_t)Cin;
-    }
-    c.valid = valid;
-    c.base = base;
-    c.anchor = anchor;
-    c.iy0 = iy0;
-    c.ix0 = ix0;
+  struct ECtx {};
+  __device__ void init_cta(uint8_t* extra, int ptid) const {
+    build_im2col_table(reinterpret_cast<ChunkEntry*>(extra), ((K + kBK - 1) / kBK) * 8, K, Cin, ksz, W, ptid, PT);
   }
+  __device__ void tile_producer(PCtx& c, uint8_t* extra, int m0, int, int, int ptid, int ti) const {
+    RowInfo* rows = reinterpret_cast<RowInfo*>(extra + kMaxChunks * sizeof(ChunkEntry)) + (ti & 1) * kBM;
+    if (ptid < kBM) rows[ptid] = conv_row_info(m0 + ptid, M, OH, OW, H, W, Cin, stride, pad_y, pad_x, n_img0);
+    c.tab = reinterpret_cast<const ChunkEntry*>(extra);
+    c.rows = rows;
+  }
+  __device__ void chunk_producer(PCtx&, uint8_t*, int, int, int) const {}
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = (K + kBK - 1) / kBK; }
-  __device__ void load_a(const Ctx& c, uint32_t stage, int kc, int tid) const {
+  __device__ void load_a(const PCtx& c, uint32_t stage, int kc, int ptid) const {
+    if (!IN_U8_) {
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      gather_im2col_chunk<IN_U8_>(stage + kmajor_off(tid, ch), c.base, c.anchor, c.valid, c.iy0, c.ix0, c.tab[kc * 8 + ch], H, W,
-                                  Cin, in0);
+      for (int i = 0; i < TASKS; ++i) {
+        const int t = ptid + i * PT;
+        const int ch = t & 7, r = t >> 3;
+        gather_chunk_bf16(stage + kmajor_off<true>(r, ch), in0, in1, c.rows[r], c.tab[kc * 8 + ch], H, W);
+      }
+    } else {
+      uint2 px[TASKS];
+#pragma unroll
+      for (int i = 0; i < TASKS; ++i) {
+        const int t = ptid + i * PT;
+        px[i] = fetch_chunk_u8(in0, in1, c.rows[t >> 3], c.tab[kc * 8 + (t & 7)], H, W);
+      }
+#pragma unroll
+      for (int i = 0; i < TASKS; ++i) {
+        const int t = ptid + i * PT;
+        store_chunk_u8(stage + kmajor_off<true>(t >> 3, t & 7), px[i]);
+      }
+    }
   }
-  __device__ void load_b(const Ctx&, uint32_t stage, int kc, int tid) const {
-    load_rows_mnmajor(w, Cout, kc * kBK, K, 0, Cout, stage, tid, BN / 8);
+  __device__ void load_b(const PCtx&, uint32_t stage, int kc, int ptid) const {
+    load_rows_mnmajor<BN / 8, PT, B_SW>(w, Cout, kc * kBK, K, 0, Cout, stage, ptid);
   }
-  __device__ void epilogue(const Ctx&, uint32_t tmem_lane_base, bool, int m0, int, int tid, int) const {
-    const int m = m0 + tid;
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
+    const int m = m0 + etid;
     float mean = 0.f, rs = 1.f;
     if (ln_g) {  // flax LayerNorm: var = max(0, E[x^2] - E[x]^2), eps = 1e-6
       float s = 0.f, s2 = 0.f;
@@ -282,131 +330,111 @@ struct ConvFwdTC {
 
 // --------------------------------------------------------------------------------------- conv weight gradient
 // dW[kc][co] (partial of split z) = sum_{pixels of the split} im2col(x)[pix][kc] dz[pix][co]
-// A' = the im2col rows taken MN-major (row index = reduction), B' = dz MN-major.
+// A' = the im2col rows taken MN-major (row index = reduction), B' = dz MN-major.  The 64 reduction rows (pixels) of
+// a chunk change every chunk, so their anchors are published per chunk (CHUNK_SYNC).
 template <int BN_, bool IN_U8_>
 struct ConvWgradTC {
-  static constexpr int BN = BN_, STAGES = 3, EXTRA_BYTES = 16 * (int)sizeof(ChunkEntry);
-  static constexpr bool A_MN = true, B_MN = true;
+  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = IN_U8_ ? 8 : 4;
+  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBK * 16 / PT;
+  static constexpr int EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry) + kRowInfoBytes;
+  static constexpr bool A_MN = true, B_MN = true, CHUNK_SYNC = true, B_SW = BN_ >= 64;
   const void* in;  // layer input of the rows with a backward pass
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, M, K;
   const bf16* dz;  // [M][Cout]
   float* part;     // [splits][K][Cout]
   int chunks_per_split;
-  struct Ctx {
-    const ChunkEntry* tab;  // the 16 column chunks of this CTA's 128-column tile
+  struct PCtx {
+    const ChunkEntry* tab;  // the 16 column chunks of this tile
+    const RowInfo* rows;    // the 64 pixel rows of the current chunk
+    int n0;
   };
-  __device__ void init(Ctx& c, uint8_t* extra, int m0, int, int tid) const {
-    ChunkEntry* tab = reinterpret_cast<ChunkEntry*>(extra);
-    if (tid < 16) {
-      const int k = m0 + 8 * tid;
-      ChunkEntry e;
-      if (k < K) {
-        const int c0 = k % Cin;
-        const int t = k / Cin;
-        const int kx = t % ksz, ky = t / ksz;
-        e.off = (ky * W + kx) * Cin + c0;
-        e.yx = (ky << 16) | kx;
-      } else {
-        e.off = 0;
-        e.yx = -1;
-      }
-      tab[tid] = e;
-    }
-    c.tab = tab;
+  struct ECtx {};
+  __device__ void init_cta(uint8_t* extra, int ptid) const {  // whole K axis, padded to whole 128-column tiles
+    build_im2col_table(reinterpret_cast<ChunkEntry*>(extra), ((K + kBM - 1) / kBM) * 16, K, Cin, ksz, W, ptid, PT);
   }
+  __device__ void tile_producer(PCtx& c, uint8_t* extra, int m0, int n0, int, int, int) const {
+    c.tab = reinterpret_cast<const ChunkEntry*>(extra) + m0 / 8;
+    c.n0 = n0;
+  }
+  __device__ void chunk_producer(PCtx& c, uint8_t* extra, int kc, int ptid, int j) const {
+    RowInfo* rows = reinterpret_cast<RowInfo*>(extra + kMaxChunks * sizeof(ChunkEntry)) + (j & 1) * kBM;
+    if (ptid < kBK) rows[ptid] = conv_row_info(kc * kBK + ptid, M, OH, OW, H, W, Cin, stride, pad_y, pad_x, 1 << 30);
+    c.rows = rows;
+  }
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
   __device__ void k_range(int split, int& b, int& e) const {
     const int total = (M + kBK - 1) / kBK;
     b = split * chunks_per_split;
     e = min(total, b + chunks_per_split);
-    if (e < b) e = b;
   }
-  __device__ void load_a(const Ctx& c, uint32_t stage, int kc, int tid) const {
-    const int kk = tid & 63, half = tid >> 6;
-    const int m = kc * kBK + kk;  // pixel row (reduction index)
-    const bool mv = m < M;
-    int iy0 = 0, ix0 = 0;
-    int64_t anchor = 0;
-    if (mv) {
-      const int img = m / (OH * OW);
-      const int rem = m - img * (OH * OW);
-      const int oy = rem / OW, ox = rem - oy * OW;
-      iy0 = oy * stride - pad_y;
-      ix0 = ox * stride - pad_x;
-      anchor = (((int64_t)img * H + iy0) * W + ix0) * (int64_t)Cin;
-    }
+  __device__ void load_a(const PCtx& c, uint32_t stage, int, int ptid) const {
+    if (!IN_U8_) {
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      const int ch = half * 8 + cc;  // 16-byte chunk of the MN (= im2col column) axis
-      gather_im2col_chunk<IN_U8_>(stage + mnmajor_off(kk, ch), reinterpret_cast<const uint8_t*>(in), anchor, mv, iy0, ix0,
-                                  c.tab[ch], H, W, Cin, in);
+      for (int i = 0; i < TASKS; ++i) {
+        const int t = ptid + i * PT;
+        const int ch = t & 15, kk = t >> 4;
+        gather_chunk_bf16(stage + mnmajor_off<true>(kk, ch), in, in, c.rows[kk], c.tab[ch], H, W);
+      }
+    } else {
+      uint2 px[TASKS];
+#pragma unroll
+      for (int i = 0; i < TASKS; ++i) {
+        const int t = ptid + i * PT;
+        px[i] = fetch_chunk_u8(in, in, c.rows[t >> 4], c.tab[t & 15], H, W);
+      }
+#pragma unroll
+      for (int i = 0; i < TASKS; ++i) {
+        const int t = ptid + i * PT;
+        store_chunk_u8(stage + mnmajor_off<true>(t >> 4, t & 15), px[i]);
+      }
     }
   }
-  __device__ void load_b(const Ctx&, uint32_t stage, int kc, int tid) const {
-    load_rows_mnmajor(dz, Cout, kc * kBK, M, blockIdx.y * BN, Cout, stage, tid, BN / 8);
+  __device__ void load_b(const PCtx& c, uint32_t stage, int kc, int ptid) const {
+    load_rows_mnmajor<BN / 8, PT, B_SW>(dz, Cout, kc * kBK, M, c.n0, Cout, stage, ptid);
   }
-  __device__ void epilogue(const Ctx&, uint32_t tmem_lane_base, bool has_acc, int m0, int n0, int tid, int split) const {
-    const int k = m0 + tid;
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
+    const int k = m0 + etid;
     float* dst = part + ((int64_t)split * K + (k < K ? k : 0)) * Cout;
-    store_rows_f32<BN>(tmem_lane_base, has_acc, dst, Cout, k < K, n0, Cout);
+    store_rows_f32<BN>(tmem_lane_base, dst, k < K, n0, Cout);
   }
 };
 
 // ---------------------------------------------------------------------------------------- conv input gradient
 // dX[pix_in][c] = sum_{tap, co} dz[pix_out(pix_in, tap)][co] W[tap][c][co]; rows grouped by stride parity class
-// (blockIdx.z) so that only taps that hit the pixel are multiplied.  A gathered K-major, B = W K-major per tap.
-// Table entry per chunk k = (tap, co0): off = -(ty*OW + tx)*Cout + co0 (relative to the row's anchor output pixel),
-// yx = (ty << 16) | tx, or -1 when the tap does not exist for this parity class.  A second table holds the weight
-// offsets ((ky*ksz + kx)*Cin)*Cout + co0.
+// (tile z) so that only taps that hit the pixel are multiplied.  A gathered K-major, B = W K-major per tap.
+// Table entry per (class, chunk k = (tap, co0)): off = -(ty*OW + tx)*Cout + co0 (relative to the row's anchor output
+// pixel), yx = (ty << 16) | tx, or -1 when the tap does not exist for this class; wtab = weight offset of the chunk.
 template <int BN_>
 struct ConvDgradTC {
-  static constexpr int BN = BN_, STAGES = 3, EXTRA_BYTES = kMaxChunks * (int)(sizeof(ChunkEntry) + sizeof(int));
-  static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4;
+  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT;
+  static constexpr int EXTRA_BYTES = kMaxChunks * (int)(sizeof(ChunkEntry) + sizeof(int)) + kRowInfoBytes;
+  static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, B_SW = BN_ >= 64;
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, n_img, taps, Kd;
   const bf16* dz;  // [n_img*OH*OW][Cout]
   const bf16* w;   // [ksz][ksz][Cin][Cout]
   float* dx;       // [n_img*H*W][Cin]
-  struct Ctx {
-    int img, oy, ox, pix;
-    int64_t anchor;  // element offset of dz[(img, oy, ox, 0)]
+  struct PCtx {
+    int n0;
     const ChunkEntry* tab;
     const int* wtab;
+    const RowInfo* rows;  // anchor = element offset of dz[(img, oy, ox, 0)], (y0, x0) = (oy, ox)
   };
-  __device__ void init(Ctx& c, uint8_t* extra, int m0, int, int tid) const {
+  struct ECtx {
+    int pix;
+    bool valid;
+  };
+  __device__ int chunks_padded() const { return ((Kd + kBK - 1) / kBK) * 8; }
+  // input pixel m of parity class cls -> (valid, output anchor (oy, ox), input pixel index)
+  __device__ void decode_row(int m, int cls, int& img, int& oy, int& ox, int& pix) const {
     const int s = stride;
-    const int ry = blockIdx.z / s, rx = blockIdx.z % s;
-    ChunkEntry* tab = reinterpret_cast<ChunkEntry*>(extra);
-    int* wtab = reinterpret_cast<int*>(extra + kMaxChunks * sizeof(ChunkEntry));
-    const int n_chunks = ((Kd + kBK - 1) / kBK) * 8;  // padded to whole stages
-    for (int ch = tid; ch < n_chunks; ch += kThreads) {
-      const int k = 8 * ch;
-      const int co = k % Cout;
-      const int t = k / Cout;
-      const int tx = t % taps, ty = t / taps;
-      const int ky = ry + s * ty, kx = rx + s * tx;
-      ChunkEntry e;
-      if (k < Kd && ky < ksz && kx < ksz) {
-        e.off = -(ty * OW + tx) * Cout + co;
-        e.yx = (ty << 16) | tx;
-        wtab[ch] = ((ky * ksz + kx) * Cin) * Cout + co;
-      } else {
-        e.off = 0;
-        e.yx = -1;
-        wtab[ch] = -1;
-      }
-      tab[ch] = e;
-    }
-    c.tab = tab;
-    c.wtab = wtab;
+    const int ry = cls / s, rx = cls % s;
     const int iy_first = ((ry - pad_y) % s + s) % s, ix_first = ((rx - pad_x) % s + s) % s;
     const int ny = iy_first < H ? (H - iy_first + s - 1) / s : 0;
     const int nx = ix_first < W ? (W - ix_first + s - 1) / s : 0;
-    const int rows = n_img * ny * nx;
-    const int m = m0 + tid;
-    // (plain locals, assigned to the context once at the end: conditional stores into the by-reference context were
-    //  observed to be dropped by nvcc 12.9 at -O3)
-    int img = -1, oy = 0, ox = 0, pix = 0;
-    int64_t anchor = 0;
-    if (m < rows) {
+    img = -1;
+    oy = ox = pix = 0;
+    if (m < n_img * ny * nx) {
       img = m / (ny * nx);
       const int rem = m - img * (ny * nx);
       const int iyc = rem / nx, ixc = rem - iyc * nx;
@@ -414,39 +442,83 @@ struct ConvDgradTC {
       oy = (iy + pad_y - ry) / s;
       ox = (ix + pad_x - rx) / s;
       pix = (img * H + iy) * W + ix;
-      anchor = (((int64_t)img * OH + oy) * OW + ox) * (int64_t)Cout;
     }
-    c.img = img;
-    c.oy = oy;
-    c.ox = ox;
-    c.pix = pix;
-    c.anchor = anchor;
+  }
+  __device__ void init_cta(uint8_t* extra, int ptid) const {
+    ChunkEntry* tab = reinterpret_cast<ChunkEntry*>(extra);
+    int* wtab = reinterpret_cast<int*>(extra + kMaxChunks * sizeof(ChunkEntry));
+    const int s = stride, n_chunks = chunks_padded();
+    for (int i = ptid; i < s * s * n_chunks; i += PT) {
+      const int cls = i / n_chunks, ch = i - cls * n_chunks;
+      const int ry = cls / s, rx = cls % s;
+      const int k = 8 * ch;
+      const int co = k % Cout;
+      const int t = k / Cout;
+      const int tx = t % taps, ty = t / taps;
+      const int ky = ry + s * ty, kx = rx + s * tx;
+      ChunkEntry e;
+      int wo = -1;
+      if (k < Kd && ky < ksz && kx < ksz) {
+        e.off = -(ty * OW + tx) * Cout + co;
+        e.yx = (ty << 16) | tx;
+        wo = ((ky * ksz + kx) * Cin) * Cout + co;
+      } else {
+        e.off = 0;
+        e.yx = -1;
+      }
+      tab[i] = e;
+      wtab[i] = wo;
+    }
+  }
+  __device__ void tile_producer(PCtx& c, uint8_t* extra, int m0, int n0, int cls, int ptid, int ti) const {
+    RowInfo* rows = reinterpret_cast<RowInfo*>(extra + kMaxChunks * (sizeof(ChunkEntry) + sizeof(int))) + (ti & 1) * kBM;
+    if (ptid < kBM) {
+      int img, oy, ox, pix;
+      decode_row(m0 + ptid, cls, img, oy, ox, pix);
+      RowInfo ri;
+      ri.anchor = img >= 0 ? (((int64_t)img * OH + oy) * OW + ox) * (int64_t)Cout : 0;
+      ri.y0 = img >= 0 ? oy : kInvalidRow;
+      ri.x0 = (short)ox;
+      ri.second = 0;
+      rows[ptid] = ri;
+    }
+    c.n0 = n0;
+    c.tab = reinterpret_cast<const ChunkEntry*>(extra) + cls * chunks_padded();
+    c.wtab = reinterpret_cast<const int*>(extra + kMaxChunks * sizeof(ChunkEntry)) + cls * chunks_padded();
+    c.rows = rows;
+  }
+  __device__ void chunk_producer(PCtx&, uint8_t*, int, int, int) const {}
+  __device__ void tile_epilogue(ECtx& e, int m0, int, int cls, int etid) const {
+    int img, oy, ox, pix;
+    decode_row(m0 + etid, cls, img, oy, ox, pix);
+    e.pix = pix;
+    e.valid = img >= 0;
   }
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = (Kd + kBK - 1) / kBK; }
-  __device__ void load_a(const Ctx& c, uint32_t stage, int kc, int tid) const {
+  __device__ void load_a(const PCtx& c, uint32_t stage, int kc, int ptid) const {
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int i = 0; i < TASKS; ++i) {
+      const int t = ptid + i * PT;
+      const int ch = t & 7, r = t >> 3;
+      const RowInfo ri = c.rows[r];
       const ChunkEntry e = c.tab[kc * 8 + ch];
-      const int oy = c.oy - (e.yx >> 16), ox = c.ox - (e.yx & 0xffff);
-      const bool v = c.img >= 0 && e.yx >= 0 && (unsigned)oy < (unsigned)OH && (unsigned)ox < (unsigned)OW;
-      cp_async16(stage + kmajor_off(tid, ch), v ? dz + (c.anchor + e.off) : dz, v);
+      const int oy = ri.y0 - (e.yx >> 16), ox = ri.x0 - (e.yx & 0xffff);
+      const bool v = e.yx >= 0 && (unsigned)oy < (unsigned)OH && (unsigned)ox < (unsigned)OW;
+      cp_async16(stage + kmajor_off<true>(r, ch), v ? dz + (ri.anchor + e.off) : dz, v);
     }
   }
-  __device__ void load_b(const Ctx& c, uint32_t stage, int kc, int tid) const {
-    const int n0 = blockIdx.y * BN;
-    for (int r = tid; r < BN; r += kThreads) {
-      const int cin = n0 + r;
+  __device__ void load_b(const PCtx& c, uint32_t stage, int kc, int ptid) const {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const int wo = c.wtab[kc * 8 + ch];
-        const bool v = cin < Cin && wo >= 0;
-        cp_async16(stage + kmajor_off(r, ch), v ? w + wo + (int64_t)cin * Cout : w, v);
-      }
+    for (int t = ptid; t < BN * 8; t += PT) {
+      const int ch = t & 7, r = t >> 3;
+      const int cin = c.n0 + r;
+      const int wo = c.wtab[kc * 8 + ch];
+      const bool v = cin < Cin && wo >= 0;
+      cp_async16(stage + kmajor_off<B_SW>(r, ch), v ? w + wo + (int64_t)cin * Cout : w, v);
     }
   }
-  __device__ void epilogue(const Ctx& c, uint32_t tmem_lane_base, bool has_acc, int, int n0, int, int) const {
-    float* dst = dx + (int64_t)c.pix * Cin;
-    store_rows_f32<BN>(tmem_lane_base, has_acc, dst, Cin, c.img >= 0, n0, Cin);
+  __device__ void epilogue(const ECtx& e, uint32_t tmem_lane_base, int, int n0, int, int) const {
+    store_rows_f32<BN>(tmem_lane_base, dx + (int64_t)e.pix * Cin, e.valid, n0, Cin);
   }
 };
 
