@@ -240,9 +240,8 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
       ISDQN_PROF(s, "ln_relu_bwd");
       if (ln_bwd_use_warp(P.out_dim)) {
-        ln_relu_bwd_warp_kernel<<<w.col_ctas[l - 1], 256, 0, s>>>(dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]),
-                                                                  g_, b_, wsp(ws, w.act[l - 1]), rows_p, P.out_dim,
-                                                                  wsp(ws, w.colpart[l - 1]));
+        launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
+                                wsp(ws, w.act[l - 1]), rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]), nullptr, nullptr);
       } else {
         ln_relu_bwd_block_kernel<<<w.col_ctas[l - 1], kRowThreads, 0, s>>>(
             dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, wsp(ws, w.act[l - 1]), rows_p, P.out_dim,

@@ -514,14 +514,15 @@ dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_
 //   mask = out > 0 ; dy = d*mask ; g = dy*gamma ; dz = rstd * (g - mean(g) - xhat*mean(g*xhat))
 // Column partial sums per CTA (fixed order => deterministic): [0]=sum dz (dbias) [1]=sum dy*xhat (dgamma)
 // [2]=sum dy (dbeta).  Without LayerNorm: dz = dy, only [0] is meaningful.
-// Variant A: C <= 256, one warp per row.
-static __global__ void __launch_bounds__(256)
+// Variant A: C <= 256, one warp per row, R rows in flight per warp (all loads of the R rows are issued before any
+// reduction: the kernel is pure streaming and needs the memory-level parallelism).
+template <int MAXJ, int R>
+__global__ void __launch_bounds__(256)
 ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
                         const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                         const float* __restrict__ act, int rows, int C, float* __restrict__ colpart,
-                        __nv_bfloat16* __restrict__ dz16 = nullptr, const __nv_bfloat16* __restrict__ act16 = nullptr) {
-  constexpr int MAXJ = 8;
-  __shared__ float sm[8][3][256];
+                        __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16* __restrict__ act16) {
+  __shared__ float sm[8][3][32 * MAXJ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float c0[MAXJ], c1[MAXJ], c2[MAXJ], gam[MAXJ], bet[MAXJ];
 #pragma unroll
@@ -532,44 +533,59 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
     bet[j] = (ln_g && n < C) ? ln_b[n] : 0.f;
   }
   const float inv_c = 1.0f / (float)C;
-  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
-    float dy[MAXJ], xh[MAXJ];
-    float sg = 0.f, sgx = 0.f;
+  for (int r0 = (blockIdx.x * 8 + warp) * R; r0 < rows; r0 += gridDim.x * 8 * R) {
+    float dv[R][MAXJ], xh[R][MAXJ], rs[R];
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      const int n = lane + 32 * j;
-      dy[j] = xh[j] = 0.f;
-      if (n < C) {
-        const int64_t idx = (int64_t)r * C + n;
-        const float dv = d[idx];
-        if (ln_g) {
-          xh[j] = xhat[idx];
-          dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;
-          const float g = dy[j] * gam[j];
-          sg += g;
-          sgx += g * xh[j];
-        } else {
-          const float a = act16 ? __bfloat162float(act16[idx]) : act[idx];
-          dy[j] = a > 0.f ? dv : 0.f;
+    for (int q = 0; q < R; ++q) {
+      const int r = r0 + q;
+      rs[q] = (ln_g && r < rows) ? rstd[r] : 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int n = lane + 32 * j;
+        dv[q][j] = xh[q][j] = 0.f;
+        if (r < rows && n < C) {
+          const int64_t idx = (int64_t)r * C + n;
+          dv[q][j] = d[idx];
+          if (ln_g) xh[q][j] = xhat[idx];
+          else xh[q][j] = act16 ? __bfloat162float(act16[idx]) : act[idx];  // (post-ReLU output: only its sign is used)
         }
       }
     }
-    float rs = 0.f, mg = 0.f, mgx = 0.f;
-    if (ln_g) {
-      mg = warp_sum(sg) * inv_c;
-      mgx = warp_sum(sgx) * inv_c;
-      rs = rstd[r];
-    }
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      const int n = lane + 32 * j;
-      if (n < C) {
-        const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
-        d[(int64_t)r * C + n] = dz;
-        if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
-        c0[j] += dz;
-        c1[j] += dy[j] * xh[j];
-        c2[j] += dy[j];
+    for (int q = 0; q < R; ++q) {
+      const int r = r0 + q;
+      float dy[MAXJ];
+      float sg = 0.f, sgx = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        if (ln_g) {
+          dy[j] = (xh[q][j] * gam[j] + bet[j] > 0.f) ? dv[q][j] : 0.f;
+          const float g = dy[j] * gam[j];
+          sg += g;
+          sgx += g * xh[q][j];
+        } else {
+          dy[j] = xh[q][j] > 0.f ? dv[q][j] : 0.f;
+          xh[q][j] = 0.f;
+        }
+      }
+      float mg = 0.f, mgx = 0.f;
+      if (ln_g) {
+        mg = warp_sum(sg) * inv_c;
+        mgx = warp_sum(sgx) * inv_c;
+      }
+      if (r < rows) {
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+          const int n = lane + 32 * j;
+          if (n < C) {
+            const float dz = ln_g ? rs[q] * (dy[j] * gam[j] - mg - xh[q][j] * mgx) : dy[j];
+            d[(int64_t)r * C + n] = dz;
+            if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
+            c0[j] += dz;
+            c1[j] += dy[j] * xh[q][j];
+            c2[j] += dy[j];
+          }
+        }
       }
     }
   }
@@ -587,6 +603,16 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
     for (int w = 0; w < 8; ++w) t += sm[w][which][n];
     colpart[((int64_t)blockIdx.x * 3 + which) * C + n] = t;
   }
+}
+
+// host-side dispatch over the channel count (C <= 256)
+static inline void launch_ln_relu_bwd_warp(int ctas, cudaStream_t s, float* d, const float* xhat, const float* rstd,
+                                           const float* ln_g, const float* ln_b, const float* act, int rows, int C,
+                                           float* colpart, __nv_bfloat16* dz16, const __nv_bfloat16* act16) {
+  if (C <= 32) ln_relu_bwd_warp_kernel<1, 4><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
+  else if (C <= 64) ln_relu_bwd_warp_kernel<2, 4><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
+  else if (C <= 128) ln_relu_bwd_warp_kernel<4, 2><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
+  else ln_relu_bwd_warp_kernel<8, 1><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
 }
 
 // Variant B: any C <= 2048 (dense layers), one CTA walks its rows, thread t owns columns t, t+256, ...

@@ -141,11 +141,23 @@ static inline int conv_wgrad_splits(int M, int K, int N) {
   return s;
 }
 
+// weight gradient of the (fp32) head layer on the tensor-core path: split the batch axis once it is long
+static inline int head_wgrad_splits(int B, int K, int N) {
+  const int tiles = ceil_div(K, 64) * ceil_div(N, 64);
+  int s = (2 * kNumSMs) / tiles;
+  const int max_by_b = B / 128 > 0 ? B / 128 : 1;
+  if (s > max_by_b) s = max_by_b;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
+}
+
 // LN/ReLU backward: <= 256 channels -> one warp per row (8 rows per CTA pass); wider -> one CTA per row
 static inline bool ln_bwd_use_warp(int C) { return C <= 256; }
 static inline int ln_bwd_ctas(int rows, int C) {
   int c = ln_bwd_use_warp(C) ? ceil_div(rows, 64) : rows;
-  if (c > 2 * kNumSMs) c = 2 * kNumSMs;
+  const int cap = ln_bwd_use_warp(C) ? 8 * kNumSMs : 2 * kNumSMs;  // streaming kernel: many resident warps
+  if (c > cap) c = cap;
   if (c < 1) c = 1;
   return c;
 }
@@ -179,6 +191,9 @@ static inline void carve_workspace(const Plan& p, int rows, int B, Workspace* w)
       const Layer& L = p.L[l];
       if (L.type == 0) {
         w->wsplits[l] = conv_wgrad_splits(B * L.pix, L.in_dim, L.out_dim);
+        w->wpart[l] = take((int64_t)w->wsplits[l] * L.in_dim * L.out_dim);
+      } else if (l == p.n_layers - 1 && head_wgrad_splits(B, L.in_dim, L.out_dim) > 1) {
+        w->wsplits[l] = head_wgrad_splits(B, L.in_dim, L.out_dim);  // (used by the tensor-core path only)
         w->wpart[l] = take((int64_t)w->wsplits[l] * L.in_dim * L.out_dim);
       } else {
         w->wsplits[l] = 1;

@@ -35,6 +35,8 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     ISDQN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_gemm_kernel<P>, threads, smem));
     const int by_tmem = 512 / tc::tmem_cols_for(2 * P::BN);  // every resident CTA owns two accumulators in TMEM
@@ -144,6 +146,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
     p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
     p.ln_b = L.has_ln ? params + L.beta_off : nullptr;                                                 \
     p.relu = L.relu; p.out = out; p.xhat = xhat; p.rstd = rstd; p.m_train = m_train;                   \
+    p.acc_scale = U8 ? 1.0f / 255.0f : 1.0f;                                                           \
     return launch_tc(p, ceil_div(p.M, tc::kBM), 1, 1, s, "tc_conv_fwd");                               \
   }
   switch (L.out_dim) {
@@ -168,6 +171,7 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
     p.in = in; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;     \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
     p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
+    p.acc_scale = U8 ? 1.0f / 255.0f : 1.0f;                                                           \
     return launch_tc(p, ceil_div(L.in_dim, tc::kBM), 1, *real_splits, s, "tc_conv_wgrad");             \
   }
   switch (L.out_dim) {
@@ -202,7 +206,7 @@ int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* d
 }
 
 int launch_simt_gemm(const GemmArgs& g, cudaStream_t s, const char* tag) {
-  dim3 grid(ceil_div(g.M, 64), ceil_div(g.N, 64), 1);
+  dim3 grid(ceil_div(g.M, 64), ceil_div(g.N, 64), g.split_stride ? ceil_div(g.K, g.k_per_split) : 1);
   ISDQN_PROF(s, tag);
   const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
   if (a_kfast && b_nfast) gemm_strided_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g);
@@ -327,6 +331,13 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       g.B = dz32; g.sbk = L.out_dim; g.sbn = 1;
       g.C = grads + L.w_off; g.ldc = L.out_dim; g.split_stride = 0;
       g.M = L.in_dim; g.N = L.out_dim; g.K = B; g.k_per_split = ceil_div(B, kBK) * kBK; g.bias = nullptr;
+      if (w.wsplits[l] > 1) {  // long batch axis: split it over CTAs, partial sums folded by reduce_segments
+        g.k_per_split = ceil_div(ceil_div(B, w.wsplits[l]), kBK) * kBK;
+        const int real_splits = ceil_div(B, (int)g.k_per_split);
+        g.C = wsp(ws, w.wpart[l]);
+        g.split_stride = (int64_t)L.in_dim * L.out_dim;
+        add_seg(g.C, grads + L.w_off, g.split_stride, L.in_dim * L.out_dim, real_splits);
+      }
       rc = launch_simt_gemm(g, s, "head_wgrad_gemm");
     } else if (L.type == 1) {
       rc = launch_gemm_tc<true, true>(w16(wt, t.act16[l - 1]), L.in_dim, dz16, L.out_dim, grads + L.w_off, L.out_dim, 0,
@@ -374,10 +385,9 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       // the ReLU mask of a layer without LayerNorm needs its post-activation output: fp32 for Dense, bf16 for conv
       ISDQN_PROF(s, "ln_relu_bwd");
       if (ln_bwd_use_warp(P.out_dim)) {
-        ln_relu_bwd_warp_kernel<<<w.col_ctas[l - 1], 256, 0, s>>>(dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
-                                                                  P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p,
-                                                                  P.out_dim, wsp(ws, w.colpart[l - 1]), dz16_prev,
-                                                                  P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr);
+        launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
+                                P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]),
+                                dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr);
       } else {
         ln_relu_bwd_block_kernel<<<w.col_ctas[l - 1], kRowThreads, 0, s>>>(
             dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p,

@@ -27,9 +27,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// x/255 (architectures/dqn.py:51) for a uint8 pair -> packed bf16 pair
-__device__ __forceinline__ uint32_t norm_pair_bf16(uint32_t b0, uint32_t b1) {
-  return pack_bf16(__fmul_rn((float)b0, 1.0f / 255.0f), __fmul_rn((float)b1, 1.0f / 255.0f));
+// A uint8 pair -> packed bf16 pair holding the INTEGER values: 0..255 need 8 significant bits, bf16 has 8, so the
+// conversion is exact (the high half of the fp32 encoding); the x/255 of architectures/dqn.py:51 is applied to the
+// fp32 accumulator in the epilogue instead (acc_scale) — fewer instructions and no input rounding at all.
+__device__ __forceinline__ uint32_t int_pair_bf16(uint32_t b0, uint32_t b1) {
+  return __byte_perm(__float_as_uint((float)b0), __float_as_uint((float)b1), 0x7632);
 }
 
 struct ChunkEntry {
@@ -74,11 +76,15 @@ __device__ __forceinline__ void load_rows_mnmajor(const bf16* __restrict__ src, 
 // plain fp32 store of the accumulator tile: thread t owns row t
 template <int BN>
 __device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, float* __restrict__ dst, bool row_valid, int n0,
-                                               int n_end) {
+                                               int n_end, float scale = 1.0f) {
 #pragma unroll 1
   for (int cb = 0; cb < BN / 32; ++cb) {
     float v[32];
     tmem_ld32(tmem_lane_base + cb * 32, v);
+    if (scale != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= scale;
+    }
     if (row_valid) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -211,8 +217,8 @@ __device__ __forceinline__ uint2 fetch_chunk_u8(const void* in0, const void* in1
   return r;
 }
 __device__ __forceinline__ void store_chunk_u8(uint32_t dst, const uint2 p) {
-  st_shared_v4(dst, norm_pair_bf16(p.x & 0xff, (p.x >> 8) & 0xff), norm_pair_bf16((p.x >> 16) & 0xff, p.x >> 24),
-               norm_pair_bf16(p.y & 0xff, (p.y >> 8) & 0xff), norm_pair_bf16((p.y >> 16) & 0xff, p.y >> 24));
+  st_shared_v4(dst, int_pair_bf16(p.x & 0xff, (p.x >> 8) & 0xff), int_pair_bf16((p.x >> 16) & 0xff, p.x >> 24),
+               int_pair_bf16(p.y & 0xff, (p.y >> 8) & 0xff), int_pair_bf16((p.y >> 16) & 0xff, p.y >> 24));
 }
 
 // ------------------------------------------------------------------------------------------------ conv forward
@@ -229,6 +235,7 @@ struct ConvFwdTC {
   const bf16* w;  // [K][Cout]
   const float* bias; const float* ln_g; const float* ln_b; int relu;
   bf16* out; float* xhat; float* rstd; int m_train;
+  float acc_scale;  // 1/255 when the A operand holds raw uint8 pixel values, else 1
   struct PCtx {
     const ChunkEntry* tab;
     const RowInfo* rows;
@@ -282,7 +289,7 @@ struct ConvFwdTC {
         tmem_ld32(tmem_lane_base + cb * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float z = v[i] + __ldg(bias + cb * 32 + i);
+          const float z = fmaf(v[i], acc_scale, __ldg(bias + cb * 32 + i));
           s += z;
           s2 += z * z;
         }
@@ -303,7 +310,7 @@ struct ConvFwdTC {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int n = cb * 32 + i + j;
-          float z = v[i + j] + __ldg(bias + n);
+          float z = fmaf(v[i + j], acc_scale, __ldg(bias + n));
           if (ln_g) {
             z = (z - mean) * rs;
             v[i + j] = z;  // normalised value, saved for the backward pass
@@ -343,6 +350,7 @@ struct ConvWgradTC {
   const bf16* dz;  // [M][Cout]
   float* part;     // [splits][K][Cout]
   int chunks_per_split;
+  float acc_scale;  // 1/255 when the im2col operand holds raw uint8 pixel values, else 1
   struct PCtx {
     const ChunkEntry* tab;  // the 16 column chunks of this tile
     const RowInfo* rows;    // the 64 pixel rows of the current chunk
@@ -395,7 +403,7 @@ struct ConvWgradTC {
   __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
     const int k = m0 + etid;
     float* dst = part + ((int64_t)split * K + (k < K ? k : 0)) * Cout;
-    store_rows_f32<BN>(tmem_lane_base, dst, k < K, n0, Cout);
+    store_rows_f32<BN>(tmem_lane_base, dst, k < K, n0, Cout, acc_scale);
   }
 };
 

@@ -137,7 +137,9 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
     ln = 0
     d = 0
     if arch == "cnn":
-        x = rnd(x.to(dtype) / 255.0)
+        # (the CUDA bf16 path feeds the exact integer pixel values to the tensor cores and applies 1/255 to the fp32
+        #  accumulator, so the normalised input carries no bf16 rounding)
+        x = x.to(dtype) / 255.0
         for i, (k, s) in enumerate(CONV_GEOMETRY):
             w = rnd(params[f"Conv_{i}"]["kernel"])  # HWIO
             _, plo_h, phi_h = same_padding(x.shape[1], k, s)

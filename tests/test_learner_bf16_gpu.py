@@ -92,6 +92,12 @@ def test_batch_not_multiple_of_tile_bf16():
     check_bf16(dict(ATARI, layer_norm=False), 16, seed=5, n_steps=1)
 
 
+def test_large_batch_bf16():
+    # batch 300: split batch axis in the head weight gradient (2 splits, ragged), many-row LayerNorm backward with a
+    # ragged tail, several M tiles in every tensor-core problem
+    check_bf16(ATARI, 300, seed=7, n_steps=1)
+
+
 def test_ineligible_network_is_refused():
     from isdqn_b200 import _lib
 
