@@ -254,18 +254,28 @@ def run_ours(args, rank, world, local_rank):
         # ---- e2e: host batch -> H2D -> step -> D2H of the losses, through the reference-facing call
         pool = [rb.sample() for _ in range(8)]
         h2d = sum(np.asarray(x).nbytes for x in pool[0])
-        for i in range(max(3, args.warmup // 2)):
-            agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])[2].cpu()
+        # 1-deep software pipeline, as a training loop runs it: step i+1 (host copy into pinned staging, H2D on the copy
+        # engine, graph launch) is enqueued before step i's losses are read back; every step's H2D and D2H happen
+        # inside the timed region.
+        def e2e_loop(n):
+            pending, host = None, None
+            for i in range(n):
+                agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])
+                handle = agent.losses_to_host_async()
+                if pending is not None:
+                    host = pending.get()
+                pending = handle
+            return pending.get()
+
+        e2e_loop(max(3, args.warmup // 2))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            _, _, losses = agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])
-            losses_host = losses.cpu()
+        losses_host = e2e_loop(args.steps)
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
-        d2h = losses_host.numel() * 4
+        d2h = losses_host.size * 4
         # ---- replay throughput shape: 2048 batches of 32 per launch (sampler + gather only)
         n_big = 2048 * BATCH
         for _ in range(3):
@@ -332,7 +342,9 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(cap),
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "pipeline": "host numpy batch -> pinned slot -> H2D on the copy engine (2 slots) -> step; the losses of "
+                            "step i are read on the host after step i+1 is enqueued"},
         "gpu_launches": launches * args.steps,
         "gpu_launches_per_step": launches,
         "roofline": roofline,

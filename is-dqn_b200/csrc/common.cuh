@@ -37,6 +37,38 @@ void profile_mark(cudaStream_t s, const char* name);
     if (::isdqn::g_profile_on) ::isdqn::profile_mark(stream, name); \
   } while (0)
 
+// Programmatic dependent launch (PDL).  The kernels of one learner step form a chain of short dependent launches; with
+// the launch attribute below the NEXT kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM
+// allocation) while the current kernel still executes, and block in pdl_wait() until it has completed and its memory
+// is visible.  Every kernel launched through launch_pdl calls pdl_sync() (or trigger + wait) before it touches global
+// memory, so the chain keeps full stream-order semantics (completion is transitive: a grid cannot complete before
+// the grids it waited on).  A kernel that allocates TMEM triggers only AFTER its allocation (a dependent that grabbed
+// the columns first would wait on a grid that waits on it).  Opt-in with ISDQN_PDL=1 (measured slower at batch 32:
+// early-resident dependents compete with the running kernel); the instructions are no-ops without the attribute.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
   return (a + b - 1) / b;

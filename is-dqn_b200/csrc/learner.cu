@@ -240,8 +240,8 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
       ISDQN_PROF(s, "ln_relu_bwd");
       if (ln_bwd_use_warp(P.out_dim)) {
-        launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
-                                wsp(ws, w.act[l - 1]), rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]), nullptr, nullptr);
+        ISDQN_CUDA_CHECK(launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
+                                wsp(ws, w.act[l - 1]), rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]), nullptr, nullptr));
       } else {
         ln_relu_bwd_block_kernel<<<w.col_ctas[l - 1], kRowThreads, 0, s>>>(
             dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, wsp(ws, w.act[l - 1]), rows_p, P.out_dim,
@@ -371,8 +371,8 @@ int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float*
   int64_t grid = ceil_div<int64_t>(n4, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   ISDQN_PROF(as_stream(stream), "adam");
-  adam_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n4,
-                                                             reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16));
+  ISDQN_CUDA_CHECK(launch_pdl(adam_kernel, dim3((unsigned)grid), dim3(256), 0, as_stream(stream), d_params, d_grads, d_mu,
+                              d_nu, d_count, lr, b1, b2, eps, n4, reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16)));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

@@ -392,6 +392,7 @@ struct GemmArgs {
 
 template <bool A_KFAST, bool B_NFAST>
 __global__ void __launch_bounds__(kGemmThreads) gemm_strided_kernel(const GemmArgs g) {
+  pdl_sync();
   constexpr int BM = 64, BN = 64, TN = 8;
   typedef TileCfg<BM, BN, TN> Cfg;
   __shared__ __align__(16) float As[kBK][BM + 4];
@@ -461,6 +462,7 @@ dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_
                       const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                       int relu, float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd,
                       int rows_train, __nv_bfloat16* __restrict__ out16 = nullptr) {
+  pdl_sync();
   __shared__ float red[kRowThreads / 32];
   const int r = blockIdx.x;
   float z[kRowMaxPerThread];
@@ -522,6 +524,7 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
                         const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                         const float* __restrict__ act, int rows, int C, float* __restrict__ colpart,
                         __nv_bfloat16* __restrict__ dz16, const __nv_bfloat16* __restrict__ act16) {
+  pdl_sync();
   __shared__ float sm[8][3][32 * MAXJ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float c0[MAXJ], c1[MAXJ], c2[MAXJ], gam[MAXJ], bet[MAXJ];
@@ -606,13 +609,17 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
 }
 
 // host-side dispatch over the channel count (C <= 256)
-static inline void launch_ln_relu_bwd_warp(int ctas, cudaStream_t s, float* d, const float* xhat, const float* rstd,
-                                           const float* ln_g, const float* ln_b, const float* act, int rows, int C,
-                                           float* colpart, __nv_bfloat16* dz16, const __nv_bfloat16* act16) {
-  if (C <= 32) ln_relu_bwd_warp_kernel<1, 4><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
-  else if (C <= 64) ln_relu_bwd_warp_kernel<2, 4><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
-  else if (C <= 128) ln_relu_bwd_warp_kernel<4, 2><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
-  else ln_relu_bwd_warp_kernel<8, 1><<<ctas, 256, 0, s>>>(d, xhat, rstd, ln_g, ln_b, act, rows, C, colpart, dz16, act16);
+static inline cudaError_t launch_ln_relu_bwd_warp(int ctas, cudaStream_t s, float* d, const float* xhat, const float* rstd,
+                                                  const float* ln_g, const float* ln_b, const float* act, int rows, int C,
+                                                  float* colpart, __nv_bfloat16* dz16, const __nv_bfloat16* act16) {
+#define ISDQN_LN_BWD(MAXJ, R)                                                                                          \
+  return launch_pdl((ln_relu_bwd_warp_kernel<MAXJ, R>), dim3(ctas), dim3(256), 0, s, d, xhat, rstd, ln_g, ln_b, act, rows, \
+                    C, colpart, dz16, act16)
+  if (C <= 32) ISDQN_LN_BWD(1, 4);
+  if (C <= 64) ISDQN_LN_BWD(2, 4);
+  if (C <= 128) ISDQN_LN_BWD(4, 2);
+  ISDQN_LN_BWD(8, 1);
+#undef ISDQN_LN_BWD
 }
 
 // Variant B: any C <= 2048 (dense layers), one CTA walks its rows, thread t owns columns t, t+256, ...
@@ -621,6 +628,7 @@ ln_relu_bwd_block_kernel(float* __restrict__ d, const float* __restrict__ xhat, 
                          const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                          const float* __restrict__ act, int rows, int C, float* __restrict__ colpart,
                          __nv_bfloat16* __restrict__ dz16 = nullptr, const __nv_bfloat16* __restrict__ act16 = nullptr) {
+  pdl_sync();
   __shared__ float red[kRowThreads / 32];
   float c0[kRowMaxPerThread], c1[kRowMaxPerThread], c2[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
 #pragma unroll
@@ -700,6 +708,7 @@ struct SegmentList {
 // flight per warp), then the 8 warp sums are combined in a fixed order => deterministic, and short segments
 // with many partials (LayerNorm/bias column sums: 32-64 elements x ~200 partials) are no longer one serial chain.
 static __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
+  pdl_sync();
   __shared__ float sm[8][33];
   const Segment sg = list.s[blockIdx.y];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -734,6 +743,7 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
                      const double* __restrict__ reward, const uint8_t* __restrict__ terminal, float gamma_n, int B,
                      int B_global, int K, int A, float* __restrict__ losses, float* __restrict__ dq,
                      float* __restrict__ dbias, int32_t* count) {
+  pdl_sync();
   __shared__ float red[kLossThreads / 32];
   __shared__ float dbw[kLossThreads / 32][kMaxActions];
   const int k = blockIdx.x;
@@ -796,6 +806,7 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
 static __global__ void __launch_bounds__(512)
 head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int K, int N,
                 float* __restrict__ out) {
+  pdl_sync();
   extern __shared__ float xs[];  // [K]
   __shared__ float part[4][128];
   const int r = blockIdx.x, tid = threadIdx.x;
@@ -821,6 +832,7 @@ static __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
             const int32_t* __restrict__ count, float lr, float b1, float b2, float eps, int64_t n4,
             __nv_bfloat16* __restrict__ shadow) {
+  pdl_sync();
   const int t = *count;
   const float c1 = (float)(1.0 - pow((double)b1, (double)t));
   const float c2 = (float)(1.0 - pow((double)b2, (double)t));

@@ -1,4 +1,5 @@
 // Library plumbing: error strings, CUDA-graph helpers, NCCL (dlopen'ed) for the data-parallel mode.
+#include <cstdlib>
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
@@ -13,6 +14,14 @@ void set_last_cuda_error(cudaError_t e, const char* where) {
 
 // ---------------------------------------------------------------------------------------------- profiler
 bool g_profile_on = false;
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_PDL");  // opt-in: measured 5 % SLOWER on the batch-32 step (profiles/r01_summary.md)
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 namespace {
 constexpr int kMaxMarks = 512;
 cudaEvent_t g_marks[kMaxMarks];

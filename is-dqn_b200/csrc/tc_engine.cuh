@@ -232,11 +232,13 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
+  pdl_trigger();  // (after the TMEM allocation: see common.cuh)
 
   if (warp >= kFirstProducerWarp) {
     // ------------------------------------------------------------------------------------------ producers
     const int ptid = tid - 32 * kFirstProducerWarp;
-    p.init_cta(extra_sm, ptid);
+    p.init_cta(extra_sm, ptid);  // index tables from the kernel arguments only: overlaps the previous kernel's tail
+    pdl_wait();
     named_bar_sync(1, PT);
     typename P::PCtx ctx;
     int j = 0;  // chunk counter of this CTA (stage = j % STAGES)
@@ -301,6 +303,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
     // -------------------------------------------------------------------------------------------- epilogue
     typename P::ECtx ectx;
     int ti = 0;
+    pdl_wait();
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
       const int m0 = tx * kBM, n0 = ty * BN;

@@ -48,7 +48,7 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
   const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   ISDQN_PROF(s, tag);
-  tc::tc_gemm_kernel<P><<<grid, threads, smem, s>>>(p, tiles_x, tiles_y, tiles_z);
+  ISDQN_CUDA_CHECK(launch_pdl((tc::tc_gemm_kernel<P>), dim3(grid), dim3(threads), smem, s, p, tiles_x, tiles_y, tiles_z));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -209,10 +209,10 @@ int launch_simt_gemm(const GemmArgs& g, cudaStream_t s, const char* tag) {
   dim3 grid(ceil_div(g.M, 64), ceil_div(g.N, 64), g.split_stride ? ceil_div(g.K, g.k_per_split) : 1);
   ISDQN_PROF(s, tag);
   const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
-  if (a_kfast && b_nfast) gemm_strided_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g);
-  else if (a_kfast) gemm_strided_kernel<true, false><<<grid, kGemmThreads, 0, s>>>(g);
-  else if (b_nfast) gemm_strided_kernel<false, true><<<grid, kGemmThreads, 0, s>>>(g);
-  else gemm_strided_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g);
+  if (a_kfast && b_nfast) ISDQN_CUDA_CHECK(launch_pdl((gemm_strided_kernel<true, true>), dim3(grid), dim3(kGemmThreads), 0, s, g));
+  else if (a_kfast) ISDQN_CUDA_CHECK(launch_pdl((gemm_strided_kernel<true, false>), dim3(grid), dim3(kGemmThreads), 0, s, g));
+  else if (b_nfast) ISDQN_CUDA_CHECK(launch_pdl((gemm_strided_kernel<false, true>), dim3(grid), dim3(kGemmThreads), 0, s, g));
+  else ISDQN_CUDA_CHECK(launch_pdl((gemm_strided_kernel<false, false>), dim3(grid), dim3(kGemmThreads), 0, s, g));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -251,7 +251,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     int64_t grid = ceil_div<int64_t>(n4, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     ISDQN_PROF(s, "cast_params_bf16");
-    cast_f32_bf16_kernel<<<(unsigned)grid, 256, 0, s>>>(params, shadow, n4);
+    ISDQN_CUDA_CHECK(launch_pdl(cast_f32_bf16_kernel, dim3((unsigned)grid), dim3(256), 0, s, params, shadow, n4));
     ISDQN_LAUNCH_CHECK();
   }
   // ------------------------------------------------------------------------------------------ forward
@@ -280,14 +280,14 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
                                        L.out_dim, split_stride, rows, L.out_dim, L.in_dim, splits, s, "tc_dense_fwd");
       if (rc) return rc;
       ISDQN_PROF(s, "dense_finalize");
-      dense_finalize_kernel<<<rows, kRowThreads, 0, s>>>(wsp(ws, w.fwd_part), real_splits, split_stride, rows, L.out_dim,
+      ISDQN_CUDA_CHECK(launch_pdl(dense_finalize_kernel, dim3(rows), dim3(kRowThreads), 0, s, wsp(ws, w.fwd_part), real_splits, split_stride, rows, L.out_dim,
                                                          params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]), xhat, rstd,
-                                                         rows_train, w16(wt, t.act16[l]));
+                                                         rows_train, w16(wt, t.act16[l])));
       ISDQN_LAUNCH_CHECK();
     } else if (L.out_dim <= 128 && L.in_dim <= 8192) {  // head layer: fp32 (N = (1+K)A is tiny, not 16-byte aligned)
       ISDQN_PROF(s, "head_fwd");
-      head_fwd_kernel<<<rows, 512, L.in_dim * sizeof(float), s>>>(wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
-                                                                L.in_dim, L.out_dim, wsp(ws, w.act[l]));
+      ISDQN_CUDA_CHECK(launch_pdl(head_fwd_kernel, dim3(rows), dim3(512), L.in_dim * sizeof(float), s, wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
+                                                                L.in_dim, L.out_dim, wsp(ws, w.act[l])));
       ISDQN_LAUNCH_CHECK();
     } else {
       GemmArgs g;
@@ -303,10 +303,10 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   const float* q_all = wsp(ws, w.act[nl - 1]);
   const Layer& last = p.L[nl - 1];
   ISDQN_PROF(s, "heads_td_loss");
-  heads_td_loss_kernel<<<net->n_heads, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
+  ISDQN_CUDA_CHECK(launch_pdl(heads_td_loss_kernel, dim3(net->n_heads), dim3(kLossThreads), 0, s, q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
                                                   tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
                                                   backward ? wsp(ws, w.dq) : nullptr, backward ? grads + last.b_off : nullptr,
-                                                  update ? tr->d_count : nullptr);
+                                                  update ? tr->d_count : nullptr));
   ISDQN_LAUNCH_CHECK();
   if (q_out)
     ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * (size_t)rows * p.n_out, cudaMemcpyDeviceToDevice, s));
@@ -385,13 +385,13 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       // the ReLU mask of a layer without LayerNorm needs its post-activation output: fp32 for Dense, bf16 for conv
       ISDQN_PROF(s, "ln_relu_bwd");
       if (ln_bwd_use_warp(P.out_dim)) {
-        launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
+        ISDQN_CUDA_CHECK(launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
                                 P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]),
-                                dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr);
+                                dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr));
       } else {
-        ln_relu_bwd_block_kernel<<<w.col_ctas[l - 1], kRowThreads, 0, s>>>(
+        ISDQN_CUDA_CHECK(launch_pdl(ln_relu_bwd_block_kernel, dim3(w.col_ctas[l - 1]), dim3(kRowThreads), 0, s, 
             dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p,
-            P.out_dim, wsp(ws, w.colpart[l - 1]), dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr);
+            P.out_dim, wsp(ws, w.colpart[l - 1]), dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr));
       }
       ISDQN_LAUNCH_CHECK();
     }
@@ -403,7 +403,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     int gx = ceil_div(max_n, 256);
     if (gx > 64) gx = 64;
     ISDQN_PROF(s, "reduce_segments");
-    reduce_segments_kernel<<<dim3(gx, segs.count), 256, 0, s>>>(segs);
+    ISDQN_CUDA_CHECK(launch_pdl(reduce_segments_kernel, dim3(gx, segs.count), dim3(256), 0, s, segs));
     ISDQN_LAUNCH_CHECK();
   }
   if (!update) return ISDQN_OK;

@@ -21,6 +21,17 @@ def _key_to_seed(key) -> np.random.SeedSequence:
     return np.random.SeedSequence(np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8).tolist() or [0])
 
 
+class HostLosses:
+    """Handle on an in-flight device->host copy of one step's losses (`iSDQN.losses_to_host_async`)."""
+
+    def __init__(self, buf, event):
+        self._buf, self._event = buf, event
+
+    def get(self) -> np.ndarray:
+        self._event.synchronize()
+        return self._buf.numpy().copy()
+
+
 class OptState(dict):
     """`optax.adam` state: {"count": int32[1], "mu": ParamTree, "nu": ParamTree} (optax 0.2.4 ScaleByAdamState)."""
 
@@ -92,6 +103,9 @@ class iSDQN:
         self._nccl_comm = None
         self._dp_world = 1
         self._side_stream = None
+        self._copy_stream = None
+        self._loss_ring = None
+        self._last_step = None
 
     # ------------------------------------------------------------------------------------- loss bookkeeping
     @property
@@ -124,11 +138,28 @@ class iSDQN:
             shape, dt = (B,) + tuple(net.observation_dim), t.uint8
         else:
             shape, dt = (B,) + tuple(net.observation_dim), t.float32
-        ctx["state"] = t.zeros(shape, dtype=dt, device="cuda")
-        ctx["next_state"] = t.zeros(shape, dtype=dt, device="cuda")
-        ctx["action"] = t.zeros(B, dtype=t.int64, device="cuda")
-        ctx["reward"] = t.zeros(B, dtype=t.float64, device="cuda")
-        ctx["terminal"] = t.zeros(B, dtype=t.uint8, device="cuda")
+        # the five batch fields live in ONE device allocation (16-byte aligned sub-ranges) so that a staged host batch
+        # reaches them with a single device-to-device copy
+        item = 1 if dt == t.uint8 else 4
+        n_state = int(np.prod(shape)) * item
+        al = lambda n: (n + 15) // 16 * 16
+        offs, o = {}, 0
+        for name, nb in (("state", n_state), ("next_state", n_state), ("action", 8 * B), ("reward", 8 * B), ("terminal", B)):
+            offs[name] = (o, nb)
+            o = al(o + nb)
+        ctx["pack_bytes"], ctx["pack_offs"] = o, offs
+        ctx["dev_pack"] = t.zeros(o, dtype=t.uint8, device="cuda")
+
+        def views(pack):
+            v = {}
+            for name, vdt, vshape in (("state", dt, shape), ("next_state", dt, shape), ("action", t.int64, (B,)),
+                                      ("reward", t.float64, (B,)), ("terminal", t.uint8, (B,))):
+                a, nb = offs[name]
+                v[name] = pack[a : a + nb].view(vdt).view(vshape)
+            return v
+
+        ctx["views"] = views
+        ctx.update(views(ctx["dev_pack"]))
         ctx["losses"] = t.zeros(self.n_bellman_iterations, dtype=t.float32, device="cuda")
         nbytes = self._lib.isdqn_learn_workspace_bytes(net._net, B)
         if nbytes < 0:
@@ -143,12 +174,9 @@ class iSDQN:
                     "widths that are multiples of 64; use compute_dtype='float32' for this network"
                 )
             ctx["ws_tc"] = t.empty(nb, dtype=t.uint8, device="cuda")
-        # pinned staging for host batches (the reference's implicit device_put at the jit boundary)
-        ctx["h_state"] = t.zeros(shape, dtype=dt).pin_memory()
-        ctx["h_next_state"] = t.zeros(shape, dtype=dt).pin_memory()
-        ctx["h_action"] = t.zeros(B, dtype=t.int64).pin_memory()
-        ctx["h_reward"] = t.zeros(B, dtype=t.float64).pin_memory()
-        ctx["h_terminal"] = t.zeros(B, dtype=t.uint8).pin_memory()
+        # double-buffered pinned + device staging for host batches (the reference's implicit device_put at the jit
+        # boundary): allocated on first use by _stage_host_batch
+        ctx["stage"] = None
         batch = _lib.Batch(
             ctx["state"].data_ptr(), ctx["next_state"].data_ptr(), ctx["action"].data_ptr(),
             ctx["reward"].data_ptr(), ctx["terminal"].data_ptr(),
@@ -207,25 +235,83 @@ class iSDQN:
                 params.shadow_dirty = False
         return tr
 
-    def _load_batch(self, ctx, batch) -> int:
-        """Copies `batch` (host numpy, like `rb.sample()`; or CUDA tensors) into the persistent device buffers."""
+    def _stage_host_batch(self, ctx, fields, stream) -> None:
+        """Host numpy batch -> pinned slot -> (copy stream) device slot -> (step stream) the batch buffers.  Two slots:
+        the H2D copy of step i+1 runs on the copy engine while step i computes; the CPU only blocks when it is two
+        steps ahead of the GPU."""
+        t = self._torch
+        st = ctx["stage"]
+        if st is None:
+            st = ctx["stage"] = {
+                "slot": 0,
+                "host": [t.zeros(ctx["pack_bytes"], dtype=t.uint8).pin_memory() for _ in range(2)],
+                "dev": [t.zeros(ctx["pack_bytes"], dtype=t.uint8, device="cuda") for _ in range(2)],
+                "h2d_done": [t.cuda.Event() for _ in range(2)],
+                "d2d_done": [t.cuda.Event() for _ in range(2)],
+            }
+            st["host_np"] = [{k: v.numpy() for k, v in ctx["views"](h).items()} for h in st["host"]]
+            if self._copy_stream is None:
+                self._copy_stream = t.cuda.Stream()
+        slot = st["slot"]
+        st["slot"] = slot ^ 1
+        st["h2d_done"][slot].synchronize()  # the previous copy out of this pinned slot has finished
+        for name, f in fields.items():
+            arr = np.asarray(f)
+            if name in ("state", "next_state") and self.network.architecture_type == "cnn" and arr.dtype != np.uint8:
+                raise TypeError("cnn batches must be uint8 frames (float states: use loss_on_batch / apply)")
+            dst = st["host_np"][slot][name]
+            dst[...] = arr.reshape(dst.shape)
+        cs = self._copy_stream
+        cs.wait_event(st["d2d_done"][slot])  # the step that consumed this device slot has copied it out
+        with t.cuda.stream(cs):
+            st["dev"][slot].copy_(st["host"][slot], non_blocking=True)
+            st["h2d_done"][slot].record(cs)
+        stream.wait_event(st["h2d_done"][slot])
+        with t.cuda.stream(stream):
+            ctx["dev_pack"].copy_(st["dev"][slot], non_blocking=True)
+            st["d2d_done"][slot].record(stream)
+
+    def _load_batch(self, ctx, batch, stream) -> int:
+        """Copies `batch` (host numpy, like `rb.sample()`; or CUDA tensors) into the persistent device buffers, ordered
+        on `stream` (a torch.cuda.Stream)."""
         t = self._torch
         names = ("state", "action", "reward", "next_state", "terminal")
-        fields = (batch.state, batch.action, batch.reward, batch.next_state, batch.is_terminal)
-        for name, f in zip(names, fields):
-            dst = ctx[name]
-            if isinstance(f, t.Tensor):
-                if f.data_ptr() == dst.data_ptr():
-                    continue
-                dst.copy_(f.reshape(dst.shape) if f.dtype == dst.dtype else f.reshape(dst.shape).to(dst.dtype), non_blocking=True)
-            else:
-                h = ctx["h_" + name]
-                arr = np.asarray(f)
-                if name in ("state", "next_state") and self.network.architecture_type == "cnn" and arr.dtype != np.uint8:
-                    raise TypeError("cnn batches must be uint8 frames (float states: use loss_on_batch / apply)")
-                h.numpy()[...] = arr.reshape(h.shape)
-                dst.copy_(h, non_blocking=True)
+        fields = dict(zip(names, (batch.state, batch.action, batch.reward, batch.next_state, batch.is_terminal)))
+        if not any(isinstance(f, t.Tensor) for f in fields.values()):
+            self._stage_host_batch(ctx, fields, stream)
+            return int(ctx["action"].shape[0])
+        with t.cuda.stream(stream):
+            for name, f in fields.items():
+                dst = ctx[name]
+                if isinstance(f, t.Tensor):
+                    if f.data_ptr() == dst.data_ptr():
+                        continue
+                    dst.copy_(f.reshape(dst.shape) if f.dtype == dst.dtype else f.reshape(dst.shape).to(dst.dtype), non_blocking=True)
+                else:
+                    dst.copy_(t.as_tensor(np.asarray(f)).reshape(dst.shape).to(dst.dtype), non_blocking=False)
         return int(ctx["action"].shape[0])
+
+    def losses_to_host_async(self) -> "HostLosses":
+        """Enqueues the device->host copy of the latest step's K losses behind that step and returns a handle;
+        `handle.get()` blocks on THAT copy only, so a training loop can read step i's losses while step i+1 runs
+        (jax's asynchronous dispatch gives the reference the same overlap).  A handle stays valid for the next 8 calls."""
+        t = self._torch
+        if self._loss_ring is None:
+            self._loss_ring = {
+                "i": 0,
+                "buf": [t.zeros(self.n_bellman_iterations, dtype=t.float32).pin_memory() for _ in range(8)],
+                "ev": [t.cuda.Event() for _ in range(8)],
+            }
+        if self._last_step is None:
+            raise RuntimeError("losses_to_host_async() follows a learn_on_batch() call")
+        losses, stream = self._last_step
+        r = self._loss_ring
+        i = r["i"]
+        r["i"] = (i + 1) % 8
+        with t.cuda.stream(stream):
+            r["buf"][i].copy_(losses, non_blocking=True)
+            r["ev"][i].record(stream)
+        return HostLosses(r["buf"][i], r["ev"][i])
 
     # ------------------------------------------------------------------------------------------------ update
     def update_online_params(self, step: int, replay_buffer):
@@ -267,7 +353,6 @@ class iSDQN:
         state are updated in place (donated) and returned."""
         B = int(batch_samples.action.shape[0])
         ctx = self._context(B)
-        self._load_batch(ctx, batch_samples)
         cur = self._torch.cuda.current_stream()
         side = None
         if self._use_graph and cur.cuda_stream == 0:
@@ -276,9 +361,12 @@ class iSDQN:
                 self._side_stream = self._torch.cuda.Stream()
             side = self._side_stream
             side.wait_stream(cur)
-        stream = side.cuda_stream if side is not None else cur.cuda_stream
+        run = side if side is not None else cur
+        self._load_batch(ctx, batch_samples, run)
         try:
-            return self._learn_on_stream(ctx, params, optimizer_state, B, stream)
+            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream)
+            self._last_step = (out[2], run)
+            return out
         finally:
             if side is not None:
                 cur.wait_stream(side)
@@ -317,7 +405,7 @@ class iSDQN:
         """Gradient of the loss without the update: (grads ParamTree, losses[K]).  Used by parity tests / DP."""
         B = int(batch_samples.action.shape[0])
         ctx = self._context(B)
-        self._load_batch(ctx, batch_samples)
+        self._load_batch(ctx, batch_samples, self._torch.cuda.current_stream())
         tr = self._train_struct(ctx, params, None, B)
         _lib.check(self._lib.isdqn_grad_on_batch(self.network._net, tr, ctx["batch"], _lib.stream_ptr()), "isdqn_grad_on_batch")
         return self._grads, ctx["losses"]
@@ -349,7 +437,8 @@ class iSDQN:
             )
         else:
             ctx = self._context(B)
-            self._load_batch(ctx, ReplayElement(state, samples.action, samples.reward, next_state, samples.is_terminal))
+            self._load_batch(ctx, ReplayElement(state, samples.action, samples.reward, next_state, samples.is_terminal),
+                             t.cuda.current_stream())
             tr = self._train_struct(ctx, params, None, B)
             all_q = t.empty((2 * B, net.final_feature), dtype=t.float32, device="cuda")
             _lib.check(

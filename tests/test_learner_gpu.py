@@ -239,3 +239,31 @@ def test_adam_kernel_standalone():
         assert rel_err(pd, po["m"]["w"]) <= 1e-6
     assert int(cnt.item()) == 5
     assert torch.equal(pd.cpu()[::7], p[::7])  # zero gradient: parameter untouched (head 0 between shifts)
+
+
+def test_pipelined_host_batches_match_device_batches():
+    """Host numpy batches through the double-buffered staging (H2D on the copy stream, losses read one step late)
+    give bit-identical parameters and losses to the same batches passed as CUDA tensors with a sync per step."""
+    import torch
+
+    cfg = dict(obs_dim=(84, 84, 4), A=6, K=3, features=[32, 64, 64, 512], layer_norm=True, arch="cnn")
+    a_host, a_dev = make_agent(11, **cfg), make_agent(11, **cfg)
+    p = oracle_params_for(a_host, 11)
+    push_params(a_host, p)
+    push_params(a_dev, p)
+    batches = [L.make_batch(700 + i, 16, cfg["obs_dim"], cfg["A"], "cnn") for i in range(7)]
+    handles, dev_losses = [], []
+    with torch.cuda.stream(torch.cuda.Stream()):
+        for b in batches:
+            a_host.learn_on_batch(a_host.params, a_host.optimizer_state, batch_as_element(b))
+            handles.append(a_host.losses_to_host_async())
+        host_losses = [h.get() for h in handles[-4:]]
+    for b in batches:
+        el = batch_as_element(b)
+        el = type(el)(*[torch.as_tensor(np.asarray(f)).cuda() for f in el])
+        _, _, losses = a_dev.learn_on_batch(a_dev.params, a_dev.optimizer_state, el)
+        dev_losses.append(losses.cpu().numpy().copy())
+    torch.cuda.synchronize()
+    assert a_host.params.flat.cpu().numpy().tobytes() == a_dev.params.flat.cpu().numpy().tobytes()
+    for got, want in zip(host_losses, dev_losses[-4:]):
+        assert got.tobytes() == want.tobytes()
