@@ -252,13 +252,9 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
     dz = dprev;
   }
   if (segs.count > 0) {
-    int max_n = 0;
-    for (int i = 0; i < segs.count; ++i) max_n = segs.s[i].n > max_n ? segs.s[i].n : max_n;
-    int gx = ceil_div(max_n, 256);
-    if (gx > 64) gx = 64;
+    const int n_tiles = finish_segments(&segs);
     ISDQN_PROF(s, "reduce_segments");
-    reduce_segments_kernel<<<dim3(gx, segs.count), 256, 0, s>>>(segs);
-    ISDQN_LAUNCH_CHECK();
+    ISDQN_CUDA_CHECK(launch_pdl(reduce_segments_kernel, dim3(n_tiles), dim3(256), 0, s, segs));
   }
   return ISDQN_OK;
 }

@@ -701,32 +701,51 @@ struct Segment {
 };
 struct SegmentList {
   int count;
+  int tile_start[kMaxSegments + 1];  // prefix sum of ceil(n / 32) over the segments (filled by finish_segments)
   Segment s[kMaxSegments];
 };
+static inline int finish_segments(SegmentList* l) {
+  int t = 0;
+  for (int i = 0; i < l->count; ++i) {
+    l->tile_start[i] = t;
+    t += (l->s[i].n + 31) / 32;
+  }
+  l->tile_start[l->count] = t;
+  return t;  // = grid size of reduce_segments_kernel
+}
 
-// One CTA sums a tile of 32 elements: its 8 warps take the partials p = w, w+8, ... (32 independent loads in
-// flight per warp), then the 8 warp sums are combined in a fixed order => deterministic, and short segments
-// with many partials (LayerNorm/bias column sums: 32-64 elements x ~200 partials) are no longer one serial chain.
+// One CTA sums ONE tile of 32 elements of one segment (grid = all tiles of all segments, so every partial of the
+// step is in flight at once): its 8 warps take the partials p = w, w+8, ... (independent loads), then the 8 warp sums
+// are combined in a fixed order => deterministic.
 static __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
   pdl_sync();
   __shared__ float sm[8][33];
-  const Segment sg = list.s[blockIdx.y];
+  int seg = 0;
+  while (seg + 1 < list.count && (int)blockIdx.x >= list.tile_start[seg + 1]) ++seg;
+  const Segment sg = list.s[seg];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_tiles = (sg.n + 31) / 32;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int i = tile * 32 + lane;
-    float t = 0.f;
-    if (i < sg.n)
-      for (int p = w; p < sg.parts; p += 8) t += sg.src[(int64_t)p * sg.stride + i];
-    sm[w][lane] = t;
-    __syncthreads();
-    if (w == 0 && i < sg.n) {
-      float tot = sm[0][lane];
-#pragma unroll
-      for (int k = 1; k < 8; ++k) tot += sm[k][lane];
-      sg.dst[i] = tot;
+  const int i = ((int)blockIdx.x - list.tile_start[seg]) * 32 + lane;
+  float t = 0.f;
+  if (i < sg.n) {
+    const float* src = sg.src + i;
+    int p = w;
+    for (; p + 24 < sg.parts; p += 32) {  // four independent loads per warp iteration
+      const float a0 = src[(int64_t)p * sg.stride], a1 = src[(int64_t)(p + 8) * sg.stride];
+      const float a2 = src[(int64_t)(p + 16) * sg.stride], a3 = src[(int64_t)(p + 24) * sg.stride];
+      t += a0;
+      t += a1;
+      t += a2;
+      t += a3;
     }
-    __syncthreads();
+    for (; p < sg.parts; p += 8) t += src[(int64_t)p * sg.stride];
+  }
+  sm[w][lane] = t;
+  __syncthreads();
+  if (w == 0 && i < sg.n) {
+    float tot = sm[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) tot += sm[k][lane];
+    sg.dst[i] = tot;
   }
 }
 

@@ -2,6 +2,8 @@
 // iSDQN.learn_on_batch (slimdqn/networks/isdqn.py:82-103, architectures/dqn.py:55-103) as implicit GEMMs on the
 // 5th-generation tensor cores; the tiny head layer, the K-head TD loss, LayerNorm backward, the deterministic
 // reductions and Adam stay on the fp32 kernels of learner_kernels.cuh.  Tolerance of this path: 2e-2 (north_star).
+#include <cstdio>
+#include <cstdlib>
 #include "learner_kernels.cuh"
 #include "plan.cuh"
 #include "tc_problems.cuh"
@@ -21,6 +23,27 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
   }
 }
 
+// uint8 frames -> bf16 holding the exact integer pixel values 0..255 (the 1/255 of `x / 255` is applied to the fp32
+// accumulator in the epilogues): each pixel is converted ONCE here instead of once per convolution window it is part of,
+// and the first convolution then takes the same asynchronous-copy gather as the others.  16 pixels per thread.
+__global__ void __launch_bounds__(256)
+u8_frames_to_bf16_kernel(const uint8_t* __restrict__ s0, const uint8_t* __restrict__ s1, bf16* __restrict__ dst, int64_t n16_each) {
+  pdl_sync();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n16_each; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = i < n16_each ? __ldg(reinterpret_cast<const uint4*>(s0) + i) : __ldg(reinterpret_cast<const uint4*>(s1) + (i - n16_each));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      o[2 * q] = tc::int_pair_bf16(w[q] & 0xff, (w[q] >> 8) & 0xff);
+      o[2 * q + 1] = tc::int_pair_bf16((w[q] >> 16) & 0xff, w[q] >> 24);
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst) + 2 * i;
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
 }  // namespace isdqn
 
 namespace {
@@ -37,10 +60,24 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           (int)cudaSharedmemCarveoutMaxShared));
-    int occ = 0;
-    ISDQN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_gemm_kernel<P>, threads, smem));
-    const int by_tmem = 512 / tc::tmem_cols_for(2 * P::BN);  // every resident CTA owns two accumulators in TMEM
+    // Resident CTAs per SM from the kernel's own resources (228 KB shared memory with 1 KB reserved per CTA, 64 K
+    // registers allocated per warp in units of 256, 2048 threads, 512 TMEM columns: every CTA owns two accumulators).
+    cudaFuncAttributes fa;
+    ISDQN_CUDA_CHECK(cudaFuncGetAttributes(&fa, tc::tc_gemm_kernel<P>));
+    const int by_smem = (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+    const int by_regs = 65536 / (regs_per_warp * (threads / 32));
+    const int by_threads = 2048 / threads;
+    const int by_tmem = 512 / tc::tmem_cols_for(2 * P::BN);
+    int occ = by_smem < by_regs ? by_smem : by_regs;
+    if (occ > by_threads) occ = by_threads;
     if (occ > by_tmem) occ = by_tmem;
+    if (getenv("ISDQN_DEBUG_OCC")) {
+      int api = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&api, tc::tc_gemm_kernel<P>, threads, smem);
+      fprintf(stderr, "[isdqn] %s: regs %d static smem %zu dyn %zu threads %d -> smem %d regs %d thr %d tmem %d (api %d)\n", tag,
+              fa.numRegs, fa.sharedSizeBytes, smem, threads, by_smem, by_regs, by_threads, by_tmem, api);
+    }
     ctas_per_sm = occ < 1 ? 1 : occ;
   }
   const int64_t n_tiles = (int64_t)tiles_x * tiles_y * tiles_z;
@@ -90,8 +127,16 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
 struct TcWorkspace {
   int64_t act16[ISDQN_MAX_FEATURES + 1];  // byte offsets; bf16 [rows*pix][out_dim] for every non-final layer
   int64_t dz16[2];                        // bf16 ping-pong [B*pix][out_dim]
+  int64_t x16;                            // bf16 [2B][H][W][4] integer-valued copy of the uint8 frames (or -1)
   int64_t total;                          // bytes
 };
+
+// The first convolution reads a bf16 copy of the frames when a 16-byte gather chunk (two horizontally adjacent taps of
+// the 4 stacked frames) can never straddle the left/right image border; otherwise it converts uint8 in its producers.
+bool frames_as_bf16(const Layer& L) {
+  return L.type == 0 && L.Cin == 4 && L.pad_x % 2 == 0 && L.W % 2 == 0 && L.ksz % 2 == 0 && L.stride % 2 == 0 &&
+         ((int64_t)L.H * L.W * L.Cin) % 16 == 0;
+}
 
 void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
   int64_t off = 0;
@@ -107,6 +152,7 @@ void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
     const int64_t d = (int64_t)B * L.pix * L.out_dim * 2;
     if (d > max_d) max_d = d;
   }
+  w->x16 = frames_as_bf16(p.L[0]) ? take((int64_t)rows * p.L[0].H * p.L[0].W * p.L[0].Cin * 2) : -1;
   w->dz16[0] = take(max_d > 0 ? max_d : 16);
   w->dz16[1] = take(max_d > 0 ? max_d : 16);
   w->total = off;
@@ -134,7 +180,7 @@ bool tc_eligible(const Plan& p, const isdqn_net* net) {
 
 template <bool U8>
 int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0, int rows, const bf16* w, const float* params,
-                       bf16* out, float* xhat, float* rstd, int m_train, cudaStream_t s) {
+                       bf16* out, float* xhat, float* rstd, int m_train, cudaStream_t s, float in_scale = 1.0f) {
 #define ISDQN_CONV_FWD_TC(BN)                                                                          \
   {                                                                                                    \
     tc::ConvFwdTC<BN, U8> p;                                                                           \
@@ -146,7 +192,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
     p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
     p.ln_b = L.has_ln ? params + L.beta_off : nullptr;                                                 \
     p.relu = L.relu; p.out = out; p.xhat = xhat; p.rstd = rstd; p.m_train = m_train;                   \
-    p.acc_scale = U8 ? 1.0f / 255.0f : 1.0f;                                                           \
+    p.acc_scale = U8 ? 1.0f / 255.0f : in_scale;                                                       \
     return launch_tc(p, ceil_div(p.M, tc::kBM), 1, 1, s, "tc_conv_fwd");                               \
   }
   switch (L.out_dim) {
@@ -161,7 +207,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
 
 template <bool U8>
 int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* part, int rows, int splits, int* real_splits,
-                         cudaStream_t s) {
+                         cudaStream_t s, float in_scale = 1.0f) {
   const int total_chunks = ceil_div(rows, tc::kBK);
   const int cps = ceil_div(total_chunks, splits);
   *real_splits = ceil_div(total_chunks, cps);
@@ -171,7 +217,7 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
     p.in = in; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;     \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
     p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
-    p.acc_scale = U8 ? 1.0f / 255.0f : 1.0f;                                                           \
+    p.acc_scale = U8 ? 1.0f / 255.0f : in_scale;                                                       \
     return launch_tc(p, ceil_div(L.in_dim, tc::kBM), 1, *real_splits, s, "tc_conv_wgrad");             \
   }
   switch (L.out_dim) {
@@ -263,7 +309,17 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     float* xhat = rows_train > 0 ? wsp(ws, w.xhat[l]) : nullptr;
     float* rstd = rows_train > 0 ? wsp(ws, w.rstd[l]) : nullptr;
     if (L.type == 0) {
-      if (l == 0)
+      if (l == 0 && t.x16 >= 0) {
+        const int64_t n16 = (int64_t)B * L.H * L.W * L.Cin / 16;
+        int64_t grid = ceil_div<int64_t>(2 * n16, 256);
+        if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+        ISDQN_PROF(s, "frames_to_bf16");
+        ISDQN_CUDA_CHECK(launch_pdl(u8_frames_to_bf16_kernel, dim3((unsigned)grid), dim3(256), 0, s,
+                                    reinterpret_cast<const uint8_t*>(b->d_state), reinterpret_cast<const uint8_t*>(b->d_next_state),
+                                    w16(wt, t.x16), n16));
+        rc = launch_conv_fwd_tc<false>(L, w16(wt, t.x16), nullptr, rows, rows, shadow + L.w_off, params, w16(wt, t.act16[l]), xhat,
+                                       rstd, rows_train * L.pix, s, 1.0f / 255.0f);
+      } else if (l == 0)
         rc = launch_conv_fwd_tc<true>(L, b->d_state, b->d_next_state, B, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
                                       xhat, rstd, rows_train * L.pix, s);
       else
@@ -345,7 +401,9 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     } else {
       int real_splits = 1;
       float* part = wsp(ws, w.wpart[l]);
-      if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, s);
+      if (l == 0 && t.x16 >= 0)
+        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, s, 1.0f / 255.0f);
+      else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, s);
       else rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits[l], &real_splits, s);
       add_seg(part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
     }
@@ -398,13 +456,9 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     dz32 = dprev;
   }
   if (segs.count > 0) {
-    int max_n = 0;
-    for (int i = 0; i < segs.count; ++i) max_n = segs.s[i].n > max_n ? segs.s[i].n : max_n;
-    int gx = ceil_div(max_n, 256);
-    if (gx > 64) gx = 64;
+    const int n_tiles = finish_segments(&segs);
     ISDQN_PROF(s, "reduce_segments");
-    ISDQN_CUDA_CHECK(launch_pdl(reduce_segments_kernel, dim3(gx, segs.count), dim3(256), 0, s, segs));
-    ISDQN_LAUNCH_CHECK();
+    ISDQN_CUDA_CHECK(launch_pdl(reduce_segments_kernel, dim3(n_tiles), dim3(256), 0, s, segs));
   }
   if (!update) return ISDQN_OK;
   if (tr->nccl_comm) {
