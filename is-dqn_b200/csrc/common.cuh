@@ -37,6 +37,12 @@ void profile_mark(cudaStream_t s, const char* name);
     if (::isdqn::g_profile_on) ::isdqn::profile_mark(stream, name); \
   } while (0)
 
+// two-stream backward pass (runtime.cu)
+constexpr int kSideEvents = 16, kSideStreams = 2;
+bool fork_enabled();
+cudaStream_t side_stream(int i);
+cudaEvent_t side_event(int i);
+
 // Programmatic dependent launch (PDL).  The kernels of one learner step form a chain of short dependent launches; with
 // the launch attribute below the NEXT kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM
 // allocation) while the current kernel still executes, and block in pdl_wait() until it has completed and its memory

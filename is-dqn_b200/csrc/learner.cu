@@ -360,15 +360,19 @@ extern "C" int isdqn_heads_td_loss(const float* d_q_all, const int64_t* d_action
 // Adam over the flat vector; *d_count must already hold the step number t >= 1.  `shadow` (optional): bf16 copy of
 // the updated parameters, written in the same pass.
 int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
-                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream) {
+                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream, int64_t skip_begin,
+                      int64_t skip_len, int max_ctas) {
   if (!d_params || !d_grads || !d_mu || !d_nu || !d_count || n < 0 || (n & 3)) return ISDQN_E_INVALID;
-  if (n == 0) return ISDQN_OK;
-  const int64_t n4 = n / 4;
+  if (skip_begin < 0 || skip_len < 0 || (skip_begin & 3) || (skip_len & 3) || skip_begin + skip_len > n) return ISDQN_E_INVALID;
+  const int64_t n4 = (n - skip_len) / 4;
+  if (n4 == 0) return ISDQN_OK;
   int64_t grid = ceil_div<int64_t>(n4, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   ISDQN_PROF(as_stream(stream), "adam");
   ISDQN_CUDA_CHECK(launch_pdl(adam_kernel, dim3((unsigned)grid), dim3(256), 0, as_stream(stream), d_params, d_grads, d_mu,
-                              d_nu, d_count, lr, b1, b2, eps, n4, reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16)));
+                              d_nu, d_count, lr, b1, b2, eps, n4, reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16), skip_begin / 4,
+                              skip_len / 4));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -376,7 +380,7 @@ int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float*
 extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu,
                                        const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
                                        void* stream) {
-  return isdqn_adam_launch(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n, nullptr, stream);
+  return isdqn_adam_launch(d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, n, nullptr, stream, 0, 0, 0);
 }
 
 extern "C" int isdqn_adam_step(float* d_params, const float* d_grads, float* d_mu, float* d_nu, int32_t* d_count,

@@ -850,13 +850,16 @@ head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 static __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
             const int32_t* __restrict__ count, float lr, float b1, float b2, float eps, int64_t n4,
-            __nv_bfloat16* __restrict__ shadow) {
+            __nv_bfloat16* __restrict__ shadow, int64_t skip_begin4, int64_t skip_len4) {
+  // n4 float4 groups are updated; the groups [skip_begin4, skip_begin4 + skip_len4) of the vector are passed over
+  // (they were already updated by an earlier launch of the same step)
   pdl_sync();
   const int t = *count;
   const float c1 = (float)(1.0 - pow((double)b1, (double)t));
   const float c2 = (float)(1.0 - pow((double)b2, (double)t));
   const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j < skip_begin4 ? j : j + skip_len4;
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(mu)[i];
     float4 vv = reinterpret_cast<float4*>(nu)[i];

@@ -22,6 +22,32 @@ bool pdl_enabled() {
   }();
   return on;
 }
+// Side stream + events of the two-stream backward pass (tc_learner.cu).  One set per process: the learner entry points
+// are not re-entrant across host threads.  ISDQN_FORK=1 enables it (measured slower at batch 32).
+bool fork_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_FORK");  // opt-in: cross-stream graph edges cost more than the overlap gains
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+cudaStream_t side_stream(int i) {
+  static cudaStream_t s[kSideStreams] = {};
+  static bool tried[kSideStreams] = {};
+  if (i < 0 || i >= kSideStreams) return nullptr;
+  if (!tried[i]) {
+    tried[i] = true;
+    if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) s[i] = nullptr;
+  }
+  return s[i];
+}
+cudaEvent_t side_event(int i) {
+  static cudaEvent_t ev[kSideEvents] = {};
+  if (i < 0 || i >= kSideEvents) return nullptr;
+  if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) ev[i] = nullptr;
+  return ev[i];
+}
+
 namespace {
 constexpr int kMaxMarks = 512;
 cudaEvent_t g_marks[kMaxMarks];

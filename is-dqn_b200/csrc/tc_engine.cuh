@@ -249,6 +249,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
       const int m0 = tx * kBM, n0 = ty * BN;
       p.tile_producer(ctx, extra_sm, m0, n0, tz, ptid, ti);  // may publish per-row info in shared memory (parity ti & 1)
       named_bar_sync(1, PT);
+      p.tile_rows(ctx, ptid);  // per-thread copy (registers) of the rows this thread gathers for the whole tile
       int kb, ke;
       p.k_range(tz, kb, ke);
       for (int kc = kb; kc < ke; ++kc, ++j) {

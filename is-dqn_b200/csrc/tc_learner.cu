@@ -12,7 +12,12 @@ using namespace isdqn;
 using isdqn::tc::bf16;
 
 int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
-                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream);
+                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream, int64_t skip_begin,
+                      int64_t skip_len, int max_ctas = 0);
+
+namespace isdqn {
+constexpr int kSideCtas = 64;  // grid cap of the tensor-core weight-gradient kernels that run beside the critical path
+}
 
 namespace isdqn {
 
@@ -52,7 +57,7 @@ inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpre
 
 // Persistent launch: the tiles (x fastest) are dealt round-robin to min(#tiles, SMs x resident CTAs) CTAs.
 template <class P>
-int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag) {
+int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0) {
   constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
   constexpr int threads = 32 * (tc::kFirstProducerWarp + P::PRODUCER_WARPS);
   static int ctas_per_sm = 0;
@@ -82,7 +87,8 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
   }
   const int64_t n_tiles = (int64_t)tiles_x * tiles_y * tiles_z;
   if (n_tiles < 1 || n_tiles > 0x7fffffff) return ISDQN_E_INVALID;
-  const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  if (max_ctas > 0 && cap > max_ctas) cap = max_ctas;  // side-stream work: leave most SMs to the critical path
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   ISDQN_PROF(s, tag);
   ISDQN_CUDA_CHECK(launch_pdl((tc::tc_gemm_kernel<P>), dim3(grid), dim3(threads), smem, s, p, tiles_x, tiles_y, tiles_z));
@@ -101,18 +107,19 @@ int pick_bn_parallel(int n, int other_ctas) {
 // D[M][N] (fp32, + split partials) = A B^T with the four operand-major combinations
 template <bool A_MN, bool B_MN>
 int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C, int64_t ldc, int64_t split_stride, int M,
-                   int N, int K, int splits, cudaStream_t s, const char* tag) {
+                   int N, int K, int splits, cudaStream_t s, const char* tag, int max_ctas = 0) {
   const int total_chunks = ceil_div(K, tc::kBK);
   const int cps = ceil_div(total_chunks, splits);
   const int real_splits = ceil_div(total_chunks, cps);
-  const int bn = pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
+  // (a capped side-stream launch takes the narrow tile: half the shared memory, so it can share an SM)
+  const int bn = max_ctas > 0 ? pick_bn(N < 64 ? N : 64) : pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
 #define ISDQN_GEMM_TC(BN)                                                      \
   {                                                                            \
     tc::GemmTC<BN, A_MN, B_MN> p;                                              \
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;          \
     p.split_stride = split_stride; p.M = M; p.N = N; p.K = K;                  \
     p.chunks_per_split = cps;                                                  \
-    return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag); \
+    return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag, max_ctas); \
   }
   switch (bn) {
     case 32: ISDQN_GEMM_TC(32)
@@ -126,7 +133,7 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
 // ---------------------------------------------------------------------------------------------- workspace
 struct TcWorkspace {
   int64_t act16[ISDQN_MAX_FEATURES + 1];  // byte offsets; bf16 [rows*pix][out_dim] for every non-final layer
-  int64_t dz16[2];                        // bf16 ping-pong [B*pix][out_dim]
+  int64_t dz16[ISDQN_MAX_FEATURES + 1];   // bf16 [B*pix][out_dim] gradient w.r.t. the pre-activation of every non-final layer
   int64_t x16;                            // bf16 [2B][H][W][4] integer-valued copy of the uint8 frames (or -1)
   int64_t total;                          // bytes
 };
@@ -145,16 +152,17 @@ void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
     off = (off + bytes + 255) & ~(int64_t)255;
     return o;
   };
-  int64_t max_d = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     const Layer& L = p.L[l];
     w->act16[l] = l + 1 < p.n_layers ? take((int64_t)rows * L.pix * L.out_dim * 2) : -1;
-    const int64_t d = (int64_t)B * L.pix * L.out_dim * 2;
-    if (d > max_d) max_d = d;
   }
   w->x16 = frames_as_bf16(p.L[0]) ? take((int64_t)rows * p.L[0].H * p.L[0].W * p.L[0].Cin * 2) : -1;
-  w->dz16[0] = take(max_d > 0 ? max_d : 16);
-  w->dz16[1] = take(max_d > 0 ? max_d : 16);
+  // one buffer per layer (not a ping-pong): the weight gradient of layer l runs on the side stream while the main
+  // stream is already producing the gradients of the layers below it
+  for (int l = 0; l < p.n_layers; ++l) {
+    const Layer& L = p.L[l];
+    w->dz16[l] = (B > 0 && l + 1 < p.n_layers) ? take((int64_t)B * L.pix * L.out_dim * 2) : -1;
+  }
   w->total = off;
 }
 
@@ -207,7 +215,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
 
 template <bool U8>
 int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* part, int rows, int splits, int* real_splits,
-                         cudaStream_t s, float in_scale = 1.0f) {
+                         cudaStream_t s, float in_scale = 1.0f, int max_ctas = 0) {
   const int total_chunks = ceil_div(rows, tc::kBK);
   const int cps = ceil_div(total_chunks, splits);
   *real_splits = ceil_div(total_chunks, cps);
@@ -218,7 +226,7 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
     p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
     p.acc_scale = U8 ? 1.0f / 255.0f : in_scale;                                                       \
-    return launch_tc(p, ceil_div(L.in_dim, tc::kBM), 1, *real_splits, s, "tc_conv_wgrad");             \
+    return launch_tc(p, ceil_div(L.in_dim, tc::kBM), 1, *real_splits, s, "tc_conv_wgrad", max_ctas);   \
   }
   switch (L.out_dim) {
     case 32: ISDQN_CONV_WGRAD_TC(32)
@@ -376,10 +384,55 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts;
   };
   float* dz32 = wsp(ws, w.dq);
+  // Two streams: the chain  input gradient -> LayerNorm/ReLU backward -> input gradient ...  is the critical path; the
+  // weight gradient of every layer but the first only feeds the optimiser, so it runs on a side stream (forked off an
+  // event, joined before the partial reduction).  The Adam update of a hidden Dense kernel (97 % of the parameters of
+  // the Atari network) follows its weight gradient on the side stream as soon as the input-gradient GEMM that reads
+  // the same weights has finished, and the final Adam launch passes over that range.
+  cudaStream_t s2 = s, s3 = s;
+  const bool fork = !g_profile_on && !tr->nccl_comm && fork_enabled() && side_stream(0) != nullptr && side_stream(1) != nullptr;
+  if (fork) {
+    s2 = side_stream(0);  // weight gradients
+    s3 = side_stream(1);  // early Adam
+  }
+  // small batches are latency bound (every kernel is a fraction of a wave): keep the side work narrow so that it shares
+  // the SMs with the critical path instead of queueing in front of it; large batches are throughput bound: no cap
+  const bool narrow_side = fork && B <= 256;
+  const int side_cap = narrow_side ? kSideCtas : 0;
+  int n_ev = 0;
+  auto fork_to_side = [&]() -> int {
+    cudaEvent_t e = side_event(n_ev++);
+    if (!e) return ISDQN_E_CUDA;
+    ISDQN_CUDA_CHECK(cudaEventRecord(e, s));
+    ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s2, e, 0));
+    return ISDQN_OK;
+  };
+  int64_t pend_off = -1, pend_n = 0;    // Dense kernel whose early Adam waits for the next fork point
+  int64_t early_off = 0, early_n = 0;   // range already updated on the side stream
   for (int l = nl - 1; l >= 0; --l) {
     const Layer& L = p.L[l];
-    const bf16* dz16 = w16(wt, t.dz16[l & 1]);
+    const bf16* dz16 = w16(wt, t.dz16[l]);
     const int rows_l = B * L.pix;
+    const bool side = fork && l > 0;
+    cudaStream_t sw = side ? s2 : s;
+    if (side) {
+      rc = fork_to_side();  // everything the main stream has produced so far (dz of this layer, the input gradient above)
+      if (rc) return rc;
+      if (pend_n > 0) {
+        // after the weight gradient it consumes (side stream) and the input-gradient GEMM reading the same weights (main)
+        cudaEvent_t e = side_event(n_ev++);
+        if (!e) return ISDQN_E_CUDA;
+        ISDQN_CUDA_CHECK(cudaEventRecord(e, s2));
+        ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s3, e, 0));
+        ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s3, side_event(n_ev - 2), 0));
+        rc = isdqn_adam_launch(tr->d_params + pend_off, tr->d_grads + pend_off, tr->d_mu + pend_off, tr->d_nu + pend_off,
+                               tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps, pend_n, shadow + pend_off, s3, 0, 0, narrow_side ? 2 * kNumSMs : 0);
+        if (rc) return rc;
+        early_off = pend_off;
+        early_n = pend_n;
+        pend_n = 0;
+      }
+    }
     // ---- weight gradient
     if (l == nl - 1) {
       GemmArgs g;
@@ -394,17 +447,25 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         g.split_stride = (int64_t)L.in_dim * L.out_dim;
         add_seg(g.C, grads + L.w_off, g.split_stride, L.in_dim * L.out_dim, real_splits);
       }
-      rc = launch_simt_gemm(g, s, "head_wgrad_gemm");
+      rc = launch_simt_gemm(g, sw, "head_wgrad_gemm");
     } else if (L.type == 1) {
       rc = launch_gemm_tc<true, true>(w16(wt, t.act16[l - 1]), L.in_dim, dz16, L.out_dim, grads + L.w_off, L.out_dim, 0,
-                                      L.in_dim, L.out_dim, B, 1, s, "tc_dense_wgrad");
+                                      L.in_dim, L.out_dim, B, 1, sw, "tc_dense_wgrad", side ? side_cap : 0);
+      // (the early range must be the only one: the final Adam launch passes over a single range)
+      if (side && update && early_n == 0 && pend_n == 0 && ((int64_t)L.in_dim * L.out_dim) % 4 == 0 && L.w_off % 4 == 0) {
+        pend_off = L.w_off;
+        pend_n = (int64_t)L.in_dim * L.out_dim;
+      }
     } else {
       int real_splits = 1;
       float* part = wsp(ws, w.wpart[l]);
       if (l == 0 && t.x16 >= 0)
-        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, s, 1.0f / 255.0f);
-      else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, s);
-      else rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits[l], &real_splits, s);
+        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, sw, 1.0f / 255.0f,
+                                         side ? side_cap : 0);
+      else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, sw);
+      else
+        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits[l], &real_splits, sw, 1.0f,
+                                         side ? side_cap : 0);
       add_seg(part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
     }
     if (rc) return rc;
@@ -439,7 +500,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       const int rows_p = B * P.pix;
       const float* g_ = P.has_ln ? params + P.g_off : nullptr;
       const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
-      bf16* dz16_prev = w16(wt, t.dz16[(l - 1) & 1]);
+      bf16* dz16_prev = w16(wt, t.dz16[l - 1]);
       // the ReLU mask of a layer without LayerNorm needs its post-activation output: fp32 for Dense, bf16 for conv
       ISDQN_PROF(s, "ln_relu_bwd");
       if (ln_bwd_use_warp(P.out_dim)) {
@@ -455,6 +516,15 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     }
     dz32 = dprev;
   }
+  if (fork) {  // join
+    for (cudaStream_t x : {s2, s3}) {
+      if (x == s3 && early_n == 0) continue;  // (never forked: not part of a capture)
+      cudaEvent_t e = side_event(n_ev++);
+      if (!e) return ISDQN_E_CUDA;
+      ISDQN_CUDA_CHECK(cudaEventRecord(e, x));
+      ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s, e, 0));
+    }
+  }
   if (segs.count > 0) {
     const int n_tiles = finish_segments(&segs);
     ISDQN_PROF(s, "reduce_segments");
@@ -467,7 +537,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     if (rc) return rc;
   }
   return isdqn_adam_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
-                           p.layout.total, shadow, stream);
+                           p.layout.total, shadow, stream, early_off, early_n);
 }
 
 }  // namespace

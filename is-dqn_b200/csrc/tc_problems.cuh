@@ -45,6 +45,14 @@ struct __align__(16) RowInfo {
   short second;    // 1: the row's image lives in the second input pointer (the s' half of concat(s, s'))
 };
 constexpr int kInvalidRow = -(1 << 28);
+// (y0, x0) of a row packed into one register for the per-thread row copies: an invalid row keeps a y0 no tap can lift
+// back into the image
+__device__ __forceinline__ int pack_row_yx(const RowInfo& ri) {
+  const int y = ri.y0 == kInvalidRow ? -0x4000 : ri.y0;
+  return (y << 16) | ((int)ri.x0 & 0xffff);
+}
+__device__ __forceinline__ int row_y(int yx) { return yx >> 16; }
+__device__ __forceinline__ int row_x(int yx) { return (int)(short)(yx & 0xffff); }
 constexpr int kRowInfoBytes = 2 * kBM * (int)sizeof(RowInfo);  // double buffered (tile / chunk parity)
 
 // ------------------------------------------------------------------------------------------- generic loaders
@@ -121,6 +129,7 @@ struct GemmTC {
     c.m0 = m0;
     c.n0 = n0;
   }
+  __device__ void tile_rows(PCtx&, int) const {}
   __device__ void chunk_producer(PCtx&, uint8_t*, int, int, int) const {}
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
   __device__ void k_range(int split, int& b, int& e) const {
@@ -239,10 +248,22 @@ struct ConvFwdTC {
   struct PCtx {
     const ChunkEntry* tab;
     const RowInfo* rows;
+    // bf16 gather: thread ptid always fills 16-byte column (ptid & 7) of the rows (ptid >> 3) + i * PT/8
+    uint64_t row_addr[TASKS];  // byte address of the row's anchor element
+    int row_yx[TASKS];         // pack_row_yx
   };
   struct ECtx {};
   __device__ void init_cta(uint8_t* extra, int ptid) const {
     build_im2col_table(reinterpret_cast<ChunkEntry*>(extra), ((K + kBK - 1) / kBK) * 8, K, Cin, ksz, W, ptid, PT);
+  }
+  __device__ void tile_rows(PCtx& c, int ptid) const {
+    if (IN_U8_) return;
+#pragma unroll
+    for (int i = 0; i < TASKS; ++i) {
+      const RowInfo ri = c.rows[(ptid >> 3) + i * (PT / 8)];
+      c.row_addr[i] = (uint64_t)(uintptr_t)(ri.second ? in1 : in0) + (uint64_t)(ri.anchor * 2);
+      c.row_yx[i] = pack_row_yx(ri);
+    }
   }
   __device__ void tile_producer(PCtx& c, uint8_t* extra, int m0, int, int, int ptid, int ti) const {
     RowInfo* rows = reinterpret_cast<RowInfo*>(extra + kMaxChunks * sizeof(ChunkEntry)) + (ti & 1) * kBM;
@@ -255,11 +276,16 @@ struct ConvFwdTC {
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = (K + kBK - 1) / kBK; }
   __device__ void load_a(const PCtx& c, uint32_t stage, int kc, int ptid) const {
     if (!IN_U8_) {
+      const int ch = ptid & 7;
+      const ChunkEntry e = c.tab[kc * 8 + ch];
+      const int dy = e.yx >> 16, dx = e.yx & 0xffff;
+      const int64_t eoff = (int64_t)e.off * 2;
+      const uint32_t dst = stage + kmajor_off<true>(ptid >> 3, ch);  // rows 8 apart share the swizzle phase
 #pragma unroll
       for (int i = 0; i < TASKS; ++i) {
-        const int t = ptid + i * PT;
-        const int ch = t & 7, r = t >> 3;
-        gather_chunk_bf16(stage + kmajor_off<true>(r, ch), in0, in1, c.rows[r], c.tab[kc * 8 + ch], H, W);
+        const int iy = row_y(c.row_yx[i]) + dy, ix = row_x(c.row_yx[i]) + dx;
+        const bool v = e.yx >= 0 && (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+        cp_async16(dst + i * (PT / 8) * 128, v ? reinterpret_cast<const void*>((uintptr_t)(c.row_addr[i] + eoff)) : in0, v);
       }
     } else {
       uint2 px[TASKS];
@@ -364,6 +390,7 @@ struct ConvWgradTC {
     c.tab = reinterpret_cast<const ChunkEntry*>(extra) + m0 / 8;
     c.n0 = n0;
   }
+  __device__ void tile_rows(PCtx&, int) const {}
   __device__ void chunk_producer(PCtx& c, uint8_t* extra, int kc, int ptid, int j) const {
     RowInfo* rows = reinterpret_cast<RowInfo*>(extra + kMaxChunks * sizeof(ChunkEntry)) + (j & 1) * kBM;
     if (ptid < kBK) rows[ptid] = conv_row_info(kc * kBK + ptid, M, OH, OW, H, W, Cin, stride, pad_y, pad_x, 1 << 30);
@@ -427,7 +454,17 @@ struct ConvDgradTC {
     const ChunkEntry* tab;
     const int* wtab;
     const RowInfo* rows;  // anchor = element offset of dz[(img, oy, ox, 0)], (y0, x0) = (oy, ox)
+    uint64_t row_addr[TASKS];  // per-thread copies, as in ConvFwdTC
+    int row_yx[TASKS];
   };
+  __device__ void tile_rows(PCtx& c, int ptid) const {
+#pragma unroll
+    for (int i = 0; i < TASKS; ++i) {
+      const RowInfo ri = c.rows[(ptid >> 3) + i * (PT / 8)];
+      c.row_addr[i] = (uint64_t)(uintptr_t)dz + (uint64_t)(ri.anchor * 2);
+      c.row_yx[i] = pack_row_yx(ri);
+    }
+  }
   struct ECtx {
     int pix;
     bool valid;
@@ -504,15 +541,16 @@ struct ConvDgradTC {
   }
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = (Kd + kBK - 1) / kBK; }
   __device__ void load_a(const PCtx& c, uint32_t stage, int kc, int ptid) const {
+    const int ch = ptid & 7;
+    const ChunkEntry e = c.tab[kc * 8 + ch];
+    const int dy = e.yx >> 16, dx = e.yx & 0xffff;
+    const int64_t eoff = (int64_t)e.off * 2;
+    const uint32_t dst = stage + kmajor_off<true>(ptid >> 3, ch);
 #pragma unroll
     for (int i = 0; i < TASKS; ++i) {
-      const int t = ptid + i * PT;
-      const int ch = t & 7, r = t >> 3;
-      const RowInfo ri = c.rows[r];
-      const ChunkEntry e = c.tab[kc * 8 + ch];
-      const int oy = ri.y0 - (e.yx >> 16), ox = ri.x0 - (e.yx & 0xffff);
+      const int oy = row_y(c.row_yx[i]) - dy, ox = row_x(c.row_yx[i]) - dx;
       const bool v = e.yx >= 0 && (unsigned)oy < (unsigned)OH && (unsigned)ox < (unsigned)OW;
-      cp_async16(stage + kmajor_off<true>(r, ch), v ? dz + (ri.anchor + e.off) : dz, v);
+      cp_async16(dst + i * (PT / 8) * 128, v ? reinterpret_cast<const void*>((uintptr_t)(c.row_addr[i] + eoff)) : dz, v);
     }
   }
   __device__ void load_b(const PCtx& c, uint32_t stage, int kc, int ptid) const {
