@@ -260,6 +260,10 @@ int isdqn_dp_init(const uint8_t* h_unique_id_128, int32_t rank, int32_t world, v
 int isdqn_dp_allreduce_f32(void* comm, float* d_buf, int64_t n, void* stream);
 int isdqn_dp_destroy(void* comm);
 
+/* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
+ * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */
+int isdqn_trace_set(void* d_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,7 @@ PROTOTYPES = {
     "isdqn_profile_begin": (C.c_int, []),
     "isdqn_profile_end": (C.c_int, [_P, _I32, C.c_char_p, _I32, C.POINTER(C.c_float)]),
     "isdqn_spin": (C.c_int, [_P, _I32]),
+    "isdqn_trace_set": (C.c_int, [_P]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),

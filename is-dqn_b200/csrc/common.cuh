@@ -52,16 +52,39 @@ cudaEvent_t side_event(int i);
 // the columns first would wait on a grid that waits on it).  Opt-in with ISDQN_PDL=1 (measured slower at batch 32:
 // early-resident dependents compete with the running kernel); the instructions are no-ops without the attribute.
 bool pdl_enabled();
+
+// Optional device-side timeline (isdqn_trace_set): CTA (0,0,0) of every step kernel appends its start time (globaltimer,
+// ns) to a buffer — [0] = count, [1..] = times — which gives kernel-to-kernel intervals INSIDE a graph replay, where
+// neither events nor a profiler can look without perturbing it.  One (static) pointer per translation unit.
+static __device__ unsigned long long* g_trace_buf = nullptr;
+static inline cudaError_t trace_set_local(unsigned long long* p) { return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+__device__ __forceinline__ void trace_kernel_start() {
+  if ((threadIdx.x | blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+    unsigned long long* t = g_trace_buf;
+    if (t) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      const unsigned long long i = atomicAdd(t, 1ull);
+      if (i < 4000) t[1 + i] = now;
+    }
+  }
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() {
+  trace_kernel_start();
   pdl_trigger();
   pdl_wait();
 }
 
+// Experiment (ISDQN_CARVEOUT=1): give every kernel of the step the same (maximum) shared-memory carve-out so that the
+// SMs never reconfigure the L1/shared split between a tensor-core kernel and a small streaming one.  Measured slower.
+void prefer_max_shared_once(const void* kernel);
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args&&... args) {
+  prefer_max_shared_once(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -73,6 +96,35 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint).  The optimiser state of the Atari network
+// (parameters, both Adam moments, the bf16 shadow: 57 MB) fits the 126 MB L2 next to everything else a batch-32 step
+// touches; marking it evict_last keeps it resident from one step to the next, so Adam streams from L2, not HBM.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float4* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_f4_hint(float4* ptr, const float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_u2_hint(uint2* ptr, const uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(ptr), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
 
 template <typename T>

@@ -252,9 +252,8 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
     dz = dprev;
   }
   if (segs.count > 0) {
-    const int n_tiles = finish_segments(&segs);
     ISDQN_PROF(s, "reduce_segments");
-    ISDQN_CUDA_CHECK(launch_pdl(reduce_segments_kernel, dim3(n_tiles), dim3(256), 0, s, segs));
+    ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s));
   }
   return ISDQN_OK;
 }
@@ -432,3 +431,5 @@ extern "C" int isdqn_best_action(const isdqn_net* net, const float* d_params, co
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
+
+int isdqn_trace_set_learner(unsigned long long* buf) { return isdqn::trace_set_local(buf) == cudaSuccess ? ISDQN_OK : ISDQN_E_CUDA; }

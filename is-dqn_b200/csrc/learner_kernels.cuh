@@ -691,6 +691,118 @@ ln_relu_bwd_block_kernel(float* __restrict__ d, const float* __restrict__ xhat, 
   }
 }
 
+// Whole backward pass of the head layer + the ReLU/LayerNorm backward of the last hidden layer in ONE launch (small
+// batches: three dependent launches of ~10 us each otherwise).  Two roles by blockIdx.x:
+//   [0, row_ctas)        rows b = blockIdx.x, += row_ctas ...:  d[b][n] = sum_k dq[b][k] Wh[n][k]  (input gradient of the
+//                        head layer), then exactly ln_relu_bwd_block_kernel's LayerNorm/ReLU backward of that row;
+//   [row_ctas, gridDim)  one thread per element of the head kernel gradient: dWh[n][k] = sum_b act[b][n] dq[b][k].
+// Both sums run over their index in ascending order with fmaf, as gemm_strided_kernel does, and skip terms whose dq
+// factor is exactly zero — which leaves the fp32 result bit-identical (x + 0*w == x) and makes use of the TD loss
+// gradient being zero outside the taken action of every head (isdqn.py:97-103).
+static __global__ void __launch_bounds__(kRowThreads)
+head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ wh, const float* __restrict__ act_in, int B, int C,
+                int NH, int row_ctas, float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
+                const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ colpart,
+                __nv_bfloat16* __restrict__ dz16, float* __restrict__ dwh) {
+  pdl_sync();
+  __shared__ float red[kRowThreads / 32];
+  __shared__ float nzv[128];
+  __shared__ int nzk[128];
+  __shared__ int nnz_sh;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= row_ctas) {  // ---- head kernel gradient
+    const int o = ((int)blockIdx.x - row_ctas) * kRowThreads + tid;
+    if (o < C * NH) {
+      const int n = o / NH, k = o - n * NH;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int b = 0; b < B; ++b) {
+        const float g = dq[(int64_t)b * NH + k];
+        if (g != 0.f) acc = fmaf(act_in[(int64_t)b * C + n], g, acc);
+      }
+      dwh[o] = acc;
+    }
+    return;
+  }
+  float c0[kRowMaxPerThread], c1[kRowMaxPerThread], c2[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    c0[j] = c1[j] = c2[j] = 0.f;
+    const int n = tid + j * kRowThreads;
+    gam[j] = (ln_g && n < C) ? ln_g[n] : 0.f;
+    bet[j] = (ln_g && n < C) ? ln_b[n] : 0.f;
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int r = blockIdx.x; r < B; r += row_ctas) {
+    __syncthreads();  // (the previous row's list is no longer read)
+    if (tid < 32) {   // compact the non-zero entries of dq[r][:] in ascending k (NH <= 128)
+      int base = 0;
+      for (int c = 0; c < NH; c += 32) {
+        const int k = c + tid;
+        const float v = k < NH ? dq[(int64_t)r * NH + k] : 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+        if (v != 0.f) {
+          const int pos = base + __popc(m & ((1u << tid) - 1u));
+          nzv[pos] = v;
+          nzk[pos] = k;
+        }
+        base += __popc(m);
+      }
+      if (tid == 0) nnz_sh = base;
+    }
+    __syncthreads();
+    const int nnz = nnz_sh;
+    float dy[kRowMaxPerThread], xh[kRowMaxPerThread];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = tid + j * kRowThreads;
+      dy[j] = xh[j] = 0.f;
+      if (n < C) {
+        float dv = 0.f;
+        for (int i = 0; i < nnz; ++i) dv = fmaf(nzv[i], __ldg(wh + (int64_t)n * NH + nzk[i]), dv);
+        const int64_t idx = (int64_t)r * C + n;
+        if (ln_g) {
+          xh[j] = xhat[idx];
+          dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;
+          const float g = dy[j] * gam[j];
+          sg += g;
+          sgx += g * xh[j];
+        } else {
+          dy[j] = act_in[idx] > 0.f ? dv : 0.f;
+        }
+      }
+    }
+    float rs = 0.f, mg = 0.f, mgx = 0.f;
+    if (ln_g) {
+      mg = block_sum_256(sg, red) * inv_c;
+      mgx = block_sum_256(sgx, red) * inv_c;
+      rs = rstd[r];
+    }
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = tid + j * kRowThreads;
+      if (n < C) {
+        const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
+        d[(int64_t)r * C + n] = dz;
+        if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
+        c0[j] += dz;
+        c1[j] += dy[j] * xh[j];
+        c2[j] += dy[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = tid + j * kRowThreads;
+    if (n < C) {
+      colpart[((int64_t)blockIdx.x * 3 + 0) * C + n] = c0[j];
+      colpart[((int64_t)blockIdx.x * 3 + 1) * C + n] = c1[j];
+      colpart[((int64_t)blockIdx.x * 3 + 2) * C + n] = c2[j];
+    }
+  }
+}
+
 // --------------------------------------------------------------------------- deterministic partial reduce
 constexpr int kMaxSegments = 40;
 struct Segment {
@@ -704,49 +816,94 @@ struct SegmentList {
   int tile_start[kMaxSegments + 1];  // prefix sum of ceil(n / 32) over the segments (filled by finish_segments)
   Segment s[kMaxSegments];
 };
-static inline int finish_segments(SegmentList* l) {
+// tile = 32 lanes x VEC elements; returns the grid size.  VEC = 4 needs every segment 16-byte aligned (checked by
+// segments_vec4_ok)
+static inline int finish_segments(SegmentList* l, int vec) {
   int t = 0;
   for (int i = 0; i < l->count; ++i) {
     l->tile_start[i] = t;
-    t += (l->s[i].n + 31) / 32;
+    t += (l->s[i].n + 32 * vec - 1) / (32 * vec);
   }
   l->tile_start[l->count] = t;
-  return t;  // = grid size of reduce_segments_kernel
+  return t;
+}
+static inline bool segments_vec4_ok(const SegmentList& l) {
+  for (int i = 0; i < l.count; ++i) {
+    const Segment& g = l.s[i];
+    if ((g.n & 3) || (g.stride & 3) || (reinterpret_cast<uintptr_t>(g.src) & 15) || (reinterpret_cast<uintptr_t>(g.dst) & 15))
+      return false;
+  }
+  return true;
 }
 
-// One CTA sums ONE tile of 32 elements of one segment (grid = all tiles of all segments, so every partial of the
+// One CTA sums ONE tile of 32 x VEC elements of one segment (grid = all tiles of all segments, so every partial of the
 // step is in flight at once): its 8 warps take the partials p = w, w+8, ... (independent loads), then the 8 warp sums
-// are combined in a fixed order => deterministic.
-static __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
+// are combined in a fixed order => deterministic, and identical for VEC = 1 and VEC = 4.
+template <int VEC>
+__global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
   pdl_sync();
-  __shared__ float sm[8][33];
+  __shared__ float sm[8][32 * VEC + 4];
   int seg = 0;
   while (seg + 1 < list.count && (int)blockIdx.x >= list.tile_start[seg + 1]) ++seg;
   const Segment sg = list.s[seg];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int i = ((int)blockIdx.x - list.tile_start[seg]) * 32 + lane;
-  float t = 0.f;
+  const int i = (((int)blockIdx.x - list.tile_start[seg]) * 32 + lane) * VEC;
+  float t[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) t[v] = 0.f;
   if (i < sg.n) {
     const float* src = sg.src + i;
+    auto load = [&](int p, float (&x)[VEC]) {
+      if (VEC == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(src + (int64_t)p * sg.stride);
+        x[0] = q.x; x[VEC > 1 ? 1 : 0] = q.y; x[VEC > 2 ? 2 : 0] = q.z; x[VEC > 3 ? 3 : 0] = q.w;
+      } else {
+        x[0] = src[(int64_t)p * sg.stride];
+      }
+    };
     int p = w;
     for (; p + 24 < sg.parts; p += 32) {  // four independent loads per warp iteration
-      const float a0 = src[(int64_t)p * sg.stride], a1 = src[(int64_t)(p + 8) * sg.stride];
-      const float a2 = src[(int64_t)(p + 16) * sg.stride], a3 = src[(int64_t)(p + 24) * sg.stride];
-      t += a0;
-      t += a1;
-      t += a2;
-      t += a3;
-    }
-    for (; p < sg.parts; p += 8) t += src[(int64_t)p * sg.stride];
-  }
-  sm[w][lane] = t;
-  __syncthreads();
-  if (w == 0 && i < sg.n) {
-    float tot = sm[0][lane];
+      float a0[VEC], a1[VEC], a2[VEC], a3[VEC];
+      load(p, a0);
+      load(p + 8, a1);
+      load(p + 16, a2);
+      load(p + 24, a3);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) tot += sm[k][lane];
-    sg.dst[i] = tot;
+      for (int v = 0; v < VEC; ++v) {
+        t[v] += a0[v];
+        t[v] += a1[v];
+        t[v] += a2[v];
+        t[v] += a3[v];
+      }
+    }
+    for (; p < sg.parts; p += 8) {
+      float a0[VEC];
+      load(p, a0);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) t[v] += a0[v];
+    }
   }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) sm[w][lane * VEC + v] = t[v];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * VEC; e += 256) {
+    const int idx = (((int)blockIdx.x - list.tile_start[seg]) * 32) * VEC + e;
+    if (idx < sg.n) {
+      float tot = sm[0][e];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) tot += sm[k][e];
+      sg.dst[idx] = tot;
+    }
+  }
+}
+
+static inline cudaError_t launch_reduce_segments(SegmentList& segs, cudaStream_t s) {
+  if (segments_vec4_ok(segs)) {
+    const int n_tiles = finish_segments(&segs, 4);
+    return launch_pdl((reduce_segments_kernel<4>), dim3(n_tiles), dim3(256), 0, s, segs);
+  }
+  const int n_tiles = finish_segments(&segs, 1);
+  return launch_pdl((reduce_segments_kernel<1>), dim3(n_tiles), dim3(256), 0, s, segs);
 }
 
 // ------------------------------------------------------------------------------ K-head TD loss fwd + bwd
@@ -836,12 +993,95 @@ head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   if (n < N) {
     const int kq = (K + 3) / 4;
     const int k_end = min(K, (g + 1) * kq);
-#pragma unroll 8
+#pragma unroll 32
     for (int k = g * kq; k < k_end; ++k) acc = fmaf(xs[k], __ldg(w + (int64_t)k * N + n), acc);
   }
   part[g][n] = acc;
   __syncthreads();
   if (g == 0 && n < N) out[(int64_t)r * N + n] = ((part[0][n] + part[1][n]) + (part[2][n] + part[3][n])) + bias[n];
+}
+
+// dense_finalize_kernel + head_fwd_kernel in one launch (the tensor-core path at small batch is bound by the number of
+// dependent launches): one CTA per row finishes the hidden Dense layer (split-K partial sum, bias, LayerNorm, ReLU; the
+// first 256 threads, same arithmetic order as dense_finalize_kernel), keeps the row in shared memory and multiplies
+// it with the head kernel (all 512 threads, same order as head_fwd_kernel).  N <= 2048 hidden units, NH <= 128 outputs.
+static __global__ void __launch_bounds__(512)
+dense_finalize_head_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int N,
+                           const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                           int relu, float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd, int rows_train,
+                           const float* __restrict__ wh, const float* __restrict__ bh, int NH, float* __restrict__ out_head) {
+  pdl_sync();
+  extern __shared__ float xs[];  // [N]
+  __shared__ float red[16];
+  __shared__ float hpart[4][128];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const bool fin = tid < kRowThreads;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowThreads / 32; ++w) t += red[w];  // (warps 8..15 hold zeros)
+    __syncthreads();
+    return t;
+  };
+  float z[kRowMaxPerThread];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = tid + j * kRowThreads;
+    z[j] = 0.f;
+    if (fin && n < N) {
+      float v = 0.f;
+      for (int sp = 0; sp < splits; ++sp) v += part[(int64_t)sp * split_stride + (int64_t)r * N + n];
+      z[j] = v + bias[n];
+      s += z[j];
+    }
+  }
+  float rs = 0.f;
+  if (ln_g) {
+    const float mean = block_sum(s) / (float)N;
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = tid + j * kRowThreads;
+      if (fin && n < N) {
+        z[j] -= mean;
+        s2 += z[j] * z[j];
+      }
+    }
+    rs = rsqrtf(block_sum(s2) / (float)N + kLnEps);
+  }
+  const bool save = ln_g && xhat && r < rows_train;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = tid + j * kRowThreads;
+    if (fin && n < N) {
+      float y = z[j];
+      if (ln_g) {
+        const float xh = z[j] * rs;
+        if (save) xhat[(int64_t)r * N + n] = xh;
+        y = xh * ln_g[n] + ln_b[n];
+      }
+      y = relu ? fmaxf(y, 0.f) : y;
+      out[(int64_t)r * N + n] = y;
+      xs[n] = y;
+    }
+  }
+  if (save && tid == 0) rstd[r] = rs;
+  __syncthreads();
+  const int n = tid & 127, g = tid >> 7;
+  float acc = 0.f;
+  if (n < NH) {
+    const int kq = (N + 3) / 4;
+    const int k_end = min(N, (g + 1) * kq);
+#pragma unroll 32
+    for (int k = g * kq; k < k_end; ++k) acc = fmaf(xs[k], __ldg(wh + (int64_t)k * NH + n), acc);
+  }
+  hpart[g][n] = acc;
+  __syncthreads();
+  if (g == 0 && n < NH) out_head[(int64_t)r * NH + n] = ((hpart[0][n] + hpart[1][n]) + (hpart[2][n] + hpart[3][n])) + bh[n];
 }
 
 // ------------------------------------------------------------------------------------------------- Adam
@@ -858,24 +1098,26 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   const float c1 = (float)(1.0 - pow((double)b1, (double)t));
   const float c2 = (float)(1.0 - pow((double)b2, (double)t));
   const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
+  const uint64_t keep = l2_policy_evict_last(), stream_once = l2_policy_evict_first();
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = j < skip_begin4 ? j : j + skip_len4;
-    const float4 gv = reinterpret_cast<const float4*>(g)[i];
-    float4 mv = reinterpret_cast<float4*>(mu)[i];
-    float4 vv = reinterpret_cast<float4*>(nu)[i];
-    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = ld_f4_hint(reinterpret_cast<const float4*>(g) + i, stream_once);
+    float4 mv = ld_f4_hint(reinterpret_cast<const float4*>(mu) + i, keep);
+    float4 vv = ld_f4_hint(reinterpret_cast<const float4*>(nu) + i, keep);
+    float4 pv = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, keep);
 #define ISDQN_ADAM1(c)                                    \
   mv.c = ob1 * gv.c + b1 * mv.c;                          \
   vv.c = ob2 * (gv.c * gv.c) + b2 * vv.c;                 \
   pv.c -= lr * ((mv.c / c1) / (sqrtf(vv.c / c2) + eps));
     ISDQN_ADAM1(x) ISDQN_ADAM1(y) ISDQN_ADAM1(z) ISDQN_ADAM1(w)
 #undef ISDQN_ADAM1
-    reinterpret_cast<float4*>(mu)[i] = mv;
-    reinterpret_cast<float4*>(nu)[i] = vv;
-    reinterpret_cast<float4*>(p)[i] = pv;
+    st_f4_hint(reinterpret_cast<float4*>(mu) + i, mv, keep);
+    st_f4_hint(reinterpret_cast<float4*>(nu) + i, vv, keep);
+    st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, keep);
     if (shadow) {  // bf16 copy of the updated parameters for the tensor-core path of the next step
       __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
-      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      st_u2_hint(reinterpret_cast<uint2*>(shadow) + i, make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi)),
+                 keep);
     }
   }
 }

@@ -15,6 +15,20 @@ void set_last_cuda_error(cudaError_t e, const char* where) {
 // ---------------------------------------------------------------------------------------------- profiler
 bool g_profile_on = false;
 
+void prefer_max_shared_once(const void* kernel) {
+  static const void* seen[256];
+  static int n_seen = 0;
+  static const bool off = [] {
+    const char* e = getenv("ISDQN_CARVEOUT");  // opt-in: measured 6 % slower at batch 32 (the small kernels lose L1)
+    return !(e && e[0] == '1');
+  }();
+  if (off) return;
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i] == kernel) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  if (n_seen < 256) seen[n_seen++] = kernel;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("ISDQN_PDL");  // opt-in: measured 5 % SLOWER on the batch-32 step (profiles/r01_summary.md)
@@ -234,4 +248,14 @@ extern "C" int isdqn_dp_destroy(void* comm) {
   if (!comm) return ISDQN_OK;
   if (!g_nccl.handle) return ISDQN_E_NCCL;
   return nccl_check(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}
+
+// Device-side kernel-start timeline (common.cuh: trace_kernel_start).  d_buf: uint64[4001] zero-initialised device memory
+// (NULL switches it off).  Diagnostic only.
+int isdqn_trace_set_learner(unsigned long long* buf);
+int isdqn_trace_set_tc(unsigned long long* buf);
+extern "C" int isdqn_trace_set(void* d_buf) {
+  int rc = isdqn_trace_set_learner(reinterpret_cast<unsigned long long*>(d_buf));
+  if (rc) return rc;
+  return isdqn_trace_set_tc(reinterpret_cast<unsigned long long*>(d_buf));
 }

@@ -180,7 +180,8 @@ constexpr int kFirstProducerWarp = 5;
 //              epilogue, arrives on tmem_empty[a] — so the gather of tile i+1 overlaps the epilogue of tile i.
 //
 // P (the problem) provides:
-//   static constexpr int BN, STAGES, PRODUCER_WARPS, EXTRA_BYTES; static constexpr bool A_MN, B_MN, CHUNK_SYNC;
+//   static constexpr int BN, STAGES, PRODUCER_WARPS, EXTRA_BYTES, EP_FLOATS; static constexpr bool A_MN, B_MN, CHUNK_SYNC;
+//   __device__ void init_epilogue(ECtx&, float* ep_sm, int etid) const;        (EP_FLOATS > 0 only; an epilogue barrier follows)
 //   (the A stage is always 128B-swizzled; the B stage is swizzled when BN >= 64, core-matrix layout for BN == 32)
 //   struct PCtx, ECtx;
 //   __device__ void init_cta(uint8_t* extra, int ptid) const;                  (producers only; a producer barrier follows)
@@ -205,8 +206,10 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_sh;
   __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
+  __shared__ __align__(16) float ep_sm[P::EP_FLOATS > 0 ? P::EP_FLOATS : 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  trace_kernel_start();
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * kABytes;
   const int n_tiles = tiles_x * tiles_y * tiles_z;
@@ -305,6 +308,10 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
     typename P::ECtx ectx;
     int ti = 0;
     pdl_wait();
+    if (P::EP_FLOATS > 0) {  // per-channel epilogue parameters -> shared memory, once per CTA, while the first tile is gathered
+      p.init_epilogue(ectx, ep_sm, tid);
+      named_bar_sync(2, 32 * kEpilogueWarps);
+    }
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
       const int m0 = tx * kBM, n0 = ty * BN;

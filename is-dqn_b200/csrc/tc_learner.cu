@@ -55,9 +55,15 @@ namespace {
 
 inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret_cast<float*>(ws) + off; }
 
+// Same problem with a deeper shared-memory ring (the producers keep STAGES-1 chunks of asynchronous copies in flight)
+template <class P, int S>
+struct WithStages : P {
+  static constexpr int STAGES = S;
+};
+
 // Persistent launch: the tiles (x fastest) are dealt round-robin to min(#tiles, SMs x resident CTAs) CTAs.
 template <class P>
-int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0) {
+int launch_tc_impl(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas) {
   constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
   constexpr int threads = 32 * (tc::kFirstProducerWarp + P::PRODUCER_WARPS);
   static int ctas_per_sm = 0;
@@ -67,6 +73,7 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
                                           (int)cudaSharedmemCarveoutMaxShared));
     // Resident CTAs per SM from the kernel's own resources (228 KB shared memory with 1 KB reserved per CTA, 64 K
     // registers allocated per warp in units of 256, 2048 threads, 512 TMEM columns: every CTA owns two accumulators).
+    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for these kernels whatever the carve-out.)
     cudaFuncAttributes fa;
     ISDQN_CUDA_CHECK(cudaFuncGetAttributes(&fa, tc::tc_gemm_kernel<P>));
     const int by_smem = (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024));
@@ -77,12 +84,9 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
     int occ = by_smem < by_regs ? by_smem : by_regs;
     if (occ > by_threads) occ = by_threads;
     if (occ > by_tmem) occ = by_tmem;
-    if (getenv("ISDQN_DEBUG_OCC")) {
-      int api = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&api, tc::tc_gemm_kernel<P>, threads, smem);
-      fprintf(stderr, "[isdqn] %s: regs %d static smem %zu dyn %zu threads %d -> smem %d regs %d thr %d tmem %d (api %d)\n", tag,
-              fa.numRegs, fa.sharedSizeBytes, smem, threads, by_smem, by_regs, by_threads, by_tmem, api);
-    }
+    if (getenv("ISDQN_DEBUG_OCC"))
+      fprintf(stderr, "[isdqn] %s: regs %d static smem %zu dyn %zu threads %d -> smem %d regs %d thr %d tmem %d\n", tag,
+              fa.numRegs, fa.sharedSizeBytes, smem, threads, by_smem, by_regs, by_threads, by_tmem);
     ctas_per_sm = occ < 1 ? 1 : occ;
   }
   const int64_t n_tiles = (int64_t)tiles_x * tiles_y * tiles_z;
@@ -94,6 +98,24 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
   ISDQN_CUDA_CHECK(launch_pdl((tc::tc_gemm_kernel<P>), dim3(grid), dim3(threads), smem, s, p, tiles_x, tiles_y, tiles_z));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
+}
+
+// A launch that is a single partial wave is latency bound (batch 32): every CTA walks its reduction axis once, so the
+// only lever is how many chunks are in flight — take the 8-stage ring (one CTA per SM is all such a launch needs).
+template <class P>
+int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0) {
+  if constexpr (P::BN <= 64) {
+    static const bool deep = [] {
+      const char* e = getenv("ISDQN_DEEP_RING");
+      return !(e && e[0] == '0');
+    }();
+    if (deep && (int64_t)tiles_x * tiles_y * tiles_z <= kNumSMs) {
+      WithStages<P, 8> q;
+      static_cast<P&>(q) = p;
+      return launch_tc_impl(q, tiles_x, tiles_y, tiles_z, s, tag, max_ctas);
+    }
+  }
+  return launch_tc_impl(p, tiles_x, tiles_y, tiles_z, s, tag, max_ctas);
 }
 
 int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
@@ -186,12 +208,12 @@ bool tc_eligible(const Plan& p, const isdqn_net* net) {
   return true;
 }
 
-template <bool U8>
+template <bool U8, bool SEG4 = false>
 int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0, int rows, const bf16* w, const float* params,
                        bf16* out, float* xhat, float* rstd, int m_train, cudaStream_t s, float in_scale = 1.0f) {
 #define ISDQN_CONV_FWD_TC(BN)                                                                          \
   {                                                                                                    \
-    tc::ConvFwdTC<BN, U8> p;                                                                           \
+    tc::ConvFwdTC<BN, U8, SEG4> p;                                                                     \
     p.in0 = in0; p.in1 = in1; p.n_img0 = n0;                                                           \
     p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;                \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
@@ -213,7 +235,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
 #undef ISDQN_CONV_FWD_TC
 }
 
-template <bool U8>
+template <bool U8, bool SEG4 = false>
 int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* part, int rows, int splits, int* real_splits,
                          cudaStream_t s, float in_scale = 1.0f, int max_ctas = 0) {
   const int total_chunks = ceil_div(rows, tc::kBK);
@@ -221,7 +243,7 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
   *real_splits = ceil_div(total_chunks, cps);
 #define ISDQN_CONV_WGRAD_TC(BN)                                                                        \
   {                                                                                                    \
-    tc::ConvWgradTC<BN, U8> p;                                                                         \
+    tc::ConvWgradTC<BN, U8, SEG4> p;                                                                   \
     p.in = in; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;     \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
     p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
@@ -325,8 +347,12 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         ISDQN_CUDA_CHECK(launch_pdl(u8_frames_to_bf16_kernel, dim3((unsigned)grid), dim3(256), 0, s,
                                     reinterpret_cast<const uint8_t*>(b->d_state), reinterpret_cast<const uint8_t*>(b->d_next_state),
                                     w16(wt, t.x16), n16));
-        rc = launch_conv_fwd_tc<false>(L, w16(wt, t.x16), nullptr, rows, rows, shadow + L.w_off, params, w16(wt, t.act16[l]), xhat,
-                                       rstd, rows_train * L.pix, s, 1.0f / 255.0f);
+        if (L.ksz * L.Cin == 32)  // 64-byte image rows per window: the lane mapping that keeps a warp on few cache lines
+          rc = launch_conv_fwd_tc<false, true>(L, w16(wt, t.x16), nullptr, rows, rows, shadow + L.w_off, params,
+                                               w16(wt, t.act16[l]), xhat, rstd, rows_train * L.pix, s, 1.0f / 255.0f);
+        else
+          rc = launch_conv_fwd_tc<false>(L, w16(wt, t.x16), nullptr, rows, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
+                                         xhat, rstd, rows_train * L.pix, s, 1.0f / 255.0f);
       } else if (l == 0)
         rc = launch_conv_fwd_tc<true>(L, b->d_state, b->d_next_state, B, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
                                       xhat, rstd, rows_train * L.pix, s);
@@ -343,11 +369,21 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       rc = launch_gemm_tc<false, true>(w16(wt, t.act16[l - 1]), L.in_dim, shadow + L.w_off, L.out_dim, wsp(ws, w.fwd_part),
                                        L.out_dim, split_stride, rows, L.out_dim, L.in_dim, splits, s, "tc_dense_fwd");
       if (rc) return rc;
-      ISDQN_PROF(s, "dense_finalize");
-      ISDQN_CUDA_CHECK(launch_pdl(dense_finalize_kernel, dim3(rows), dim3(kRowThreads), 0, s, wsp(ws, w.fwd_part), real_splits, split_stride, rows, L.out_dim,
-                                                         params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]), xhat, rstd,
-                                                         rows_train, w16(wt, t.act16[l])));
-      ISDQN_LAUNCH_CHECK();
+      const Layer& Hd = p.L[l + 1];
+      if (l + 2 == nl && rows <= 1024 && Hd.out_dim <= 128 && L.out_dim <= kRowThreads * kRowMaxPerThread) {
+        // last hidden layer: finish it and apply the (fp32) head layer in the same launch
+        ISDQN_PROF(s, "dense_finalize_head");
+        ISDQN_CUDA_CHECK(launch_pdl(dense_finalize_head_kernel, dim3(rows), dim3(512), L.out_dim * sizeof(float), s,
+                                    wsp(ws, w.fwd_part), real_splits, split_stride, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu,
+                                    wsp(ws, w.act[l]), xhat, rstd, rows_train, params + Hd.w_off, params + Hd.b_off, Hd.out_dim,
+                                    wsp(ws, w.act[l + 1])));
+        ++l;  // the head layer is done
+      } else {  // (large batches: two launches, each with all its threads busy)
+        ISDQN_PROF(s, "dense_finalize");
+        ISDQN_CUDA_CHECK(launch_pdl(dense_finalize_kernel, dim3(rows), dim3(kRowThreads), 0, s, wsp(ws, w.fwd_part), real_splits,
+                                    split_stride, rows, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]), xhat,
+                                    rstd, rows_train, w16(wt, t.act16[l])));
+      }
     } else if (L.out_dim <= 128 && L.in_dim <= 8192) {  // head layer: fp32 (N = (1+K)A is tiny, not 16-byte aligned)
       ISDQN_PROF(s, "head_fwd");
       ISDQN_CUDA_CHECK(launch_pdl(head_fwd_kernel, dim3(rows), dim3(512), L.in_dim * sizeof(float), s, wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
@@ -413,6 +449,22 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     const Layer& L = p.L[l];
     const bf16* dz16 = w16(wt, t.dz16[l]);
     const int rows_l = B * L.pix;
+    if (l == nl - 1 && l >= 1 && p.L[l - 1].type == 1 && B <= 256 && w.wsplits[l] == 1 && L.out_dim <= 128 &&
+        p.L[l - 1].out_dim <= kRowThreads * kRowMaxPerThread) {
+      // small batch: head weight gradient + head input gradient + LayerNorm/ReLU backward of the hidden layer, one launch
+      const Layer& P = p.L[l - 1];
+      float* dprev = wsp(ws, w.dbuf[l & 1]);
+      const int row_ctas = w.col_ctas[l - 1];
+      const int wg_ctas = ceil_div(P.out_dim * L.out_dim, kRowThreads);
+      ISDQN_PROF(s, "head_bwd");
+      ISDQN_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3(row_ctas + wg_ctas), dim3(kRowThreads), 0, s, dz32, params + L.w_off,
+                                  wsp(ws, w.act[l - 1]), B, P.out_dim, L.out_dim, row_ctas, dprev, wsp(ws, w.xhat[l - 1]),
+                                  wsp(ws, w.rstd[l - 1]), P.has_ln ? params + P.g_off : nullptr,
+                                  P.has_ln ? params + P.beta_off : nullptr, wsp(ws, w.colpart[l - 1]), w16(wt, t.dz16[l - 1]),
+                                  grads + L.w_off));
+      dz32 = dprev;
+      continue;
+    }
     const bool side = fork && l > 0;
     cudaStream_t sw = side ? s2 : s;
     if (side) {
@@ -459,7 +511,10 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     } else {
       int real_splits = 1;
       float* part = wsp(ws, w.wpart[l]);
-      if (l == 0 && t.x16 >= 0)
+      if (l == 0 && t.x16 >= 0 && L.ksz * L.Cin == 32)
+        rc = launch_conv_wgrad_tc<false, true>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, sw,
+                                               1.0f / 255.0f, side ? side_cap : 0);
+      else if (l == 0 && t.x16 >= 0)
         rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, sw, 1.0f / 255.0f,
                                          side ? side_cap : 0);
       else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, sw);
@@ -526,9 +581,8 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     }
   }
   if (segs.count > 0) {
-    const int n_tiles = finish_segments(&segs);
     ISDQN_PROF(s, "reduce_segments");
-    ISDQN_CUDA_CHECK(launch_pdl(reduce_segments_kernel, dim3(n_tiles), dim3(256), 0, s, segs));
+    ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s));
   }
   if (!update) return ISDQN_OK;
   if (tr->nccl_comm) {
@@ -587,3 +641,5 @@ extern "C" int isdqn_tc_gemm_bf16(const void* d_a, int64_t lda, int32_t a_mn_maj
   if (b_mn_major) return launch_gemm_tc<false, true>(A, lda, B, ldb, d_c, N, ss, M, N, K, splits, s, "tc_gemm");
   return launch_gemm_tc<false, false>(A, lda, B, ldb, d_c, N, ss, M, N, K, splits, s, "tc_gemm");
 }
+
+int isdqn_trace_set_tc(unsigned long long* buf) { return isdqn::trace_set_local(buf) == cudaSuccess ? ISDQN_OK : ISDQN_E_CUDA; }

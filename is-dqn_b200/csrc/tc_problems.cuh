@@ -113,7 +113,7 @@ __device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, float* _
 // D[M][N] = sum_k A(m,k) B(n,k); A: K-major [M][lda] or MN-major [K][lda]; B likewise.  fp32 output (partials).
 template <int BN_, bool A_MN_, bool B_MN_>
 struct GemmTC {
-  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4, EXTRA_BYTES = 0;
+  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4, EXTRA_BYTES = 0, EP_FLOATS = 0;
   static constexpr int PT = 32 * PRODUCER_WARPS;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, B_SW = BN_ >= 64;
   const bf16* A; int64_t lda;
@@ -130,6 +130,7 @@ struct GemmTC {
     c.n0 = n0;
   }
   __device__ void tile_rows(PCtx&, int) const {}
+  __device__ void init_epilogue(ECtx&, float*, int) const {}
   __device__ void chunk_producer(PCtx&, uint8_t*, int, int, int) const {}
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
   __device__ void k_range(int split, int& b, int& e) const {
@@ -233,10 +234,16 @@ __device__ __forceinline__ void store_chunk_u8(uint32_t dst, const uint2 p) {
 // ------------------------------------------------------------------------------------------------ conv forward
 // out[m][co] = ReLU(LN(sum_k im2col(x)[m][k] W[k][co] + bias)); A gathered K-major, B = W (HWIO = [K][Cout]) MN-major.
 // IN_U8 requires Cin == 4 (the stacked Atari frames); bf16 input requires Cin % 8 == 0.
-template <int BN_, bool IN_U8_>
+// SEG4: one image row of a window is only 64 contiguous bytes (4 chunks; the 8x8x4 first convolution): the lanes of a
+// warp then take 4 chunks x 8 CONSECUTIVE output pixels, whose windows overlap in memory, instead of 8 chunks (two
+// image rows) x 4 pixels — a third of the distinct 128-byte lines per LDGSTS, which is what bounds that kernel (the
+// L1 data pipe: profiles/r01_summary.md).
+template <int BN_, bool IN_U8_, bool SEG4_ = false>
 struct ConvFwdTC {
+  __device__ static int task_ch(int ptid) { return SEG4_ ? ((ptid >> 5) & 1) * 4 + (ptid & 3) : (ptid & 7); }
+  __device__ static int task_r0(int ptid) { return SEG4_ ? (ptid >> 6) * 8 + ((ptid & 31) >> 2) : (ptid >> 3); }
   static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = IN_U8_ ? 8 : 4;
-  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT;
+  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT, EP_FLOATS = 3 * BN_;
   static constexpr int EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry) + kRowInfoBytes;
   static constexpr bool A_MN = false, B_MN = true, CHUNK_SYNC = false, B_SW = BN_ >= 64;
   const void* in0; const void* in1; int n_img0;
@@ -252,7 +259,17 @@ struct ConvFwdTC {
     uint64_t row_addr[TASKS];  // byte address of the row's anchor element
     int row_yx[TASKS];         // pack_row_yx
   };
-  struct ECtx {};
+  struct ECtx {
+    const float* prm;  // shared memory: bias[BN] | ln_g[BN] | ln_b[BN]
+  };
+  __device__ void init_epilogue(ECtx& e, float* ep_sm, int etid) const {
+    for (int i = etid; i < BN; i += kThreads) {
+      ep_sm[i] = bias[i];
+      ep_sm[BN + i] = ln_g ? ln_g[i] : 1.f;
+      ep_sm[2 * BN + i] = ln_g ? ln_b[i] : 0.f;
+    }
+    e.prm = ep_sm;
+  }
   __device__ void init_cta(uint8_t* extra, int ptid) const {
     build_im2col_table(reinterpret_cast<ChunkEntry*>(extra), ((K + kBK - 1) / kBK) * 8, K, Cin, ksz, W, ptid, PT);
   }
@@ -260,7 +277,7 @@ struct ConvFwdTC {
     if (IN_U8_) return;
 #pragma unroll
     for (int i = 0; i < TASKS; ++i) {
-      const RowInfo ri = c.rows[(ptid >> 3) + i * (PT / 8)];
+      const RowInfo ri = c.rows[task_r0(ptid) + i * (PT / 8)];
       c.row_addr[i] = (uint64_t)(uintptr_t)(ri.second ? in1 : in0) + (uint64_t)(ri.anchor * 2);
       c.row_yx[i] = pack_row_yx(ri);
     }
@@ -276,11 +293,11 @@ struct ConvFwdTC {
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = (K + kBK - 1) / kBK; }
   __device__ void load_a(const PCtx& c, uint32_t stage, int kc, int ptid) const {
     if (!IN_U8_) {
-      const int ch = ptid & 7;
+      const int ch = task_ch(ptid);
       const ChunkEntry e = c.tab[kc * 8 + ch];
       const int dy = e.yx >> 16, dx = e.yx & 0xffff;
       const int64_t eoff = (int64_t)e.off * 2;
-      const uint32_t dst = stage + kmajor_off<true>(ptid >> 3, ch);  // rows 8 apart share the swizzle phase
+      const uint32_t dst = stage + kmajor_off<true>(task_r0(ptid), ch);  // rows 8 apart share the swizzle phase
 #pragma unroll
       for (int i = 0; i < TASKS; ++i) {
         const int iy = row_y(c.row_yx[i]) + dy, ix = row_x(c.row_yx[i]) + dx;
@@ -304,8 +321,11 @@ struct ConvFwdTC {
   __device__ void load_b(const PCtx&, uint32_t stage, int kc, int ptid) const {
     load_rows_mnmajor<BN / 8, PT, B_SW>(w, Cout, kc * kBK, K, 0, Cout, stage, ptid);
   }
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
+  __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
     const int m = m0 + etid;
+    const float4* pb = reinterpret_cast<const float4*>(ec.prm);
+    const float4* pg = reinterpret_cast<const float4*>(ec.prm + BN);
+    const float4* pbeta = reinterpret_cast<const float4*>(ec.prm + 2 * BN);
     float mean = 0.f, rs = 1.f;
     if (ln_g) {  // flax LayerNorm: var = max(0, E[x^2] - E[x]^2), eps = 1e-6
       float s = 0.f, s2 = 0.f;
@@ -314,10 +334,15 @@ struct ConvFwdTC {
         float v[32];
         tmem_ld32(tmem_lane_base + cb * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float z = fmaf(v[i], acc_scale, __ldg(bias + cb * 32 + i));
-          s += z;
-          s2 += z * z;
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = pb[cb * 8 + q];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float z = fmaf(v[4 * q + j], acc_scale, bb[j]);
+            s += z;
+            s2 += z * z;
+          }
         }
       }
       mean = s / (float)BN;
@@ -331,20 +356,22 @@ struct ConvFwdTC {
       tmem_ld32(tmem_lane_base + cb * 32, v);
       uint32_t packed[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float y[2];
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = pb[cb * 8 + q], g4 = pg[cb * 8 + q], e4 = pbeta[cb * 8 + q];
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+        float y[4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int n = cb * 32 + i + j;
-          float z = fmaf(v[i + j], acc_scale, __ldg(bias + n));
+        for (int j = 0; j < 4; ++j) {
+          float z = fmaf(v[4 * q + j], acc_scale, bb[j]);
           if (ln_g) {
             z = (z - mean) * rs;
-            v[i + j] = z;  // normalised value, saved for the backward pass
-            z = z * __ldg(ln_g + n) + __ldg(ln_b + n);
+            v[4 * q + j] = z;  // normalised value, saved for the backward pass
+            z = z * gg[j] + ee[j];
           }
           y[j] = relu ? fmaxf(z, 0.f) : z;
         }
-        packed[i / 2] = pack_bf16(y[0], y[1]);
+        packed[2 * q] = pack_bf16(y[0], y[1]);
+        packed[2 * q + 1] = pack_bf16(y[2], y[3]);
       }
       if (valid) {
         uint4* o = reinterpret_cast<uint4*>(out + (int64_t)m * BN + cb * 32);
@@ -365,10 +392,14 @@ struct ConvFwdTC {
 // dW[kc][co] (partial of split z) = sum_{pixels of the split} im2col(x)[pix][kc] dz[pix][co]
 // A' = the im2col rows taken MN-major (row index = reduction), B' = dz MN-major.  The 64 reduction rows (pixels) of
 // a chunk change every chunk, so their anchors are published per chunk (CHUNK_SYNC).
-template <int BN_, bool IN_U8_>
+template <int BN_, bool IN_U8_, bool SEG4_ = false>
 struct ConvWgradTC {
+  // (SEG4: as in ConvFwdTC — 4 chunks of one image row x 8 consecutive pixels per warp)
+  __device__ static int task_ch(int ptid) { return SEG4_ ? (ptid >> 5) * 4 + (ptid & 3) : (ptid & 15); }
+  __device__ static int task_k0(int ptid) { return SEG4_ ? ((ptid & 31) >> 2) : (ptid >> 4); }
+  static constexpr int kTaskRowStep = SEG4_ ? 8 : (32 * (IN_U8_ ? 8 : 4)) / 16;
   static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = IN_U8_ ? 8 : 4;
-  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBK * 16 / PT;
+  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBK * 16 / PT, EP_FLOATS = 0;
   static constexpr int EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry) + kRowInfoBytes;
   static constexpr bool A_MN = true, B_MN = true, CHUNK_SYNC = true, B_SW = BN_ >= 64;
   const void* in;  // layer input of the rows with a backward pass
@@ -391,6 +422,7 @@ struct ConvWgradTC {
     c.n0 = n0;
   }
   __device__ void tile_rows(PCtx&, int) const {}
+  __device__ void init_epilogue(ECtx&, float*, int) const {}
   __device__ void chunk_producer(PCtx& c, uint8_t* extra, int kc, int ptid, int j) const {
     RowInfo* rows = reinterpret_cast<RowInfo*>(extra + kMaxChunks * sizeof(ChunkEntry)) + (j & 1) * kBM;
     if (ptid < kBK) rows[ptid] = conv_row_info(kc * kBK + ptid, M, OH, OW, H, W, Cin, stride, pad_y, pad_x, 1 << 30);
@@ -406,8 +438,7 @@ struct ConvWgradTC {
     if (!IN_U8_) {
 #pragma unroll
       for (int i = 0; i < TASKS; ++i) {
-        const int t = ptid + i * PT;
-        const int ch = t & 15, kk = t >> 4;
+        const int ch = task_ch(ptid), kk = task_k0(ptid) + i * kTaskRowStep;
         gather_chunk_bf16(stage + mnmajor_off<true>(kk, ch), in, in, c.rows[kk], c.tab[ch], H, W);
       }
     } else {
@@ -442,7 +473,7 @@ struct ConvWgradTC {
 template <int BN_>
 struct ConvDgradTC {
   static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4;
-  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT;
+  static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT, EP_FLOATS = 0;
   static constexpr int EXTRA_BYTES = kMaxChunks * (int)(sizeof(ChunkEntry) + sizeof(int)) + kRowInfoBytes;
   static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, B_SW = BN_ >= 64;
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, n_img, taps, Kd;
@@ -532,6 +563,7 @@ struct ConvDgradTC {
     c.wtab = reinterpret_cast<const int*>(extra + kMaxChunks * sizeof(ChunkEntry)) + cls * chunks_padded();
     c.rows = rows;
   }
+  __device__ void init_epilogue(ECtx&, float*, int) const {}
   __device__ void chunk_producer(PCtx&, uint8_t*, int, int, int) const {}
   __device__ void tile_epilogue(ECtx& e, int m0, int, int cls, int etid) const {
     int img, oy, ox, pix;
