@@ -58,16 +58,20 @@ bool pdl_enabled();
 // neither events nor a profiler can look without perturbing it.  One (static) pointer per translation unit.
 static __device__ unsigned long long* g_trace_buf = nullptr;
 static inline cudaError_t trace_set_local(unsigned long long* p) { return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
-__device__ __forceinline__ void trace_kernel_start() {
-  if ((threadIdx.x | blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+// entry = (tag << 56) | time; tag 0 = kernel start, 1.. = phase marks inside tc_gemm_kernel (any one thread of CTA 0)
+__device__ __forceinline__ void trace_mark(unsigned tag) {
+  if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
     unsigned long long* t = g_trace_buf;
     if (t) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       const unsigned long long i = atomicAdd(t, 1ull);
-      if (i < 4000) t[1 + i] = now;
+      if (i < 4000) t[1 + i] = ((unsigned long long)tag << 56) | (now & 0x00ffffffffffffffull);
     }
   }
+}
+__device__ __forceinline__ void trace_kernel_start() {
+  if (threadIdx.x == 0) trace_mark(0);
 }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

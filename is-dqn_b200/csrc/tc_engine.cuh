@@ -60,6 +60,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, b
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// arrive on `bar` (counted in its expected arrivals) once all prior cp.async of this thread have completed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -180,7 +185,8 @@ constexpr int kFirstProducerWarp = 5;
 //              epilogue, arrives on tmem_empty[a] — so the gather of tile i+1 overlaps the epilogue of tile i.
 //
 // P (the problem) provides:
-//   static constexpr int BN, STAGES, PRODUCER_WARPS, EXTRA_BYTES, EP_FLOATS; static constexpr bool A_MN, B_MN, CHUNK_SYNC;
+//   static constexpr int BN, STAGES, PRODUCER_WARPS, EXTRA_BYTES, EP_FLOATS; static constexpr bool A_MN, B_MN, CHUNK_SYNC,
+//   SYNC_STORES (the producers also fill the stage with plain st.shared);
 //   __device__ void init_epilogue(ECtx&, float* ep_sm, int etid) const;        (EP_FLOATS > 0 only; an epilogue barrier follows)
 //   (the A stage is always 128B-swizzled; the B stage is swizzled when BN >= 64, core-matrix layout for BN == 32)
 //   struct PCtx, ECtx;
@@ -192,7 +198,7 @@ constexpr int kFirstProducerWarp = 5;
 //   __device__ void load_a(const PCtx&, uint32_t stage_smem, int kc, int ptid) const;   load_b(...)
 //   __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int z, int etid) const;
 template <class P>
-__global__ void __launch_bounds__(32 * (kFirstProducerWarp + P::PRODUCER_WARPS), (P::BN <= 64 ? 2 : 1))
+__global__ void __launch_bounds__(32 * (kFirstProducerWarp + P::PRODUCER_WARPS), P::MIN_CTAS)
 tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   constexpr int BN = P::BN, STAGES = P::STAGES;
   constexpr int B_BYTES = BN * kBK * 2;
@@ -235,6 +241,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
+  if (tid == 0) trace_mark(1);  // prologue done (barriers, TMEM)
   pdl_trigger();  // (after the TMEM allocation: see common.cuh)
 
   if (warp >= kFirstProducerWarp) {
@@ -246,13 +253,13 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
     typename P::PCtx ctx;
     int j = 0;  // chunk counter of this CTA (stage = j % STAGES)
     int ti = 0;
-    constexpr int D = STAGES - 1;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
       const int m0 = tx * kBM, n0 = ty * BN;
       p.tile_producer(ctx, extra_sm, m0, n0, tz, ptid, ti);  // may publish per-row info in shared memory (parity ti & 1)
       named_bar_sync(1, PT);
       p.tile_rows(ctx, ptid);  // per-thread copy (registers) of the rows this thread gathers for the whole tile
+      if (ptid == 0 && ti == 0) trace_mark(2);  // tables + row info ready: first gather is issued next
       int kb, ke;
       p.k_range(tz, kb, ke);
       for (int kc = kb; kc < ke; ++kc, ++j) {
@@ -264,17 +271,14 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
         mbar_wait(&empty_bar[s], (uint32_t)(((j / STAGES) & 1) ^ 1));  // stage free (first lap: passes)
         p.load_a(ctx, sA + s * kABytes, kc, ptid);
         p.load_b(ctx, sB + s * B_BYTES, kc, ptid);
-        cp_async_commit();
-        if (j >= D) {  // chunk j-D of this thread has landed: publish it
-          cp_async_wait<D>();
-          fence_proxy_async();
-          mbar_arrive(&full_bar[(j - D) % STAGES]);
-        }
+        // This thread's arrival on the stage's "full" barrier is performed by the hardware when its asynchronous copies
+        // of the chunk have landed: the producer never waits for data, so every free stage of the ring is in flight and
+        // a chunk is published the moment it is complete.
+        if (P::SYNC_STORES) fence_proxy_async();  // (plain st.shared of this thread, uint8 path)
+        cp_async_mbar_arrive_noinc(&full_bar[s]);
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int q = (j > D ? j - D : 0); q < j; ++q) mbar_arrive(&full_bar[q % STAGES]);
+    cp_async_wait_all();
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
@@ -291,6 +295,8 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
         for (int kc = kb; kc < ke; ++kc, ++j) {
           const int s = j % STAGES;
           mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+          if (j == 0) trace_mark(3);  // first chunk landed in shared memory
+          fence_proxy_async();  // the LDGSTS / st.shared writes of the producers -> the tensor core's (async proxy) reads
           tcgen05_fence_after();
 #pragma unroll
           for (int q = 0; q < kBK / 16; ++q) {
@@ -301,6 +307,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar[a]);
+        if (ti == 0) trace_mark(4);  // all MMAs of the first tile issued
       }
     }
   } else {
@@ -318,6 +325,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
       const int a = ti & 1;
       p.tile_epilogue(ectx, m0, n0, tz, tid);
       mbar_wait(&tmem_full_bar[a], (uint32_t)((ti >> 1) & 1));
+      if (tid == 0 && ti == 0) trace_mark(5);  // first accumulator complete
       tcgen05_fence_after();
       p.epilogue(ectx, tmem_d + a * BN + ((uint32_t)(warp * 32) << 16), m0, n0, tz, tid);
       tcgen05_fence_before();
@@ -326,6 +334,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (tid == 0) trace_mark(6);  // all roles of CTA 0 done
   if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 

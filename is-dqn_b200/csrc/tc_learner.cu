@@ -55,15 +55,9 @@ namespace {
 
 inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpret_cast<float*>(ws) + off; }
 
-// Same problem with a deeper shared-memory ring (the producers keep STAGES-1 chunks of asynchronous copies in flight)
-template <class P, int S>
-struct WithStages : P {
-  static constexpr int STAGES = S;
-};
-
 // Persistent launch: the tiles (x fastest) are dealt round-robin to min(#tiles, SMs x resident CTAs) CTAs.
 template <class P>
-int launch_tc_impl(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas) {
+int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0) {
   constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
   constexpr int threads = 32 * (tc::kFirstProducerWarp + P::PRODUCER_WARPS);
   static int ctas_per_sm = 0;
@@ -100,22 +94,14 @@ int launch_tc_impl(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream
   return ISDQN_OK;
 }
 
-// A launch that is a single partial wave is latency bound (batch 32): every CTA walks its reduction axis once, so the
-// only lever is how many chunks are in flight — take the 8-stage ring (one CTA per SM is all such a launch needs).
-template <class P>
-int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0) {
-  if constexpr (P::BN <= 64) {
-    static const bool deep = [] {
-      const char* e = getenv("ISDQN_DEEP_RING");
-      return !(e && e[0] == '0');
-    }();
-    if (deep && (int64_t)tiles_x * tiles_y * tiles_z <= kNumSMs) {
-      WithStages<P, 8> q;
-      static_cast<P&>(q) = p;
-      return launch_tc_impl(q, tiles_x, tiles_y, tiles_z, s, tag, max_ctas);
-    }
-  }
-  return launch_tc_impl(p, tiles_x, tiles_y, tiles_z, s, tag, max_ctas);
+// A launch that is a single partial wave is latency bound (batch 32): it takes the WIDE shape of its problem
+// (tc_problems.cuh).  ISDQN_WIDE=0 keeps the throughput shape everywhere.
+bool wide_launch(int64_t n_tiles) {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_WIDE");
+    return !(e && e[0] == '0');
+  }();
+  return on && n_tiles <= kNumSMs;
 }
 
 int pick_bn(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
@@ -135,20 +121,24 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
   const int real_splits = ceil_div(total_chunks, cps);
   // (a capped side-stream launch takes the narrow tile: half the shared memory, so it can share an SM)
   const int bn = max_ctas > 0 ? pick_bn(N < 64 ? N : 64) : pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
-#define ISDQN_GEMM_TC(BN)                                                      \
+#define ISDQN_GEMM_TC_W(BN, WIDE)                                              \
   {                                                                            \
-    tc::GemmTC<BN, A_MN, B_MN> p;                                              \
+    tc::GemmTC<BN, A_MN, B_MN, WIDE> p;                                        \
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;          \
     p.split_stride = split_stride; p.M = M; p.N = N; p.K = K;                  \
     p.chunks_per_split = cps;                                                  \
     return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag, max_ctas); \
   }
+#define ISDQN_GEMM_TC(BN)                                                      \
+  if (wide_launch((int64_t)ceil_div(M, tc::kBM) * ceil_div(N, BN) * real_splits)) ISDQN_GEMM_TC_W(BN, true) \
+  else ISDQN_GEMM_TC_W(BN, false)
   switch (bn) {
     case 32: ISDQN_GEMM_TC(32)
     case 64: ISDQN_GEMM_TC(64)
     case 128: ISDQN_GEMM_TC(128)
     default: ISDQN_GEMM_TC(256)
   }
+#undef ISDQN_GEMM_TC_W
 #undef ISDQN_GEMM_TC
 }
 
@@ -211,9 +201,9 @@ bool tc_eligible(const Plan& p, const isdqn_net* net) {
 template <bool U8, bool SEG4 = false>
 int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0, int rows, const bf16* w, const float* params,
                        bf16* out, float* xhat, float* rstd, int m_train, cudaStream_t s, float in_scale = 1.0f) {
-#define ISDQN_CONV_FWD_TC(BN)                                                                          \
+#define ISDQN_CONV_FWD_TC_W(BN, WIDE)                                                                  \
   {                                                                                                    \
-    tc::ConvFwdTC<BN, U8, SEG4> p;                                                                     \
+    tc::ConvFwdTC<BN, U8, SEG4, WIDE> p;                                                               \
     p.in0 = in0; p.in1 = in1; p.n_img0 = n0;                                                           \
     p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;                \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
@@ -225,6 +215,9 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
     p.acc_scale = U8 ? 1.0f / 255.0f : in_scale;                                                       \
     return launch_tc(p, ceil_div(p.M, tc::kBM), 1, 1, s, "tc_conv_fwd");                               \
   }
+#define ISDQN_CONV_FWD_TC(BN)                                                                          \
+  if (!U8 && wide_launch(ceil_div(rows * L.pix, tc::kBM))) ISDQN_CONV_FWD_TC_W(BN, true)               \
+  else ISDQN_CONV_FWD_TC_W(BN, false)
   switch (L.out_dim) {
     case 32: ISDQN_CONV_FWD_TC(32)
     case 64: ISDQN_CONV_FWD_TC(64)
@@ -232,6 +225,7 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
     case 256: ISDQN_CONV_FWD_TC(256)
     default: return ISDQN_E_UNSUPPORTED;
   }
+#undef ISDQN_CONV_FWD_TC_W
 #undef ISDQN_CONV_FWD_TC
 }
 
@@ -241,15 +235,18 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
   const int total_chunks = ceil_div(rows, tc::kBK);
   const int cps = ceil_div(total_chunks, splits);
   *real_splits = ceil_div(total_chunks, cps);
-#define ISDQN_CONV_WGRAD_TC(BN)                                                                        \
+#define ISDQN_CONV_WGRAD_TC_W(BN, WIDE)                                                                \
   {                                                                                                    \
-    tc::ConvWgradTC<BN, U8, SEG4> p;                                                                   \
+    tc::ConvWgradTC<BN, U8, SEG4, WIDE> p;                                                             \
     p.in = in; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;     \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x;                          \
     p.M = rows; p.K = L.in_dim; p.dz = dz; p.part = part; p.chunks_per_split = cps;                    \
     p.acc_scale = U8 ? 1.0f / 255.0f : in_scale;                                                       \
     return launch_tc(p, ceil_div(L.in_dim, tc::kBM), 1, *real_splits, s, "tc_conv_wgrad", max_ctas);   \
   }
+#define ISDQN_CONV_WGRAD_TC(BN)                                                                        \
+  if (!U8 && wide_launch((int64_t)ceil_div(L.in_dim, tc::kBM) * *real_splits)) ISDQN_CONV_WGRAD_TC_W(BN, true) \
+  else ISDQN_CONV_WGRAD_TC_W(BN, false)
   switch (L.out_dim) {
     case 32: ISDQN_CONV_WGRAD_TC(32)
     case 64: ISDQN_CONV_WGRAD_TC(64)
@@ -257,6 +254,7 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
     case 256: ISDQN_CONV_WGRAD_TC(256)
     default: return ISDQN_E_UNSUPPORTED;
   }
+#undef ISDQN_CONV_WGRAD_TC_W
 #undef ISDQN_CONV_WGRAD_TC
 }
 
@@ -264,20 +262,25 @@ int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* d
   const int taps = ceil_div(L.ksz, L.stride);
   const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
   const int bn = pick_bn(L.Cin);
-#define ISDQN_CONV_DGRAD_TC(BN)                                                                        \
+#define ISDQN_CONV_DGRAD_TC_W(BN, WIDE)                                                                \
   {                                                                                                    \
-    tc::ConvDgradTC<BN> p;                                                                             \
+    tc::ConvDgradTC<BN, WIDE> p;                                                                       \
     p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.OH = L.OH; p.OW = L.OW; p.Cout = L.out_dim;                \
     p.ksz = L.ksz; p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.n_img = B;             \
     p.taps = taps; p.Kd = taps * taps * L.out_dim; p.dz = dz; p.w = w; p.dx = dx;                      \
     return launch_tc(p, ceil_div(rows_max, tc::kBM), ceil_div(L.Cin, BN), L.stride * L.stride, s, "tc_conv_dgrad"); \
   }
+#define ISDQN_CONV_DGRAD_TC(BN)                                                                        \
+  if (wide_launch((int64_t)ceil_div(rows_max, tc::kBM) * ceil_div(L.Cin, BN) * L.stride * L.stride))   \
+    ISDQN_CONV_DGRAD_TC_W(BN, true)                                                                    \
+  else ISDQN_CONV_DGRAD_TC_W(BN, false)
   switch (bn) {
     case 32: ISDQN_CONV_DGRAD_TC(32)
     case 64: ISDQN_CONV_DGRAD_TC(64)
     case 128: ISDQN_CONV_DGRAD_TC(128)
     default: ISDQN_CONV_DGRAD_TC(256)
   }
+#undef ISDQN_CONV_DGRAD_TC_W
 #undef ISDQN_CONV_DGRAD_TC
 }
 

@@ -111,11 +111,15 @@ __device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, float* _
 
 // --------------------------------------------------------------------------------------- plain GEMM (+ split-K)
 // D[M][N] = sum_k A(m,k) B(n,k); A: K-major [M][lda] or MN-major [K][lda]; B likewise.  fp32 output (partials).
-template <int BN_, bool A_MN_, bool B_MN_>
+// WIDE_ (every problem): the latency shape for launches that are a single partial wave (batch 32) — 8 producer warps
+// (the gather is bound by instruction issue: twice the warps, half the work each), an 8-stage ring for the narrow
+// tiles, one CTA per SM.  Default: the throughput shape — 4 producer warps, 4 stages, two CTAs per SM when they fit.
+template <int BN_, bool A_MN_, bool B_MN_, bool WIDE_ = false>
 struct GemmTC {
-  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4, EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = WIDE_ ? 8 : 4, EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr int PT = 32 * PRODUCER_WARPS;
-  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, B_SW = BN_ >= 64;
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = BN_ >= 64;
   const bf16* A; int64_t lda;
   const bf16* B; int64_t ldb;
   float* C; int64_t ldc; int64_t split_stride;
@@ -238,14 +242,15 @@ __device__ __forceinline__ void store_chunk_u8(uint32_t dst, const uint2 p) {
 // warp then take 4 chunks x 8 CONSECUTIVE output pixels, whose windows overlap in memory, instead of 8 chunks (two
 // image rows) x 4 pixels — a third of the distinct 128-byte lines per LDGSTS, which is what bounds that kernel (the
 // L1 data pipe: profiles/r01_summary.md).
-template <int BN_, bool IN_U8_, bool SEG4_ = false>
+template <int BN_, bool IN_U8_, bool SEG4_ = false, bool WIDE_ = false>
 struct ConvFwdTC {
   __device__ static int task_ch(int ptid) { return SEG4_ ? ((ptid >> 5) & 1) * 4 + (ptid & 3) : (ptid & 7); }
   __device__ static int task_r0(int ptid) { return SEG4_ ? (ptid >> 6) * 8 + ((ptid & 31) >> 2) : (ptid >> 3); }
-  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = IN_U8_ ? 8 : 4;
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = (IN_U8_ || WIDE_) ? 8 : 4;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT, EP_FLOATS = 3 * BN_;
   static constexpr int EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry) + kRowInfoBytes;
-  static constexpr bool A_MN = false, B_MN = true, CHUNK_SYNC = false, B_SW = BN_ >= 64;
+  static constexpr bool A_MN = false, B_MN = true, CHUNK_SYNC = false, SYNC_STORES = IN_U8_, B_SW = BN_ >= 64;
   const void* in0; const void* in1; int n_img0;
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, M, K;
   const bf16* w;  // [K][Cout]
@@ -392,16 +397,18 @@ struct ConvFwdTC {
 // dW[kc][co] (partial of split z) = sum_{pixels of the split} im2col(x)[pix][kc] dz[pix][co]
 // A' = the im2col rows taken MN-major (row index = reduction), B' = dz MN-major.  The 64 reduction rows (pixels) of
 // a chunk change every chunk, so their anchors are published per chunk (CHUNK_SYNC).
-template <int BN_, bool IN_U8_, bool SEG4_ = false>
+template <int BN_, bool IN_U8_, bool SEG4_ = false, bool WIDE_ = false>
 struct ConvWgradTC {
-  // (SEG4: as in ConvFwdTC — 4 chunks of one image row x 8 consecutive pixels per warp)
-  __device__ static int task_ch(int ptid) { return SEG4_ ? (ptid >> 5) * 4 + (ptid & 3) : (ptid & 15); }
-  __device__ static int task_k0(int ptid) { return SEG4_ ? ((ptid & 31) >> 2) : (ptid >> 4); }
-  static constexpr int kTaskRowStep = SEG4_ ? 8 : (32 * (IN_U8_ ? 8 : 4)) / 16;
-  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = IN_U8_ ? 8 : 4;
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = (IN_U8_ || WIDE_) ? 8 : 4;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
+  // (SEG4: as in ConvFwdTC — 4 chunks of one image row x 8 consecutive pixels per warp; warp w takes image row w & 3 of
+  // the window, pixel group w >> 2)
+  __device__ static int task_ch(int ptid) { return SEG4_ ? ((ptid >> 5) & 3) * 4 + (ptid & 3) : (ptid & 15); }
+  __device__ static int task_k0(int ptid) { return SEG4_ ? (ptid >> 7) * 8 + ((ptid & 31) >> 2) : (ptid >> 4); }
+  static constexpr int kTaskRowStep = SEG4_ ? (PRODUCER_WARPS / 4) * 8 : (32 * PRODUCER_WARPS) / 16;
   static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBK * 16 / PT, EP_FLOATS = 0;
   static constexpr int EXTRA_BYTES = kMaxChunks * (int)sizeof(ChunkEntry) + kRowInfoBytes;
-  static constexpr bool A_MN = true, B_MN = true, CHUNK_SYNC = true, B_SW = BN_ >= 64;
+  static constexpr bool A_MN = true, B_MN = true, CHUNK_SYNC = true, SYNC_STORES = IN_U8_, B_SW = BN_ >= 64;
   const void* in;  // layer input of the rows with a backward pass
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, M, K;
   const bf16* dz;  // [M][Cout]
@@ -470,12 +477,13 @@ struct ConvWgradTC {
 // (tile z) so that only taps that hit the pixel are multiplied.  A gathered K-major, B = W K-major per tap.
 // Table entry per (class, chunk k = (tap, co0)): off = -(ty*OW + tx)*Cout + co0 (relative to the row's anchor output
 // pixel), yx = (ty << 16) | tx, or -1 when the tap does not exist for this class; wtab = weight offset of the chunk.
-template <int BN_>
+template <int BN_, bool WIDE_ = false>
 struct ConvDgradTC {
-  static constexpr int BN = BN_, STAGES = 4, PRODUCER_WARPS = 4;
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = WIDE_ ? 8 : 4;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr int PT = 32 * PRODUCER_WARPS, TASKS = kBM * 8 / PT, EP_FLOATS = 0;
   static constexpr int EXTRA_BYTES = kMaxChunks * (int)(sizeof(ChunkEntry) + sizeof(int)) + kRowInfoBytes;
-  static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, B_SW = BN_ >= 64;
+  static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = BN_ >= 64;
   int H, W, Cin, OH, OW, Cout, ksz, stride, pad_y, pad_x, n_img, taps, Kd;
   const bf16* dz;  // [n_img*OH*OW][Cout]
   const bf16* w;   // [ksz][ksz][Cin][Cout]

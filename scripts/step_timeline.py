@@ -39,16 +39,32 @@ with torch.cuda.stream(stream):
         lib.isdqn_graph_launch(ctx["graph"], stream.cuda_stream)
     torch.cuda.synchronize()
     _lib.check(lib.isdqn_trace_set(None), "trace_set")
-t = buf.cpu().numpy()
+t = buf.cpu().numpy().astype(np.uint64)
 n = int(t[0])
-per = n // n_rep
-ts = t[1 : 1 + per * n_rep].reshape(n_rep, per).astype(np.float64)
-print(f"{n} kernel starts, {per} per replay; names from profile: {len(names)}")
-d = np.diff(np.concatenate([ts, np.roll(ts[:, :1], -1, axis=0)], axis=1), axis=1)[:-1]  # last column: to the next replay's first
-med = np.median(d, axis=0) / 1e3
+ent = t[1 : 1 + n]
+tags = (ent >> np.uint64(56)).astype(np.int64)
+times = (ent & np.uint64(0x00FFFFFFFFFFFFFF)).astype(np.float64)
+order = np.argsort(times, kind="stable")
+tags, times = tags[order], times[order]
+starts = np.flatnonzero(tags == 0)
+per = len(starts) // n_rep
+print(f"{n} entries, {len(starts)} kernel starts, {per} per replay; names from profile: {len(names)}")
+# per kernel slot: interval to the next kernel start, and the phase marks (relative to the kernel start)
+rows = {}
+for si, s0 in enumerate(starts[:-1]):
+    slot = si % per
+    s1 = starts[si + 1]
+    rec = rows.setdefault(slot, {"dt": [], "ph": {}})
+    rec["dt"].append(times[s1] - times[s0])
+    for e in range(s0 + 1, s1):
+        rec["ph"].setdefault(int(tags[e]), []).append(times[e] - times[s0])
 tot = 0.0
-for i in range(per):
-    nm = names[i] if i < len(names) else "?"
-    print(f"{i:3d} {nm:22s} {med[i]:8.2f} us")
-    tot += med[i]
+print("  # kernel                 start->next |  prologue  tables  1st-chunk  mma-issued  acc-ready  cta0-done   (us from kernel start)")
+for slot in range(per):
+    rec = rows[slot]
+    nm = names[slot] if slot < len(names) else "?"
+    med = np.median(rec["dt"]) / 1e3
+    tot += med
+    ph = "".join(f"{np.median(rec['ph'][k]) / 1e3:10.2f}" if k in rec["ph"] else "         -" for k in range(1, 7))
+    print(f"{slot:3d} {nm:22s} {med:8.2f}    |{ph}")
 print(f"sum {tot:.1f} us")
