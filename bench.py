@@ -175,8 +175,8 @@ def workload_config(capacity):
 def kernel_work(name: str, P: int):
     """Algorithmic work of one launch for the roofline: ('hbm', bytes) or ('tensor', flops)."""
     B = BATCH
-    if name == "adam":
-        return "hbm", 28 * P
+    if name == "adam":  # read p, g, mu, nu; write p, mu, nu (fp32) + the bf16 shadow of p
+        return "hbm", 30 * P
     if name == "gather_stack4_u8":
         return "hbm", 91_728 * B
     if name == "dense_wgrad_gemm":
@@ -295,6 +295,29 @@ def run_ours(args, rank, world, local_rank):
         agent._use_graph = False
         prof = _lib.profile(lambda: agent.update_online_params(1, rb))
         agent._use_graph = True
+        # ---- the same step INSIDE the graph replay: device-side kernel-start timeline (isdqn_trace_set); interval k =
+        # start of kernel k -> start of kernel k+1 (duration + launch gap), median over 30 replays
+        graph_names = [n for n, _ in prof if n not in ("sample_uniform", "gather_stack4_u8", "cast_params_bf16")]
+        in_graph_us = None
+        ctx = agent._context(BATCH)
+        if ctx.get("graph") is not None:
+            lib = _lib.load()
+            tbuf = torch.zeros(4001, dtype=torch.int64, device="cuda")
+            n_rep = 30
+            torch.cuda.synchronize()
+            _lib.check(lib.isdqn_trace_set(tbuf.data_ptr()), "isdqn_trace_set")
+            for _ in range(n_rep):
+                lib.isdqn_graph_launch(ctx["graph"], stream.cuda_stream)
+            torch.cuda.synchronize()
+            _lib.check(lib.isdqn_trace_set(None), "isdqn_trace_set")
+            tr = tbuf.cpu().numpy().astype(np.uint64)
+            ent = tr[1 : 1 + int(tr[0])]
+            tg = (ent >> np.uint64(56)).astype(np.int64)
+            tm = np.sort((ent & np.uint64(0x00FFFFFFFFFFFFFF)).astype(np.float64)[tg == 0])
+            per = len(tm) // n_rep
+            if per == len(graph_names) and per > 0:
+                iv = np.diff(tm)[: per * (n_rep - 1)].reshape(n_rep - 1, per)
+                in_graph_us = [(graph_names[k], float(np.median(iv[:, k]) / 1e3)) for k in range(per)]
     per_kernel = {}
     for name, t in prof:
         per_kernel.setdefault(name, [0, 0.0])
@@ -302,7 +325,8 @@ def run_ours(args, rank, world, local_rank):
         per_kernel[name][1] += t
     launches = len(prof)
     step_prof_ms = sum(t for _, t in prof)
-    dominant = max(per_kernel.items(), key=lambda kv: kv[1][1])
+    # dominant kernel = the longest single launch (three different convolutions share the name tc_conv_fwd)
+    dominant = max(per_kernel.items(), key=lambda kv: kv[1][1] / kv[1][0])
     dom_name, (dom_count, dom_ms) = dominant
     kind, work = kernel_work(dom_name, P)
 
@@ -330,6 +354,18 @@ def run_ours(args, rank, world, local_rank):
     else:
         roofline = {"kernel": dom_name, "bound": "tensor", "achieved": None, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                     "frac": None, "traffic": None, "peak_src": peaks["src"], "share_of_step": dom_ms / step_prof_ms}
+    # every kernel of the step against its own bound (events, same measurement as `roofline`)
+    roofline_kernels = []
+    for name, (cnt, tot_ms) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1]):
+        k2, w2 = kernel_work(name, P)
+        if k2 == "tensor":
+            a2 = (w2 / 1e12) / (tot_ms / 1e3)
+            roofline_kernels.append({"kernel": name, "launches": cnt, "ms": round(tot_ms, 5), "bound": "tensor",
+                                     "achieved": a2, "unit": "TFLOP/s", "frac": a2 / peaks["tflops_burst"]})
+        elif k2 == "hbm":
+            a2 = (w2 / 1e9) / ((tot_ms / cnt) / 1e3)
+            roofline_kernels.append({"kernel": name, "launches": cnt, "ms": round(tot_ms, 5), "bound": "hbm",
+                                     "achieved": a2, "unit": "GB/s", "frac": a2 / peaks["hbm_gbs"]})
     gather_gbs = 91_728 * n_big / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else None
     cpu = None
     if world == 1 or True:
@@ -348,6 +384,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches * args.steps,
         "gpu_launches_per_step": launches,
         "roofline": roofline,
+        "roofline_kernels": roofline_kernels,
+        "in_graph_us": in_graph_us,
         "cpu_baseline": cpu,
         "learner_tflops": world * args.steps * BATCH * FLOP_PER_TRANSITION / (ms / 1e3) / 1e12,
         "replay": {"samples_per_s": world * n_big / (ms_replay / 1e3), "launch_samples": n_big,

@@ -39,7 +39,7 @@ void profile_mark(cudaStream_t s, const char* name);
 
 // two-stream backward pass (runtime.cu)
 constexpr int kSideEvents = 16, kSideStreams = 2;
-bool fork_enabled();
+int fork_mode();
 cudaStream_t side_stream(int i);
 cudaEvent_t side_event(int i);
 
@@ -84,6 +84,11 @@ __device__ __forceinline__ void pdl_sync() {
 // Experiment (ISDQN_CARVEOUT=1): give every kernel of the step the same (maximum) shared-memory carve-out so that the
 // SMs never reconfigure the L1/shared split between a tensor-core kernel and a small streaming one.  Measured slower.
 void prefer_max_shared_once(const void* kernel);
+void prefer_max_shared(const void* kernel);  // unconditional (kernels that must co-reside with the tensor-core kernels)
+template <typename... KArgs>
+static inline void co_resident_with_tc(void (*kernel)(KArgs...)) {
+  prefer_max_shared(reinterpret_cast<const void*>(kernel));
+}
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,

@@ -369,6 +369,7 @@ int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float*
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   ISDQN_PROF(as_stream(stream), "adam");
+  co_resident_with_tc(adam_kernel);
   ISDQN_CUDA_CHECK(launch_pdl(adam_kernel, dim3((unsigned)grid), dim3(256), 0, as_stream(stream), d_params, d_grads, d_mu,
                               d_nu, d_count, lr, b1, b2, eps, n4, reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16), skip_begin / 4,
                               skip_len / 4));

@@ -613,11 +613,12 @@ static inline cudaError_t launch_ln_relu_bwd_warp(int ctas, cudaStream_t s, floa
                                                   const float* ln_g, const float* ln_b, const float* act, int rows, int C,
                                                   float* colpart, __nv_bfloat16* dz16, const __nv_bfloat16* act16) {
 #define ISDQN_LN_BWD(MAXJ, R)                                                                                          \
+  co_resident_with_tc(ln_relu_bwd_warp_kernel<MAXJ, R>);                                                               \
   return launch_pdl((ln_relu_bwd_warp_kernel<MAXJ, R>), dim3(ctas), dim3(256), 0, s, d, xhat, rstd, ln_g, ln_b, act, rows, \
                     C, colpart, dz16, act16)
-  if (C <= 32) ISDQN_LN_BWD(1, 4);
-  if (C <= 64) ISDQN_LN_BWD(2, 4);
-  if (C <= 128) ISDQN_LN_BWD(4, 2);
+  if (C <= 32) { ISDQN_LN_BWD(1, 4); }
+  if (C <= 64) { ISDQN_LN_BWD(2, 4); }
+  if (C <= 128) { ISDQN_LN_BWD(4, 2); }
   ISDQN_LN_BWD(8, 1);
 #undef ISDQN_LN_BWD
 }
@@ -898,6 +899,8 @@ __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList 
 }
 
 static inline cudaError_t launch_reduce_segments(SegmentList& segs, cudaStream_t s) {
+  co_resident_with_tc(reduce_segments_kernel<4>);
+  co_resident_with_tc(reduce_segments_kernel<1>);
   if (segments_vec4_ok(segs)) {
     const int n_tiles = finish_segments(&segs, 4);
     return launch_pdl((reduce_segments_kernel<4>), dim3(n_tiles), dim3(256), 0, s, segs);

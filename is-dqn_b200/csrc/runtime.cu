@@ -15,18 +15,24 @@ void set_last_cuda_error(cudaError_t e, const char* where) {
 // ---------------------------------------------------------------------------------------------- profiler
 bool g_profile_on = false;
 
-void prefer_max_shared_once(const void* kernel) {
+// Kernels whose shared-memory carve-outs differ cannot be resident on one SM at the same time (measured: a default-
+// carve-out Adam on a side stream serialised against the tensor-core kernels).  The streaming kernels that run between
+// the fork and the join of the backward pass therefore ask for the tensor-core kernels' carve-out (maximum shared);
+// ISDQN_CARVEOUT=1 extends that to every kernel launched through launch_pdl (measured slower: the rest lose L1).
+void prefer_max_shared(const void* kernel) {
   static const void* seen[256];
   static int n_seen = 0;
-  static const bool off = [] {
-    const char* e = getenv("ISDQN_CARVEOUT");  // opt-in: measured 6 % slower at batch 32 (the small kernels lose L1)
-    return !(e && e[0] == '1');
-  }();
-  if (off) return;
   for (int i = 0; i < n_seen; ++i)
     if (seen[i] == kernel) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (n_seen < 256) seen[n_seen++] = kernel;
+}
+void prefer_max_shared_once(const void* kernel) {
+  static const bool all = [] {
+    const char* e = getenv("ISDQN_CARVEOUT");
+    return e && e[0] == '1';
+  }();
+  if (all) prefer_max_shared(kernel);
 }
 
 bool pdl_enabled() {
@@ -38,12 +44,15 @@ bool pdl_enabled() {
 }
 // Side stream + events of the two-stream backward pass (tc_learner.cu).  One set per process: the learner entry points
 // are not re-entrant across host threads.  ISDQN_FORK=1 enables it (measured slower at batch 32).
-bool fork_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("ISDQN_FORK");  // opt-in: cross-stream graph edges cost more than the overlap gains
-    return e && e[0] == '1';
+int fork_mode() {
+  static const int mode = [] {
+    // 0 (default) one stream | 1 weight gradients + early Adam on side streams | 2 early Adam only.  Measured at batch
+    // 32 (profiles/r01_summary.md): neither beats the single stream once every kernel of the backward pass shares one
+    // carve-out — the cross-stream graph edges cost what the overlap gains.
+    const char* e = getenv("ISDQN_FORK");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
   }();
-  return on;
+  return mode;
 }
 cudaStream_t side_stream(int i) {
   static cudaStream_t s[kSideStreams] = {};

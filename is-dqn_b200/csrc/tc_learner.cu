@@ -429,14 +429,16 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   // the Atari network) follows its weight gradient on the side stream as soon as the input-gradient GEMM that reads
   // the same weights has finished, and the final Adam launch passes over that range.
   cudaStream_t s2 = s, s3 = s;
-  const bool fork = !g_profile_on && !tr->nccl_comm && fork_enabled() && side_stream(0) != nullptr && side_stream(1) != nullptr;
-  if (fork) {
-    s2 = side_stream(0);  // weight gradients
-    s3 = side_stream(1);  // early Adam
+  // fork_mode(): 0 = one stream; 1 = weight gradients + early Adam on side streams; 2 = only the early Adam
+  const int fmode = (!g_profile_on && !tr->nccl_comm && side_stream(0) != nullptr && side_stream(1) != nullptr) ? fork_mode() : 0;
+  const bool fork = fmode == 1;
+  if (fmode) {
+    if (fork) s2 = side_stream(0);  // weight gradients
+    s3 = side_stream(1);            // early Adam
   }
   // small batches are latency bound (every kernel is a fraction of a wave): keep the side work narrow so that it shares
   // the SMs with the critical path instead of queueing in front of it; large batches are throughput bound: no cap
-  const bool narrow_side = fork && B <= 256;
+  const bool narrow_side = fmode && B <= 256;
   const int side_cap = narrow_side ? kSideCtas : 0;
   int n_ev = 0;
   auto fork_to_side = [&]() -> int {
@@ -470,7 +472,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     }
     const bool side = fork && l > 0;
     cudaStream_t sw = side ? s2 : s;
-    if (side) {
+    if (side || (fmode == 2 && pend_n > 0)) {
       rc = fork_to_side();  // everything the main stream has produced so far (dz of this layer, the input gradient above)
       if (rc) return rc;
       if (pend_n > 0) {
@@ -478,7 +480,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         cudaEvent_t e = side_event(n_ev++);
         if (!e) return ISDQN_E_CUDA;
         ISDQN_CUDA_CHECK(cudaEventRecord(e, s2));
-        ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s3, e, 0));
+        if (s2 != s) ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s3, e, 0));
         ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s3, side_event(n_ev - 2), 0));
         rc = isdqn_adam_launch(tr->d_params + pend_off, tr->d_grads + pend_off, tr->d_mu + pend_off, tr->d_nu + pend_off,
                                tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps, pend_n, shadow + pend_off, s3, 0, 0, narrow_side ? 2 * kNumSMs : 0);
@@ -507,7 +509,8 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       rc = launch_gemm_tc<true, true>(w16(wt, t.act16[l - 1]), L.in_dim, dz16, L.out_dim, grads + L.w_off, L.out_dim, 0,
                                       L.in_dim, L.out_dim, B, 1, sw, "tc_dense_wgrad", side ? side_cap : 0);
       // (the early range must be the only one: the final Adam launch passes over a single range)
-      if (side && update && early_n == 0 && pend_n == 0 && ((int64_t)L.in_dim * L.out_dim) % 4 == 0 && L.w_off % 4 == 0) {
+      if ((side || fmode == 2) && l > 0 && update && early_n == 0 && pend_n == 0 && ((int64_t)L.in_dim * L.out_dim) % 4 == 0 &&
+          L.w_off % 4 == 0) {
         pend_off = L.w_off;
         pend_n = (int64_t)L.in_dim * L.out_dim;
       }
@@ -574,8 +577,9 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     }
     dz32 = dprev;
   }
-  if (fork) {  // join
+  if (fmode) {  // join
     for (cudaStream_t x : {s2, s3}) {
+      if (x == s) continue;
       if (x == s3 && early_n == 0) continue;  // (never forked: not part of a capture)
       cudaEvent_t e = side_event(n_ev++);
       if (!e) return ISDQN_E_CUDA;
