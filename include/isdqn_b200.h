@@ -207,6 +207,8 @@ typedef struct isdqn_train {
   void* d_params_bf16;      /* bf16 path only: bf16 shadow of d_params (layout.total elements).  Adam keeps it current;  */
   int32_t refresh_shadow;   /* set to 1 to rebuild it from d_params at the start of the call (parameters were changed     */
                             /* outside isdqn_learn_on_batch since the last call)                                          */
+  double* d_cumulated;      /* NULL, or [K]: isdqn_learn_on_batch also does d_cumulated[k] += d_losses[k] (the                */
+                            /* `self.cumulated_losses += losses` of isdqn.py:62, kept on the device)                        */
 } isdqn_train;
 #define ISDQN_COMPUTE_F32 0
 #define ISDQN_COMPUTE_BF16 1

@@ -90,6 +90,7 @@ class Train(C.Structure):
         ("workspace_tc_bytes", C.c_int64),
         ("d_params_bf16", C.c_void_p),
         ("refresh_shadow", C.c_int32),
+        ("d_cumulated", C.c_void_p),
     ]
 
 

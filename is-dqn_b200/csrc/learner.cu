@@ -92,11 +92,9 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
       const int splits = dense_fwd_splits(rows, L.out_dim, L.in_dim);
       const int kps = ceil_div(ceil_div(L.in_dim, splits), kBK) * kBK;
       const int real_splits = ceil_div(L.in_dim, kps);
-      if (!first && !L.has_ln && !L.relu && L.out_dim <= 128 && L.in_dim <= 8192) {  // the head layer
+      if (!first && !L.has_ln && !L.relu && L.out_dim <= 128 && L.in_dim <= kHeadMaxK) {  // the head layer
         ISDQN_PROF(s, "head_fwd");
-        head_fwd_kernel<<<rows, 512, L.in_dim * sizeof(float), s>>>(wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
-                                                                  L.in_dim, L.out_dim, out);
-        ISDQN_LAUNCH_CHECK();
+        ISDQN_CUDA_CHECK(launch_head_fwd(s, wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off, L.in_dim, L.out_dim, out, rows));
         continue;
       }
       const bool direct = real_splits == 1 && !L.has_ln && !L.relu;
@@ -144,7 +142,7 @@ int run_loss(const Plan& p, const isdqn_net* net, const isdqn_train* tr, const i
   ISDQN_PROF(s, "heads_td_loss");
   heads_td_loss_kernel<<<net->n_heads, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n,
                                                   tr->batch, tr->batch_global, net->n_heads, net->n_actions,
-                                                  tr->d_losses, dq, dbias, count);
+                                                  tr->d_losses, dq, dbias, count, count ? tr->d_cumulated : nullptr);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

@@ -518,7 +518,8 @@ dense_finalize_kernel(const float* __restrict__ part, int splits, int64_t split_
 // [2]=sum dy (dbeta).  Without LayerNorm: dz = dy, only [0] is meaningful.
 // Variant A: C <= 256, one warp per row, R rows in flight per warp (all loads of the R rows are issued before any
 // reduction: the kernel is pure streaming and needs the memory-level parallelism).
-template <int MAXJ, int R>
+// STORE_D = false: only the bf16 copy of dz is written (the tensor-core path never reads the fp32 one again).
+template <int MAXJ, int R, bool STORE_D>
 __global__ void __launch_bounds__(256)
 ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, const float* __restrict__ rstd,
                         const float* __restrict__ ln_g, const float* __restrict__ ln_b,
@@ -582,7 +583,7 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
           const int n = lane + 32 * j;
           if (n < C) {
             const float dz = ln_g ? rs[q] * (dy[j] * gam[j] - mg - xh[q][j] * mgx) : dy[j];
-            d[(int64_t)r * C + n] = dz;
+            if (STORE_D) d[(int64_t)r * C + n] = dz;
             if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
             c0[j] += dz;
             c1[j] += dy[j] * xh[q][j];
@@ -611,11 +612,17 @@ ln_relu_bwd_warp_kernel(float* __restrict__ d, const float* __restrict__ xhat, c
 // host-side dispatch over the channel count (C <= 256)
 static inline cudaError_t launch_ln_relu_bwd_warp(int ctas, cudaStream_t s, float* d, const float* xhat, const float* rstd,
                                                   const float* ln_g, const float* ln_b, const float* act, int rows, int C,
-                                                  float* colpart, __nv_bfloat16* dz16, const __nv_bfloat16* act16) {
+                                                  float* colpart, __nv_bfloat16* dz16, const __nv_bfloat16* act16,
+                                                  bool store_d = true) {
 #define ISDQN_LN_BWD(MAXJ, R)                                                                                          \
-  co_resident_with_tc(ln_relu_bwd_warp_kernel<MAXJ, R>);                                                               \
-  return launch_pdl((ln_relu_bwd_warp_kernel<MAXJ, R>), dim3(ctas), dim3(256), 0, s, d, xhat, rstd, ln_g, ln_b, act, rows, \
-                    C, colpart, dz16, act16)
+  if (store_d || !dz16) {                                                                                              \
+    co_resident_with_tc(ln_relu_bwd_warp_kernel<MAXJ, R, true>);                                                       \
+    return launch_pdl((ln_relu_bwd_warp_kernel<MAXJ, R, true>), dim3(ctas), dim3(256), 0, s, d, xhat, rstd, ln_g, ln_b, act, \
+                      rows, C, colpart, dz16, act16);                                                                  \
+  }                                                                                                                    \
+  co_resident_with_tc(ln_relu_bwd_warp_kernel<MAXJ, R, false>);                                                        \
+  return launch_pdl((ln_relu_bwd_warp_kernel<MAXJ, R, false>), dim3(ctas), dim3(256), 0, s, d, xhat, rstd, ln_g, ln_b, act, \
+                    rows, C, colpart, dz16, act16)
   if (C <= 32) { ISDQN_LN_BWD(1, 4); }
   if (C <= 64) { ISDQN_LN_BWD(2, 4); }
   if (C <= 128) { ISDQN_LN_BWD(4, 2); }
@@ -921,7 +928,7 @@ static __global__ void __launch_bounds__(kLossThreads)
 heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action,
                      const double* __restrict__ reward, const uint8_t* __restrict__ terminal, float gamma_n, int B,
                      int B_global, int K, int A, float* __restrict__ losses, float* __restrict__ dq,
-                     float* __restrict__ dbias, int32_t* count) {
+                     float* __restrict__ dbias, int32_t* count, double* __restrict__ cumulated = nullptr) {
   pdl_sync();
   __shared__ float red[kLossThreads / 32];
   __shared__ float dbw[kLossThreads / 32][kMaxActions];
@@ -971,6 +978,7 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
     float t = 0.f;
     for (int w = 0; w < kLossThreads / 32; ++w) t += red[w];
     losses[k] = t * inv_b;
+    if (cumulated) cumulated[k] += (double)(t * inv_b);
   }
   if (dbias && tid < A) {
     float t = 0.f;
@@ -981,27 +989,57 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
   if (count && k == 0 && tid == 0) *count += 1;
 }
 
-// Head layer forward (tiny: N = (1+K)A <= 128 columns): one CTA per row, 4 k-groups x 128 columns.
-static __global__ void __launch_bounds__(512)
+// Head layer forward (tiny: N = (1+K)A <= 128 columns): one CTA per kHeadRows rows (the head kernel is read once per
+// CTA, not once per row), 4 k-groups x 128 columns; per row the sum runs in the same order as for a single row.
+template <int kHeadRows>
+__global__ void __launch_bounds__(512)
 head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int K, int N,
-                float* __restrict__ out) {
+                float* __restrict__ out, int rows) {
   pdl_sync();
-  extern __shared__ float xs[];  // [K]
-  __shared__ float part[4][128];
-  const int r = blockIdx.x, tid = threadIdx.x;
-  for (int k = tid; k < K; k += 512) xs[k] = x[(int64_t)r * K + k];
+  extern __shared__ float xs[];  // [kHeadRows][K]
+  __shared__ float part[4][kHeadRows][128];
+  const int r0 = blockIdx.x * kHeadRows, tid = threadIdx.x;
+  const int nr = min(kHeadRows, rows - r0);
+  for (int i = tid; i < kHeadRows * K; i += 512) {
+    const int r = i / K;
+    xs[i] = r < nr ? x[(int64_t)(r0 + r) * K + (i - r * K)] : 0.f;
+  }
   __syncthreads();
   const int n = tid & 127, g = tid >> 7;
-  float acc = 0.f;
+  float acc[kHeadRows];
+#pragma unroll
+  for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
   if (n < N) {
     const int kq = (K + 3) / 4;
     const int k_end = min(K, (g + 1) * kq);
-#pragma unroll 32
-    for (int k = g * kq; k < k_end; ++k) acc = fmaf(xs[k], __ldg(w + (int64_t)k * N + n), acc);
+#pragma unroll(kHeadRows == 1 ? 16 : 4)
+    for (int k = g * kq; k < k_end; ++k) {
+      const float wv = __ldg(w + (int64_t)k * N + n);
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
+    }
   }
-  part[g][n] = acc;
+#pragma unroll
+  for (int r = 0; r < kHeadRows; ++r) part[g][r][n] = acc[r];
   __syncthreads();
-  if (g == 0 && n < N) out[(int64_t)r * N + n] = ((part[0][n] + part[1][n]) + (part[2][n] + part[3][n])) + bias[n];
+  for (int i = tid; i < kHeadRows * 128; i += 512) {
+    const int r = i >> 7, c = i & 127;
+    if (r < nr && c < N) out[(int64_t)(r0 + r) * N + c] = ((part[0][r][c] + part[1][r][c]) + (part[2][r][c] + part[3][r][c])) + bias[c];
+  }
+}
+
+// rows per CTA: 1 while the launch is small (parallelism first), 8 for large batches (K <= kHeadMaxK: 96 KB of rows)
+constexpr int kHeadMaxK = 3072;
+static inline cudaError_t launch_head_fwd(cudaStream_t s, const float* x, const float* w, const float* bias, int K, int N,
+                                          float* out, int rows) {
+  if (rows <= 1024) return launch_pdl((head_fwd_kernel<1>), dim3(rows), dim3(512), K * sizeof(float), s, x, w, bias, K, N, out, rows);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kHeadMaxK * 4);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  return launch_pdl((head_fwd_kernel<8>), dim3(ceil_div(rows, 8)), dim3(512), 8 * K * sizeof(float), s, x, w, bias, K, N, out, rows);
 }
 
 // dense_finalize_kernel + head_fwd_kernel in one launch (the tensor-core path at small batch is bound by the number of

@@ -115,6 +115,7 @@ struct Workspace {
   int64_t dq;                            // [B][n_out]
   int64_t dbuf[2];                       // ping-pong gradient buffers (d_out / dz of the current layer)
   int64_t wpart[ISDQN_MAX_FEATURES + 1]; // split partial sums of the conv weight gradients
+  int wsplits_tc[ISDQN_MAX_FEATURES + 1];
   int wsplits[ISDQN_MAX_FEATURES + 1];
   int64_t colpart[ISDQN_MAX_FEATURES + 1];  // [ctas][3][out_dim] column partials of the LN/ReLU backward
   int col_ctas[ISDQN_MAX_FEATURES + 1];
@@ -137,6 +138,16 @@ static inline int conv_wgrad_splits(int M, int K, int N) {
   const int max_by_m = M / 128 > 0 ? M / 128 : 1;
   if (s > max_by_m) s = max_by_m;
   if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  return s;
+}
+// tensor-core path: 128-row tiles of the K axis, all output channels in one tile => fewer tiles, more splits to fill
+// two CTAs per SM (the partial buffer is sized for the larger of the two counts)
+static inline int conv_wgrad_splits_tc(int M, int K) {
+  int s = (2 * kNumSMs) / ceil_div(K, 128);
+  const int max_by_m = M / 128 > 0 ? M / 128 : 1;
+  if (s > max_by_m) s = max_by_m;
+  if (s > 160) s = 160;
   if (s < 1) s = 1;
   return s;
 }
@@ -191,7 +202,9 @@ static inline void carve_workspace(const Plan& p, int rows, int B, Workspace* w)
       const Layer& L = p.L[l];
       if (L.type == 0) {
         w->wsplits[l] = conv_wgrad_splits(B * L.pix, L.in_dim, L.out_dim);
-        w->wpart[l] = take((int64_t)w->wsplits[l] * L.in_dim * L.out_dim);
+        w->wsplits_tc[l] = conv_wgrad_splits_tc(B * L.pix, L.in_dim);
+        const int most = w->wsplits[l] > w->wsplits_tc[l] ? w->wsplits[l] : w->wsplits_tc[l];
+        w->wpart[l] = take((int64_t)most * L.in_dim * L.out_dim);
       } else if (l == p.n_layers - 1 && head_wgrad_splits(B, L.in_dim, L.out_dim) > 1) {
         w->wsplits[l] = head_wgrad_splits(B, L.in_dim, L.out_dim);  // (used by the tensor-core path only)
         w->wpart[l] = take((int64_t)w->wsplits[l] * L.in_dim * L.out_dim);

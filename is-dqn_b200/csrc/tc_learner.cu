@@ -387,11 +387,10 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
                                     split_stride, rows, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]), xhat,
                                     rstd, rows_train, w16(wt, t.act16[l])));
       }
-    } else if (L.out_dim <= 128 && L.in_dim <= 8192) {  // head layer: fp32 (N = (1+K)A is tiny, not 16-byte aligned)
+    } else if (L.out_dim <= 128 && L.in_dim <= kHeadMaxK) {  // head layer: fp32 (N = (1+K)A is tiny, not 16-byte aligned)
       ISDQN_PROF(s, "head_fwd");
-      ISDQN_CUDA_CHECK(launch_pdl(head_fwd_kernel, dim3(rows), dim3(512), L.in_dim * sizeof(float), s, wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off,
-                                                                L.in_dim, L.out_dim, wsp(ws, w.act[l])));
-      ISDQN_LAUNCH_CHECK();
+      ISDQN_CUDA_CHECK(launch_head_fwd(s, wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off, L.in_dim, L.out_dim,
+                                       wsp(ws, w.act[l]), rows));
     } else {
       GemmArgs g;
       g.A = wsp(ws, w.act[l - 1]); g.sam = L.in_dim; g.sak = 1;
@@ -409,7 +408,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   ISDQN_CUDA_CHECK(launch_pdl(heads_td_loss_kernel, dim3(net->n_heads), dim3(kLossThreads), 0, s, q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
                                                   tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
                                                   backward ? wsp(ws, w.dq) : nullptr, backward ? grads + last.b_off : nullptr,
-                                                  update ? tr->d_count : nullptr));
+                                                  update ? tr->d_count : nullptr, update ? tr->d_cumulated : nullptr));
   ISDQN_LAUNCH_CHECK();
   if (q_out)
     ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * (size_t)rows * p.n_out, cudaMemcpyDeviceToDevice, s));
@@ -518,14 +517,14 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       int real_splits = 1;
       float* part = wsp(ws, w.wpart[l]);
       if (l == 0 && t.x16 >= 0 && L.ksz * L.Cin == 32)
-        rc = launch_conv_wgrad_tc<false, true>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, sw,
+        rc = launch_conv_wgrad_tc<false, true>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw,
                                                1.0f / 255.0f, side ? side_cap : 0);
       else if (l == 0 && t.x16 >= 0)
-        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits[l], &real_splits, sw, 1.0f / 255.0f,
+        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw, 1.0f / 255.0f,
                                          side ? side_cap : 0);
-      else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits[l], &real_splits, sw);
+      else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw);
       else
-        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits[l], &real_splits, sw, 1.0f,
+        rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw, 1.0f,
                                          side ? side_cap : 0);
       add_seg(part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
     }
@@ -567,7 +566,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       if (ln_bwd_use_warp(P.out_dim)) {
         ISDQN_CUDA_CHECK(launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
                                 P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]),
-                                dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr));
+                                dz16_prev, P.type == 0 ? w16(wt, t.act16[l - 1]) : nullptr, /*store_d=*/false));
       } else {
         ISDQN_CUDA_CHECK(launch_pdl(ln_relu_bwd_block_kernel, dim3(w.col_ctas[l - 1]), dim3(kRowThreads), 0, s, 
             dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, P.type == 1 ? wsp(ws, w.act[l - 1]) : nullptr, rows_p,

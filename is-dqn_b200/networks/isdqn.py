@@ -322,10 +322,10 @@ class iSDQN:
             else:
                 batch_samples = replay_buffer.sample()
 
+            # (`self.cumulated_losses += losses`, isdqn.py:62, happens inside the step's loss kernel)
             self.params, self.optimizer_state, losses = self.learn_on_batch(
-                self.params, self.optimizer_state, batch_samples
+                self.params, self.optimizer_state, batch_samples, _accumulate=True
             )
-            self._d_cumulated += losses
 
     def update_target_params(self, step: int):
         if step % self.target_update_frequency == 0:
@@ -348,7 +348,7 @@ class iSDQN:
 
         return False, {}
 
-    def learn_on_batch(self, params: ParamTree, optimizer_state: OptState, batch_samples):
+    def learn_on_batch(self, params: ParamTree, optimizer_state: OptState, batch_samples, _accumulate: bool = False):
         """isdqn.py:82-90.  Returns (params, optimizer_state, losses[K] float32 CUDA tensor); params / optimizer
         state are updated in place (donated) and returned."""
         B = int(batch_samples.action.shape[0])
@@ -364,22 +364,23 @@ class iSDQN:
         run = side if side is not None else cur
         self._load_batch(ctx, batch_samples, run)
         try:
-            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream)
+            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream, _accumulate)
             self._last_step = (out[2], run)
             return out
         finally:
             if side is not None:
                 cur.wait_stream(side)
 
-    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream):
+    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False):
         key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
-               optimizer_state["count"].data_ptr(), stream)
+               optimizer_state["count"].data_ptr(), stream, bool(accumulate))
         if self._use_graph and ctx["graph"] is not None and ctx["graph_key"] == key:
             if ctx["ws_tc"] is not None and params.shadow_dirty:
                 self._refresh_shadow(params, stream)
             _lib.check(self._lib.isdqn_graph_launch(ctx["graph"], stream), "isdqn_graph_launch")
             return params, optimizer_state, ctx["losses"]
         tr = self._train_struct(ctx, params, optimizer_state, B)
+        tr.d_cumulated = self._d_cumulated.data_ptr() if accumulate else None
         if self._use_graph and ctx["warm"] >= 1 and self._nccl_comm is None:
             # capture this very step (it executes on replay, not during capture)
             if ctx["graph"] is not None:

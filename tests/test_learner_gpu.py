@@ -267,3 +267,34 @@ def test_pipelined_host_batches_match_device_batches():
     assert a_host.params.flat.cpu().numpy().tobytes() == a_dev.params.flat.cpu().numpy().tobytes()
     for got, want in zip(host_losses, dev_losses[-4:]):
         assert got.tobytes() == want.tobytes()
+
+
+def test_update_online_params_accumulates_losses_on_device():
+    """isdqn.py:55-62: `cumulated_losses += losses` — done by the loss kernel of the captured step; learn_on_batch alone
+    must not touch the accumulator."""
+
+    class OneBatchReplay:
+        def __init__(self, batches):
+            self.batches, self.i = batches, 0
+
+        def sample(self):
+            b = self.batches[self.i % len(self.batches)]
+            self.i += 1
+            return batch_as_element(b)
+
+    cfg = dict(obs_dim=(84, 84, 4), A=6, K=3, features=[32, 64, 64, 512], layer_norm=True, arch="cnn")
+    a, twin = make_agent(12, **cfg), make_agent(12, **cfg)
+    p = oracle_params_for(a, 12)
+    push_params(a, p)
+    push_params(twin, p)
+    batches = [L.make_batch(800 + i, 8, cfg["obs_dim"], cfg["A"], "cnn") for i in range(5)]
+    rb = OneBatchReplay(batches)
+    want = np.zeros(cfg["K"], dtype=np.float64)
+    for i in range(5):
+        a.update_online_params(i + 1, rb)
+        _, _, losses = twin.learn_on_batch(twin.params, twin.optimizer_state, batch_as_element(batches[i]))
+        want += losses.cpu().numpy().astype(np.float64)
+    assert np.array_equal(a.cumulated_losses, want)
+    assert np.array_equal(twin.cumulated_losses, np.zeros(cfg["K"]))
+    a.cumulated_losses = np.zeros(cfg["K"])
+    assert np.array_equal(a.cumulated_losses, np.zeros(cfg["K"]))
