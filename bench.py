@@ -172,6 +172,11 @@ def workload_config(capacity):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the step
+# (profiles/r01_b32_step_ncu.md; cold caches: the fp32 reads all come from DRAM, most writes are still in L2 at the end)
+NCU_TRAFFIC_BYTES = {"adam": 67_726_848}
+
+
 def kernel_work(name: str, P: int):
     """Algorithmic work of one launch for the roofline: ('hbm', bytes) or ('tensor', flops)."""
     B = BATCH
@@ -349,8 +354,8 @@ def run_ours(args, rank, world, local_rank):
     elif kind == "hbm":
         ach = (work / 1e9) / ((dom_ms / dom_count) / 1e3)
         roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
-                    "share_of_step": dom_ms / step_prof_ms}
+                    "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES.get(dom_name), "peak_src": peaks["src"],
+                    "share_of_step": dom_ms / step_prof_ms, "algorithmic_bytes": work}
     else:
         roofline = {"kernel": dom_name, "bound": "tensor", "achieved": None, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                     "frac": None, "traffic": None, "peak_src": peaks["src"], "share_of_step": dom_ms / step_prof_ms}

@@ -3,14 +3,17 @@
 // the accumulator back with tcgen05.ld — thread t owns output row t, so row-wise LayerNorm is thread-local.
 // Persistent and warp-specialised: see tc_gemm_kernel below.
 //
-// Shared-memory operand layout: the canonical NO-SWIZZLE ("interleave") UMMA layout of 8x16-byte core matrices,
-// which — unlike the 128B-swizzle atoms TMA produces — accepts any extent that is a multiple of 8 and is cheap to
-// fill from a gather.  One pipeline stage holds 64 elements of the reduction (K) dimension:
-//     K-major  operand (reduction contiguous in the source):  byte(row r, 16B-chunk c of K) = (r/8)*1024 + c*128 + (r%8)*16
-//     MN-major operand (row index contiguous in the source):  byte(K-row kk, 16B-chunk c of MN) = c*1024 + (kk/8)*128 + (kk%8)*16
-// In both cases the descriptor has LBO = 128 B (next core matrix along K), SBO = 1024 B (next core matrix along
-// M/N), and one MMA (K = 16) advances the start address by 256 B.  (cute/arch/mma_sm100_desc.hpp and
-// cute/atom/mma_traits_sm100.hpp::make_umma_desc document the field semantics.)
+// Shared-memory operand layouts (one pipeline stage holds 64 elements = 128 bytes of the reduction (K) dimension):
+//   128-byte swizzle (the A stage always, the B stage when BN >= 64): 8-row atoms of 1024 B, row r at
+//       (r/8)*1024 + (r%8)*128, its eight 16-byte chunks XOR-permuted by r%8 — conflict-free for a gather that writes
+//       one row per 8 lanes, and what the tensor core reads fastest.  MN-major operands use the transposed atom
+//       (64 MN elements x 8 K rows).
+//   core-matrix ("interleave", no swizzle) layout for the BN == 32 B stage, which is narrower than a swizzle atom:
+//       K-major  byte(row r, 16B-chunk c of K)     = (r/8)*1024 + c*128 + (r%8)*16
+//       MN-major byte(K-row kk, 16B-chunk c of MN) = c*1024 + (kk/8)*128 + (kk%8)*16
+// kmajor_off / mnmajor_off give the byte offsets, stage_desc the matching shared-memory descriptors; one MMA (K = 16)
+// advances the start address inside the stage.  (cute/arch/mma_sm100_desc.hpp and
+// cute/atom/mma_traits_sm100.hpp::make_umma_desc document the descriptor fields.)
 #pragma once
 #include <cuda_bf16.h>
 
@@ -177,8 +180,9 @@ constexpr int kFirstProducerWarp = 5;
 
 // Persistent, warp-specialised kernel.  Tiles (x fastest, then y, then z) are dealt round-robin to the CTAs; inside
 // a CTA three roles run concurrently and meet only through mbarriers:
-//   producers  gather the operands of k-chunk j into stage j % STAGES (cp.async / LDG+convert), keep STAGES-1 chunks
-//              in flight, and arrive on full[s] once their part of a chunk has landed and is fenced to the async proxy;
+//   producers  gather the operands of k-chunk j into stage j % STAGES with 16-byte cp.async (LDG + convert for the uint8
+//              fallback) as soon as the stage is free, and never wait for data: the arrival of each producer thread on
+//              full[s] is triggered by the completion of its copies (cp.async.mbarrier.arrive.noinc);
 //   MMA warp   waits full[s], issues 4 x tcgen05.mma (K = 16 each) into accumulator a = tile & 1, tcgen05.commit ->
 //              empty[s]; after the last chunk of a tile commit -> tmem_full[a];
 //   epilogue   waits tmem_full[a], reads the accumulator with tcgen05.ld (thread t owns row t), runs the problem's
