@@ -221,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
 
     cap = args.capacity
     rb = ReplayBuffer(UniformSamplingDistribution(rank), BATCH, cap, stack_size=4, update_horizon=1, gamma=GAMMA,
-                      clipping=lambda x: np.clip(x, -1, 1), frame_capacity=cap + cap // 8 + 64)
+                      clipping=lambda x: np.clip(x, -1, 1), frame_capacity=cap + cap // 8 + 64, pinned_ring=16)
     t_fill = time.perf_counter()
     n_fill = cap + max(cap // 10, 64)
     for obs, a, r, d in synthetic_stream(1000 + rank, n_fill):
@@ -384,8 +384,9 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps,
-                "pipeline": "host numpy batch -> pinned slot -> H2D on the copy engine (2 slots) -> step; the losses of "
-                            "step i are read on the host after step i+1 is enqueued"},
+                "pipeline": "host numpy batches as rb.sample() returns them with pinned_ring=16 (views of a pinned block in "
+                            "the packed batch layout) -> one H2D per step on the copy engine (2 device slots) -> step; the "
+                            "losses of step i are read on the host after step i+1 is enqueued"},
         "gpu_launches": launches * args.steps,
         "gpu_launches_per_step": launches,
         "roofline": roofline,

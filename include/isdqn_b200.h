@@ -262,6 +262,18 @@ int isdqn_dp_init(const uint8_t* h_unique_id_128, int32_t rank, int32_t world, v
 int isdqn_dp_allreduce_f32(void* comm, float* d_buf, int64_t n, void* stream);
 int isdqn_dp_destroy(void* comm);
 
+/* Host-batch staging for the reference-facing call `learn_on_batch(params, opt_state, host batch)` (isdqn.py:82; the
+ * reference's implicit device_put at the jit boundary).  Events are created without timing.
+ * isdqn_stage_batch: h_src (pinned) -> d_stage on copy_stream [after ev_stage_free], record ev_h2d_done; step_stream waits
+ * it, copies d_stage -> d_dst and re-records ev_stage_free.  isdqn_read_async: d_src -> h_dst (pinned) on stream, then
+ * records event.  Nothing synchronises except isdqn_event_synchronize. */
+int isdqn_event_create(void** out_event);
+int isdqn_event_destroy(void* event);
+int isdqn_event_synchronize(void* event);
+int isdqn_stage_batch(const void* h_src, void* d_stage, void* d_dst, int64_t bytes, void* copy_stream, void* step_stream,
+                      void* ev_h2d_done, void* ev_stage_free);
+int isdqn_read_async(void* h_dst, const void* d_src, int64_t bytes, void* stream, void* event);
+
 /* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
  * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */
 int isdqn_trace_set(void* d_buf);

@@ -138,6 +138,11 @@ PROTOTYPES = {
     "isdqn_profile_end": (C.c_int, [_P, _I32, C.c_char_p, _I32, C.POINTER(C.c_float)]),
     "isdqn_spin": (C.c_int, [_P, _I32]),
     "isdqn_trace_set": (C.c_int, [_P]),
+    "isdqn_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "isdqn_event_destroy": (C.c_int, [_P]),
+    "isdqn_event_synchronize": (C.c_int, [_P]),
+    "isdqn_stage_batch": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
+    "isdqn_read_async": (C.c_int, [_P, _P, _I64, _P, _P]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),
@@ -215,3 +220,48 @@ def stream_ptr() -> int:
 
 def ptr(t) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------- packed host batches
+BATCH_FIELDS = ("state", "next_state", "action", "reward", "terminal")
+
+
+def batch_pack_layout(batch: int, state_bytes_per_row: int):
+    """One batch as ONE block: state | next_state | action int64 | reward float64 | terminal uint8, every field on a
+    16-byte boundary.  Returns (total bytes, {field: (offset, nbytes)}).  The learner's device batch buffers, its staging
+    slots and the pinned blocks `ReplayBuffer.sample()` returns all use this layout, so a sampled batch reaches the
+    learner with a single host -> device copy."""
+    offs, o = {}, 0
+    for name, nb in zip(BATCH_FIELDS, (batch * state_bytes_per_row, batch * state_bytes_per_row, 8 * batch, 8 * batch, batch)):
+        offs[name] = (o, nb)
+        o = (o + nb + 15) // 16 * 16
+    return o, offs
+
+
+_PINNED_BLOCKS = {}  # base address -> (tensor, nbytes): pinned blocks handed out by pinned_block()
+
+
+def pinned_block(nbytes: int):
+    """A zeroed pinned uint8 tensor, remembered so that arrays living inside it can be recognised later."""
+    torch = require_cuda()
+    t = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8).pin_memory()
+    _PINNED_BLOCKS[t.data_ptr()] = (t, t.numel())
+    return t
+
+
+def pinned_pack_base(arrays, offs) -> Optional[int]:
+    """Base address of the registered pinned block that holds the five numpy `arrays` (BATCH_FIELDS order) exactly at
+    the offsets of `offs`, or None."""
+    try:
+        a0 = arrays[0]
+        base = a0.ctypes.data - offs[BATCH_FIELDS[0]][0]
+        blk = _PINNED_BLOCKS.get(base)
+        if blk is None:
+            return None
+        for name, a in zip(BATCH_FIELDS, arrays):
+            off, nb = offs[name]
+            if a.ctypes.data != base + off or a.nbytes != nb or not a.flags.c_contiguous:
+                return None
+        return base if off + nb <= blk[1] else None
+    except AttributeError:
+        return None

@@ -268,3 +268,48 @@ extern "C" int isdqn_trace_set(void* d_buf) {
   if (rc) return rc;
   return isdqn_trace_set_tc(reinterpret_cast<unsigned long long*>(d_buf));
 }
+
+// ---------------------------------------------------------------------------------------------- host-batch staging
+// Plumbing for the reference-facing call with HOST batches (iSDQN.learn_on_batch): events and the two asynchronous copy
+// sequences, so that the Python side issues one call per step instead of a dozen framework calls.
+extern "C" int isdqn_event_create(void** out_event) {
+  if (!out_event) return ISDQN_E_INVALID;
+  cudaEvent_t e = nullptr;
+  ISDQN_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *out_event = e;
+  return ISDQN_OK;
+}
+extern "C" int isdqn_event_destroy(void* event) {
+  if (event) ISDQN_CUDA_CHECK(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event)));
+  return ISDQN_OK;
+}
+extern "C" int isdqn_event_synchronize(void* event) {
+  if (!event) return ISDQN_E_INVALID;
+  ISDQN_CUDA_CHECK(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event)));
+  return ISDQN_OK;
+}
+
+// h_src (pinned) -> d_stage on copy_stream, then d_stage -> d_dst on step_stream:
+//   copy_stream waits ev_stage_free (the step-stream copy that last read d_stage), copies, records ev_h2d_done;
+//   step_stream waits ev_h2d_done, copies d_stage -> d_dst, re-records ev_stage_free.
+extern "C" int isdqn_stage_batch(const void* h_src, void* d_stage, void* d_dst, int64_t bytes, void* copy_stream,
+                                 void* step_stream, void* ev_h2d_done, void* ev_stage_free) {
+  if (!h_src || !d_stage || !d_dst || bytes < 1 || !ev_h2d_done || !ev_stage_free) return ISDQN_E_INVALID;
+  cudaStream_t cs = as_stream(copy_stream), ss = as_stream(step_stream);
+  cudaEvent_t e_h2d = reinterpret_cast<cudaEvent_t>(ev_h2d_done), e_free = reinterpret_cast<cudaEvent_t>(ev_stage_free);
+  ISDQN_CUDA_CHECK(cudaStreamWaitEvent(cs, e_free, 0));
+  ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_stage, h_src, (size_t)bytes, cudaMemcpyHostToDevice, cs));
+  ISDQN_CUDA_CHECK(cudaEventRecord(e_h2d, cs));
+  ISDQN_CUDA_CHECK(cudaStreamWaitEvent(ss, e_h2d, 0));
+  ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_dst, d_stage, (size_t)bytes, cudaMemcpyDeviceToDevice, ss));
+  ISDQN_CUDA_CHECK(cudaEventRecord(e_free, ss));
+  return ISDQN_OK;
+}
+
+// d_src -> h_dst (pinned) on `stream`, then record `event` (isdqn_event_synchronize(event) makes h_dst readable)
+extern "C" int isdqn_read_async(void* h_dst, const void* d_src, int64_t bytes, void* stream, void* event) {
+  if (!h_dst || !d_src || bytes < 1 || !event) return ISDQN_E_INVALID;
+  ISDQN_CUDA_CHECK(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+  ISDQN_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), as_stream(stream)));
+  return ISDQN_OK;
+}

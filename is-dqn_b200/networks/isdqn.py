@@ -21,15 +21,21 @@ def _key_to_seed(key) -> np.random.SeedSequence:
     return np.random.SeedSequence(np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8).tolist() or [0])
 
 
+def _new_event(lib):
+    ev = _lib.C.c_void_p()
+    _lib.check(lib.isdqn_event_create(ev), "isdqn_event_create")
+    return ev
+
+
 class HostLosses:
     """Handle on an in-flight device->host copy of one step's losses (`iSDQN.losses_to_host_async`)."""
 
-    def __init__(self, buf, event):
-        self._buf, self._event = buf, event
+    def __init__(self, lib, buf, event):
+        self._lib, self._buf, self._event = lib, buf, event
 
     def get(self) -> np.ndarray:
-        self._event.synchronize()
-        return self._buf.numpy().copy()
+        _lib.check(self._lib.isdqn_event_synchronize(self._event), "isdqn_event_synchronize")
+        return self._buf.copy()
 
 
 class OptState(dict):
@@ -141,12 +147,7 @@ class iSDQN:
         # the five batch fields live in ONE device allocation (16-byte aligned sub-ranges) so that a staged host batch
         # reaches them with a single device-to-device copy
         item = 1 if dt == t.uint8 else 4
-        n_state = int(np.prod(shape)) * item
-        al = lambda n: (n + 15) // 16 * 16
-        offs, o = {}, 0
-        for name, nb in (("state", n_state), ("next_state", n_state), ("action", 8 * B), ("reward", 8 * B), ("terminal", B)):
-            offs[name] = (o, nb)
-            o = al(o + nb)
+        o, offs = _lib.batch_pack_layout(B, int(np.prod(shape[1:])) * item)
         ctx["pack_bytes"], ctx["pack_offs"] = o, offs
         ctx["dev_pack"] = t.zeros(o, dtype=t.uint8, device="cuda")
 
@@ -236,40 +237,48 @@ class iSDQN:
         return tr
 
     def _stage_host_batch(self, ctx, fields, stream) -> None:
-        """Host numpy batch -> pinned slot -> (copy stream) device slot -> (step stream) the batch buffers.  Two slots:
-        the H2D copy of step i+1 runs on the copy engine while step i computes; the CPU only blocks when it is two
-        steps ahead of the GPU."""
+        """Host numpy batch -> (pinned slot ->) device slot on the copy stream -> the batch buffers on the step stream.
+        Two slots: the H2D copy of step i+1 runs on the copy engine while step i computes; the CPU only blocks when it
+        is two steps ahead of the GPU.  A batch that already lives in a pinned block of the packed layout (what
+        `ReplayBuffer.sample()` returns) is copied straight from there: no host-side copy at all."""
         t = self._torch
+        lib = self._lib
         st = ctx["stage"]
         if st is None:
             st = ctx["stage"] = {
                 "slot": 0,
-                "host": [t.zeros(ctx["pack_bytes"], dtype=t.uint8).pin_memory() for _ in range(2)],
-                "dev": [t.zeros(ctx["pack_bytes"], dtype=t.uint8, device="cuda") for _ in range(2)],
-                "h2d_done": [t.cuda.Event() for _ in range(2)],
-                "d2d_done": [t.cuda.Event() for _ in range(2)],
+                "host": [_lib.pinned_block(ctx["pack_bytes"]) for _ in range(2)],
+                # (torch.empty: a zero-fill would be a kernel on the CURRENT stream, which the copy stream does not follow
+                # — it could land after the first batch was staged and wipe it)
+                "dev": [t.empty(ctx["pack_bytes"], dtype=t.uint8, device="cuda") for _ in range(2)],
+                "h2d_done": [_new_event(lib) for _ in range(2)],
+                "stage_free": [_new_event(lib) for _ in range(2)],
             }
             st["host_np"] = [{k: v.numpy() for k, v in ctx["views"](h).items()} for h in st["host"]]
             if self._copy_stream is None:
                 self._copy_stream = t.cuda.Stream()
+            # whatever the allocator did to these blocks on the current stream is ordered before both users
+            cur = t.cuda.current_stream()
+            self._copy_stream.wait_stream(cur)
+            stream.wait_stream(cur)
         slot = st["slot"]
         st["slot"] = slot ^ 1
-        st["h2d_done"][slot].synchronize()  # the previous copy out of this pinned slot has finished
-        for name, f in fields.items():
-            arr = np.asarray(f)
-            if name in ("state", "next_state") and self.network.architecture_type == "cnn" and arr.dtype != np.uint8:
-                raise TypeError("cnn batches must be uint8 frames (float states: use loss_on_batch / apply)")
-            dst = st["host_np"][slot][name]
-            dst[...] = arr.reshape(dst.shape)
-        cs = self._copy_stream
-        cs.wait_event(st["d2d_done"][slot])  # the step that consumed this device slot has copied it out
-        with t.cuda.stream(cs):
-            st["dev"][slot].copy_(st["host"][slot], non_blocking=True)
-            st["h2d_done"][slot].record(cs)
-        stream.wait_event(st["h2d_done"][slot])
-        with t.cuda.stream(stream):
-            ctx["dev_pack"].copy_(st["dev"][slot], non_blocking=True)
-            st["d2d_done"][slot].record(stream)
+        arrays = [np.asarray(fields[k]) for k in _lib.BATCH_FIELDS]
+        if self.network.architecture_type == "cnn" and (arrays[0].dtype != np.uint8 or arrays[1].dtype != np.uint8):
+            raise TypeError("cnn batches must be uint8 frames (float states: use loss_on_batch / apply)")
+        h_src = _lib.pinned_pack_base(arrays, ctx["pack_offs"])
+        if h_src is None:
+            # pageable (or differently laid out) arrays: through this slot's pinned block, once its last copy has left
+            _lib.check(lib.isdqn_event_synchronize(st["h2d_done"][slot]), "isdqn_event_synchronize")
+            for name, arr in zip(_lib.BATCH_FIELDS, arrays):
+                dst = st["host_np"][slot][name]
+                dst[...] = arr.reshape(dst.shape)
+            h_src = st["host"][slot].data_ptr()
+        _lib.check(
+            lib.isdqn_stage_batch(h_src, st["dev"][slot].data_ptr(), ctx["dev_pack"].data_ptr(), ctx["pack_bytes"],
+                                  self._copy_stream.cuda_stream, stream.cuda_stream, st["h2d_done"][slot], st["stage_free"][slot]),
+            "isdqn_stage_batch",
+        )
 
     def _load_batch(self, ctx, batch, stream) -> int:
         """Copies `batch` (host numpy, like `rb.sample()`; or CUDA tensors) into the persistent device buffers, ordered
@@ -296,22 +305,22 @@ class iSDQN:
         `handle.get()` blocks on THAT copy only, so a training loop can read step i's losses while step i+1 runs
         (jax's asynchronous dispatch gives the reference the same overlap).  A handle stays valid for the next 8 calls."""
         t = self._torch
+        lib = self._lib
         if self._loss_ring is None:
-            self._loss_ring = {
-                "i": 0,
-                "buf": [t.zeros(self.n_bellman_iterations, dtype=t.float32).pin_memory() for _ in range(8)],
-                "ev": [t.cuda.Event() for _ in range(8)],
-            }
+            buf = _lib.pinned_block(8 * 4 * self.n_bellman_iterations).view(t.float32).view(8, self.n_bellman_iterations)
+            self._loss_ring = {"i": 0, "buf": buf, "np": buf.numpy(), "ev": [_new_event(lib) for _ in range(8)]}
         if self._last_step is None:
             raise RuntimeError("losses_to_host_async() follows a learn_on_batch() call")
         losses, stream = self._last_step
         r = self._loss_ring
         i = r["i"]
         r["i"] = (i + 1) % 8
-        with t.cuda.stream(stream):
-            r["buf"][i].copy_(losses, non_blocking=True)
-            r["ev"][i].record(stream)
-        return HostLosses(r["buf"][i], r["ev"][i])
+        _lib.check(
+            lib.isdqn_read_async(r["buf"][i].data_ptr(), losses.data_ptr(), 4 * self.n_bellman_iterations, stream.cuda_stream,
+                                 r["ev"][i]),
+            "isdqn_read_async",
+        )
+        return HostLosses(lib, r["np"][i], r["ev"][i])
 
     # ------------------------------------------------------------------------------------------------ update
     def update_online_params(self, step: int, replay_buffer):

@@ -101,6 +101,7 @@ class ReplayBuffer:
         clipping: callable = None,
         frame_capacity: Optional[int] = None,
         staging_frames: int = 2048,
+        pinned_ring: int = 0,
     ):
         torch = _lib.require_cuda()
         self._torch = torch
@@ -139,6 +140,11 @@ class ReplayBuffer:
         self._flushed_elems = 0     # elements whose metadata is already on the device
         self._pending_event = None
         self._action_dtype = None
+        # pinned_ring = N > 0: sample() returns views of one of N pinned blocks (round-robin) in the learner's packed batch
+        # layout instead of fresh arrays, so learn_on_batch can DMA the batch back without a host-side copy; such a
+        # batch is valid until N - 1 further sample() calls of the same size.  0 (default): fresh arrays, as the reference.
+        self._pinned_ring = int(pinned_ring)
+        self._host_rings = {}       # batch size -> ring of pinned blocks handed out by sample()
 
     # ------------------------------------------------------------------------------------------ allocation
     def _allocate(self, observation: np.ndarray) -> None:
@@ -317,12 +323,49 @@ class ReplayBuffer:
         return ReplayElement(state, action, reward, nxt, terminal)
 
     def _to_host(self, b: ReplayElement) -> ReplayElement:
+        """Device batch -> host numpy arrays: fresh arrays by default; with `pinned_ring=N` views of ONE pinned block in
+        the learner's packed batch layout (_lib.batch_pack_layout), so that
+        `agent.learn_on_batch(params, opt_state, rb.sample())` moves the batch back with a single DMA and no host copy."""
+        if self._pinned_ring <= 0:
+            n = b.action.numel()
+            shape = (n,) + tuple(self._obs_shape) + (self._stack_size,)
+            state = b.state.cpu().numpy().view(self._obs_dtype).reshape(shape)
+            nxt = b.next_state.cpu().numpy().view(self._obs_dtype).reshape(shape)
+            action = b.action.cpu().numpy().astype(self._action_dtype or np.int64, copy=False)
+            return ReplayElement(state, action, b.reward.cpu().numpy(), nxt, b.is_terminal.cpu().numpy().astype(np.bool_))
+        t = self._torch
         n = b.action.numel()
         shape = (n,) + tuple(self._obs_shape) + (self._stack_size,)
-        state = b.state.cpu().numpy().view(self._obs_dtype).reshape(shape)
-        nxt = b.next_state.cpu().numpy().view(self._obs_dtype).reshape(shape)
-        action = b.action.cpu().numpy().astype(self._action_dtype or np.int64, copy=False)
-        return ReplayElement(state, action, b.reward.cpu().numpy(), nxt, b.is_terminal.cpu().numpy().astype(np.bool_))
+        row_bytes = int(np.prod(shape[1:])) * self._elem_size
+        ring = self._host_rings.get(n)
+        if ring is None:
+            total, offs = _lib.batch_pack_layout(n, row_bytes)
+            ring = self._host_rings[n] = {"i": 0, "offs": offs, "blocks": [_lib.pinned_block(total) for _ in range(self._pinned_ring)]}
+        blk = ring["blocks"][ring["i"] % self._pinned_ring]
+        ring["i"] += 1
+        offs = ring["offs"]
+
+        def field(name, dtype):
+            o, nb = offs[name]
+            return blk[o : o + nb].view(dtype)
+
+        field("state", t.uint8).copy_(b.state.reshape(-1).view(t.uint8), non_blocking=True)
+        field("next_state", t.uint8).copy_(b.next_state.reshape(-1).view(t.uint8), non_blocking=True)
+        field("action", t.int64).copy_(b.action, non_blocking=True)
+        field("reward", t.float64).copy_(b.reward, non_blocking=True)
+        field("terminal", t.uint8).copy_(b.is_terminal, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        h = blk.numpy()
+
+        def host(name, dtype):
+            o, nb = offs[name]
+            return h[o : o + nb].view(dtype)
+
+        action = host("action", np.int64)
+        if self._action_dtype is not None:
+            action = action.astype(self._action_dtype, copy=False)
+        return ReplayElement(host("state", self._obs_dtype).reshape(shape), action, host("reward", np.float64),
+                             host("next_state", self._obs_dtype).reshape(shape), host("terminal", np.bool_))
 
     def _gather_keys(self, keys: np.ndarray) -> ReplayElement:
         slots = (np.asarray(keys, dtype=np.int64) % self._slots).astype(np.int32)

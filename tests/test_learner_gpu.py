@@ -298,3 +298,34 @@ def test_update_online_params_accumulates_losses_on_device():
     assert np.array_equal(twin.cumulated_losses, np.zeros(cfg["K"]))
     a.cumulated_losses = np.zeros(cfg["K"])
     assert np.array_equal(a.cumulated_losses, np.zeros(cfg["K"]))
+
+
+def test_pinned_ring_batches_take_the_zero_copy_path():
+    """`ReplayBuffer(pinned_ring=N).sample()` returns views of a pinned block in the learner's packed layout: learn_on_batch
+    recognises it (no host copy) and computes exactly what it computes from ordinary (pageable) copies of the arrays."""
+    from isdqn_b200 import _lib
+    from isdqn_b200.sample_collection.replay_buffer import ReplayBuffer, ReplayElement, TransitionElement
+    from isdqn_b200.sample_collection.samplers import UniformSamplingDistribution
+
+    rb = ReplayBuffer(UniformSamplingDistribution(3), 8, 200, stack_size=4, update_horizon=1, gamma=0.99, pinned_ring=4)
+    rng = np.random.default_rng(5)
+    for i in range(120):
+        rb.add(TransitionElement(rng.integers(0, 256, (84, 84), dtype=np.uint8), int(rng.integers(6)), float(rng.integers(-1, 2)),
+                                 bool(i % 37 == 36), False))
+    cfg = dict(obs_dim=(84, 84, 4), A=6, K=3, features=[32, 64, 64, 512], layer_norm=True, arch="cnn")
+    a, twin = make_agent(13, **cfg), make_agent(13, **cfg)
+    p = oracle_params_for(a, 13)
+    push_params(a, p)
+    push_params(twin, p)
+    for _ in range(6):  # more steps than ring slots: blocks are reused
+        batch = rb.sample()
+        offs = a._context(8)["pack_offs"]
+        arrays = [np.asarray(x) for x in (batch.state, batch.next_state, batch.action, batch.reward, batch.is_terminal)]
+        assert _lib.pinned_pack_base(arrays, offs) is not None
+        copy = ReplayElement(*[np.array(x) for x in batch])
+        assert _lib.pinned_pack_base([np.asarray(x) for x in (copy.state, copy.next_state, copy.action, copy.reward, copy.is_terminal)], offs) is None
+        _, _, l1 = a.learn_on_batch(a.params, a.optimizer_state, batch)
+        _, _, l2 = twin.learn_on_batch(twin.params, twin.optimizer_state, copy)
+        assert l1.cpu().numpy().tobytes() == l2.cpu().numpy().tobytes()
+    torch.cuda.synchronize()
+    assert a.params.flat.cpu().numpy().tobytes() == twin.params.flat.cpu().numpy().tobytes()
