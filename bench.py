@@ -296,6 +296,44 @@ def run_ours(args, rank, world, local_rank):
         ms_replay = r0.elapsed_time(r1) / reps
         prof_replay = _lib.profile(lambda: rb.sample_device(n_big))
         gather_ms = sum(t for n, t in prof_replay if n == "gather_stack4_u8")
+        # ---- prioritized replay at the throughput shape: 65,536 draws per launch through the sum tree,
+        # and the batch-32 priority update; 262,144 live keys (the Python-side fill of the key maps is what bounds this)
+        prio = None
+        if rank == 0:
+            from isdqn_b200.sample_collection.samplers import PrioritizedSamplingDistribution
+
+            n_keys = min(cap, 262_144)
+            ps = PrioritizedSamplingDistribution(7, n_keys)
+            prio_rng = np.random.default_rng(7)
+            pv = np.abs(prio_rng.standard_normal(n_keys)) + 1e-3
+            for k in range(n_keys):
+                ps.add(k, float(pv[k]))
+            for _ in range(3):
+                ps.sample_device(n_big, n_keys + 1)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(reps):
+                ps.sample_device(n_big, n_keys + 1)
+            p1.record()
+            torch.cuda.synchronize()
+            ms_prio = p0.elapsed_time(p1) / reps
+            upd_keys = np.arange(0, 32 * 97, 97, dtype=np.int32)
+            for _ in range(3):
+                ps.update(upd_keys, np.abs(prio_rng.standard_normal(32)) + 1e-3)
+                ps._sum_tree.flush()
+            torch.cuda.synchronize()
+            p0.record()
+            for _ in range(50):
+                ps.update(upd_keys, np.abs(prio_rng.standard_normal(32)) + 1e-3)
+                ps._sum_tree.flush()
+            p1.record()
+            torch.cuda.synchronize()
+            depth = ps._sum_tree._depth
+            bytes_per_sample = (depth - 1) * 8 + 12
+            prio = {"keys": n_keys, "tree_depth": depth, "samples_per_s": n_big / (ms_prio / 1e3), "launch_samples": n_big,
+                    "ms_per_launch": ms_prio, "algorithmic_GBps": bytes_per_sample * n_big / (ms_prio / 1e3) / 1e9,
+                    "update32_us": p0.elapsed_time(p1) / 50 * 1e3}
         # ---- per-kernel profile of one step (direct launches behind a spin kernel: no launch gaps)
         agent._use_graph = False
         prof = _lib.profile(lambda: agent.update_online_params(1, rb))
@@ -397,6 +435,7 @@ def run_ours(args, rank, world, local_rank):
         "replay": {"samples_per_s": world * n_big / (ms_replay / 1e3), "launch_samples": n_big,
                    "gather_GBps": gather_gbs, "gather_frac_of_hbm": (gather_gbs / peaks["hbm_gbs"]) if gather_gbs else None,
                    "kernels_ms": {n: t for n, t in prof_replay}},
+        "replay_prioritized": prio,
         "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 5)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
         "fill": {"adds": n_fill, "seconds": t_fill},
     }

@@ -90,6 +90,14 @@ int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t size, const i
                          int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
                          void* stream);
 
+/* isdqn_sample_uniform for large draws: same results and generator state, spread over the whole GPU (two passes over the
+ * draw positions + a finish kernel).  d_workspace: isdqn_sample_uniform_workspace_bytes() of device scratch owned by the
+ * caller; draws below 8192 (or a NULL workspace) take the single-CTA kernel. */
+int64_t isdqn_sample_uniform_workspace_bytes(void);
+int isdqn_sample_uniform_ws(uint64_t* d_rng, int32_t n_valid, int32_t size, const int32_t* d_index_to_key,
+                            int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
+                            void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* replaces: PrioritizedSamplingDistribution.sample  samplers.py:105-116 (+ SumTree.query).
  * targets = Generator.uniform(0.0, root, size) with root read on the device, then the descent of
  * isdqn_sumtree_query.  d_out_target may be NULL.  Sets ISDQN_ST_EMPTY_TREE when root == 0. */

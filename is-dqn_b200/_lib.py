@@ -138,6 +138,8 @@ PROTOTYPES = {
     "isdqn_profile_end": (C.c_int, [_P, _I32, C.c_char_p, _I32, C.POINTER(C.c_float)]),
     "isdqn_spin": (C.c_int, [_P, _I32]),
     "isdqn_trace_set": (C.c_int, [_P]),
+    "isdqn_sample_uniform_workspace_bytes": (C.c_int64, []),
+    "isdqn_sample_uniform_ws": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "isdqn_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "isdqn_event_destroy": (C.c_int, [_P]),
     "isdqn_event_synchronize": (C.c_int, [_P]),

@@ -14,7 +14,8 @@ template <int kUniformThreads>
 __global__ void __launch_bounds__(kUniformThreads)
 sample_uniform_kernel(uint64_t* rng, uint32_t n_valid, int size, const int32_t* __restrict__ index_to_key,
                       int capacity, int32_t* __restrict__ out_index, int32_t* __restrict__ out_key,
-                      int32_t* __restrict__ out_slot) {
+                      int32_t* __restrict__ out_slot, const int* only_if = nullptr) {
+  if (only_if && !*only_if) return;  // fallback launch of the many-CTA path: normally nothing to do
   __shared__ int warp_tot[32];
   __shared__ int total_sh;
   __shared__ unsigned long long consumed_final;
@@ -62,6 +63,88 @@ sample_uniform_kernel(uint64_t* rng, uint32_t n_valid, int size, const int32_t* 
     __syncthreads();
   }
   if (tid == 0) pcg_store(rng, pcg_after_next32(m0, consumed));
+}
+
+// ---- many-CTA variant for large draws (the throughput shape: 65,536 per launch).  The accept/reject test of draw
+// position p depends only on p, and a draw lands at output index p - (#rejected positions before p).  Pass 1 counts the
+// rejections of every CTA's slice of positions, pass 2 re-evaluates the slice and emits; rejections are rare
+// (probability n_valid / 2^32 each), so the slices cover size + kUniformMargin positions and the single-CTA kernel is the
+// fallback for the astronomically unlikely case that this is not enough (flag in the workspace).
+constexpr int kUniformMargin = 2048;
+constexpr int kUniformWide = 1024;  // threads per CTA
+struct UniformWs {                  // device workspace (isdqn_sample_uniform_workspace_bytes)
+  uint64_t new_rng[6];
+  int fallback;                     // 1: pass 2 gave up, the single-CTA kernel must run
+  int pad;
+  int rej[1024];                    // rejections per CTA slice
+};
+
+__global__ void __launch_bounds__(kUniformWide)
+uniform_count_kernel(const uint64_t* __restrict__ rng, uint32_t n_valid, int slice, UniformWs* ws) {
+  __shared__ int warp_tot[32];
+  __shared__ int total_sh;
+  const PcgMirror m0 = pcg_load(rng);
+  const uint32_t threshold = (uint32_t)((0x100000000ull - n_valid) % n_valid);
+  int rejected = 0;
+  const unsigned long long p0 = (unsigned long long)blockIdx.x * slice;
+  for (int r = threadIdx.x; r < slice; r += kUniformWide) {
+    const uint32_t v = pcg_next32_at(m0, p0 + r);
+    rejected += ((uint32_t)((unsigned long long)v * n_valid) >= threshold) ? 0 : 1;
+  }
+  block_exclusive_scan<kUniformWide>(rejected, warp_tot, &total_sh);
+  if (threadIdx.x == 0) {
+    ws->rej[blockIdx.x] = total_sh;
+    if (blockIdx.x == 0) ws->fallback = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kUniformWide)
+uniform_emit_kernel(const uint64_t* __restrict__ rng, uint32_t n_valid, int size, int slice,
+                    const int32_t* __restrict__ index_to_key, int capacity, int32_t* __restrict__ out_index,
+                    int32_t* __restrict__ out_key, int32_t* __restrict__ out_slot, UniformWs* ws) {
+  __shared__ int warp_tot[32];
+  __shared__ int total_sh;
+  const int tid = threadIdx.x;
+  const PcgMirror m0 = pcg_load(rng);
+  const uint32_t threshold = (uint32_t)((0x100000000ull - n_valid) % n_valid);
+  long long rej_before = 0, rej_all = 0;
+  for (int c = 0; c < (int)gridDim.x; ++c) {
+    const int r = ws->rej[c];
+    if (c < (int)blockIdx.x) rej_before += r;
+    rej_all += r;
+  }
+  if ((long long)gridDim.x * slice - rej_all < size) {  // not enough accepted draws in the covered positions
+    if (blockIdx.x == 0 && tid == 0) ws->fallback = 1;
+    return;
+  }
+  const unsigned long long p0 = (unsigned long long)blockIdx.x * slice;
+  long long out_base = (long long)p0 - rej_before;  // output index of this CTA's first accepted draw
+  for (int r0 = 0; r0 < slice && out_base < size; r0 += kUniformWide) {
+    const unsigned long long p = p0 + r0 + tid;
+    const uint32_t v = pcg_next32_at(m0, p);
+    const unsigned long long prod = (unsigned long long)v * n_valid;
+    const int accept = ((uint32_t)prod >= threshold) ? 1 : 0;
+    const int rank = block_exclusive_scan<kUniformWide>(accept, warp_tot, &total_sh);
+    const long long o = out_base + rank;
+    if (accept && o < size) {
+      const int32_t index = (int32_t)(prod >> 32);
+      if (out_index) out_index[o] = index;
+      if (index_to_key) {
+        const int32_t key = index_to_key[index];
+        if (out_key) out_key[o] = key;
+        if (out_slot) out_slot[o] = key % capacity;
+      }
+      if (o == size - 1) pcg_store(ws->new_rng, pcg_after_next32(m0, p + 1));  // exactly the values numpy consumed
+    }
+    out_base += total_sh;
+    __syncthreads();
+  }
+}
+
+// runs after pass 2: installs the new generator state, or (fallback) hands over to the single-CTA kernel's logic
+__global__ void uniform_finish_kernel(uint64_t* rng, const UniformWs* ws) {
+  if (ws->fallback) return;
+  if (threadIdx.x < 6) rng[threadIdx.x] = ws->new_rng[threadIdx.x];
 }
 
 constexpr int kPrioThreads = 128;
@@ -144,6 +227,34 @@ extern "C" int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t si
   else
     sample_uniform_kernel<1024><<<1, 1024, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key, capacity,
                                                                    d_out_index, d_out_key, d_out_slot);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int64_t isdqn_sample_uniform_workspace_bytes(void) { return (int64_t)sizeof(UniformWs); }
+
+extern "C" int isdqn_sample_uniform_ws(uint64_t* d_rng, int32_t n_valid, int32_t size, const int32_t* d_index_to_key,
+                                       int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
+                                       void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (size < 8192 || n_valid == 1 || !d_workspace || workspace_bytes < (int64_t)sizeof(UniformWs))
+    return isdqn_sample_uniform(d_rng, n_valid, size, d_index_to_key, capacity, d_out_index, d_out_key, d_out_slot, stream);
+  if (!d_rng || n_valid < 1 || (d_index_to_key && capacity < 1)) return ISDQN_E_INVALID;
+  if (size > (1 << 20)) return ISDQN_E_TOO_LARGE;
+  cudaStream_t s = as_stream(stream);
+  UniformWs* ws = reinterpret_cast<UniformWs*>(d_workspace);
+  int grid = ceil_div(size + kUniformMargin, kUniformWide);
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  const int slice = ceil_div(ceil_div(size + kUniformMargin, grid), kUniformWide) * kUniformWide;
+  ISDQN_PROF(s, "sample_uniform");
+  uniform_count_kernel<<<grid, kUniformWide, 0, s>>>(d_rng, (uint32_t)n_valid, slice, ws);
+  ISDQN_LAUNCH_CHECK();
+  uniform_emit_kernel<<<grid, kUniformWide, 0, s>>>(d_rng, (uint32_t)n_valid, size, slice, d_index_to_key, capacity, d_out_index,
+                                                    d_out_key, d_out_slot, ws);
+  ISDQN_LAUNCH_CHECK();
+  uniform_finish_kernel<<<1, 32, 0, s>>>(d_rng, ws);
+  ISDQN_LAUNCH_CHECK();
+  sample_uniform_kernel<1024><<<1, 1024, 0, s>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key, capacity, d_out_index, d_out_key,
+                                                 d_out_slot, &ws->fallback);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

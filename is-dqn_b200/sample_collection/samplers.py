@@ -33,6 +33,7 @@ class UniformSamplingDistribution:
         self._device = torch.device("cuda", torch.cuda.current_device())
         self._rng_key = np.random.default_rng(seed)
         self._d_rng = torch.zeros(6, dtype=torch.int64, device=self._device)
+        self._d_uniform_ws = None
         self._push_rng_state()
 
         self._key_to_index = {}
@@ -107,12 +108,15 @@ class UniformSamplingDistribution:
         d_index = t.empty(size, dtype=t.int32, device=self._device)
         d_key = t.empty(size, dtype=t.int32, device=self._device)
         d_slot = t.empty(size, dtype=t.int32, device=self._device)
+        if self._d_uniform_ws is None:  # scratch of the many-CTA variant (large draws)
+            self._d_uniform_ws = t.zeros(int(self._lib.isdqn_sample_uniform_workspace_bytes()), dtype=t.uint8, device=self._device)
         _lib.check(
-            self._lib.isdqn_sample_uniform(
+            self._lib.isdqn_sample_uniform_ws(
                 self._d_rng.data_ptr(), len(self._index_to_key), size, self._d_index_to_key.data_ptr(),
-                max(int(capacity), 1), d_index.data_ptr(), d_key.data_ptr(), d_slot.data_ptr(), _lib.stream_ptr(),
+                max(int(capacity), 1), d_index.data_ptr(), d_key.data_ptr(), d_slot.data_ptr(),
+                self._d_uniform_ws.data_ptr(), self._d_uniform_ws.numel(), _lib.stream_ptr(),
             ),
-            "isdqn_sample_uniform",
+            "isdqn_sample_uniform_ws",
         )
         return d_index, d_key, d_slot
 

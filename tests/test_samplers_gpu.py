@@ -45,6 +45,41 @@ def test_uniform_rejection_heavy(samplers):
             assert s._rng_key.bit_generator.state == g.bit_generator.state
 
 
+def test_uniform_many_cta_variant(samplers):
+    """isdqn_sample_uniform_ws (two passes over the draw positions, whole GPU) gives numpy's draws and generator state:
+    large draws with few rejections (the fast path), 25-50 % rejections (more than the margin: the single-CTA fallback
+    runs), and a moderate rejection rate that still fits the margin."""
+    import torch
+
+    from isdqn_b200 import _lib
+
+    lib = _lib.load()
+    s = samplers.UniformSamplingDistribution(seed=11)
+    g = np.random.default_rng(11)
+    ws = torch.zeros(int(lib.isdqn_sample_uniform_workspace_bytes()), dtype=torch.uint8, device="cuda")
+    cases = [(1_000_000, 65_536), (999_983, 8192), (1_048_577, 200_001), (37, 65_536), (2**30 + 12345, 70_000),
+             (2**31 - 1, 9000), (2**32 // 3 + 1, 100_000), (1_000_000, 1_048_576), (2**26 + 5, 65_536)]
+    for n, size in cases:
+        out = torch.empty(size, dtype=torch.int32, device="cuda")
+        _lib.check(lib.isdqn_sample_uniform_ws(s._d_rng.data_ptr(), n, size, None, 1, out.data_ptr(), None, None, ws.data_ptr(),
+                                               ws.numel(), _lib.stream_ptr()))
+        np.testing.assert_array_equal(out.cpu().numpy().astype(np.int64), g.integers(n, size=size), err_msg=f"n={n} size={size}")
+        s._pull_rng_state()
+        assert s._rng_key.bit_generator.state == g.bit_generator.state, (n, size)
+    # through the sampler class (keys + slots) at the throughput shape
+    s2 = samplers.UniformSamplingDistribution(seed=5)
+    g2 = np.random.default_rng(5)
+    for k in range(50_000):
+        s2.add(k * 2 + 7)
+    for size in (65_536, 32, 10_000):
+        want = g2.integers(50_000, size=size) * 2 + 7
+        d_index, d_key, d_slot = s2.sample_device(size, 50_001)
+        np.testing.assert_array_equal(d_key.cpu().numpy(), want.astype(np.int32))
+        np.testing.assert_array_equal(d_slot.cpu().numpy(), (want % 50_001).astype(np.int32))
+        s2._pull_rng_state()
+        assert s2._rng_key.bit_generator.state == g2.bit_generator.state
+
+
 def test_swap_remove_key_maps(samplers):
     s = samplers.UniformSamplingDistribution(seed=0)
     g = np.random.default_rng(0)
