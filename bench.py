@@ -334,6 +334,14 @@ def run_ours(args, rank, world, local_rank):
             prio = {"keys": n_keys, "tree_depth": depth, "samples_per_s": n_big / (ms_prio / 1e3), "launch_samples": n_big,
                     "ms_per_launch": ms_prio, "algorithmic_GBps": bytes_per_sample * n_big / (ms_prio / 1e3) / 1e9,
                     "update32_us": p0.elapsed_time(p1) / 50 * 1e3}
+        # ---- acting path: one greedy action for one host observation stack, read back with .item()
+        act_state = np.random.default_rng(3).integers(0, 256, OBS, dtype=np.uint8)
+        for i in range(20):
+            agent.best_action(agent.params, act_state, i).item()
+        t_act = time.perf_counter()
+        for i in range(300):
+            agent.best_action(agent.params, act_state, i).item()
+        acting_us = (time.perf_counter() - t_act) / 300 * 1e6
         # ---- per-kernel profile of one step (direct launches behind a spin kernel: no launch gaps)
         agent._use_graph = False
         prof = _lib.profile(lambda: agent.update_online_params(1, rb))
@@ -436,6 +444,7 @@ def run_ours(args, rank, world, local_rank):
                    "gather_GBps": gather_gbs, "gather_frac_of_hbm": (gather_gbs / peaks["hbm_gbs"]) if gather_gbs else None,
                    "kernels_ms": {n: t for n, t in prof_replay}},
         "replay_prioritized": prio,
+        "acting_us_per_action": acting_us,
         "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 5)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
         "fill": {"adds": n_fill, "seconds": t_fill},
     }

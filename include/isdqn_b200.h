@@ -281,6 +281,12 @@ int isdqn_event_synchronize(void* event);
 int isdqn_stage_batch(const void* h_src, void* d_stage, void* d_dst, int64_t bytes, void* copy_stream, void* step_stream,
                       void* ev_h2d_done, void* ev_stage_free);
 int isdqn_read_async(void* h_dst, const void* d_src, int64_t bytes, void* stream, void* event);
+int isdqn_write_async(void* d_dst, const void* h_src, int64_t bytes, void* stream); /* pinned host -> device */
+
+/* Acting path (isdqn.py:127-135): d_out[h] = argmax_a d_q[h * n_actions + a] for every head h of ONE row of Q-values
+ * (first maximum, like jnp.argmax); the caller picks head 1 + idx on the host.  Together with isdqn_loss_on_batch on a
+ * batch of one (s' aliased to s) this is captured in a CUDA graph by the Python host (iSDQN.best_action). */
+int isdqn_argmax_heads(const float* d_q, int32_t n_heads_total, int32_t n_actions, int32_t* d_out, void* stream);
 
 /* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
  * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */

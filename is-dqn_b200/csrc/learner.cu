@@ -431,4 +431,11 @@ extern "C" int isdqn_best_action(const isdqn_net* net, const float* d_params, co
   return ISDQN_OK;
 }
 
+extern "C" int isdqn_argmax_heads(const float* d_q, int32_t n_heads_total, int32_t n_actions, int32_t* d_out, void* stream) {
+  if (!d_q || !d_out || n_heads_total < 1 || n_actions < 1) return ISDQN_E_INVALID;
+  argmax_heads_kernel<<<ceil_div(n_heads_total, 64), 64, 0, as_stream(stream)>>>(d_q, n_heads_total, n_actions, d_out);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
 int isdqn_trace_set_learner(unsigned long long* buf) { return isdqn::trace_set_local(buf) == cudaSuccess ? ISDQN_OK : ISDQN_E_CUDA; }

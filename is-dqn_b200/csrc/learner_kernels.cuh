@@ -1194,4 +1194,16 @@ static __global__ void argmax_head_kernel(const float* __restrict__ q, int A, in
   }
 }
 
+// the greedy action of EVERY head of one row of Q-values (acting path: the head is chosen on the host afterwards)
+static __global__ void argmax_heads_kernel(const float* __restrict__ q, int n_heads_total, int A, int32_t* out) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < n_heads_total) {
+    const float* v = q + h * A;
+    int best = 0;
+    for (int a = 1; a < A; ++a)
+      if (v[a] > v[best]) best = a;
+    out[h] = best;
+  }
+}
+
 }  // namespace isdqn

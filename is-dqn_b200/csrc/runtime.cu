@@ -306,6 +306,12 @@ extern "C" int isdqn_stage_batch(const void* h_src, void* d_stage, void* d_dst, 
   return ISDQN_OK;
 }
 
+extern "C" int isdqn_write_async(void* d_dst, const void* h_src, int64_t bytes, void* stream) {
+  if (!d_dst || !h_src || bytes < 1) return ISDQN_E_INVALID;
+  ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+  return ISDQN_OK;
+}
+
 // d_src -> h_dst (pinned) on `stream`, then record `event` (isdqn_event_synchronize(event) makes h_dst readable)
 extern "C" int isdqn_read_async(void* h_dst, const void* d_src, int64_t bytes, void* stream, void* event) {
   if (!h_dst || !d_src || bytes < 1 || !event) return ISDQN_E_INVALID;

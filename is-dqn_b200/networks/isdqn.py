@@ -497,9 +497,82 @@ class iSDQN:
         idx_network = int(np.random.default_rng(_key_to_seed(key)).integers(self.n_bellman_iterations))
         return self.best_action_of_head(params, state, idx_network)
 
+    def _greedy_actions_fast(self, params: ParamTree, obs: np.ndarray):
+        """Greedy action of every head for ONE host observation, as host int32[1 + K]: pinned staging -> H2D -> the
+        learner's own forward on a batch of one (s' aliased to s; fp32 or tensor-core path like the learner) + argmax of
+        every head, replayed as one CUDA graph -> D2H; one synchronisation (the reference's `.item()`)."""
+        t = self._torch
+        lib = self._lib
+        net = self.network
+        ctx = self._context(1)
+        a = ctx.get("act")
+        nq = 1 + self.n_bellman_iterations
+        if a is None:
+            nbytes = ctx["state"].numel() * ctx["state"].element_size()
+            h_obs = _lib.pinned_block(nbytes)
+            h_arg = _lib.pinned_block(4 * nq).view(t.int32)
+            a = ctx["act"] = {
+                "h_obs": h_obs, "h_obs_np": h_obs.numpy().view(np.uint8 if ctx["state"].dtype == t.uint8 else np.float32),
+                "nbytes": nbytes, "q": t.empty((2, net.final_feature), dtype=t.float32, device="cuda"),
+                "d_arg": t.empty(nq, dtype=t.int32, device="cuda"), "h_arg": h_arg, "h_arg_np": h_arg.numpy(),
+                "ev": _new_event(lib), "graph": None, "key": None, "warm": 0,
+                "batch": _lib.Batch(ctx["state"].data_ptr(), ctx["state"].data_ptr(), ctx["action"].data_ptr(),
+                                    ctx["reward"].data_ptr(), ctx["terminal"].data_ptr()),
+            }
+        a["h_obs_np"][...] = obs.reshape(-1)
+        cur = t.cuda.current_stream()
+        side = None
+        if self._use_graph and cur.cuda_stream == 0:
+            if self._side_stream is None:
+                self._side_stream = t.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+        run = side if side is not None else cur
+        sp = run.cuda_stream
+        _lib.check(lib.isdqn_write_async(ctx["state"].data_ptr(), a["h_obs"].data_ptr(), a["nbytes"], sp), "isdqn_write_async")
+        if ctx["ws_tc"] is not None and (params.shadow is None or params.shadow_dirty):
+            self._refresh_shadow(params, sp)
+
+        def forward():
+            tr = self._train_struct(ctx, params, None, 1, refresh_shadow=False)
+            rc = lib.isdqn_loss_on_batch(net._net, tr, a["batch"], a["q"].data_ptr(), sp)
+            if rc == 0:
+                rc = lib.isdqn_argmax_heads(a["q"].data_ptr(), nq, self.n_actions, a["d_arg"].data_ptr(), sp)
+            return rc
+
+        key = (params.flat.data_ptr(), sp)
+        if self._use_graph and a["graph"] is not None and a["key"] == key:
+            _lib.check(lib.isdqn_graph_launch(a["graph"], sp), "isdqn_graph_launch")
+        elif self._use_graph and a["warm"] >= 1:
+            if a["graph"] is not None:
+                lib.isdqn_graph_destroy(a["graph"])
+                a["graph"] = None
+            _lib.check(lib.isdqn_graph_begin(sp), "isdqn_graph_begin")
+            rc = forward()
+            exec_ = _lib.C.c_void_p()
+            rc2 = lib.isdqn_graph_end(sp, exec_)
+            _lib.check(rc, "best_action forward (capture)")
+            _lib.check(rc2, "isdqn_graph_end")
+            a["graph"], a["key"] = exec_, key
+            _lib.check(lib.isdqn_graph_launch(a["graph"], sp), "isdqn_graph_launch")
+        else:
+            _lib.check(forward(), "best_action forward")
+            a["warm"] += 1
+        _lib.check(lib.isdqn_read_async(a["h_arg"].data_ptr(), a["d_arg"].data_ptr(), 4 * nq, sp, a["ev"]), "isdqn_read_async")
+        if side is not None:
+            cur.wait_stream(side)
+        _lib.check(lib.isdqn_event_synchronize(a["ev"]), "isdqn_event_synchronize")
+        return a["h_arg_np"]
+
     def best_action_of_head(self, params: ParamTree, state, idx_network: int):
         t = self._torch
         net = self.network
+        if not isinstance(state, t.Tensor):
+            obs = np.asarray(state)
+            want = np.uint8 if net.architecture_type == "cnn" else np.float32
+            if obs.dtype == want and obs.size == int(np.prod(net.observation_dim)) and self._nccl_comm is None:
+                # host observation of the stored dtype: the graph-replayed path; a host int32 (`.item()` works on it)
+                return np.int32(self._greedy_actions_fast(params, obs)[1 + int(idx_network)])
         x, rows, is_float = net.prepare_input(state)
         assert rows == 1
         out = t.empty((), dtype=t.int32, device="cuda")

@@ -329,3 +329,37 @@ def test_pinned_ring_batches_take_the_zero_copy_path():
         assert l1.cpu().numpy().tobytes() == l2.cpu().numpy().tobytes()
     torch.cuda.synchronize()
     assert a.params.flat.cpu().numpy().tobytes() == twin.params.flat.cpu().numpy().tobytes()
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_best_action_graph_path(dtype):
+    """Host uint8 observations take the graph-replayed acting path (pinned staging, batch-of-one forward, argmax of every
+    head): it must follow the parameters through learner steps and shift_params, and agree with the float forward."""
+    cfg = dict(obs_dim=(84, 84, 4), A=9, K=9, features=[32, 64, 64, 512], layer_norm=True, arch="cnn")
+    agent = make_agent(21, **cfg, compute_dtype=dtype)
+    p = oracle_params_for(agent, 21)
+    push_params(agent, p)
+    g = np.random.default_rng(21)
+    K, A = cfg["K"], cfg["A"]
+
+    def check(tag):
+        for trial in range(3):
+            obs = g.integers(0, 256, (84, 84, 4), dtype=np.uint8)
+            q = agent.network.apply(agent.params, obs).reshape(1 + K, A).cpu().numpy()  # fp32 forward of the same params
+            for head in (0, K // 2, K - 1):
+                act = agent.best_action_of_head(agent.params, obs, head)
+                assert isinstance(act.item(), int) and 0 <= int(act) < A
+                row = q[1 + head]
+                if dtype == "float32":
+                    assert int(act) == int(np.argmax(row)), (tag, trial, head)
+                else:  # bf16 forward: the chosen action is a maximiser up to the 2e-2 parity bar
+                    assert row[int(act)] >= row.max() - 2e-2 * max(np.abs(q).max(), 1e-6), (tag, trial, head, row, int(act))
+            assert 0 <= int(agent.best_action(agent.params, obs, trial).item()) < A
+
+    check("initial")
+    for step in range(3):
+        el = batch_as_element(L.make_batch(300 + step, 16, cfg["obs_dim"], A, "cnn"))
+        agent.params, agent.optimizer_state, _ = agent.learn_on_batch(agent.params, agent.optimizer_state, el)
+    check("after learner steps")
+    agent.params = agent.shift_params(agent.params)
+    check("after shift_params")
