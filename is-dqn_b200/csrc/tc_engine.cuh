@@ -15,7 +15,10 @@
 // advances the start address inside the stage.  (cute/arch/mma_sm100_desc.hpp and
 // cute/atom/mma_traits_sm100.hpp::make_umma_desc document the descriptor fields.)
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -68,6 +71,33 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- TMA (tensor-map bulk copies; completion counted in bytes on an mbarrier) ---------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   dst_smem),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+// problems that feed their stages with TMA declare `static constexpr bool TMA = true`
+template <class P, class = void>
+struct uses_tma : std::false_type {};
+template <class P>
+struct uses_tma<P, std::void_t<decltype(P::TMA)>> : std::bool_constant<P::TMA> {};
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -203,7 +233,7 @@ constexpr int kFirstProducerWarp = 5;
 //   __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int z, int etid) const;
 template <class P>
 __global__ void __launch_bounds__(32 * (kFirstProducerWarp + P::PRODUCER_WARPS), P::MIN_CTAS)
-tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
+tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_z) {
   constexpr int BN = P::BN, STAGES = P::STAGES;
   constexpr int B_BYTES = BN * kBK * 2;
   constexpr int PT = 32 * P::PRODUCER_WARPS;
@@ -227,7 +257,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], PT);
+      mbar_init(&full_bar[s], uses_tma<P>::value ? 1 : PT);  // TMA: one arrive.expect_tx, the bytes complete the phase
       mbar_init(&empty_bar[s], 1);
     }
 #pragma unroll
@@ -249,6 +279,28 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
   pdl_trigger();  // (after the TMEM allocation: see common.cuh)
 
   if (warp >= kFirstProducerWarp) {
+   if constexpr (uses_tma<P>::value) {
+    // --------------------------------------------------------------------------------- TMA producer (one thread)
+    // No gather code at all: per 64-deep K chunk the thread announces the stage's byte count on full[s] and issues the
+    // problem's tensor-map copies, which land swizzled exactly as the MMA descriptors expect and bypass the LSU.
+    if (warp == kFirstProducerWarp && lane == 0) {
+      p.tma_prefetch();
+      pdl_wait();
+      int j = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
+        int kb, ke;
+        p.k_range(tz, kb, ke);
+        for (int kc = kb; kc < ke; ++kc, ++j) {
+          const int s = j % STAGES;
+          mbar_wait(&empty_bar[s], (uint32_t)(((j / STAGES) & 1) ^ 1));
+          if (j == 0) trace_mark(2);
+          mbar_arrive_expect_tx(&full_bar[s], p.stage_tx_bytes());
+          p.tma_load(sA + s * kABytes, sB + s * B_BYTES, &full_bar[s], tx, ty, tz, kc);
+        }
+      }
+    }
+   } else {
     // ------------------------------------------------------------------------------------------ producers
     const int ptid = tid - 32 * kFirstProducerWarp;
     p.init_cta(extra_sm, ptid);  // index tables from the kernel arguments only: overlaps the previous kernel's tail
@@ -283,6 +335,7 @@ tc_gemm_kernel(const P p, int tiles_x, int tiles_y, int tiles_z) {
       }
     }
     cp_async_wait_all();
+   }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {

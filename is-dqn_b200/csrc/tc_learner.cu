@@ -229,6 +229,74 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
 #undef ISDQN_CONV_FWD_TC
 }
 
+// ---- TMA-fed forward convolution (stride 1, Cin % 64 == 0, one image = one M tile) -----------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    const char* e = getenv("ISDQN_TMA");
+    if (e && e[0] == '0') return (EncodeTiledFn) nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+bool conv_fwd_tma_ok(const Layer& L) {
+  return tensor_map_encoder() != nullptr && L.type == 0 && L.stride == 1 && L.Cin % 64 == 0 && L.OH == L.H && L.OW == L.W &&
+         L.pix <= tc::kBM && L.W <= 256 && L.H <= 256 && (L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256);
+}
+
+int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w, const float* params, bf16* out, float* xhat,
+                        float* rstd, int m_train, cudaStream_t s) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  CUtensorMap tm_x, tm_w;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)n_img};
+    const cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)L.W * L.Cin * 2, (cuuint64_t)L.H * L.W * L.Cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)L.OW, (cuuint32_t)L.OH, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)L.out_dim, (cuuint64_t)L.in_dim};
+    const cuuint64_t strides[1] = {(cuuint64_t)L.out_dim * 2};
+    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t es[2] = {1, 1};
+    if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+#define ISDQN_CONV_FWD_TMA_W(BN, WIDE)                                                                 \
+  {                                                                                                    \
+    tc::ConvFwdTmaTC<BN, WIDE> p;                                                                      \
+    p.tm_x = tm_x; p.tm_w = tm_w; p.n_img = n_img; p.pix = L.pix; p.ksz = L.ksz;                       \
+    p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.cchunks = L.Cin / 64;                                      \
+    p.bias = params + L.b_off;                                                                         \
+    p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
+    p.ln_b = L.has_ln ? params + L.beta_off : nullptr;                                                 \
+    p.relu = L.relu; p.out = out; p.xhat = xhat; p.rstd = rstd; p.m_train = m_train;                   \
+    p.acc_scale = 1.0f;                                                                                \
+    return launch_tc(p, n_img, 1, 1, s, "tc_conv_fwd_tma");                                            \
+  }
+#define ISDQN_CONV_FWD_TMA(BN)                                                                         \
+  if (wide_launch(n_img)) ISDQN_CONV_FWD_TMA_W(BN, true) else ISDQN_CONV_FWD_TMA_W(BN, false)
+  switch (L.out_dim) {
+    case 64: ISDQN_CONV_FWD_TMA(64)
+    case 128: ISDQN_CONV_FWD_TMA(128)
+    case 256: ISDQN_CONV_FWD_TMA(256)
+    default: return ISDQN_E_UNSUPPORTED;
+  }
+#undef ISDQN_CONV_FWD_TMA_W
+#undef ISDQN_CONV_FWD_TMA
+}
+
 template <bool U8, bool SEG4 = false>
 int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* part, int rows, int splits, int* real_splits,
                          cudaStream_t s, float in_scale = 1.0f, int max_ctas = 0) {
@@ -359,6 +427,9 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       } else if (l == 0)
         rc = launch_conv_fwd_tc<true>(L, b->d_state, b->d_next_state, B, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
                                       xhat, rstd, rows_train * L.pix, s);
+      else if (conv_fwd_tma_ok(L))
+        rc = launch_conv_fwd_tma(L, w16(wt, t.act16[l - 1]), rows, shadow + L.w_off, params, w16(wt, t.act16[l]), xhat, rstd,
+                                 rows_train * L.pix, s);
       else
         rc = launch_conv_fwd_tc<false>(L, w16(wt, t.act16[l - 1]), nullptr, rows, rows, shadow + L.w_off, params,
                                        w16(wt, t.act16[l]), xhat, rstd, rows_train * L.pix, s);

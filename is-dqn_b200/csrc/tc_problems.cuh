@@ -235,6 +235,80 @@ __device__ __forceinline__ void store_chunk_u8(uint32_t dst, const uint2 p) {
                int_pair_bf16(p.y & 0xff, (p.y >> 8) & 0xff), int_pair_bf16((p.y >> 16) & 0xff, p.y >> 24));
 }
 
+// Epilogue of a forward convolution for ONE accumulator row (thread = row): bias + LayerNorm + ReLU, bf16 activation
+// out, fp32 x-hat and rstd for the rows with a backward pass.  Every lane of the warp must call it (tcgen05.ld).
+struct ConvEpilogueArgs {
+  const float* prm;  // shared memory: bias[BN] | ln_g[BN] | ln_b[BN]
+  bool ln_g;         // LayerNorm present
+  int relu;
+  bf16* out; float* xhat; float* rstd; int m_train;
+  float acc_scale;
+};
+template <int BN>
+__device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e, uint32_t tmem_lane_base, int64_t m, bool valid) {
+    const float4* pb = reinterpret_cast<const float4*>(e.prm);
+    const float4* pg = reinterpret_cast<const float4*>(e.prm + BN);
+    const float4* pbeta = reinterpret_cast<const float4*>(e.prm + 2 * BN);
+    float mean = 0.f, rs = 1.f;
+    if (e.ln_g) {  // flax LayerNorm: var = max(0, E[x^2] - E[x]^2), eps = 1e-6
+      float s = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_lane_base + cb * 32, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = pb[cb * 8 + q];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float z = fmaf(v[4 * q + j], e.acc_scale, bb[j]);
+            s += z;
+            s2 += z * z;
+          }
+        }
+      }
+      mean = s / (float)BN;
+      rs = rsqrtf(fmaxf(s2 / (float)BN - mean * mean, 0.f) + 1e-6f);
+    }
+    const bool save = valid && e.ln_g && e.xhat != nullptr && m < e.m_train;
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      float v[32];
+      tmem_ld32(tmem_lane_base + cb * 32, v);
+      uint32_t packed[16];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = pb[cb * 8 + q], g4 = pg[cb * 8 + q], e4 = pbeta[cb * 8 + q];
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float z = fmaf(v[4 * q + j], e.acc_scale, bb[j]);
+          if (e.ln_g) {
+            z = (z - mean) * rs;
+            v[4 * q + j] = z;  // normalised value, saved for the backward pass
+            z = z * gg[j] + ee[j];
+          }
+          y[j] = e.relu ? fmaxf(z, 0.f) : z;
+        }
+        packed[2 * q] = pack_bf16(y[0], y[1]);
+        packed[2 * q + 1] = pack_bf16(y[2], y[3]);
+      }
+      if (valid) {
+        uint4* o = reinterpret_cast<uint4*>(e.out + (int64_t)m * BN + cb * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+      }
+      if (save) {
+        float4* x = reinterpret_cast<float4*>(e.xhat + (int64_t)m * BN + cb * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    if (save) e.rstd[m] = rs;
+  }
+
 // ------------------------------------------------------------------------------------------------ conv forward
 // out[m][co] = ReLU(LN(sum_k im2col(x)[m][k] W[k][co] + bias)); A gathered K-major, B = W (HWIO = [K][Cout]) MN-major.
 // IN_U8 requires Cin == 4 (the stacked Atari frames); bf16 input requires Cin % 8 == 0.
@@ -328,68 +402,65 @@ struct ConvFwdTC {
   }
   __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
     const int m = m0 + etid;
-    const float4* pb = reinterpret_cast<const float4*>(ec.prm);
-    const float4* pg = reinterpret_cast<const float4*>(ec.prm + BN);
-    const float4* pbeta = reinterpret_cast<const float4*>(ec.prm + 2 * BN);
-    float mean = 0.f, rs = 1.f;
-    if (ln_g) {  // flax LayerNorm: var = max(0, E[x^2] - E[x]^2), eps = 1e-6
-      float s = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        float v[32];
-        tmem_ld32(tmem_lane_base + cb * 32, v);
+    ConvEpilogueArgs e;
+    e.prm = ec.prm; e.ln_g = ln_g != nullptr; e.relu = relu; e.out = out; e.xhat = xhat; e.rstd = rstd; e.m_train = m_train;
+    e.acc_scale = acc_scale;
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, m < M);
+  }
+};
+
+// ------------------------------------------------------------------------------- conv forward, TMA-fed (stride 1)
+// Same contraction and epilogue as ConvFwdTC, but no gather code: one M tile = ONE image (OH*OW <= 128 output pixels,
+// the remaining accumulator rows are computed on stale shared memory and never stored); per 64-deep K chunk — one tap
+// (ky, kx) x 64 input channels — a single 4-D tensor-map copy of the box {64 channels, OW, OH, 1 image} starting at
+// (c0, kx - pad, ky - pad, image) brings the whole A stage: rows land at 128-byte pitch with the hardware 128-byte
+// swizzle (= kmajor_off<true>), pixels outside the image are zero-filled by the TMA unit.  The weight chunk (64 K rows x
+// BN output channels) is BN/64 2-D copies in the MN-major swizzled layout.  Nothing goes through the LSU.
+template <int BN_, bool WIDE_ = false>
+struct ConvFwdTmaTC {
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
+  static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 3 * BN_;
+  static constexpr bool A_MN = false, B_MN = true, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  static_assert(BN_ % 64 == 0, "the weight stage is filled in 64-column swizzle groups");
+  CUtensorMap tm_x;  // activations [N][H][W][Cin] bf16, box {64, OW, OH, 1}, SWIZZLE_128B
+  CUtensorMap tm_w;  // weights [K][Cout] bf16, box {64, 64}, SWIZZLE_128B
+  int n_img, pix, ksz, pad_y, pad_x, cchunks;  // cchunks = Cin / 64
+  const float* bias; const float* ln_g; const float* ln_b; int relu;
+  bf16* out; float* xhat; float* rstd; int m_train;
+  float acc_scale;
+  struct PCtx {};
+  struct ECtx {
+    const float* prm;
+  };
+  __device__ void tma_prefetch() const {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+  }
+  __device__ uint32_t stage_tx_bytes() const { return (uint32_t)(pix * 128 + BN * 128); }
+  __device__ void k_range(int, int& b, int& e) const { b = 0; e = ksz * ksz * cchunks; }
+  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int img, int, int, int kc) const {
+    const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * 64;
+    const int ky = tap / ksz, kx = tap - ky * ksz;
+    tma_load_4d(stage_a, &tm_x, c0, kx - pad_x, ky - pad_y, img, bar);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b4 = pb[cb * 8 + q];
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float z = fmaf(v[4 * q + j], acc_scale, bb[j]);
-            s += z;
-            s2 += z * z;
-          }
-        }
-      }
-      mean = s / (float)BN;
-      rs = rsqrtf(fmaxf(s2 / (float)BN - mean * mean, 0.f) + 1e-6f);
+    for (int g = 0; g < BN / 64; ++g) tma_load_2d(stage_b + g * 8192, &tm_w, g * 64, kc * 64, bar);
+  }
+  __device__ void init_epilogue(ECtx& e, float* ep_sm, int etid) const {
+    for (int i = etid; i < BN; i += kThreads) {
+      ep_sm[i] = bias[i];
+      ep_sm[BN + i] = ln_g ? ln_g[i] : 1.f;
+      ep_sm[2 * BN + i] = ln_g ? ln_b[i] : 0.f;
     }
-    const bool valid = m < M;
-    const bool save = valid && ln_g != nullptr && xhat != nullptr && m < m_train;
-#pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      float v[32];
-      tmem_ld32(tmem_lane_base + cb * 32, v);
-      uint32_t packed[16];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 b4 = pb[cb * 8 + q], g4 = pg[cb * 8 + q], e4 = pbeta[cb * 8 + q];
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
-        float y[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float z = fmaf(v[4 * q + j], acc_scale, bb[j]);
-          if (ln_g) {
-            z = (z - mean) * rs;
-            v[4 * q + j] = z;  // normalised value, saved for the backward pass
-            z = z * gg[j] + ee[j];
-          }
-          y[j] = relu ? fmaxf(z, 0.f) : z;
-        }
-        packed[2 * q] = pack_bf16(y[0], y[1]);
-        packed[2 * q + 1] = pack_bf16(y[2], y[3]);
-      }
-      if (valid) {
-        uint4* o = reinterpret_cast<uint4*>(out + (int64_t)m * BN + cb * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-      }
-      if (save) {
-        float4* x = reinterpret_cast<float4*>(xhat + (int64_t)m * BN + cb * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) x[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-    }
-    if (save) rstd[m] = rs;
+    e.prm = ep_sm;
+  }
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
+  __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
+    const int img = m0 / kBM;  // (the engine numbers tiles in units of 128 rows; here tile = image)
+    ConvEpilogueArgs e;
+    e.prm = ec.prm; e.ln_g = ln_g != nullptr; e.relu = relu; e.out = out; e.xhat = xhat; e.rstd = rstd; e.m_train = m_train;
+    e.acc_scale = acc_scale;
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, (int64_t)img * pix + etid, etid < pix && img < n_img);
   }
 };
 
