@@ -112,6 +112,37 @@ int pick_bn_parallel(int n, int other_ctas) {
   return bn;
 }
 
+// ---- tensor maps (the driver entry point is fetched at run time: no link dependency on libcuda) -----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    const char* e = getenv("ISDQN_TMA");
+    if (e && e[0] == '0') return (EncodeTiledFn) nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+
+// 2-D bf16 row-major matrix [rows][ld] as a tensor map with a {box_inner, box_rows} box and the 128-byte swizzle
+int encode_matrix_map(CUtensorMap* tm, const bf16* base, int64_t inner, int64_t rows, int64_t ld, int box_inner, int box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  return tensor_map_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? ISDQN_OK
+             : ISDQN_E_CUDA;
+}
+
 // D[M][N] (fp32, + split partials) = A B^T with the four operand-major combinations
 template <bool A_MN, bool B_MN>
 int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C, int64_t ldc, int64_t split_stride, int M,
@@ -132,6 +163,32 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
 #define ISDQN_GEMM_TC(BN)                                                      \
   if (wide_launch((int64_t)ceil_div(M, tc::kBM) * ceil_div(N, BN) * real_splits)) ISDQN_GEMM_TC_W(BN, true) \
   else ISDQN_GEMM_TC_W(BN, false)
+#define ISDQN_GEMM_TMA_W(BN, WIDE)                                             \
+  {                                                                            \
+    tc::GemmTmaTC<BN, A_MN, B_MN, WIDE> p;                                     \
+    p.tm_a = tm_a; p.tm_b = tm_b; p.C = C; p.ldc = ldc;                        \
+    p.split_stride = split_stride; p.M = M; p.N = N; p.K = K;                  \
+    p.chunks_per_split = cps;                                                  \
+    return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag, max_ctas); \
+  }
+#define ISDQN_GEMM_TMA(BN)                                                     \
+  if (wide_launch((int64_t)ceil_div(M, tc::kBM) * ceil_div(N, BN) * real_splits)) ISDQN_GEMM_TMA_W(BN, true) \
+  else ISDQN_GEMM_TMA_W(BN, false)
+  if (bn >= 64 && tensor_map_encoder() != nullptr && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(B) & 15) == 0 && lda % 8 == 0 && ldb % 8 == 0) {
+    CUtensorMap tm_a, tm_b;
+    int rc = A_MN ? encode_matrix_map(&tm_a, A, M, K, lda, 64, 64) : encode_matrix_map(&tm_a, A, K, M, lda, 64, tc::kBM);
+    if (rc) return rc;
+    rc = B_MN ? encode_matrix_map(&tm_b, B, N, K, ldb, 64, 64) : encode_matrix_map(&tm_b, B, K, N, ldb, 64, bn);
+    if (rc) return rc;
+    switch (bn) {
+      case 64: ISDQN_GEMM_TMA(64)
+      case 128: ISDQN_GEMM_TMA(128)
+      default: ISDQN_GEMM_TMA(256)
+    }
+  }
+#undef ISDQN_GEMM_TMA_W
+#undef ISDQN_GEMM_TMA
   switch (bn) {
     case 32: ISDQN_GEMM_TC(32)
     case 64: ISDQN_GEMM_TC(64)
@@ -230,22 +287,6 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
 }
 
 // ---- TMA-fed forward convolution (stride 1, Cin % 64 == 0, one image = one M tile) -----------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn fn = [] {
-    const char* e = getenv("ISDQN_TMA");
-    if (e && e[0] == '0') return (EncodeTiledFn) nullptr;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
 bool conv_fwd_tma_ok(const Layer& L) {
   return tensor_map_encoder() != nullptr && L.type == 0 && L.stride == 1 && L.Cin % 64 == 0 && L.OH == L.H && L.OW == L.W &&
          L.pix <= tc::kBM && L.W <= 256 && L.H <= 256 && (L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256);
@@ -264,15 +305,7 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ISDQN_E_CUDA;
   }
-  {
-    const cuuint64_t dims[2] = {(cuuint64_t)L.out_dim, (cuuint64_t)L.in_dim};
-    const cuuint64_t strides[1] = {(cuuint64_t)L.out_dim * 2};
-    const cuuint32_t box[2] = {64, 64};
-    const cuuint32_t es[2] = {1, 1};
-    if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return ISDQN_E_CUDA;
-  }
+  if (encode_matrix_map(&tm_w, w, L.out_dim, L.in_dim, L.out_dim, 64, 64)) return ISDQN_E_CUDA;
 #define ISDQN_CONV_FWD_TMA_W(BN, WIDE)                                                                 \
   {                                                                                                    \
     tc::ConvFwdTmaTC<BN, WIDE> p;                                                                      \

@@ -157,6 +157,55 @@ struct GemmTC {
   }
 };
 
+// The same GEMM with both operand stages filled by TMA (2-D tensor maps over the row-major matrices, 128-byte swizzle,
+// out-of-range rows/columns zero-filled by the copy engine — ragged M, N and K need no predicates): one producer thread,
+// no LSU traffic.  BN >= 64 (a 32-wide B stage is narrower than a swizzle atom: GemmTC handles it).
+template <int BN_, bool A_MN_, bool B_MN_, bool WIDE_ = false>
+struct GemmTmaTC {
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1, EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  static_assert(BN_ % 64 == 0, "swizzled B stage");
+  CUtensorMap tm_a;  // A K-major: dims {K, M}, box {64, 128};  A MN-major: dims {M, K}, box {64, 64}
+  CUtensorMap tm_b;  // B K-major: dims {K, N}, box {64, BN};   B MN-major: dims {N, K}, box {64, 64}
+  float* C; int64_t ldc; int64_t split_stride;
+  int M, N, K, chunks_per_split;
+  struct PCtx {};
+  struct ECtx {};
+  __device__ void tma_prefetch() const {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  __device__ uint32_t stage_tx_bytes() const { return (uint32_t)(kABytes + BN * 128); }
+  __device__ void k_range(int split, int& b, int& e) const {
+    const int total = (K + kBK - 1) / kBK;
+    b = split * chunks_per_split;
+    e = min(total, b + chunks_per_split);
+  }
+  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int tx, int ty, int, int kc) const {
+    const int m0 = tx * kBM, n0 = ty * BN, k0 = kc * kBK;
+    if (A_MN) {
+      tma_load_2d(stage_a, &tm_a, m0, k0, bar);
+      tma_load_2d(stage_a + 8192, &tm_a, m0 + 64, k0, bar);
+    } else {
+      tma_load_2d(stage_a, &tm_a, k0, m0, bar);
+    }
+    if (B_MN) {
+#pragma unroll
+      for (int g = 0; g < BN / 64; ++g) tma_load_2d(stage_b + g * 8192, &tm_b, n0 + 64 * g, k0, bar);
+    } else {
+      tma_load_2d(stage_b, &tm_b, k0, n0, bar);
+    }
+  }
+  __device__ void init_epilogue(ECtx&, float*, int) const {}
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
+    const int m = m0 + etid;
+    float* dst = C + (int64_t)split * split_stride + (int64_t)(m < M ? m : 0) * ldc;
+    store_rows_f32<BN>(tmem_lane_base, dst, m < M, n0, N);
+  }
+};
+
 // im2col chunk table shared by the conv forward and weight-gradient problems.
 // bf16 input (Cin % 8 == 0): chunk = 8 channels of one tap.   uint8 input with Cin == 4: chunk = 2 taps (kx, kx+1).
 // entry.off = ((ky*W + kx)*Cin + c0) elements, entry.yx = (ky << 16) | kx.
