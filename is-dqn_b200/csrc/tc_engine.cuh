@@ -295,7 +295,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
           const int s = j % STAGES;
           mbar_wait(&empty_bar[s], (uint32_t)(((j / STAGES) & 1) ^ 1));
           if (j == 0) trace_mark(2);
-          mbar_arrive_expect_tx(&full_bar[s], p.stage_tx_bytes());
+          mbar_arrive_expect_tx(&full_bar[s], p.stage_tx_bytes(tz));
           p.tma_load(sA + s * kABytes, sB + s * B_BYTES, &full_bar[s], tx, ty, tz, kc);
         }
       }
@@ -358,7 +358,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
 #pragma unroll
           for (int q = 0; q < kBK / 16; ++q) {
             const uint64_t adesc = stage_desc<P::A_MN, true>(sA + s * kABytes, q);
-            const uint64_t bdesc = stage_desc<P::B_MN, (BN >= 64)>(sB + s * B_BYTES, q);
+            const uint64_t bdesc = stage_desc<P::B_MN, P::B_SW>(sB + s * B_BYTES, q);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kc > kb || q > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);

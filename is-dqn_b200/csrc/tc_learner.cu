@@ -359,7 +359,61 @@ int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* 
 #undef ISDQN_CONV_WGRAD_TC
 }
 
+// TMA-fed input gradient: stride <= 2, Cout % 64 == 0, every parity class of one image fits one M tile
+bool conv_dgrad_tma_ok(const Layer& L) {
+  if (tensor_map_encoder() == nullptr || L.type != 0 || L.stride > 2 || L.out_dim % 64 != 0) return false;
+  if (!(L.Cin == 32 || L.Cin == 64 || L.Cin == 128 || L.Cin == 256)) return false;
+  const int ny = ceil_div(L.H, L.stride), nx = ceil_div(L.W, L.stride);
+  return ny * nx <= tc::kBM && nx <= 256 && ny <= 256;
+}
+
+int launch_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  CUtensorMap tm_dz[4], tm_w;
+  const int st = L.stride;
+  for (int cls = 0; cls < st * st; ++cls) {
+    const int ry = cls / st, rx = cls % st;
+    const int iy_first = ((ry - L.pad_y) % st + st) % st, ix_first = ((rx - L.pad_x) % st + st) % st;
+    int ny = iy_first < L.H ? (L.H - iy_first + st - 1) / st : 0;
+    int nx = ix_first < L.W ? (L.W - ix_first + st - 1) / st : 0;
+    if (ny < 1) ny = 1;  // (an empty class issues no copies; the map only has to be valid)
+    if (nx < 1) nx = 1;
+    const cuuint64_t dims[4] = {(cuuint64_t)L.out_dim, (cuuint64_t)L.OW, (cuuint64_t)L.OH, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)L.out_dim * 2, (cuuint64_t)L.OW * L.out_dim * 2, (cuuint64_t)L.OH * L.OW * L.out_dim * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)nx, (cuuint32_t)ny, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tm_dz[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(dz), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  for (int cls = st * st; cls < 4; ++cls) tm_dz[cls] = tm_dz[0];
+  const int bn = pick_bn(L.Cin);
+  if (encode_matrix_map(&tm_w, w, L.out_dim, (int64_t)L.ksz * L.ksz * L.Cin, L.out_dim, 64, bn)) return ISDQN_E_CUDA;
+#define ISDQN_CONV_DGRAD_TMA_W(BN, WIDE)                                                               \
+  {                                                                                                    \
+    tc::ConvDgradTmaTC<BN, WIDE> p;                                                                    \
+    for (int i = 0; i < 4; ++i) p.tm_dz[i] = tm_dz[i];                                                 \
+    p.tm_w = tm_w; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.Cout = L.out_dim; p.ksz = L.ksz;             \
+    p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.n_img = B; p.cchunks = L.out_dim / 64; \
+    p.dx = dx;                                                                                         \
+    return launch_tc(p, B, ceil_div(L.Cin, BN), st * st, s, "tc_conv_dgrad_tma");                      \
+  }
+#define ISDQN_CONV_DGRAD_TMA(BN)                                                                       \
+  if (wide_launch((int64_t)B * ceil_div(L.Cin, BN) * st * st)) ISDQN_CONV_DGRAD_TMA_W(BN, true)        \
+  else ISDQN_CONV_DGRAD_TMA_W(BN, false)
+  switch (bn) {
+    case 32: ISDQN_CONV_DGRAD_TMA(32)
+    case 64: ISDQN_CONV_DGRAD_TMA(64)
+    case 128: ISDQN_CONV_DGRAD_TMA(128)
+    default: ISDQN_CONV_DGRAD_TMA(256)
+  }
+#undef ISDQN_CONV_DGRAD_TMA_W
+#undef ISDQN_CONV_DGRAD_TMA
+}
+
 int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s) {
+  if (conv_dgrad_tma_ok(L)) return launch_conv_dgrad_tma(L, dz, w, dx, B, s);
   const int taps = ceil_div(L.ksz, L.stride);
   const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
   const int bn = pick_bn(L.Cin);

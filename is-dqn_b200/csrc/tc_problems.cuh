@@ -176,7 +176,7 @@ struct GemmTmaTC {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
   }
-  __device__ uint32_t stage_tx_bytes() const { return (uint32_t)(kABytes + BN * 128); }
+  __device__ uint32_t stage_tx_bytes(int) const { return (uint32_t)(kABytes + BN * 128); }
   __device__ void k_range(int split, int& b, int& e) const {
     const int total = (K + kBK - 1) / kBK;
     b = split * chunks_per_split;
@@ -486,7 +486,7 @@ struct ConvFwdTmaTC {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
   }
-  __device__ uint32_t stage_tx_bytes() const { return (uint32_t)(pix * 128 + BN * 128); }
+  __device__ uint32_t stage_tx_bytes(int) const { return (uint32_t)(pix * 128 + BN * 128); }
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = ksz * ksz * cchunks; }
   __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int img, int, int, int kc) const {
     const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * 64;
@@ -725,6 +725,75 @@ struct ConvDgradTC {
   }
   __device__ void epilogue(const ECtx& e, uint32_t tmem_lane_base, int, int n0, int, int) const {
     store_rows_f32<BN>(tmem_lane_base, dx + (int64_t)e.pix * Cin, e.valid, n0, Cin);
+  }
+};
+
+// ------------------------------------------------------------------------------- conv input gradient, TMA-fed
+// One M tile = (image, stride-parity class): the class's input pixels form an ny x nx grid, and for tap (ty, tx) of the
+// class the output pixels they touch are the same grid shifted by (-ty, -tx) — a plain box of dz, whatever the stride.
+// Per chunk (valid tap x 64 output channels): one 4-D copy {64, nx, ny, 1} of dz at (co0, ox0 - tx, oy0 - ty, image) with
+// out-of-range output pixels zero-filled, and one 2-D copy {64 co, BN input channels} of the tap's weights (K-major B).
+// Up to 4 classes (stride <= 2): one tensor map per class because the box extents differ.
+template <int BN_, bool WIDE_ = false>
+struct ConvDgradTmaTC {
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
+  static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  CUtensorMap tm_dz[4];  // dz [N][OH][OW][Cout] bf16, box {64, nx(cls), ny(cls), 1}
+  CUtensorMap tm_w;      // weights as [ksz*ksz*Cin rows][Cout], box {64, BN}
+  int H, W, Cin, Cout, ksz, stride, pad_y, pad_x, n_img, cchunks;  // cchunks = Cout / 64
+  float* dx;             // [n_img*H*W][Cin]
+  struct PCtx {};
+  struct ECtx {};
+  struct Cls {
+    int ry, rx, iy_first, ix_first, ny, nx, oy0, ox0, n_ty, n_tx;
+  };
+  __device__ Cls cls_of(int cls) const {
+    Cls c;
+    const int s = stride;
+    c.ry = cls / s;
+    c.rx = cls % s;
+    c.iy_first = ((c.ry - pad_y) % s + s) % s;
+    c.ix_first = ((c.rx - pad_x) % s + s) % s;
+    c.ny = c.iy_first < H ? (H - c.iy_first + s - 1) / s : 0;
+    c.nx = c.ix_first < W ? (W - c.ix_first + s - 1) / s : 0;
+    c.oy0 = (c.iy_first + pad_y - c.ry) / s;
+    c.ox0 = (c.ix_first + pad_x - c.rx) / s;
+    c.n_ty = c.ry < ksz ? (ksz - c.ry + s - 1) / s : 0;
+    c.n_tx = c.rx < ksz ? (ksz - c.rx + s - 1) / s : 0;
+    return c;
+  }
+  __device__ void tma_prefetch() const {
+    for (int i = 0; i < stride * stride; ++i) tma_prefetch_desc(&tm_dz[i]);
+    tma_prefetch_desc(&tm_w);
+  }
+  __device__ uint32_t stage_tx_bytes(int cls) const {
+    const Cls c = cls_of(cls);
+    return (uint32_t)(c.ny * c.nx * 128 + BN * 128);
+  }
+  __device__ void k_range(int cls, int& b, int& e) const {
+    const Cls c = cls_of(cls);
+    b = 0;
+    e = c.n_ty * c.n_tx * cchunks;
+  }
+  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int img, int ty_n, int cls, int kc) const {
+    const Cls c = cls_of(cls);
+    const int t = kc / cchunks, co0 = (kc - t * cchunks) * 64;
+    const int ty = t / c.n_tx, tx = t - ty * c.n_tx;
+    const int ky = c.ry + stride * ty, kx = c.rx + stride * tx;
+    tma_load_4d(stage_a, &tm_dz[cls], co0, c.ox0 - tx, c.oy0 - ty, img, bar);
+    tma_load_2d(stage_b, &tm_w, co0, (ky * ksz + kx) * Cin + ty_n * BN, bar);
+  }
+  __device__ void init_epilogue(ECtx&, float*, int) const {}
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int cls, int etid) const {
+    const Cls c = cls_of(cls);
+    const int img = m0 / kBM;
+    const bool valid = etid < c.ny * c.nx && img < n_img;
+    const int iyc = etid / (c.nx > 0 ? c.nx : 1), ixc = etid - iyc * c.nx;
+    const int64_t pix = valid ? ((int64_t)img * H + (c.iy_first + stride * iyc)) * W + (c.ix_first + stride * ixc) : 0;
+    store_rows_f32<BN>(tmem_lane_base, dx + pix * Cin, valid, n0, Cin);
   }
 };
 
