@@ -156,7 +156,7 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
   segs.count = 0;
   auto add_seg = [&](const float* src, float* dst, int64_t stride, int n, int parts) {
     Segment& sg = segs.s[segs.count++];
-    sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts;
+    sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts; sg.s2d_cout = 0;
   };
   float* dz = wsp(ws, w.dq);  // gradient w.r.t. the pre-activation output of layer l
   for (int l = p.n_layers - 1; l >= 0; --l) {

@@ -818,7 +818,17 @@ struct Segment {
   float* dst;
   int64_t stride;
   int n, parts;
+  // != 0: the partials are the weight gradient of the first convolution in 4x4 space-to-depth order
+  // [(by, bx, py, px, c)][s2d_cout]; dst is the HWIO kernel [(ky = 4 by + py, kx = 4 bx + px, c)][s2d_cout]
+  int s2d_cout;
 };
+// element i of a space-to-depth ordered conv0 kernel -> its index in the 8x8x4 HWIO kernel (cout % 4 == 0)
+__host__ __device__ inline int s2d_to_hwio(int i, int cout) {
+  const int kp = i / cout, co = i - kp * cout;
+  const int tap = kp >> 6, q = kp & 63;
+  const int by = tap >> 1, bx = tap & 1, py = q >> 4, px = (q >> 2) & 3, c = q & 3;
+  return (((4 * by + py) * 8 + 4 * bx + px) * 4 + c) * cout + co;
+}
 struct SegmentList {
   int count;
   int tile_start[kMaxSegments + 1];  // prefix sum of ceil(n / 32) over the segments (filled by finish_segments)
@@ -900,7 +910,7 @@ __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList 
       float tot = sm[0][e];
 #pragma unroll
       for (int k = 1; k < 8; ++k) tot += sm[k][e];
-      sg.dst[idx] = tot;
+      sg.dst[sg.s2d_cout ? s2d_to_hwio(idx, sg.s2d_cout) : idx] = tot;
     }
   }
 }

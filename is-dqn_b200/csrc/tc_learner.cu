@@ -49,6 +49,58 @@ u8_frames_to_bf16_kernel(const uint8_t* __restrict__ s0, const uint8_t* __restri
   }
 }
 
+// The first convolution (8x8, stride 4, SAME => 2 pixels of padding, 4 stacked frames) as an ordinary 64-channel
+// convolution: the frames are stored 4x4 space-to-depth with the padding folded in,
+//     dst[n][Y][X][(py*4 + px)*4 + c] = frame[n][4Y - 2 + py][4X - 2 + px][c]   (0 outside the frame),  Y, X in [0, H/4 + 1),
+// which turns conv0 into a 2x2, stride-1, unpadded convolution over (H/4+1) x (W/4+1) x 64: one tap is one 128-byte line
+// (TMA-able; 4 shared-memory wavefronts per LDGSTS instead of 12.7 for the 64-byte window rows of the raw layout).
+// One thread = one (Y, X, py): 16 input bytes -> 16 bf16.  Blocks >= frame_blocks re-order the conv0 kernel of the bf16
+// shadow to the matching K order, as [K'][Cout] (wp) and transposed [Cout][K'] (wt).
+__global__ void __launch_bounds__(256)
+u8_frames_to_s2d_kernel(const uint8_t* __restrict__ s0, const uint8_t* __restrict__ s1, bf16* __restrict__ dst, int n_each, int H,
+                        int W, int frame_blocks, const bf16* __restrict__ w_hwio, bf16* __restrict__ wp, bf16* __restrict__ wt,
+                        int cout) {
+  pdl_sync();
+  if ((int)blockIdx.x >= frame_blocks) {
+    const int n = 256 * cout;
+    for (int i = ((int)blockIdx.x - frame_blocks) * 256 + threadIdx.x; i < n; i += ((int)gridDim.x - frame_blocks) * 256) {
+      const bf16 v = w_hwio[s2d_to_hwio(i, cout)];
+      const int kp = i / cout, co = i - kp * cout;
+      wp[i] = v;
+      wt[co * 256 + kp] = v;
+    }
+    return;
+  }
+  const int GY = H / 4 + 1, GX = W / 4 + 1;
+  const int64_t total = (int64_t)2 * n_each * GY * GX * 4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)frame_blocks * 256) {
+    const int py = (int)(i & 3);
+    int64_t r = i >> 2;
+    const int X = (int)(r % GX);
+    r /= GX;
+    const int Y = (int)(r % GY);
+    const int n = (int)(r / GY);
+    const int iy = 4 * Y - 2 + py, x0 = 4 * X - 2;
+    const uint8_t* img = n < n_each ? s0 + (int64_t)n * H * W * 4 : s1 + (int64_t)(n - n_each) * H * W * 4;
+    uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+    if ((unsigned)iy < (unsigned)H) {
+      const uint8_t* p = img + ((int64_t)iy * W + x0) * 4;
+      if (x0 >= 0) lo = __ldg(reinterpret_cast<const uint2*>(p));
+      if (x0 + 3 < W) hi = __ldg(reinterpret_cast<const uint2*>(p + 8));
+    }
+    const uint32_t w[4] = {lo.x, lo.y, hi.x, hi.y};
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      o[2 * q] = tc::int_pair_bf16(w[q] & 0xff, (w[q] >> 8) & 0xff);
+      o[2 * q + 1] = tc::int_pair_bf16((w[q] >> 16) & 0xff, w[q] >> 24);
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst + (((int64_t)n * GY + Y) * GX + X) * 64 + py * 16);
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
 }  // namespace isdqn
 
 namespace {
@@ -203,7 +255,9 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
 struct TcWorkspace {
   int64_t act16[ISDQN_MAX_FEATURES + 1];  // byte offsets; bf16 [rows*pix][out_dim] for every non-final layer
   int64_t dz16[ISDQN_MAX_FEATURES + 1];   // bf16 [B*pix][out_dim] gradient w.r.t. the pre-activation of every non-final layer
-  int64_t x16;                            // bf16 [2B][H][W][4] integer-valued copy of the uint8 frames (or -1)
+  int64_t x16;                            // bf16 [2B][H][W][4] integer-valued copy of the uint8 frames (or -1); with
+                                          // frames_s2d: [2B][H/4+1][W/4+1][64] (4x4 space-to-depth, padding folded in)
+  int64_t w0p, w0t;                       // frames_s2d: conv0 kernel in space-to-depth K order [256][Cout] / [Cout][256]
   int64_t total;                          // bytes
 };
 
@@ -212,6 +266,26 @@ struct TcWorkspace {
 bool frames_as_bf16(const Layer& L) {
   return L.type == 0 && L.Cin == 4 && L.pad_x % 2 == 0 && L.W % 2 == 0 && L.ksz % 2 == 0 && L.stride % 2 == 0 &&
          ((int64_t)L.H * L.W * L.Cin) % 16 == 0;
+}
+
+// conv0 = 8x8 / stride 4 / padding 2 over 4 stacked frames: stored 4x4 space-to-depth it is a 2x2 stride-1 convolution over
+// 64 channels (u8_frames_to_s2d_kernel).  Taken when the TMA path is available.
+EncodeTiledFn tensor_map_encoder();
+bool frames_s2d(const Layer& L) {
+  return tensor_map_encoder() != nullptr && L.type == 0 && L.Cin == 4 && L.ksz == 8 && L.stride == 4 && L.pad_y == 2 &&
+         L.pad_x == 2 && L.H % 4 == 0 && L.W % 4 == 0 && L.OH == L.H / 4 && L.OW == L.W / 4 && L.OW <= tc::kBM &&
+         (L.out_dim == 32 || L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256);
+}
+// the same layer as the engine sees it on the space-to-depth image
+Layer s2d_layer(const Layer& L) {
+  Layer S = L;
+  S.H = L.H / 4 + 1;
+  S.W = L.W / 4 + 1;
+  S.Cin = 64;
+  S.ksz = 2;
+  S.stride = 1;
+  S.pad_y = S.pad_x = 0;
+  return S;
 }
 
 void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
@@ -225,7 +299,13 @@ void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
     const Layer& L = p.L[l];
     w->act16[l] = l + 1 < p.n_layers ? take((int64_t)rows * L.pix * L.out_dim * 2) : -1;
   }
-  w->x16 = frames_as_bf16(p.L[0]) ? take((int64_t)rows * p.L[0].H * p.L[0].W * p.L[0].Cin * 2) : -1;
+  w->x16 = (!frames_s2d(p.L[0]) && frames_as_bf16(p.L[0])) ? take((int64_t)rows * p.L[0].H * p.L[0].W * p.L[0].Cin * 2) : -1;
+  w->w0p = w->w0t = -1;
+  if (frames_s2d(p.L[0])) {
+    w->x16 = take((int64_t)rows * (p.L[0].H / 4 + 1) * (p.L[0].W / 4 + 1) * 64 * 2);
+    w->w0p = take((int64_t)256 * p.L[0].out_dim * 2);
+    w->w0t = take((int64_t)256 * p.L[0].out_dim * 2);
+  }
   // one buffer per layer (not a ping-pong): the weight gradient of layer l runs on the side stream while the main
   // stream is already producing the gradients of the layers below it
   for (int l = 0; l < p.n_layers; ++l) {
@@ -288,42 +368,52 @@ int launch_conv_fwd_tc(const Layer& L, const void* in0, const void* in1, int n0,
 
 // ---- TMA-fed forward convolution (stride 1, Cin % 64 == 0, one image = one M tile) -----------------------------------
 bool conv_fwd_tma_ok(const Layer& L) {
-  return tensor_map_encoder() != nullptr && L.type == 0 && L.stride == 1 && L.Cin % 64 == 0 && L.OH == L.H && L.OW == L.W &&
-         L.pix <= tc::kBM && L.W <= 256 && L.H <= 256 && (L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256);
+  return tensor_map_encoder() != nullptr && L.type == 0 && L.stride == 1 && L.Cin % 64 == 0 && L.OW <= tc::kBM && L.W <= 256 &&
+         L.H <= 256 && (L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256);
 }
 
-int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w, const float* params, bf16* out, float* xhat,
-                        float* rstd, int m_train, cudaStream_t s) {
+// w: [K][Cout] (MN-major B), or — BN = 32 — the transposed kernel wt [Cout][K] (K-major B)
+int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w, const bf16* wt, const float* params, bf16* out,
+                        float* xhat, float* rstd, int m_train, float in_scale, cudaStream_t s) {
   EncodeTiledFn enc = tensor_map_encoder();
   CUtensorMap tm_x, tm_w;
+  int th = tc::kBM / L.OW;  // whole output rows per M tile
+  if (th > L.OH) th = L.OH;
+  const int tpi = ceil_div(L.OH, th);
   {
     const cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)n_img};
     const cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)L.W * L.Cin * 2, (cuuint64_t)L.H * L.W * L.Cin * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)L.OW, (cuuint32_t)L.OH, 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)L.OW, (cuuint32_t)th, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ISDQN_E_CUDA;
   }
-  if (encode_matrix_map(&tm_w, w, L.out_dim, L.in_dim, L.out_dim, 64, 64)) return ISDQN_E_CUDA;
-#define ISDQN_CONV_FWD_TMA_W(BN, WIDE)                                                                 \
+  const bool kmajor_b = L.out_dim == 32;
+  if (kmajor_b ? encode_matrix_map(&tm_w, wt, L.in_dim, L.out_dim, L.in_dim, 64, 32)
+               : encode_matrix_map(&tm_w, w, L.out_dim, L.in_dim, L.out_dim, 64, 64))
+    return ISDQN_E_CUDA;
+  const int n_tiles = n_img * tpi;
+#define ISDQN_CONV_FWD_TMA_W(BN, WIDE, KB)                                                             \
   {                                                                                                    \
-    tc::ConvFwdTmaTC<BN, WIDE> p;                                                                      \
-    p.tm_x = tm_x; p.tm_w = tm_w; p.n_img = n_img; p.pix = L.pix; p.ksz = L.ksz;                       \
+    tc::ConvFwdTmaTC<BN, WIDE, KB> p;                                                                  \
+    p.tm_x = tm_x; p.tm_w = tm_w; p.n_img = n_img; p.pix = L.pix; p.OW = L.OW; p.OH = L.OH;            \
+    p.th = th; p.tpi = tpi; p.ksz = L.ksz;                                                             \
     p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.cchunks = L.Cin / 64;                                      \
     p.bias = params + L.b_off;                                                                         \
     p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
     p.ln_b = L.has_ln ? params + L.beta_off : nullptr;                                                 \
     p.relu = L.relu; p.out = out; p.xhat = xhat; p.rstd = rstd; p.m_train = m_train;                   \
-    p.acc_scale = 1.0f;                                                                                \
-    return launch_tc(p, n_img, 1, 1, s, "tc_conv_fwd_tma");                                            \
+    p.acc_scale = in_scale;                                                                            \
+    return launch_tc(p, n_tiles, 1, 1, s, "tc_conv_fwd_tma");                                          \
   }
-#define ISDQN_CONV_FWD_TMA(BN)                                                                         \
-  if (wide_launch(n_img)) ISDQN_CONV_FWD_TMA_W(BN, true) else ISDQN_CONV_FWD_TMA_W(BN, false)
+#define ISDQN_CONV_FWD_TMA(BN, KB)                                                                     \
+  if (wide_launch(n_tiles)) ISDQN_CONV_FWD_TMA_W(BN, true, KB) else ISDQN_CONV_FWD_TMA_W(BN, false, KB)
   switch (L.out_dim) {
-    case 64: ISDQN_CONV_FWD_TMA(64)
-    case 128: ISDQN_CONV_FWD_TMA(128)
-    case 256: ISDQN_CONV_FWD_TMA(256)
+    case 32: ISDQN_CONV_FWD_TMA(32, true)
+    case 64: ISDQN_CONV_FWD_TMA(64, false)
+    case 128: ISDQN_CONV_FWD_TMA(128, false)
+    case 256: ISDQN_CONV_FWD_TMA(256, false)
     default: return ISDQN_E_UNSUPPORTED;
   }
 #undef ISDQN_CONV_FWD_TMA_W
@@ -497,7 +587,18 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     float* xhat = rows_train > 0 ? wsp(ws, w.xhat[l]) : nullptr;
     float* rstd = rows_train > 0 ? wsp(ws, w.rstd[l]) : nullptr;
     if (L.type == 0) {
-      if (l == 0 && t.x16 >= 0) {
+      if (l == 0 && t.w0p >= 0) {  // space-to-depth frames: conv0 is a TMA-fed 2x2 convolution over 64 channels
+        const Layer S = s2d_layer(L);
+        const int64_t threads = (int64_t)rows * S.H * S.W * 4;
+        int64_t fb = ceil_div<int64_t>(threads, 256);
+        if (fb > kNumSMs * 16) fb = kNumSMs * 16;
+        ISDQN_PROF(s, "frames_to_bf16");
+        ISDQN_CUDA_CHECK(launch_pdl(u8_frames_to_s2d_kernel, dim3((unsigned)fb + 8), dim3(256), 0, s,
+                                    reinterpret_cast<const uint8_t*>(b->d_state), reinterpret_cast<const uint8_t*>(b->d_next_state),
+                                    w16(wt, t.x16), B, L.H, L.W, (int)fb, shadow + L.w_off, w16(wt, t.w0p), w16(wt, t.w0t), L.out_dim));
+        rc = launch_conv_fwd_tma(S, w16(wt, t.x16), rows, w16(wt, t.w0p), w16(wt, t.w0t), params, w16(wt, t.act16[l]), xhat, rstd,
+                                 rows_train * L.pix, 1.0f / 255.0f, s);
+      } else if (l == 0 && t.x16 >= 0) {
         const int64_t n16 = (int64_t)B * L.H * L.W * L.Cin / 16;
         int64_t grid = ceil_div<int64_t>(2 * n16, 256);
         if (grid > kNumSMs * 8) grid = kNumSMs * 8;
@@ -515,8 +616,8 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         rc = launch_conv_fwd_tc<true>(L, b->d_state, b->d_next_state, B, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
                                       xhat, rstd, rows_train * L.pix, s);
       else if (conv_fwd_tma_ok(L))
-        rc = launch_conv_fwd_tma(L, w16(wt, t.act16[l - 1]), rows, shadow + L.w_off, params, w16(wt, t.act16[l]), xhat, rstd,
-                                 rows_train * L.pix, s);
+        rc = launch_conv_fwd_tma(L, w16(wt, t.act16[l - 1]), rows, shadow + L.w_off, nullptr, params, w16(wt, t.act16[l]), xhat,
+                                 rstd, rows_train * L.pix, 1.0f, s);
       else
         rc = launch_conv_fwd_tc<false>(L, w16(wt, t.act16[l - 1]), nullptr, rows, rows, shadow + L.w_off, params,
                                        w16(wt, t.act16[l]), xhat, rstd, rows_train * L.pix, s);
@@ -577,7 +678,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   segs.count = 0;
   auto add_seg = [&](const float* src, float* dst, int64_t stride, int n, int parts) {
     Segment& sg = segs.s[segs.count++];
-    sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts;
+    sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts; sg.s2d_cout = 0;
   };
   float* dz32 = wsp(ws, w.dq);
   // Two streams: the chain  input gradient -> LayerNorm/ReLU backward -> input gradient ...  is the critical path; the
@@ -674,7 +775,10 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     } else {
       int real_splits = 1;
       float* part = wsp(ws, w.wpart[l]);
-      if (l == 0 && t.x16 >= 0 && L.ksz * L.Cin == 32)
+      if (l == 0 && t.w0p >= 0) {  // gather from the space-to-depth frames (128-byte taps); partials come out in s2d K order
+        rc = launch_conv_wgrad_tc<false>(s2d_layer(L), w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw,
+                                         1.0f / 255.0f, side ? side_cap : 0);
+      } else if (l == 0 && t.x16 >= 0 && L.ksz * L.Cin == 32)
         rc = launch_conv_wgrad_tc<false, true>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw,
                                                1.0f / 255.0f, side ? side_cap : 0);
       else if (l == 0 && t.x16 >= 0)
@@ -685,6 +789,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw, 1.0f,
                                          side ? side_cap : 0);
       add_seg(part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
+      if (l == 0 && t.w0p >= 0) segs.s[segs.count - 1].s2d_cout = L.out_dim;
     }
     if (rc) return rc;
     if (L.relu) {

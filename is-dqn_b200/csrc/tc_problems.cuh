@@ -459,22 +459,24 @@ struct ConvFwdTC {
 };
 
 // ------------------------------------------------------------------------------- conv forward, TMA-fed (stride 1)
-// Same contraction and epilogue as ConvFwdTC, but no gather code: one M tile = ONE image (OH*OW <= 128 output pixels,
-// the remaining accumulator rows are computed on stale shared memory and never stored); per 64-deep K chunk — one tap
-// (ky, kx) x 64 input channels — a single 4-D tensor-map copy of the box {64 channels, OW, OH, 1 image} starting at
-// (c0, kx - pad, ky - pad, image) brings the whole A stage: rows land at 128-byte pitch with the hardware 128-byte
-// swizzle (= kmajor_off<true>), pixels outside the image are zero-filled by the TMA unit.  The weight chunk (64 K rows x
-// BN output channels) is BN/64 2-D copies in the MN-major swizzled layout.  Nothing goes through the LSU.
-template <int BN_, bool WIDE_ = false>
+// Same contraction and epilogue as ConvFwdTC, but no gather code: one M tile = `th` whole output rows of ONE image
+// (th * OW <= 128 output pixels; accumulator rows beyond that are computed on stale shared memory and never stored); per
+// 64-deep K chunk — one tap (ky, kx) x 64 input channels — a single 4-D tensor-map copy of the box {64 channels, OW, th,
+// 1 image} starting at (c0, kx - pad, y0 + ky - pad, image) brings the whole A stage: rows land at 128-byte pitch with the
+// hardware 128-byte swizzle (= kmajor_off<true>), pixels outside the image are zero-filled by the TMA unit.  The weight
+// chunk is BN/64 2-D copies in the MN-major swizzled layout, or (B_KMAJOR_, for BN = 32: narrower than a swizzle atom
+// the other way round) one copy of a TRANSPOSED weight matrix [Cout][K] in the K-major layout.  Nothing goes through the
+// LSU.
+template <int BN_, bool WIDE_ = false, bool B_KMAJOR_ = false>
 struct ConvFwdTmaTC {
   static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
   static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 3 * BN_;
-  static constexpr bool A_MN = false, B_MN = true, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
-  static_assert(BN_ % 64 == 0, "the weight stage is filled in 64-column swizzle groups");
-  CUtensorMap tm_x;  // activations [N][H][W][Cin] bf16, box {64, OW, OH, 1}, SWIZZLE_128B
-  CUtensorMap tm_w;  // weights [K][Cout] bf16, box {64, 64}, SWIZZLE_128B
-  int n_img, pix, ksz, pad_y, pad_x, cchunks;  // cchunks = Cin / 64
+  static constexpr bool A_MN = false, B_MN = !B_KMAJOR_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  static_assert(B_KMAJOR_ || BN_ % 64 == 0, "the MN-major weight stage is filled in 64-column swizzle groups");
+  CUtensorMap tm_x;  // activations [N][H][W][Cin] bf16, box {64, OW, th, 1}, SWIZZLE_128B
+  CUtensorMap tm_w;  // weights [K][Cout] bf16, box {64, 64} — or transposed [Cout][K], box {64, BN}
+  int n_img, pix, OW, OH, th, tpi, ksz, pad_y, pad_x, cchunks;  // tpi = tiles per image, cchunks = Cin / 64
   const float* bias; const float* ln_g; const float* ln_b; int relu;
   bf16* out; float* xhat; float* rstd; int m_train;
   float acc_scale;
@@ -486,14 +488,19 @@ struct ConvFwdTmaTC {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
   }
-  __device__ uint32_t stage_tx_bytes(int) const { return (uint32_t)(pix * 128 + BN * 128); }
+  __device__ uint32_t stage_tx_bytes(int) const { return (uint32_t)(th * OW * 128 + BN * 128); }
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = ksz * ksz * cchunks; }
-  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int img, int, int, int kc) const {
+  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int tile, int, int, int kc) const {
+    const int img = tile / tpi, y0 = (tile - img * tpi) * th;
     const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * 64;
     const int ky = tap / ksz, kx = tap - ky * ksz;
-    tma_load_4d(stage_a, &tm_x, c0, kx - pad_x, ky - pad_y, img, bar);
+    tma_load_4d(stage_a, &tm_x, c0, kx - pad_x, y0 + ky - pad_y, img, bar);
+    if (B_KMAJOR_) {
+      tma_load_2d(stage_b, &tm_w, kc * 64, 0, bar);
+    } else {
 #pragma unroll
-    for (int g = 0; g < BN / 64; ++g) tma_load_2d(stage_b + g * 8192, &tm_w, g * 64, kc * 64, bar);
+      for (int g = 0; g < BN / 64; ++g) tma_load_2d(stage_b + g * 8192, &tm_w, g * 64, kc * 64, bar);
+    }
   }
   __device__ void init_epilogue(ECtx& e, float* ep_sm, int etid) const {
     for (int i = etid; i < BN; i += kThreads) {
@@ -505,11 +512,13 @@ struct ConvFwdTmaTC {
   }
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
   __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
-    const int img = m0 / kBM;  // (the engine numbers tiles in units of 128 rows; here tile = image)
+    const int tile = m0 / kBM;  // (the engine numbers tiles in units of 128 rows)
+    const int img = tile / tpi, y0 = (tile - img * tpi) * th;
+    const int r = etid / OW, ox = etid - r * OW, oy = y0 + r;
     ConvEpilogueArgs e;
     e.prm = ec.prm; e.ln_g = ln_g != nullptr; e.relu = relu; e.out = out; e.xhat = xhat; e.rstd = rstd; e.m_train = m_train;
     e.acc_scale = acc_scale;
-    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, (int64_t)img * pix + etid, etid < pix && img < n_img);
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, (int64_t)img * pix + oy * OW + ox, r < th && oy < OH && img < n_img);
   }
 };
 
