@@ -291,12 +291,15 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
         const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
         int kb, ke;
         p.k_range(tz, kb, ke);
+        typename P::PCtx ctx;
+        p.tma_tile(ctx, tx, ty, tz);  // per-tile coordinates, computed once (this thread is the whole producer)
+        const uint32_t tx_bytes = p.stage_tx_bytes(ctx);
         for (int kc = kb; kc < ke; ++kc, ++j) {
           const int s = j % STAGES;
           mbar_wait(&empty_bar[s], (uint32_t)(((j / STAGES) & 1) ^ 1));
           if (j == 0) trace_mark(2);
-          mbar_arrive_expect_tx(&full_bar[s], p.stage_tx_bytes(tz));
-          p.tma_load(sA + s * kABytes, sB + s * B_BYTES, &full_bar[s], tx, ty, tz, kc);
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          p.tma_load(ctx, sA + s * kABytes, sB + s * B_BYTES, &full_bar[s], kc);
         }
       }
     }

@@ -379,7 +379,14 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
   CUtensorMap tm_x, tm_w;
   int th = tc::kBM / L.OW;  // whole output rows per M tile
   if (th > L.OH) th = L.OH;
-  const int tpi = ceil_div(L.OH, th);
+  int tpi = ceil_div(L.OH, th);
+  // few images (batch 32): more, shorter tiles so that the launch covers the SMs — the K loop of one CTA is bound by the
+  // shared-memory fill rate of ONE SM, so halving the rows of a tile halves its latency
+  while (n_img * tpi < 96 && th > 1) {
+    ++tpi;
+    th = ceil_div(L.OH, tpi);
+  }
+  tpi = ceil_div(L.OH, th);
   {
     const cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)n_img};
     const cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)L.W * L.Cin * 2, (cuuint64_t)L.H * L.W * L.Cin * 2};

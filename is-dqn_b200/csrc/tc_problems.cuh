@@ -170,20 +170,26 @@ struct GemmTmaTC {
   CUtensorMap tm_b;  // B K-major: dims {K, N}, box {64, BN};   B MN-major: dims {N, K}, box {64, 64}
   float* C; int64_t ldc; int64_t split_stride;
   int M, N, K, chunks_per_split;
-  struct PCtx {};
+  struct PCtx {
+    int m0, n0;
+  };
   struct ECtx {};
   __device__ void tma_prefetch() const {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
   }
-  __device__ uint32_t stage_tx_bytes(int) const { return (uint32_t)(kABytes + BN * 128); }
+  __device__ void tma_tile(PCtx& c, int tx, int ty, int) const {
+    c.m0 = tx * kBM;
+    c.n0 = ty * BN;
+  }
+  __device__ uint32_t stage_tx_bytes(const PCtx&) const { return (uint32_t)(kABytes + BN * 128); }
   __device__ void k_range(int split, int& b, int& e) const {
     const int total = (K + kBK - 1) / kBK;
     b = split * chunks_per_split;
     e = min(total, b + chunks_per_split);
   }
-  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int tx, int ty, int, int kc) const {
-    const int m0 = tx * kBM, n0 = ty * BN, k0 = kc * kBK;
+  __device__ void tma_load(const PCtx& c, uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int kc) const {
+    const int m0 = c.m0, n0 = c.n0, k0 = kc * kBK;
     if (A_MN) {
       tma_load_2d(stage_a, &tm_a, m0, k0, bar);
       tma_load_2d(stage_a + 8192, &tm_a, m0 + 64, k0, bar);
@@ -480,7 +486,10 @@ struct ConvFwdTmaTC {
   const float* bias; const float* ln_g; const float* ln_b; int relu;
   bf16* out; float* xhat; float* rstd; int m_train;
   float acc_scale;
-  struct PCtx {};
+  struct PCtx {
+    int img, y0;         // tile
+    int ky, kx, cc;      // running tap / channel-chunk counters (chunks are visited in order)
+  };
   struct ECtx {
     const float* prm;
   };
@@ -488,13 +497,22 @@ struct ConvFwdTmaTC {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
   }
-  __device__ uint32_t stage_tx_bytes(int) const { return (uint32_t)(th * OW * 128 + BN * 128); }
+  __device__ void tma_tile(PCtx& c, int tile, int, int) const {
+    c.img = tile / tpi;
+    c.y0 = (tile - c.img * tpi) * th - pad_y;
+    c.ky = c.kx = c.cc = 0;
+  }
+  __device__ uint32_t stage_tx_bytes(const PCtx&) const { return (uint32_t)(th * OW * 128 + BN * 128); }
   __device__ void k_range(int, int& b, int& e) const { b = 0; e = ksz * ksz * cchunks; }
-  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int tile, int, int, int kc) const {
-    const int img = tile / tpi, y0 = (tile - img * tpi) * th;
-    const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * 64;
-    const int ky = tap / ksz, kx = tap - ky * ksz;
-    tma_load_4d(stage_a, &tm_x, c0, kx - pad_x, y0 + ky - pad_y, img, bar);
+  __device__ void tma_load(PCtx& c, uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int kc) const {
+    tma_load_4d(stage_a, &tm_x, c.cc * 64, c.kx - pad_x, c.y0 + c.ky, c.img, bar);
+    if (++c.cc == cchunks) {  // next chunk: next 64 channels, then next tap (kx fastest) — no divisions in the loop
+      c.cc = 0;
+      if (++c.kx == ksz) {
+        c.kx = 0;
+        ++c.ky;
+      }
+    }
     if (B_KMAJOR_) {
       tma_load_2d(stage_b, &tm_w, kc * 64, 0, bar);
     } else {
@@ -753,11 +771,15 @@ struct ConvDgradTmaTC {
   CUtensorMap tm_w;      // weights as [ksz*ksz*Cin rows][Cout], box {64, BN}
   int H, W, Cin, Cout, ksz, stride, pad_y, pad_x, n_img, cchunks;  // cchunks = Cout / 64
   float* dx;             // [n_img*H*W][Cin]
-  struct PCtx {};
-  struct ECtx {};
   struct Cls {
     int ry, rx, iy_first, ix_first, ny, nx, oy0, ox0, n_ty, n_tx;
   };
+  struct PCtx {
+    Cls c;
+    int img, n0, cls;
+    int ty, tx, cc;  // running counters over (tap row, tap column, 64-channel chunk)
+  };
+  struct ECtx {};
   __device__ Cls cls_of(int cls) const {
     Cls c;
     const int s = stride;
@@ -777,22 +799,30 @@ struct ConvDgradTmaTC {
     for (int i = 0; i < stride * stride; ++i) tma_prefetch_desc(&tm_dz[i]);
     tma_prefetch_desc(&tm_w);
   }
-  __device__ uint32_t stage_tx_bytes(int cls) const {
-    const Cls c = cls_of(cls);
-    return (uint32_t)(c.ny * c.nx * 128 + BN * 128);
+  __device__ void tma_tile(PCtx& p, int img, int ty_n, int cls) const {
+    p.c = cls_of(cls);
+    p.img = img;
+    p.n0 = ty_n * BN;
+    p.cls = cls;
+    p.ty = p.tx = p.cc = 0;
   }
+  __device__ uint32_t stage_tx_bytes(const PCtx& p) const { return (uint32_t)(p.c.ny * p.c.nx * 128 + BN * 128); }
   __device__ void k_range(int cls, int& b, int& e) const {
     const Cls c = cls_of(cls);
     b = 0;
     e = c.n_ty * c.n_tx * cchunks;
   }
-  __device__ void tma_load(uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int img, int ty_n, int cls, int kc) const {
-    const Cls c = cls_of(cls);
-    const int t = kc / cchunks, co0 = (kc - t * cchunks) * 64;
-    const int ty = t / c.n_tx, tx = t - ty * c.n_tx;
-    const int ky = c.ry + stride * ty, kx = c.rx + stride * tx;
-    tma_load_4d(stage_a, &tm_dz[cls], co0, c.ox0 - tx, c.oy0 - ty, img, bar);
-    tma_load_2d(stage_b, &tm_w, co0, (ky * ksz + kx) * Cin + ty_n * BN, bar);
+  __device__ void tma_load(PCtx& p, uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int) const {
+    const int ky = p.c.ry + stride * p.ty, kx = p.c.rx + stride * p.tx, co0 = p.cc * 64;
+    tma_load_4d(stage_a, &tm_dz[p.cls], co0, p.c.ox0 - p.tx, p.c.oy0 - p.ty, p.img, bar);
+    tma_load_2d(stage_b, &tm_w, co0, (ky * ksz + kx) * Cin + p.n0, bar);
+    if (++p.cc == cchunks) {
+      p.cc = 0;
+      if (++p.tx == p.c.n_tx) {
+        p.tx = 0;
+        ++p.ty;
+      }
+    }
   }
   __device__ void init_epilogue(ECtx&, float*, int) const {}
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
