@@ -258,6 +258,8 @@ struct TcWorkspace {
   int64_t x16;                            // bf16 [2B][H][W][4] integer-valued copy of the uint8 frames (or -1); with
                                           // frames_s2d: [2B][H/4+1][W/4+1][64] (4x4 space-to-depth, padding folded in)
   int64_t w0p, w0t;                       // frames_s2d: conv0 kernel in space-to-depth K order [256][Cout] / [Cout][256]
+  bool pair_view;                         // act16[0] is stored [rows][OH][OW + 1][C] with a zero column on the left, so that the
+                                          // second convolution reads it as [rows][OH][(OW + 1) / 2][2C] through TMA
   int64_t total;                          // bytes
 };
 
@@ -288,6 +290,20 @@ Layer s2d_layer(const Layer& L) {
   return S;
 }
 
+// Second convolution (4x4, stride 2, SAME => 1 pixel of padding left/top) read through TMA: with its input stored with one
+// zero column on the left, two horizontally adjacent pixels are one 2C-channel pixel of a view with half the width; the
+// window columns 2ox-1 .. 2ox+2 are the view pixels ox, ox+1 (column stride 1, 2 taps), rows keep stride 2 (traversal
+// stride of the tensor map).  The K order (ky, kx, c) is unchanged, so the weights are used as they are.  Needs conv0 on the
+// space-to-depth TMA path (its epilogue writes the padded layout) with LayerNorm (nothing else reads act16[0] flat).
+bool conv1_pair_view(const Plan& p) {
+  if (p.n_layers < 2) return false;
+  const Layer& A = p.L[0];
+  const Layer& L = p.L[1];
+  return frames_s2d(A) && A.has_ln && L.type == 0 && L.ksz == 4 && L.stride == 2 && L.pad_y == 1 && L.pad_x == 1 &&
+         (L.Cin == 32 || L.Cin == 64 || L.Cin == 128) && (L.W + 1) % 2 == 0 && L.OW == (L.W + 1) / 2 && L.OW <= tc::kBM &&
+         (L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256);
+}
+
 void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
@@ -295,9 +311,11 @@ void carve_tc(const Plan& p, int rows, int B, TcWorkspace* w) {
     off = (off + bytes + 255) & ~(int64_t)255;
     return o;
   };
+  w->pair_view = conv1_pair_view(p);
   for (int l = 0; l < p.n_layers; ++l) {
     const Layer& L = p.L[l];
-    w->act16[l] = l + 1 < p.n_layers ? take((int64_t)rows * L.pix * L.out_dim * 2) : -1;
+    const int64_t pix = (l == 0 && w->pair_view) ? (int64_t)L.OH * (L.OW + 1) : L.pix;
+    w->act16[l] = l + 1 < p.n_layers ? take((int64_t)rows * pix * L.out_dim * 2) : -1;
   }
   w->x16 = (!frames_s2d(p.L[0]) && frames_as_bf16(p.L[0])) ? take((int64_t)rows * p.L[0].H * p.L[0].W * p.L[0].Cin * 2) : -1;
   w->w0p = w->w0t = -1;
@@ -373,8 +391,12 @@ bool conv_fwd_tma_ok(const Layer& L) {
 }
 
 // w: [K][Cout] (MN-major B), or — BN = 32 — the transposed kernel wt [Cout][K] (K-major B)
+// `L` describes the convolution on the VIEW the tensor map is built over (H, W, Cin, taps ksz x ksz_x, row stride sy,
+// column stride 1); ksz_x = 0 means a square stride-1 kernel.  out_pitch: see ConvFwdTmaTC.
 int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w, const bf16* wt, const float* params, bf16* out,
-                        float* xhat, float* rstd, int m_train, float in_scale, cudaStream_t s) {
+                        float* xhat, float* rstd, int m_train, float in_scale, cudaStream_t s, int ksz_x = 0, int sy = 1,
+                        int out_pitch = 0) {
+  if (ksz_x == 0) ksz_x = L.ksz;
   EncodeTiledFn enc = tensor_map_encoder();
   CUtensorMap tm_x, tm_w;
   int th = tc::kBM / L.OW;  // whole output rows per M tile
@@ -390,8 +412,9 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
   {
     const cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)n_img};
     const cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)L.W * L.Cin * 2, (cuuint64_t)L.H * L.W * L.Cin * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)L.OW, (cuuint32_t)th, 1};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
+    // (traversal stride sy along H: the box spans sy*(th-1)+1 rows of which every sy-th is copied)
+    const cuuint32_t box[4] = {64, (cuuint32_t)L.OW, (cuuint32_t)(sy * (th - 1) + 1), 1};
+    const cuuint32_t es[4] = {1, 1, (cuuint32_t)sy, 1};
     if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ISDQN_E_CUDA;
@@ -405,7 +428,7 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
   {                                                                                                    \
     tc::ConvFwdTmaTC<BN, WIDE, KB> p;                                                                  \
     p.tm_x = tm_x; p.tm_w = tm_w; p.n_img = n_img; p.pix = L.pix; p.OW = L.OW; p.OH = L.OH;            \
-    p.th = th; p.tpi = tpi; p.ksz = L.ksz;                                                             \
+    p.th = th; p.tpi = tpi; p.ksz_y = L.ksz; p.ksz_x = ksz_x; p.sy = sy; p.out_pitch = out_pitch;      \
     p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.cchunks = L.Cin / 64;                                      \
     p.bias = params + L.b_off;                                                                         \
     p.ln_g = L.has_ln ? params + L.g_off : nullptr;                                                    \
@@ -604,7 +627,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
                                     reinterpret_cast<const uint8_t*>(b->d_state), reinterpret_cast<const uint8_t*>(b->d_next_state),
                                     w16(wt, t.x16), B, L.H, L.W, (int)fb, shadow + L.w_off, w16(wt, t.w0p), w16(wt, t.w0t), L.out_dim));
         rc = launch_conv_fwd_tma(S, w16(wt, t.x16), rows, w16(wt, t.w0p), w16(wt, t.w0t), params, w16(wt, t.act16[l]), xhat, rstd,
-                                 rows_train * L.pix, 1.0f / 255.0f, s);
+                                 rows_train * L.pix, 1.0f / 255.0f, s, 0, 1, t.pair_view ? L.OW + 1 : 0);
       } else if (l == 0 && t.x16 >= 0) {
         const int64_t n16 = (int64_t)B * L.H * L.W * L.Cin / 16;
         int64_t grid = ceil_div<int64_t>(2 * n16, 256);
@@ -622,7 +645,14 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       } else if (l == 0)
         rc = launch_conv_fwd_tc<true>(L, b->d_state, b->d_next_state, B, rows, shadow + L.w_off, params, w16(wt, t.act16[l]),
                                       xhat, rstd, rows_train * L.pix, s);
-      else if (conv_fwd_tma_ok(L))
+      else if (l == 1 && t.pair_view) {
+        Layer V = L;  // the view: half the width, twice the channels, 4 x 2 taps, row stride 2, no left padding
+        V.W = (L.W + 1) / 2;
+        V.Cin = 2 * L.Cin;
+        V.pad_x = 0;
+        rc = launch_conv_fwd_tma(V, w16(wt, t.act16[l - 1]), rows, shadow + L.w_off, nullptr, params, w16(wt, t.act16[l]), xhat,
+                                 rstd, rows_train * L.pix, 1.0f, s, /*ksz_x=*/2, /*sy=*/2);
+      } else if (conv_fwd_tma_ok(L))
         rc = launch_conv_fwd_tma(L, w16(wt, t.act16[l - 1]), rows, shadow + L.w_off, nullptr, params, w16(wt, t.act16[l]), xhat,
                                  rstd, rows_train * L.pix, 1.0f, s);
       else
@@ -792,7 +822,13 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw, 1.0f / 255.0f,
                                          side ? side_cap : 0);
       else if (l == 0) rc = launch_conv_wgrad_tc<true>(L, b->d_state, dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw);
-      else
+      else if (l == 1 && t.pair_view) {
+        Layer G = L;  // the same pixels at stored column x + 1: one more column, no left padding
+        G.W = L.W + 1;
+        G.pad_x = L.pad_x - 1;
+        rc = launch_conv_wgrad_tc<false>(G, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw, 1.0f,
+                                         side ? side_cap : 0);
+      } else
         rc = launch_conv_wgrad_tc<false>(L, w16(wt, t.act16[l - 1]), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw, 1.0f,
                                          side ? side_cap : 0);
       add_seg(part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);

@@ -299,8 +299,11 @@ struct ConvEpilogueArgs {
   bf16* out; float* xhat; float* rstd; int m_train;
   float acc_scale;
 };
+// m_out: row index of the bf16 activation (differs from m when the activation is stored with a padded row pitch);
+// zero_left: also write a zero pixel at m_out - 1 (the left padding column of that layout)
 template <int BN>
-__device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e, uint32_t tmem_lane_base, int64_t m, bool valid) {
+__device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e, uint32_t tmem_lane_base, int64_t m, bool valid,
+                                                      int64_t m_out, bool zero_left) {
     const float4* pb = reinterpret_cast<const float4*>(e.prm);
     const float4* pg = reinterpret_cast<const float4*>(e.prm + BN);
     const float4* pbeta = reinterpret_cast<const float4*>(e.prm + 2 * BN);
@@ -351,9 +354,13 @@ __device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e,
         packed[2 * q + 1] = pack_bf16(y[2], y[3]);
       }
       if (valid) {
-        uint4* o = reinterpret_cast<uint4*>(e.out + (int64_t)m * BN + cb * 32);
+        uint4* o = reinterpret_cast<uint4*>(e.out + m_out * BN + cb * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        if (zero_left) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) (o - BN / 8)[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
       if (save) {
         float4* x = reinterpret_cast<float4*>(e.xhat + (int64_t)m * BN + cb * 32);
@@ -460,7 +467,7 @@ struct ConvFwdTC {
     ConvEpilogueArgs e;
     e.prm = ec.prm; e.ln_g = ln_g != nullptr; e.relu = relu; e.out = out; e.xhat = xhat; e.rstd = rstd; e.m_train = m_train;
     e.acc_scale = acc_scale;
-    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, m < M);
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, m < M, m, false);
   }
 };
 
@@ -482,7 +489,9 @@ struct ConvFwdTmaTC {
   static_assert(B_KMAJOR_ || BN_ % 64 == 0, "the MN-major weight stage is filled in 64-column swizzle groups");
   CUtensorMap tm_x;  // activations [N][H][W][Cin] bf16, box {64, OW, th, 1}, SWIZZLE_128B
   CUtensorMap tm_w;  // weights [K][Cout] bf16, box {64, 64} — or transposed [Cout][K], box {64, BN}
-  int n_img, pix, OW, OH, th, tpi, ksz, pad_y, pad_x, cchunks;  // tpi = tiles per image, cchunks = Cin / 64
+  int n_img, pix, OW, OH, th, tpi, cchunks;  // tpi = tiles per image, cchunks = Cin / 64
+  int ksz_y, ksz_x, sy, pad_y, pad_x;        // taps and row stride OF THE VIEW the tensor map describes (column stride 1)
+  int out_pitch;                             // 0, or pixels per stored output row (OW + 1: a zero column on the left)
   const float* bias; const float* ln_g; const float* ln_b; int relu;
   bf16* out; float* xhat; float* rstd; int m_train;
   float acc_scale;
@@ -499,16 +508,16 @@ struct ConvFwdTmaTC {
   }
   __device__ void tma_tile(PCtx& c, int tile, int, int) const {
     c.img = tile / tpi;
-    c.y0 = (tile - c.img * tpi) * th - pad_y;
+    c.y0 = (tile - c.img * tpi) * th * sy - pad_y;
     c.ky = c.kx = c.cc = 0;
   }
   __device__ uint32_t stage_tx_bytes(const PCtx&) const { return (uint32_t)(th * OW * 128 + BN * 128); }
-  __device__ void k_range(int, int& b, int& e) const { b = 0; e = ksz * ksz * cchunks; }
+  __device__ void k_range(int, int& b, int& e) const { b = 0; e = ksz_y * ksz_x * cchunks; }
   __device__ void tma_load(PCtx& c, uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int kc) const {
     tma_load_4d(stage_a, &tm_x, c.cc * 64, c.kx - pad_x, c.y0 + c.ky, c.img, bar);
     if (++c.cc == cchunks) {  // next chunk: next 64 channels, then next tap (kx fastest) — no divisions in the loop
       c.cc = 0;
-      if (++c.kx == ksz) {
+      if (++c.kx == ksz_x) {
         c.kx = 0;
         ++c.ky;
       }
@@ -536,7 +545,9 @@ struct ConvFwdTmaTC {
     ConvEpilogueArgs e;
     e.prm = ec.prm; e.ln_g = ln_g != nullptr; e.relu = relu; e.out = out; e.xhat = xhat; e.rstd = rstd; e.m_train = m_train;
     e.acc_scale = acc_scale;
-    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, (int64_t)img * pix + oy * OW + ox, r < th && oy < OH && img < n_img);
+    const int64_t m = (int64_t)img * pix + oy * OW + ox;
+    const int64_t m_out = out_pitch ? ((int64_t)img * OH + oy) * out_pitch + ox + 1 : m;
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, r < th && oy < OH && img < n_img, m_out, out_pitch != 0 && ox == 0);
   }
 };
 
