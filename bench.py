@@ -196,11 +196,11 @@ def kernel_work(name: str, P: int):
         return "hbm", 4 * 7744 * 512 + 2 * B * (7744 + 512)
     if name in ("tc_dense_dgrad", "tc_dense_fwd"):
         return "hbm", 2 * 7744 * 512 + 2 * 2 * B * (7744 + 512)
-    if name == "tc_conv_fwd":  # three launches: torso forward on 2B images
+    if name in ("tc_conv_fwd", "tc_conv_fwd_tma"):  # three launches: torso forward on 2B images
         return "tensor", 2 * B * 24_076_288
     if name == "tc_conv_wgrad":
         return "tensor", B * 24_076_288
-    if name == "tc_conv_dgrad":
+    if name in ("tc_conv_dgrad", "tc_conv_dgrad_tma"):
         return "tensor", B * (24_076_288 - 2 * 441 * 256 * 32)
     return None, 0
 
@@ -524,7 +524,7 @@ def run_dp(args, rank, world, local_rank):
         # FLOPs per transition scale with width^2 for every layer but the first conv (x width) and the head (x width)
         P = agent.network.n_params
         flops = Bg * flops_per_transition(feats)
-        torso = sum(v[1] for k, v in per_kernel.items() if k in ("tc_conv_fwd", "conv_fwd"))
+        torso = sum(v[1] for k, v in per_kernel.items() if k in ("tc_conv_fwd", "tc_conv_fwd_tma", "conv_fwd"))
         torso_flops = 2 * Bl * torso_fwd_flops(feats)
         line = {
             "metric": "iS-DQN K=9 learner updates/sec (data parallel)", "value": args.steps / (ms / 1e3), "unit": "updates/s",
