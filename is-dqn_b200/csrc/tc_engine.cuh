@@ -93,6 +93,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 // problems that feed their stages with TMA declare `static constexpr bool TMA = true`
+// problems whose epilogue stores through the per-warp shared-memory staging block declare `EP_STAGE = true`
+template <class P, class = void>
+struct uses_ep_stage : std::false_type {};
+template <class P>
+struct uses_ep_stage<P, std::void_t<decltype(P::EP_STAGE)>> : std::bool_constant<P::EP_STAGE> {};
+constexpr int kEpStageWords = 32 * 20;  // per epilogue warp: 32 rows x 16 words, 20-word pitch
+
 template <class P, class = void>
 struct uses_tma : std::false_type {};
 template <class P>
@@ -247,6 +254,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
   __shared__ uint32_t tmem_base_sh;
   __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
   __shared__ __align__(16) float ep_sm[P::EP_FLOATS > 0 ? P::EP_FLOATS : 4];
+  __shared__ __align__(16) uint32_t ep_stage[uses_ep_stage<P>::value ? kEpilogueWarps * kEpStageWords : 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   trace_kernel_start();
@@ -387,7 +395,8 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
       mbar_wait(&tmem_full_bar[a], (uint32_t)((ti >> 1) & 1));
       if (tid == 0 && ti == 0) trace_mark(5);  // first accumulator complete
       tcgen05_fence_after();
-      p.epilogue(ectx, tmem_d + a * BN + ((uint32_t)(warp * 32) << 16), m0, n0, tz, tid);
+      p.epilogue(ectx, tmem_d + a * BN + ((uint32_t)(warp * 32) << 16), m0, n0, tz, tid,
+                 uses_ep_stage<P>::value ? ep_stage + warp * kEpStageWords : nullptr);
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[a]);
     }

@@ -81,6 +81,52 @@ __device__ __forceinline__ void load_rows_mnmajor(const bf16* __restrict__ src, 
   }
 }
 
+// Coalesced store of a 32-row x 16-word block that the warp owns row-per-thread (the layout tcgen05.ld 32x32b delivers):
+// staged in shared memory (20-word pitch), then written eight rows (8 x 64 contiguous bytes) per 128-bit store instruction:
+// 4 full-sector store instructions instead of 4 that touch 32 half-used sectors each.
+// row_ptr: where word 0 of the block goes in THIS thread's row; valid: this thread's row is stored; n_words: words of the
+// block inside the matrix (ragged N).  Warp-collective: every lane must call it.
+constexpr int kStagePitch = 20;  // words: 16 + 4 (keeps every row 16-byte aligned for the 128-bit accesses)
+__device__ __forceinline__ void warp_store_block16(uint32_t* stg, const uint32_t (&w)[16], void* row_ptr, bool valid,
+                                                   int n_words = 16) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  uint4* mine4 = reinterpret_cast<uint4*>(stg + lane * kStagePitch);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) mine4[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  __syncwarp();
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned long long mine = (unsigned long long)(uintptr_t)row_ptr;
+  const int sub = lane >> 2, c4 = lane & 3;  // 8 rows x 4 quads per instruction: 8 x 64 contiguous bytes
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = 8 * it + sub;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, mine, r);
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + r * kStagePitch + 4 * c4);
+    if (((vmask >> r) & 1u) && 4 * c4 < n_words) reinterpret_cast<uint4*>((uintptr_t)rp)[c4] = v;  // (n_words % 4 == 0)
+  }
+}
+
+// fp32 store of the accumulator tile through warp_store_block16 (stg != nullptr) — thread t owns row t
+template <int BN>
+__device__ __forceinline__ void store_rows_f32_coalesced(uint32_t tmem_lane_base, float* __restrict__ dst, bool row_valid, int n0,
+                                                         int n_end, uint32_t* stg, float scale = 1.0f) {
+#pragma unroll 1
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    float v[32];
+    tmem_ld32(tmem_lane_base + cb * 32, v);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[16 * h + i] * scale);
+      const int n = n0 + cb * 32 + 16 * h;
+      const int left = n_end - n;
+      warp_store_block16(stg, w, dst + n, row_valid && left > 0, left < 16 ? left : 16);
+    }
+  }
+}
+
 // plain fp32 store of the accumulator tile: thread t owns row t
 template <int BN>
 __device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, float* __restrict__ dst, bool row_valid, int n0,
@@ -150,7 +196,7 @@ struct GemmTC {
     if (B_MN) load_rows_mnmajor<BN / 8, PT, B_SW>(B, ldb, kc * kBK, K, c.n0, N, stage, ptid);
     else load_rows_kmajor<BN, PT, B_SW>(B, ldb, c.n0, N, kc * kBK, K, stage, ptid);
   }
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid, uint32_t* stg) const {
     const int m = m0 + etid;
     float* dst = C + (int64_t)split * split_stride + (int64_t)(m < M ? m : 0) * ldc;
     store_rows_f32<BN>(tmem_lane_base, dst, m < M, n0, N);
@@ -164,7 +210,7 @@ template <int BN_, bool A_MN_, bool B_MN_, bool WIDE_ = false>
 struct GemmTmaTC {
   static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1, EXTRA_BYTES = 0, EP_FLOATS = 0;
   static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
-  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
   static_assert(BN_ % 64 == 0, "swizzled B stage");
   CUtensorMap tm_a;  // A K-major: dims {K, M}, box {64, 128};  A MN-major: dims {M, K}, box {64, 64}
   CUtensorMap tm_b;  // B K-major: dims {K, N}, box {64, BN};   B MN-major: dims {N, K}, box {64, 64}
@@ -205,10 +251,10 @@ struct GemmTmaTC {
   }
   __device__ void init_epilogue(ECtx&, float*, int) const {}
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid, uint32_t* stg) const {
     const int m = m0 + etid;
     float* dst = C + (int64_t)split * split_stride + (int64_t)(m < M ? m : 0) * ldc;
-    store_rows_f32<BN>(tmem_lane_base, dst, m < M, n0, N);
+    store_rows_f32_coalesced<BN>(tmem_lane_base, dst, m < M, n0, N, stg);
   }
 };
 
@@ -303,7 +349,7 @@ struct ConvEpilogueArgs {
 // zero_left: also write a zero pixel at m_out - 1 (the left padding column of that layout)
 template <int BN>
 __device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e, uint32_t tmem_lane_base, int64_t m, bool valid,
-                                                      int64_t m_out, bool zero_left) {
+                                                      int64_t m_out, bool zero_left, uint32_t* stg = nullptr) {
     const float4* pb = reinterpret_cast<const float4*>(e.prm);
     const float4* pg = reinterpret_cast<const float4*>(e.prm + BN);
     const float4* pbeta = reinterpret_cast<const float4*>(e.prm + 2 * BN);
@@ -353,19 +399,37 @@ __device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e,
         packed[2 * q] = pack_bf16(y[0], y[1]);
         packed[2 * q + 1] = pack_bf16(y[2], y[3]);
       }
-      if (valid) {
-        uint4* o = reinterpret_cast<uint4*>(e.out + m_out * BN + cb * 32);
+      if (stg) {  // coalesced through shared memory (warp-collective: no early outs above)
+        warp_store_block16(stg, packed, e.out + m_out * BN + cb * 32, valid);
+        if (e.xhat != nullptr && e.ln_g) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-        if (zero_left) {
+          for (int h = 0; h < 2; ++h) {
+            uint32_t w[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) (o - BN / 8)[q] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[16 * h + i]);
+            warp_store_block16(stg, w, e.xhat + (int64_t)m * BN + cb * 32 + 16 * h, save);
+          }
         }
-      }
-      if (save) {
-        float4* x = reinterpret_cast<float4*>(e.xhat + (int64_t)m * BN + cb * 32);
+        if (valid && zero_left) {
+          uint4* o = reinterpret_cast<uint4*>(e.out + (m_out - 1) * BN + cb * 32);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) x[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      } else {
+        if (valid) {
+          uint4* o = reinterpret_cast<uint4*>(e.out + m_out * BN + cb * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          if (zero_left) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) (o - BN / 8)[q] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        if (save) {
+          float4* x = reinterpret_cast<float4*>(e.xhat + (int64_t)m * BN + cb * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
       }
     }
     if (save) e.rstd[m] = rs;
@@ -462,7 +526,7 @@ struct ConvFwdTC {
   __device__ void load_b(const PCtx&, uint32_t stage, int kc, int ptid) const {
     load_rows_mnmajor<BN / 8, PT, B_SW>(w, Cout, kc * kBK, K, 0, Cout, stage, ptid);
   }
-  __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
+  __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid, uint32_t* stg) const {
     const int m = m0 + etid;
     ConvEpilogueArgs e;
     e.prm = ec.prm; e.ln_g = ln_g != nullptr; e.relu = relu; e.out = out; e.xhat = xhat; e.rstd = rstd; e.m_train = m_train;
@@ -485,7 +549,7 @@ struct ConvFwdTmaTC {
   static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
   static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 3 * BN_;
-  static constexpr bool A_MN = false, B_MN = !B_KMAJOR_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  static constexpr bool A_MN = false, B_MN = !B_KMAJOR_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
   static_assert(B_KMAJOR_ || BN_ % 64 == 0, "the MN-major weight stage is filled in 64-column swizzle groups");
   CUtensorMap tm_x;  // activations [N][H][W][Cin] bf16, box {64, OW, th, 1}, SWIZZLE_128B
   CUtensorMap tm_w;  // weights [K][Cout] bf16, box {64, 64} — or transposed [Cout][K], box {64, BN}
@@ -538,7 +602,7 @@ struct ConvFwdTmaTC {
     e.prm = ep_sm;
   }
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
-  __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid) const {
+  __device__ void epilogue(const ECtx& ec, uint32_t tmem_lane_base, int m0, int, int, int etid, uint32_t* stg) const {
     const int tile = m0 / kBM;  // (the engine numbers tiles in units of 128 rows)
     const int img = tile / tpi, y0 = (tile - img * tpi) * th;
     const int r = etid / OW, ox = etid - r * OW, oy = y0 + r;
@@ -547,7 +611,7 @@ struct ConvFwdTmaTC {
     e.acc_scale = acc_scale;
     const int64_t m = (int64_t)img * pix + oy * OW + ox;
     const int64_t m_out = out_pitch ? ((int64_t)img * OH + oy) * out_pitch + ox + 1 : m;
-    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, r < th && oy < OH && img < n_img, m_out, out_pitch != 0 && ox == 0);
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, r < th && oy < OH && img < n_img, m_out, out_pitch != 0 && ox == 0, stg);
   }
 };
 
@@ -623,7 +687,7 @@ struct ConvWgradTC {
   __device__ void load_b(const PCtx& c, uint32_t stage, int kc, int ptid) const {
     load_rows_mnmajor<BN / 8, PT, B_SW>(dz, Cout, kc * kBK, M, c.n0, Cout, stage, ptid);
   }
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid) const {
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid, uint32_t* stg) const {
     const int k = m0 + etid;
     float* dst = part + ((int64_t)split * K + (k < K ? k : 0)) * Cout;
     store_rows_f32<BN>(tmem_lane_base, dst, k < K, n0, Cout, acc_scale);
@@ -761,7 +825,7 @@ struct ConvDgradTC {
       cp_async16(stage + kmajor_off<B_SW>(r, ch), v ? w + wo + (int64_t)cin * Cout : w, v);
     }
   }
-  __device__ void epilogue(const ECtx& e, uint32_t tmem_lane_base, int, int n0, int, int) const {
+  __device__ void epilogue(const ECtx& e, uint32_t tmem_lane_base, int, int n0, int, int, uint32_t* stg) const {
     store_rows_f32<BN>(tmem_lane_base, dx + (int64_t)e.pix * Cin, e.valid, n0, Cin);
   }
 };
@@ -777,7 +841,7 @@ struct ConvDgradTmaTC {
   static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
   static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 0;
-  static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true;
+  static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
   CUtensorMap tm_dz[4];  // dz [N][OH][OW][Cout] bf16, box {64, nx(cls), ny(cls), 1}
   CUtensorMap tm_w;      // weights as [ksz*ksz*Cin rows][Cout], box {64, BN}
   int H, W, Cin, Cout, ksz, stride, pad_y, pad_x, n_img, cchunks;  // cchunks = Cout / 64
@@ -837,13 +901,13 @@ struct ConvDgradTmaTC {
   }
   __device__ void init_epilogue(ECtx&, float*, int) const {}
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int cls, int etid) const {
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int cls, int etid, uint32_t* stg) const {
     const Cls c = cls_of(cls);
     const int img = m0 / kBM;
     const bool valid = etid < c.ny * c.nx && img < n_img;
     const int iyc = etid / (c.nx > 0 ? c.nx : 1), ixc = etid - iyc * c.nx;
     const int64_t pix = valid ? ((int64_t)img * H + (c.iy_first + stride * iyc)) * W + (c.ix_first + stride * ixc) : 0;
-    store_rows_f32<BN>(tmem_lane_base, dx + pix * Cin, valid, n0, Cin);
+    store_rows_f32_coalesced<BN>(tmem_lane_base, dx + pix * Cin, valid, n0, Cin, stg);
   }
 };
 
