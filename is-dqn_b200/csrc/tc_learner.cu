@@ -450,6 +450,63 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
 #undef ISDQN_CONV_FWD_TMA
 }
 
+// TMA-fed weight gradient.  V: the convolution on the view the input tensor map is built over (as in launch_conv_fwd_tma);
+// dz is [n_img][OH][OW][Cout].  Partials come out as [real_splits][K][Cout].
+bool conv_wgrad_tma_ok(const Layer& V) {
+  return tensor_map_encoder() != nullptr && V.type == 0 && V.Cin % 64 == 0 && V.OW <= 64 && V.W <= 256 && V.H <= 256 &&
+         (V.out_dim == 64 || V.out_dim == 128 || V.out_dim == 256);
+}
+
+int launch_conv_wgrad_tma(const Layer& V, const bf16* x, const bf16* dz, float* part, int n_img, int splits, int* real_splits,
+                          cudaStream_t s, float in_scale, int ksz_x, int sy) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (ksz_x == 0) ksz_x = V.ksz;
+  const int wb = V.OW <= 16 ? 16 : V.OW <= 32 ? 32 : 64, rpc = 64 / wb;
+  const int cpi = ceil_div(V.OH, rpc);
+  const int total_chunks = n_img * cpi;
+  const int cps = ceil_div(total_chunks, splits);
+  *real_splits = ceil_div(total_chunks, cps);
+  CUtensorMap tm_x, tm_dz;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)V.Cin, (cuuint64_t)V.W, (cuuint64_t)V.H, (cuuint64_t)n_img};
+    const cuuint64_t strides[3] = {(cuuint64_t)V.Cin * 2, (cuuint64_t)V.W * V.Cin * 2, (cuuint64_t)V.H * V.W * V.Cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)wb, (cuuint32_t)(sy * (rpc - 1) + 1), 1};
+    const cuuint32_t es[4] = {1, 1, (cuuint32_t)sy, 1};
+    if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)V.out_dim, (cuuint64_t)V.OW, (cuuint64_t)V.OH, (cuuint64_t)n_img};
+    const cuuint64_t strides[3] = {(cuuint64_t)V.out_dim * 2, (cuuint64_t)V.OW * V.out_dim * 2, (cuuint64_t)V.OH * V.OW * V.out_dim * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)wb, (cuuint32_t)rpc, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tm_dz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(dz), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  const int tiles_k = ceil_div(V.in_dim, tc::kBM);
+#define ISDQN_CONV_WGRAD_TMA_W(BN, WIDE)                                                               \
+  {                                                                                                    \
+    tc::ConvWgradTmaTC<BN, WIDE> p;                                                                    \
+    p.tm_x = tm_x; p.tm_dz = tm_dz; p.K = V.in_dim; p.Cout = V.out_dim; p.cchunks = V.Cin / 64;        \
+    p.ksz_x = ksz_x; p.sy = sy; p.pad_y = V.pad_y; p.pad_x = V.pad_x; p.rpc = rpc; p.cpi = cpi;        \
+    p.total_chunks = total_chunks; p.chunks_per_split = cps; p.part = part; p.acc_scale = in_scale;    \
+    return launch_tc(p, tiles_k, 1, *real_splits, s, "tc_conv_wgrad_tma");                             \
+  }
+#define ISDQN_CONV_WGRAD_TMA(BN)                                                                       \
+  if (wide_launch((int64_t)tiles_k * *real_splits)) ISDQN_CONV_WGRAD_TMA_W(BN, true)                   \
+  else ISDQN_CONV_WGRAD_TMA_W(BN, false)
+  switch (V.out_dim) {
+    case 64: ISDQN_CONV_WGRAD_TMA(64)
+    case 128: ISDQN_CONV_WGRAD_TMA(128)
+    case 256: ISDQN_CONV_WGRAD_TMA(256)
+    default: return ISDQN_E_UNSUPPORTED;
+  }
+#undef ISDQN_CONV_WGRAD_TMA_W
+#undef ISDQN_CONV_WGRAD_TMA
+}
+
 template <bool U8, bool SEG4 = false>
 int launch_conv_wgrad_tc(const Layer& L, const void* in, const bf16* dz, float* part, int rows, int splits, int* real_splits,
                          cudaStream_t s, float in_scale = 1.0f, int max_ctas = 0) {
@@ -812,9 +869,27 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     } else {
       int real_splits = 1;
       float* part = wsp(ws, w.wpart[l]);
-      if (l == 0 && t.w0p >= 0) {  // gather from the space-to-depth frames (128-byte taps); partials come out in s2d K order
-        rc = launch_conv_wgrad_tc<false>(s2d_layer(L), w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw,
-                                         1.0f / 255.0f, side ? side_cap : 0);
+      static const bool wgrad_tma = [] {
+        const char* e = getenv("ISDQN_TMA_WGRAD");
+        return !(e && e[0] == '0');
+      }();
+      if (l == 0 && t.w0p >= 0) {  // space-to-depth frames (128-byte taps); partials come out in s2d K order
+        const Layer S = s2d_layer(L);
+        if (wgrad_tma && conv_wgrad_tma_ok(S))
+          rc = launch_conv_wgrad_tma(S, w16(wt, t.x16), dz16, part, B, w.wsplits_tc[l], &real_splits, sw, 1.0f / 255.0f, 0, 1);
+        else
+          rc = launch_conv_wgrad_tc<false>(S, w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw,
+                                           1.0f / 255.0f, side ? side_cap : 0);
+      } else if (l == 1 && t.pair_view && wgrad_tma) {
+        Layer V = L;  // the pair-of-pixels view of the padded activation (as in the forward pass)
+        V.W = (L.W + 1) / 2;
+        V.Cin = 2 * L.Cin;
+        V.pad_x = 0;
+        rc = conv_wgrad_tma_ok(V)
+                 ? launch_conv_wgrad_tma(V, w16(wt, t.act16[l - 1]), dz16, part, B, w.wsplits_tc[l], &real_splits, sw, 1.0f, 2, 2)
+                 : ISDQN_E_UNSUPPORTED;
+      } else if (l > 0 && wgrad_tma && L.stride == 1 && conv_wgrad_tma_ok(L)) {
+        rc = launch_conv_wgrad_tma(L, w16(wt, t.act16[l - 1]), dz16, part, B, w.wsplits_tc[l], &real_splits, sw, 1.0f, 0, 1);
       } else if (l == 0 && t.x16 >= 0 && L.ksz * L.Cin == 32)
         rc = launch_conv_wgrad_tc<false, true>(L, w16(wt, t.x16), dz16, part, rows_l, w.wsplits_tc[l], &real_splits, sw,
                                                1.0f / 255.0f, side ? side_cap : 0);

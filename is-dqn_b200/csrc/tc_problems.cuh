@@ -911,5 +911,74 @@ struct ConvDgradTmaTC {
   }
 };
 
+// ------------------------------------------------------------------------------- conv weight gradient, TMA-fed
+// dW[k][co] = sum over output pixels of im2col(x)[pix][k] dz[pix][co]; both operands MN-major, the reduction axis is the
+// pixel axis.  A reduction chunk is a box of wb x rpc = 64 pixel positions of ONE image (wb = 16/32/64 columns >= OW,
+// rpc = 64 / wb output rows): the box columns beyond OW are out of range for dz, so the copy engine zero-fills those rows
+// of the dz stage and they contribute nothing, whatever the input stage holds there.  A 128-wide tile of k is two 64-wide
+// groups = two (tap, 64-channel chunk) pairs, each ONE 4-D copy of the input view at the tap's offset (row traversal stride
+// sy); the dz stage is Cout/64 copies.  63-69 % of the rows are real pixels (OW = 11: 44 of 64) — the price for having no
+// gather at all.
+template <int BN_, bool WIDE_ = false>
+struct ConvWgradTmaTC {
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
+  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
+  static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr bool A_MN = true, B_MN = true, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
+  static_assert(BN_ % 64 == 0, "swizzled dz stage");
+  CUtensorMap tm_x;   // input view [N][H][W][Cin] bf16, box {64, wb, sy*(rpc-1)+1, 1}, traversal stride sy along H
+  CUtensorMap tm_dz;  // dz [N][OH][OW][Cout] bf16, box {64, wb, rpc, 1}
+  int K, Cout, cchunks, ksz_x, sy, pad_y, pad_x, rpc, cpi, total_chunks, chunks_per_split;  // cpi = chunks per image
+  float* part;        // [splits][K][Cout]
+  float acc_scale;
+  struct PCtx {
+    int c0[2], kx[2], ky[2], n_groups;  // the (up to) two 64-wide k groups of the tile
+    int img, yc;                        // running reduction chunk: image, chunk inside the image
+  };
+  struct ECtx {};
+  __device__ void tma_prefetch() const {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_dz);
+  }
+  __device__ void tma_tile(PCtx& c, int tx, int, int split) const {
+    c.n_groups = 0;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int gi = 2 * tx + g;
+      const int tap = gi / cchunks;
+      c.c0[g] = (gi - tap * cchunks) * 64;
+      c.ky[g] = tap / ksz_x;
+      c.kx[g] = tap - c.ky[g] * ksz_x;
+      if (gi * 64 < K) c.n_groups = g + 1;
+    }
+    const int kb = split * chunks_per_split;
+    c.img = kb / cpi;
+    c.yc = kb - c.img * cpi;
+  }
+  __device__ uint32_t stage_tx_bytes(const PCtx& c) const { return (uint32_t)(c.n_groups * 8192 + (BN / 64) * 8192); }
+  __device__ void k_range(int split, int& b, int& e) const {
+    b = split * chunks_per_split;
+    e = min(total_chunks, b + chunks_per_split);
+  }
+  __device__ void tma_load(PCtx& c, uint32_t stage_a, uint32_t stage_b, uint64_t* bar, int) const {
+    const int y0 = c.yc * rpc;
+    for (int g = 0; g < c.n_groups; ++g)
+      tma_load_4d(stage_a + g * 8192, &tm_x, c.c0[g], c.kx[g] - pad_x, sy * y0 + c.ky[g] - pad_y, c.img, bar);
+#pragma unroll
+    for (int g = 0; g < BN / 64; ++g) tma_load_4d(stage_b + g * 8192, &tm_dz, 64 * g, 0, y0, c.img, bar);
+    if (++c.yc == cpi) {
+      c.yc = 0;
+      ++c.img;
+    }
+  }
+  __device__ void init_epilogue(ECtx&, float*, int) const {}
+  __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
+  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid, uint32_t* stg) const {
+    const int k = m0 + etid;
+    float* dst = part + ((int64_t)split * K + (k < K ? k : 0)) * Cout;
+    store_rows_f32_coalesced<BN>(tmem_lane_base, dst, k < K, n0, Cout, stg, acc_scale);
+  }
+};
+
 }  // namespace tc
 }  // namespace isdqn
