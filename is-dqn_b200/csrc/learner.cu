@@ -375,6 +375,55 @@ int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float*
   return ISDQN_OK;
 }
 
+// Rank-B weight gradient of a Dense kernel [Kin][N] recomputed on the fly + its Adam update (dense_wgrad_adam_kernel).
+// act: bf16 [B][lda] (first Kin columns), dz: bf16 [B][N].  The caller checks isdqn_dense_wgrad_adam_ok first and keeps
+// the separate weight gradient + Adam when the shape does not qualify.
+bool isdqn_dense_wgrad_adam_ok(int B, int Kin, int N, int64_t w_off) {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_FUSED_DENSE_ADAM");
+    return !(e && e[0] == '0');
+  }();
+  return on && B >= 1 && B <= 64 && Kin % 8 == 0 && N % 8 == 0 && w_off % 8 == 0;
+}
+int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count,
+                                  float lr, float b1, float b2, float eps, void* d_shadow_bf16, int64_t n_total, int64_t w_off,
+                                  const void* d_act_bf16, int64_t lda, const void* d_dz_bf16, int B, int Kin, int N,
+                                  void* stream) {
+  // the whole flat vector [0, n_total): the Dense kernel at w_off from its recomputed gradient, every other leaf from d_grads
+  if (!d_params || !d_grads || !d_mu || !d_nu || !d_count || !d_act_bf16 || !d_dz_bf16 || (n_total & 3)) return ISDQN_E_INVALID;
+  if (!isdqn_dense_wgrad_adam_ok(B, Kin, N, w_off) || w_off + (int64_t)Kin * N > n_total) return ISDQN_E_UNSUPPORTED;
+  static const int want_ctas = [] {
+    const char* e = getenv("ISDQN_DWA_CTAS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 2 * kNumSMs;
+  }();
+  const int gy = ceil_div(N, kDwaCols);
+  const int n_tiles = ceil_div(Kin, kDwaTileRows);
+  int gx = want_ctas / gy;
+  if (gx < 1) gx = 1;
+  const int tpc = ceil_div(n_tiles, gx);
+  gx = ceil_div(n_tiles, tpc);
+  const int64_t rest4 = (n_total - (int64_t)Kin * N) / 4;
+  int rest_ctas = (int)ceil_div<int64_t>(rest4, 2 * kDwaThreads);
+  if (rest_ctas > kNumSMs) rest_ctas = kNumSMs;
+  const size_t smem = (size_t)B * kDwaCols * 2 + (size_t)B * tpc * kDwaTileRows * 4;
+  if (smem > 100 * 1024) return ISDQN_E_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ISDQN_CUDA_CHECK(cudaFuncSetAttribute(dense_wgrad_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  ISDQN_PROF(as_stream(stream), "dense_wgrad_adam");
+  co_resident_with_tc(dense_wgrad_adam_kernel);
+  ISDQN_CUDA_CHECK(launch_pdl(dense_wgrad_adam_kernel, dim3((unsigned)(rest_ctas + gx), (unsigned)gy), dim3(kDwaThreads), smem,
+                              as_stream(stream), d_params, d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps,
+                              reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16), w_off, n_total / 4,
+                              reinterpret_cast<const __nv_bfloat16*>(d_act_bf16), lda,
+                              reinterpret_cast<const __nv_bfloat16*>(d_dz_bf16), B, Kin, N, tpc, rest_ctas));
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
 extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, float* d_mu, float* d_nu,
                                        const int32_t* d_count, float lr, float b1, float b2, float eps, int64_t n,
                                        void* stream) {

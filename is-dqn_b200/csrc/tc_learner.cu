@@ -11,6 +11,11 @@
 using namespace isdqn;
 using isdqn::tc::bf16;
 
+bool isdqn_dense_wgrad_adam_ok(int B, int Kin, int N, int64_t w_off);
+int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count,
+                                  float lr, float b1, float b2, float eps, void* d_shadow_bf16, int64_t n_total, int64_t w_off,
+                                  const void* d_act_bf16, int64_t lda, const void* d_dz_bf16, int B, int Kin, int N,
+                                  void* stream);
 int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
                       float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream, int64_t skip_begin,
                       int64_t skip_len, int max_ctas = 0);
@@ -802,6 +807,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   };
   int64_t pend_off = -1, pend_n = 0;    // Dense kernel whose early Adam waits for the next fork point
   int64_t early_off = 0, early_n = 0;   // range already updated on the side stream
+  int fused_l = -1;                     // small batch: Dense layer whose weight gradient is recomputed inside its Adam update
   for (int l = nl - 1; l >= 0; --l) {
     const Layer& L = p.L[l];
     const bf16* dz16 = w16(wt, t.dz16[l]);
@@ -857,6 +863,9 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         add_seg(g.C, grads + L.w_off, g.split_stride, L.in_dim * L.out_dim, real_splits);
       }
       rc = launch_simt_gemm(g, sw, "head_wgrad_gemm");
+    } else if (L.type == 1 && update && fmode == 0 && !tr->nccl_comm && fused_l < 0 && l > 0 &&
+               isdqn_dense_wgrad_adam_ok(B, L.in_dim, L.out_dim, L.w_off)) {
+      fused_l = l;  // no gradient launch: dense_wgrad_adam_kernel (below, after the last reader of this kernel's shadow)
     } else if (L.type == 1) {
       rc = launch_gemm_tc<true, true>(w16(wt, t.act16[l - 1]), L.in_dim, dz16, L.out_dim, grads + L.w_off, L.out_dim, 0,
                                       L.in_dim, L.out_dim, B, 1, sw, "tc_dense_wgrad", side ? side_cap : 0);
@@ -976,6 +985,12 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     ISDQN_PROF(s, "nccl_allreduce");
     rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, p.layout.total, stream);
     if (rc) return rc;
+  }
+  if (fused_l >= 0) {  // the Dense kernel from its recomputed gradient + every other leaf from `grads`: one launch
+    const Layer& L = p.L[fused_l];
+    return isdqn_dense_wgrad_adam_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2,
+                                         tr->eps, shadow, p.layout.total, L.w_off, w16(wt, t.act16[fused_l - 1]), L.in_dim,
+                                         w16(wt, t.dz16[fused_l]), B, L.in_dim, L.out_dim, stream);
   }
   return isdqn_adam_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
                            p.layout.total, shadow, stream, early_off, early_n);

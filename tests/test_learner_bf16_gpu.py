@@ -116,3 +116,36 @@ def test_bf16_graph_replay_is_deterministic():
             agent.learn_on_batch(agent.params, agent.optimizer_state, el)
         outs.append(agent.params.flat.cpu().numpy().tobytes())
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("B", [32, 5, 64, 300])
+def test_update_is_adam_of_the_reported_gradient_bf16(B):
+    """learn_on_batch from a zero optimiser state must leave mu = (1-b1) g, nu = (1-b2) g^2 and the optax step of exactly
+    the gradient grad_on_batch reports — for every leaf.  At batch <= 64 the hidden Dense kernel takes the fused
+    rank-B gradient + Adam kernel (its gradient never reaches memory), above that the separate launches: both must agree
+    with the tensor-core gradient (fp32 accumulation order is the only difference)."""
+    agent = make_agent(11, **ATARI, compute_dtype="bfloat16")
+    push_params(agent, oracle_params_for(agent, 11))
+    el = batch_as_element(L.make_batch(1234 + B, B, ATARI["obs_dim"], 9, "cnn"))
+    for _ in range(2):  # two steps: the second is the graph-captured launch on a non-zero state
+        mu0 = agent.optimizer_state["mu"].flat.detach().clone().double()
+        nu0 = agent.optimizer_state["nu"].flat.detach().clone().double()
+        t = int(agent.optimizer_state["count"].item()) + 1
+        p0 = agent.params.flat.detach().clone().double()
+        grads, _ = agent.grad_on_batch(agent.params, el)
+        g = grads.flat.detach().clone().double()
+        agent.params, agent.optimizer_state, _ = agent.learn_on_batch(agent.params, agent.optimizer_state, el)
+        torch.cuda.synchronize()
+        b1, b2 = agent.adam_b1, agent.adam_b2
+        mu = b1 * mu0 + (1 - b1) * g
+        nu = b2 * nu0 + (1 - b2) * g * g
+        step = agent.learning_rate * (mu / (1 - b1**t)) / (torch.sqrt(nu / (1 - b2**t)) + agent.adam_eps)
+        got_mu = agent.optimizer_state["mu"].flat.double()
+        got_nu = agent.optimizer_state["nu"].flat.double()
+        got_step = p0 - agent.params.flat.double()
+        # (the step is read back as a difference of fp32 parameters: their rounding is ~1e-4 of a 6e-5 step)
+        for name, got, want, tol in (("mu", got_mu, mu, 2e-5), ("nu", got_nu, nu, 4e-5), ("step", got_step, step, 2e-3)):
+            e = float((got - want).norm() / want.norm().clamp_min(1e-30))
+            assert e <= tol, f"B={B} t={t}: {name} differs from Adam(grad_on_batch) by {e:.3e} (rel L2)"
+        # the bf16 shadow the next forward reads is the rounding of the new parameters, everywhere
+        assert torch.equal(agent.params.shadow.float(), agent.params.flat.to(torch.bfloat16).float())
