@@ -288,6 +288,22 @@ int isdqn_write_async(void* d_dst, const void* h_src, int64_t bytes, void* strea
  * batch of one (s' aliased to s) this is captured in a CUDA graph by the Python host (iSDQN.best_action). */
 int isdqn_argmax_heads(const float* d_q, int32_t n_heads_total, int32_t n_actions, int32_t* d_out, void* stream);
 
+/* Acting path as ONE kernel (replaces the jitted body of iSDQN.best_action, isdqn.py:127-135, and the
+ * DQNNet forward it runs, architectures/dqn.py:47-103, for the `cnn` architecture on ONE uint8 observation stack
+ * [H][W][C]): conv torso + LayerNorm + hidden Dense + head layer + the greedy action of EVERY head (d_actions[1 + K],
+ * first maximum like jnp.argmax; the caller picks head 1 + idx).  fp32 master weights whatever the learner's compute
+ * dtype.  d_q (optional) receives the (1 + K) * A Q-values.  d_workspace: isdqn_act_workspace_bytes(net) bytes, ZEROED
+ * once by the caller (its first 16 bytes are the grid barrier, re-armed by every launch); 0 bytes = the network is
+ * outside what this path covers (ISDQN_E_UNSUPPORTED from isdqn_act; use isdqn_best_action).
+ * isdqn_act_host: the whole env-step call — pinned observation -> d_obs, the kernel, actions -> pinned host, and the
+ * one synchronisation the reference's `.item()` performs (on `event`). */
+int64_t isdqn_act_workspace_bytes(const isdqn_net* net);
+int isdqn_act(const isdqn_net* net, const float* d_params, const uint8_t* d_obs, float* d_q, int32_t* d_actions,
+              void* d_workspace, int64_t workspace_bytes, void* stream);
+int isdqn_act_host(const isdqn_net* net, const float* d_params, const uint8_t* h_obs_pinned, uint8_t* d_obs,
+                   int64_t obs_bytes, float* d_q, int32_t* d_actions, int32_t* h_actions_pinned, void* d_workspace,
+                   int64_t workspace_bytes, void* stream, void* event);
+
 /* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
  * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */
 int isdqn_trace_set(void* d_buf);

@@ -147,6 +147,9 @@ PROTOTYPES = {
     "isdqn_read_async": (C.c_int, [_P, _P, _I64, _P, _P]),
     "isdqn_write_async": (C.c_int, [_P, _P, _I64, _P]),
     "isdqn_argmax_heads": (C.c_int, [_P, _I32, _I32, _P, _P]),
+    "isdqn_act_workspace_bytes": (_I64, [C.POINTER(Net)]),
+    "isdqn_act": (C.c_int, [C.POINTER(Net), _P, _P, _P, _P, _P, _I64, _P]),
+    "isdqn_act_host": (C.c_int, [C.POINTER(Net), _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),

@@ -383,7 +383,7 @@ bool isdqn_dense_wgrad_adam_ok(int B, int Kin, int N, int64_t w_off) {
     const char* e = getenv("ISDQN_FUSED_DENSE_ADAM");
     return !(e && e[0] == '0');
   }();
-  return on && B >= 1 && B <= 64 && Kin % 8 == 0 && N % 8 == 0 && w_off % 8 == 0;
+  return on && B >= 1 && B <= kDwaMaxB && Kin % 8 == 0 && N % 8 == 0 && w_off % 8 == 0;
 }
 int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count,
                                   float lr, float b1, float b2, float eps, void* d_shadow_bf16, int64_t n_total, int64_t w_off,
@@ -395,7 +395,7 @@ int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* 
   static const int want_ctas = [] {
     const char* e = getenv("ISDQN_DWA_CTAS");
     const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 2 * kNumSMs;
+    return v > 0 ? v : 3 * kNumSMs;
   }();
   const int gy = ceil_div(N, kDwaCols);
   const int n_tiles = ceil_div(Kin, kDwaTileRows);
@@ -406,7 +406,7 @@ int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* 
   const int64_t rest4 = (n_total - (int64_t)Kin * N) / 4;
   int rest_ctas = (int)ceil_div<int64_t>(rest4, 2 * kDwaThreads);
   if (rest_ctas > kNumSMs) rest_ctas = kNumSMs;
-  const size_t smem = (size_t)B * kDwaCols * 2 + (size_t)B * tpc * kDwaTileRows * 4;
+  const size_t smem = dwa_smem_bytes(B, tpc);
   if (smem > 100 * 1024) return ISDQN_E_UNSUPPORTED;
   static bool attr_done = false;
   if (!attr_done) {

@@ -1135,13 +1135,24 @@ dense_finalize_head_kernel(const float* __restrict__ part, int splits, int64_t s
   if (g == 0 && n < NH) out_head[(int64_t)r * NH + n] = ((hpart[0][n] + hpart[1][n]) + (hpart[2][n] + hpart[3][n])) + bh[n];
 }
 
-// 1 / (1 - b^t) for both Adam decays, evaluated in double; ONE thread per CTA runs the two pow() (a few hundred
-// dependent FP64 instructions) while the others go on, instead of every thread of the grid.
+// 1 / (1 - b^t) for both Adam decays, in double.  Two threads of different warps (the last lane of the last two warps)
+// evaluate one power each by repeated squaring (t is a positive step count: <= 62 dependent multiplications, against a
+// few hundred FP64 instructions for pow()) while the rest of the CTA goes on; the result agrees with pow() to ~1e-15
+// relative before it is rounded to float.
+__device__ __forceinline__ double pow_int(double b, int t) {
+  double r = 1.0;
+  for (unsigned e = (unsigned)max(t, 0); e; e >>= 1) {
+    if (e & 1u) r *= b;
+    b *= b;
+  }
+  return r;
+}
 __device__ __forceinline__ void adam_bias_corrections(const int32_t* count, float b1, float b2, float* s_c /*[2], shared*/) {
-  if (threadIdx.x == blockDim.x - 1) {
+  const int who = (int)blockDim.x - 1 - (int)threadIdx.x;
+  if (who == 0 || who == 32 || (who == 1 && blockDim.x <= 32)) {
     const int t = *count;
-    s_c[0] = (float)(1.0 / (1.0 - pow((double)b1, (double)t)));
-    s_c[1] = (float)(1.0 / (1.0 - pow((double)b2, (double)t)));
+    const int j = who == 0 ? 0 : 1;
+    s_c[j] = (float)(1.0 / (1.0 - pow_int((double)(j == 0 ? b1 : b2), t)));
   }
 }
 // The element update.  optax: p -= lr * (mu / c1) / (sqrt(nu / c2) + eps).  The two bias-correction divisions are
@@ -1201,16 +1212,41 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   P.c -= lr * __fdividef(M.c * c1, adam_sqrt_approx(V.c * c2) + eps);
 
 // Small-batch hidden Dense kernel (97 % of the Atari network's parameters): its gradient is the rank-B product
-// g[k][n] = sum_b act[b][k] dz[b][n] of two small bf16 matrices, so it is recomputed in registers here and fed straight
-// into the Adam update — the 4 B/param gradient is never written nor read back (26 B/param instead of 4 + 30), and the
-// separate weight-gradient launch disappears.  bf16 x bf16 products are exact in fp32; the sum runs b = 0..B-1.
-// CTA = 2 row groups x 128 column groups; a thread owns 4 kernel rows x 4 columns per tile of 8 rows (12 independent
-// 16-byte loads in flight before the product starts); every CTA takes a contiguous range of tiles so that its slice of
-// act^T is staged once (as fp32), next to dz[B][512] (bf16).  grid.x = rest CTAs + row CTAs, grid.y = ceil(N / 512);
-// the `rest` CTAs (the first ones, blockIdx.y == 0 only) run the plain Adam update of every OTHER leaf of the flat vector, so the step
-// ends with one launch.
-constexpr int kDwaThreads = 256, kDwaCols = 512, kDwaRowsPerThread = 4, kDwaTileRows = 2 * kDwaRowsPerThread;
-static __global__ void __launch_bounds__(kDwaThreads, 2)
+// g[k][n] = sum_b act[b][k] dz[b][n] of two small bf16 matrices, so it is recomputed on chip here and fed straight into
+// the Adam update — the 4 B/param gradient is never written nor read back (26 B/param instead of 4 + 30), and the
+// separate weight-gradient launch disappears.  The kernel is HBM-bound; the product is 0.25 GFLOP, so it runs on
+// warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate — the same products and accumulator type as the tcgen05 path;
+// a first version with FFMA was issue-bound at 47 % issue utilisation, ncu profiles/r01_adam_ncu.md).  Not a tcgen05
+// problem: one 16-row tile is 2 k-steps of work per warp between two streaming phases.
+// CTA (256 threads) = tiles of 16 kernel rows x 256 columns over a contiguous range of rows: dz[B][256] and its slice
+// of act^T are staged once in shared memory (bf16, padded rows: conflict-free ldmatrix), zero-filled up to a multiple
+// of 16 batch rows.  Per tile: warp w computes the 16 x 32 block of columns 32 w.. (8 MMAs), stores it to a
+// double-buffered fp32 tile in shared memory; then every thread owns 4 rows x 4 columns: 12 independent 16-byte loads
+// of p / mu / nu are issued BEFORE the barrier that publishes the gradient tile, so they are in flight while it waits.
+// grid.x = rest CTAs + row CTAs, grid.y = ceil(N / 256); the `rest` CTAs (the first ones, blockIdx.y == 0 only) run
+// the plain Adam update of every OTHER leaf of the flat vector, so the step ends with one launch.
+constexpr int kDwaThreads = 256, kDwaCols = 256, kDwaTileRows = 16, kDwaMaxB = 64;
+constexpr int kDwaLdB = kDwaCols + 8;  // bf16 elements per staged dz row
+constexpr int kDwaLdC = kDwaCols + 8;  // fp32 elements per row of the gradient tile
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+static inline size_t dwa_smem_bytes(int B, int tiles_per_cta) {
+  const int Bp = (B + 15) / 16 * 16;
+  return (size_t)Bp * kDwaLdB * 2 + (size_t)Bp * (tiles_per_cta * kDwaTileRows + 8) * 2 + 2 * (size_t)kDwaTileRows * kDwaLdC * 4;
+}
+
+static __global__ void __launch_bounds__(kDwaThreads, 3)
 dense_wgrad_adam_kernel(float* __restrict__ p_all, const float* __restrict__ g_all, float* __restrict__ mu_all,
                         float* __restrict__ nu_all, const int32_t* __restrict__ count, float lr, float b1, float b2, float eps,
                         __nv_bfloat16* __restrict__ shadow_all, int64_t w_off, int64_t n_total4,
@@ -1251,69 +1287,87 @@ dense_wgrad_adam_kernel(float* __restrict__ p_all, const float* __restrict__ g_a
   float* __restrict__ mu = mu_all + w_off;
   float* __restrict__ nu = nu_all + w_off;
   __nv_bfloat16* __restrict__ shadow = shadow_all ? shadow_all + w_off : nullptr;
+  const int Bp = (B + 15) / 16 * 16;
   const int rows_cta = tiles_per_cta * kDwaTileRows;
-  __nv_bfloat16* s_dz = reinterpret_cast<__nv_bfloat16*>(dwa_smem);                              // [B][kDwaCols] bf16
-  float* s_act = reinterpret_cast<float*>(dwa_smem + (size_t)B * kDwaCols * 2);                  // [B][rows_cta] fp32
+  const int lda_s = rows_cta + 8;  // (lda_s / 8 is odd: the 8 rows of an ldmatrix land in 8 different 16-byte banks)
+  __nv_bfloat16* s_dz = reinterpret_cast<__nv_bfloat16*>(dwa_smem);                                   // [Bp][kDwaLdB]
+  __nv_bfloat16* s_act = s_dz + (size_t)Bp * kDwaLdB;                                                 // [Bp][lda_s]
+  float* s_g = reinterpret_cast<float*>(s_act + (size_t)Bp * lda_s);                                  // [2][16][kDwaLdC]
   const int n_tiles = (Kin + kDwaTileRows - 1) / kDwaTileRows;
   const int tile0 = ((int)blockIdx.x - rest_ctas) * tiles_per_cta;
   const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
   if (tile0 >= tile1) return;
   const int col0 = blockIdx.y * kDwaCols;
   const int row0 = tile0 * kDwaTileRows;
-  for (int i = threadIdx.x; i < B * (kDwaCols / 8); i += kDwaThreads) {  // 16-byte pieces of dz (N % 8 == 0)
+  for (int i = threadIdx.x; i < Bp * (kDwaCols / 8); i += kDwaThreads) {  // 16-byte pieces of dz (N % 8 == 0)
     const int b = i / (kDwaCols / 8), c = (i - b * (kDwaCols / 8)) * 8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (col0 + c < N) v = *reinterpret_cast<const uint4*>(dz + (int64_t)b * N + col0 + c);
-    *reinterpret_cast<uint4*>(s_dz + (size_t)b * kDwaCols + c) = v;
+    if (b < B && col0 + c < N) v = *reinterpret_cast<const uint4*>(dz + (int64_t)b * N + col0 + c);
+    *reinterpret_cast<uint4*>(s_dz + (size_t)b * kDwaLdB + c) = v;
   }
-  for (int i = threadIdx.x; i < B * (rows_cta / 2); i += kDwaThreads) {  // bf16 pairs of act^T (Kin even) -> fp32
-    const int b = i / (rows_cta / 2), r = (i - b * (rows_cta / 2)) * 2;
-    uint32_t v = 0u;
-    if (row0 + r < Kin) v = *reinterpret_cast<const uint32_t*>(act + (int64_t)b * lda + row0 + r);
-    *reinterpret_cast<float2*>(s_act + (size_t)b * rows_cta + r) = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  for (int i = threadIdx.x; i < Bp * (rows_cta / 8); i += kDwaThreads) {  // 16-byte pieces of act (Kin, lda % 8 == 0)
+    const int b = i / (rows_cta / 8), r = (i - b * (rows_cta / 8)) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (b < B && row0 + r < Kin) v = *reinterpret_cast<const uint4*>(act + (int64_t)b * lda + row0 + r);
+    *reinterpret_cast<uint4*>(s_act + (size_t)b * lda_s + r) = v;
   }
   __syncthreads();
   const float c1 = s_c[0], c2 = s_c[1];
-  const int cg = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;  // this thread's 4 columns / 4 rows of a tile
   const int col = col0 + cg * 4;
-  if (col >= N) return;
+  const bool col_ok = col < N;
+  // ldmatrix row addresses (see the fragment layouts of mma.m16n8k16): lane -> matrix lane / 8, row lane % 8
+  const int lm = lane >> 3, lj = lane & 7;
+  const __nv_bfloat16* a_base = s_act + (size_t)(lj + (lm >> 1) * 8) * lda_s + (lm & 1) * 8;           // + k0 * lda_s + m0
+  const __nv_bfloat16* b_base = s_dz + (size_t)(lj + (lm & 1) * 8) * kDwaLdB + warp * 32 + (lm >> 1) * 8;  // + k0 * ld + 16 j
   for (int tile = tile0; tile < tile1; ++tile) {
-    const int r_local = (tile - tile0) * kDwaTileRows + rg * kDwaRowsPerThread;
-    const int row = row0 + r_local;
-    if (row >= Kin) break;
-    const int64_t i0 = (int64_t)row * N + col;
-    // issue the streaming loads first; the rank-B product below hides their latency.  (Rows beyond Kin: clamped loads,
-    // no stores.)
-    float4 pv[kDwaRowsPerThread], mv[kDwaRowsPerThread], vv[kDwaRowsPerThread], g[kDwaRowsPerThread];
+    const int m0 = (tile - tile0) * kDwaTileRows;
+    float* gt = s_g + (size_t)((tile - tile0) & 1) * kDwaTileRows * kDwaLdC;
+    // ---- gradient tile: 16 rows x (32 columns per warp)
+    {
+      float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < kDwaRowsPerThread; ++r) {
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      for (int k0 = 0; k0 < Bp; k0 += 16) {
+        uint32_t af[4], bf0[4], bf1[4];
+        ldmatrix_x4_trans(af, a_base + (size_t)k0 * lda_s + m0);
+        ldmatrix_x4_trans(bf0, b_base + (size_t)k0 * kDwaLdB);
+        ldmatrix_x4_trans(bf1, b_base + (size_t)k0 * kDwaLdB + 16);
+        mma_bf16_m16n8k16(acc[0], af, bf0[0], bf0[1]);
+        mma_bf16_m16n8k16(acc[1], af, bf0[2], bf0[3]);
+        mma_bf16_m16n8k16(acc[2], af, bf1[0], bf1[1]);
+        mma_bf16_m16n8k16(acc[3], af, bf1[2], bf1[3]);
+      }
+      const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float* dst = gt + (size_t)gq * kDwaLdC + warp * 32 + nt * 8 + tq * 2;
+        *reinterpret_cast<float2*>(dst) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(dst + 8 * kDwaLdC) = make_float2(acc[nt][2], acc[nt][3]);
+      }
+    }
+    // ---- streaming loads of this thread's 4 x 4 block (rows beyond Kin / columns beyond N: clamped loads, no stores)
+    const int row = row0 + m0 + rg * 4;
+    const int64_t i0 = (int64_t)min(row, Kin - 1) * N + (col_ok ? col : 0);
+    float4 pv[4], mv[4], vv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
       const int64_t i = row + r < Kin ? i0 + (int64_t)r * N : i0;
       pv[r] = *reinterpret_cast<const float4*>(p + i);
       mv[r] = *reinterpret_cast<const float4*>(mu + i);
       vv[r] = *reinterpret_cast<const float4*>(nu + i);
-      g[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll 4
-    for (int b = 0; b < B; ++b) {
-      const float4 a = *reinterpret_cast<const float4*>(s_act + (size_t)b * rows_cta + r_local);
-      const uint2 d4 = *reinterpret_cast<const uint2*>(s_dz + (size_t)b * kDwaCols + cg * 4);
-      const float dx = __uint_as_float(d4.x << 16), dy = __uint_as_float(d4.x & 0xffff0000u);
-      const float dzz = __uint_as_float(d4.y << 16), dw = __uint_as_float(d4.y & 0xffff0000u);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+    __syncthreads();  // the gradient tile is complete (and, double-buffered, nobody still reads the one written next)
 #pragma unroll
-      for (int r = 0; r < kDwaRowsPerThread; ++r) {
-        g[r].x = fmaf(av[r], dx, g[r].x);
-        g[r].y = fmaf(av[r], dy, g[r].y);
-        g[r].z = fmaf(av[r], dzz, g[r].z);
-        g[r].w = fmaf(av[r], dw, g[r].w);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < kDwaRowsPerThread; ++r) {
-      if (row + r < Kin) {
+    for (int r = 0; r < 4; ++r) {
+      if (col_ok && row + r < Kin) {
+        const float4 g = *reinterpret_cast<const float4*>(gt + (size_t)(rg * 4 + r) * kDwaLdC + cg * 4);
         const int64_t i = i0 + (int64_t)r * N;
-        ISDQN_ADAM_ELEM(g[r], mv[r], vv[r], pv[r], x) ISDQN_ADAM_ELEM(g[r], mv[r], vv[r], pv[r], y)
-        ISDQN_ADAM_ELEM(g[r], mv[r], vv[r], pv[r], z) ISDQN_ADAM_ELEM(g[r], mv[r], vv[r], pv[r], w)
+        ISDQN_ADAM_ELEM(g, mv[r], vv[r], pv[r], x) ISDQN_ADAM_ELEM(g, mv[r], vv[r], pv[r], y)
+        ISDQN_ADAM_ELEM(g, mv[r], vv[r], pv[r], z) ISDQN_ADAM_ELEM(g, mv[r], vv[r], pv[r], w)
         *reinterpret_cast<float4*>(mu + i) = mv[r];
         *reinterpret_cast<float4*>(nu + i) = vv[r];
         *reinterpret_cast<float4*>(p + i) = pv[r];

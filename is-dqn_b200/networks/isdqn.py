@@ -10,6 +10,8 @@ are the (updated in place) inputs, i.e. the arguments are donated.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .. import _lib
@@ -521,6 +523,22 @@ class iSDQN:
             }
         a["h_obs_np"][...] = obs.reshape(-1)
         cur = t.cuda.current_stream()
+        if a.get("fused") is None:
+            # the single-kernel forward (csrc/acting.cu): cnn on uint8 frames; 0 bytes = not covered, keep the layer chain
+            nb = int(lib.isdqn_act_workspace_bytes(net._net)) if net.architecture_type == "cnn" else 0
+            if os.environ.get("ISDQN_ACT_FUSED", "1") == "0":
+                nb = 0
+            a["fused"] = t.zeros(nb, dtype=t.uint8, device="cuda") if nb > 0 else False
+            if nb > 0:
+                t.cuda.current_stream().synchronize()  # the zeroed barrier words precede the first launch on any stream
+        if a["fused"] is not False:
+            _lib.check(
+                lib.isdqn_act_host(net._net, params.flat.data_ptr(), a["h_obs"].data_ptr(), ctx["state"].data_ptr(), a["nbytes"],
+                                   a["q"].data_ptr(), a["d_arg"].data_ptr(), a["h_arg"].data_ptr(), a["fused"].data_ptr(),
+                                   a["fused"].numel(), cur.cuda_stream, a["ev"]),
+                "isdqn_act_host",
+            )
+            return a["h_arg_np"]
         side = None
         if self._use_graph and cur.cuda_stream == 0:
             if self._side_stream is None:
@@ -563,6 +581,36 @@ class iSDQN:
             cur.wait_stream(side)
         _lib.check(lib.isdqn_event_synchronize(a["ev"]), "isdqn_event_synchronize")
         return a["h_arg_np"]
+
+    def best_actions(self, params: ParamTree, states, keys):
+        """Batched acting for N environments at once (new functionality, the reference acts on one
+        environment): states (N, *observation_dim) host array of the stored dtype, keys a sequence of N seeds.  Row i
+        draws its online head from keys[i] exactly like best_action(params, states[i], keys[i]) and takes that head's
+        greedy action.  One forward on N rows + the argmax of every head, one synchronisation.  Returns int32[N]."""
+        t = self._torch
+        lib = self._lib
+        net = self.network
+        states = np.ascontiguousarray(states)
+        N = int(states.shape[0])
+        heads = np.array([int(np.random.default_rng(_key_to_seed(k)).integers(self.n_bellman_iterations)) for k in keys],
+                         dtype=np.int64)
+        if heads.shape[0] != N:
+            raise ValueError("best_actions needs one key per state")
+        ctx = self._context(N)
+        nq = 1 + self.n_bellman_iterations
+        cur = t.cuda.current_stream()
+        ctx["state"].copy_(t.from_numpy(states).reshape(ctx["state"].shape), non_blocking=False)
+        if ctx["ws_tc"] is not None and (params.shadow is None or params.shadow_dirty):
+            self._refresh_shadow(params, cur.cuda_stream)
+        q = t.empty((2 * N, net.final_feature), dtype=t.float32, device="cuda")
+        d_arg = t.empty(N * nq, dtype=t.int32, device="cuda")
+        batch = _lib.Batch(ctx["state"].data_ptr(), ctx["state"].data_ptr(), ctx["action"].data_ptr(), ctx["reward"].data_ptr(),
+                           ctx["terminal"].data_ptr())
+        tr = self._train_struct(ctx, params, None, N, refresh_shadow=False)
+        _lib.check(lib.isdqn_loss_on_batch(net._net, tr, batch, q.data_ptr(), cur.cuda_stream), "isdqn_loss_on_batch")
+        _lib.check(lib.isdqn_argmax_heads(q.data_ptr(), N * nq, self.n_actions, d_arg.data_ptr(), cur.cuda_stream), "isdqn_argmax_heads")
+        greedy = d_arg.cpu().numpy().reshape(N, nq)
+        return greedy[np.arange(N), 1 + heads].astype(np.int32)
 
     def best_action_of_head(self, params: ParamTree, state, idx_network: int):
         t = self._torch
