@@ -348,6 +348,21 @@ def run_ours(args, rank, world, local_rank):
         for i in range(300):
             agent.best_action(agent.params, act_state, i).item()
         acting_us = (time.perf_counter() - t_act) / 300 * 1e6
+        t_act = time.perf_counter()
+        for i in range(300):
+            int(agent.best_action_of_head(agent.params, act_state, i % K_HEADS))
+        acting_head_us = (time.perf_counter() - t_act) / 300 * 1e6
+        act_ctx = agent._ctx[1]["act"]
+        act_fused = isinstance(act_ctx.get("fused"), torch.Tensor)
+        acting = {"us_per_action": acting_us, "us_per_action_head_given": acting_head_us,
+                  "path": "single kernel (isdqn_act_host)" if act_fused else "layer chain (CUDA graph)"}
+        if act_fused:
+            lib_ = _lib.load()
+            c1 = agent._ctx[1]
+            prof_act = _lib.profile(lambda: lib_.isdqn_act(agent.network._net, agent.params.flat.data_ptr(), c1["state"].data_ptr(),
+                                                           act_ctx["q"].data_ptr(), act_ctx["d_arg"].data_ptr(),
+                                                           act_ctx["fused"].data_ptr(), act_ctx["fused"].numel(), stream.cuda_stream))
+            acting["kernel_us"] = prof_act[0][1] * 1e3
         # ---- per-kernel profile of one step (direct launches behind a spin kernel: no launch gaps)
         agent._use_graph = False
         prof = _lib.profile(lambda: agent.update_online_params(1, rb))
@@ -452,6 +467,7 @@ def run_ours(args, rank, world, local_rank):
                    "kernels_ms": {n: t for n, t in prof_replay}},
         "replay_prioritized": prio,
         "acting_us_per_action": acting_us,
+        "acting": acting,
         "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 5)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
         "fill": {"adds": n_fill, "seconds": t_fill},
     }

@@ -634,6 +634,13 @@ class iSDQN:
         )
         return out
 
+    def load_model(self, model_or_path) -> None:
+        """Inverse of get_model: a `{"params": ...}` dict or the path of a pickle the reference's
+        save_data wrote (experiments/base/utils.py:134-135; jax-array leaves are read without jax, checkpoint.py)."""
+        from ..checkpoint import load_model
+
+        load_model(self, model_or_path)
+
     def get_model(self):
         """isdqn.py:137-138: `{"params": params}` with host numpy leaves (pickle-able, flax-shaped)."""
         return {
