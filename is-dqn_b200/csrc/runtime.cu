@@ -264,10 +264,13 @@ extern "C" int isdqn_dp_destroy(void* comm) {
 int isdqn_trace_set_learner(unsigned long long* buf);
 int isdqn_trace_set_tc(unsigned long long* buf);
 int isdqn_trace_set_acting(unsigned long long* buf);
+int isdqn_trace_set_adam_stream(unsigned long long* buf);
 extern "C" int isdqn_trace_set(void* d_buf) {
   int rc = isdqn_trace_set_learner(reinterpret_cast<unsigned long long*>(d_buf));
   if (rc) return rc;
   rc = isdqn_trace_set_acting(reinterpret_cast<unsigned long long*>(d_buf));
+  if (rc) return rc;
+  rc = isdqn_trace_set_adam_stream(reinterpret_cast<unsigned long long*>(d_buf));
   if (rc) return rc;
   return isdqn_trace_set_tc(reinterpret_cast<unsigned long long*>(d_buf));
 }

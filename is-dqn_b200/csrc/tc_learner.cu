@@ -16,6 +16,10 @@ int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* 
                                   float lr, float b1, float b2, float eps, void* d_shadow_bf16, int64_t n_total, int64_t w_off,
                                   const void* d_act_bf16, int64_t lda, const void* d_dz_bf16, int B, int Kin, int N,
                                   void* stream);
+int isdqn_dense_wgrad_adam_stream_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count,
+                                         float lr, float b1, float b2, float eps, void* d_shadow_bf16, int64_t n_total,
+                                         int64_t w_off, const void* d_act_bf16, int64_t lda, const void* d_dz_bf16, int B,
+                                         int Kin, int N, void* stream);
 int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
                       float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream, int64_t skip_begin,
                       int64_t skip_len, int max_ctas = 0);
@@ -988,6 +992,11 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   }
   if (fused_l >= 0) {  // the Dense kernel from its recomputed gradient + every other leaf from `grads`: one launch
     const Layer& L = p.L[fused_l];
+    // the bulk-copy pipelined version first (adam_stream.cu); shapes it does not take go to the per-thread-load kernel
+    rc = isdqn_dense_wgrad_adam_stream_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2,
+                                              tr->eps, shadow, p.layout.total, L.w_off, w16(wt, t.act16[fused_l - 1]), L.in_dim,
+                                              w16(wt, t.dz16[fused_l]), B, L.in_dim, L.out_dim, stream);
+    if (rc != ISDQN_E_UNSUPPORTED) return rc;
     return isdqn_dense_wgrad_adam_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2,
                                          tr->eps, shadow, p.layout.total, L.w_off, w16(wt, t.act16[fused_l - 1]), L.in_dim,
                                          w16(wt, t.dz16[fused_l]), B, L.in_dim, L.out_dim, stream);

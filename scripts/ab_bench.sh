@@ -17,3 +17,15 @@ for spec in sys.argv[1:]:
     except Exception as e:
         print(n, "ERR", e)
 PY
+python - "$@" <<'PY'
+import json, sys
+for spec in sys.argv[1:]:
+    n = spec.split("=")[0]
+    try:
+        d = json.loads(open("gpurun_out/ab_%s.json" % n).read().strip().splitlines()[-1])
+        ig = d.get("in_graph_us")
+        if ig:
+            print(n, "in-graph sum", round(sum(t for _, t in ig), 1), " ".join("%s:%.1f" % (k.replace("tc_", "")[:10], t) for k, t in ig))
+    except Exception as e:
+        print(n, "ERR", e)
+PY
