@@ -174,7 +174,7 @@ def workload_config(capacity):
 # ------------------------------------------------------------------------------------------------ CUDA arm
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the step
 # (profiles/r01_b32_step_ncu.md; cold caches: the fp32 reads all come from DRAM, most writes are still in L2 at the end)
-NCU_TRAFFIC_BYTES = {"adam": 67_726_848}
+NCU_TRAFFIC_BYTES = {"adam": 67_726_848, "dense_wgrad_adam": 53_222_400}
 
 
 DENSE0 = 7744 * 512  # the hidden Dense kernel (11*11*64 -> 512)
