@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libisdqn_b200.so")
+# (ISDQN_LIB: another build of the same library, e.g. an experiment variant next to the default one)
+LIB_PATH = os.environ.get("ISDQN_LIB") or os.path.join(_HERE, "lib", "libisdqn_b200.so")
 
 ABI_VERSION = 1
 MAX_FEATURES = 8

@@ -49,8 +49,9 @@ cudaEvent_t side_event(int i);
 // is visible.  Every kernel launched through launch_pdl calls pdl_sync() (or trigger + wait) before it touches global
 // memory, so the chain keeps full stream-order semantics (completion is transitive: a grid cannot complete before
 // the grids it waited on).  A kernel that allocates TMEM triggers only AFTER its allocation (a dependent that grabbed
-// the columns first would wait on a grid that waits on it).  Opt-in with ISDQN_PDL=1 (measured slower at batch 32:
-// early-resident dependents compete with the running kernel); the instructions are no-ops without the attribute.
+// the columns first would wait on a grid that waits on it).  On by default since the TMA-fed kernels (ISDQN_PDL=0
+// switches it off; with the LDGSTS-era kernels it had measured 5 % slower); the instructions are no-ops without the
+// attribute.
 bool pdl_enabled();
 
 // Optional device-side timeline (isdqn_trace_set): CTA (0,0,0) of every step kernel appends its start time (globaltimer,
@@ -75,10 +76,27 @@ __device__ __forceinline__ void trace_kernel_start() {
 }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ISDQN_PDL_LATE = 1 (default): trigger AFTER the wait, so that only the direct successor of the running kernel is
+// resident early instead of the whole chain cascading onto the SMs; 0 = trigger first (the earlier placement).  Both
+// measured 141.5-142.1 us per batch-32 step against 149.5-156 us without PDL (profiles/r01_summary.md).
+#ifndef ISDQN_PDL_LATE
+#define ISDQN_PDL_LATE 1
+#endif
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  pdl_wait();
+#if ISDQN_PDL_LATE
+  pdl_trigger();
+#endif
+}
 __device__ __forceinline__ void pdl_sync() {
   trace_kernel_start();
+#if ISDQN_PDL_LATE
+  pdl_wait();
+  pdl_trigger();
+#else
   pdl_trigger();
   pdl_wait();
+#endif
 }
 
 // Experiment (ISDQN_CARVEOUT=1): give every kernel of the step the same (maximum) shared-memory carve-out so that the

@@ -37,8 +37,9 @@ void prefer_max_shared_once(const void* kernel) {
 
 bool pdl_enabled() {
   static const bool on = [] {
-    const char* e = getenv("ISDQN_PDL");  // opt-in: measured 5 % SLOWER on the batch-32 step (profiles/r01_summary.md)
-    return e && e[0] == '1';
+    // on by default: 141.7 vs 150.9 us per batch-32 step on the same box (profiles/r01_summary.md); ISDQN_PDL=0 disables
+    const char* e = getenv("ISDQN_PDL");
+    return !(e && e[0] == '0');
   }();
   return on;
 }

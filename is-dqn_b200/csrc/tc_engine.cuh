@@ -284,7 +284,9 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
   tcgen05_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
   if (tid == 0) trace_mark(1);  // prologue done (barriers, TMEM)
+#if !ISDQN_PDL_LATE
   pdl_trigger();  // (after the TMEM allocation: see common.cuh)
+#endif
 
   if (warp >= kFirstProducerWarp) {
    if constexpr (uses_tma<P>::value) {
@@ -293,7 +295,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
     // problem's tensor-map copies, which land swizzled exactly as the MMA descriptors expect and bypass the LSU.
     if (warp == kFirstProducerWarp && lane == 0) {
       p.tma_prefetch();
-      pdl_wait();
+      pdl_wait_then_trigger();
       int j = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
@@ -315,7 +317,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
     // ------------------------------------------------------------------------------------------ producers
     const int ptid = tid - 32 * kFirstProducerWarp;
     p.init_cta(extra_sm, ptid);  // index tables from the kernel arguments only: overlaps the previous kernel's tail
-    pdl_wait();
+    pdl_wait_then_trigger();
     named_bar_sync(1, PT);
     typename P::PCtx ctx;
     int j = 0;  // chunk counter of this CTA (stage = j % STAGES)
@@ -382,7 +384,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
     // -------------------------------------------------------------------------------------------- epilogue
     typename P::ECtx ectx;
     int ti = 0;
-    pdl_wait();
+    pdl_wait_then_trigger();
     if (P::EP_FLOATS > 0) {  // per-channel epilogue parameters -> shared memory, once per CTA, while the first tile is gathered
       p.init_epilogue(ectx, ep_sm, tid);
       named_bar_sync(2, 32 * kEpilogueWarps);
