@@ -64,7 +64,19 @@ dense_wgrad_adam_stream_kernel(float* __restrict__ p_all, const float* __restric
                                float eps, __nv_bfloat16* __restrict__ shadow_all, int64_t w_off, int64_t n_total4,
                                const __nv_bfloat16* __restrict__ act, int64_t lda, const __nv_bfloat16* __restrict__ dz, int B,
                                int Kin, int N, int stages) {
+  // Programmatic dependent launch: this kernel's predecessor is the partial reduction, which only produces `g_all` —
+  // the gradients of the OTHER leaves.  p / mu / nu / shadow of the Dense kernel, dz, act and the step counter were all
+  // written by grids that completed before the predecessor even started (every kernel of the chain waits for its own
+  // predecessor), and the predecessor touches none of them.  So the tile pipeline starts at once, under the
+  // predecessor's execution; only the consumers' rest-leaf phase at the end waits (griddepcontrol.wait) for `g_all`.
+#ifndef ISDQN_ADAM_EARLY
+#define ISDQN_ADAM_EARLY 1  // 0: wait for the predecessor at the top like every other kernel (A/B builds)
+#endif
+#if ISDQN_ADAM_EARLY
+  trace_kernel_start();
+#else
   pdl_sync();
+#endif
   extern __shared__ __align__(128) unsigned char tp_smem[];
   __shared__ float s_c[2];
   const int Bp = (B + 15) / 16 * 16;
@@ -204,6 +216,10 @@ dense_wgrad_adam_stream_kernel(float* __restrict__ p_all, const float* __restric
     named_bar_sync(1, kTpConsumers);  // everybody has read the gradient tile: the next one may be written
   }
   // ---- every other leaf: the plain update over [0, n_total4) minus the Dense kernel's range
+#if ISDQN_ADAM_EARLY
+  pdl_wait();     // the predecessor's gradients are complete and visible
+  pdl_trigger();  // (the successor may start its prologue; it waits for this grid's completion before it reads anything)
+#endif
   {
     const int64_t skip_begin4 = w_off / 4, skip_len4 = (int64_t)Kin * N / 4;
     const int64_t n4 = n_total4 - skip_len4;
