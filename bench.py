@@ -152,7 +152,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "iS-DQN K=9 learner updates/sec", "value": ups, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(20_000),
+        # the arm's config is OUR arm's (same workload); what the CPU actually ran — a bounded sample — is in cpu_baseline
+        "config": workload_config(args.capacity),
         "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
