@@ -4,9 +4,9 @@ The reference saves `agent.get_model()` = `{"params": {"params": {"Conv_0": {"ke
 {"scale", "bias"}, ..., "Dense_1": {...}}}}` with `pickle.dump` (experiments/base/utils.py:123-135, isdqn.py:137-138).
 Its leaves are `jax.Array`s, whose pickle stream calls `jax._src.array._reconstruct_array(fun, args, arr_state,
 aval_state)` — i.e. NumPy's own reconstruction triple plus a device_put.  `load_model_pickle` reads such a file WITHOUT
-jax by resolving exactly that global to a NumPy-only stand-in (every other global outside numpy / builtins / collections
-is refused: a checkpoint is data, not code), and also reads pickles whose leaves already are NumPy arrays
-(`jax.device_get`, or this package's `save_model`).
+jax by resolving exactly that global to a NumPy-only stand-in (every other global is refused except NumPy's own array /
+dtype / scalar reconstruction and plain containers: a checkpoint is data, not code), and also reads pickles whose leaves
+already are NumPy arrays (`jax.device_get`, or this package's `save_model`).
 
 `agent_state` / `load_agent_state` are the resume format the reference lacks (it saves parameters only): parameters,
 both Adam moments, the step counter and the per-head loss sums, as one `.npz`.
@@ -19,7 +19,11 @@ from typing import Any, Dict
 
 import numpy as np
 
-_ALLOWED_PREFIXES = ("numpy", "collections", "builtins", "flax.core.frozen_dict")
+# what a parameter checkpoint legitimately refers to: NumPy's array / dtype / scalar reconstruction and plain containers
+_NUMPY_NAMES = {"_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"}
+_BUILTIN_NAMES = {"dict", "list", "tuple", "set", "frozenset", "int", "float", "complex", "bool", "str", "bytes", "bytearray",
+                  "slice", "range"}
+_COLLECTIONS_NAMES = {"OrderedDict", "defaultdict"}
 
 
 def _reconstruct_array(fun, args, arr_state, aval_state=None):
@@ -43,7 +47,11 @@ class _CheckpointUnpickler(pickle.Unpickler):
             return _reconstruct_array
         if module == "flax.core.frozen_dict" and name == "FrozenDict":
             return _FrozenDictStandIn
-        if module.split(".")[0] in ("numpy", "collections", "builtins") or module.startswith("numpy"):
+        if (module == "numpy" or module.startswith("numpy.")) and name in _NUMPY_NAMES:
+            return super().find_class(module, name)
+        if module == "builtins" and name in _BUILTIN_NAMES:
+            return super().find_class(module, name)
+        if module == "collections" and name in _COLLECTIONS_NAMES:
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"checkpoint refers to {module}.{name}: only numpy / jax-array leaves are accepted")
 

@@ -70,6 +70,14 @@ def test_reference_pickle_with_jax_leaves_loads_without_jax():
             assert np.array_equal(leaves[m][l], v)
 
 
+def test_numpy_scalars_and_dtypes_round_trip():
+    model = {"params": {"params": {"Dense_0": {"kernel": np.arange(6, dtype=np.float16).reshape(2, 3), "bias": np.float32(1.5)}}},
+             "step": np.int64(7)}
+    got = ck.load_model_pickle(pickle.dumps(model))
+    assert got["step"] == 7 and got["params"]["params"]["Dense_0"]["bias"] == np.float32(1.5)
+    assert got["params"]["params"]["Dense_0"]["kernel"].dtype == np.float16
+
+
 def test_numpy_pickle_and_file_path(tmp_path):
     tree = _tree(1)
     path = tmp_path / "model"
@@ -91,6 +99,20 @@ def test_code_in_a_checkpoint_is_refused():
 
     with pytest.raises(pickle.UnpicklingError):
         ck.load_model_pickle(pickle.dumps({"params": {"params": {"Dense_0": {"kernel": Evil()}}}}))
+
+    class EvilBuiltin:  # builtins.eval is as much code as os.system
+        def __reduce__(self):
+            return eval, ("1 + 1",)
+
+    with pytest.raises(pickle.UnpicklingError):
+        ck.load_model_pickle(pickle.dumps({"params": EvilBuiltin()}))
+
+    class EvilNumpy:  # so is anything in numpy that is not array reconstruction
+        def __reduce__(self):
+            return np.load, ("/etc/passwd",)
+
+    with pytest.raises(pickle.UnpicklingError):
+        ck.load_model_pickle(pickle.dumps({"params": EvilNumpy()}))
 
 
 def test_mismatches_are_listed():
