@@ -142,3 +142,71 @@ def test_fc_architecture_config1_shapes():
     batch = L.make_batch(0, 32, (8,), A, "fc")
     loss, losses, q, _ = L.loss_on_batch(p, batch, "fc", False, K, A, 0.99, 1)
     assert q.shape == (64, 1 + K, A) and losses.shape == (K,) and torch.isfinite(loss)
+
+
+# ---- second opinions (CPU): the restatement against INDEPENDENT implementations of the same operators.  The learner
+# oracle cannot be pinned on the reference itself (jax / flax / optax are not installable here); these
+# tests pin each building block on PyTorch's own kernels instead, which share no code with the restatement.
+def test_adam_matches_torch_optim_adam():
+    """optax.adam(lr, eps) and torch.optim.Adam use the same update (eps outside the square root, bias corrections on
+    both moments): five steps on random gradients, including exact zeros."""
+    g0 = torch.Generator().manual_seed(5)
+    w0 = torch.randn(64, generator=g0, dtype=torch.float64)
+    p = {"m": {"w": w0.clone()}}
+    mu, nu = L.zeros_like_params(p), L.zeros_like_params(p)
+    tw = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.Adam([tw], lr=6.25e-5, betas=(0.9, 0.999), eps=1.5e-4)
+    count = 0
+    for step in range(5):
+        g = torch.randn(64, generator=g0, dtype=torch.float64) * 10.0 ** (step - 3)
+        g[::7] = 0.0
+        count = L.adam_step(p, {"m": {"w": g}}, mu, nu, count, 6.25e-5, 1.5e-4)
+        tw.grad = g.clone()
+        opt.step()
+        assert torch.allclose(p["m"]["w"], tw.detach(), rtol=1e-12, atol=1e-15), step
+
+
+def test_layer_norm_matches_torch_layer_norm():
+    """flax's fast variance E[x^2] - E[x]^2 against F.layer_norm's two-pass statistics, float64."""
+    import torch.nn.functional as F
+
+    g0 = torch.Generator().manual_seed(6)
+    for shape in ((5, 21, 21, 32), (3, 512), (2, 11, 11, 64)):
+        x = torch.randn(shape, generator=g0, dtype=torch.float64) * 3 + 0.7
+        scale = torch.randn(shape[-1], generator=g0, dtype=torch.float64)
+        bias = torch.randn(shape[-1], generator=g0, dtype=torch.float64)
+        got = L.layer_norm_lastdim(x, scale, bias)
+        want = F.layer_norm(x, (shape[-1],), scale, bias, eps=1e-6)
+        assert torch.allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+def test_same_padded_conv_matches_an_unfold_matmul():
+    """The oracle's SAME-padded convolution (F.conv2d on an explicitly padded image, HWIO kernel) against a convolution
+    written as im2col + matmul with its own index arithmetic (the form the CUDA kernels implement)."""
+    g0 = torch.Generator().manual_seed(7)
+    x = torch.randint(0, 256, (2, 84, 84, 4), generator=g0, dtype=torch.uint8)
+    p = L.init_params(3, "cnn", (84, 84, 4), [8, 16, 16, 32], 6, False)
+    taps = []
+    L.forward(p, x, "cnn", False, 2, 3, taps=taps)  # taps[i] = pre-ReLU output of conv i (NHWC)
+    act = x.double() / 255.0
+    for i, (k, s) in enumerate(L.CONV_GEOMETRY):
+        w = p[f"Conv_{i}"]["kernel"]  # [kh][kw][cin][cout]
+        n, H, W, C = act.shape
+        OH, OW = -(-H // s), -(-W // s)
+        pad_h = max((OH - 1) * s + k - H, 0)
+        pad_w = max((OW - 1) * s + k - W, 0)
+        lo_h, lo_w = pad_h // 2, pad_w // 2
+        cols = torch.zeros(n, OH, OW, k, k, C, dtype=torch.float64)
+        for ky in range(k):
+            for kx in range(k):
+                for oy in range(OH):
+                    iy = oy * s - lo_h + ky
+                    if not 0 <= iy < H:
+                        continue
+                    ix = torch.arange(OW) * s - lo_w + kx
+                    ok = (ix >= 0) & (ix < W)
+                    cols[:, oy, ok, ky, kx, :] = act[:, iy, ix[ok], :]
+        z = cols.reshape(n, OH, OW, k * k * C) @ w.reshape(k * k * C, -1) + p[f"Conv_{i}"]["bias"]
+        assert z.shape == taps[i].shape
+        assert torch.allclose(z, taps[i], rtol=1e-10, atol=1e-12), i
+        act = torch.relu(z)
