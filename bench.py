@@ -441,10 +441,9 @@ def run_ours(args, rank, world, local_rank):
             roofline_kernels.append({"kernel": name, "launches": cnt, "ms": round(tot_ms, 5), "bound": "hbm",
                                      "achieved": a2, "unit": "GB/s", "frac": a2 / peaks["hbm_gbs"]})
     gather_gbs = 91_728 * n_big / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else None
-    cpu = None
-    if world == 1 or True:
-        ups, done, cores, desc, _ = cpu_reference_steps(10**9, 2, time_budget_s=args.cpu_seconds)
-        cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc}
+    # host-CPU baseline (rank 0 only: the other ranks have returned above), a bounded sample of the same workload
+    ups, done, cores, desc, _ = cpu_reference_steps(10**9, 2, time_budget_s=args.cpu_seconds)
+    cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc}
     line = {
         "metric": "iS-DQN K=9 learner updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
