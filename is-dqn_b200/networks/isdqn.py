@@ -20,7 +20,10 @@ from .architectures.dqn import DQNNet, ParamTree
 
 
 def _key_to_seed(key) -> np.random.SeedSequence:
-    return np.random.SeedSequence(np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8).tolist() or [0])
+    """One 32-bit entropy word per byte of the key (what `SeedSequence(list_of_bytes)` builds, without the per-element
+    Python loop of that path: 2x cheaper, same pool — tests/test_key_seed.py)."""
+    b = np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8)
+    return np.random.SeedSequence(b.astype(np.uint32) if b.size else [0])
 
 
 def _new_event(lib):
