@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ISDQN_ABI_VERSION 1
+#define ISDQN_ABI_VERSION 2
 
 /* return codes */
 #define ISDQN_OK 0
@@ -44,6 +44,7 @@ extern "C" {
 #define ISDQN_ST_EMPTY_TREE 8u       /* samplers.py:106 root == 0.0 */
 #define ISDQN_ST_INDEX_RANGE 16u      /* leaf index outside the heap (NumPy would raise IndexError / wrap) */
 #define ISDQN_ST_OP_TOO_LARGE 32u     /* an op of isdqn_sumtree_set_ops exceeds ISDQN_SUMTREE_OP_MAX */
+#define ISDQN_ST_KEY_MISSING 64u      /* samplers.py:84 `self._key_to_index[key]` would raise KeyError */
 
 int isdqn_abi_version(void);
 const char* isdqn_strerror(int code);
@@ -70,13 +71,29 @@ int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_index, const 
 /* A queue of `n_ops` sets applied strictly in order by one launch: op j covers entries
  * [d_op_offset[j], d_op_offset[j+1]) of d_index/d_value, each op at most ISDQN_SUMTREE_OP_MAX entries.
  * In this entry point only, a value -(1+j) means "the value leaf j holds when the op starts" (the swap-remove
- * of samplers.py:99-102 without a device->host read).
+ * of samplers.py:99-102 without a device->host read) and ISDQN_SUMTREE_TAG_MAX means "max_recorded_priority as it
+ * is when the op starts" (a prioritized training loop inserts new transitions at that priority).
  * replaces: the per-transition SumTree.set calls of PrioritizedSamplingDistribution.add / .remove
  * (samplers.py:67-74, 90-103), which the reference issues one NumPy call at a time. */
 #define ISDQN_SUMTREE_OP_MAX 1024
+#define ISDQN_SUMTREE_TAG_MAX (-0.5)
 int isdqn_sumtree_set_ops(double* d_nodes, int depth, const int32_t* d_op_offset, int32_t n_ops,
                           const int32_t* d_index, const double* d_value, double* d_max_priority,
                           uint32_t* d_status, void* stream);
+
+/* replaces: PrioritizedSamplingDistribution.update  samplers.py:76-88 (+ ReplayBuffer.update, replay_buffer.py:215-220)
+ * for keys and priorities that already live on the device (the |TD| of the step that just ran): index =
+ * d_key_slot_to_index[key mod n_slots] (device mirror of `_key_to_index`, verified against d_index_to_key), value =
+ * (priority + prio_offset) ** alpha (0 stays 0; alpha == 1 is exact, otherwise CUDA's pow; prio_offset is the usual
+ * small constant that keeps a zero TD error drawable, 0 for the reference's semantics), then one isdqn_sumtree_set.
+ * prio_kind: 0 = float64 [n]; 1 = float32 [n]; 2 = float32 [prio_rows][n], averaged over the rows (the per-head |TD| matrix
+ * of isdqn_train.d_td_abs).  A key that is not live sets ISDQN_ST_KEY_MISSING and leaves the tree untouched.  n <= 1024.
+ * d_workspace: isdqn_sumtree_set_keys_workspace_bytes(n) bytes of device scratch. */
+int64_t isdqn_sumtree_set_keys_workspace_bytes(int32_t n);
+int isdqn_sumtree_set_keys(double* d_nodes, int depth, const int32_t* d_keys, const void* d_priorities, int32_t prio_kind,
+                           int32_t prio_rows, int32_t n, double prio_offset, double alpha, const int32_t* d_key_slot_to_index, int32_t n_slots,
+                           const int32_t* d_index_to_key, int32_t n_valid, double* d_max_priority, uint32_t* d_status,
+                           void* d_workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ samplers
  * d_rng: 6 x uint64 mirror of numpy's PCG64 state:
@@ -100,10 +117,14 @@ int isdqn_sample_uniform_ws(uint64_t* d_rng, int32_t n_valid, int32_t size, cons
 
 /* replaces: PrioritizedSamplingDistribution.sample  samplers.py:105-116 (+ SumTree.query).
  * targets = Generator.uniform(0.0, root, size) with root read on the device, then the descent of
- * isdqn_sumtree_query.  d_out_target may be NULL.  Sets ISDQN_ST_EMPTY_TREE when root == 0. */
-int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size,
+ * isdqn_sumtree_query.  d_out_target / d_out_prob may be NULL; d_out_prob[i] = leaf priority / root, the probability
+ * the draw had (importance weights).  Sets ISDQN_ST_EMPTY_TREE when root == 0.  n_valid = number of live dense
+ * indices: a descent that ends at or beyond it (empty tree, or a rounding that lands on a zero leaf — the reference's
+ * `self._index_to_key[index]` raises IndexError there) sets ISDQN_ST_INDEX_RANGE and yields a live key instead, so the
+ * slots handed to the gather are always valid; n_valid < 0 skips the check. */
+int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size, int32_t n_valid,
                              const int32_t* d_index_to_key, int32_t capacity, int32_t* d_out_index,
-                             int32_t* d_out_key, int32_t* d_out_slot, double* d_out_target,
+                             int32_t* d_out_key, int32_t* d_out_slot, double* d_out_target, double* d_out_prob,
                              uint32_t* d_status, void* stream);
 
 /* Scatter of host-accumulated patches into a device int32 table (index_to_key, element metadata):
@@ -178,6 +199,11 @@ int isdqn_forward(const isdqn_net* net, const float* d_params, const void* d_inp
 int isdqn_heads_td_loss(const float* d_q_all, const int64_t* d_action, const double* d_reward,
                         const uint8_t* d_terminal, float gamma_n, int32_t batch, int32_t batch_global,
                         int32_t n_heads, int32_t n_actions, float* d_losses, float* d_dq, void* stream);
+/* the same with the prioritized-replay extras of isdqn_train (either may be NULL) */
+int isdqn_heads_td_loss_weighted(const float* d_q_all, const int64_t* d_action, const double* d_reward,
+                                 const uint8_t* d_terminal, float gamma_n, int32_t batch, int32_t batch_global,
+                                 int32_t n_heads, int32_t n_actions, const float* d_is_weights, float* d_losses,
+                                 float* d_dq, float* d_td_abs, void* stream);
 
 /* replaces: optax.adam(lr, eps).update + optax.apply_updates  isdqn.py:46,85-86 (optax 0.2.4 semantics:
  * eps outside the sqrt, bias correction with count+1).  *d_count is incremented on the device. */
@@ -217,6 +243,9 @@ typedef struct isdqn_train {
                             /* outside isdqn_learn_on_batch since the last call)                                          */
   double* d_cumulated;      /* NULL, or [K]: isdqn_learn_on_batch also does d_cumulated[k] += d_losses[k] (the                */
                             /* `self.cumulated_losses += losses` of isdqn.py:62, kept on the device)                        */
+  /* prioritized training driver (new functionality: the reference never wires its prioritized sampler to an agent) */
+  const float* d_is_weights; /* NULL, or [B] importance weights: losses[k] = mean_b w_b td^2 (gradient scaled alike)        */
+  float* d_td_abs;           /* NULL, or [K][B]: |td| of every online head and sample (isdqn_sumtree_set_keys, prio_kind 2)    */
 } isdqn_train;
 #define ISDQN_COMPUTE_F32 0
 #define ISDQN_COMPUTE_BF16 1

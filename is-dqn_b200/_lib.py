@@ -9,11 +9,13 @@ import ctypes as C
 import os
 from typing import Optional
 
+import numpy as np
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # (ISDQN_LIB: another build of the same library, e.g. an experiment variant next to the default one)
 LIB_PATH = os.environ.get("ISDQN_LIB") or os.path.join(_HERE, "lib", "libisdqn_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_FEATURES = 8
 MAX_LEAVES = 48
 SUMTREE_SET_MAX = 8192
@@ -25,6 +27,8 @@ ST_DESCENT_ASSERT = 4
 ST_EMPTY_TREE = 8
 ST_INDEX_RANGE = 16
 ST_OP_TOO_LARGE = 32
+ST_KEY_MISSING = 64
+SUMTREE_TAG_MAX = -0.5
 
 OUT_RAW, OUT_F32, OUT_BF16 = 0, 1, 2
 ARCH_CNN, ARCH_FC = 0, 1
@@ -92,6 +96,8 @@ class Train(C.Structure):
         ("d_params_bf16", C.c_void_p),
         ("refresh_shadow", C.c_int32),
         ("d_cumulated", C.c_void_p),
+        ("d_is_weights", C.c_void_p),
+        ("d_td_abs", C.c_void_p),
     ]
 
 
@@ -109,7 +115,9 @@ PROTOTYPES = {
     "isdqn_sumtree_set": (C.c_int, [_P, C.c_int, _P, _P, _I32, _P, _P, _P]),
     "isdqn_sumtree_set_ops": (C.c_int, [_P, C.c_int, _P, _I32, _P, _P, _P, _P, _P]),
     "isdqn_sample_uniform": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
-    "isdqn_sample_prioritized": (C.c_int, [_P, _P, C.c_int, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "isdqn_sample_prioritized": (C.c_int, [_P, _P, C.c_int, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "isdqn_sumtree_set_keys_workspace_bytes": (_I64, [_I32]),
+    "isdqn_sumtree_set_keys": (C.c_int, [_P, C.c_int, _P, _P, _I32, _I32, _I32, C.c_double, C.c_double, _P, _I32, _P, _I32, _P, _P, _P, _I64, _P]),
     "isdqn_scatter_rows_i32": (C.c_int, [_P, _I32, _P, _P, _I32, _P]),
     "isdqn_scatter_rows_f64": (C.c_int, [_P, _P, _P, _I32, _P]),
     "isdqn_gather_stacks": (
@@ -124,6 +132,7 @@ PROTOTYPES = {
     "isdqn_tc_gemm_bf16": (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I32, _I32, _I32, _I32, _P]),
     "isdqn_forward": (C.c_int, [C.POINTER(Net), _P, _P, _I32, _I32, _P, _P, _I64, _P]),
     "isdqn_heads_td_loss": (C.c_int, [_P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "isdqn_heads_td_loss_weighted": (C.c_int, [_P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "isdqn_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
     "isdqn_adam_step_nocount": (C.c_int, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
     "isdqn_shift_heads": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
@@ -273,3 +282,62 @@ def pinned_pack_base(arrays, offs) -> Optional[int]:
         return base if off + nb <= blk[1] else None
     except AttributeError:
         return None
+
+
+class PinnedStager:
+    """Small host arrays -> device with ONE asynchronous copy from pinned memory (instead of one synchronous pageable copy
+    per array): a ring of `slots` (pinned block, device block) pairs.  The device views `put` returns stay valid until the
+    same slot comes round again (`slots` - 1 further calls); consumers must be enqueued on the stream `put` was called on."""
+
+    def __init__(self, nbytes: int = 1 << 16, slots: int = 4):
+        self._torch = require_cuda()
+        self._n = 0
+        self._slots = slots
+        self._i = 0
+        self._host, self._dev, self._ev = [], [], []
+        self._grow(nbytes)
+
+    def _grow(self, nbytes: int) -> None:
+        t = self._torch
+        for ev in self._ev:
+            ev.synchronize()
+        self._n = max(int(nbytes), 2 * self._n)
+        self._host = [t.empty(self._n, dtype=t.uint8).pin_memory() for _ in range(self._slots)]
+        self._host_np = [h.numpy() for h in self._host]
+        self._dev = [t.empty(self._n, dtype=t.uint8, device="cuda") for _ in range(self._slots)]
+        self._ev = [t.cuda.Event() for _ in range(self._slots)]
+
+    def put(self, *arrays):
+        t = self._torch
+        offs, o = [], 0
+        for a in arrays:
+            offs.append(o)
+            o = (o + a.nbytes + 15) // 16 * 16
+        if o > self._n:
+            self._grow(o)
+        s = self._i
+        self._i = (s + 1) % self._slots
+        self._ev[s].synchronize()  # the previous copy out of this pinned block has completed
+        h = self._host_np[s]
+        for a, off in zip(arrays, offs):
+            h[off : off + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+        self._dev[s][:o].copy_(self._host[s][:o], non_blocking=True)
+        self._ev[s].record()
+        d = self._dev[s]
+        return [d[off : off + a.nbytes].view(_TORCH_DTYPES[a.dtype.str]()) for a, off in zip(arrays, offs)]
+
+
+def _torch_dtype(name):
+    def get():
+        import torch
+
+        return getattr(torch, name)
+
+    return get
+
+
+_TORCH_DTYPES = {
+    np.dtype(np.int32).str: _torch_dtype("int32"), np.dtype(np.int64).str: _torch_dtype("int64"),
+    np.dtype(np.float64).str: _torch_dtype("float64"), np.dtype(np.float32).str: _torch_dtype("float32"),
+    np.dtype(np.uint8).str: _torch_dtype("uint8"),
+}

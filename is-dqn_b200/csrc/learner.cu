@@ -142,7 +142,8 @@ int run_loss(const Plan& p, const isdqn_net* net, const isdqn_train* tr, const i
   ISDQN_PROF(s, "heads_td_loss");
   heads_td_loss_kernel<<<net->n_heads, kLossThreads, 0, s>>>(q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n,
                                                   tr->batch, tr->batch_global, net->n_heads, net->n_actions,
-                                                  tr->d_losses, dq, dbias, count, count ? tr->d_cumulated : nullptr);
+                                                  tr->d_losses, dq, dbias, count, count ? tr->d_cumulated : nullptr,
+                                                  tr->d_is_weights, tr->d_td_abs);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -340,18 +341,26 @@ extern "C" int isdqn_forward(const isdqn_net* net, const float* d_params, const 
   return ISDQN_OK;
 }
 
-extern "C" int isdqn_heads_td_loss(const float* d_q_all, const int64_t* d_action, const double* d_reward,
-                                   const uint8_t* d_terminal, float gamma_n, int32_t batch, int32_t batch_global,
-                                   int32_t n_heads, int32_t n_actions, float* d_losses, float* d_dq, void* stream) {
+extern "C" int isdqn_heads_td_loss_weighted(const float* d_q_all, const int64_t* d_action, const double* d_reward,
+                                            const uint8_t* d_terminal, float gamma_n, int32_t batch, int32_t batch_global,
+                                            int32_t n_heads, int32_t n_actions, const float* d_is_weights, float* d_losses,
+                                            float* d_dq, float* d_td_abs, void* stream) {
   if (!d_q_all || !d_action || !d_reward || !d_terminal || !d_losses || batch < 1 || batch_global < batch ||
       n_heads < 1 || n_actions < 1)
     return ISDQN_E_INVALID;
   if (n_heads > kMaxHeads || n_actions > kMaxActions) return ISDQN_E_TOO_LARGE;
   heads_td_loss_kernel<<<n_heads, kLossThreads, 0, as_stream(stream)>>>(d_q_all, d_action, d_reward, d_terminal, gamma_n, batch,
                                                                   batch_global, n_heads, n_actions, d_losses, d_dq,
-                                                                  nullptr, nullptr);
+                                                                  nullptr, nullptr, nullptr, d_is_weights, d_td_abs);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
+}
+
+extern "C" int isdqn_heads_td_loss(const float* d_q_all, const int64_t* d_action, const double* d_reward,
+                                   const uint8_t* d_terminal, float gamma_n, int32_t batch, int32_t batch_global,
+                                   int32_t n_heads, int32_t n_actions, float* d_losses, float* d_dq, void* stream) {
+  return isdqn_heads_td_loss_weighted(d_q_all, d_action, d_reward, d_terminal, gamma_n, batch, batch_global, n_heads, n_actions,
+                                      nullptr, d_losses, d_dq, nullptr, stream);
 }
 
 // Adam over the flat vector; *d_count must already hold the step number t >= 1.  `shadow` (optional): bf16 copy of

@@ -938,7 +938,8 @@ static __global__ void __launch_bounds__(kLossThreads)
 heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action,
                      const double* __restrict__ reward, const uint8_t* __restrict__ terminal, float gamma_n, int B,
                      int B_global, int K, int A, float* __restrict__ losses, float* __restrict__ dq,
-                     float* __restrict__ dbias, int32_t* count, double* __restrict__ cumulated = nullptr) {
+                     float* __restrict__ dbias, int32_t* count, double* __restrict__ cumulated = nullptr,
+                     const float* __restrict__ is_weights = nullptr, float* __restrict__ td_abs = nullptr) {
   pdl_sync();
   __shared__ float red[kLossThreads / 32];
   __shared__ float dbw[kLossThreads / 32][kMaxActions];
@@ -970,9 +971,12 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
       for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
       const float target = r + coef * mx;
       const float td = q_all[(int64_t)b * n_out + (k + 1) * A + a] - target;
-      part += td * td;
-      val = 2.0f * td * inv_b;
+      // importance weight of a prioritized batch (1 without: both products are then exact, the reference's loss bit for bit)
+      const float wb = is_weights ? is_weights[b] : 1.0f;
+      part += (wb * td) * td;
+      val = 2.0f * td * inv_b * wb;
       if (dq) dq[(int64_t)b * n_out + (k + 1) * A + a] = val;
+      if (td_abs) td_abs[(int64_t)k * B + b] = fabsf(td);
     }
     if (dbias) {
       for (int j = 0; j < A; ++j) {

@@ -151,9 +151,9 @@ constexpr int kPrioThreads = 128;
 
 __global__ void __launch_bounds__(kPrioThreads)
 sample_prioritized_kernel(const uint64_t* __restrict__ rng, const double* __restrict__ nodes, int depth, int size,
-                          const int32_t* __restrict__ index_to_key, int capacity, int32_t* __restrict__ out_index,
-                          int32_t* __restrict__ out_key, int32_t* __restrict__ out_slot,
-                          double* __restrict__ out_target, uint32_t* status) {
+                          int n_valid, const int32_t* __restrict__ index_to_key, int capacity,
+                          int32_t* __restrict__ out_index, int32_t* __restrict__ out_key, int32_t* __restrict__ out_slot,
+                          double* __restrict__ out_target, double* __restrict__ out_prob, uint32_t* status) {
   const PcgMirror m0 = pcg_load(rng);
   const double root = nodes[0];
   const int first_leaf = (1 << (depth - 1)) - 1;
@@ -180,10 +180,20 @@ sample_prioritized_kernel(const uint64_t* __restrict__ rng, const double* __rest
     }
     const int32_t index = node - first_leaf;
     if (out_index) out_index[i] = index;
+    // probability of the drawn leaf (importance weights of a prioritized training loop): leaf / root
+    if (out_prob) out_prob[i] = root > 0.0 ? __ldg(nodes + node) / root : 0.0;
     if (index_to_key) {
-      const int32_t key = index_to_key[index];
+      // samplers.py:112 `self._index_to_key[index]` raises IndexError for an index past the live keys (an empty tree or a
+      // rounding that lands on a zero leaf): flag it and look a live entry up instead, so that nothing downstream (key %
+      // capacity, the gather) ever sees a slot outside the tables
+      int32_t safe = index;
+      if (n_valid >= 0 && index >= n_valid) {
+        st |= ISDQN_ST_INDEX_RANGE;
+        safe = n_valid > 0 ? n_valid - 1 : 0;
+      }
+      const int32_t key = n_valid == 0 ? 0 : index_to_key[safe];
       if (out_key) out_key[i] = key;
-      if (out_slot) out_slot[i] = key % capacity;
+      if (out_slot) out_slot[i] = (int32_t)(((int64_t)key % capacity + capacity) % capacity);
     }
   }
   if (st && status) atomicOr(status, st);
@@ -259,18 +269,19 @@ extern "C" int isdqn_sample_uniform_ws(uint64_t* d_rng, int32_t n_valid, int32_t
   return ISDQN_OK;
 }
 
-extern "C" int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size,
+extern "C" int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size, int32_t n_valid,
                                         const int32_t* d_index_to_key, int32_t capacity, int32_t* d_out_index,
                                         int32_t* d_out_key, int32_t* d_out_slot, double* d_out_target,
-                                        uint32_t* d_status, void* stream) {
+                                        double* d_out_prob, uint32_t* d_status, void* stream) {
   if (!d_rng || !d_nodes || depth < 1 || depth > 31 || size < 0 || (d_index_to_key && capacity < 1))
     return ISDQN_E_INVALID;
   if (size == 0) return ISDQN_OK;
   int grid = ceil_div(size, kPrioThreads);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   ISDQN_PROF(as_stream(stream), "sample_prioritized");
-  sample_prioritized_kernel<<<grid, kPrioThreads, 0, as_stream(stream)>>>(
-      d_rng, d_nodes, depth, size, d_index_to_key, capacity, d_out_index, d_out_key, d_out_slot, d_out_target, d_status);
+  sample_prioritized_kernel<<<grid, kPrioThreads, 0, as_stream(stream)>>>(d_rng, d_nodes, depth, size, n_valid, d_index_to_key,
+                                                                          capacity, d_out_index, d_out_key, d_out_slot,
+                                                                          d_out_target, d_out_prob, d_status);
   ISDQN_LAUNCH_CHECK();
   ISDQN_PROF(as_stream(stream), "pcg_advance");
   pcg_advance64_kernel<<<1, 1, 0, as_stream(stream)>>>(d_rng, (uint64_t)size);

@@ -88,10 +88,14 @@ struct SetSmem {
 
 // With TAGS a value -(1+j) stands for "the current value of leaf j" (read before this op modifies anything):
 // PrioritizedSamplingDistribution.remove moves the last leaf's priority into the hole (samplers.py:99-102)
-// and would otherwise need a device->host read per eviction.
+// and would otherwise need a device->host read per eviction.  A value in (-1, 0) (ISDQN_SUMTREE_TAG_MAX = -0.5)
+// stands for "max_recorded_priority as it is when the op starts": a prioritized training loop inserts new
+// transitions at that priority without reading it back.
 template <bool TAGS>
-__device__ __forceinline__ double resolve_value(double v, const double* nodes, int first_leaf, int n_leaves, int* bad) {
+__device__ __forceinline__ double resolve_value(double v, const double* nodes, int first_leaf, int n_leaves, double max_old,
+                                                int* bad) {
   if (TAGS && v < 0.0) {
+    if (v > -1.0) return max_old;
     const int src = (int)(-v) - 1;
     if (src < 0 || src >= n_leaves) {
       *bad |= 2;
@@ -114,8 +118,10 @@ __device__ void sumtree_set_block(double* nodes, int depth, const int32_t* __res
   // (0) sum_tree.py:31 — nothing is modified when any value is negative (or NaN); indices must be leaves.
   int bad = 0;
   double vmax = 0.0;
+  // (max_prio is only written by thread 0 in step (1), after the barrier below: every thread reads the same old value)
+  const double max_old = (TAGS && max_prio) ? *max_prio : 0.0;
   for (int i = tid; i < m; i += THREADS) {
-    const double v = resolve_value<TAGS>(val[i], nodes, first_leaf, n_leaves, &bad);
+    const double v = resolve_value<TAGS>(val[i], nodes, first_leaf, n_leaves, max_old, &bad);
     const int l = idx[i];
     if (!(v >= 0.0)) bad |= 1;
     if (l < 0 || l >= n_leaves) bad |= 2;
@@ -127,7 +133,7 @@ __device__ void sumtree_set_block(double* nodes, int depth, const int32_t* __res
     int mine = 0;
     for (int i = tid; i < m; i += THREADS) {
       int b2 = 0;
-      if (!(resolve_value<TAGS>(val[i], nodes, first_leaf, n_leaves, &b2) >= 0.0)) mine |= ISDQN_ST_NEGATIVE_VALUE;
+      if (!(resolve_value<TAGS>(val[i], nodes, first_leaf, n_leaves, max_old, &b2) >= 0.0)) mine |= ISDQN_ST_NEGATIVE_VALUE;
       if (b2 || idx[i] < 0 || idx[i] >= n_leaves) mine |= ISDQN_ST_INDEX_RANGE;
     }
     if (mine && status) atomicOr(status, (uint32_t)mine);
@@ -184,7 +190,7 @@ __device__ void sumtree_set_block(double* nodes, int depth, const int32_t* __res
     if (i == 0 || leaf != (uint32_t)(sm.keys[i - 1] >> 32)) {
       sm.uleaf[pos] = (int)leaf;
       int b2 = 0;
-      sm.udelta[pos] = resolve_value<TAGS>(val[(uint32_t)key], nodes, first_leaf, n_leaves, &b2) - nodes[first_leaf + (int)leaf];
+      sm.udelta[pos] = resolve_value<TAGS>(val[(uint32_t)key], nodes, first_leaf, n_leaves, max_old, &b2) - nodes[first_leaf + (int)leaf];
       ++pos;
     }
   }
@@ -228,8 +234,9 @@ constexpr size_t set_smem_bytes() {
 template <int MAXM, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sumtree_set_kernel(double* nodes, int depth, const int32_t* __restrict__ idx, const double* __restrict__ val, int m,
-                   double* max_prio, uint32_t* status) {
+                   double* max_prio, uint32_t* status, const int32_t* abort_flag = nullptr) {
   extern __shared__ __align__(16) unsigned char set_raw[];
+  if (abort_flag && *abort_flag) return;  // isdqn_sumtree_set_keys: a key was not live, nothing is modified
   SetSmem sm = carve_set_smem<MAXM, THREADS>(set_raw);
   sumtree_set_block<MAXM, THREADS, false>(nodes, depth, idx, val, m, max_prio, status, sm);
 }
@@ -251,6 +258,45 @@ sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_
     sumtree_set_block<MAXM, THREADS, true>(nodes, depth, idx + b, val + b, e - b, max_prio, status, sm);
   }
 }
+
+
+// PrioritizedSamplingDistribution.update (samplers.py:76-88) with keys and priorities that live on the device: key ->
+// dense index through the device mirror of `_key_to_index` (slot = key mod n_slots), priority -> priority ** alpha (0 stays 0).
+// PRIO: 0 = float64 [n], 1 = float32 [n], 2 = float32 [prio_rows][n] averaged over the rows in ascending order (the per-head
+// |TD| matrix the loss kernel writes).  A key that is not live sets ISDQN_ST_KEY_MISSING and the abort flag (the
+// reference raises KeyError before it touches the tree).
+__global__ void __launch_bounds__(256)
+sumtree_keys_to_set_kernel(const int32_t* __restrict__ keys, const void* __restrict__ prio, int prio_kind, int prio_rows, int n,
+                           double prio_offset, double alpha, const int32_t* __restrict__ key_slot_to_index, int n_slots,
+                           const int32_t* __restrict__ index_to_key, int n_valid, int32_t* __restrict__ out_idx,
+                           double* __restrict__ out_val, int32_t* abort_flag, uint32_t* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t key = keys[i];
+  const int slot = (int)((((int64_t)key % n_slots) + n_slots) % n_slots);
+  const int32_t idx = key_slot_to_index[slot];
+  const bool live = idx >= 0 && idx < n_valid && index_to_key[idx] == key;
+  if (!live) {
+    if (status) atomicOr(status, ISDQN_ST_KEY_MISSING);
+    atomicExch(abort_flag, 1);
+  }
+  double p;
+  if (prio_kind == 0) {
+    p = reinterpret_cast<const double*>(prio)[i];
+  } else if (prio_kind == 1) {
+    p = (double)reinterpret_cast<const float*>(prio)[i];
+  } else {
+    float acc = 0.f;
+    for (int r = 0; r < prio_rows; ++r) acc += reinterpret_cast<const float*>(prio)[(int64_t)r * n + i];
+    p = (double)(acc / (float)prio_rows);
+  }
+  p += prio_offset;
+  if (!(alpha == 1.0)) p = p == 0.0 ? 0.0 : pow(p, alpha);
+  out_idx[i] = live ? idx : 0;
+  out_val[i] = p;
+}
+
+__global__ void clear_flag_kernel(int32_t* flag) { *flag = 0; }
 
 }  // namespace isdqn
 
@@ -296,6 +342,36 @@ extern "C" int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_in
         <<<1, 1024, set_smem_bytes<ISDQN_SUMTREE_SET_MAX>(), as_stream(stream)>>>(d_nodes, depth, d_index, d_value, n,
                                                                                   d_max_priority, d_status);
   }
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int64_t isdqn_sumtree_set_keys_workspace_bytes(int32_t n) {
+  return n < 0 ? -1 : 16 + (int64_t)(((int64_t)n * 4 + 15) / 16 * 16) + (int64_t)n * 8;
+}
+
+extern "C" int isdqn_sumtree_set_keys(double* d_nodes, int depth, const int32_t* d_keys, const void* d_priorities,
+                                      int32_t prio_kind, int32_t prio_rows, int32_t n, double prio_offset, double alpha,
+                                      const int32_t* d_key_slot_to_index, int32_t n_slots, const int32_t* d_index_to_key,
+                                      int32_t n_valid, double* d_max_priority, uint32_t* d_status, void* d_workspace,
+                                      int64_t workspace_bytes, void* stream) {
+  if (!d_nodes || !d_keys || !d_priorities || !d_key_slot_to_index || !d_index_to_key || !d_workspace || depth < 1 || depth > 31 ||
+      n < 0 || n_slots < 1 || prio_kind < 0 || prio_kind > 2 || (prio_kind == 2 && prio_rows < 1))
+    return ISDQN_E_INVALID;
+  if (n == 0) return ISDQN_OK;
+  if (n > 1024) return ISDQN_E_TOO_LARGE;
+  if (workspace_bytes < isdqn_sumtree_set_keys_workspace_bytes(n)) return ISDQN_E_INVALID;
+  cudaStream_t s = as_stream(stream);
+  int32_t* flag = reinterpret_cast<int32_t*>(d_workspace);
+  int32_t* idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + 16);
+  double* val = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(d_workspace) + 16 + ((int64_t)n * 4 + 15) / 16 * 16);
+  ISDQN_PROF(s, "sumtree_keys_to_set");
+  clear_flag_kernel<<<1, 1, 0, s>>>(flag);
+  sumtree_keys_to_set_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_keys, d_priorities, prio_kind, prio_rows, n, prio_offset, alpha, d_key_slot_to_index,
+                                                             n_slots, d_index_to_key, n_valid, idx, val, flag, d_status);
+  ISDQN_LAUNCH_CHECK();
+  ISDQN_PROF(s, "sumtree_set");
+  sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), s>>>(d_nodes, depth, idx, val, n, d_max_priority, d_status, flag);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

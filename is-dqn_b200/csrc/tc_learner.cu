@@ -770,7 +770,8 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   ISDQN_CUDA_CHECK(launch_pdl(heads_td_loss_kernel, dim3(net->n_heads), dim3(kLossThreads), 0, s, q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
                                                   tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
                                                   backward ? wsp(ws, w.dq) : nullptr, backward ? grads + last.b_off : nullptr,
-                                                  update ? tr->d_count : nullptr, update ? tr->d_cumulated : nullptr));
+                                                  update ? tr->d_count : nullptr, update ? tr->d_cumulated : nullptr,
+                                                  tr->d_is_weights, tr->d_td_abs));
   ISDQN_LAUNCH_CHECK();
   if (q_out)
     ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * (size_t)rows * p.n_out, cudaMemcpyDeviceToDevice, s));

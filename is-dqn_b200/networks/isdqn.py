@@ -117,6 +117,14 @@ class iSDQN:
         self._copy_stream = None
         self._loss_ring = None
         self._last_step = None
+        # prioritized replay (set by the training script): beta of the importance weights (None = plain replay, the
+        # reference's behaviour) and the constant added to |TD| before it becomes a priority
+        self.prioritized_beta = None
+        self.prioritized_eps = 1e-6
+
+    def td_abs(self, B: int):
+        """float32 CUDA tensor [K][B]: |TD| of every online head and sample of the latest step on a batch of B."""
+        return self._context(B)["td_abs"]
 
     # ------------------------------------------------------------------------------------- loss bookkeeping
     @property
@@ -167,6 +175,10 @@ class iSDQN:
         ctx["views"] = views
         ctx.update(views(ctx["dev_pack"]))
         ctx["losses"] = t.zeros(self.n_bellman_iterations, dtype=t.float32, device="cuda")
+        # prioritized training driver: |TD| of every (online head, sample) of the latest step, and the importance
+        # weights the loss applies when a prioritized batch is learned from (ones otherwise: never read then)
+        ctx["td_abs"] = t.zeros((self.n_bellman_iterations, B), dtype=t.float32, device="cuda")
+        ctx["is_weights"] = t.ones(B, dtype=t.float32, device="cuda")
         nbytes = self._lib.isdqn_learn_workspace_bytes(net._net, B)
         if nbytes < 0:
             raise _lib.IsdqnNativeError("isdqn_learn_workspace_bytes failed")
@@ -226,6 +238,8 @@ class iSDQN:
         tr.d_nu = opt["nu"].flat.data_ptr() if opt is not None else None
         tr.d_count = opt["count"].data_ptr() if opt is not None else None
         tr.d_losses = ctx["losses"].data_ptr()
+        tr.d_td_abs = ctx["td_abs"].data_ptr()
+        tr.d_is_weights = None
         tr.d_workspace = ctx["ws"].data_ptr()
         tr.workspace_bytes = ctx["ws"].numel()
         tr.nccl_comm = self._nccl_comm
@@ -330,7 +344,20 @@ class iSDQN:
     # ------------------------------------------------------------------------------------------------ update
     def update_online_params(self, step: int, replay_buffer):
         if step % self.data_to_update == 0:
-            if hasattr(replay_buffer, "sample_device") and self.network.architecture_type == "cnn":
+            device_rb = hasattr(replay_buffer, "sample_device") and self.network.architecture_type == "cnn"
+            sd = getattr(replay_buffer, "_sampling_distribution", None)
+            if device_rb and self.prioritized_beta is not None and hasattr(sd, "update_device"):
+                # prioritized training driver (new: the reference never wires its prioritized sampler to an agent,
+                # SURVEY F10): draw with probabilities, learn with importance weights, write |TD| back — all on the device
+                B = replay_buffer._batch_size
+                batch_samples, d_keys, d_w = replay_buffer.sample_device(out=self.batch_buffers(B), beta=self.prioritized_beta)
+                self.params, self.optimizer_state, losses = self.learn_on_batch(
+                    self.params, self.optimizer_state, batch_samples, _accumulate=True, is_weights=d_w
+                )
+                replay_buffer.update_device(d_keys, self.td_abs(B), prio_rows=self.n_bellman_iterations,
+                                            offset=self.prioritized_eps)
+                return
+            if device_rb:
                 B = replay_buffer._batch_size
                 batch_samples = replay_buffer.sample_device(out=self.batch_buffers(B))
             else:
@@ -362,9 +389,11 @@ class iSDQN:
 
         return False, {}
 
-    def learn_on_batch(self, params: ParamTree, optimizer_state: OptState, batch_samples, _accumulate: bool = False):
+    def learn_on_batch(self, params: ParamTree, optimizer_state: OptState, batch_samples, _accumulate: bool = False,
+                       is_weights=None):
         """isdqn.py:82-90.  Returns (params, optimizer_state, losses[K] float32 CUDA tensor); params / optimizer
-        state are updated in place (donated) and returned."""
+        state are updated in place (donated) and returned.  is_weights (optional, [B]): importance weights of a
+        prioritized batch — losses[k] = mean_b w_b td^2."""
         B = int(batch_samples.action.shape[0])
         ctx = self._context(B)
         cur = self._torch.cuda.current_stream()
@@ -377,17 +406,21 @@ class iSDQN:
             side.wait_stream(cur)
         run = side if side is not None else cur
         self._load_batch(ctx, batch_samples, run)
+        if is_weights is not None:
+            with self._torch.cuda.stream(run):
+                w = is_weights if isinstance(is_weights, self._torch.Tensor) else self._torch.as_tensor(np.asarray(is_weights))
+                ctx["is_weights"].copy_(w.reshape(B).to(self._torch.float32), non_blocking=True)
         try:
-            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream, _accumulate)
+            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream, _accumulate, is_weights is not None)
             self._last_step = (out[2], run)
             return out
         finally:
             if side is not None:
                 cur.wait_stream(side)
 
-    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False):
+    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False, weighted=False):
         key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
-               optimizer_state["count"].data_ptr(), stream, bool(accumulate))
+               optimizer_state["count"].data_ptr(), stream, bool(accumulate), bool(weighted))
         if self._use_graph and ctx["graph"] is not None and ctx["graph_key"] == key:
             if ctx["ws_tc"] is not None and params.shadow_dirty:
                 self._refresh_shadow(params, stream)
@@ -395,6 +428,7 @@ class iSDQN:
             return params, optimizer_state, ctx["losses"]
         tr = self._train_struct(ctx, params, optimizer_state, B)
         tr.d_cumulated = self._d_cumulated.data_ptr() if accumulate else None
+        tr.d_is_weights = ctx["is_weights"].data_ptr() if weighted else None
         if self._use_graph and ctx["warm"] >= 1 and self._nccl_comm is None:
             # capture this very step (it executes on replay, not during capture)
             if ctx["graph"] is not None:

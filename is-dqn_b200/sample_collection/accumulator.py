@@ -82,3 +82,45 @@ class NStepAccumulator:
                 yield self._emit(len(traj) - 1 - n, False)
             if episode_end:  # truncation: the trajectory is dropped (replay_buffer.py:181-183)
                 traj.clear()
+
+    # ------------------------------------------------------------------------------------------ batched form
+    def steady_run(self, terminals, episode_ends, start: int) -> int:
+        """Length of the run of transitions start, start+1, ... that can be accumulated in closed form: the trajectory is
+        full (n + S entries, all committed), no transition of the run is terminal, and a truncation may only end it."""
+        if len(self.trajectory) != self.n + self.S or any(f.frame_id < 0 for f in self.trajectory):
+            return 0
+        N = len(terminals)
+        stop = start
+        while stop < N and not terminals[stop]:
+            stop += 1
+            if episode_ends[stop - 1]:
+                break
+        return stop - start
+
+    def accumulate_run(self, first_frame_id: int, actions, rewards, truncated_at_end: bool):
+        """Closed form of `accumulate` for a steady run of m transitions whose observations were committed as the
+        consecutive frame ids first_frame_id ... (see steady_run): the deque slides by one per transition and every
+        transition emits exactly the element whose state ends at position S - 1 (replay_buffer.py:116-126, 177-183).
+        Returns (refs [m][2S] int64, actions [m], rewards [m] float64); no element of such a run is terminal."""
+        S, n, D = self.S, self.n, self.n + self.S
+        traj = self.trajectory
+        m = len(actions)
+        prev_ids = np.fromiter((f.frame_id for f in traj), dtype=np.int64, count=D)
+        assert (prev_ids >= 0).all(), "steady run on a trajectory with uncommitted frames"
+        ids = np.concatenate((prev_ids, first_frame_id + np.arange(m, dtype=np.int64)))
+        acts = np.concatenate((np.asarray([f.action for f in traj]), np.asarray(actions)))
+        rews = np.concatenate((np.asarray([f.reward for f in traj], dtype=np.float64), np.asarray(rewards, dtype=np.float64)))
+        win = np.lib.stride_tricks.sliding_window_view(ids, D)[1 : m + 1]  # the deque after every append
+        refs = np.concatenate((win[:, :S], win[:, n : n + S]), axis=1)
+        out_actions = acts[S : S + m]
+        # r_t = sum_i gamma^i r_{e+i}, folded left to right from 0.0 like the reference's loop (replay_buffer.py:139-142)
+        out_rewards = np.zeros(m, dtype=np.float64)
+        for i in range(n):
+            out_rewards += rews[S + i : S + i + m] * (self.gamma**i)
+        traj.clear()
+        if not truncated_at_end:
+            for j in range(m, m + D):
+                fr = Frame(None, acts[j], rews[j])
+                fr.frame_id = int(ids[j])
+                traj.append(fr)
+        return refs, out_actions, out_rewards

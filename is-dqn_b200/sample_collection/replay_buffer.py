@@ -236,6 +236,10 @@ class ReplayBuffer:
     def _commit(self, fr: _Frame) -> int:
         if fr.frame_id >= 0:
             return fr.frame_id
+        if isinstance(fr.observation, self._torch.Tensor) and fr.observation.is_cuda:
+            fr.frame_id = self._commit_many(fr.observation.unsqueeze(0), 1)
+            self._check_ring()
+            return fr.frame_id
         self._wait_pending()  # an async flush may still be reading the pinned staging slots
         live_from = self._elem_min_frame[self._oldest_key % self._slots] if self.add_count > self._oldest_key else self._next_frame
         if self._next_frame - live_from >= self._frame_capacity:
@@ -262,7 +266,8 @@ class ReplayBuffer:
         """Add a transition to the accumulator, maybe receive valid replay elements (replay_buffer.py:151-183).
         Yields (frame refs, action, reward, is_terminal) records instead of materialised stacks."""
         if not self._allocated:
-            self._allocate(transition.observation)
+            o = transition.observation
+            self._allocate(o.cpu().numpy() if isinstance(o, self._torch.Tensor) else o)
         return self._accumulator.accumulate(
             transition.observation, transition.action, transition.reward, transition.is_terminal, transition.episode_end
         )
@@ -288,6 +293,118 @@ class ReplayBuffer:
                 oldest_key = self._oldest_key
                 self._oldest_key += 1
                 self._sampling_distribution.remove(oldest_key)
+
+    # ------------------------------------------------------------------------------------------ batched add
+    def _check_ring(self) -> None:
+        live_from = self._elem_min_frame[self._oldest_key % self._slots] if self.add_count > self._oldest_key else self._next_frame
+        if self._next_frame - live_from > self._frame_capacity:
+            raise _lib.IsdqnNativeError(
+                f"frame ring overflow: {self._frame_capacity} slots cannot hold the frames of the live elements; "
+                "pass a larger frame_capacity= to ReplayBuffer"
+            )
+
+    def _commit_many(self, observations, m: int) -> int:
+        """Commits m consecutive observations (host array or CUDA tensor, [m, *obs_shape]) to the frame ring; returns the
+        id of the first.  Device observations never touch the host: one or two device-to-device copies into the ring."""
+        t = self._torch
+        R = self._frame_capacity
+        first = self._next_frame
+        if isinstance(observations, t.Tensor) and observations.is_cuda:
+            self._wait_pending()
+            self._flush_frames()  # staged frames have smaller ids: they reach the ring first (same stream)
+            src = observations.contiguous().view(t.uint8).reshape(m, self._frame_bytes)
+            done = 0
+            while done < m:
+                a = (first + done) % R
+                run = min(m - done, R - a)
+                self._d_frames[a : a + run, : self._frame_bytes].copy_(src[done : done + run], non_blocking=True)
+                done += run
+            self._next_frame = first + m
+            self._flushed_frames = self._next_frame
+            return first
+        obs = np.ascontiguousarray(observations).reshape(m, -1).view(np.uint8)
+        if obs.shape[1] != self._frame_bytes:
+            raise ValueError("observation block does not match the buffer's observation shape / dtype")
+        St = self._staging_frames
+        done = 0
+        while done < m:
+            self._wait_pending()
+            if self._next_frame - self._flushed_frames >= St:
+                self._flush_frames()
+                ev = t.cuda.Event()
+                ev.record()
+                ev.synchronize()  # the staging slots are about to be overwritten
+            fid = self._next_frame
+            room = St - (fid - self._flushed_frames)
+            run = min(m - done, room, St - fid % St)
+            self._h_stage_np[fid % St : fid % St + run, : self._frame_bytes] = obs[done : done + run]
+            self._next_frame = fid + run
+            done += run
+        return first
+
+    def add_batch(self, observations, actions, rewards, is_terminals, episode_ends=None, priorities=None) -> None:
+        """N environment steps at once: identical in effect to
+            for i in range(N): rb.add(TransitionElement(observations[i], actions[i], rewards[i], is_terminals[i], episode_ends[i]),
+                                      [priority=priorities[i]])
+        (replay_buffer.py:151-196), but the steady part of a trajectory — full n-step window, no terminal — is accumulated
+        in closed form (accumulator.accumulate_run), its frames reach the ring with one copy (device-to-device when
+        `observations` is a CUDA tensor: a device-resident environment never touches the host), the element records
+        are written with array assignments and the sampler receives one run (`_add_remove_run`).  Transitions around
+        episode boundaries take the per-transition path.  priorities: None, "max" (insert at max_recorded_priority,
+        resolved on the device) or one value per transition (prioritized samplers only)."""
+        t = self._torch
+        N = len(actions)
+        if episode_ends is None:
+            episode_ends = is_terminals
+        is_dev = isinstance(observations, t.Tensor) and observations.is_cuda
+        terms = np.asarray(is_terminals, dtype=bool)
+        ends = np.asarray(episode_ends, dtype=bool)
+        acts = np.asarray(actions)
+        rews = np.asarray(rewards)
+        if not self._allocated and N:
+            first = observations[0]
+            self._allocate(first.cpu().numpy() if is_dev else np.asarray(first))
+        per_key = priorities is not None and not isinstance(priorities, str)
+        acc = self._accumulator
+        cap = self._max_capacity
+        i = 0
+        while i < N:
+            m = acc.steady_run(terms, ends, i)
+            if m == 0:
+                kw = {} if priorities is None else {"priority": priorities[i] if per_key else priorities}
+                obs_i = observations[i]
+                self.add(TransitionElement(obs_i, acts[i], rews[i], bool(terms[i]), bool(ends[i])), **kw)
+                i += 1
+                continue
+            m = min(m, cap)  # one pass never laps the element ring
+            self._wait_pending()
+            fid0 = self._commit_many(observations[i : i + m], m)
+            refs, e_act, e_rew = acc.accumulate_run(fid0, acts[i : i + m], rews[i : i + m], bool(ends[i + m - 1]))
+            if self._action_dtype is None:
+                self._action_dtype = np.asarray(acts[i]).dtype
+            keys = self.add_count + np.arange(m, dtype=np.int64)
+            slots = keys % self._slots
+            self._hn_elem_frames[slots] = refs % self._frame_capacity  # (no padding inside a steady run)
+            self._elem_min_frame[slots] = refs[:, 0]
+            self._hn_action[slots] = e_act
+            self._hn_reward[slots] = e_rew
+            self._hn_terminal[slots] = 0
+            evict_from = max(cap - self.add_count, 0)  # add j is followed by an eviction once add_count + j + 1 > cap
+            n_evict = max(m - evict_from, 0)
+            sd = self._sampling_distribution
+            pr = None if priorities is None else (priorities if not per_key else priorities[i : i + m])
+            if hasattr(sd, "_add_remove_run"):
+                sd._add_remove_run(int(keys[0]), m, self._oldest_key, min(evict_from, m), pr)
+            else:  # a user-supplied sampling distribution: the one-at-a-time calls
+                for j in range(m):
+                    kw = {} if pr is None else {"priority": pr[j] if per_key else pr}
+                    sd.add(ReplayItemID(int(keys[j])), **kw)
+                    if j >= evict_from:
+                        sd.remove(self._oldest_key + (j - evict_from))
+            self.add_count += m
+            self._oldest_key += n_evict
+            self._check_ring()
+            i += m
 
     # --------------------------------------------------------------------------------------------- sampling
     def _gather_slots_device(self, d_slots, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None):
@@ -372,26 +489,53 @@ class ReplayBuffer:
         d_slots = self._torch.from_numpy(slots).to(self._device)
         return self._to_host(self._gather_slots_device(d_slots))
 
-    def sample_device(self, size=None, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None) -> ReplayElement:
+    def sample_device(self, size=None, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None,
+                      return_keys: bool = False, beta: Optional[float] = None):
         """Device-resident `sample`: draw -> key -> slot -> gather without leaving the GPU.  For uint8 stack-4
-        frames the state tensors are (size, H, W, stack) uint8 (or f32/bf16 normalised with out_dtype)."""
+        frames the state tensors are (size, H, W, stack) uint8 (or f32/bf16 normalised with out_dtype).
+        return_keys: also return the int32 CUDA keys of the batch (what `update` / `update_device` take); beta (prioritized
+        samplers): also return the float32 CUDA importance weights (N P(i))^-beta / max.  Returns batch,
+        (batch, keys) or (batch, keys, weights)."""
         assert self.add_count, ValueError("No samples in replay buffer!")
         if size is None:
             size = self._batch_size
-        _, _, d_slot = self._sampling_distribution.sample_device(size, self._slots)
+        sd = self._sampling_distribution
+        if beta is not None:
+            _, d_key, d_slot = sd.sample_device(size, self._slots, want_prob=True)
+        else:
+            _, d_key, d_slot = sd.sample_device(size, self._slots)
         b = self._gather_slots_device(d_slot, out_dtype, out)
         if out is None and out_dtype == _lib.OUT_RAW and self._elem_size == 1:
             shape = (size,) + tuple(self._obs_shape) + (self._stack_size,)
             b = b._replace(state=b.state.view(shape), next_state=b.next_state.view(shape))
+        if beta is not None:
+            return b, d_key, sd.importance_weights(beta)
+        if return_keys:
+            return b, d_key
         return b
 
-    def sample(self, size=None) -> ReplayElement:
-        """Sample a batch of elements from the replay buffer (replay_buffer.py:198-213); host numpy arrays."""
+    def sample(self, size=None, return_keys: bool = False, beta: Optional[float] = None):
+        """Sample a batch of elements from the replay buffer (replay_buffer.py:198-213); host numpy arrays.
+        return_keys / beta: as in `sample_device`, with host arrays (the reference's `sample` returns the batch only, so a
+        prioritized training loop could not name the elements it should re-prioritise)."""
         assert self.add_count, ValueError("No samples in replay buffer!")
         if size is None:
             size = self._batch_size
+        if beta is not None:
+            b, d_key, d_w = self.sample_device(size, beta=beta)
+            host = self._to_host(b._replace(state=b.state.reshape(size, -1), next_state=b.next_state.reshape(size, -1)))
+            keys, w = d_key.cpu().numpy(), d_w.cpu().numpy()
+            self._sampling_distribution._pull_rng_state()
+            self._sampling_distribution.check_status()
+            return host, keys, w
         samples = self._sampling_distribution.sample(size)
-        return self._gather_keys(samples)
+        batch = self._gather_keys(samples)
+        return (batch, samples) if return_keys else batch
 
     def update(self, keys, **kwargs: Any) -> None:  # replay_buffer.py:215-220
         self._sampling_distribution.update(keys, **kwargs)
+
+    def update_device(self, d_keys, d_priorities, prio_rows: int = 0, offset: float = 0.0) -> None:
+        """`update(keys, priorities=...)` for keys and priorities that live on the device (e.g. the keys of
+        `sample_device(return_keys=True)` and the |TD| matrix of the step, `agent.td_abs`): no synchronisation."""
+        self._sampling_distribution.update_device(d_keys, d_priorities, prio_rows, offset)

@@ -30,9 +30,11 @@ class SumTree:
         self._d_nodes = torch.zeros((2**self._depth) - 1, dtype=torch.float64, device=self._device)
         self._d_max = torch.ones(1, dtype=torch.float64, device=self._device)  # max_recorded_priority = 1.0
         self._d_status = torch.zeros(1, dtype=torch.int32, device=self._device)
-        self._q_idx: list = []
+        self._q_idx: list = []   # queued sets: leaf indices / values of every op, concatenated on flush
         self._q_val: list = []
-        self._q_off = [0]
+        self._q_len: list = []   # ... and the number of entries of every op (arrays)
+        self._q_entries = 0
+        self._stager = None
 
     # ---------------------------------------------------------------------------------------------- set
     def set(self, indices, values) -> None:
@@ -60,9 +62,9 @@ class SumTree:
                 raise _lib.IsdqnNativeError(
                     f"SumTree.set with {m} indices exceeds the kernel limit {_lib.SUMTREE_SET_MAX}"
                 )
-            t = self._torch
-            d_idx = t.from_numpy(idx32).to(self._device)
-            d_val = t.from_numpy(val64).to(self._device)
+            if self._stager is None:
+                self._stager = _lib.PinnedStager(1 << 14)
+            d_idx, d_val = self._stager.put(idx32, val64)
             _lib.check(
                 self._lib.isdqn_sumtree_set(
                     self._d_nodes.data_ptr(), self._depth, d_idx.data_ptr(), d_val.data_ptr(), m,
@@ -73,27 +75,53 @@ class SumTree:
             return
         self._q_idx.append(idx32)
         self._q_val.append(val64)
-        self._q_off.append(self._q_off[-1] + m)
-        if self._q_off[-1] >= self._QUEUE_LIMIT:
+        self._q_len.append(np.asarray([m], dtype=np.int32))
+        self._q_entries += m
+        if self._q_entries >= self._QUEUE_LIMIT:
             self.flush()
 
-    def flush(self) -> None:
-        """Applies every queued `set`, in order, with one launch."""
-        if len(self._q_off) == 1:
+    def _enqueue_ops(self, idx32: np.ndarray, val64: np.ndarray, lengths: np.ndarray) -> None:
+        """Queue many sets at once: op j covers the next lengths[j] entries of idx32 / val64 (every op at most
+        SUMTREE_OP_MAX entries; values may carry the tags of `_enqueue` and SUMTREE_TAG_MAX)."""
+        if lengths.size == 0:
             return
-        t = self._torch
-        idx = t.from_numpy(np.concatenate(self._q_idx)).to(self._device)
-        val = t.from_numpy(np.concatenate(self._q_val)).to(self._device)
-        off = t.from_numpy(np.asarray(self._q_off, dtype=np.int32)).to(self._device)
-        n_ops = len(self._q_off) - 1
-        self._q_idx, self._q_val, self._q_off = [], [], [0]
-        _lib.check(
-            self._lib.isdqn_sumtree_set_ops(
-                self._d_nodes.data_ptr(), self._depth, off.data_ptr(), n_ops, idx.data_ptr(), val.data_ptr(),
-                self._d_max.data_ptr(), self._d_status.data_ptr(), _lib.stream_ptr(),
-            ),
-            "isdqn_sumtree_set_ops",
-        )
+        assert int(lengths.max()) <= _lib.SUMTREE_OP_MAX and int(lengths.sum()) == idx32.size == val64.size
+        self._q_idx.append(np.ascontiguousarray(idx32, dtype=np.int32))
+        self._q_val.append(np.ascontiguousarray(val64, dtype=np.float64))
+        self._q_len.append(np.ascontiguousarray(lengths, dtype=np.int32))
+        self._q_entries += idx32.size
+        if self._q_entries >= self._QUEUE_LIMIT:
+            self.flush()
+
+    _FLUSH_ENTRIES = 1 << 18  # entries per launch (bounds the pinned staging block)
+
+    def flush(self) -> None:
+        """Applies every queued `set`, in order (one launch per _FLUSH_ENTRIES entries)."""
+        if not self._q_len:
+            return
+        idx = np.concatenate(self._q_idx) if len(self._q_idx) > 1 else self._q_idx[0]
+        val = np.concatenate(self._q_val) if len(self._q_val) > 1 else self._q_val[0]
+        lens = np.concatenate(self._q_len) if len(self._q_len) > 1 else self._q_len[0]
+        self._q_idx, self._q_val, self._q_len, self._q_entries = [], [], [], 0
+        if self._stager is None:
+            self._stager = _lib.PinnedStager(1 << 14)
+        off = np.zeros(lens.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        op0 = 0
+        while op0 < lens.size:
+            # ops [op0, op1): as many as fit _FLUSH_ENTRIES entries (at least one)
+            op1 = int(np.searchsorted(off, off[op0] + self._FLUSH_ENTRIES, side="right")) - 1
+            op1 = min(max(op1, op0 + 1), lens.size)
+            e0, e1 = int(off[op0]), int(off[op1])
+            d_idx, d_val, d_off = self._stager.put(idx[e0:e1], val[e0:e1], (off[op0 : op1 + 1] - e0).astype(np.int32))
+            _lib.check(
+                self._lib.isdqn_sumtree_set_ops(
+                    self._d_nodes.data_ptr(), self._depth, d_off.data_ptr(), op1 - op0, d_idx.data_ptr(), d_val.data_ptr(),
+                    self._d_max.data_ptr(), self._d_status.data_ptr(), _lib.stream_ptr(),
+                ),
+                "isdqn_sumtree_set_ops",
+            )
+            op0 = op1
 
     def _check_status(self) -> int:
         st = int(self._d_status.item())

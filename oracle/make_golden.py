@@ -2,6 +2,7 @@
 `/root/reference` is mounted.
 
     python oracle/make_golden.py            # regenerate tests/golden/*.npz and pin the restatements
+    python oracle/make_golden.py --big      # only the 1 M-capacity scenarios (minutes of reference time each)
 
 For every scenario in `tests/scenarios.py` it
   1. imports the UNMODIFIED reference modules (`slimdqn.sample_collection.*`) under `oracle/refshim.py`,
@@ -119,15 +120,17 @@ def main() -> int:
     from slimdqn.sample_collection import sum_tree as ref_sum_tree
 
     os.makedirs(GOLDEN, exist_ok=True)
-    for sc in S.SCENARIOS:
+    big = "--big" in sys.argv
+    for sc in (S.BIG_SCENARIOS if big else S.SCENARIOS):
         want = S.run_scenario(sc, ReferenceAdapter(sc))
-        got = S.run_scenario(sc, OracleAdapter(sc))
-        S.compare_results(got, want, where=f"oracle-vs-reference:{sc.name}")
+        if not big or "--with-oracle" in sys.argv:  # (the restatement is pinned at the small sizes; at 1 M it doubles the run)
+            got = S.run_scenario(sc, OracleAdapter(sc))
+            S.compare_results(got, want, where=f"oracle-vs-reference:{sc.name}")
         path = os.path.join(GOLDEN, f"replay_{sc.name}.npz")
         np.savez_compressed(path, **want)
         print(f"[golden] {sc.name:24s} adds={int(want['add_count']):5d} batches={len(want['digests']):3d} "
               f"-> {os.path.relpath(path, ROOT)} ({os.path.getsize(path) / 1024:.1f} KiB)  oracle==reference")
-    for tt in S.TREE_TRACES:
+    for tt in ([] if big else S.TREE_TRACES):
         want = S.run_tree_trace(tt, ref_sum_tree.SumTree(tt.capacity))
         got = S.run_tree_trace(tt, SumTreeOracle(tt.capacity))
         S.compare_results(got, want, where=f"oracle-vs-reference:{tt.name}")

@@ -35,6 +35,7 @@ class Scenario:
     priority_exponent: float = 1.0
     full_batches: int = 2
     int_rewards: bool = False  # the reference's tests feed Python ints as rewards/actions
+    digest_only: bool = False  # big scenarios: maps / tree nodes are stored as digests, not in full
 
 
 SCENARIOS = [
@@ -55,8 +56,17 @@ SCENARIOS = [
 ]
 
 
+# BASELINE.json configs[2] at its real size: a 1 M-transition prioritized buffer (sum tree of depth 21, leaf index =
+# capacity touched by every add-then-evict), filled and then driven through 130 k evictions with priority updates in
+# between.  Small frames keep the reference run that produced the fixture (oracle/make_golden.py --big) to minutes.
+BIG_SCENARIOS = [
+    Scenario("prioritized_cap1M", 8, 1_000_000, 32, 4, 1, 0.99, 1_131_000, (4, 4), "uint8", 0.001, 0.0005, "prioritized",
+             50_000, sparse=0.5, digest_only=True),
+]
+
+
 def scenario_by_name(name: str) -> Scenario:
-    for s in SCENARIOS:
+    for s in SCENARIOS + BIG_SCENARIOS:
         if s.name == name:
             return s
     raise KeyError(name)
@@ -131,9 +141,19 @@ def run_scenario(sc: Scenario, ad: Adapter) -> dict:
                 ad.update(np.asarray(keys), new_p)
     out["digests"] = np.asarray(digests)
     out["add_count"] = np.asarray(ad.add_count())
+    nodes = ad.tree_nodes()
+    if sc.digest_only:
+        mk = np.asarray(ad.memory_keys(), dtype=np.int64)
+        out["memory_keys_span"] = np.asarray([mk[0], mk[-1], mk.size], dtype=np.int64)
+        assert (np.diff(mk) == 1).all()
+        out["index_to_key_digest"] = np.asarray(digest(np.asarray(ad.index_to_key(), dtype=np.int64)))
+        if nodes is not None:
+            nodes = np.asarray(nodes, dtype=np.float64)
+            out["tree_nodes_digest"] = np.asarray(digest(nodes))
+            out["tree_root"] = np.asarray(nodes[0])
+        return out
     out["memory_keys"] = np.asarray(ad.memory_keys(), dtype=np.int64)
     out["index_to_key"] = np.asarray(ad.index_to_key(), dtype=np.int64)
-    nodes = ad.tree_nodes()
     if nodes is not None:
         out["tree_nodes"] = np.asarray(nodes, dtype=np.float64)
     return out
