@@ -53,6 +53,29 @@ def synthetic_stream(seed: int, n: int, chunk: int = 4096):
         done += m
 
 
+def synthetic_chunks(seed: int, n: int, chunk: int = 4096):
+    """The same stream as synthetic_stream, as arrays: (frames [m,84,84] u8, actions, rewards f64, terminal bool)."""
+    rng = np.random.default_rng(seed)
+    done = 0
+    while done < n:
+        m = min(chunk, n - done)
+        frames = rng.integers(0, 256, (m, 84, 84), dtype=np.uint8)
+        frames *= rng.random((m, 84, 84), dtype=np.float32) >= 0.9
+        actions = rng.integers(0, N_ACTIONS, m)
+        rewards = rng.integers(-1, 2, m).astype(np.float64)
+        terminal = rng.random(m) < 1e-3
+        yield frames, actions, rewards, terminal
+        done += m
+
+
+def fill_replay(rb, seed: int, n: int, priorities=None):
+    """Fills `rb` with n synthetic transitions through the batched add path; returns seconds."""
+    t0 = time.perf_counter()
+    for frames, a, r, d in synthetic_chunks(seed, n):
+        rb.add_batch(frames, a, r, d, d, priorities=priorities)
+    return time.perf_counter() - t0
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -65,7 +88,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -144,17 +167,73 @@ def cpu_reference_steps(n_steps: int, warmup: int, capacity: int = 20_000, time_
     return done / dt, done, cores, desc, dt
 
 
+def cpu_replay_baseline(capacity: int = 100_000, reps: int = 200):
+    """the replay half of the metric on the host cores — the oracle restatements of rb.sample(32),
+    SumTree.query(32), SumTree.set(32) and the prioritized sample(32) (single Python thread: the reference's replay side is
+    single-threaded NumPy by construction).  Small frames would flatter rb.sample, so it runs at Atari shapes on a
+    bounded buffer; the tree runs at the full 1 M capacity (depth 21)."""
+    from oracle.replay_oracle import ReplayOracle
+    from oracle.samplers_oracle import PrioritizedSamplingOracle, UniformSamplingOracle
+    from oracle.sum_tree_oracle import SumTreeOracle
+
+    out = {"cores": 1, "kind": "port", "unit": "samples/s"}
+    n_el = min(capacity, 20_000)
+    rb = ReplayOracle(UniformSamplingOracle(0), BATCH, n_el, 4, 1, GAMMA)
+    for obs, a, r, d in synthetic_stream(0, n_el + 200):
+        rb.add(obs, a, r, d, d)
+    for _ in range(5):
+        rb.sample()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rb.sample()
+    out["rb_sample32_samples_per_s"] = BATCH * reps / (time.perf_counter() - t0)
+    out["rb_sample32_sample"] = f"{reps} x ReplayOracle.sample(32), Atari shapes, {n_el}-element buffer (stacked copies: 56 KB each)"
+    rng = np.random.default_rng(0)
+    tree = SumTreeOracle(1_000_000)
+    for lo in range(0, 1_000_000, 8192):  # distinct ascending leaves: one big set equals the single adds
+        hi = min(lo + 8192, 1_000_000)
+        tree.set(np.arange(lo, hi, dtype=np.int32), np.abs(rng.standard_normal(hi - lo)) + 1e-3)
+    root = tree.root
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        tree.query(rng.random(BATCH) * root)
+    out["sumtree_query32_samples_per_s"] = BATCH * reps / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        tree.set(rng.integers(0, 1_000_000, BATCH).astype(np.int32), np.abs(rng.standard_normal(BATCH)) + 1e-3)
+    dt_set = time.perf_counter() - t0
+    out["sumtree_set32_leaves_per_s"] = BATCH * reps / dt_set
+    out["sumtree_set32_us"] = dt_set / reps * 1e6
+    ps = PrioritizedSamplingOracle(1, 1_000_000)
+    ps.tree = tree
+    ps.index_to_key = list(range(1_000_000))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ps.sample(BATCH)
+    out["prioritized_sample32_samples_per_s"] = BATCH * reps / (time.perf_counter() - t0)
+    out["tree"] = "SumTreeOracle(1,000,000): depth 21, numpy float64"
+    return out
+
+
+REFERENCE_ARM_CAPACITY = 20_000  # elements the CPU arm's buffer holds (the oracle stores two stacked copies per element)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    ups, done, cores, desc, dt = cpu_reference_steps(args.steps, args.warmup)
+    ups, done, cores, desc, dt = cpu_reference_steps(args.steps, args.warmup, capacity=REFERENCE_ARM_CAPACITY)
     line = {
         "impl": "reference", "metric": "iS-DQN K=9 learner updates/sec", "value": ups, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the arm's config is OUR arm's (same workload); what the CPU actually ran — a bounded sample — is in cpu_baseline
-        "config": workload_config(args.capacity),
-        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc},
+        # the workload is OUR arm's (same network, batch, K, uniform replay); the CPU arm holds a bounded buffer — the oracle
+        # keeps two stacked uint8 copies per element like the reference (56 KB each: 1 M elements would need 56 GB of
+        # host memory) — and says so: `replay_capacity` is what it ran
+        "config": dict(workload_config(REFERENCE_ARM_CAPACITY),
+                       replay_capacity_note=f"bounded CPU sample: {REFERENCE_ARM_CAPACITY} of the CUDA arm's {args.capacity} elements; "
+                                            "the sampled batch shape and the learner step are identical"),
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc,
+                         "replay": cpu_replay_baseline()},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -212,6 +291,52 @@ def kernel_work(name: str, P: int, fused: bool = False):
     return None, 0
 
 
+def measure_agent(agent, rb, steps, warmup, barrier, stream, local_rank):
+    """updates/s of `agent` on `rb`: device-resident loop and the end-to-end loop (host batch -> H2D -> step -> D2H of the
+    losses).  Returns (ms, ms_e2e, h2d bytes, d2h bytes, clocks summary); runs on `stream`."""
+    import torch
+
+    step_no = [0]
+
+    def step():
+        step_no[0] += 1
+        agent.update_online_params(step_no[0], rb)
+
+    for _ in range(warmup):
+        step()
+    pool = [rb.sample() for _ in range(8)]
+    h2d = sum(np.asarray(x).nbytes for x in pool[0])
+
+    # 1-deep software pipeline, as a training loop runs it: step i+1 (host copy into pinned staging, H2D on the copy
+    # engine, graph launch) is enqueued before step i's losses are read back; every step's H2D and D2H happen inside
+    # the timed region.
+    def e2e_loop(n):
+        pending = None
+        for i in range(n):
+            agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])
+            handle = agent.losses_to_host_async()
+            if pending is not None:
+                pending.get()
+            pending = handle
+        return pending.get()
+
+    e2e_loop(max(3, warmup // 2))
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:  # spans both timed regions (one alone is shorter than nvidia-smi's sampling period)
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        barrier()
+        e0.record()
+        losses_host = e2e_loop(steps)
+        e1.record()
+        barrier()
+    return ev0.elapsed_time(ev1), e0.elapsed_time(e1), int(h2d), int(losses_host.size * 4), clk.summary()
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -229,11 +354,14 @@ def run_ours(args, rank, world, local_rank):
     cap = args.capacity
     rb = ReplayBuffer(UniformSamplingDistribution(rank), BATCH, cap, stack_size=4, update_horizon=1, gamma=GAMMA,
                       clipping=lambda x: np.clip(x, -1, 1), frame_capacity=cap + cap // 8 + 64, pinned_ring=16)
-    t_fill = time.perf_counter()
     n_fill = cap + max(cap // 10, 64)
-    for obs, a, r, d in synthetic_stream(1000 + rank, n_fill):
+    t_fill = fill_replay(rb, 1000 + rank, n_fill)
+    # the per-transition path (what the reference's training loop calls) on a bounded sample, for the comparison
+    t_one = time.perf_counter()
+    n_one = 2000
+    for obs, a, r, d in synthetic_stream(5000 + rank, n_one):
         rb.add(TransitionElement(obs, a, r, d, d))
-    t_fill = time.perf_counter() - t_fill
+    t_one = time.perf_counter() - t_one
     agent = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "cnn", LR, GAMMA, 1, 1, 8000, adam_eps=ADAM_EPS,
                   compute_dtype="bfloat16" if args.dtype == "bf16" else "float32")
     P = agent.network.n_params
@@ -246,48 +374,16 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
-        step_no = [0]
-
-        def step():
-            step_no[0] += 1
-            agent.update_online_params(step_no[0], rb)
-
-        for _ in range(args.warmup):
-            step()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            ev0.record()
-            for _ in range(args.steps):
-                step()
-            ev1.record()
-            barrier()
-        ms = ev0.elapsed_time(ev1)
-        # ---- e2e: host batch -> H2D -> step -> D2H of the losses, through the reference-facing call
-        pool = [rb.sample() for _ in range(8)]
-        h2d = sum(np.asarray(x).nbytes for x in pool[0])
-        # 1-deep software pipeline, as a training loop runs it: step i+1 (host copy into pinned staging, H2D on the copy
-        # engine, graph launch) is enqueued before step i's losses are read back; every step's H2D and D2H happen
-        # inside the timed region.
-        def e2e_loop(n):
-            pending, host = None, None
-            for i in range(n):
-                agent.learn_on_batch(agent.params, agent.optimizer_state, pool[i % 8])
-                handle = agent.losses_to_host_async()
-                if pending is not None:
-                    host = pending.get()
-                pending = handle
-            return pending.get()
-
-        e2e_loop(max(3, args.warmup // 2))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        losses_host = e2e_loop(args.steps)
-        e1.record()
-        barrier()
-        ms_e2e = e0.elapsed_time(e1)
-        d2h = losses_host.size * 4
+        ms, ms_e2e, h2d, d2h, clocks = measure_agent(agent, rb, args.steps, args.warmup, barrier, stream, local_rank)
+        # ---- the reference's own arithmetic (fp32, 1e-5 parity path) on the same buffer: a second agent, fewer steps
+        fp32 = None
+        if args.dtype == "bf16":
+            agent32 = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "cnn", LR, GAMMA, 1, 1, 8000,
+                            adam_eps=ADAM_EPS, compute_dtype="float32")
+            n32 = max(20, args.steps // 4)
+            ms32, ms32_e2e, _, _, _ = measure_agent(agent32, rb, n32, max(3, args.warmup // 4), barrier, stream, local_rank)
+            fp32 = {"steps": n32, "ms": ms32, "ms_e2e": ms32_e2e}
+            del agent32
         # ---- replay throughput shape: 2048 batches of 32 per launch (sampler + gather only)
         n_big = 2048 * BATCH
         for _ in range(3):
@@ -309,12 +405,20 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             from isdqn_b200.sample_collection.samplers import PrioritizedSamplingDistribution
 
-            n_keys = min(cap, 262_144)
+            n_keys = cap  # BASELINE configs[2]: 1 M keys, a tree of depth 21
             ps = PrioritizedSamplingDistribution(7, n_keys)
             prio_rng = np.random.default_rng(7)
             pv = np.abs(prio_rng.standard_normal(n_keys)) + 1e-3
-            for k in range(n_keys):
-                ps.add(k, float(pv[k]))
+            t_pfill = time.perf_counter()
+            for k0 in range(0, n_keys, 65536):  # the add / add-then-evict call sequence of ReplayBuffer.add, batched
+                k1 = min(k0 + 65536, n_keys)
+                ps._add_remove_run(k0, k1 - k0, 0, k1 - k0, pv[k0:k1].tolist())
+            n_evict = max(n_keys // 10, 64)
+            pv2 = np.abs(prio_rng.standard_normal(n_evict)) + 1e-3
+            ps._add_remove_run(n_keys, n_evict, 0, 0, pv2.tolist())  # every add evicts the oldest key (swap-remove, tagged set)
+            ps._sum_tree.flush()
+            torch.cuda.synchronize()
+            t_pfill = time.perf_counter() - t_pfill
             for _ in range(3):
                 ps.sample_device(n_big, n_keys + 1)
             torch.cuda.synchronize()
@@ -325,7 +429,7 @@ def run_ours(args, rank, world, local_rank):
             p1.record()
             torch.cuda.synchronize()
             ms_prio = p0.elapsed_time(p1) / reps
-            upd_keys = np.arange(0, 32 * 97, 97, dtype=np.int32)
+            upd_keys = np.arange(n_evict, n_evict + 32 * 97, 97, dtype=np.int32)
             for _ in range(3):
                 ps.update(upd_keys, np.abs(prio_rng.standard_normal(32)) + 1e-3)
                 ps._sum_tree.flush()
@@ -340,7 +444,25 @@ def run_ours(args, rank, world, local_rank):
             bytes_per_sample = (depth - 1) * 8 + 12
             prio = {"keys": n_keys, "tree_depth": depth, "samples_per_s": n_big / (ms_prio / 1e3), "launch_samples": n_big,
                     "ms_per_launch": ms_prio, "algorithmic_GBps": bytes_per_sample * n_big / (ms_prio / 1e3) / 1e9,
-                    "update32_us": p0.elapsed_time(p1) / 50 * 1e3}
+                    "update32_us": p0.elapsed_time(p1) / 50 * 1e3,
+                    "fill": {"adds": n_keys + n_evict, "evictions": n_evict, "seconds": t_pfill,
+                             "us_per_add": t_pfill / (n_keys + n_evict) * 1e6},
+                    "bound": "L2 latency: the 16.8 MB heap is L2-resident, a draw is 20 dependent 8-byte reads; HBM is not the "
+                             "limiter (profiles/r02_replay_ncu.md)"}
+            # device-resident update: keys and priorities already on the GPU (the prioritized training driver's path)
+            d_keys = torch.from_numpy(upd_keys).cuda()
+            d_pr = torch.from_numpy(np.abs(prio_rng.standard_normal(32)) + 1e-3).cuda()
+            for _ in range(3):
+                ps.update_device(d_keys, d_pr)
+            torch.cuda.synchronize()
+            p0.record()
+            for _ in range(50):
+                ps.update_device(d_keys, d_pr)
+            p1.record()
+            torch.cuda.synchronize()
+            ps.check_status()
+            prio["update32_device_us"] = p0.elapsed_time(p1) / 50 * 1e3
+            del ps
         # ---- acting path: one greedy action for one host observation stack, read back with .item()
         act_state = np.random.default_rng(3).integers(0, 256, OBS, dtype=np.uint8)
         for i in range(20):
@@ -364,6 +486,18 @@ def run_ours(args, rank, world, local_rank):
                                                            act_ctx["q"].data_ptr(), act_ctx["d_arg"].data_ptr(),
                                                            act_ctx["fused"].data_ptr(), act_ctx["fused"].numel(), stream.cuda_stream))
             acting["kernel_us"] = prof_act[0][1] * 1e3
+        # batched acting: one forward for N environments, one synchronisation
+        for n_env in (8, 64):
+            states = np.random.default_rng(4).integers(0, 256, (n_env,) + OBS, dtype=np.uint8)
+            keys = list(range(n_env))
+            for _ in range(5):
+                agent.best_actions(agent.params, states, keys)
+            t_act = time.perf_counter()
+            for _ in range(50):
+                agent.best_actions(agent.params, states, keys)
+            dt_act = (time.perf_counter() - t_act) / 50
+            acting[f"best_actions_{n_env}_us_per_call"] = dt_act * 1e6
+            acting[f"best_actions_{n_env}_us_per_action"] = dt_act * 1e6 / n_env
         # ---- per-kernel profile of one step (direct launches behind a spin kernel: no launch gaps)
         agent._use_graph = False
         prof = _lib.profile(lambda: agent.update_online_params(1, rb))
@@ -404,10 +538,26 @@ def run_ours(args, rank, world, local_rank):
     fused = "dense_wgrad_adam" in per_kernel
     kind, work = kernel_work(dom_name, P, fused)
 
-    t_max = torch.tensor([ms, ms_e2e, ms_replay], dtype=torch.float64, device="cuda")
+    t_max = torch.tensor([ms, ms_e2e, ms_replay] + ([fp32["ms"], fp32["ms_e2e"]] if fp32 else []), dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_replay = (float(x) for x in t_max.cpu())
+    t_host = [float(x) for x in t_max.cpu()]
+    ms, ms_e2e, ms_replay = t_host[:3]
+    if fp32:
+        fp32 = {"dtype": "f32", "parity": "1e-5 (the reference's own arithmetic; CUDA-core FFMA path)", "steps": fp32["steps"],
+                "value": world * fp32["steps"] / (t_host[3] / 1e3), "ms_per_step": t_host[3] / fp32["steps"],
+                "e2e": world * fp32["steps"] / (t_host[4] / 1e3), "unit": "updates/s", "replay_capacity": cap}
+    # release the agents-mode buffers before the large-batch measurements
+    del rb, agent
+    torch.cuda.empty_cache()
+    # ---- BASELINE configs[4]: the data-parallel learner (global batch 4096, widths x1 and x2), strong scaling over the
+    # same N GPUs; at N = 1 it is the single-device baseline the driver's efficiency is computed from
+    dp = None
+    if not args.no_dp:
+        dp = {}
+        for width in (1, 2):
+            dp[f"w{width}"] = dp_measure(args, rank, world, local_rank, 4096, width, steps=max(10, min(args.steps // 10, 30)),
+                                         warmup=5, dist=dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -442,14 +592,19 @@ def run_ours(args, rank, world, local_rank):
                                      "achieved": a2, "unit": "GB/s", "frac": a2 / peaks["hbm_gbs"]})
     gather_gbs = 91_728 * n_big / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else None
     # host-CPU baseline (rank 0 only: the other ranks have returned above), a bounded sample of the same workload
-    ups, done, cores, desc, _ = cpu_reference_steps(10**9, 2, time_budget_s=args.cpu_seconds)
-    cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc}
+    ups, done, cores, desc, _ = cpu_reference_steps(10**9, 2, capacity=REFERENCE_ARM_CAPACITY, time_budget_s=args.cpu_seconds)
+    cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": desc,
+           "replay": cpu_replay_baseline() if world == 1 else None}
+    torso = None
+    if dp and dp.get("w1"):
+        torso = dict(dp["w1"]["torso_fwd"], batch=4096, width=1,
+                     tensor_pipe_active_ncu="see profiles/ (ncu sm__pipe_tensor_op_hmma_cycles_active, not measurable live)")
     line = {
         "metric": "iS-DQN K=9 learner updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(cap),
-        "clocks": clk.summary(),
+        "clocks": clocks,
         "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps,
                 "pipeline": "host numpy batches as rb.sample() returns them with pinned_ring=16 (views of a pinned block in "
@@ -469,38 +624,35 @@ def run_ours(args, rank, world, local_rank):
         "acting_us_per_action": acting_us,
         "acting": acting,
         "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 5)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
-        "fill": {"adds": n_fill, "seconds": t_fill},
+        "fill": {"adds": n_fill, "seconds": t_fill, "us_per_add": t_fill / n_fill * 1e6, "path": "ReplayBuffer.add_batch (4096 per call)",
+                 "per_transition_add_us": t_one / n_one * 1e6},
+        "fp32": fp32,
+        "torso": torso,
+        "dp": dp,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_dp(args, rank, world, local_rank):
-    """BASELINE configs[4]: large-batch (default 4096, CNN x2) data-parallel learner; strong scaling over N GPUs."""
+def dp_measure(args, rank, world, local_rank, Bg, width, steps, warmup, dist=None):
+    """One configuration of the data-parallel learner: global batch Bg split over `world` ranks (same draws on every rank,
+    replicated storage), NCCL gradient all-reduce inside the step.  Returns the record (identical on every rank)."""
     import torch
 
-    torch.cuda.set_device(local_rank)
-    import torch.distributed as dist
-
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from isdqn_b200 import _lib
     from isdqn_b200.distributed import init_data_parallel, shard_bounds
     from isdqn_b200.networks.isdqn import iSDQN
-    from isdqn_b200.sample_collection.replay_buffer import ReplayBuffer, TransitionElement
+    from isdqn_b200.sample_collection.replay_buffer import ReplayBuffer
     from isdqn_b200.sample_collection.samplers import UniformSamplingDistribution
 
-    Bg = args.batch or 4096
-    width = args.width or 2
     feats = [f * width for f in FEATURES]
     lo, hi = shard_bounds(Bg, rank, world)
     Bl = hi - lo
-    cap = min(args.capacity, 200_000)
+    cap = min(args.capacity, 50_000)
     rb = ReplayBuffer(UniformSamplingDistribution(0), Bg, cap, stack_size=4, update_horizon=1, gamma=GAMMA,
                       frame_capacity=cap + cap // 8 + 64)  # replicated storage, same seed => same draws on every rank
-    for obs, a, r, d in synthetic_stream(1000, cap + 64):
-        rb.add(TransitionElement(obs, a, r, d, d))
+    fill_replay(rb, 1000, cap + 64)
     agent = iSDQN(0, OBS, N_ACTIONS, K_HEADS, feats, True, False, "cnn", LR, GAMMA, 1, 1, 8000, adam_eps=ADAM_EPS,
                   compute_dtype="bfloat16" if args.dtype == "bf16" else "float32")
     if world > 1:
@@ -521,19 +673,21 @@ def run_dp(args, rank, world, local_rank):
             batch = rb._gather_slots_device(d_slot[lo:hi].contiguous(), out=bufs)
             agent.learn_on_batch(agent.params, agent.optimizer_state, batch)
 
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             step()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clk:
             ev0.record()
-            for _ in range(args.steps):
+            for _ in range(steps):
                 step()
             ev1.record()
             barrier()
         ms = ev0.elapsed_time(ev1)
+        use_graph = agent._use_graph
         agent._use_graph = False
         prof = _lib.profile(step)
+        agent._use_graph = use_graph
     per_kernel = {}
     for name, t in prof:
         per_kernel.setdefault(name, [0, 0.0])
@@ -543,25 +697,49 @@ def run_dp(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     ms = float(t_max.item())
+    P = agent.network.n_params
+    flops = Bg * flops_per_transition(feats)
+    torso = sum(v[1] for k, v in per_kernel.items() if k in ("tc_conv_fwd", "tc_conv_fwd_tma", "conv_fwd"))
+    torso_flops = 2 * Bl * torso_fwd_flops(feats)
+    ar = sum(v[1] for k, v in per_kernel.items() if k.startswith("nccl_allreduce"))
+    rec = {
+        "value": steps / (ms / 1e3), "unit": "updates/s", "scaling": "strong", "global_batch": Bg, "local_batch": Bl, "width": width,
+        "features": feats, "params": P, "steps": steps, "ms_per_step": ms / steps,
+        "transitions_per_s": Bg * steps / (ms / 1e3), "learner_tflops": flops * steps / (ms / 1e3) / 1e12,
+        "allreduce": {"bytes": 4 * P, "ms_serial": ar, "note": "duration of the all-reduce launches in a serialised, event-timed "
+                      "replay of one step (rank 0); inside the timed steps part of it overlaps the backward pass"} if world > 1 else None,
+        "torso_fwd": {"ms": torso, "tflops": torso_flops / (torso / 1e3) / 1e12 if torso > 0 else None,
+                      "frac_of_sustained": (torso_flops / (torso / 1e3) / 1e12 / peaks["tflops_sustained"]) if torso > 0 else None,
+                      "peak_tflops_sustained": peaks["tflops_sustained"]},
+        "clocks": clk.summary(),
+        "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
+    }
+    del rb, agent
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_dp(args, rank, world, local_rank):
+    """BASELINE configs[4] on its own (`--mode dp`): large-batch (default 4096, CNN x2) data-parallel learner."""
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    Bg, width = args.batch or 4096, args.width or 2
+    rec = dp_measure(args, rank, world, local_rank, Bg, width, args.steps, args.warmup, dist=dist)
     if rank == 0:
-        # FLOPs per transition scale with width^2 for every layer but the first conv (x width) and the head (x width)
-        P = agent.network.n_params
-        flops = Bg * flops_per_transition(feats)
-        torso = sum(v[1] for k, v in per_kernel.items() if k in ("tc_conv_fwd", "tc_conv_fwd_tma", "conv_fwd"))
-        torso_flops = 2 * Bl * torso_fwd_flops(feats)
         line = {
-            "metric": "iS-DQN K=9 learner updates/sec (data parallel)", "value": args.steps / (ms / 1e3), "unit": "updates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": "iS-DQN K=9 learner updates/sec (data parallel)", "value": rec["value"], "unit": "updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"large-batch iS-DQN K=9 data parallel, global batch {Bg}, CNN width x{width} "
-                                   "(BASELINE.json configs[4])", "global_batch": Bg, "features": feats, "params": P,
-                       "parallelism": f"dp{world}: NCCL all-reduce of the {4 * P / 1e6:.1f} MB fp32 gradient"},
-            "clocks": clk.summary(),
-            "transitions_per_s": Bg * args.steps / (ms / 1e3),
-            "learner_tflops": flops * args.steps / (ms / 1e3) / 1e12,
-            "torso_fwd": {"ms": torso, "tflops": torso_flops / (torso / 1e3) / 1e12 if torso > 0 else None,
-                          "frac_of_bf16_peak": (torso_flops / (torso / 1e3) / 1e12 / peaks["tflops_sustained"]) if torso > 0 else None},
-            "step_kernels_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
+                                   "(BASELINE.json configs[4])", "global_batch": Bg, "features": rec["features"], "params": rec["params"],
+                       "parallelism": f"dp{world}: NCCL all-reduce of the {4 * rec['params'] / 1e6:.1f} MB fp32 gradient"},
+            "clocks": rec["clocks"], "transitions_per_s": rec["transitions_per_s"], "learner_tflops": rec["learner_tflops"],
+            "torso_fwd": rec["torso_fwd"], "allreduce": rec["allreduce"], "step_kernels_ms": rec["step_kernels_ms"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -594,6 +772,7 @@ def main():
                          "global batch split over the GPUs, NCCL gradient all-reduce (strong scaling, configs[4])")
     ap.add_argument("--batch", type=int, default=None, help="dp mode: global batch (default 4096)")
     ap.add_argument("--width", type=int, default=None, choices=[1, 2, 4], help="dp mode: CNN width multiplier (default 2)")
+    ap.add_argument("--no-dp", action="store_true", help="agents mode: skip the data-parallel sub-records (configs[4])")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"],
                     help="bf16: tcgen05 tensor-core path (fp32 accumulate/master weights); f32: CUDA-core fp32 parity path")
     args = ap.parse_args()

@@ -54,7 +54,7 @@ def init_data_parallel(agent, group=None) -> None:
     uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
     comm = C.c_void_p()
     _lib.check(lib.isdqn_dp_init(uid, rank, world, C.byref(comm)), "isdqn_dp_init")
-    agent.enable_data_parallel(comm, world)
+    agent.enable_data_parallel(comm, world, rank)
     sync_from_rank0(agent, group)
 
 

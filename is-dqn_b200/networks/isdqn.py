@@ -113,6 +113,7 @@ class iSDQN:
         self._ctx = {}  # batch size -> persistent buffers + captured graph
         self._nccl_comm = None
         self._dp_world = 1
+        self._dp_rank = 0
         self._side_stream = None
         self._copy_stream = None
         self._loss_ring = None
@@ -138,11 +139,12 @@ class iSDQN:
         self._d_cumulated.copy_(self._torch.as_tensor(np.asarray(value, dtype=np.float64)))
 
     # ----------------------------------------------------------------------------------------- data parallel
-    def enable_data_parallel(self, comm_handle: int, world_size: int) -> None:
+    def enable_data_parallel(self, comm_handle: int, world_size: int, rank: int = 0) -> None:
         """Large-batch data-parallel mode (new functionality): every rank runs the step on its
         slice of the global batch; gradients are all-reduced over NCCL before the (replicated) Adam step."""
         self._nccl_comm = comm_handle
         self._dp_world = int(world_size)
+        self._dp_rank = int(rank)
         self._ctx.clear()
 
     # ------------------------------------------------------------------------------------------- step context
@@ -357,7 +359,19 @@ class iSDQN:
                 replay_buffer.update_device(d_keys, self.td_abs(B), prio_rows=self.n_bellman_iterations,
                                             offset=self.prioritized_eps)
                 return
-            if device_rb:
+            if self._dp_world > 1:
+                # data parallel: the replay buffer's batch is the GLOBAL batch — the same draw on every rank (replicated
+                # storage, same sampler seed) — and this rank learns from its contiguous slice of it
+                from ..distributed import shard_batch, shard_bounds
+
+                Bg = replay_buffer._batch_size
+                lo, hi = shard_bounds(Bg, self._dp_rank, self._dp_world)
+                if device_rb:
+                    _, _, d_slot = replay_buffer._sampling_distribution.sample_device(Bg, replay_buffer._slots)
+                    batch_samples = replay_buffer._gather_slots_device(d_slot[lo:hi].contiguous(), out=self.batch_buffers(hi - lo))
+                else:
+                    batch_samples = shard_batch(replay_buffer.sample(), self._dp_rank, self._dp_world)
+            elif device_rb:
                 B = replay_buffer._batch_size
                 batch_samples = replay_buffer.sample_device(out=self.batch_buffers(B))
             else:
@@ -373,9 +387,18 @@ class iSDQN:
             # Window shift
             self.params = self.shift_params(self.params)
 
-            cumulated = self.cumulated_losses
             if self._dp_world > 1:
-                cumulated = cumulated  # per-rank share; callers all-reduce K floats when they log
+                # every rank holds its share of the global means (loss sums use 1 / B_global): K floats, summed when logged
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized():
+                    if dist.get_backend() == "nccl":
+                        dist.all_reduce(self._d_cumulated)
+                    else:
+                        h = self._d_cumulated.cpu()
+                        dist.all_reduce(h)
+                        self._d_cumulated.copy_(h)
+            cumulated = self.cumulated_losses
             logs = {
                 "loss": np.mean(cumulated) / (self.target_update_frequency / self.data_to_update),
             }

@@ -18,7 +18,10 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "iS-DQN K=9 learner updates/sec" and d["unit"] == "updates/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] >= 1 and d["value"] > 0
     assert d["config"]["batch"] == 32 and d["config"]["K"] == 9 and d["config"]["features"] == [32, 64, 64, 512]
-    assert d["config"]["replay_capacity"] == 1_000_000  # the CUDA arm's default workload
+    # same workload as the CUDA arm, and the capacity the CPU arm REALLY held (a bounded sample), stated as such
+    assert d["config"]["replay_capacity"] == 20_000 and "1000000" in d["config"]["replay_capacity_note"]
+    rp = d["cpu_baseline"]["replay"]  # the replay half of the metric on the host cores
+    assert rp["rb_sample32_samples_per_s"] > 0 and rp["sumtree_query32_samples_per_s"] > 0 and rp["sumtree_set32_leaves_per_s"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
