@@ -238,26 +238,36 @@ constexpr int kFirstProducerWarp = 5;
 //   __device__ void k_range(int z, int& kc_begin, int& kc_end) const;          (64-element chunks, never empty)
 //   __device__ void load_a(const PCtx&, uint32_t stage_smem, int kc, int ptid) const;   load_b(...)
 //   __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int z, int etid) const;
+// shared-memory objects of one CTA besides the dynamic stage ring (declared by the kernel, sized for its problem(s))
+struct TcShared {
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  uint64_t* tmem_full_bar;
+  uint64_t* tmem_empty_bar;
+  uint32_t* tmem_base_sh;
+  uint8_t* extra_sm;
+  float* ep_sm;
+  uint32_t* ep_stage;
+};
+
+// The whole CTA program for problem P: this CTA is number `cta` of the `n_ctas` that share P's tiles.
 template <class P>
-__global__ void __launch_bounds__(32 * (kFirstProducerWarp + P::PRODUCER_WARPS), P::MIN_CTAS)
-tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_z) {
+__device__ __forceinline__ void tc_gemm_body(const P& p, int tiles_x, int tiles_y, int tiles_z, int cta, int n_ctas,
+                                             uint8_t* smem_dyn, const TcShared& sh) {
   constexpr int BN = P::BN, STAGES = P::STAGES;
   constexpr int B_BYTES = BN * kBK * 2;
   constexpr int PT = 32 * P::PRODUCER_WARPS;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * BN);
   static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
-  extern __shared__ uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ uint32_t tmem_base_sh;
-  __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
-  __shared__ __align__(16) float ep_sm[P::EP_FLOATS > 0 ? P::EP_FLOATS : 4];
-  __shared__ __align__(16) uint32_t ep_stage[uses_ep_stage<P>::value ? kEpilogueWarps * kEpStageWords : 4];
+  uint64_t* full_bar = sh.full_bar;
+  uint64_t* empty_bar = sh.empty_bar;
+  uint64_t* tmem_full_bar = sh.tmem_full_bar;
+  uint64_t* tmem_empty_bar = sh.tmem_empty_bar;
+  uint8_t* extra_sm = sh.extra_sm;
+  float* ep_sm = sh.ep_sm;
+  uint32_t* ep_stage = sh.ep_stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  trace_kernel_start();
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * kABytes;
   const int n_tiles = tiles_x * tiles_y * tiles_z;
@@ -276,13 +286,13 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
     mbar_fence_init();
   }
   if (warp == 0) {
-    tmem_alloc(&tmem_base_sh, TMEM_COLS);
+    tmem_alloc(sh.tmem_base_sh, TMEM_COLS);
     tmem_relinquish();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_d = tmem_base_sh;
+  const uint32_t tmem_d = *sh.tmem_base_sh;
   if (tid == 0) trace_mark(1);  // prologue done (barriers, TMEM)
 #if !ISDQN_PDL_LATE
   pdl_trigger();  // (after the TMEM allocation: see common.cuh)
@@ -297,7 +307,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
       p.tma_prefetch();
       pdl_wait_then_trigger();
       int j = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = cta; t < n_tiles; t += n_ctas) {
         const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
         int kb, ke;
         p.k_range(tz, kb, ke);
@@ -316,13 +326,14 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
    } else {
     // ------------------------------------------------------------------------------------------ producers
     const int ptid = tid - 32 * kFirstProducerWarp;
+    if (ptid < PT) {  // (a two-problem kernel is launched with the larger producer count of the two)
     p.init_cta(extra_sm, ptid);  // index tables from the kernel arguments only: overlaps the previous kernel's tail
     pdl_wait_then_trigger();
     named_bar_sync(1, PT);
     typename P::PCtx ctx;
     int j = 0;  // chunk counter of this CTA (stage = j % STAGES)
     int ti = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+    for (int t = cta; t < n_tiles; t += n_ctas, ++ti) {
       const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
       const int m0 = tx * kBM, n0 = ty * BN;
       p.tile_producer(ctx, extra_sm, m0, n0, tz, ptid, ti);  // may publish per-row info in shared memory (parity ti & 1)
@@ -348,13 +359,14 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
       }
     }
     cp_async_wait_all();
+    }
    }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, P::A_MN, P::B_MN);
       int j = 0, ti = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      for (int t = cta; t < n_tiles; t += n_ctas, ++ti) {
         const int tz = t / (tiles_x * tiles_y);
         int kb, ke;
         p.k_range(tz, kb, ke);
@@ -389,7 +401,7 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
       p.init_epilogue(ectx, ep_sm, tid);
       named_bar_sync(2, 32 * kEpilogueWarps);
     }
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+    for (int t = cta; t < n_tiles; t += n_ctas, ++ti) {
       const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, tz = t / (tiles_x * tiles_y);
       const int m0 = tx * kBM, n0 = ty * BN;
       const int a = ti & 1;
@@ -407,6 +419,48 @@ tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_
   __syncthreads();
   if (tid == 0) trace_mark(6);  // all roles of CTA 0 done
   if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <class P>
+__global__ void __launch_bounds__(32 * (kFirstProducerWarp + P::PRODUCER_WARPS), P::MIN_CTAS)
+tc_gemm_kernel(const __grid_constant__ P p, int tiles_x, int tiles_y, int tiles_z) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[P::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[P::STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ __align__(16) uint8_t extra_sm[P::EXTRA_BYTES > 0 ? P::EXTRA_BYTES : 16];
+  __shared__ __align__(16) float ep_sm[P::EP_FLOATS > 0 ? P::EP_FLOATS : 4];
+  __shared__ __align__(16) uint32_t ep_stage[uses_ep_stage<P>::value ? kEpilogueWarps * kEpStageWords : 4];
+  trace_kernel_start();
+  const TcShared sh = {full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, &tmem_base_sh, extra_sm, ep_sm, ep_stage};
+  tc_gemm_body<P>(p, tiles_x, tiles_y, tiles_z, (int)blockIdx.x, (int)gridDim.x, smem_dyn, sh);
+}
+
+// Two independent problems in ONE launch: CTAs [0, ctas1) run P1's tiles, the others P2's.  For short dependent chains
+// (the batch-32 backward pass) where the weight gradient and the input gradient of a layer consume the same dz: one launch
+// latency instead of two, and the two half-empty waves share the GPU.  Both problems must use the same thread count.
+__host__ __device__ constexpr int tc_cmax(int a, int b) { return a > b ? a : b; }
+template <class P1, class P2>
+__global__ void __launch_bounds__(32 * (kFirstProducerWarp + tc_cmax(P1::PRODUCER_WARPS, P2::PRODUCER_WARPS)), 1)
+tc_gemm2_kernel(const __grid_constant__ P1 p1, int t1x, int t1y, int t1z, const __grid_constant__ P2 p2, int t2x, int t2y, int t2z,
+                int ctas1) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[tc_cmax(P1::STAGES, P2::STAGES)];
+  __shared__ __align__(8) uint64_t empty_bar[tc_cmax(P1::STAGES, P2::STAGES)];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ __align__(16) uint8_t extra_sm[tc_cmax(tc_cmax(P1::EXTRA_BYTES, P2::EXTRA_BYTES), 16)];
+  __shared__ __align__(16) float ep_sm[tc_cmax(tc_cmax(P1::EP_FLOATS, P2::EP_FLOATS), 4)];
+  __shared__ __align__(16) uint32_t ep_stage[(uses_ep_stage<P1>::value || uses_ep_stage<P2>::value) ? kEpilogueWarps * kEpStageWords : 4];
+  trace_kernel_start();
+  const TcShared sh = {full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, &tmem_base_sh, extra_sm, ep_sm, ep_stage};
+  if ((int)blockIdx.x < ctas1)
+    tc_gemm_body<P1>(p1, t1x, t1y, t1z, (int)blockIdx.x, ctas1, smem_dyn, sh);
+  else
+    tc_gemm_body<P2>(p2, t2x, t2y, t2z, (int)blockIdx.x - ctas1, (int)gridDim.x - ctas1, smem_dyn, sh);
 }
 
 }  // namespace tc

@@ -598,6 +598,156 @@ int launch_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* 
 #undef ISDQN_CONV_DGRAD_TMA
 }
 
+// ---- weight gradient + input gradient of one layer in ONE launch (small batches) -------------------------------------------
+// Both consume the same dz and neither reads what the other writes.  At batch 32 each of them is a fraction of a wave and
+// costs a full launch latency on the critical path of the backward chain; together they fill the GPU once.
+template <class P1, class P2>
+int launch_tc2(const P1& p1, int t1x, int t1y, int t1z, int ctas1, const P2& p2, int t2x, int t2y, int t2z, int ctas2,
+               cudaStream_t s, const char* tag) {
+  constexpr size_t sm1 = tc::smem_bytes<P1::BN, P1::STAGES>(), sm2 = tc::smem_bytes<P2::BN, P2::STAGES>();
+  constexpr size_t smem = sm1 > sm2 ? sm1 : sm2;
+  constexpr int pw = P1::PRODUCER_WARPS > P2::PRODUCER_WARPS ? P1::PRODUCER_WARPS : P2::PRODUCER_WARPS;
+  constexpr int threads = 32 * (tc::kFirstProducerWarp + pw);
+  ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm2_kernel<P1, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ctas1 < 1 || ctas2 < 1) return ISDQN_E_INVALID;
+  ISDQN_PROF(s, tag);
+  ISDQN_CUDA_CHECK(launch_pdl((tc::tc_gemm2_kernel<P1, P2>), dim3(ctas1 + ctas2), dim3(threads), smem, s, p1, t1x, t1y, t1z, p2,
+                              t2x, t2y, t2z, ctas1));
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+bool pair_launch_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int BNW>
+int build_conv_wgrad_tma(const Layer& V, const bf16* x, const bf16* dz, float* part, int n_img, int splits, float in_scale,
+                         int ksz_x, int sy, tc::ConvWgradTmaTC<BNW, true>* p, int* tiles_k, int* real_splits) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (ksz_x == 0) ksz_x = V.ksz;
+  const int wb = V.OW <= 16 ? 16 : V.OW <= 32 ? 32 : 64, rpc = 64 / wb;
+  const int cpi = ceil_div(V.OH, rpc);
+  const int total_chunks = n_img * cpi;
+  if (splits > total_chunks) splits = total_chunks;
+  if (splits < 1) splits = 1;
+  const int cps = ceil_div(total_chunks, splits);
+  *real_splits = ceil_div(total_chunks, cps);
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)V.Cin, (cuuint64_t)V.W, (cuuint64_t)V.H, (cuuint64_t)n_img};
+    const cuuint64_t strides[3] = {(cuuint64_t)V.Cin * 2, (cuuint64_t)V.W * V.Cin * 2, (cuuint64_t)V.H * V.W * V.Cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)wb, (cuuint32_t)(sy * (rpc - 1) + 1), 1};
+    const cuuint32_t es[4] = {1, 1, (cuuint32_t)sy, 1};
+    if (enc(&p->tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)V.out_dim, (cuuint64_t)V.OW, (cuuint64_t)V.OH, (cuuint64_t)n_img};
+    const cuuint64_t strides[3] = {(cuuint64_t)V.out_dim * 2, (cuuint64_t)V.OW * V.out_dim * 2, (cuuint64_t)V.OH * V.OW * V.out_dim * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)wb, (cuuint32_t)rpc, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&p->tm_dz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(dz), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  *tiles_k = ceil_div(V.in_dim, tc::kBM);
+  p->K = V.in_dim; p->Cout = V.out_dim; p->cchunks = V.Cin / 64;
+  p->ksz_x = ksz_x; p->sy = sy; p->pad_y = V.pad_y; p->pad_x = V.pad_x; p->rpc = rpc; p->cpi = cpi;
+  p->total_chunks = total_chunks; p->chunks_per_split = cps; p->part = part; p->acc_scale = in_scale;
+  return ISDQN_OK;
+}
+
+template <int BND>
+int build_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, tc::ConvDgradTmaTC<BND, true>* p) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  const int st = L.stride;
+  for (int cls = 0; cls < st * st; ++cls) {
+    const int ry = cls / st, rx = cls % st;
+    const int iy_first = ((ry - L.pad_y) % st + st) % st, ix_first = ((rx - L.pad_x) % st + st) % st;
+    int ny = iy_first < L.H ? (L.H - iy_first + st - 1) / st : 0;
+    int nx = ix_first < L.W ? (L.W - ix_first + st - 1) / st : 0;
+    if (ny < 1) ny = 1;
+    if (nx < 1) nx = 1;
+    const cuuint64_t dims[4] = {(cuuint64_t)L.out_dim, (cuuint64_t)L.OW, (cuuint64_t)L.OH, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)L.out_dim * 2, (cuuint64_t)L.OW * L.out_dim * 2, (cuuint64_t)L.OH * L.OW * L.out_dim * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)nx, (cuuint32_t)ny, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&p->tm_dz[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(dz), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ISDQN_E_CUDA;
+  }
+  for (int cls = st * st; cls < 4; ++cls) p->tm_dz[cls] = p->tm_dz[0];
+  if (encode_matrix_map(&p->tm_w, w, L.out_dim, (int64_t)L.ksz * L.ksz * L.Cin, L.out_dim, 64, BND)) return ISDQN_E_CUDA;
+  p->H = L.H; p->W = L.W; p->Cin = L.Cin; p->Cout = L.out_dim; p->ksz = L.ksz;
+  p->stride = L.stride; p->pad_y = L.pad_y; p->pad_x = L.pad_x; p->n_img = B; p->cchunks = L.out_dim / 64;
+  p->dx = dx;
+  return ISDQN_OK;
+}
+
+// V: the weight gradient's view of the layer (as for launch_conv_wgrad_tma); L: the layer itself (input gradient).
+bool conv_bwd_pair_ok(const Layer& V, const Layer& L, int B) {
+  if (!pair_launch_enabled() || B > 64 || !conv_wgrad_tma_ok(V) || !conv_dgrad_tma_ok(L)) return false;
+  if (!(V.out_dim == 64 || V.out_dim == 128)) return false;
+  const int bnd = pick_bn(L.Cin);
+  if (!(bnd == 32 || bnd == 64 || bnd == 128)) return false;
+  const int64_t dgrad_tiles = (int64_t)B * ceil_div(L.Cin, bnd) * L.stride * L.stride;
+  return dgrad_tiles <= 2 * kNumSMs;
+}
+
+template <int BNW, int BND>
+int launch_conv_bwd_pair_t(const Layer& V, const bf16* x, const bf16* dz, float* part, int B, int max_splits, int* real_splits,
+                           float in_scale, int ksz_x, int sy, const Layer& L, const bf16* w, float* dx, cudaStream_t s) {
+  tc::ConvWgradTmaTC<BNW, true> pw;
+  tc::ConvDgradTmaTC<BND, true> pd;
+  const int st = L.stride;
+  const int d_tiles = B * ceil_div(L.Cin, BND) * st * st;
+  const int taps = ceil_div(L.ksz, st);
+  const int wb = V.OW <= 16 ? 16 : V.OW <= 32 ? 32 : 64, cpi = ceil_div(V.OH, 64 / wb);
+  const int tiles_k0 = ceil_div(V.in_dim, tc::kBM);
+  // split the SMs in proportion to the chunk loads of the two problems (+ ~4 chunk times per tile for its epilogue)
+  const double work_d = (double)d_tiles * (taps * taps * (L.out_dim / 64) + 4);
+  const double work_w = (double)tiles_k0 * B * cpi + 4.0 * tiles_k0 * 8;
+  int ctas_d = (int)(kNumSMs * work_d / (work_d + work_w) + 0.5);
+  if (ctas_d < 1) ctas_d = 1;
+  if (ctas_d > d_tiles) ctas_d = d_tiles;
+  ctas_d = ceil_div(d_tiles, ceil_div(d_tiles, ctas_d));  // every CTA the same number of tiles
+  if (ctas_d > kNumSMs - tiles_k0) ctas_d = kNumSMs - tiles_k0;
+  int splits = (kNumSMs - ctas_d) / tiles_k0;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int tiles_k = 0;
+  int rc = build_conv_wgrad_tma<BNW>(V, x, dz, part, B, splits, in_scale, ksz_x, sy, &pw, &tiles_k, real_splits);
+  if (rc) return rc;
+  rc = build_conv_dgrad_tma<BND>(L, dz, w, dx, B, &pd);
+  if (rc) return rc;
+  return launch_tc2(pw, tiles_k, 1, *real_splits, tiles_k * *real_splits, pd, B, ceil_div(L.Cin, BND), st * st, ctas_d, s,
+                    "tc_conv_wgrad_dgrad");
+}
+
+int launch_conv_bwd_pair(const Layer& V, const bf16* x, const bf16* dz, float* part, int B, int max_splits, int* real_splits,
+                         float in_scale, int ksz_x, int sy, const Layer& L, const bf16* w, float* dx, cudaStream_t s) {
+  const int bnd = pick_bn(L.Cin);
+#define ISDQN_PAIR(BNW, BND) \
+  return launch_conv_bwd_pair_t<BNW, BND>(V, x, dz, part, B, max_splits, real_splits, in_scale, ksz_x, sy, L, w, dx, s);
+  if (V.out_dim == 64) {
+    if (bnd == 32) ISDQN_PAIR(64, 32)
+    if (bnd == 64) ISDQN_PAIR(64, 64)
+    if (bnd == 128) ISDQN_PAIR(64, 128)
+  } else if (V.out_dim == 128) {
+    if (bnd == 32) ISDQN_PAIR(128, 32)
+    if (bnd == 64) ISDQN_PAIR(128, 64)
+    if (bnd == 128) ISDQN_PAIR(128, 128)
+  }
+#undef ISDQN_PAIR
+  return ISDQN_E_UNSUPPORTED;
+}
+
 int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s) {
   if (conv_dgrad_tma_ok(L)) return launch_conv_dgrad_tma(L, dz, w, dx, B, s);
   const int taps = ceil_div(L.ksz, L.stride);
@@ -835,6 +985,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     }
     const bool side = fork && l > 0;
     cudaStream_t sw = side ? s2 : s;
+    bool paired_dgrad = false;  // the input gradient of this layer was computed by the weight-gradient launch
     if (side || (fmode == 2 && pend_n > 0)) {
       rc = fork_to_side();  // everything the main stream has produced so far (dz of this layer, the input gradient above)
       if (rc) return rc;
@@ -887,7 +1038,26 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
         const char* e = getenv("ISDQN_TMA_WGRAD");
         return !(e && e[0] == '0');
       }();
-      if (l == 0 && t.w0p >= 0) {  // space-to-depth frames (128-byte taps); partials come out in s2d K order
+      if (l > 0 && !side && wgrad_tma) {  // small batch: this layer's weight gradient and input gradient in one launch
+        Layer V = L;
+        int kx = 0, sy = 1;
+        bool view_ok = L.stride == 1;
+        if (l == 1 && t.pair_view) {  // the pair-of-pixels view of the padded activation (as in the forward pass)
+          V.W = (L.W + 1) / 2;
+          V.Cin = 2 * L.Cin;
+          V.pad_x = 0;
+          kx = 2;
+          sy = 2;
+          view_ok = true;
+        }
+        if (view_ok && conv_bwd_pair_ok(V, L, B)) {
+          rc = launch_conv_bwd_pair(V, w16(wt, t.act16[l - 1]), dz16, part, B, w.wsplits_tc[l], &real_splits, 1.0f, kx, sy, L,
+                                    shadow + L.w_off, wsp(ws, w.dbuf[l & 1]), s);
+          paired_dgrad = true;
+        }
+      }
+      if (paired_dgrad) {
+      } else if (l == 0 && t.w0p >= 0) {  // space-to-depth frames (128-byte taps); partials come out in s2d K order
         const Layer S = s2d_layer(L);
         if (wgrad_tma && conv_wgrad_tma_ok(S))
           rc = launch_conv_wgrad_tma(S, w16(wt, t.x16), dz16, part, B, w.wsplits_tc[l], &real_splits, sw, 1.0f / 255.0f, 0, 1);
@@ -947,7 +1117,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     } else if (L.type == 1) {
       rc = launch_gemm_tc<false, false>(dz16, L.out_dim, shadow + L.w_off, L.out_dim, dprev, L.in_dim, 0, B, L.in_dim,
                                         L.out_dim, 1, s, "tc_dense_dgrad");
-    } else {
+    } else if (!paired_dgrad) {
       rc = launch_conv_dgrad_tc(L, dz16, shadow + L.w_off, dprev, B, s);
     }
     if (rc) return rc;
