@@ -53,8 +53,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
-    while (ld_acquire_u32(bar) < target) {
-    }
+    // (a CTA that never arrives — the grid was not co-resident after all — must fault, not hang the GPU; the launch is
+    // cooperative, so the runtime refuses a grid that cannot be resident, and this bound is the second line of defence)
+    for (unsigned spins = 0; ld_acquire_u32(bar) < target; ++spins)
+      if (spins > (1u << 24)) __trap();
   }
   __syncthreads();
 }
@@ -364,12 +366,29 @@ int build_act_plan(const isdqn_net* net, const Plan& p, int grid, ActPlan* a, in
 
 int isdqn_trace_set_acting(unsigned long long* buf) { return isdqn::trace_set_local(buf) == cudaSuccess ? ISDQN_OK : ISDQN_E_CUDA; }
 
+// one CTA per SM of THIS device must be co-resident for the grid barrier (checked once per device)
+static int act_grid_ctas() {
+  static PerDevice<int> grid;
+  int& g = grid.get();
+  if (g == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, act_forward_kernel, kActThreads, 0) != cudaSuccess) per_sm = 0;
+    int dev = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    g = (per_sm >= 1 && coop) ? num_sms() : -1;
+  }
+  return g;
+}
+
 extern "C" int64_t isdqn_act_workspace_bytes(const isdqn_net* net) {
   Plan p;
   if (build_plan(net, &p)) return -1;
+  const int G = act_grid_ctas();
+  if (G < 1) return 0;  // no co-resident grid on this device: the caller keeps the layer chain
   ActPlan a;
   int64_t floats = 0;
-  const int rc = build_act_plan(net, p, kNumSMs, &a, &floats);
+  const int rc = build_act_plan(net, p, G, &a, &floats);
   if (rc == ISDQN_E_UNSUPPORTED) return 0;
   if (rc) return -1;
   return floats * (int64_t)sizeof(float);
@@ -381,26 +400,20 @@ extern "C" int isdqn_act(const isdqn_net* net, const float* d_params, const uint
   Plan p;
   int rc = build_plan(net, &p);
   if (rc) return rc;
+  const int G = act_grid_ctas();
+  if (G < 1) return ISDQN_E_UNSUPPORTED;
   ActPlan a;
   int64_t floats = 0;
-  rc = build_act_plan(net, p, kNumSMs, &a, &floats);
+  rc = build_act_plan(net, p, G, &a, &floats);
   if (rc) return rc;
   if (floats * (int64_t)sizeof(float) > workspace_bytes) return ISDQN_E_INVALID;
-  static int resident = -1;  // one CTA per SM must be resident for the grid barrier
-  if (resident < 0) {
-    int per_sm = 0, dev = 0, sms = 0;
-    ISDQN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, act_forward_kernel, kActThreads, 0));
-    ISDQN_CUDA_CHECK(cudaGetDevice(&dev));
-    ISDQN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    resident = per_sm * sms;
-  }
-  if (resident < kNumSMs) return ISDQN_E_UNSUPPORTED;
   cudaStream_t s = as_stream(stream);
   ISDQN_PROF(s, "act_forward");
   float* scratch = reinterpret_cast<float*>(d_workspace);
-  act_forward_kernel<<<kNumSMs, kActThreads, 0, s>>>(a, d_params, d_obs, scratch, reinterpret_cast<unsigned*>(d_workspace), d_q,
-                                                     d_actions);
-  ISDQN_LAUNCH_CHECK();
+  unsigned* bar = reinterpret_cast<unsigned*>(d_workspace);
+  // cooperative launch: the runtime guarantees (or refuses) the co-residency the grid barrier relies on
+  void* args[] = {(void*)&a, (void*)&d_params, (void*)&d_obs, (void*)&scratch, (void*)&bar, (void*)&d_q, (void*)&d_actions};
+  ISDQN_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(act_forward_kernel), dim3(G), dim3(kActThreads), args, 0, s));
   return ISDQN_OK;
 }
 

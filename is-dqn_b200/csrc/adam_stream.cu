@@ -264,10 +264,9 @@ int isdqn_dense_wgrad_adam_stream_launch(float* d_params, const float* d_grads, 
   while (stages > 1 && tp_smem_bytes(B, N, stages) > 225 * 1024) --stages;
   if (stages < 2) return ISDQN_E_UNSUPPORTED;
   const size_t smem = tp_smem_bytes(B, N, stages);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(dense_wgrad_adam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    attr_done = true;
   }
   ISDQN_PROF(as_stream(stream), "dense_wgrad_adam");
   ISDQN_CUDA_CHECK(launch_pdl(dense_wgrad_adam_stream_kernel, dim3((unsigned)kNumSMs), dim3(kTpThreads), smem, as_stream(stream), d_params,

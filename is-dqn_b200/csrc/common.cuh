@@ -28,6 +28,33 @@ void set_last_cuda_error(cudaError_t e, const char* where);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Function attributes (opt-in shared-memory sizes), occupancy results and side streams belong to ONE device context: caches
+// of them are kept per device, so that a process driving several GPUs (two agents behind torch.cuda.set_device) gets the
+// opt-in on each of them.  `first()` is true once per device for each PerDevice object.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices] = {};
+  T& get() { return v[current_device()]; }
+};
+// SM count of the current device (cached); the grid-sizing heuristics use the B200 constant kNumSMs, the kernels whose
+// CORRECTNESS depends on co-residency (acting: grid barrier) use this
+int num_sms();
+
 // Optional per-kernel timing (isdqn_profile_begin/end): every launch site marks its name; a mark records a CUDA
 // event on the launching stream, so consecutive marks bracket one kernel.  Off (one predictable branch) by default.
 extern bool g_profile_on;

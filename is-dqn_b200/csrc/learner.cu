@@ -417,10 +417,9 @@ int isdqn_dense_wgrad_adam_launch(float* d_params, const float* d_grads, float* 
   if (rest_ctas > kNumSMs) rest_ctas = kNumSMs;
   const size_t smem = dwa_smem_bytes(B, tpc);
   if (smem > 100 * 1024) return ISDQN_E_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(dense_wgrad_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_done = true;
   }
   ISDQN_PROF(as_stream(stream), "dense_wgrad_adam");
   co_resident_with_tc(dense_wgrad_adam_kernel);

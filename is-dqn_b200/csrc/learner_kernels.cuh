@@ -829,6 +829,60 @@ __host__ __device__ inline int s2d_to_hwio(int i, int cout) {
   const int by = tap >> 1, bx = tap & 1, py = q >> 4, px = (q >> 2) & 3, c = q & 3;
   return (((4 * by + py) * 8 + 4 * bx + px) * 4 + c) * cout + co;
 }
+// Cross-sample tail of the fused head step (head_mid_kernel): per-head loss means, head bias gradient, head kernel
+// gradient, computed by extra CTAs of the partial-reduction launch.  tdq is [B][2K]: [b][k] = d(loss)/dq at the taken
+// action of head k+1, [b][K + k] = the (weighted) squared TD error.
+struct HeadTail {
+  int ctas;  // 0: none
+  const float* tdq;
+  const int64_t* action;
+  const float* act;  // [B][C] hidden activations (fp32)
+  int B, K, A, C, NH;
+  float inv_b;
+  float* losses;
+  double* cumulated;
+  float* dbias;  // [NH]
+  float* dwh;    // [C][NH]
+};
+static inline int head_tail_ctas(int C, int NH) { return 1 + (C * NH + 255) / 256; }
+
+__device__ __forceinline__ void head_tail_block(const HeadTail& h, int j) {
+  const int tid = threadIdx.x;
+  if (j == 0) {
+    // losses[k] = mean_b w_b td^2 (isdqn.py:102), sequential over b: deterministic
+    if (tid < h.K) {
+      float t = 0.f;
+      for (int b = 0; b < h.B; ++b) t += h.tdq[(int64_t)b * 2 * h.K + h.K + tid];
+      const float l = t * h.inv_b;
+      h.losses[tid] = l;
+      if (h.cumulated) h.cumulated[tid] += (double)l;
+    }
+    // head bias gradient: column sums of dq; head 0 (the frozen target) receives none
+    for (int c = tid; c < h.NH; c += 256) {
+      const int hd = c / h.A - 1, a = c - (hd + 1) * h.A;
+      float t = 0.f;
+      if (hd >= 0)
+        for (int b = 0; b < h.B; ++b)
+          if ((int)h.action[b] == a) t += h.tdq[(int64_t)b * 2 * h.K + hd];
+      h.dbias[c] = t;
+    }
+    return;
+  }
+  const int o = (j - 1) * 256 + tid;
+  if (o >= h.C * h.NH) return;
+  const int n = o / h.NH, c = o - n * h.NH;
+  const int hd = c / h.A - 1, a = c - (hd + 1) * h.A;
+  float acc = 0.f;
+  if (hd >= 0) {
+    for (int b = 0; b < h.B; ++b) {
+      if ((int)h.action[b] != a) continue;
+      const float g = h.tdq[(int64_t)b * 2 * h.K + hd];
+      if (g != 0.f) acc = fmaf(h.act[(int64_t)b * h.C + n], g, acc);
+    }
+  }
+  h.dwh[o] = acc;
+}
+
 struct SegmentList {
   int count;
   int tile_start[kMaxSegments + 1];  // prefix sum of ceil(n / 32) over the segments (filled by finish_segments)
@@ -858,8 +912,12 @@ static inline bool segments_vec4_ok(const SegmentList& l) {
 // step is in flight at once): its 8 warps take the partials p = w, w+8, ... (independent loads), then the 8 warp sums
 // are combined in a fixed order => deterministic, and identical for VEC = 1 and VEC = 4.
 template <int VEC>
-__global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list) {
+__global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list, const HeadTail tail, int n_tiles) {
   pdl_sync();
+  if ((int)blockIdx.x >= n_tiles) {
+    head_tail_block(tail, (int)blockIdx.x - n_tiles);
+    return;
+  }
   __shared__ float sm[8][32 * VEC + 4];
   int seg = 0;
   while (seg + 1 < list.count && (int)blockIdx.x >= list.tile_start[seg + 1]) ++seg;
@@ -915,15 +973,17 @@ __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList 
   }
 }
 
-static inline cudaError_t launch_reduce_segments(SegmentList& segs, cudaStream_t s) {
+static inline cudaError_t launch_reduce_segments(SegmentList& segs, cudaStream_t s, const HeadTail* tail = nullptr) {
   co_resident_with_tc(reduce_segments_kernel<4>);
   co_resident_with_tc(reduce_segments_kernel<1>);
+  HeadTail none = {};
+  const HeadTail& ht = tail ? *tail : none;
   if (segments_vec4_ok(segs)) {
     const int n_tiles = finish_segments(&segs, 4);
-    return launch_pdl((reduce_segments_kernel<4>), dim3(n_tiles), dim3(256), 0, s, segs);
+    return launch_pdl((reduce_segments_kernel<4>), dim3(n_tiles + ht.ctas), dim3(256), 0, s, segs, ht, n_tiles);
   }
   const int n_tiles = finish_segments(&segs, 1);
-  return launch_pdl((reduce_segments_kernel<1>), dim3(n_tiles), dim3(256), 0, s, segs);
+  return launch_pdl((reduce_segments_kernel<1>), dim3(n_tiles + ht.ctas), dim3(256), 0, s, segs, ht, n_tiles);
 }
 
 // ------------------------------------------------------------------------------ K-head TD loss fwd + bwd
@@ -1047,11 +1107,10 @@ constexpr int kHeadMaxK = 3072;
 static inline cudaError_t launch_head_fwd(cudaStream_t s, const float* x, const float* w, const float* bias, int K, int N,
                                           float* out, int rows) {
   if (rows <= 1024) return launch_pdl((head_fwd_kernel<1>), dim3(rows), dim3(512), K * sizeof(float), s, x, w, bias, K, N, out, rows);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kHeadMaxK * 4);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   return launch_pdl((head_fwd_kernel<8>), dim3(ceil_div(rows, 8)), dim3(512), 8 * K * sizeof(float), s, x, w, bias, K, N, out, rows);
 }
@@ -1137,6 +1196,178 @@ dense_finalize_head_kernel(const float* __restrict__ part, int splits, int64_t s
   hpart[g][n] = acc;
   __syncthreads();
   if (g == 0 && n < NH) out_head[(int64_t)r * NH + n] = ((hpart[0][n] + hpart[1][n]) + (hpart[2][n] + hpart[3][n])) + bh[n];
+}
+
+// The whole middle of a small-batch step in ONE launch, one CTA per sample b (everything here is local to a sample):
+//   A  finish the last hidden Dense layer for rows b (s) and B + b (s'): split-K partial sum, bias, LayerNorm, ReLU
+//      (threads 0-255 row b, 256-511 row B + b; arithmetic order of dense_finalize_kernel)
+//   B  head layer for both rows, every head-kernel element loaded once for the two rows
+//   C  iterated TD targets and errors of the K online heads (isdqn.py:97-109), d(loss)/dq, |TD|
+//   D  head input gradient + ReLU / LayerNorm backward of the hidden layer for row b (the normalised values never
+//      leave the registers), bf16 dz for the tensor-core kernels below, column partials for the bias / LayerNorm gradients
+// It replaces dense_finalize_head + heads_td_loss + head_bwd (three dependent launches of the batch-32 chain); what
+// needs every sample — the K loss means, the head bias and kernel gradients — is left to head_tail_block.
+static __global__ void __launch_bounds__(512)
+head_mid_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int N, const float* __restrict__ bias,
+                const float* __restrict__ ln_g, const float* __restrict__ ln_b, int relu, float* __restrict__ out,
+                const float* __restrict__ wh, const float* __restrict__ bh, int NH, float* __restrict__ out_head,
+                const int64_t* __restrict__ action, const double* __restrict__ reward, const uint8_t* __restrict__ terminal,
+                float gamma_n, int B, int B_global, int K, int A, const float* __restrict__ is_weights,
+                float* __restrict__ td_abs, float* __restrict__ tdq, float* __restrict__ colpart,
+                __nv_bfloat16* __restrict__ dz16, int32_t* count) {
+  pdl_sync();
+  extern __shared__ float xs[];  // [2][N]
+  __shared__ float red[16];
+  __shared__ float hpart[2][4][128];
+  __shared__ float qs[2][128];
+  __shared__ float vals[kMaxHeads];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int half = tid >> 8, ht = tid & 255;
+  const int r = half ? B + b : b;
+  auto half_sum = [&](float v) {  // sum over the 256 threads of this thread's half, fixed order
+    v = warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[half * 8 + w];
+    __syncthreads();
+    return t;
+  };
+  if (count && b == 0 && tid == 0) *count += 1;  // the Adam step number of this update (read many launches later)
+  // ---- A
+  float z[kRowMaxPerThread], xh[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = ht + j * kRowThreads;
+    z[j] = xh[j] = gam[j] = bet[j] = 0.f;
+    if (n < N) {
+      float v = 0.f;
+      for (int sp = 0; sp < splits; ++sp) v += part[(int64_t)sp * split_stride + (int64_t)r * N + n];
+      z[j] = v + bias[n];
+      s += z[j];
+      if (ln_g) {
+        gam[j] = ln_g[n];
+        bet[j] = ln_b[n];
+      }
+    }
+  }
+  float rs = 0.f;
+  if (ln_g) {
+    const float mean = half_sum(s) / (float)N;
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = ht + j * kRowThreads;
+      if (n < N) {
+        z[j] -= mean;
+        s2 += z[j] * z[j];
+      }
+    }
+    rs = rsqrtf(half_sum(s2) / (float)N + kLnEps);
+  }
+  float* xrow = xs + half * N;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = ht + j * kRowThreads;
+    if (n < N) {
+      float y = z[j];
+      if (ln_g) {
+        xh[j] = z[j] * rs;
+        y = xh[j] * gam[j] + bet[j];
+      }
+      y = relu ? fmaxf(y, 0.f) : y;
+      out[(int64_t)r * N + n] = y;
+      xrow[n] = y;
+    }
+  }
+  __syncthreads();
+  // ---- B
+  {
+    const int n = tid & 127, g = tid >> 7;
+    float a0 = 0.f, a1 = 0.f;
+    if (n < NH) {
+      const int kq = (N + 3) / 4;
+      const int k_end = min(N, (g + 1) * kq);
+#pragma unroll 16
+      for (int k = g * kq; k < k_end; ++k) {
+        const float w = __ldg(wh + (int64_t)k * NH + n);
+        a0 = fmaf(xs[k], w, a0);
+        a1 = fmaf(xs[N + k], w, a1);
+      }
+    }
+    hpart[0][g][n] = a0;
+    hpart[1][g][n] = a1;
+    __syncthreads();
+    if (g < 2 && n < NH) {
+      const float q = ((hpart[g][0][n] + hpart[g][1][n]) + (hpart[g][2][n] + hpart[g][3][n])) + bh[n];
+      qs[g][n] = q;
+      out_head[(int64_t)(g ? B + b : b) * NH + n] = q;
+    }
+    __syncthreads();
+  }
+  // ---- C
+  const int act_b = (int)action[b];
+  if (tid < K) {
+    const int k = tid;
+    const float rw = (float)reward[b];                             // f64 -> f32 at the jit boundary
+    const float coef = (float)(1 - (int)terminal[b]) * gamma_n;    // ((1 - d) * gamma^n) in fp32
+    const float* qn = &qs[1][k * A];                               // Q_k(s', .)
+    float mx = qn[0];
+    for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
+    const float target = rw + coef * mx;
+    const float td = qs[0][(k + 1) * A + act_b] - target;
+    const float wb = is_weights ? is_weights[b] : 1.0f;
+    const float val = 2.0f * td * (1.0f / (float)B_global) * wb;
+    vals[k] = val;
+    tdq[(int64_t)b * 2 * K + k] = val;
+    tdq[(int64_t)b * 2 * K + K + k] = (wb * td) * td;
+    if (td_abs) td_abs[(int64_t)k * B + b] = fabsf(td);
+  }
+  __syncthreads();
+  // ---- D (row b: the first half of the CTA holds its normalised values)
+  float dy[kRowMaxPerThread];
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = ht + j * kRowThreads;
+    dy[j] = 0.f;
+    if (half == 0 && n < N) {
+      float dv = 0.f;
+      for (int i = 0; i < K; ++i) {
+        const float v = vals[i];
+        if (v != 0.f) dv = fmaf(v, __ldg(wh + (int64_t)n * NH + (i + 1) * A + act_b), dv);
+      }
+      if (ln_g) {
+        dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;
+        const float g = dy[j] * gam[j];
+        sg += g;
+        sgx += g * xh[j];
+      } else {
+        dy[j] = xs[n] > 0.f ? dv : 0.f;
+      }
+    }
+  }
+  float mg = 0.f, mgx = 0.f;
+  if (ln_g) {
+    const float inv_c = 1.0f / (float)N;
+    mg = half_sum(sg) * inv_c;
+    mgx = half_sum(sgx) * inv_c;
+  }
+  if (half == 0) {
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = ht + j * kRowThreads;
+      if (n < N) {
+        const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
+        dz16[(int64_t)b * N + n] = __float2bfloat16_rn(dz);
+        colpart[((int64_t)b * 3 + 0) * N + n] = dz;
+        colpart[((int64_t)b * 3 + 1) * N + n] = dy[j] * xh[j];
+        colpart[((int64_t)b * 3 + 2) * N + n] = dy[j];
+      }
+    }
+  }
 }
 
 // 1 / (1 - b^t) for both Adam decays, in double.  Two threads of different warps (the last lane of the last two warps)

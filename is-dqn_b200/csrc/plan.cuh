@@ -163,6 +163,7 @@ static inline int head_wgrad_splits(int B, int K, int N) {
   return s;
 }
 
+constexpr int kColpartFusedCap = 4 * kNumSMs;
 // LN/ReLU backward: <= 256 channels -> one warp per row (8 rows per CTA pass); wider -> one CTA per row
 static inline bool ln_bwd_use_warp(int C) { return C <= 256; }
 static inline int ln_bwd_ctas(int rows, int C) {
@@ -214,7 +215,10 @@ static inline void carve_workspace(const Plan& p, int rows, int B, Workspace* w)
       }
       if (L.relu) {
         w->col_ctas[l] = ln_bwd_ctas(B * L.pix, L.out_dim);
-        w->colpart[l] = take((int64_t)w->col_ctas[l] * 3 * L.out_dim);
+        // (conv layers of <= 64 channels: room for one partial per CTA of the input-gradient launch that fuses this
+        // layer's LayerNorm backward, tc_learner.cu)
+        const int cap = (L.type == 0 && L.out_dim <= 64 && w->col_ctas[l] < kColpartFusedCap) ? kColpartFusedCap : w->col_ctas[l];
+        w->colpart[l] = take((int64_t)cap * 3 * L.out_dim);
       } else {
         w->col_ctas[l] = 0;
         w->colpart[l] = -1;

@@ -20,12 +20,13 @@ bool g_profile_on = false;
 // the fork and the join of the backward pass therefore ask for the tensor-core kernels' carve-out (maximum shared);
 // ISDQN_CARVEOUT=1 extends that to every kernel launched through launch_pdl (measured slower: the rest lose L1).
 void prefer_max_shared(const void* kernel) {
-  static const void* seen[256];
-  static int n_seen = 0;
-  for (int i = 0; i < n_seen; ++i)
-    if (seen[i] == kernel) return;
+  static const void* seen[kMaxDevices][256];
+  static int n_seen[kMaxDevices] = {};
+  const int d = current_device();
+  for (int i = 0; i < n_seen[d]; ++i)
+    if (seen[d][i] == kernel) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-  if (n_seen < 256) seen[n_seen++] = kernel;
+  if (n_seen[d] < 256) seen[d][n_seen[d]++] = kernel;
 }
 void prefer_max_shared_once(const void* kernel) {
   static const bool all = [] {
@@ -55,21 +56,24 @@ int fork_mode() {
   }();
   return mode;
 }
+// (streams and events belong to one device: one set per device)
 cudaStream_t side_stream(int i) {
-  static cudaStream_t s[kSideStreams] = {};
-  static bool tried[kSideStreams] = {};
+  static cudaStream_t s[kMaxDevices][kSideStreams] = {};
+  static bool tried[kMaxDevices][kSideStreams] = {};
   if (i < 0 || i >= kSideStreams) return nullptr;
-  if (!tried[i]) {
-    tried[i] = true;
-    if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) s[i] = nullptr;
+  const int d = current_device();
+  if (!tried[d][i]) {
+    tried[d][i] = true;
+    if (cudaStreamCreateWithFlags(&s[d][i], cudaStreamNonBlocking) != cudaSuccess) s[d][i] = nullptr;
   }
-  return s[i];
+  return s[d][i];
 }
 cudaEvent_t side_event(int i) {
-  static cudaEvent_t ev[kSideEvents] = {};
+  static cudaEvent_t ev[kMaxDevices][kSideEvents] = {};
   if (i < 0 || i >= kSideEvents) return nullptr;
-  if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) ev[i] = nullptr;
-  return ev[i];
+  const int d = current_device();
+  if (!ev[d][i] && cudaEventCreateWithFlags(&ev[d][i], cudaEventDisableTiming) != cudaSuccess) ev[d][i] = nullptr;
+  return ev[d][i];
 }
 
 namespace {
@@ -131,6 +135,18 @@ extern "C" int isdqn_spin(void* stream, int32_t micros) {
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
+
+namespace isdqn {
+int num_sms() {
+  static PerDevice<int> sms;
+  int& n = sms.get();
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n > 0 ? n : kNumSMs;
+}
+}  // namespace isdqn
 
 extern "C" int isdqn_abi_version(void) { return ISDQN_ABI_VERSION; }
 

@@ -331,13 +331,12 @@ extern "C" int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_in
     sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), as_stream(stream)>>>(
         d_nodes, depth, d_index, d_value, n, d_max_priority, d_status);
   } else {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
       ISDQN_CUDA_CHECK(cudaFuncSetAttribute(sumtree_set_kernel<ISDQN_SUMTREE_SET_MAX, 1024>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)set_smem_bytes<ISDQN_SUMTREE_SET_MAX>()));
-      attr_done = true;
-    }
+      }
     sumtree_set_kernel<ISDQN_SUMTREE_SET_MAX, 1024>
         <<<1, 1024, set_smem_bytes<ISDQN_SUMTREE_SET_MAX>(), as_stream(stream)>>>(d_nodes, depth, d_index, d_value, n,
                                                                                   d_max_priority, d_status);

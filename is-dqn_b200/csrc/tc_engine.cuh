@@ -100,6 +100,12 @@ template <class P>
 struct uses_ep_stage<P, std::void_t<decltype(P::EP_STAGE)>> : std::bool_constant<P::EP_STAGE> {};
 constexpr int kEpStageWords = 32 * 20;  // per epilogue warp: 32 rows x 16 words, 20-word pitch
 
+// problems whose epilogue keeps per-CTA state that is written out after the last tile declare `EP_FINISH = true`
+template <class P, class = void>
+struct uses_ep_finish : std::false_type {};
+template <class P>
+struct uses_ep_finish<P, std::void_t<decltype(P::EP_FINISH)>> : std::bool_constant<P::EP_FINISH> {};
+
 template <class P, class = void>
 struct uses_tma : std::false_type {};
 template <class P>
@@ -414,6 +420,7 @@ __device__ __forceinline__ void tc_gemm_body(const P& p, int tiles_x, int tiles_
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[a]);
     }
+    if constexpr (uses_ep_finish<P>::value) p.finish_epilogue(ectx, cta, tid);
   }
   tcgen05_fence_before();
   __syncthreads();

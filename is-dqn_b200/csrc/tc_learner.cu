@@ -118,10 +118,12 @@ inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpre
 
 // Persistent launch: the tiles (x fastest) are dealt round-robin to min(#tiles, SMs x resident CTAs) CTAs.
 template <class P>
-int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0) {
+int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0,
+              int* grid_out = nullptr) {
   constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
   constexpr int threads = 32 * (tc::kFirstProducerWarp + P::PRODUCER_WARPS);
-  static int ctas_per_sm = 0;
+  static PerDevice<int> ctas_per_sm_dev;  // (the opt-in attributes below are per device context)
+  int& ctas_per_sm = ctas_per_sm_dev.get();
   if (!ctas_per_sm) {
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -149,6 +151,7 @@ int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s,
   int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
   if (max_ctas > 0 && cap > max_ctas) cap = max_ctas;  // side-stream work: leave most SMs to the critical path
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+  if (grid_out) *grid_out = grid;
   ISDQN_PROF(s, tag);
   ISDQN_CUDA_CHECK(launch_pdl((tc::tc_gemm_kernel<P>), dim3(grid), dim3(threads), smem, s, p, tiles_x, tiles_y, tiles_z));
   ISDQN_LAUNCH_CHECK();
@@ -205,14 +208,23 @@ int encode_matrix_map(CUtensorMap* tm, const bf16* base, int64_t inner, int64_t 
 }
 
 // D[M][N] (fp32, + split partials) = A B^T with the four operand-major combinations
+bool gemm_tma_operands_ok(const bf16* A, int64_t lda, const bf16* B, int64_t ldb) {
+  return tensor_map_encoder() != nullptr && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+         lda % 8 == 0 && ldb % 8 == 0;
+}
+
+// ln (optional): fuse the LayerNorm / ReLU backward of the layer whose output is D (64 channels per pixel, N / 64 pixels per
+// row) into the epilogue — requires gemm_tma_operands_ok and splits == 1; *ln_parts receives the number of column partials
 template <bool A_MN, bool B_MN>
 int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float* C, int64_t ldc, int64_t split_stride, int M,
-                   int N, int K, int splits, cudaStream_t s, const char* tag, int max_ctas = 0) {
+                   int N, int K, int splits, cudaStream_t s, const char* tag, int max_ctas = 0, const tc::LnBwdFuse* ln = nullptr,
+                   int* ln_parts = nullptr) {
   const int total_chunks = ceil_div(K, tc::kBK);
   const int cps = ceil_div(total_chunks, splits);
   const int real_splits = ceil_div(total_chunks, cps);
   // (a capped side-stream launch takes the narrow tile: half the shared memory, so it can share an SM)
-  const int bn = max_ctas > 0 ? pick_bn(N < 64 ? N : 64) : pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
+  const int bn = ln ? 64 : max_ctas > 0 ? pick_bn(N < 64 ? N : 64) : pick_bn_parallel(N, ceil_div(M, tc::kBM) * real_splits);
+  if (ln && (real_splits != 1 || N % 64 != 0 || !gemm_tma_operands_ok(A, lda, B, ldb))) return ISDQN_E_UNSUPPORTED;
 #define ISDQN_GEMM_TC_W(BN, WIDE)                                              \
   {                                                                            \
     tc::GemmTC<BN, A_MN, B_MN, WIDE> p;                                        \
@@ -230,13 +242,13 @@ int launch_gemm_tc(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, float
     p.tm_a = tm_a; p.tm_b = tm_b; p.C = C; p.ldc = ldc;                        \
     p.split_stride = split_stride; p.M = M; p.N = N; p.K = K;                  \
     p.chunks_per_split = cps;                                                  \
-    return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag, max_ctas); \
+    if (ln) { p.ln = *ln; p.ln_rows_per_m = N / BN; }                          \
+    return launch_tc(p, ceil_div(M, tc::kBM), ceil_div(N, BN), real_splits, s, tag, max_ctas, ln_parts); \
   }
 #define ISDQN_GEMM_TMA(BN)                                                     \
   if (wide_launch((int64_t)ceil_div(M, tc::kBM) * ceil_div(N, BN) * real_splits)) ISDQN_GEMM_TMA_W(BN, true) \
   else ISDQN_GEMM_TMA_W(BN, false)
-  if (bn >= 64 && tensor_map_encoder() != nullptr && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(B) & 15) == 0 && lda % 8 == 0 && ldb % 8 == 0) {
+  if (bn >= 64 && gemm_tma_operands_ok(A, lda, B, ldb)) {
     CUtensorMap tm_a, tm_b;
     int rc = A_MN ? encode_matrix_map(&tm_a, A, M, K, lda, 64, 64) : encode_matrix_map(&tm_a, A, K, M, lda, 64, tc::kBM);
     if (rc) return rc;
@@ -553,7 +565,8 @@ bool conv_dgrad_tma_ok(const Layer& L) {
   return ny * nx <= tc::kBM && nx <= 256 && ny <= 256;
 }
 
-int launch_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s) {
+int launch_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s,
+                          const tc::LnBwdFuse* ln = nullptr, int* ln_parts = nullptr) {
   EncodeTiledFn enc = tensor_map_encoder();
   CUtensorMap tm_dz[4], tm_w;
   const int st = L.stride;
@@ -583,7 +596,8 @@ int launch_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* 
     p.tm_w = tm_w; p.H = L.H; p.W = L.W; p.Cin = L.Cin; p.Cout = L.out_dim; p.ksz = L.ksz;             \
     p.stride = L.stride; p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.n_img = B; p.cchunks = L.out_dim / 64; \
     p.dx = dx;                                                                                         \
-    return launch_tc(p, B, ceil_div(L.Cin, BN), st * st, s, "tc_conv_dgrad_tma");                      \
+    if (ln) p.ln = *ln;                                                                                \
+    return launch_tc(p, B, ceil_div(L.Cin, BN), st * st, s, "tc_conv_dgrad_tma", 0, ln_parts);         \
   }
 #define ISDQN_CONV_DGRAD_TMA(BN)                                                                       \
   if (wide_launch((int64_t)B * ceil_div(L.Cin, BN) * st * st)) ISDQN_CONV_DGRAD_TMA_W(BN, true)        \
@@ -663,7 +677,9 @@ int build_conv_wgrad_tma(const Layer& V, const bf16* x, const bf16* dz, float* p
 }
 
 template <int BND>
-int build_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, tc::ConvDgradTmaTC<BND, true>* p) {
+int build_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, tc::ConvDgradTmaTC<BND, true>* p,
+                         const tc::LnBwdFuse* ln = nullptr) {
+  if (ln) p->ln = *ln;
   EncodeTiledFn enc = tensor_map_encoder();
   const int st = L.stride;
   for (int cls = 0; cls < st * st; ++cls) {
@@ -702,7 +718,8 @@ bool conv_bwd_pair_ok(const Layer& V, const Layer& L, int B) {
 
 template <int BNW, int BND>
 int launch_conv_bwd_pair_t(const Layer& V, const bf16* x, const bf16* dz, float* part, int B, int max_splits, int* real_splits,
-                           float in_scale, int ksz_x, int sy, const Layer& L, const bf16* w, float* dx, cudaStream_t s) {
+                           float in_scale, int ksz_x, int sy, const Layer& L, const bf16* w, float* dx, cudaStream_t s,
+                           const tc::LnBwdFuse* ln, int* ln_parts) {
   tc::ConvWgradTmaTC<BNW, true> pw;
   tc::ConvDgradTmaTC<BND, true> pd;
   const int st = L.stride;
@@ -724,17 +741,19 @@ int launch_conv_bwd_pair_t(const Layer& V, const bf16* x, const bf16* dz, float*
   int tiles_k = 0;
   int rc = build_conv_wgrad_tma<BNW>(V, x, dz, part, B, splits, in_scale, ksz_x, sy, &pw, &tiles_k, real_splits);
   if (rc) return rc;
-  rc = build_conv_dgrad_tma<BND>(L, dz, w, dx, B, &pd);
+  rc = build_conv_dgrad_tma<BND>(L, dz, w, dx, B, &pd, ln);
   if (rc) return rc;
+  if (ln_parts) *ln_parts = ctas_d;
   return launch_tc2(pw, tiles_k, 1, *real_splits, tiles_k * *real_splits, pd, B, ceil_div(L.Cin, BND), st * st, ctas_d, s,
                     "tc_conv_wgrad_dgrad");
 }
 
 int launch_conv_bwd_pair(const Layer& V, const bf16* x, const bf16* dz, float* part, int B, int max_splits, int* real_splits,
-                         float in_scale, int ksz_x, int sy, const Layer& L, const bf16* w, float* dx, cudaStream_t s) {
+                         float in_scale, int ksz_x, int sy, const Layer& L, const bf16* w, float* dx, cudaStream_t s,
+                         const tc::LnBwdFuse* ln = nullptr, int* ln_parts = nullptr) {
   const int bnd = pick_bn(L.Cin);
 #define ISDQN_PAIR(BNW, BND) \
-  return launch_conv_bwd_pair_t<BNW, BND>(V, x, dz, part, B, max_splits, real_splits, in_scale, ksz_x, sy, L, w, dx, s);
+  return launch_conv_bwd_pair_t<BNW, BND>(V, x, dz, part, B, max_splits, real_splits, in_scale, ksz_x, sy, L, w, dx, s, ln, ln_parts);
   if (V.out_dim == 64) {
     if (bnd == 32) ISDQN_PAIR(64, 32)
     if (bnd == 64) ISDQN_PAIR(64, 64)
@@ -748,8 +767,10 @@ int launch_conv_bwd_pair(const Layer& V, const bf16* x, const bf16* dz, float* p
   return ISDQN_E_UNSUPPORTED;
 }
 
-int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s) {
-  if (conv_dgrad_tma_ok(L)) return launch_conv_dgrad_tma(L, dz, w, dx, B, s);
+int launch_conv_dgrad_tc(const Layer& L, const bf16* dz, const bf16* w, float* dx, int B, cudaStream_t s,
+                         const tc::LnBwdFuse* ln = nullptr, int* ln_parts = nullptr) {
+  if (conv_dgrad_tma_ok(L)) return launch_conv_dgrad_tma(L, dz, w, dx, B, s, ln, ln_parts);
+  if (ln) return ISDQN_E_UNSUPPORTED;
   const int taps = ceil_div(L.ksz, L.stride);
   const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
   const int bn = pick_bn(L.Cin);
@@ -826,6 +847,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   }
   // ------------------------------------------------------------------------------------------ forward
   const int rows_train = backward ? B : 0;
+  bool mid_done = false;  // head_mid_kernel ran: TD loss + head backward are done, their cross-sample tail is pending
   for (int l = 0; l < nl; ++l) {
     const Layer& L = p.L[l];
     const float* ln_g = L.has_ln ? params + L.g_off : nullptr;
@@ -885,7 +907,29 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
                                        L.out_dim, split_stride, rows, L.out_dim, L.in_dim, splits, s, "tc_dense_fwd");
       if (rc) return rc;
       const Layer& Hd = p.L[l + 1];
-      if (l + 2 == nl && rows <= 1024 && Hd.out_dim <= 128 && L.out_dim <= kRowThreads * kRowMaxPerThread) {
+      static const bool mid_on = [] {
+        const char* e = getenv("ISDQN_MID");
+        return !(e && e[0] == '0');
+      }();
+      if (mid_on && backward && l + 2 == nl && B <= 256 && Hd.out_dim <= 128 && L.out_dim <= kRowThreads * kRowMaxPerThread &&
+          w.wsplits[nl - 1] == 1 && w.col_ctas[l] == B && p.n_out >= 2 * net->n_heads && L.relu) {
+        // small batch: finish the hidden layer, head layer, TD loss and the head / hidden-layer backward in ONE launch
+        static PerDeviceOnce attr_once;
+        if (attr_once.first()) {
+          ISDQN_CUDA_CHECK(cudaFuncSetAttribute(head_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                2 * kRowThreads * kRowMaxPerThread * (int)sizeof(float)));
+        }
+        ISDQN_PROF(s, "head_mid");
+        ISDQN_CUDA_CHECK(launch_pdl(head_mid_kernel, dim3(B), dim3(512), 2 * L.out_dim * sizeof(float), s, wsp(ws, w.fwd_part),
+                                    real_splits, split_stride, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu, wsp(ws, w.act[l]),
+                                    params + Hd.w_off, params + Hd.b_off, Hd.out_dim, wsp(ws, w.act[l + 1]), b->d_action,
+                                    b->d_reward, b->d_terminal, tr->gamma_n, B, tr->batch_global, net->n_heads, net->n_actions,
+                                    tr->d_is_weights, tr->d_td_abs, wsp(ws, w.dq), wsp(ws, w.colpart[l]), w16(wt, t.dz16[l]),
+                                    update ? tr->d_count : nullptr));
+        ISDQN_LAUNCH_CHECK();
+        mid_done = true;
+        ++l;  // the head layer is done
+      } else if (l + 2 == nl && rows <= 1024 && Hd.out_dim <= 128 && L.out_dim <= kRowThreads * kRowMaxPerThread) {
         // last hidden layer: finish it and apply the (fp32) head layer in the same launch
         ISDQN_PROF(s, "dense_finalize_head");
         ISDQN_CUDA_CHECK(launch_pdl(dense_finalize_head_kernel, dim3(rows), dim3(512), L.out_dim * sizeof(float), s,
@@ -916,6 +960,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   }
   const float* q_all = wsp(ws, w.act[nl - 1]);
   const Layer& last = p.L[nl - 1];
+  if (!mid_done) {
   ISDQN_PROF(s, "heads_td_loss");
   ISDQN_CUDA_CHECK(launch_pdl(heads_td_loss_kernel, dim3(net->n_heads), dim3(kLossThreads), 0, s, q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
                                                   tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
@@ -923,6 +968,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
                                                   update ? tr->d_count : nullptr, update ? tr->d_cumulated : nullptr,
                                                   tr->d_is_weights, tr->d_td_abs));
   ISDQN_LAUNCH_CHECK();
+  }
   if (q_out)
     ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * (size_t)rows * p.n_out, cudaMemcpyDeviceToDevice, s));
   if (!backward) return ISDQN_OK;
@@ -963,10 +1009,32 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   int64_t pend_off = -1, pend_n = 0;    // Dense kernel whose early Adam waits for the next fork point
   int64_t early_off = 0, early_n = 0;   // range already updated on the side stream
   int fused_l = -1;                     // small batch: Dense layer whose weight gradient is recomputed inside its Adam update
+  int col_parts[ISDQN_MAX_FEATURES + 1];  // column partials every layer's LayerNorm / ReLU backward produced
+  for (int l = 0; l < nl; ++l) col_parts[l] = w.col_ctas[l];
+  static const bool ln_fuse_on = [] {
+    const char* e = getenv("ISDQN_LNFUSE");
+    return !(e && e[0] == '0');
+  }();
+  // The LayerNorm / ReLU backward of conv layer l - 1 (<= 64 channels) runs in the epilogue of layer l's input gradient:
+  // the accumulator row of an epilogue thread IS one pixel of layer l - 1 with all its channels (tc_problems.cuh).
+  auto ln_fuse_for = [&](int l, tc::LnBwdFuse* f) -> bool {
+    if (!ln_fuse_on || l < 1 || fmode) return false;
+    const Layer& P = p.L[l - 1];
+    if (P.type != 0 || !P.has_ln || !P.relu || !(P.out_dim == 32 || P.out_dim == 64)) return false;
+    f->xhat = wsp(ws, w.xhat[l - 1]);
+    f->rstd = wsp(ws, w.rstd[l - 1]);
+    f->ln_g = params + P.g_off;
+    f->ln_b = params + P.beta_off;
+    f->dz16 = w16(wt, t.dz16[l - 1]);
+    f->colpart = wsp(ws, w.colpart[l - 1]);
+    return true;
+  };
   for (int l = nl - 1; l >= 0; --l) {
     const Layer& L = p.L[l];
     const bf16* dz16 = w16(wt, t.dz16[l]);
     const int rows_l = B * L.pix;
+    bool ln_fused = false;  // layer l - 1's LayerNorm / ReLU backward was done by this layer's input-gradient launch
+    if (mid_done && l == nl - 1) continue;  // head backward + the hidden layer's LayerNorm/ReLU backward: head_mid_kernel
     if (l == nl - 1 && l >= 1 && p.L[l - 1].type == 1 && B <= 256 && w.wsplits[l] == 1 && L.out_dim <= 128 &&
         p.L[l - 1].out_dim <= kRowThreads * kRowMaxPerThread) {
       // small batch: head weight gradient + head input gradient + LayerNorm/ReLU backward of the hidden layer, one launch
@@ -1051,9 +1119,16 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
           view_ok = true;
         }
         if (view_ok && conv_bwd_pair_ok(V, L, B)) {
+          tc::LnBwdFuse lf;
+          int parts = 0;
+          const bool fuse = ln_fuse_for(l, &lf) && pick_bn(L.Cin) == p.L[l - 1].out_dim;
           rc = launch_conv_bwd_pair(V, w16(wt, t.act16[l - 1]), dz16, part, B, w.wsplits_tc[l], &real_splits, 1.0f, kx, sy, L,
-                                    shadow + L.w_off, wsp(ws, w.dbuf[l & 1]), s);
+                                    shadow + L.w_off, wsp(ws, w.dbuf[l & 1]), s, fuse ? &lf : nullptr, &parts);
           paired_dgrad = true;
+          if (fuse) {
+            ln_fused = true;
+            col_parts[l - 1] = parts;
+          }
         }
       }
       if (paired_dgrad) {
@@ -1097,10 +1172,10 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     if (L.relu) {
       const float* cp = wsp(ws, w.colpart[l]);
       const int64_t st = 3 * (int64_t)L.out_dim;
-      add_seg(cp, grads + L.b_off, st, L.out_dim, w.col_ctas[l]);
+      add_seg(cp, grads + L.b_off, st, L.out_dim, col_parts[l]);
       if (L.has_ln) {
-        add_seg(cp + L.out_dim, grads + L.g_off, st, L.out_dim, w.col_ctas[l]);
-        add_seg(cp + 2 * L.out_dim, grads + L.beta_off, st, L.out_dim, w.col_ctas[l]);
+        add_seg(cp + L.out_dim, grads + L.g_off, st, L.out_dim, col_parts[l]);
+        add_seg(cp + 2 * L.out_dim, grads + L.beta_off, st, L.out_dim, col_parts[l]);
       }
     }
     if (l == 0) break;
@@ -1115,13 +1190,32 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       g.M = B; g.N = L.in_dim; g.K = L.out_dim; g.k_per_split = ceil_div(L.out_dim, kBK) * kBK; g.bias = nullptr;
       rc = launch_simt_gemm(g, s, "head_dgrad_gemm");
     } else if (L.type == 1) {
-      rc = launch_gemm_tc<false, false>(dz16, L.out_dim, shadow + L.w_off, L.out_dim, dprev, L.in_dim, 0, B, L.in_dim,
-                                        L.out_dim, 1, s, "tc_dense_dgrad");
+      tc::LnBwdFuse lf;
+      int parts = 0;
+      if (ln_fuse_for(l, &lf) && p.L[l - 1].out_dim == 64 && L.in_dim % 64 == 0 &&
+          gemm_tma_operands_ok(dz16, L.out_dim, shadow + L.w_off, L.out_dim)) {
+        rc = launch_gemm_tc<false, false>(dz16, L.out_dim, shadow + L.w_off, L.out_dim, dprev, L.in_dim, 0, B, L.in_dim,
+                                          L.out_dim, 1, s, "tc_dense_dgrad_ln", 0, &lf, &parts);
+        ln_fused = true;
+        col_parts[l - 1] = parts;
+      } else {
+        rc = launch_gemm_tc<false, false>(dz16, L.out_dim, shadow + L.w_off, L.out_dim, dprev, L.in_dim, 0, B, L.in_dim,
+                                          L.out_dim, 1, s, "tc_dense_dgrad");
+      }
     } else if (!paired_dgrad) {
-      rc = launch_conv_dgrad_tc(L, dz16, shadow + L.w_off, dprev, B, s);
+      tc::LnBwdFuse lf;
+      int parts = 0;
+      if (ln_fuse_for(l, &lf) && conv_dgrad_tma_ok(L) && pick_bn(L.Cin) == p.L[l - 1].out_dim) {
+        rc = launch_conv_dgrad_tc(L, dz16, shadow + L.w_off, dprev, B, s, &lf, &parts);
+        ln_fused = true;
+        col_parts[l - 1] = parts;
+      } else {
+        rc = launch_conv_dgrad_tc(L, dz16, shadow + L.w_off, dprev, B, s);
+      }
     }
     if (rc) return rc;
-    {
+    if (ln_fused && col_parts[l - 1] > kColpartFusedCap) return ISDQN_E_INVALID;  // (grids are <= 4 CTAs per SM)
+    if (!ln_fused) {
       const int rows_p = B * P.pix;
       const float* g_ = P.has_ln ? params + P.g_off : nullptr;
       const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
@@ -1152,8 +1246,22 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     }
   }
   if (segs.count > 0) {
+    HeadTail tail = {};
+    if (mid_done) {  // loss means, head bias / kernel gradients: the part of the head step that needs every sample
+      const Layer& Hp = p.L[nl - 2];
+      tail.ctas = head_tail_ctas(Hp.out_dim, last.out_dim);
+      tail.tdq = wsp(ws, w.dq);
+      tail.action = b->d_action;
+      tail.act = wsp(ws, w.act[nl - 2]);
+      tail.B = B; tail.K = net->n_heads; tail.A = net->n_actions; tail.C = Hp.out_dim; tail.NH = last.out_dim;
+      tail.inv_b = 1.0f / (float)tr->batch_global;
+      tail.losses = tr->d_losses;
+      tail.cumulated = update ? tr->d_cumulated : nullptr;
+      tail.dbias = grads + last.b_off;
+      tail.dwh = grads + last.w_off;
+    }
     ISDQN_PROF(s, "reduce_segments");
-    ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s));
+    ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s, mid_done ? &tail : nullptr));
   }
   if (!update) return ISDQN_OK;
   if (tr->nccl_comm) {

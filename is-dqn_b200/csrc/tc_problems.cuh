@@ -155,6 +155,127 @@ __device__ __forceinline__ void store_rows_f32(uint32_t tmem_lane_base, float* _
   }
 }
 
+// ---- LayerNorm / ReLU backward of the layer BELOW, fused into an input-gradient epilogue -----------------------------------
+// The accumulator row of thread t is d(loss)/d(output) of one pixel of the layer below (all its C = BN channels), so its
+// LayerNorm backward is thread-local; only the three column sums that become the bias / scale / shift gradients cross rows.
+// Column sums of 32 values per lane over the 32 lanes of a warp with 31 shuffles (recursive halving: after the step with
+// offset o a lane keeps the half of its values whose index has bit o equal to its own lane bit): lane l ends up with the
+// sum of value l over the warp, in a fixed order.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+constexpr int ln_bwd_ep_floats(int bn) { return bn <= 64 ? (2 + 12 + 3) * bn : 0; }  // gamma | beta | part[4][3 bn] | acc[3 bn]
+struct LnBwdFuse {
+  const float* xhat = nullptr;  // [rows][C] normalised values of the layer below (null: no fusion, plain fp32 input gradient)
+  const float* rstd = nullptr;  // [rows]
+  const float* ln_g = nullptr;  // [C]
+  const float* ln_b = nullptr;  // [C]
+  bf16* dz16 = nullptr;         // [rows][C] gradient w.r.t. the pre-activation of the layer below
+  float* colpart = nullptr;     // [CTAs of the launch][3][C] column sums (dz | dy * xhat | dy) of every CTA
+};
+struct LnBwdCtx {
+  float* prm;   // shared memory: gamma[BN] | beta[BN]
+  float* part;  // [4 warps][3 BN]
+  float* acc;   // [3 BN] running column sums of this CTA
+};
+template <int BN>
+__device__ __forceinline__ void ln_bwd_init(const LnBwdFuse& f, LnBwdCtx& c, float* ep_sm, int etid) {
+  c.prm = ep_sm;
+  c.part = ep_sm + 2 * BN;
+  c.acc = ep_sm + 14 * BN;
+  if (f.xhat) {
+    for (int i = etid; i < BN; i += 32 * kEpilogueWarps) {
+      ep_sm[i] = f.ln_g[i];
+      ep_sm[BN + i] = f.ln_b[i];
+    }
+    for (int i = etid; i < 3 * BN; i += 32 * kEpilogueWarps) c.acc[i] = 0.f;
+  }
+}
+// one tile: thread etid owns LayerNorm row m (valid or not); warp-collective and epilogue-collective (two named barriers)
+template <int BN>
+__device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& c, uint32_t tmem_lane_base, bool valid, int64_t m,
+                                            uint32_t* stg, int etid) {
+  static_assert(BN == 32 || BN == 64, "fused LayerNorm backward: 32 or 64 channels");
+  const int lane = etid & 31, warp = etid >> 5;
+  const float4* xr = reinterpret_cast<const float4*>(f.xhat + (valid ? m : 0) * BN);
+  const float4* pg = reinterpret_cast<const float4*>(c.prm);
+  const float4* pb = reinterpret_cast<const float4*>(c.prm + BN);
+  float dy[BN];
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    float v[32];
+    tmem_ld32(tmem_lane_base + cb * 32, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 x4 = valid ? __ldg(xr + cb * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g4 = pg[cb * 8 + q], b4 = pb[cb * 8 + q];
+      const float xx[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = (valid && xx[j] * gg[j] + bb[j] > 0.f) ? v[4 * q + j] : 0.f;
+        dy[cb * 32 + 4 * q + j] = d;
+        const float g = d * gg[j];
+        sg += g;
+        sgx += g * xx[j];
+      }
+    }
+  }
+  const float inv_c = 1.0f / (float)BN;
+  const float mg = sg * inv_c, mgx = sgx * inv_c;
+  const float rs = valid ? f.rstd[m] : 0.f;
+  named_bar_sync(2, 32 * kEpilogueWarps);  // the previous tile's partial sums have been folded into acc
+#pragma unroll
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    float a0[32], a1[32], a2[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 x4 = valid ? __ldg(xr + cb * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g4 = pg[cb * 8 + q];
+      const float xx[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = dy[cb * 32 + 4 * q + j];
+        a0[4 * q + j] = rs * (d * gg[j] - mg - xx[j] * mgx);
+        a1[4 * q + j] = d * xx[j];
+        a2[4 * q + j] = d;
+      }
+    }
+    {
+      uint32_t w[16];  // 32 bf16 = one 64-byte segment of the row
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16(a0[2 * i], a0[2 * i + 1]);
+      warp_store_block16(stg, w, f.dz16 + (valid ? m : 0) * BN + cb * 32, valid);
+    }
+    const float r0 = warp_transpose_sum32(a0), r1 = warp_transpose_sum32(a1), r2 = warp_transpose_sum32(a2);
+    float* pw = c.part + warp * 3 * BN + cb * 32 + lane;
+    pw[0] = r0;
+    pw[BN] = r1;
+    pw[2 * BN] = r2;
+  }
+  named_bar_sync(2, 32 * kEpilogueWarps);
+  for (int t = etid; t < 3 * BN; t += 32 * kEpilogueWarps)
+    c.acc[t] += (c.part[t] + c.part[3 * BN + t]) + (c.part[6 * BN + t] + c.part[9 * BN + t]);
+}
+template <int BN>
+__device__ __forceinline__ void ln_bwd_finish(const LnBwdFuse& f, const LnBwdCtx& c, int cta, int etid) {
+  if (!f.xhat) return;
+  named_bar_sync(2, 32 * kEpilogueWarps);
+  for (int t = etid; t < 3 * BN; t += 32 * kEpilogueWarps) f.colpart[(int64_t)cta * 3 * BN + t] = c.acc[t];
+}
+
 // --------------------------------------------------------------------------------------- plain GEMM (+ split-K)
 // D[M][N] = sum_k A(m,k) B(n,k); A: K-major [M][lda] or MN-major [K][lda]; B likewise.  fp32 output (partials).
 // WIDE_ (every problem): the latency shape for launches that are a single partial wave (batch 32) — 8 producer warps
@@ -208,18 +329,26 @@ struct GemmTC {
 // no LSU traffic.  BN >= 64 (a 32-wide B stage is narrower than a swizzle atom: GemmTC handles it).
 template <int BN_, bool A_MN_, bool B_MN_, bool WIDE_ = false>
 struct GemmTmaTC {
-  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1, EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1, EXTRA_BYTES = 0;
+  static constexpr int EP_FLOATS = ln_bwd_ep_floats(BN_);
   static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
+  static constexpr bool EP_FINISH = true;
   static_assert(BN_ % 64 == 0, "swizzled B stage");
   CUtensorMap tm_a;  // A K-major: dims {K, M}, box {64, 128};  A MN-major: dims {M, K}, box {64, 64}
   CUtensorMap tm_b;  // B K-major: dims {K, N}, box {64, BN};   B MN-major: dims {N, K}, box {64, 64}
   float* C; int64_t ldc; int64_t split_stride;
   int M, N, K, chunks_per_split;
+  // Dense input gradient with the LayerNorm / ReLU backward of the layer below fused (ln.xhat != null, BN == its channel
+  // count): row m of D holds ln_rows_per_m = N / BN pixels of BN channels each; tile column n0 is pixel n0 / BN
+  LnBwdFuse ln;
+  int ln_rows_per_m = 1;
   struct PCtx {
     int m0, n0;
   };
-  struct ECtx {};
+  struct ECtx {
+    LnBwdCtx lc;
+  };
   __device__ void tma_prefetch() const {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -249,12 +378,23 @@ struct GemmTmaTC {
       tma_load_2d(stage_b, &tm_b, k0, n0, bar);
     }
   }
-  __device__ void init_epilogue(ECtx&, float*, int) const {}
+  __device__ void init_epilogue(ECtx& e, float* ep_sm, int etid) const {
+    if constexpr (BN <= 64) ln_bwd_init<BN>(ln, e.lc, ep_sm, etid);
+  }
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int split, int etid, uint32_t* stg) const {
+  __device__ void epilogue(const ECtx& e, uint32_t tmem_lane_base, int m0, int n0, int split, int etid, uint32_t* stg) const {
     const int m = m0 + etid;
+    if constexpr (BN <= 64) {
+      if (ln.xhat) {
+        ln_bwd_tile<BN>(ln, e.lc, tmem_lane_base, m < M, (int64_t)m * ln_rows_per_m + n0 / BN, stg, etid);
+        return;
+      }
+    }
     float* dst = C + (int64_t)split * split_stride + (int64_t)(m < M ? m : 0) * ldc;
     store_rows_f32_coalesced<BN>(tmem_lane_base, dst, m < M, n0, N, stg);
+  }
+  __device__ void finish_epilogue(const ECtx& e, int cta, int etid) const {
+    if constexpr (BN <= 64) ln_bwd_finish<BN>(ln, e.lc, cta, etid);
   }
 };
 
@@ -840,12 +980,14 @@ template <int BN_, bool WIDE_ = false>
 struct ConvDgradTmaTC {
   static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
   static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
-  static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 0;
+  static constexpr int EXTRA_BYTES = 0, EP_FLOATS = ln_bwd_ep_floats(BN_);
   static constexpr bool A_MN = false, B_MN = false, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
+  static constexpr bool EP_FINISH = true;
   CUtensorMap tm_dz[4];  // dz [N][OH][OW][Cout] bf16, box {64, nx(cls), ny(cls), 1}
   CUtensorMap tm_w;      // weights as [ksz*ksz*Cin rows][Cout], box {64, BN}
   int H, W, Cin, Cout, ksz, stride, pad_y, pad_x, n_img, cchunks;  // cchunks = Cout / 64
-  float* dx;             // [n_img*H*W][Cin]
+  float* dx;             // [n_img*H*W][Cin] (unused when the LayerNorm backward is fused)
+  LnBwdFuse ln;          // xhat != null (BN == Cin <= 64): the epilogue goes on to the pre-activation gradient of the layer below
   struct Cls {
     int ry, rx, iy_first, ix_first, ny, nx, oy0, ox0, n_ty, n_tx;
   };
@@ -854,7 +996,9 @@ struct ConvDgradTmaTC {
     int img, n0, cls;
     int ty, tx, cc;  // running counters over (tap row, tap column, 64-channel chunk)
   };
-  struct ECtx {};
+  struct ECtx {
+    LnBwdCtx lc;
+  };
   __device__ Cls cls_of(int cls) const {
     Cls c;
     const int s = stride;
@@ -899,15 +1043,26 @@ struct ConvDgradTmaTC {
       }
     }
   }
-  __device__ void init_epilogue(ECtx&, float*, int) const {}
+  __device__ void init_epilogue(ECtx& e, float* ep_sm, int etid) const {
+    if constexpr (BN <= 64) ln_bwd_init<BN>(ln, e.lc, ep_sm, etid);
+  }
   __device__ void tile_epilogue(ECtx&, int, int, int, int) const {}
-  __device__ void epilogue(const ECtx&, uint32_t tmem_lane_base, int m0, int n0, int cls, int etid, uint32_t* stg) const {
+  __device__ void epilogue(const ECtx& e, uint32_t tmem_lane_base, int m0, int n0, int cls, int etid, uint32_t* stg) const {
     const Cls c = cls_of(cls);
     const int img = m0 / kBM;
     const bool valid = etid < c.ny * c.nx && img < n_img;
     const int iyc = etid / (c.nx > 0 ? c.nx : 1), ixc = etid - iyc * c.nx;
     const int64_t pix = valid ? ((int64_t)img * H + (c.iy_first + stride * iyc)) * W + (c.ix_first + stride * ixc) : 0;
+    if constexpr (BN <= 64) {
+      if (ln.xhat) {
+        ln_bwd_tile<BN>(ln, e.lc, tmem_lane_base, valid, pix, stg, etid);
+        return;
+      }
+    }
     store_rows_f32_coalesced<BN>(tmem_lane_base, dx + pix * Cin, valid, n0, Cin, stg);
+  }
+  __device__ void finish_epilogue(const ECtx& e, int cta, int etid) const {
+    if constexpr (BN <= 64) ln_bwd_finish<BN>(ln, e.lc, cta, etid);
   }
 };
 
