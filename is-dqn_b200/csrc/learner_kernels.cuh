@@ -846,13 +846,27 @@ struct HeadTail {
 };
 static inline int head_tail_ctas(int C, int NH) { return 1 + (C * NH + 255) / 256; }
 
+// (the per-sample values are staged in shared memory first: the sums below then run over shared memory in a fixed order
+// instead of over a chain of dependent global loads)
+constexpr int kTailMaxB = 256;
 __device__ __forceinline__ void head_tail_block(const HeadTail& h, int j) {
   const int tid = threadIdx.x;
+  __shared__ float s_tdq[kTailMaxB * 2 * 16 > 4096 ? 4096 : kTailMaxB * 2 * 16];  // [B][2K] while it fits, else global
+  __shared__ int s_act[kTailMaxB];
+  const int n_tdq = h.B * 2 * h.K;
+  const bool staged = n_tdq <= 4096 && h.B <= kTailMaxB;
+  if (staged) {
+    for (int i = tid; i < n_tdq; i += 256) s_tdq[i] = h.tdq[i];
+    for (int i = tid; i < h.B; i += 256) s_act[i] = (int)h.action[i];
+    __syncthreads();
+  }
+  auto tdq = [&](int b, int k) { return staged ? s_tdq[b * 2 * h.K + k] : h.tdq[(int64_t)b * 2 * h.K + k]; };
+  auto act_of = [&](int b) { return staged ? s_act[b] : (int)h.action[b]; };
   if (j == 0) {
     // losses[k] = mean_b w_b td^2 (isdqn.py:102), sequential over b: deterministic
     if (tid < h.K) {
       float t = 0.f;
-      for (int b = 0; b < h.B; ++b) t += h.tdq[(int64_t)b * 2 * h.K + h.K + tid];
+      for (int b = 0; b < h.B; ++b) t += tdq(b, h.K + tid);
       const float l = t * h.inv_b;
       h.losses[tid] = l;
       if (h.cumulated) h.cumulated[tid] += (double)l;
@@ -863,7 +877,7 @@ __device__ __forceinline__ void head_tail_block(const HeadTail& h, int j) {
       float t = 0.f;
       if (hd >= 0)
         for (int b = 0; b < h.B; ++b)
-          if ((int)h.action[b] == a) t += h.tdq[(int64_t)b * 2 * h.K + hd];
+          if (act_of(b) == a) t += tdq(b, hd);
       h.dbias[c] = t;
     }
     return;
@@ -875,8 +889,8 @@ __device__ __forceinline__ void head_tail_block(const HeadTail& h, int j) {
   float acc = 0.f;
   if (hd >= 0) {
     for (int b = 0; b < h.B; ++b) {
-      if ((int)h.action[b] != a) continue;
-      const float g = h.tdq[(int64_t)b * 2 * h.K + hd];
+      if (act_of(b) != a) continue;
+      const float g = tdq(b, hd);
       if (g != 0.f) acc = fmaf(h.act[(int64_t)b * h.C + n], g, acc);
     }
   }
@@ -1143,13 +1157,27 @@ dense_finalize_head_kernel(const float* __restrict__ part, int splits, int64_t s
   float z[kRowMaxPerThread];
   float s = 0.f;
 #pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) z[j] = 0.f;
+  if (fin) {  // split partials in ascending order, the loads of 8 splits in flight together (see head_mid_kernel)
+    const float* prow = part + (int64_t)r * N + tid;
+    for (int sp0 = 0; sp0 < splits; sp0 += 8) {
+      float t[8][kRowMaxPerThread];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < kRowMaxPerThread; ++j)
+          t[u][j] = (sp0 + u < splits && tid + j * kRowThreads < N) ? prow[(int64_t)(sp0 + u) * split_stride + j * kRowThreads] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < kRowMaxPerThread; ++j) z[j] += t[u][j];
+    }
+  }
+#pragma unroll
   for (int j = 0; j < kRowMaxPerThread; ++j) {
     const int n = tid + j * kRowThreads;
-    z[j] = 0.f;
     if (fin && n < N) {
-      float v = 0.f;
-      for (int sp = 0; sp < splits; ++sp) v += part[(int64_t)sp * split_stride + (int64_t)r * N + n];
-      z[j] = v + bias[n];
+      z[j] += bias[n];
       s += z[j];
     }
   }
@@ -1239,13 +1267,29 @@ head_mid_kernel(const float* __restrict__ part, int splits, int64_t split_stride
   float z[kRowMaxPerThread], xh[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
   float s = 0.f;
 #pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) z[j] = xh[j] = gam[j] = bet[j] = 0.f;
+  {
+    // split-K partial sums in ascending split order; the loads of 8 splits x every column of the thread are issued
+    // together (a plain `v += part[...]` loop is a chain of dependent L2 round trips: 37 splits cost 37 latencies)
+    const float* prow = part + (int64_t)r * N + ht;
+    for (int sp0 = 0; sp0 < splits; sp0 += 8) {
+      float t[8][kRowMaxPerThread];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < kRowMaxPerThread; ++j)
+          t[u][j] = (sp0 + u < splits && ht + j * kRowThreads < N) ? prow[(int64_t)(sp0 + u) * split_stride + j * kRowThreads] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < kRowMaxPerThread; ++j) z[j] += t[u][j];
+    }
+  }
+#pragma unroll
   for (int j = 0; j < kRowMaxPerThread; ++j) {
     const int n = ht + j * kRowThreads;
-    z[j] = xh[j] = gam[j] = bet[j] = 0.f;
     if (n < N) {
-      float v = 0.f;
-      for (int sp = 0; sp < splits; ++sp) v += part[(int64_t)sp * split_stride + (int64_t)r * N + n];
-      z[j] = v + bias[n];
+      z[j] += bias[n];
       s += z[j];
       if (ln_g) {
         gam[j] = ln_g[n];
@@ -1335,9 +1379,16 @@ head_mid_kernel(const float* __restrict__ part, int splits, int64_t split_stride
     dy[j] = 0.f;
     if (half == 0 && n < N) {
       float dv = 0.f;
-      for (int i = 0; i < K; ++i) {
-        const float v = vals[i];
-        if (v != 0.f) dv = fmaf(v, __ldg(wh + (int64_t)n * NH + (i + 1) * A + act_b), dv);
+      const float* wrow = wh + (int64_t)n * NH + A + act_b;  // head kernel row n at the taken action of head 1, 2, ...
+      for (int i0 = 0; i0 < K; i0 += 8) {  // (loads of 8 heads in flight; zero factors are skipped: x + 0 * w == x)
+        float wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = (i0 + u < K) ? __ldg(wrow + (i0 + u) * A) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float v = (i0 + u < K) ? vals[i0 + u] : 0.f;
+          if (v != 0.f) dv = fmaf(v, wv[u], dv);
+        }
       }
       if (ln_g) {
         dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;

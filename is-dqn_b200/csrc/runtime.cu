@@ -210,6 +210,8 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclUid /* ncclUniqueId by value */, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -227,6 +229,8 @@ int nccl_load() {
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(h, "ncclGroupStart"));
+  g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
     snprintf(g_last_error, sizeof(g_last_error), "libnccl is missing a required symbol");
     return ISDQN_E_NCCL;
@@ -268,6 +272,27 @@ extern "C" int isdqn_dp_allreduce_f32(void* comm, float* d_buf, int64_t n, void*
   if (!g_nccl.handle) return ISDQN_E_NCCL;
   // ncclFloat32 = 7, ncclSum = 0
   return nccl_check(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, 7, 0, comm, as_stream(stream)), "ncclAllReduce");
+}
+
+// The gradient minus one range [skip_off, skip_off + skip_n) that was all-reduced earlier (the hidden Dense kernel, started on
+// the communication stream while the convolution backward was still running): the two remaining ranges as one NCCL group.
+int isdqn_dp_allreduce_rest(void* comm, float* d_buf, int64_t n, int64_t skip_off, int64_t skip_n, void* stream) {
+  if (!comm || !d_buf || n < 0 || skip_off < 0 || skip_n < 0 || skip_off + skip_n > n) return ISDQN_E_INVALID;
+  if (!g_nccl.handle) return ISDQN_E_NCCL;
+  const int64_t tail = n - skip_off - skip_n;
+  const bool group = g_nccl.GroupStart && g_nccl.GroupEnd && skip_off > 0 && tail > 0;
+  int rc = ISDQN_OK;
+  if (group) rc = nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+  if (!rc && skip_off > 0)
+    rc = nccl_check(g_nccl.AllReduce(d_buf, d_buf, (size_t)skip_off, 7, 0, comm, as_stream(stream)), "ncclAllReduce");
+  if (!rc && tail > 0)
+    rc = nccl_check(g_nccl.AllReduce(d_buf + skip_off + skip_n, d_buf + skip_off + skip_n, (size_t)tail, 7, 0, comm, as_stream(stream)),
+                    "ncclAllReduce");
+  if (group) {
+    const int rc2 = nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+    if (!rc) rc = rc2;
+  }
+  return rc;
 }
 
 extern "C" int isdqn_dp_destroy(void* comm) {

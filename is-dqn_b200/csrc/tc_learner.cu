@@ -23,6 +23,7 @@ int isdqn_dense_wgrad_adam_stream_launch(float* d_params, const float* d_grads, 
 int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
                       float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream, int64_t skip_begin,
                       int64_t skip_len, int max_ctas = 0);
+int isdqn_dp_allreduce_rest(void* comm, float* d_buf, int64_t n, int64_t skip_off, int64_t skip_n, void* stream);
 
 namespace isdqn {
 constexpr int kSideCtas = 64;  // grid cap of the tensor-core weight-gradient kernels that run beside the critical path
@@ -631,6 +632,14 @@ int launch_tc2(const P1& p1, int t1x, int t1y, int t1z, int ctas1, const P2& p2,
   return ISDQN_OK;
 }
 
+bool dp_overlap_on() {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_DP_OVERLAP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 bool pair_launch_enabled() {
   static const bool on = [] {
     const char* e = getenv("ISDQN_PAIR");
@@ -1009,6 +1018,7 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   int64_t pend_off = -1, pend_n = 0;    // Dense kernel whose early Adam waits for the next fork point
   int64_t early_off = 0, early_n = 0;   // range already updated on the side stream
   int fused_l = -1;                     // small batch: Dense layer whose weight gradient is recomputed inside its Adam update
+  int64_t dp_early_off = 0, dp_early_n = 0;  // data parallel: gradient range already being all-reduced on the communication stream
   int col_parts[ISDQN_MAX_FEATURES + 1];  // column partials every layer's LayerNorm / ReLU backward produced
   for (int l = 0; l < nl; ++l) col_parts[l] = w.col_ctas[l];
   static const bool ln_fuse_on = [] {
@@ -1093,6 +1103,20 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
     } else if (L.type == 1) {
       rc = launch_gemm_tc<true, true>(w16(wt, t.act16[l - 1]), L.in_dim, dz16, L.out_dim, grads + L.w_off, L.out_dim, 0,
                                       L.in_dim, L.out_dim, B, 1, sw, "tc_dense_wgrad", side ? side_cap : 0);
+      if (!rc && tr->nccl_comm && update && dp_overlap_on() && dp_early_n == 0 && l > 0 && side_stream(0) && !g_profile_on) {
+        // data parallel: this kernel's gradient is 97 % of the bytes and is complete NOW, before the convolution backward
+        // has even started — all-reduce it on the communication stream under the rest of the backward pass
+        cudaStream_t sc = side_stream(0);
+        cudaEvent_t e0 = side_event(kSideEvents - 1), e1 = side_event(kSideEvents - 2);
+        if (!e0 || !e1) return ISDQN_E_CUDA;
+        ISDQN_CUDA_CHECK(cudaEventRecord(e0, s));
+        ISDQN_CUDA_CHECK(cudaStreamWaitEvent(sc, e0, 0));
+        rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads + L.w_off, (int64_t)L.in_dim * L.out_dim, sc);
+        if (rc) return rc;
+        ISDQN_CUDA_CHECK(cudaEventRecord(e1, sc));
+        dp_early_off = L.w_off;
+        dp_early_n = (int64_t)L.in_dim * L.out_dim;
+      }
       // (the early range must be the only one: the final Adam launch passes over a single range)
       if ((side || fmode == 2) && l > 0 && update && early_n == 0 && pend_n == 0 && ((int64_t)L.in_dim * L.out_dim) % 4 == 0 &&
           L.w_off % 4 == 0) {
@@ -1266,8 +1290,14 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   if (!update) return ISDQN_OK;
   if (tr->nccl_comm) {
     ISDQN_PROF(s, "nccl_allreduce");
-    rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, p.layout.total, stream);
-    if (rc) return rc;
+    if (dp_early_n > 0) {  // the big range is in flight (or done) on the communication stream: the small rest, then join
+      rc = isdqn_dp_allreduce_rest(tr->nccl_comm, tr->d_grads, p.layout.total, dp_early_off, dp_early_n, stream);
+      if (rc) return rc;
+      ISDQN_CUDA_CHECK(cudaStreamWaitEvent(s, side_event(kSideEvents - 2), 0));
+    } else {
+      rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, p.layout.total, stream);
+      if (rc) return rc;
+    }
   }
   if (fused_l >= 0) {  // the Dense kernel from its recomputed gradient + every other leaf from `grads`: one launch
     const Layer& L = p.L[fused_l];

@@ -203,8 +203,10 @@ __device__ __forceinline__ void ln_bwd_init(const LnBwdFuse& f, LnBwdCtx& c, flo
     for (int i = etid; i < 3 * BN; i += 32 * kEpilogueWarps) c.acc[i] = 0.f;
   }
 }
-// one tile: thread etid owns LayerNorm row m (valid or not); warp-collective and epilogue-collective (two named barriers)
-template <int BN>
+// one tile: thread etid owns LayerNorm row m (valid or not); warp-collective and epilogue-collective (two named barriers).
+// KEEP_XH: the normalised values stay in registers between the two passes (single-wave launches, 255 registers available);
+// otherwise they are read a second time (L1 / L2 hits), which keeps two CTAs per SM resident in the throughput shape.
+template <int BN, bool KEEP_XH>
 __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& c, uint32_t tmem_lane_base, bool valid, int64_t m,
                                             uint32_t* stg, int etid) {
   static_assert(BN == 32 || BN == 64, "fused LayerNorm backward: 32 or 64 channels");
@@ -213,6 +215,7 @@ __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& 
   const float4* pg = reinterpret_cast<const float4*>(c.prm);
   const float4* pb = reinterpret_cast<const float4*>(c.prm + BN);
   float dy[BN];
+  float xk[KEEP_XH ? BN : 1];
   float sg = 0.f, sgx = 0.f;
 #pragma unroll
   for (int cb = 0; cb < BN / 32; ++cb) {
@@ -227,6 +230,7 @@ __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& 
       for (int j = 0; j < 4; ++j) {
         const float d = (valid && xx[j] * gg[j] + bb[j] > 0.f) ? v[4 * q + j] : 0.f;
         dy[cb * 32 + 4 * q + j] = d;
+        if (KEEP_XH) xk[KEEP_XH ? cb * 32 + 4 * q + j : 0] = xx[j];
         const float g = d * gg[j];
         sg += g;
         sgx += g * xx[j];
@@ -239,27 +243,34 @@ __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& 
   named_bar_sync(2, 32 * kEpilogueWarps);  // the previous tile's partial sums have been folded into acc
 #pragma unroll
   for (int cb = 0; cb < BN / 32; ++cb) {
-    float a0[32], a1[32], a2[32];
+    float xx[32];
+    if (KEEP_XH) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 x4 = valid ? __ldg(xr + cb * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 g4 = pg[cb * 8 + q];
-      const float xx[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+      for (int i = 0; i < 32; ++i) xx[i] = xk[KEEP_XH ? cb * 32 + i : 0];
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d = dy[cb * 32 + 4 * q + j];
-        a0[4 * q + j] = rs * (d * gg[j] - mg - xx[j] * mgx);
-        a1[4 * q + j] = d * xx[j];
-        a2[4 * q + j] = d;
+      for (int q = 0; q < 8; ++q) {
+        const float4 x4 = valid ? __ldg(xr + cb * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xx[4 * q] = x4.x; xx[4 * q + 1] = x4.y; xx[4 * q + 2] = x4.z; xx[4 * q + 3] = x4.w;
       }
     }
+    float a[32];
+    // gradient w.r.t. the pre-activation: stored as bf16, column-summed for the bias gradient
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = rs * (dy[cb * 32 + i] * c.prm[cb * 32 + i] - mg - xx[i] * mgx);
     {
       uint32_t w[16];  // 32 bf16 = one 64-byte segment of the row
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = pack_bf16(a0[2 * i], a0[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16(a[2 * i], a[2 * i + 1]);
       warp_store_block16(stg, w, f.dz16 + (valid ? m : 0) * BN + cb * 32, valid);
     }
-    const float r0 = warp_transpose_sum32(a0), r1 = warp_transpose_sum32(a1), r2 = warp_transpose_sum32(a2);
+    const float r0 = warp_transpose_sum32(a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = dy[cb * 32 + i] * xx[i];  // LayerNorm scale gradient terms
+    const float r1 = warp_transpose_sum32(a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = dy[cb * 32 + i];          // LayerNorm shift gradient terms
+    const float r2 = warp_transpose_sum32(a);
     float* pw = c.part + warp * 3 * BN + cb * 32 + lane;
     pw[0] = r0;
     pw[BN] = r1;
@@ -386,7 +397,7 @@ struct GemmTmaTC {
     const int m = m0 + etid;
     if constexpr (BN <= 64) {
       if (ln.xhat) {
-        ln_bwd_tile<BN>(ln, e.lc, tmem_lane_base, m < M, (int64_t)m * ln_rows_per_m + n0 / BN, stg, etid);
+        ln_bwd_tile<BN, WIDE_>(ln, e.lc, tmem_lane_base, m < M, (int64_t)m * ln_rows_per_m + n0 / BN, stg, etid);
         return;
       }
     }
@@ -1055,7 +1066,7 @@ struct ConvDgradTmaTC {
     const int64_t pix = valid ? ((int64_t)img * H + (c.iy_first + stride * iyc)) * W + (c.ix_first + stride * ixc) : 0;
     if constexpr (BN <= 64) {
       if (ln.xhat) {
-        ln_bwd_tile<BN>(ln, e.lc, tmem_lane_base, valid, pix, stg, etid);
+        ln_bwd_tile<BN, WIDE_>(ln, e.lc, tmem_lane_base, valid, pix, stg, etid);
         return;
       }
     }

@@ -452,7 +452,9 @@ class iSDQN:
         tr = self._train_struct(ctx, params, optimizer_state, B)
         tr.d_cumulated = self._d_cumulated.data_ptr() if accumulate else None
         tr.d_is_weights = ctx["is_weights"].data_ptr() if weighted else None
-        if self._use_graph and ctx["warm"] >= 1 and self._nccl_comm is None:
+        # (data parallel: the NCCL all-reduces are captured with the step — NCCL supports stream capture; ISDQN_DP_GRAPH=0
+        # keeps direct launches)
+        if self._use_graph and ctx["warm"] >= 1 and (self._nccl_comm is None or os.environ.get("ISDQN_DP_GRAPH", "1") != "0"):
             # capture this very step (it executes on replay, not during capture)
             if ctx["graph"] is not None:
                 self._lib.isdqn_graph_destroy(ctx["graph"])
