@@ -17,6 +17,10 @@ $(LIB): $(OBJS)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) -shared -o $@ $(OBJS) -ldl -Xlinker --version-script=$(PKG)/csrc/exports.map
 
+# optional: the XLA FFI handlers (needs xla/ffi/api/ffi.h, e.g. XLA_FFI_INCLUDE=$$(python -c "import jaxlib,os;print(os.path.join(jaxlib.__path__[0],'include'))"))
+ffi: $(LIB)
+	g++ -O2 -std=c++17 -fPIC -shared -I$(XLA_FFI_INCLUDE) -I/usr/local/cuda/include $(PKG)/csrc/xla_ffi.cc -o $(PKG)/lib/libisdqn_b200_ffi.so -L$(PKG)/lib -lisdqn_b200
+
 clean:
 	rm -rf build $(LIB)
-.PHONY: all clean
+.PHONY: all clean ffi

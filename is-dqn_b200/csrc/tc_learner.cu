@@ -743,6 +743,13 @@ int launch_conv_bwd_pair_t(const Layer& V, const bf16* x, const bf16* dz, float*
   if (ctas_d < 1) ctas_d = 1;
   if (ctas_d > d_tiles) ctas_d = d_tiles;
   ctas_d = ceil_div(d_tiles, ceil_div(d_tiles, ctas_d));  // every CTA the same number of tiles
+  // with the LayerNorm backward fused the input-gradient tiles are bound by their epilogue: one tile per CTA when the
+  // weight gradient can still have a CTA per 128-row tile of K and 4 splits (ISDQN_PAIR_D1=0: the proportional split)
+  static const bool d1 = [] {
+    const char* e = getenv("ISDQN_PAIR_D1");
+    return !(e && e[0] == '0');
+  }();
+  if (d1 && ln && d_tiles + 4 * tiles_k0 <= kNumSMs) ctas_d = d_tiles;
   if (ctas_d > kNumSMs - tiles_k0) ctas_d = kNumSMs - tiles_k0;
   int splits = (kNumSMs - ctas_d) / tiles_k0;
   if (splits > max_splits) splits = max_splits;
@@ -917,8 +924,11 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       if (rc) return rc;
       const Layer& Hd = p.L[l + 1];
       static const bool mid_on = [] {
+        // opt-in: measured 124.7 us of in-graph intervals against 119.2 us for the three kernels it replaces — its CTAs are
+        // bound by the same dependent L2 round trips, and the cross-sample tail it leaves to the partial reduction delays
+        // the optimiser (profiles/r02_summary.md)
         const char* e = getenv("ISDQN_MID");
-        return !(e && e[0] == '0');
+        return e && e[0] == '1';
       }();
       if (mid_on && backward && l + 2 == nl && B <= 256 && Hd.out_dim <= 128 && L.out_dim <= kRowThreads * kRowMaxPerThread &&
           w.wsplits[nl - 1] == 1 && w.col_ctas[l] == B && p.n_out >= 2 * net->n_heads && L.relu) {

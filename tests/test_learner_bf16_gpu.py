@@ -149,3 +149,20 @@ def test_update_is_adam_of_the_reported_gradient_bf16(B):
             assert e <= tol, f"B={B} t={t}: {name} differs from Adam(grad_on_batch) by {e:.3e} (rel L2)"
         # the bf16 shadow the next forward reads is the rounding of the new parameters, everywhere
         assert torch.equal(agent.params.shadow.float(), agent.params.flat.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("env", [{"ISDQN_MID": "1"}, {"ISDQN_PAIR": "0", "ISDQN_LNFUSE": "0"}, {"ISDQN_PAIR_D1": "0"}],
+                         ids=["head_mid", "unfused_backward", "pair_proportional"])
+def test_alternative_launch_plans_keep_parity(env):
+    """The opt-in / fallback launch plans of the batch-32 chain (one-launch head step; separate weight-gradient,
+    input-gradient and LayerNorm-backward launches) against the same oracle bars, in a fresh process (the switches are
+    read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_learner_bf16_gpu.py"), "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider", "-k", "atari_k9_batch32 or update_is_adam or graph_replay"],
+                       cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
