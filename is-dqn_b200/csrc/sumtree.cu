@@ -241,6 +241,56 @@ sumtree_set_kernel(double* nodes, int depth, const int32_t* __restrict__ idx, co
   sumtree_set_block<MAXM, THREADS, false>(nodes, depth, idx, val, m, max_prio, status, sm);
 }
 
+// One `set` of m <= 2 entries executed by ONE warp, no sort network and no block barrier: lane s owns level s above the
+// leaves (depth <= 31 <= warp size).  These are the ops of the add / evict traffic (PrioritizedSamplingDistribution.add:
+// m = 1, .remove: m = 2, samplers.py:67-103).  Same arithmetic as sumtree_set_block: first duplicate wins, deltas against
+// the leaf values before the op, ascending-leaf fold order where the two chains share an ancestor.
+__device__ __forceinline__ void sumtree_set_small(double* nodes, int depth, int m, int i0, double v0, int i1, double v1,
+                                                  double* max_prio, uint32_t* status) {
+  const int lane = threadIdx.x & 31;
+  const int n_leaves = 1 << (depth - 1);
+  const int first_leaf = n_leaves - 1;
+  const double max_old = max_prio ? *max_prio : 0.0;
+  int bad = 0;
+  v0 = resolve_value<true>(v0, nodes, first_leaf, n_leaves, max_old, &bad);
+  if (m == 2) v1 = resolve_value<true>(v1, nodes, first_leaf, n_leaves, max_old, &bad);
+  int st = 0;
+  if (bad || i0 < 0 || i0 >= n_leaves || (m == 2 && (i1 < 0 || i1 >= n_leaves))) st |= ISDQN_ST_INDEX_RANGE;
+  if (!(v0 >= 0.0) || (m == 2 && !(v1 >= 0.0))) st |= ISDQN_ST_NEGATIVE_VALUE;
+  if (st) {  // sum_tree.py:31 — nothing is modified
+    if (lane == 0 && status) atomicOr(status, (uint32_t)st);
+    return;
+  }
+  if (lane == 0 && max_prio) *max_prio = fmax(max_old, m == 2 ? fmax(v0, v1) : v0);
+  if (m == 2 && i0 == i1) m = 1;  // np.unique(..., return_index=True): the first occurrence wins
+  if (m == 2 && i1 < i0) {        // ascending leaves
+    const int ti = i0; i0 = i1; i1 = ti;
+    const double tv = v0; v0 = v1; v1 = tv;
+  }
+  // this lane's nodes (its loads are issued together with the leaf loads below: one round trip for both)
+  const bool act = lane < depth;
+  const int n0 = ((first_leaf + i0 + 1) >> lane) - 1;
+  const int n1 = m == 2 ? ((first_leaf + i1 + 1) >> lane) - 1 : n0;
+  const double c0 = act ? nodes[n0] : 0.0;
+  const double c1 = (act && n1 != n0) ? nodes[n1] : 0.0;
+  const double d0 = v0 - nodes[first_leaf + i0];
+  const double d1 = m == 2 ? v1 - nodes[first_leaf + i1] : 0.0;
+  if (act) {
+    if (m == 1) {
+      nodes[n0] = __dadd_rn(c0, d0);
+    } else if (n0 != n1) {
+      nodes[n0] = __dadd_rn(c0, d0);
+      nodes[n1] = __dadd_rn(c1, d1);
+    } else {
+      nodes[n0] = __dadd_rn(__dadd_rn(c0, d0), d1);
+    }
+  }
+  __syncwarp();  // the next op of this warp reads what other lanes wrote
+}
+
+constexpr int kOpsChunk = 256;       // ops whose descriptors are staged in shared memory at a time
+constexpr int kOpsChunkEntries = 1024;
+
 template <int MAXM, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_offset, int n_ops,
@@ -248,17 +298,54 @@ sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_
                        uint32_t* status) {
   extern __shared__ __align__(16) unsigned char set_raw[];
   SetSmem sm = carve_set_smem<MAXM, THREADS>(set_raw);
-  for (int op = 0; op < n_ops; ++op) {
-    const int b = op_offset[op], e = op_offset[op + 1];
-    if (e - b > MAXM || e < b) {
-      if (threadIdx.x == 0 && status) atomicOr(status, ISDQN_ST_OP_TOO_LARGE);
-      continue;
+  // Descriptors of the next kOpsChunk ops (offsets, and their entries when they fit) are staged with coalesced loads:
+  // a small op then costs the round trips of its tree accesses only, not three more for its own description.
+  __shared__ int s_off[kOpsChunk + 1];
+  __shared__ int s_idx[kOpsChunkEntries];
+  __shared__ double s_val[kOpsChunkEntries];
+  const int warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < n_ops; c0 += kOpsChunk) {
+    const int c1 = min(n_ops, c0 + kOpsChunk);
+    for (int i = threadIdx.x; i <= c1 - c0; i += THREADS) s_off[i] = op_offset[c0 + i];
+    __syncthreads();
+    const int e0 = s_off[0], e1 = s_off[c1 - c0];
+    const bool staged = e1 - e0 <= kOpsChunkEntries && e1 >= e0;
+    if (staged) {
+      for (int i = threadIdx.x; i < e1 - e0; i += THREADS) {
+        s_idx[i] = idx[e0 + i];
+        s_val[i] = val[e0 + i];
+      }
     }
-    // sets are strictly ordered: op+1 reads the nodes op wrote (the trailing __syncthreads orders them)
-    sumtree_set_block<MAXM, THREADS, true>(nodes, depth, idx + b, val + b, e - b, max_prio, status, sm);
+    __syncthreads();
+    bool small_pending = false;  // warp 0 may still be working on small ops the other warps have skipped
+    for (int op = c0; op < c1; ++op) {
+      const int b = s_off[op - c0], e = s_off[op - c0 + 1];
+      const int m = e - b;
+      if (m > MAXM || m < 0) {
+        if (threadIdx.x == 0 && status) atomicOr(status, ISDQN_ST_OP_TOO_LARGE);
+        continue;
+      }
+      if (m == 0) continue;
+      if (m <= 2) {
+        if (warp == 0) {
+          const int i0 = staged ? s_idx[b - e0] : idx[b];
+          const double v0 = staged ? s_val[b - e0] : val[b];
+          const int i1 = m == 2 ? (staged ? s_idx[b + 1 - e0] : idx[b + 1]) : 0;
+          const double v1 = m == 2 ? (staged ? s_val[b + 1 - e0] : val[b + 1]) : 0.0;
+          sumtree_set_small(nodes, depth, m, i0, v0, i1, v1, max_prio, status);
+        }
+        small_pending = true;
+        continue;
+      }
+      if (small_pending) {  // sets are strictly ordered: this op reads the nodes the small ops wrote
+        __syncthreads();
+        small_pending = false;
+      }
+      sumtree_set_block<MAXM, THREADS, true>(nodes, depth, idx + b, val + b, m, max_prio, status, sm);
+    }
+    __syncthreads();  // (also: the staged descriptors are no longer read)
   }
 }
-
 
 // PrioritizedSamplingDistribution.update (samplers.py:76-88) with keys and priorities that live on the device: key ->
 // dense index through the device mirror of `_key_to_index` (slot = key mod n_slots), priority -> priority ** alpha (0 stays 0).

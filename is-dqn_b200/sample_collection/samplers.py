@@ -332,6 +332,17 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         val[r0[two] + 1] = 0.0
         if idx.size and int(idx.max()) + self._sum_tree._first_leaf_offset >= self._sum_tree._d_nodes.numel():
             raise IndexError(f"index out of bounds for the sum tree of capacity {self._max_capacity}")
+        if evict_from > 1:
+            # The adds before the first eviction set DISTINCT, ASCENDING leaves (fresh dense indices): one `set` of all of
+            # them performs, node by node, the same additions in the same order as the single sets (np.add.at walks the
+            # sorted leaves), so they are merged into ops of up to SUMTREE_OP_MAX entries, which the kernel spreads over
+            # a whole CTA instead of one warp-op at a time.  (The tag "max" resolves to the same value in every merged
+            # entry: nothing in such an op can raise max_recorded_priority above the tag's own value.)
+            n_merge = evict_from
+            step = _lib.SUMTREE_OP_MAX
+            merged = np.full((n_merge + step - 1) // step, step, dtype=np.int32)
+            merged[-1] = n_merge - step * (merged.size - 1)
+            lens = np.concatenate((merged, lens[n_merge:]))
         self._sum_tree._enqueue_ops(idx, val, lens)
         return add_idx, rem_idx
 

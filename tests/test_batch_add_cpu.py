@@ -117,6 +117,18 @@ class _FakeTree:
             o += m
 
 
+def _singles(ops):
+    """Ops with the merged fill sets (distinct ascending leaves, no leaf tag) split back into single sets: node by node
+    np.add.at performs the same additions in the same order either way."""
+    out = []
+    for idx, val in ops:
+        if len(idx) >= 2 and all(v > -1.0 for v in val) and all(a < b for a, b in zip(idx, idx[1:])):
+            out.extend(([i], [v]) for i, v in zip(idx, val))
+        else:
+            out.append((idx, val))
+    return out
+
+
 def _bare_sampler(cls, capacity, exponent=1.0):
     s = object.__new__(cls)
     s._key_to_index, s._index_to_key, s._patches = {}, [], {}
@@ -157,7 +169,8 @@ def test_sampler_run_equals_add_remove_calls(capacity, exponent):
             assert one._key_to_index == run._key_to_index
             assert one._patches == run._patches
             if cls is PrioritizedSamplingDistribution:
-                assert one._sum_tree.ops == run._sum_tree.ops
+                assert _singles(one._sum_tree.ops) == _singles(run._sum_tree.ops)
+                assert all(len(i) <= 1024 for i, _ in run._sum_tree.ops)
                 one._sum_tree.ops.clear()
                 run._sum_tree.ops.clear()
 
@@ -168,4 +181,4 @@ def test_sampler_run_max_priority_tag():
 
     s = _bare_sampler(PrioritizedSamplingDistribution, 5)
     s._add_remove_run(0, 3, 0, 3, "max")
-    assert s._sum_tree.ops == [([0], [_lib.SUMTREE_TAG_MAX]), ([1], [_lib.SUMTREE_TAG_MAX]), ([2], [_lib.SUMTREE_TAG_MAX])]
+    assert _singles(s._sum_tree.ops) == [([0], [_lib.SUMTREE_TAG_MAX]), ([1], [_lib.SUMTREE_TAG_MAX]), ([2], [_lib.SUMTREE_TAG_MAX])]
