@@ -306,6 +306,7 @@ int isdqn_dp_destroy(void* comm);
  * records event.  Nothing synchronises except isdqn_event_synchronize. */
 int isdqn_event_create(void** out_event);
 int isdqn_event_destroy(void* event);
+int isdqn_event_record(void* event, void* stream);
 int isdqn_event_synchronize(void* event);
 int isdqn_stage_batch(const void* h_src, void* d_stage, void* d_dst, int64_t bytes, void* copy_stream, void* step_stream,
                       void* ev_h2d_done, void* ev_stage_free);
@@ -332,6 +333,13 @@ int isdqn_act(const isdqn_net* net, const float* d_params, const uint8_t* d_obs,
 int isdqn_act_host(const isdqn_net* net, const float* d_params, const uint8_t* h_obs_pinned, uint8_t* d_obs,
                    int64_t obs_bytes, float* d_q, int32_t* d_actions, int32_t* h_actions_pinned, void* d_workspace,
                    int64_t workspace_bytes, void* stream, void* event);
+/* isdqn_act_mapped: the same call with no copies and no event — the kernel reads the observation out of pinned host
+ * memory (mapped into the device's address space) and writes the 1 + K actions and then `seq` into *h_flag_pinned straight
+ * back; the host spins on the flag (isdqn_act_wait, or inside the call when timeout_us > 0).  ISDQN_E_CUDA on timeout. */
+int isdqn_act_mapped(const isdqn_net* net, const float* d_params, const uint8_t* h_obs_pinned, float* d_q,
+                     int32_t* h_actions_pinned, int32_t* h_flag_pinned, int32_t seq, void* d_workspace,
+                     int64_t workspace_bytes, void* stream, int64_t timeout_us);
+int isdqn_act_wait(const int32_t* h_flag_pinned, int32_t seq, int64_t timeout_us);
 
 /* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
  * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */

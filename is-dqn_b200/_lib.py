@@ -152,6 +152,7 @@ PROTOTYPES = {
     "isdqn_sample_uniform_ws": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "isdqn_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "isdqn_event_destroy": (C.c_int, [_P]),
+    "isdqn_event_record": (C.c_int, [_P, _P]),
     "isdqn_event_synchronize": (C.c_int, [_P]),
     "isdqn_stage_batch": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
     "isdqn_read_async": (C.c_int, [_P, _P, _I64, _P, _P]),
@@ -160,6 +161,8 @@ PROTOTYPES = {
     "isdqn_act_workspace_bytes": (_I64, [C.POINTER(Net)]),
     "isdqn_act": (C.c_int, [C.POINTER(Net), _P, _P, _P, _P, _P, _I64, _P]),
     "isdqn_act_host": (C.c_int, [C.POINTER(Net), _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P]),
+    "isdqn_act_mapped": (C.c_int, [C.POINTER(Net), _P, _P, _P, _P, _P, _I32, _P, _I64, _P, _I64]),
+    "isdqn_act_wait": (C.c_int, [_P, _I32, _I64]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),
@@ -286,11 +289,13 @@ def pinned_pack_base(arrays, offs) -> Optional[int]:
 
 class PinnedStager:
     """Small host arrays -> device with ONE asynchronous copy from pinned memory (instead of one synchronous pageable copy
-    per array): a ring of `slots` (pinned block, device block) pairs.  The device views `put` returns stay valid until the
-    same slot comes round again (`slots` - 1 further calls); consumers must be enqueued on the stream `put` was called on."""
+    per array): a ring of `slots` (pinned block, device block) pairs.  The device addresses / views a call returns stay
+    valid until the same slot comes round again (`slots` - 1 further calls); consumers must be enqueued on the stream the
+    call was made on.  `put_ptrs` is the lean form (a handful of ctypes calls, no tensor objects) for per-step paths."""
 
     def __init__(self, nbytes: int = 1 << 16, slots: int = 4):
         self._torch = require_cuda()
+        self._lib = load()
         self._n = 0
         self._slots = slots
         self._i = 0
@@ -300,15 +305,20 @@ class PinnedStager:
     def _grow(self, nbytes: int) -> None:
         t = self._torch
         for ev in self._ev:
-            ev.synchronize()
+            check(self._lib.isdqn_event_synchronize(ev), "isdqn_event_synchronize")
         self._n = max(int(nbytes), 2 * self._n)
         self._host = [t.empty(self._n, dtype=t.uint8).pin_memory() for _ in range(self._slots)]
         self._host_np = [h.numpy() for h in self._host]
+        self._host_ptr = [h.data_ptr() for h in self._host]
         self._dev = [t.empty(self._n, dtype=t.uint8, device="cuda") for _ in range(self._slots)]
-        self._ev = [t.cuda.Event() for _ in range(self._slots)]
+        self._dev_ptr = [d.data_ptr() for d in self._dev]
+        if not self._ev:
+            for _ in range(self._slots):
+                ev = C.c_void_p()
+                check(self._lib.isdqn_event_create(ev), "isdqn_event_create")
+                self._ev.append(ev)
 
-    def put(self, *arrays):
-        t = self._torch
+    def _stage(self, arrays):
         offs, o = [], 0
         for a in arrays:
             offs.append(o)
@@ -317,12 +327,24 @@ class PinnedStager:
             self._grow(o)
         s = self._i
         self._i = (s + 1) % self._slots
-        self._ev[s].synchronize()  # the previous copy out of this pinned block has completed
+        lib = self._lib
+        lib.isdqn_event_synchronize(self._ev[s])  # the previous copy out of this pinned block has completed
         h = self._host_np[s]
         for a, off in zip(arrays, offs):
-            h[off : off + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
-        self._dev[s][:o].copy_(self._host[s][:o], non_blocking=True)
-        self._ev[s].record()
+            h[off : off + a.nbytes] = a.reshape(-1).view(np.uint8) if a.flags.c_contiguous else np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+        stream = stream_ptr()
+        check(lib.isdqn_write_async(self._dev_ptr[s], self._host_ptr[s], o, stream), "isdqn_write_async")
+        check(lib.isdqn_event_record(self._ev[s], stream), "isdqn_event_record")
+        return s, offs
+
+    def put_ptrs(self, *arrays):
+        """Device addresses (ints) of the staged copies of `arrays`."""
+        s, offs = self._stage(arrays)
+        base = self._dev_ptr[s]
+        return [base + off for off in offs]
+
+    def put(self, *arrays):
+        s, offs = self._stage(arrays)
         d = self._dev[s]
         return [d[off : off + a.nbytes].view(_TORCH_DTYPES[a.dtype.str]()) for a, off in zip(arrays, offs)]
 

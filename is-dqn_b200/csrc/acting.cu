@@ -15,6 +15,8 @@
 //                  (75 KB from L2) instead of paying one more barrier.
 //   head layer   : CTA h computes the A Q-values of head h and their argmax (first maximum, like jnp.argmax).
 // fp32 master weights and fp32 arithmetic whatever the learner's compute dtype (the reference acts in fp32).
+#include <chrono>
+
 #include "learner_kernels.cuh"
 #include "plan.cuh"
 
@@ -120,7 +122,8 @@ __device__ void finalize_hidden(const ActLayer& P, const float* __restrict__ par
 
 __global__ void __launch_bounds__(kActThreads, 1)
 act_forward_kernel(const __grid_constant__ ActPlan plan, const float* __restrict__ params, const uint8_t* __restrict__ obs,
-                   float* scratch, unsigned* bar, float* __restrict__ q_out, int32_t* __restrict__ actions) {
+                   float* scratch, unsigned* bar, float* __restrict__ q_out, int32_t* __restrict__ actions,
+                   int* host_flag, int seq) {
   __shared__ __align__(16) float xs[kActMaxX];
   __shared__ __align__(16) float ps[kActMaxOut];
   __shared__ __align__(16) float zs[kActMaxOut];
@@ -299,12 +302,19 @@ act_forward_kernel(const __grid_constant__ ActPlan plan, const float* __restrict
   }
   if (tid == 0) trace_mark(10 + 2 * (plan.n_layers - 1));
   // last CTA out re-arms the barrier for the next launch (everybody has passed the final barrier by then)
+  // (host_flag: `actions` is mapped host memory and the host spins on *host_flag == seq instead of synchronising an event:
+  // every CTA makes its action visible system-wide before it checks out, the last one out raises the flag)
   if (tid == 0) {
-    __threadfence();
+    if (host_flag) __threadfence_system();
+    else __threadfence();
     if (atomicAdd(bar + 1, 1u) == (unsigned)G - 1u) {
       bar[0] = 0u;
       bar[1] = 0u;
       __threadfence();
+      if (host_flag) {
+        *reinterpret_cast<volatile int*>(host_flag) = seq;
+        __threadfence_system();
+      }
     }
   }
 }
@@ -412,8 +422,64 @@ extern "C" int isdqn_act(const isdqn_net* net, const float* d_params, const uint
   float* scratch = reinterpret_cast<float*>(d_workspace);
   unsigned* bar = reinterpret_cast<unsigned*>(d_workspace);
   // cooperative launch: the runtime guarantees (or refuses) the co-residency the grid barrier relies on
-  void* args[] = {(void*)&a, (void*)&d_params, (void*)&d_obs, (void*)&scratch, (void*)&bar, (void*)&d_q, (void*)&d_actions};
+  int* no_flag = nullptr;
+  int seq = 0;
+  void* args[] = {(void*)&a, (void*)&d_params, (void*)&d_obs, (void*)&scratch, (void*)&bar, (void*)&d_q, (void*)&d_actions,
+                  (void*)&no_flag, (void*)&seq};
   ISDQN_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(act_forward_kernel), dim3(G), dim3(kActThreads), args, 0, s));
+  return ISDQN_OK;
+}
+
+// The env-step call without copy or event traffic: the kernel reads the observation straight out of pinned (mapped) host
+// memory and writes the 1 + K greedy actions and a completion flag straight back; the host spins on the flag.
+extern "C" int isdqn_act_mapped(const isdqn_net* net, const float* d_params, const uint8_t* h_obs_pinned, float* d_q,
+                                int32_t* h_actions_pinned, int32_t* h_flag_pinned, int32_t seq, void* d_workspace,
+                                int64_t workspace_bytes, void* stream, int64_t timeout_us) {
+  if (!net || !d_params || !h_obs_pinned || !h_actions_pinned || !h_flag_pinned || !d_workspace) return ISDQN_E_INVALID;
+  Plan p;
+  int rc = build_plan(net, &p);
+  if (rc) return rc;
+  const int G = act_grid_ctas();
+  if (G < 1) return ISDQN_E_UNSUPPORTED;
+  ActPlan a;
+  int64_t floats = 0;
+  rc = build_act_plan(net, p, G, &a, &floats);
+  if (rc) return rc;
+  if (floats * (int64_t)sizeof(float) > workspace_bytes) return ISDQN_E_INVALID;
+  // device-side aliases of the pinned blocks (identical to the host pointers under unified addressing)
+  uint8_t* d_obs = nullptr;
+  int32_t* d_act = nullptr;
+  int* d_flag = nullptr;
+  ISDQN_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_obs), const_cast<uint8_t*>(h_obs_pinned), 0));
+  ISDQN_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_act), h_actions_pinned, 0));
+  ISDQN_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_flag), h_flag_pinned, 0));
+  cudaStream_t s = as_stream(stream);
+  ISDQN_PROF(s, "act_forward");
+  float* scratch = reinterpret_cast<float*>(d_workspace);
+  unsigned* bar = reinterpret_cast<unsigned*>(d_workspace);
+  const uint8_t* obs_c = d_obs;
+  int seq_i = seq;
+  void* args[] = {(void*)&a, (void*)&d_params, (void*)&obs_c, (void*)&scratch, (void*)&bar, (void*)&d_q, (void*)&d_act,
+                  (void*)&d_flag, (void*)&seq_i};
+  ISDQN_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(act_forward_kernel), dim3(G), dim3(kActThreads), args, 0, s));
+  if (timeout_us <= 0) return ISDQN_OK;  // the caller waits itself (isdqn_act_wait)
+  return isdqn_act_wait(h_flag_pinned, seq, timeout_us);
+}
+
+extern "C" int isdqn_act_wait(const int32_t* h_flag_pinned, int32_t seq, int64_t timeout_us) {
+  if (!h_flag_pinned) return ISDQN_E_INVALID;
+  const volatile int32_t* f = h_flag_pinned;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0; *f != seq; ++spins) {
+    if ((spins & 1023u) == 1023u) {
+      if (std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > timeout_us) {
+        // a faulted kernel never raises the flag: report the fault if the runtime knows of one, a timeout otherwise
+        const cudaError_t e = cudaPeekAtLastError();
+        set_last_cuda_error(e != cudaSuccess ? e : cudaErrorTimeout, "isdqn_act_wait");
+        return ISDQN_E_CUDA;
+      }
+    }
+  }
   return ISDQN_OK;
 }
 

@@ -331,6 +331,12 @@ extern "C" int isdqn_event_destroy(void* event) {
   if (event) ISDQN_CUDA_CHECK(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event)));
   return ISDQN_OK;
 }
+extern "C" int isdqn_event_record(void* event, void* stream) {
+  if (!event) return ISDQN_E_INVALID;
+  ISDQN_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), as_stream(stream)));
+  return ISDQN_OK;
+}
+
 extern "C" int isdqn_event_synchronize(void* event) {
   if (!event) return ISDQN_E_INVALID;
   ISDQN_CUDA_CHECK(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event)));

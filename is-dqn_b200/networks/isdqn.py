@@ -593,6 +593,19 @@ class iSDQN:
             a["fused"] = t.zeros(nb, dtype=t.uint8, device="cuda") if nb > 0 else False
             if nb > 0:
                 t.cuda.current_stream().synchronize()  # the zeroed barrier words precede the first launch on any stream
+        if a["fused"] is not False and os.environ.get("ISDQN_ACT_MAPPED", "1") != "0":
+            # no copies, no event: the kernel reads the pinned observation and writes actions + a flag the host spins on
+            if "h_flag" not in a:
+                a["h_flag"] = _lib.pinned_block(64).view(t.int32)
+                a["seq"] = 0
+            a["seq"] = (a["seq"] + 1) & 0x3FFFFFFF
+            _lib.check(
+                lib.isdqn_act_mapped(net._net, params.flat.data_ptr(), a["h_obs"].data_ptr(), a["q"].data_ptr(),
+                                     a["h_arg"].data_ptr(), a["h_flag"].data_ptr(), a["seq"], a["fused"].data_ptr(),
+                                     a["fused"].numel(), cur.cuda_stream, 5_000_000),
+                "isdqn_act_mapped",
+            )
+            return a["h_arg_np"]
         if a["fused"] is not False:
             _lib.check(
                 lib.isdqn_act_host(net._net, params.flat.data_ptr(), a["h_obs"].data_ptr(), ctx["state"].data_ptr(), a["nbytes"],

@@ -243,10 +243,14 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         if not isinstance(keys, np.ndarray):
             keys = np.asarray([keys], dtype=np.int32)
         priorities = np.where(priorities == 0.0, 0.0, priorities**self._priority_exponent)
-        self._sum_tree.set(
-            np.fromiter((self._key_to_index[key] for key in keys), dtype=np.int32),
-            priorities,
-        )
+        kti = self._key_to_index
+        idx = np.fromiter((kti[key] for key in keys.tolist()), dtype=np.int32, count=keys.size)
+        tree = self._sum_tree
+        vals = np.ascontiguousarray(priorities, dtype=np.float64).reshape(-1)
+        if 2 < idx.size <= _lib.SUMTREE_SET_MAX and vals.size == idx.size and not (vals < 0.0).any() and not np.isnan(vals).any():
+            tree._set_now(idx, vals)  # (indices come from the live maps: in range by construction)
+        else:
+            tree.set(idx, priorities)
 
     def update_device(self, d_keys, d_priorities, prio_rows: int = 0, offset: float = 0.0) -> None:
         """`update` for int32 keys and priorities that live on the device (nothing synchronises): d_priorities is

@@ -30,6 +30,7 @@ class SumTree:
         self._d_nodes = torch.zeros((2**self._depth) - 1, dtype=torch.float64, device=self._device)
         self._d_max = torch.ones(1, dtype=torch.float64, device=self._device)  # max_recorded_priority = 1.0
         self._d_status = torch.zeros(1, dtype=torch.int32, device=self._device)
+        self._p_nodes, self._p_max, self._p_status = self._d_nodes.data_ptr(), self._d_max.data_ptr(), self._d_status.data_ptr()
         self._q_idx: list = []   # queued sets: leaf indices / values of every op, concatenated on flush
         self._q_val: list = []
         self._q_len: list = []   # ... and the number of entries of every op (arrays)
@@ -62,16 +63,7 @@ class SumTree:
                 raise _lib.IsdqnNativeError(
                     f"SumTree.set with {m} indices exceeds the kernel limit {_lib.SUMTREE_SET_MAX}"
                 )
-            if self._stager is None:
-                self._stager = _lib.PinnedStager(1 << 14)
-            d_idx, d_val = self._stager.put(idx32, val64)
-            _lib.check(
-                self._lib.isdqn_sumtree_set(
-                    self._d_nodes.data_ptr(), self._depth, d_idx.data_ptr(), d_val.data_ptr(), m,
-                    self._d_max.data_ptr(), self._d_status.data_ptr(), _lib.stream_ptr(),
-                ),
-                "isdqn_sumtree_set",
-            )
+            self._set_now(idx32, val64)
             return
         self._q_idx.append(idx32)
         self._q_val.append(val64)
@@ -93,6 +85,19 @@ class SumTree:
         if self._q_entries >= self._QUEUE_LIMIT:
             self.flush()
 
+    def _set_now(self, idx32: np.ndarray, val64: np.ndarray) -> None:
+        """One `set` applied right away (after whatever is queued): one staged copy + one launch, no queue bookkeeping —
+        the path of a batch-sized priority update (PrioritizedSamplingDistribution.update)."""
+        self.flush()
+        if self._stager is None:
+            self._stager = _lib.PinnedStager(1 << 14)
+        p_idx, p_val = self._stager.put_ptrs(idx32, val64)
+        _lib.check(
+            self._lib.isdqn_sumtree_set(self._p_nodes, self._depth, p_idx, p_val, idx32.size, self._p_max, self._p_status,
+                                        _lib.stream_ptr()),
+            "isdqn_sumtree_set",
+        )
+
     _FLUSH_ENTRIES = 1 << 18  # entries per launch (bounds the pinned staging block)
 
     def flush(self) -> None:
@@ -113,11 +118,10 @@ class SumTree:
             op1 = int(np.searchsorted(off, off[op0] + self._FLUSH_ENTRIES, side="right")) - 1
             op1 = min(max(op1, op0 + 1), lens.size)
             e0, e1 = int(off[op0]), int(off[op1])
-            d_idx, d_val, d_off = self._stager.put(idx[e0:e1], val[e0:e1], (off[op0 : op1 + 1] - e0).astype(np.int32))
+            p_idx, p_val, p_off = self._stager.put_ptrs(idx[e0:e1], val[e0:e1], (off[op0 : op1 + 1] - e0).astype(np.int32))
             _lib.check(
                 self._lib.isdqn_sumtree_set_ops(
-                    self._d_nodes.data_ptr(), self._depth, d_off.data_ptr(), op1 - op0, d_idx.data_ptr(), d_val.data_ptr(),
-                    self._d_max.data_ptr(), self._d_status.data_ptr(), _lib.stream_ptr(),
+                    self._p_nodes, self._depth, p_off, op1 - op0, p_idx, p_val, self._p_max, self._p_status, _lib.stream_ptr(),
                 ),
                 "isdqn_sumtree_set_ops",
             )

@@ -23,9 +23,6 @@ def main():
                       frame_capacity=cap + cap // 8 + 64)
     bench.fill_replay(rb, 1000, cap + 1000)
     n_big = 65536
-    for _ in range(2):
-        rb.sample_device(n_big)
-    torch.cuda.synchronize()
     n_keys = 1_000_000
     ps = PrioritizedSamplingDistribution(7, n_keys)
     rng = np.random.default_rng(7)
@@ -34,15 +31,23 @@ def main():
         k1 = min(k0 + 65536, n_keys)
         ps._add_remove_run(k0, k1 - k0, 0, k1 - k0, pv[k0:k1].tolist())
     ps._sum_tree.flush()
+    rb.sample_device(n_big)
+    ps.sample_device(n_big, n_keys + 1)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()  # (ncu --profile-from-start off: the fills above are not captured)
+    for _ in range(2):
+        rb.sample_device(n_big)
     ps._add_remove_run(n_keys, 4096, 0, 0, (np.abs(rng.standard_normal(4096)) + 1e-3).tolist())  # add-then-evict ops
     ps._sum_tree.flush()
     for _ in range(2):
         ps.sample_device(n_big, n_keys + 1)
+    ps._sum_tree.query(rng.random(n_big) * float(ps._sum_tree.root) * 0.999)
     keys = np.arange(5000, 5000 + 32 * 97, 97, dtype=np.int32)
     ps.update(keys, np.abs(rng.standard_normal(32)) + 1e-3)
     ps._sum_tree.flush()
     ps.update_device(torch.from_numpy(keys).cuda(), torch.from_numpy(np.abs(rng.standard_normal(32)) + 1e-3).cuda())
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     ps.check_status()
     print("replay kernels done")
 
