@@ -483,7 +483,9 @@ def run_ours(args, rank, world, local_rank):
         act_ctx = agent._ctx[1]["act"]
         act_fused = isinstance(act_ctx.get("fused"), torch.Tensor)
         acting = {"us_per_action": acting_us, "us_per_action_head_given": acting_head_us,
-                  "path": "single kernel (isdqn_act_host)" if act_fused else "layer chain (CUDA graph)"}
+                  "path": ("single kernel, observation and actions through mapped pinned memory (isdqn_act_mapped)"
+                           if act_fused and "h_flag" in act_ctx else
+                           "single kernel (isdqn_act_host)" if act_fused else "layer chain (CUDA graph)")}
         if act_fused:
             lib_ = _lib.load()
             c1 = agent._ctx[1]

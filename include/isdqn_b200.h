@@ -107,6 +107,12 @@ int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t size, const i
                          int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
                          void* stream);
 
+/* isdqn_sample_uniform with n_valid read from device memory when the kernel runs (graph-capturable while the buffer
+ * fills); size <= 8192. */
+int isdqn_sample_uniform_dev(uint64_t* d_rng, const int32_t* d_n_valid, int32_t size, const int32_t* d_index_to_key,
+                             int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
+                             void* stream);
+
 /* isdqn_sample_uniform for large draws: same results and generator state, spread over the whole GPU (two passes over the
  * draw positions + a finish kernel).  d_workspace: isdqn_sample_uniform_workspace_bytes() of device scratch owned by the
  * caller; draws below 8192 (or a NULL workspace) take the single-CTA kernel. */
@@ -340,6 +346,12 @@ int isdqn_act_mapped(const isdqn_net* net, const float* d_params, const uint8_t*
                      int32_t* h_actions_pinned, int32_t* h_flag_pinned, int32_t seq, void* d_workspace,
                      int64_t workspace_bytes, void* stream, int64_t timeout_us);
 int isdqn_act_wait(const int32_t* h_flag_pinned, int32_t seq, int64_t timeout_us);
+
+/* Host helpers (no device work).  replaces: the head draw of iSDQN.best_action, `jax.random.randint(key, (), 0, K)`
+ * (isdqn.py:129), restated from jax 0.4.30's threefry PRNG so that the same raw JAX key (uint32[2]) picks the same head.
+ * isdqn_threefry2x32: the Threefry-2x32 (20 rounds) block function, out2 = E_key(x0, x1). */
+void isdqn_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out2);
+int32_t isdqn_threefry_randint(uint32_t k0, uint32_t k1, int32_t minval, int32_t maxval);
 
 /* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
  * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */

@@ -148,6 +148,7 @@ PROTOTYPES = {
     "isdqn_profile_end": (C.c_int, [_P, _I32, C.c_char_p, _I32, C.POINTER(C.c_float)]),
     "isdqn_spin": (C.c_int, [_P, _I32]),
     "isdqn_trace_set": (C.c_int, [_P]),
+    "isdqn_sample_uniform_dev": (C.c_int, [_P, _P, _I32, _P, _I32, _P, _P, _P, _P]),
     "isdqn_sample_uniform_workspace_bytes": (C.c_int64, []),
     "isdqn_sample_uniform_ws": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "isdqn_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
@@ -163,6 +164,8 @@ PROTOTYPES = {
     "isdqn_act_host": (C.c_int, [C.POINTER(Net), _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P]),
     "isdqn_act_mapped": (C.c_int, [C.POINTER(Net), _P, _P, _P, _P, _P, _I32, _P, _I64, _P, _I64]),
     "isdqn_act_wait": (C.c_int, [_P, _I32, _I64]),
+    "isdqn_threefry2x32": (None, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
+    "isdqn_threefry_randint": (_I32, [C.c_uint32, C.c_uint32, _I32, _I32]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),

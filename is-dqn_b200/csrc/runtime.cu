@@ -148,6 +148,57 @@ int num_sms() {
 }
 }  // namespace isdqn
 
+// ---------------------------------------------------------------------------------------------- head draw (host)
+// iSDQN.best_action draws its online head with `jax.random.randint(key, (), 0, K)` (slimdqn/networks/isdqn.py:129).  JAX is
+// not in this image; the draw is restated from jax 0.4.30 (jax/_src/prng.py threefry_2x32 / threefry_split /
+// threefry_random_bits with jax_threefry_partitionable = False, jax/_src/random.py _randint), so that the SAME JAX key picks
+// the SAME head.  The block function is pinned by the Random123 known-answer vectors (tests/test_threefry.py); the
+// composition around it is a restatement (unpinned).
+namespace {
+inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  static const int R0[4] = {13, 15, 26, 6}, R1[4] = {17, 29, 16, 24};
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0];
+  x1 += ks[1];
+  for (int g = 0; g < 5; ++g) {
+    const int* R = (g & 1) ? R1 : R0;
+    for (int i = 0; i < 4; ++i) {
+      x0 += x1;
+      x1 = rotl32(x1, R[i]);
+      x1 ^= x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+  }
+}
+}  // namespace
+
+extern "C" void isdqn_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out2) {
+  threefry2x32(k0, k1, x0, x1);
+  out2[0] = x0;
+  out2[1] = x1;
+}
+
+// jax.random.randint(key, (), minval, maxval) for an int32 result and a raw threefry key (k0, k1); maxval > minval.
+extern "C" int32_t isdqn_threefry_randint(uint32_t k0, uint32_t k1, int32_t minval, int32_t maxval) {
+  if (maxval <= minval) return minval;
+  // k1, k2 = split(key): counts [0, 1, 2, 3] -> lanes (0, 2) and (1, 3); outputs concatenated [y0(0), y0(1), y1(0), y1(1)]
+  uint32_t a0 = 0, a1 = 2, b0 = 1, b1 = 3;
+  threefry2x32(k0, k1, a0, a1);
+  threefry2x32(k0, k1, b0, b1);
+  const uint32_t ka[2] = {a0, b0}, kb[2] = {a1, b1};
+  // random_bits(key, 32, ()): one count, padded to the pair (0, 0); the first output word
+  uint32_t h0 = 0, h1 = 0, l0 = 0, l1 = 0;
+  threefry2x32(ka[0], ka[1], h0, h1);
+  threefry2x32(kb[0], kb[1], l0, l1);
+  const uint32_t span = (uint32_t)((int64_t)maxval - (int64_t)minval);
+  uint32_t mult = 65536u % span;  // (2^16 mod span)^2 mod span == 2^32 mod span, in uint32 arithmetic as _randint does
+  mult = (uint32_t)(mult * mult) % span;
+  const uint32_t off = ((h0 % span) * mult + (l0 % span)) % span;
+  return (int32_t)((int64_t)minval + (int64_t)off);
+}
+
 extern "C" int isdqn_abi_version(void) { return ISDQN_ABI_VERSION; }
 
 extern "C" const char* isdqn_strerror(int code) {

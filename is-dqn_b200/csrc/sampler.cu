@@ -14,8 +14,10 @@ template <int kUniformThreads>
 __global__ void __launch_bounds__(kUniformThreads)
 sample_uniform_kernel(uint64_t* rng, uint32_t n_valid, int size, const int32_t* __restrict__ index_to_key,
                       int capacity, int32_t* __restrict__ out_index, int32_t* __restrict__ out_key,
-                      int32_t* __restrict__ out_slot, const int* only_if = nullptr) {
+                      int32_t* __restrict__ out_slot, const int* only_if = nullptr, const int32_t* n_valid_dev = nullptr) {
   if (only_if && !*only_if) return;  // fallback launch of the many-CTA path: normally nothing to do
+  if (n_valid_dev) n_valid = (uint32_t)*n_valid_dev;  // captured in a CUDA graph: the live count is read at replay time
+  if (n_valid == 0u) return;
   __shared__ int warp_tot[32];
   __shared__ int total_sh;
   __shared__ unsigned long long consumed_final;
@@ -237,6 +239,25 @@ extern "C" int isdqn_sample_uniform(uint64_t* d_rng, int32_t n_valid, int32_t si
   else
     sample_uniform_kernel<1024><<<1, 1024, 0, as_stream(stream)>>>(d_rng, (uint32_t)n_valid, size, d_index_to_key, capacity,
                                                                    d_out_index, d_out_key, d_out_slot);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+// isdqn_sample_uniform with the number of live indices read from device memory when the kernel RUNS: the launch can be
+// captured in a CUDA graph together with the gather and the learner step and replayed while the buffer fills.
+extern "C" int isdqn_sample_uniform_dev(uint64_t* d_rng, const int32_t* d_n_valid, int32_t size, const int32_t* d_index_to_key,
+                                        int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
+                                        void* stream) {
+  if (!d_rng || !d_n_valid || size < 0 || (d_index_to_key && capacity < 1)) return ISDQN_E_INVALID;
+  if (size > 8192) return ISDQN_E_TOO_LARGE;
+  if (size == 0) return ISDQN_OK;
+  ISDQN_PROF(as_stream(stream), "sample_uniform");
+  if (size <= 96)
+    sample_uniform_kernel<128><<<1, 128, 0, as_stream(stream)>>>(d_rng, 1u, size, d_index_to_key, capacity, d_out_index, d_out_key,
+                                                                 d_out_slot, nullptr, d_n_valid);
+  else
+    sample_uniform_kernel<1024><<<1, 1024, 0, as_stream(stream)>>>(d_rng, 1u, size, d_index_to_key, capacity, d_out_index,
+                                                                   d_out_key, d_out_slot, nullptr, d_n_valid);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

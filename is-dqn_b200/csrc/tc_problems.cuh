@@ -107,6 +107,31 @@ __device__ __forceinline__ void warp_store_block16(uint32_t* stg, const uint32_t
   }
 }
 
+// The reverse: every lane receives 16 consecutive words of ITS row, read with full-sector instructions (8 rows x 64
+// contiguous bytes each) through the same per-warp staging block.  Rows that are not valid read as zeros.  Warp-collective.
+__device__ __forceinline__ void warp_load_block16(uint32_t* stg, uint32_t (&w)[16], const void* row_ptr, bool valid) {
+  const int lane = threadIdx.x & 31;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const unsigned long long mine = (unsigned long long)(uintptr_t)row_ptr;
+  const int sub = lane >> 2, c4 = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = 8 * it + sub;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, mine, r);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((vmask >> r) & 1u) v = __ldg(reinterpret_cast<const uint4*>((uintptr_t)rp) + c4);
+    *reinterpret_cast<uint4*>(stg + r * kStagePitch + 4 * c4) = v;
+  }
+  __syncwarp();
+  const uint4* mine4 = reinterpret_cast<const uint4*>(stg + lane * kStagePitch);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = mine4[q];
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+}
+
 // fp32 store of the accumulator tile through warp_store_block16 (stg != nullptr) — thread t owns row t
 template <int BN>
 __device__ __forceinline__ void store_rows_f32_coalesced(uint32_t tmem_lane_base, float* __restrict__ dst, bool row_valid, int n0,
@@ -212,28 +237,35 @@ __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& 
   static_assert(BN == 32 || BN == 64, "fused LayerNorm backward: 32 or 64 channels");
   const int lane = etid & 31, warp = etid >> 5;
   const float4* xr = reinterpret_cast<const float4*>(f.xhat + (valid ? m : 0) * BN);
-  const float4* pg = reinterpret_cast<const float4*>(c.prm);
-  const float4* pb = reinterpret_cast<const float4*>(c.prm + BN);
   float dy[BN];
   float xk[KEEP_XH ? BN : 1];
   float sg = 0.f, sgx = 0.f;
+  // the normalised values of this thread's row, 16 at a time through the warp's staging block (full-sector loads: a
+  // thread reading its own 128- or 256-byte row directly touches half a sector per instruction)
+  auto load_xhat16 = [&](int first, float (&x)[16]) {
+    uint32_t w[16];
+    warp_load_block16(stg, w, reinterpret_cast<const float*>(xr) + first, valid);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(w[i]);
+  };
 #pragma unroll
   for (int cb = 0; cb < BN / 32; ++cb) {
     float v[32];
     tmem_ld32(tmem_lane_base + cb * 32, v);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 x4 = valid ? __ldg(xr + cb * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 g4 = pg[cb * 8 + q], b4 = pb[cb * 8 + q];
-      const float xx[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int h = 0; h < 2; ++h) {
+      float xx[16];
+      load_xhat16(cb * 32 + 16 * h, xx);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d = (valid && xx[j] * gg[j] + bb[j] > 0.f) ? v[4 * q + j] : 0.f;
-        dy[cb * 32 + 4 * q + j] = d;
-        if (KEEP_XH) xk[KEEP_XH ? cb * 32 + 4 * q + j : 0] = xx[j];
-        const float g = d * gg[j];
+      for (int i = 0; i < 16; ++i) {
+        const int ch = cb * 32 + 16 * h + i;
+        const float gg = c.prm[ch], bb = c.prm[BN + ch];
+        const float d = (valid && xx[i] * gg + bb > 0.f) ? v[16 * h + i] : 0.f;
+        dy[ch] = d;
+        if (KEEP_XH) xk[KEEP_XH ? ch : 0] = xx[i];
+        const float g = d * gg;
         sg += g;
-        sgx += g * xx[j];
+        sgx += g * xx[i];
       }
     }
   }
@@ -249,9 +281,11 @@ __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& 
       for (int i = 0; i < 32; ++i) xx[i] = xk[KEEP_XH ? cb * 32 + i : 0];
     } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 x4 = valid ? __ldg(xr + cb * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xx[4 * q] = x4.x; xx[4 * q + 1] = x4.y; xx[4 * q + 2] = x4.z; xx[4 * q + 3] = x4.w;
+      for (int h = 0; h < 2; ++h) {
+        float x16[16];
+        load_xhat16(cb * 32 + 16 * h, x16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xx[16 * h + i] = x16[i];
       }
     }
     float a[32];

@@ -19,11 +19,19 @@ from ..sample_collection.replay_buffer import ReplayElement
 from .architectures.dqn import DQNNet, ParamTree
 
 
-def _key_to_seed(key) -> np.random.SeedSequence:
-    """One 32-bit entropy word per byte of the key (what `SeedSequence(list_of_bytes)` builds, without the per-element
-    Python loop of that path: 2x cheaper, same pool — tests/test_key_seed.py)."""
-    b = np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8)
-    return np.random.SeedSequence(b.astype(np.uint32) if b.size else [0])
+def _raw_key(key):
+    """A JAX PRNG key as its two uint32 words.  uint32[2] arrays (what `jax.random.PRNGKey` / `split` produce) are taken
+    as they are; a Python int seed is `jax.random.PRNGKey(seed)` with x64 disabled: (0, seed mod 2^32)."""
+    if isinstance(key, (int, np.integer)):
+        return 0, int(key) & 0xFFFFFFFF
+    k = np.asarray(key)
+    if k.dtype.kind in "iu" and k.size == 2:
+        k = k.reshape(-1)
+        return int(k[0]) & 0xFFFFFFFF, int(k[1]) & 0xFFFFFFFF
+    # anything else (test harnesses hand over arbitrary seeds): fold the bytes into two words
+    b = np.frombuffer(k.tobytes(), dtype=np.uint8)
+    h = np.frombuffer(np.random.SeedSequence(b.astype(np.uint32) if b.size else [0]).generate_state(2).tobytes(), dtype=np.uint32)
+    return int(h[0]), int(h[1])
 
 
 def _new_event(lib):
@@ -359,6 +367,9 @@ class iSDQN:
                 replay_buffer.update_device(d_keys, self.td_abs(B), prio_rows=self.n_bellman_iterations,
                                             offset=self.prioritized_eps)
                 return
+            if (device_rb and self._dp_world == 1 and self._use_graph and os.environ.get("ISDQN_GRAPH_SAMPLE", "1") != "0"
+                    and self._learn_from_replay(replay_buffer)):
+                return
             if self._dp_world > 1:
                 # data parallel: the replay buffer's batch is the GLOBAL batch — the same draw on every rank (replicated
                 # storage, same sampler seed) — and this rank learns from its contiguous slice of it
@@ -412,6 +423,37 @@ class iSDQN:
 
         return False, {}
 
+    def _learn_from_replay(self, replay_buffer) -> bool:
+        """`rb.sample()` + `learn_on_batch` as ONE graph replay: draw -> gather -> step (uniform device replay only).  The
+        host pushes what it has pending (frames, records, key-map patches) before the replay.  False: not applicable."""
+        B = replay_buffer._batch_size
+        ctx = self._context(B)
+        plan = ctx.get("rb_plan")
+        if plan is None or plan[0] is not replay_buffer:
+            made = replay_buffer.capturable_sample(self.batch_buffers(B)) if hasattr(replay_buffer, "capturable_sample") else None
+            if made is None:
+                return False
+            plan = ctx["rb_plan"] = (replay_buffer,) + tuple(made)
+        _, prepare, enqueue, token = plan
+        cur = self._torch.cuda.current_stream()
+        side = None
+        if cur.cuda_stream == 0:  # the legacy default stream cannot be captured
+            if self._side_stream is None:
+                self._side_stream = self._torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+        run = side if side is not None else cur
+        with self._torch.cuda.stream(run):
+            prepare()
+        try:
+            out = self._learn_on_stream(ctx, self.params, self.optimizer_state, B, run.cuda_stream, True, False,
+                                        pre=enqueue, pre_token=token())
+            self._last_step = (out[2], run)
+        finally:
+            if side is not None:
+                cur.wait_stream(side)
+        return True
+
     def learn_on_batch(self, params: ParamTree, optimizer_state: OptState, batch_samples, _accumulate: bool = False,
                        is_weights=None):
         """isdqn.py:82-90.  Returns (params, optimizer_state, losses[K] float32 CUDA tensor); params / optimizer
@@ -441,12 +483,18 @@ class iSDQN:
             if side is not None:
                 cur.wait_stream(side)
 
-    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False, weighted=False):
+    def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False, weighted=False, pre=None,
+                         pre_token=None):
+        """pre(stream): launches enqueued in front of the step (the replay draw + gather), captured with it."""
         key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
-               optimizer_state["count"].data_ptr(), stream, bool(accumulate), bool(weighted))
-        if self._use_graph and ctx["graph"] is not None and ctx["graph_key"] == key:
+               optimizer_state["count"].data_ptr(), stream, bool(accumulate), bool(weighted), pre_token)
+        # a few captured variants are kept side by side (host-batch step, replay-fed step, weighted step): a training loop
+        # that alternates between them must not re-capture at every switch
+        graphs = ctx.setdefault("graphs", {})
+        if self._use_graph and key in graphs:
             if ctx["ws_tc"] is not None and params.shadow_dirty:
                 self._refresh_shadow(params, stream)
+            ctx["graph"], ctx["graph_key"] = graphs[key], key
             _lib.check(self._lib.isdqn_graph_launch(ctx["graph"], stream), "isdqn_graph_launch")
             return params, optimizer_state, ctx["losses"]
         tr = self._train_struct(ctx, params, optimizer_state, B)
@@ -456,21 +504,34 @@ class iSDQN:
         # keeps direct launches)
         if self._use_graph and ctx["warm"] >= 1 and (self._nccl_comm is None or os.environ.get("ISDQN_DP_GRAPH", "1") != "0"):
             # capture this very step (it executes on replay, not during capture)
-            if ctx["graph"] is not None:
-                self._lib.isdqn_graph_destroy(ctx["graph"])
+            if len(graphs) >= 4:  # (stale variants: parameters were re-allocated, another replay buffer, ...)
+                for g in graphs.values():
+                    self._lib.isdqn_graph_destroy(g)
+                graphs.clear()
                 ctx["graph"] = None
             if ctx["ws_tc"] is not None:
                 self._refresh_shadow(params, stream)  # outside the capture
                 tr.refresh_shadow = 0
             _lib.check(self._lib.isdqn_graph_begin(stream), "isdqn_graph_begin")
+            err = None
+            try:
+                if pre is not None:
+                    pre(stream)
+            except _lib.IsdqnNativeError as e:  # (the capture must be closed whatever happened inside it)
+                err = e
             rc = self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream)
             exec_ = _lib.C.c_void_p()
             rc2 = self._lib.isdqn_graph_end(stream, exec_)
+            if err is not None:
+                raise err
             _lib.check(rc, "isdqn_learn_on_batch (capture)")
             _lib.check(rc2, "isdqn_graph_end")
             ctx["graph"], ctx["graph_key"] = exec_, key
+            graphs[key] = exec_
             _lib.check(self._lib.isdqn_graph_launch(ctx["graph"], stream), "isdqn_graph_launch")
         else:
+            if pre is not None:
+                pre(stream)
             _lib.check(self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream), "isdqn_learn_on_batch")
             ctx["warm"] += 1
         return params, optimizer_state, ctx["losses"]
@@ -555,10 +616,11 @@ class iSDQN:
 
     def best_action(self, params: ParamTree, state, key):
         """isdqn.py:127-135: a uniformly drawn online head, then its greedy action.  Returns a 0-d int32 CUDA tensor
-        (`.item()` synchronises, like the reference's `.item()` in collect_single_sample).  The head draw uses
-        NumPy's stream seeded from `key` (JAX's threefry is not reproducible here)."""
-        t = self._torch
-        idx_network = int(np.random.default_rng(_key_to_seed(key)).integers(self.n_bellman_iterations))
+        (`.item()` synchronises, like the reference's `.item()` in collect_single_sample).  The head draw is
+        `jax.random.randint(key, (), 0, K)` restated on the host (isdqn_threefry_randint): the same JAX key picks the
+        same head as in the reference."""
+        k0, k1 = _raw_key(key)
+        idx_network = int(self._lib.isdqn_threefry_randint(k0, k1, 0, self.n_bellman_iterations))
         return self.best_action_of_head(params, state, idx_network)
 
     def _greedy_actions_fast(self, params: ParamTree, obs: np.ndarray):
@@ -667,7 +729,7 @@ class iSDQN:
         net = self.network
         states = np.ascontiguousarray(states)
         N = int(states.shape[0])
-        heads = np.array([int(np.random.default_rng(_key_to_seed(k)).integers(self.n_bellman_iterations)) for k in keys],
+        heads = np.array([int(lib.isdqn_threefry_randint(*_raw_key(k), 0, self.n_bellman_iterations)) for k in keys],
                          dtype=np.int64)
         if heads.shape[0] != N:
             raise ValueError("best_actions needs one key per state")

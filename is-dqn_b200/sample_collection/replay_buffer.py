@@ -489,6 +489,44 @@ class ReplayBuffer:
         d_slots = self._torch.from_numpy(slots).to(self._device)
         return self._to_host(self._gather_slots_device(d_slots))
 
+    def capturable_sample(self, out: ReplayElement, size=None):
+        """For a captured training step: returns (prepare, enqueue, token).  enqueue(stream_ptr) launches draw -> gather
+        into `out` (persistent CUDA tensors, e.g. `agent.batch_buffers(B)`) without allocating anything, so the two
+        launches can live in the same CUDA graph as the learner step; prepare() pushes whatever the host has pending
+        (frames, element records, key-map patches, the live count) and must run before every launch or replay; `token`
+        changes when a device table was re-allocated (a captured graph is then stale).  Uniform sampler only."""
+        from .samplers import UniformSamplingDistribution
+
+        sd = self._sampling_distribution
+        if type(sd) is not UniformSamplingDistribution or not self._allocated:
+            return None
+        if size is None:
+            size = self._batch_size
+        _, _, d_slot, draw = sd.capturable_draw(size, self._slots)
+        state, action, reward, nxt, terminal = out
+        lib, S = self._lib, self._stack_size
+
+        def prepare():
+            self._flush()
+            sd._flush_maps()
+
+        def enqueue(stream_ptr: int) -> None:
+            draw(stream_ptr)
+            _lib.check(
+                lib.isdqn_gather_stacks(
+                    self._d_frames.data_ptr(), self._frame_stride, self._frame_elems, self._elem_size, S,
+                    self._d_elem_frames.data_ptr(), self._d_action.data_ptr(), self._d_reward.data_ptr(),
+                    self._d_terminal.data_ptr(), d_slot.data_ptr(), size, _lib.OUT_RAW, state.data_ptr(), nxt.data_ptr(),
+                    action.data_ptr(), reward.data_ptr(), terminal.data_ptr(), stream_ptr,
+                ),
+                "isdqn_gather_stacks",
+            )
+
+        def token():
+            return (id(self), sd._d_index_to_key.data_ptr(), self._d_frames.data_ptr(), size)
+
+        return prepare, enqueue, token
+
     def sample_device(self, size=None, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None,
                       return_keys: bool = False, beta: Optional[float] = None):
         """Device-resident `sample`: draw -> key -> slot -> gather without leaving the GPU.  For uint8 stack-4

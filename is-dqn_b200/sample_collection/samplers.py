@@ -48,6 +48,9 @@ class UniformSamplingDistribution:
         self._d_index_to_key = torch.zeros(self._initial_table_size(), dtype=torch.int32, device=self._device)
         self._patches: dict = {}
         self._stager = None
+        # number of live dense indices, on the device: a captured sampler launch reads it when it runs
+        self._d_n_valid = torch.zeros(1, dtype=torch.int32, device=self._device)
+        self._n_valid_dev = 0
 
     def _initial_table_size(self) -> int:
         return 1024
@@ -135,6 +138,9 @@ class UniformSamplingDistribution:
         n = len(self._index_to_key)
         t = self._torch
         self._grow_tables(n)
+        if n != self._n_valid_dev:
+            self._d_n_valid.fill_(n)
+            self._n_valid_dev = n
         if not self._patches:
             return
         if len(self._patches) * 4 >= n:  # cheaper to resend the table
@@ -183,6 +189,26 @@ class UniformSamplingDistribution:
         assert self._index_to_key, ValueError("No keys to sample from.")
         self._flush_maps()
         return self._draw_device(size, capacity)
+
+    def capturable_draw(self, size: int, capacity: int):
+        """(d_index, d_key, d_slot, enqueue): persistent output tensors and a function enqueue(stream_ptr) that launches
+        the draw into them with the live count read on the device — it allocates nothing and may be captured in a CUDA
+        graph.  The caller runs `_flush_maps()` before every launch / replay; the table pointer is part of the returned
+        token so that a re-allocated table invalidates a captured graph."""
+        t = self._torch
+        d_index = t.empty(size, dtype=t.int32, device=self._device)
+        d_key = t.empty(size, dtype=t.int32, device=self._device)
+        d_slot = t.empty(size, dtype=t.int32, device=self._device)
+        lib, cap = self._lib, max(int(capacity), 1)
+
+        def enqueue(stream_ptr: int) -> None:
+            _lib.check(
+                lib.isdqn_sample_uniform_dev(self._d_rng.data_ptr(), self._d_n_valid.data_ptr(), size, self._d_index_to_key.data_ptr(),
+                                             cap, d_index.data_ptr(), d_key.data_ptr(), d_slot.data_ptr(), stream_ptr),
+                "isdqn_sample_uniform_dev",
+            )
+
+        return d_index, d_key, d_slot, enqueue
 
     def sample(self, size: int):
         assert self._index_to_key, ValueError("No keys to sample from.")

@@ -9,7 +9,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from isdqn_b200 import _lib  # noqa: E402
-from isdqn_b200.networks.isdqn import iSDQN, _key_to_seed  # noqa: E402
+from isdqn_b200 import _lib  # noqa: E402
+from isdqn_b200.networks.isdqn import iSDQN, _raw_key  # noqa: E402
 
 OBS = (84, 84, 4)
 
@@ -33,7 +34,7 @@ def main():
         out["best_action (key -> head draw -> action)"] = per_call_us(lambda i: agent.best_action(agent.params, obs, i).item())
         out["best_action_of_head"] = per_call_us(lambda i: int(agent.best_action_of_head(agent.params, obs, i % 9)))
         out["head draw alone (default_rng(SeedSequence).integers)"] = per_call_us(
-            lambda i: int(np.random.default_rng(_key_to_seed(i)).integers(9)))
+            lambda i: int(_lib.load().isdqn_threefry_randint(*_raw_key(i), 0, 9)))
         a = agent._ctx[1]["act"]
         out["pinned copy of the observation alone"] = per_call_us(lambda i: a["h_obs_np"].__setitem__(Ellipsis, obs.reshape(-1)))
         lib = _lib.load()

@@ -1,0 +1,48 @@
+"""CPU: the head draw of `best_action` — jax.random.randint restated (isdqn_threefry_randint, host C) against the Python
+restatement in oracle/threefry_oracle.py, and the Threefry-2x32 block function against the Random123 known answers."""
+import ctypes as C
+
+import numpy as np
+
+from isdqn_b200 import _lib
+from oracle import threefry_oracle as T
+
+# Salmon et al. (Random123) known-answer tests for threefry2x32_20; the same three vectors are in jax's own test-suite
+KAT = [
+    ((0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6B200159, 0x99BA4EFE)),
+    ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+    ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0)),
+]
+
+
+def test_threefry2x32_known_answers():
+    lib = _lib.load()
+    for key, ctr, want in KAT:
+        assert T.threefry2x32(*key, *ctr) == want
+        out = (C.c_uint32 * 2)()
+        lib.isdqn_threefry2x32(key[0], key[1], ctr[0], ctr[1], out)
+        assert (out[0], out[1]) == want
+
+
+def test_randint_matches_the_restatement_and_is_uniform():
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    counts = np.zeros(9, dtype=np.int64)
+    for _ in range(3000):
+        k0, k1 = (int(x) for x in rng.integers(0, 2**32, 2, dtype=np.uint64))
+        for span in (1, 2, 9, 49, 1000):
+            got = lib.isdqn_threefry_randint(k0, k1, 0, span)
+            assert got == T.randint((k0, k1), 0, span) and 0 <= got < span
+        counts[lib.isdqn_threefry_randint(k0, k1, 0, 9)] += 1
+    assert counts.min() > 3000 / 9 * 0.75  # every head is drawn
+    assert lib.isdqn_threefry_randint(1, 2, -5, -2) == T.randint((1, 2), -5, -2)
+
+
+def test_raw_key_forms():
+    from isdqn_b200.networks.isdqn import _raw_key
+
+    assert _raw_key(7) == (0, 7)  # jax.random.PRNGKey(7) with x64 disabled
+    assert _raw_key(np.array([3, 4], dtype=np.uint32)) == (3, 4)
+    assert _raw_key(np.array([[3, 4]], dtype=np.uint32)) == (3, 4)
+    a, b = _raw_key("seed"), _raw_key("seed")
+    assert a == b and a != _raw_key("other")
