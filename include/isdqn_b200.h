@@ -308,7 +308,8 @@ int isdqn_dp_destroy(void* comm);
 /* Host-batch staging for the reference-facing call `learn_on_batch(params, opt_state, host batch)` (isdqn.py:82; the
  * reference's implicit device_put at the jit boundary).  Events are created without timing.
  * isdqn_stage_batch: h_src (pinned) -> d_stage on copy_stream [after ev_stage_free], record ev_h2d_done; step_stream waits
- * it, copies d_stage -> d_dst and re-records ev_stage_free.  isdqn_read_async: d_src -> h_dst (pinned) on stream, then
+ * it, copies d_stage -> d_dst and re-records ev_stage_free (d_dst == NULL: no second copy — the step reads d_stage in place
+ * and the caller records ev_stage_free behind it with isdqn_event_record).  isdqn_read_async: d_src -> h_dst (pinned) on stream, then
  * records event.  Nothing synchronises except isdqn_event_synchronize. */
 int isdqn_event_create(void** out_event);
 int isdqn_event_destroy(void* event);

@@ -399,15 +399,19 @@ extern "C" int isdqn_event_synchronize(void* event) {
 //   step_stream waits ev_h2d_done, copies d_stage -> d_dst, re-records ev_stage_free.
 extern "C" int isdqn_stage_batch(const void* h_src, void* d_stage, void* d_dst, int64_t bytes, void* copy_stream,
                                  void* step_stream, void* ev_h2d_done, void* ev_stage_free) {
-  if (!h_src || !d_stage || !d_dst || bytes < 1 || !ev_h2d_done || !ev_stage_free) return ISDQN_E_INVALID;
+  if (!h_src || !d_stage || bytes < 1 || !ev_h2d_done || !ev_stage_free) return ISDQN_E_INVALID;
   cudaStream_t cs = as_stream(copy_stream), ss = as_stream(step_stream);
   cudaEvent_t e_h2d = reinterpret_cast<cudaEvent_t>(ev_h2d_done), e_free = reinterpret_cast<cudaEvent_t>(ev_stage_free);
   ISDQN_CUDA_CHECK(cudaStreamWaitEvent(cs, e_free, 0));
   ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_stage, h_src, (size_t)bytes, cudaMemcpyHostToDevice, cs));
   ISDQN_CUDA_CHECK(cudaEventRecord(e_h2d, cs));
   ISDQN_CUDA_CHECK(cudaStreamWaitEvent(ss, e_h2d, 0));
-  ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_dst, d_stage, (size_t)bytes, cudaMemcpyDeviceToDevice, ss));
-  ISDQN_CUDA_CHECK(cudaEventRecord(e_free, ss));
+  if (d_dst) {
+    ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_dst, d_stage, (size_t)bytes, cudaMemcpyDeviceToDevice, ss));
+    ISDQN_CUDA_CHECK(cudaEventRecord(e_free, ss));
+  }
+  // d_dst == NULL: the step reads d_stage in place; the caller records ev_stage_free (isdqn_event_record) on the step
+  // stream once the work that reads the slot has been enqueued
   return ISDQN_OK;
 }
 

@@ -7,6 +7,8 @@
 //                               compaction, delta = value - old leaf, then for every level the runs of equal
 //                               ancestors are folded sequentially in ascending-leaf order — exactly the order of
 //                               np.add.at — so the float64 heap stays bit-identical to the reference's.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace isdqn {
@@ -288,6 +290,95 @@ __device__ __forceinline__ void sumtree_set_small(double* nodes, int depth, int 
   __syncwarp();  // the next op of this warp reads what other lanes wrote
 }
 
+// One `set` of m <= 32 entries executed by ONE warp with no shared memory and no block barrier (the batch-32 priority
+// update of a training step, PrioritizedSamplingDistribution.update, samplers.py:76-88).  Lane i holds entry i.
+//   sort (leaf, position) ascending with a shuffle bitonic network; the first of equal leaves wins (np.unique(...,
+//   return_index=True)); delta = value - old leaf; then level by level every run of equal ancestors is folded
+//   sequentially in ascending-leaf order by its first lane — np.add.at's order, so the float64 heap stays bit-identical.
+// All node loads of a lane (its ancestor on every level) are issued before the first fold: one round trip, not depth.
+template <bool TAGS>
+__device__ __forceinline__ void sumtree_set_warp(double* nodes, int depth, int m, int leaf_in, double v_in, double* max_prio,
+                                                 uint32_t* status) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n_leaves = 1 << (depth - 1);
+  const int first_leaf = n_leaves - 1;
+  const bool have = lane < m;
+  const double max_old = (TAGS && max_prio) ? *max_prio : 0.0;
+  int bad = 0;
+  double v = have ? resolve_value<TAGS>(v_in, nodes, first_leaf, n_leaves, max_old, &bad) : 0.0;
+  int st = 0;
+  if (have && (bad || leaf_in < 0 || leaf_in >= n_leaves)) st |= ISDQN_ST_INDEX_RANGE;
+  if (have && !(v >= 0.0)) st |= ISDQN_ST_NEGATIVE_VALUE;
+  st = __reduce_or_sync(FULL, (unsigned)st);
+  if (st) {  // sum_tree.py:31 — nothing is modified
+    if (lane == 0 && status) atomicOr(status, (uint32_t)st);
+    return;
+  }
+  {  // sum_tree.py:32
+    double vm = have ? v : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vm = fmax(vm, __shfl_xor_sync(FULL, vm, o));
+    if (lane == 0 && max_prio) *max_prio = fmax(max_old, vm);
+  }
+  // ---- sort by (leaf, position); absent lanes carry the largest key
+  unsigned long long key = have ? (((unsigned long long)(uint32_t)leaf_in) << 32) | (uint32_t)lane : ~0ull;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(FULL, key, j);
+      const double ov = __shfl_xor_sync(FULL, v, j);
+      const bool up = (lane & k) == 0;        // ascending block
+      const bool lower = (lane & j) == 0;     // this lane keeps the smaller key of the pair in an ascending block
+      const bool take_min = up == lower;
+      const bool swap = take_min ? (ok < key) : (ok > key);
+      if (swap) {
+        key = ok;
+        v = ov;
+      }
+    }
+  }
+  const int leaf = (int)(key >> 32);
+  const bool present = key != ~0ull;
+  const int prev_leaf = __shfl_up_sync(FULL, leaf, 1);
+  const bool prev_present = __shfl_up_sync(FULL, (int)present, 1) != 0;
+  const bool active = present && (lane == 0 || !prev_present || prev_leaf != leaf);  // first occurrence of its leaf
+  // ---- this lane's chain of nodes: loads first, then the folds
+  double cur[31];
+#pragma unroll
+  for (int s = 0; s < 31; ++s) cur[s] = (active && s < depth) ? nodes[((first_leaf + leaf + 1) >> s) - 1] : 0.0;
+  const double delta = active ? __dadd_rn(v, -cur[0]) : 0.0;  // against the OLD leaf value (sum_tree.py:34)
+  const unsigned amask = __ballot_sync(FULL, active);
+#pragma unroll 1
+  for (int s = 0; s < depth; ++s) {
+    const int node = active ? ((first_leaf + leaf + 1) >> s) - 1 : -1 - lane;
+    // previous ACTIVE lane's node (ascending leaves => equal ancestors are contiguous among the active lanes)
+    const unsigned below = amask & ((1u << lane) - 1u);
+    const int prev_lane = below ? 31 - __clz(below) : lane;
+    const int prev_node = __shfl_sync(FULL, node, prev_lane);
+    const bool head = active && (!below || prev_node != node);
+    double acc = cur[s < 31 ? s : 30];
+    // every head folds the deltas of the active lanes j >= its own lane that share its node, in lane order
+    for (int j = 0; j < 32; ++j) {
+      const int nj = __shfl_sync(FULL, node, j);
+      const double dj = __shfl_sync(FULL, delta, j);
+      if (head && j >= lane && ((amask >> j) & 1u) && nj == node) acc = __dadd_rn(acc, dj);
+    }
+    if (head) nodes[node] = acc;
+  }
+  __syncwarp();
+}
+
+template <bool TAGS>
+__global__ void __launch_bounds__(32)
+sumtree_set_warp_kernel(double* nodes, int depth, const int32_t* __restrict__ idx, const double* __restrict__ val, int m,
+                        double* max_prio, uint32_t* status, const int32_t* abort_flag) {
+  if (abort_flag && *abort_flag) return;
+  const int lane = threadIdx.x;
+  sumtree_set_warp<TAGS>(nodes, depth, m, lane < m ? idx[lane] : 0, lane < m ? val[lane] : 0.0, max_prio, status);
+}
+
 constexpr int kOpsChunk = 256;       // ops whose descriptors are staged in shared memory at a time
 constexpr int kOpsChunkEntries = 1024;
 
@@ -295,7 +386,7 @@ template <int MAXM, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_offset, int n_ops,
                        const int32_t* __restrict__ idx, const double* __restrict__ val, double* max_prio,
-                       uint32_t* status) {
+                       uint32_t* status, int warp_ops) {
   extern __shared__ __align__(16) unsigned char set_raw[];
   SetSmem sm = carve_set_smem<MAXM, THREADS>(set_raw);
   // Descriptors of the next kOpsChunk ops (offsets, and their entries when they fit) are staged with coalesced loads:
@@ -333,6 +424,15 @@ sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_
           const int i1 = m == 2 ? (staged ? s_idx[b + 1 - e0] : idx[b + 1]) : 0;
           const double v1 = m == 2 ? (staged ? s_val[b + 1 - e0] : val[b + 1]) : 0.0;
           sumtree_set_small(nodes, depth, m, i0, v0, i1, v1, max_prio, status);
+        }
+        small_pending = true;
+        continue;
+      }
+      if (m <= 32 && warp_ops) {  // a batch-sized update inside the queue: still one warp, no block barrier
+        if (warp == 0) {
+          const int lane = threadIdx.x & 31;
+          sumtree_set_warp<true>(nodes, depth, m, lane < m ? (staged ? s_idx[b + lane - e0] : idx[b + lane]) : 0,
+                                 lane < m ? (staged ? s_val[b + lane - e0] : val[b + lane]) : 0.0, max_prio, status);
         }
         small_pending = true;
         continue;
@@ -389,21 +489,37 @@ __global__ void clear_flag_kernel(int32_t* flag) { *flag = 0; }
 
 using namespace isdqn;
 
+static bool warp_set_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_WARP_SET");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 extern "C" int isdqn_sumtree_query(const double* d_nodes, int depth, const double* d_targets, int64_t n,
                                    int32_t* d_out_index, uint32_t* d_status, void* stream) {
   if (!d_nodes || !d_targets || !d_out_index || depth < 1 || depth > 31 || n < 0) return ISDQN_E_INVALID;
   if (n == 0) return ISDQN_OK;
-  const int64_t per_cta = (int64_t)kQueryThreads * kQueryPerThread;
-  int64_t grid = ceil_div<int64_t>(n, per_cta);
+  // A descent is a chain of dependent L2 reads: what counts is the number of descents in flight.  Up to one query per
+  // thread while that still fits the resident threads (the 65,536-query launch ran 31.7 us with 4 per thread on 64 CTAs
+  // against 20.4 us for the fused sampler's one per thread, profiles/r02_replay_ncu.md); 4 per thread beyond.
   const int64_t cap = (int64_t)kNumSMs * 8;
+  const bool one = n <= cap * kQueryThreads;
+  const int64_t per_cta = (int64_t)kQueryThreads * (one ? 1 : kQueryPerThread);
+  int64_t grid = ceil_div<int64_t>(n, per_cta);
   if (grid > cap) grid = cap;
   // staging pays once a CTA serves many queries: each query needs <= 12 of the staged nodes
   int top_levels = 0;
   if (n / grid >= 4096) top_levels = depth - 1 < kQueryMaxTopLevels ? depth - 1 : kQueryMaxTopLevels;
   const size_t smem = top_levels > 0 ? sizeof(double) * ((1u << top_levels) - 1) : 0;
   ISDQN_PROF(as_stream(stream), "sumtree_query");
-  sumtree_query_kernel<kQueryPerThread><<<(unsigned)grid, kQueryThreads, smem, as_stream(stream)>>>(
-      d_nodes, depth, d_targets, n, d_out_index, d_status, top_levels);
+  if (one)
+    sumtree_query_kernel<1><<<(unsigned)grid, kQueryThreads, smem, as_stream(stream)>>>(d_nodes, depth, d_targets, n, d_out_index,
+                                                                                        d_status, top_levels);
+  else
+    sumtree_query_kernel<kQueryPerThread><<<(unsigned)grid, kQueryThreads, smem, as_stream(stream)>>>(
+        d_nodes, depth, d_targets, n, d_out_index, d_status, top_levels);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -414,7 +530,10 @@ extern "C" int isdqn_sumtree_set(double* d_nodes, int depth, const int32_t* d_in
   if (n == 0) return ISDQN_OK;
   if (n > ISDQN_SUMTREE_SET_MAX) return ISDQN_E_TOO_LARGE;
   ISDQN_PROF(as_stream(stream), "sumtree_set");
-  if (n <= 1024) {
+  if (n <= 32 && warp_set_enabled()) {
+    sumtree_set_warp_kernel<false><<<1, 32, 0, as_stream(stream)>>>(d_nodes, depth, d_index, d_value, n, d_max_priority, d_status,
+                                                                   nullptr);
+  } else if (n <= 1024) {
     sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), as_stream(stream)>>>(
         d_nodes, depth, d_index, d_value, n, d_max_priority, d_status);
   } else {
@@ -457,7 +576,10 @@ extern "C" int isdqn_sumtree_set_keys(double* d_nodes, int depth, const int32_t*
                                                              n_slots, d_index_to_key, n_valid, idx, val, flag, d_status);
   ISDQN_LAUNCH_CHECK();
   ISDQN_PROF(s, "sumtree_set");
-  sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), s>>>(d_nodes, depth, idx, val, n, d_max_priority, d_status, flag);
+  if (n <= 32 && warp_set_enabled())
+    sumtree_set_warp_kernel<false><<<1, 32, 0, s>>>(d_nodes, depth, idx, val, n, d_max_priority, d_status, flag);
+  else
+    sumtree_set_kernel<1024, 256><<<1, 256, set_smem_bytes<1024>(), s>>>(d_nodes, depth, idx, val, n, d_max_priority, d_status, flag);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
@@ -470,7 +592,7 @@ extern "C" int isdqn_sumtree_set_ops(double* d_nodes, int depth, const int32_t* 
   if (n_ops == 0) return ISDQN_OK;
   ISDQN_PROF(as_stream(stream), "sumtree_set_ops");
   sumtree_set_ops_kernel<ISDQN_SUMTREE_OP_MAX, 256><<<1, 256, set_smem_bytes<ISDQN_SUMTREE_OP_MAX>(), as_stream(stream)>>>(
-      d_nodes, depth, d_op_offset, n_ops, d_index, d_value, d_max_priority, d_status);
+      d_nodes, depth, d_op_offset, n_ops, d_index, d_value, d_max_priority, d_status, warp_set_enabled() ? 1 : 0);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

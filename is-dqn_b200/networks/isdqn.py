@@ -265,7 +265,7 @@ class iSDQN:
                 params.shadow_dirty = False
         return tr
 
-    def _stage_host_batch(self, ctx, fields, stream) -> None:
+    def _stage_host_batch(self, ctx, fields, stream, in_place_ok: bool = False):
         """Host numpy batch -> (pinned slot ->) device slot on the copy stream -> the batch buffers on the step stream.
         Two slots: the H2D copy of step i+1 runs on the copy engine while step i computes; the CPU only blocks when it
         is two steps ahead of the GPU.  A batch that already lives in a pinned block of the packed layout (what
@@ -303,21 +303,34 @@ class iSDQN:
                 dst = st["host_np"][slot][name]
                 dst[...] = arr.reshape(dst.shape)
             h_src = st["host"][slot].data_ptr()
+        # the H2D copy lands in this slot's device block and the step reads it THERE (one captured graph per slot): no
+        # device-to-device copy into the persistent batch buffers on the step's critical path
+        in_place = in_place_ok and os.environ.get("ISDQN_STAGE_INPLACE", "1") != "0"
         _lib.check(
-            lib.isdqn_stage_batch(h_src, st["dev"][slot].data_ptr(), ctx["dev_pack"].data_ptr(), ctx["pack_bytes"],
-                                  self._copy_stream.cuda_stream, stream.cuda_stream, st["h2d_done"][slot], st["stage_free"][slot]),
+            lib.isdqn_stage_batch(h_src, st["dev"][slot].data_ptr(), None if in_place else ctx["dev_pack"].data_ptr(),
+                                  ctx["pack_bytes"], self._copy_stream.cuda_stream, stream.cuda_stream, st["h2d_done"][slot],
+                                  st["stage_free"][slot]),
             "isdqn_stage_batch",
         )
+        if in_place:
+            if "batch" not in st:
+                st["batch"] = []
+                for d in st["dev"]:
+                    v = ctx["views"](d)
+                    st["batch"].append(_lib.Batch(v["state"].data_ptr(), v["next_state"].data_ptr(), v["action"].data_ptr(),
+                                                  v["reward"].data_ptr(), v["terminal"].data_ptr()))
+            return slot
+        return None
 
-    def _load_batch(self, ctx, batch, stream) -> int:
+    def _load_batch(self, ctx, batch, stream, in_place_ok: bool = False):
         """Copies `batch` (host numpy, like `rb.sample()`; or CUDA tensors) into the persistent device buffers, ordered
-        on `stream` (a torch.cuda.Stream)."""
+        on `stream` (a torch.cuda.Stream).  Returns the staging slot the step has to read instead (host batches with the
+        in-place staging), or None."""
         t = self._torch
         names = ("state", "action", "reward", "next_state", "terminal")
         fields = dict(zip(names, (batch.state, batch.action, batch.reward, batch.next_state, batch.is_terminal)))
         if not any(isinstance(f, t.Tensor) for f in fields.values()):
-            self._stage_host_batch(ctx, fields, stream)
-            return int(ctx["action"].shape[0])
+            return self._stage_host_batch(ctx, fields, stream, in_place_ok)
         with t.cuda.stream(stream):
             for name, f in fields.items():
                 dst = ctx[name]
@@ -327,7 +340,7 @@ class iSDQN:
                     dst.copy_(f.reshape(dst.shape) if f.dtype == dst.dtype else f.reshape(dst.shape).to(dst.dtype), non_blocking=True)
                 else:
                     dst.copy_(t.as_tensor(np.asarray(f)).reshape(dst.shape).to(dst.dtype), non_blocking=False)
-        return int(ctx["action"].shape[0])
+        return None
 
     def losses_to_host_async(self) -> "HostLosses":
         """Enqueues the device->host copy of the latest step's K losses behind that step and returns a handle;
@@ -470,13 +483,17 @@ class iSDQN:
             side = self._side_stream
             side.wait_stream(cur)
         run = side if side is not None else cur
-        self._load_batch(ctx, batch_samples, run)
+        slot = self._load_batch(ctx, batch_samples, run, in_place_ok=True)
         if is_weights is not None:
             with self._torch.cuda.stream(run):
                 w = is_weights if isinstance(is_weights, self._torch.Tensor) else self._torch.as_tensor(np.asarray(is_weights))
                 ctx["is_weights"].copy_(w.reshape(B).to(self._torch.float32), non_blocking=True)
         try:
-            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream, _accumulate, is_weights is not None)
+            out = self._learn_on_stream(ctx, params, optimizer_state, B, run.cuda_stream, _accumulate, is_weights is not None,
+                                        batch_slot=slot)
+            if slot is not None:  # the slot may be overwritten once this step has read it
+                st = ctx["stage"]
+                _lib.check(self._lib.isdqn_event_record(st["stage_free"][slot], run.cuda_stream), "isdqn_event_record")
             self._last_step = (out[2], run)
             return out
         finally:
@@ -484,10 +501,12 @@ class iSDQN:
                 cur.wait_stream(side)
 
     def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False, weighted=False, pre=None,
-                         pre_token=None):
-        """pre(stream): launches enqueued in front of the step (the replay draw + gather), captured with it."""
+                         pre_token=None, batch_slot=None):
+        """pre(stream): launches enqueued in front of the step (the replay draw + gather), captured with it.
+        batch_slot: the step reads its batch from that host-batch staging slot instead of the persistent batch buffers."""
+        batch = ctx["batch"] if batch_slot is None else ctx["stage"]["batch"][batch_slot]
         key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
-               optimizer_state["count"].data_ptr(), stream, bool(accumulate), bool(weighted), pre_token)
+               optimizer_state["count"].data_ptr(), stream, bool(accumulate), bool(weighted), pre_token, batch_slot)
         # a few captured variants are kept side by side (host-batch step, replay-fed step, weighted step): a training loop
         # that alternates between them must not re-capture at every switch
         graphs = ctx.setdefault("graphs", {})
@@ -504,7 +523,7 @@ class iSDQN:
         # keeps direct launches)
         if self._use_graph and ctx["warm"] >= 1 and (self._nccl_comm is None or os.environ.get("ISDQN_DP_GRAPH", "1") != "0"):
             # capture this very step (it executes on replay, not during capture)
-            if len(graphs) >= 4:  # (stale variants: parameters were re-allocated, another replay buffer, ...)
+            if len(graphs) >= 6:  # (stale variants: parameters were re-allocated, another replay buffer, ...)
                 for g in graphs.values():
                     self._lib.isdqn_graph_destroy(g)
                 graphs.clear()
@@ -519,7 +538,7 @@ class iSDQN:
                     pre(stream)
             except _lib.IsdqnNativeError as e:  # (the capture must be closed whatever happened inside it)
                 err = e
-            rc = self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream)
+            rc = self._lib.isdqn_learn_on_batch(self.network._net, tr, batch, stream)
             exec_ = _lib.C.c_void_p()
             rc2 = self._lib.isdqn_graph_end(stream, exec_)
             if err is not None:
@@ -532,7 +551,7 @@ class iSDQN:
         else:
             if pre is not None:
                 pre(stream)
-            _lib.check(self._lib.isdqn_learn_on_batch(self.network._net, tr, ctx["batch"], stream), "isdqn_learn_on_batch")
+            _lib.check(self._lib.isdqn_learn_on_batch(self.network._net, tr, batch, stream), "isdqn_learn_on_batch")
             ctx["warm"] += 1
         return params, optimizer_state, ctx["losses"]
 

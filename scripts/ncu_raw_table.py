@@ -18,6 +18,7 @@ COLS = [
     ("L1 LSU data pipe", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
     ("SM thr", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("L2 hit", "lts__t_sector_hit_rate.pct"),
+    ("L2 sectors", "lts__t_sectors.sum"),
     ("warps active", "sm__warps_active.avg.pct_of_peak_sustained_active"),
     ("issue active", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
 ]
@@ -46,7 +47,7 @@ def main() -> None:
             v = r[idx[key]].replace(",", "")
             try:
                 f = float(v)
-                vals.append(f"{f:.0f}" if f == int(f) and abs(f) >= 10 else f"{f:.2f}")
+                vals.append(f"{f:.0f}" if f == int(f) and abs(f) >= 10 else (f"{f:.2f}" if abs(f) >= 1 or f == 0 else f"{f:.4g}"))
             except ValueError:
                 vals.append(v)
         print(f"| {n} | `{short(r[idx['Kernel Name']])}` | " + " | ".join(vals) + " |")
