@@ -304,7 +304,7 @@ __device__ __forceinline__ void sumtree_set_warp(double* nodes, int depth, int m
   const int n_leaves = 1 << (depth - 1);
   const int first_leaf = n_leaves - 1;
   const bool have = lane < m;
-  const double max_old = (TAGS && max_prio) ? *max_prio : 0.0;
+  const double max_old = max_prio ? *max_prio : 0.0;
   int bad = 0;
   double v = have ? resolve_value<TAGS>(v_in, nodes, first_leaf, n_leaves, max_old, &bad) : 0.0;
   int st = 0;

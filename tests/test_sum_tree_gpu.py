@@ -150,3 +150,36 @@ def test_tagged_swap_remove_matches_get_then_set(sum_tree):
         b.set(np.asarray([hole, last], np.int32), np.asarray([b.get(last), 0.0]))
     assert a._nodes.tobytes() == b._nodes.tobytes()
     assert a.max_recorded_priority == b.max_recorded_priority
+
+
+@pytest.mark.parametrize("path", ["direct", "queued"])
+def test_batch_sized_sets_warp_kernel_bit_exact(sum_tree, path):
+    """Sets of 3..32 entries (the batch-32 priority update) run on one warp: heap, maximum priority and first-duplicate-wins
+    must equal the oracle's, through the direct launch (`_set_now`) and inside a queue of ops, mixed with the one- and
+    two-entry ops of add / evict and with larger sets."""
+    from oracle.sum_tree_oracle import SumTreeOracle
+
+    cap = 5000
+    a, b = sum_tree.SumTree(cap), SumTreeOracle(cap)
+    rng = np.random.default_rng(9)
+    a.set(7, 123.5)  # a large recorded maximum that later, smaller sets must not lower
+    b.set(7, 123.5)
+    for it in range(300):
+        m = int(rng.choice([1, 2, 3, 5, 16, 31, 32, 33, 200]))
+        idx = rng.integers(0, cap, m).astype(np.int32)
+        if m > 2 and rng.random() < 0.6:
+            idx[rng.integers(0, m, max(1, m // 3))] = idx[0]  # duplicates: the first one wins
+        if rng.random() < 0.3:
+            idx = (idx // 64 * 64 + rng.integers(0, 4, m)).astype(np.int32)  # shared ancestors close to the leaves
+        val = np.abs(rng.standard_normal(m)) * float(rng.choice([1e-3, 1.0, 50.0]))
+        val[rng.random(m) < 0.1] = 0.0
+        if path == "direct" and 2 < m <= 32:
+            a._set_now(idx, val)
+        else:
+            a.set(idx, val)
+        b.set(idx, val)
+        if it % 25 == 0:
+            assert a._nodes.tobytes() == b._nodes.tobytes(), f"heap differs after op {it} (m = {m})"
+            assert a.max_recorded_priority == b.max_recorded_priority
+    assert a._nodes.tobytes() == b._nodes.tobytes()
+    assert a.max_recorded_priority == b.max_recorded_priority == 123.5
