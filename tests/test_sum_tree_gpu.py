@@ -162,8 +162,8 @@ def test_batch_sized_sets_warp_kernel_bit_exact(sum_tree, path):
     cap = 5000
     a, b = sum_tree.SumTree(cap), SumTreeOracle(cap)
     rng = np.random.default_rng(9)
-    a.set(7, 123.5)  # a large recorded maximum that later, smaller sets must not lower
-    b.set(7, 123.5)
+    a.set(7, 12345.5)  # a large recorded maximum that later, smaller sets must not lower
+    b.set(7, 12345.5)
     for it in range(300):
         m = int(rng.choice([1, 2, 3, 5, 16, 31, 32, 33, 200]))
         idx = rng.integers(0, cap, m).astype(np.int32)
@@ -182,4 +182,4 @@ def test_batch_sized_sets_warp_kernel_bit_exact(sum_tree, path):
             assert a._nodes.tobytes() == b._nodes.tobytes(), f"heap differs after op {it} (m = {m})"
             assert a.max_recorded_priority == b.max_recorded_priority
     assert a._nodes.tobytes() == b._nodes.tobytes()
-    assert a.max_recorded_priority == b.max_recorded_priority == 123.5
+    assert a.max_recorded_priority == b.max_recorded_priority == 12345.5
