@@ -80,13 +80,18 @@ def fill_replay(rb, seed: int, n: int, priorities=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs ~100 ms to
+    deliver its first sample and the timed region of a short run is a few milliseconds, so the sampler is started BEFORE
+    the warm-up, every sample is stamped on arrival, and `summary()` keeps the samples that fall between `begin()` and
+    `end()`.  A region that still caught none is followed by a probe: the caller re-runs the same steps untimed for
+    ~0.3 s between `begin(probe=True)` / `end()`, and the record says so."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.windows, self.probe = [], False
 
     def __enter__(self):
         try:
@@ -100,17 +105,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def begin(self, probe: bool = False):
+        self._t0 = time.perf_counter()
+        self.probe = self.probe or probe
+
+    def end(self):
+        self.windows.append((self._t0, time.perf_counter() + 0.03))  # (a sample is stamped when it arrives: one period late)
+
+    def in_window(self) -> int:
+        return sum(1 for t, _ in self.rows if any(a <= t <= b for a, b in self.windows))
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
 
     def summary(self):
         sm, smax, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.windows and not any(a <= t <= b for a, b in self.windows):
+                continue
             try:
                 sm.append(float(r[0]))
                 smax = max(smax, float(r[1]))
@@ -119,8 +136,12 @@ class ClockSampler:
                         reasons.add(name)
             except (ValueError, IndexError):
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if self.probe:
+            out["note"] = ("the timed region was shorter than nvidia-smi's sampling period: sampled while the same steps were "
+                           "re-run untimed right after it")
+        return out
 
 
 def measured_peaks():
@@ -305,6 +326,7 @@ def measure_agent(agent, rb, steps, warmup, barrier, stream, local_rank):
         step_no[0] += 1
         agent.update_online_params(step_no[0], rb)
 
+    clk = ClockSampler(local_rank).__enter__()  # (started before the warm-up: see ClockSampler)
     for _ in range(warmup):
         step()
     pool = [rb.sample() for _ in range(8)]
@@ -327,16 +349,26 @@ def measure_agent(agent, rb, steps, warmup, barrier, stream, local_rank):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:  # spans both timed regions (one alone is shorter than nvidia-smi's sampling period)
-        ev0.record()
-        for _ in range(steps):
-            step()
-        ev1.record()
-        barrier()
-        e0.record()
-        losses_host = e2e_loop(steps)
-        e1.record()
-        barrier()
+    clk.begin()  # one window over both timed regions
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    e0.record()
+    losses_host = e2e_loop(steps)
+    e1.record()
+    barrier()
+    clk.end()
+    if clk.in_window() == 0:  # too short for a sample: the same steps again, untimed, while nvidia-smi samples
+        clk.begin(probe=True)
+        t_probe = time.perf_counter()
+        while time.perf_counter() - t_probe < 0.3:
+            for _ in range(50):
+                step()
+            torch.cuda.synchronize()
+        clk.end()
+    clk.__exit__()
     return ev0.elapsed_time(ev1), e0.elapsed_time(e1), int(h2d), int(losses_host.size * 4), clk.summary()
 
 
@@ -680,17 +712,32 @@ def dp_measure(args, rank, world, local_rank, Bg, width, steps, warmup, dist=Non
             batch = rb._gather_slots_device(d_slot[lo:hi].contiguous(), out=bufs)
             agent.learn_on_batch(agent.params, agent.optimizer_state, batch)
 
+        clk = ClockSampler(local_rank).__enter__()
         for _ in range(warmup):
             step()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            ev0.record()
-            for _ in range(steps):
-                step()
-            ev1.record()
-            barrier()
+        clk.begin()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        barrier()
+        clk.end()
         ms = ev0.elapsed_time(ev1)
+        # (the step contains a collective: whether to probe, and for how many steps, is decided by ALL ranks together)
+        n_probe = max(1, int(0.3 / max(ms / steps / 1e3, 1e-6))) if clk.in_window() == 0 else 0
+        if world > 1:
+            t_n = torch.tensor([n_probe], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t_n, op=dist.ReduceOp.MAX)
+            n_probe = int(t_n.item())
+        if n_probe > 0:
+            clk.begin(probe=True)
+            for _ in range(n_probe):
+                step()
+            torch.cuda.synchronize()
+            clk.end()
+        clk.__exit__()
         use_graph = agent._use_graph
         agent._use_graph = False
         prof = _lib.profile(step)

@@ -89,6 +89,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
                "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// TMA store: shared-memory tile -> global through a tensor map (rows outside the tensor are clipped); bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory SOURCE of every committed bulk store may be overwritten
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every committed bulk store has completed (its writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -105,6 +117,13 @@ template <class P, class = void>
 struct uses_ep_finish : std::false_type {};
 template <class P>
 struct uses_ep_finish<P, std::void_t<decltype(P::EP_FINISH)>> : std::bool_constant<P::EP_FINISH> {};
+
+// problems whose epilogue stores through TMA out of a shared-memory tile declare `EP_TILE_BYTES` (> 0): that many bytes of
+// 1024-byte aligned dynamic shared memory behind the stage ring, handed to the problem with set_ep_tile()
+template <class P, class = void>
+struct ep_tile_bytes : std::integral_constant<int, 0> {};
+template <class P>
+struct ep_tile_bytes<P, std::void_t<decltype(P::EP_TILE_BYTES)>> : std::integral_constant<int, P::EP_TILE_BYTES> {};
 
 template <class P, class = void>
 struct uses_tma : std::false_type {};
@@ -208,6 +227,10 @@ __device__ __forceinline__ uint32_t mnmajor_off(int krow, int chunk) {
 template <int BN, int STAGES>
 constexpr size_t smem_bytes() {
   return (size_t)STAGES * (kABytes + (size_t)BN * kBK * 2) + 1024;  // + alignment slack
+}
+template <class P>
+constexpr size_t smem_bytes_of() {
+  return smem_bytes<P::BN, P::STAGES>() + (size_t)ep_tile_bytes<P>::value;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -402,6 +425,7 @@ __device__ __forceinline__ void tc_gemm_body(const P& p, int tiles_x, int tiles_
     // -------------------------------------------------------------------------------------------- epilogue
     typename P::ECtx ectx;
     int ti = 0;
+    if constexpr (ep_tile_bytes<P>::value > 0) p.set_ep_tile(ectx, sB + STAGES * B_BYTES);
     pdl_wait_then_trigger();
     if (P::EP_FLOATS > 0) {  // per-channel epilogue parameters -> shared memory, once per CTA, while the first tile is gathered
       p.init_epilogue(ectx, ep_sm, tid);

@@ -121,7 +121,7 @@ inline float* wsp(void* ws, int64_t off) { return off < 0 ? nullptr : reinterpre
 template <class P>
 int launch_tc(const P& p, int tiles_x, int tiles_y, int tiles_z, cudaStream_t s, const char* tag, int max_ctas = 0,
               int* grid_out = nullptr) {
-  constexpr size_t smem = tc::smem_bytes<P::BN, P::STAGES>();
+  constexpr size_t smem = tc::smem_bytes_of<P>();
   constexpr int threads = 32 * (tc::kFirstProducerWarp + P::PRODUCER_WARPS);
   static PerDevice<int> ctas_per_sm_dev;  // (the opt-in attributes below are per device context)
   int& ctas_per_sm = ctas_per_sm_dev.get();
@@ -446,9 +446,40 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
                : encode_matrix_map(&tm_w, w, L.out_dim, L.in_dim, L.out_dim, 64, 64))
     return ISDQN_E_CUDA;
   const int n_tiles = n_img * tpi;
-#define ISDQN_CONV_FWD_TMA_W(BN, WIDE, KB)                                                             \
+  // TMA-store epilogue (<= 64 output channels): tensor maps of the two outputs
+  static const bool ts_on = [] {
+    const char* e = getenv("ISDQN_TMA_STORE");
+    return !(e && e[0] == '0');
+  }();
+  const bool ts = ts_on && L.out_dim <= 64 && L.OW <= 256 && th <= 256;
+  CUtensorMap tm_out = tm_x, tm_xhat = tm_x;
+  const int n_train_img = (xhat != nullptr && L.has_ln) ? m_train / L.pix : 0;
+  if (ts) {
+    const int C = L.out_dim, OWp = out_pitch ? out_pitch : L.OW;
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)OWp, (cuuint64_t)L.OH, (cuuint64_t)n_img};
+      const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)OWp * C * 2, (cuuint64_t)L.OH * OWp * C * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)L.OW, (cuuint32_t)th, 1};
+      const cuuint32_t es[4] = {1, 1, 1, 1};
+      if (enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return ISDQN_E_CUDA;
+    }
+    if (n_train_img > 0) {
+      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L.OW, (cuuint64_t)L.OH, (cuuint64_t)n_train_img};
+      const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)L.OW * C * 4, (cuuint64_t)L.OH * L.OW * C * 4};
+      const cuuint32_t box[4] = {32, (cuuint32_t)L.OW, (cuuint32_t)th, 1};
+      const cuuint32_t es[4] = {1, 1, 1, 1};
+      if (enc(&tm_xhat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xhat, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return ISDQN_E_CUDA;
+    }
+  }
+#define ISDQN_CONV_FWD_TMA_W(BN, WIDE, KB, TS)                                                         \
   {                                                                                                    \
-    tc::ConvFwdTmaTC<BN, WIDE, KB> p;                                                                  \
+    tc::ConvFwdTmaTC<BN, WIDE, KB, TS> p;                                                              \
+    p.tm_out = tm_out; p.tm_xhat = tm_xhat; p.n_train_img = n_train_img;                               \
     p.tm_x = tm_x; p.tm_w = tm_w; p.n_img = n_img; p.pix = L.pix; p.OW = L.OW; p.OH = L.OH;            \
     p.th = th; p.tpi = tpi; p.ksz_y = L.ksz; p.ksz_x = ksz_x; p.sy = sy; p.out_pitch = out_pitch;      \
     p.pad_y = L.pad_y; p.pad_x = L.pad_x; p.cchunks = L.Cin / 64;                                      \
@@ -459,13 +490,13 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
     p.acc_scale = in_scale;                                                                            \
     return launch_tc(p, n_tiles, 1, 1, s, "tc_conv_fwd_tma");                                          \
   }
-#define ISDQN_CONV_FWD_TMA(BN, KB)                                                                     \
-  if (wide_launch(n_tiles)) ISDQN_CONV_FWD_TMA_W(BN, true, KB) else ISDQN_CONV_FWD_TMA_W(BN, false, KB)
+#define ISDQN_CONV_FWD_TMA(BN, KB, TS)                                                                 \
+  if (wide_launch(n_tiles)) ISDQN_CONV_FWD_TMA_W(BN, true, KB, TS) else ISDQN_CONV_FWD_TMA_W(BN, false, KB, TS)
   switch (L.out_dim) {
-    case 32: ISDQN_CONV_FWD_TMA(32, true)
-    case 64: ISDQN_CONV_FWD_TMA(64, false)
-    case 128: ISDQN_CONV_FWD_TMA(128, false)
-    case 256: ISDQN_CONV_FWD_TMA(256, false)
+    case 32: if (ts) ISDQN_CONV_FWD_TMA(32, true, true) else ISDQN_CONV_FWD_TMA(32, true, false)
+    case 64: if (ts) ISDQN_CONV_FWD_TMA(64, false, true) else ISDQN_CONV_FWD_TMA(64, false, false)
+    case 128: ISDQN_CONV_FWD_TMA(128, false, false)
+    case 256: ISDQN_CONV_FWD_TMA(256, false, false)
     default: return ISDQN_E_UNSUPPORTED;
   }
 #undef ISDQN_CONV_FWD_TMA_W
@@ -619,7 +650,7 @@ int launch_conv_dgrad_tma(const Layer& L, const bf16* dz, const bf16* w, float* 
 template <class P1, class P2>
 int launch_tc2(const P1& p1, int t1x, int t1y, int t1z, int ctas1, const P2& p2, int t2x, int t2y, int t2z, int ctas2,
                cudaStream_t s, const char* tag) {
-  constexpr size_t sm1 = tc::smem_bytes<P1::BN, P1::STAGES>(), sm2 = tc::smem_bytes<P2::BN, P2::STAGES>();
+  constexpr size_t sm1 = tc::smem_bytes_of<P1>(), sm2 = tc::smem_bytes_of<P2>();
   constexpr size_t smem = sm1 > sm2 ? sm1 : sm2;
   constexpr int pw = P1::PRODUCER_WARPS > P2::PRODUCER_WARPS ? P1::PRODUCER_WARPS : P2::PRODUCER_WARPS;
   constexpr int threads = 32 * (tc::kFirstProducerWarp + pw);

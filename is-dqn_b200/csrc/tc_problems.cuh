@@ -620,6 +620,80 @@ __device__ __forceinline__ void conv_fwd_epilogue_row(const ConvEpilogueArgs& e,
     if (save) e.rstd[m] = rs;
   }
 
+// The same row epilogue for the TMA-store shape: the bf16 activation row and the fp32 normalised row go into shared-memory
+// tiles (128-byte-swizzled rows, or dense 64-byte rows for 32 bf16 channels) that ONE thread then hands to the copy engine
+// (ConvFwdTmaTC::epilogue) — one st.shared per 16 bytes instead of st.shared + ld.shared + st.global through the LSU.
+//   tile_act : [128 rows][BN bf16]                      tile_xhat: BN / 32 sub-tiles of [128 rows][32 fp32]
+template <int BN>
+__device__ __forceinline__ void conv_fwd_epilogue_row_ts(const ConvEpilogueArgs& e, uint32_t tmem_lane_base, int row, int64_t m,
+                                                         bool valid, bool save, uint32_t tile_act, uint32_t tile_xhat) {
+  static_assert(BN == 32 || BN == 64, "TMA-store epilogue: 32 or 64 output channels");
+  const float4* pb = reinterpret_cast<const float4*>(e.prm);
+  const float4* pg = reinterpret_cast<const float4*>(e.prm + BN);
+  const float4* pbeta = reinterpret_cast<const float4*>(e.prm + 2 * BN);
+  float mean = 0.f, rs = 1.f;
+  if (e.ln_g) {  // flax LayerNorm: var = max(0, E[x^2] - E[x]^2), eps = 1e-6
+    float s = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      float v[32];
+      tmem_ld32(tmem_lane_base + cb * 32, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = pb[cb * 8 + q];
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float z = fmaf(v[4 * q + j], e.acc_scale, bb[j]);
+          s += z;
+          s2 += z * z;
+        }
+      }
+    }
+    mean = s / (float)BN;
+    rs = rsqrtf(fmaxf(s2 / (float)BN - mean * mean, 0.f) + 1e-6f);
+  }
+  const int sw = row & 7;
+#pragma unroll 1
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    float v[32];
+    tmem_ld32(tmem_lane_base + cb * 32, v);
+    uint32_t packed[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = pb[cb * 8 + q], g4 = pg[cb * 8 + q], e4 = pbeta[cb * 8 + q];
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float z = fmaf(v[4 * q + j], e.acc_scale, bb[j]);
+        if (e.ln_g) {
+          z = (z - mean) * rs;
+          v[4 * q + j] = z;  // normalised value, saved for the backward pass
+          z = z * gg[j] + ee[j];
+        }
+        y[j] = e.relu ? fmaxf(z, 0.f) : z;
+      }
+      packed[2 * q] = pack_bf16(y[0], y[1]);
+      packed[2 * q + 1] = pack_bf16(y[2], y[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 32 bf16 = four 16-byte chunks of the activation row
+      const uint32_t a = BN == 64 ? tile_act + row * 128 + (((cb * 4 + q) ^ sw) << 4) : tile_act + row * 64 + (q << 4);
+      st_shared_v4(a, packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    }
+    if (save) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {  // 32 fp32 = eight 16-byte chunks of one 128-byte-swizzled sub-tile row
+        const uint32_t a = tile_xhat + cb * (kBM * 128) + row * 128 + ((q ^ sw) << 4);
+        st_shared_v4(a, __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                     __float_as_uint(v[4 * q + 3]));
+      }
+    }
+  }
+  if (save && valid) e.rstd[m] = rs;
+}
+
 // ------------------------------------------------------------------------------------------------ conv forward
 // out[m][co] = ReLU(LN(sum_k im2col(x)[m][k] W[k][co] + bias)); A gathered K-major, B = W (HWIO = [K][Cout]) MN-major.
 // IN_U8 requires Cin == 4 (the stacked Atari frames); bf16 input requires Cin % 8 == 0.
@@ -729,10 +803,17 @@ struct ConvFwdTC {
 // chunk is BN/64 2-D copies in the MN-major swizzled layout, or (B_KMAJOR_, for BN = 32: narrower than a swizzle atom
 // the other way round) one copy of a TRANSPOSED weight matrix [Cout][K] in the K-major layout.  Nothing goes through the
 // LSU.
-template <int BN_, bool WIDE_ = false, bool B_KMAJOR_ = false>
+// TS_ (BN <= 64): the epilogue stores the activation and the normalised values with TMA out of shared-memory tiles
+// (`UTMASTG`): the LSU only sees one st.shared per 16 bytes.  The tiles cost 48 KB (24 KB at 32 channels) of shared memory,
+// so the ring has 6 stages in the single-wave shape and the throughput shape runs one CTA per SM (its two TMEM
+// accumulators still overlap the epilogue of tile i with the main loop of tile i + 1).
+template <int BN_, bool WIDE_ = false, bool B_KMAJOR_ = false, bool TS_ = false>
 struct ConvFwdTmaTC {
-  static constexpr int BN = BN_, STAGES = (WIDE_ && BN_ <= 64) ? 8 : 4, PRODUCER_WARPS = 1;
-  static constexpr int MIN_CTAS = WIDE_ ? 1 : (BN_ <= 64 ? 2 : 1);
+  static constexpr bool TS = TS_ && BN_ <= 64;
+  static constexpr int BN = BN_, STAGES = TS ? (WIDE_ ? 6 : 4) : ((WIDE_ && BN_ <= 64) ? 8 : 4), PRODUCER_WARPS = 1;
+  static constexpr int MIN_CTAS = (WIDE_ || TS) ? 1 : (BN_ <= 64 ? 2 : 1);
+  static constexpr int EP_TILE_BYTES = TS ? kBM * BN_ * 2 + kBM * BN_ * 4 : 0;  // bf16 activation tile + fp32 normalised tile
+  static constexpr bool EP_FINISH = true;
   static constexpr int EXTRA_BYTES = 0, EP_FLOATS = 3 * BN_;
   static constexpr bool A_MN = false, B_MN = !B_KMAJOR_, CHUNK_SYNC = false, SYNC_STORES = false, B_SW = true, TMA = true, EP_STAGE = true;
   static_assert(B_KMAJOR_ || BN_ % 64 == 0, "the MN-major weight stage is filled in 64-column swizzle groups");
@@ -744,16 +825,26 @@ struct ConvFwdTmaTC {
   const float* bias; const float* ln_g; const float* ln_b; int relu;
   bf16* out; float* xhat; float* rstd; int m_train;
   float acc_scale;
+  // TS: output tensor maps — activation [N][OH][OW or out_pitch][C] bf16, box {C, OW, th, 1} (128-byte swizzle at 64
+  // channels, none at 32); normalised values [n_train images][OH][OW][C] fp32, box {32, OW, th, 1}, 128-byte swizzle
+  CUtensorMap tm_out, tm_xhat;
+  int n_train_img;
   struct PCtx {
     int img, y0;         // tile
     int ky, kx, cc;      // running tap / channel-chunk counters (chunks are visited in order)
   };
   struct ECtx {
     const float* prm;
+    uint32_t tile;       // TS: shared-memory address of the epilogue tiles
   };
+  __device__ void set_ep_tile(ECtx& e, uint32_t addr) const { e.tile = addr; }
   __device__ void tma_prefetch() const {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
+    if constexpr (TS) {
+      tma_prefetch_desc(&tm_out);
+      tma_prefetch_desc(&tm_xhat);
+    }
   }
   __device__ void tma_tile(PCtx& c, int tile, int, int) const {
     c.img = tile / tpi;
@@ -796,7 +887,36 @@ struct ConvFwdTmaTC {
     e.acc_scale = acc_scale;
     const int64_t m = (int64_t)img * pix + oy * OW + ox;
     const int64_t m_out = out_pitch ? ((int64_t)img * OH + oy) * out_pitch + ox + 1 : m;
-    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, r < th && oy < OH && img < n_img, m_out, out_pitch != 0 && ox == 0, stg);
+    const bool valid = r < th && oy < OH && img < n_img;
+    if constexpr (TS) {
+      const bool train_tile = xhat != nullptr && ln_g != nullptr && img < n_train_img;  // (uniform: a tile is one image)
+      const uint32_t tile_act = ec.tile, tile_xhat = ec.tile + kBM * BN * 2;
+      if (etid == 0) bulk_wait_read_all();      // the previous tile's stores have read the tiles
+      named_bar_sync(2, 32 * kEpilogueWarps);
+      conv_fwd_epilogue_row_ts<BN>(e, tmem_lane_base, etid, m, valid, train_tile, tile_act, tile_xhat);
+      fence_proxy_async();                      // st.shared (generic proxy) -> the copy engine's reads (async proxy)
+      named_bar_sync(2, 32 * kEpilogueWarps);
+      if (etid == 0 && img < n_img) {
+        tma_store_4d(&tm_out, tile_act, 0, out_pitch ? 1 : 0, y0, img);
+        if (train_tile) {
+#pragma unroll
+          for (int cb = 0; cb < BN / 32; ++cb) tma_store_4d(&tm_xhat, tile_xhat + cb * (kBM * 128), cb * 32, 0, y0, img);
+        }
+        bulk_commit_group();
+      }
+      if (valid && out_pitch != 0 && ox == 0) {  // the zero column on the left of the padded layout
+        uint4* o = reinterpret_cast<uint4*>(out + (m_out - 1) * BN);
+#pragma unroll
+        for (int q = 0; q < BN / 8; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      return;
+    }
+    conv_fwd_epilogue_row<BN>(e, tmem_lane_base, m, valid, m_out, out_pitch != 0 && ox == 0, stg);
+  }
+  __device__ void finish_epilogue(const ECtx&, int, int etid) const {
+    if constexpr (TS) {
+      if (etid == 0) bulk_wait_all();  // the stores have been performed before the CTA (and with it the grid) completes
+    }
   }
 };
 
