@@ -115,7 +115,7 @@ int isdqn_sample_uniform_dev(uint64_t* d_rng, const int32_t* d_n_valid, int32_t 
 
 /* isdqn_sample_uniform for large draws: same results and generator state, spread over the whole GPU (two passes over the
  * draw positions + a finish kernel).  d_workspace: isdqn_sample_uniform_workspace_bytes() of device scratch owned by the
- * caller; draws below 8192 (or a NULL workspace) take the single-CTA kernel. */
+ * caller; draws below 2048 (or a NULL workspace) take the single-CTA kernel. */
 int64_t isdqn_sample_uniform_workspace_bytes(void);
 int isdqn_sample_uniform_ws(uint64_t* d_rng, int32_t n_valid, int32_t size, const int32_t* d_index_to_key,
                             int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,

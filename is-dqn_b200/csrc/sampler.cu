@@ -267,7 +267,7 @@ extern "C" int64_t isdqn_sample_uniform_workspace_bytes(void) { return (int64_t)
 extern "C" int isdqn_sample_uniform_ws(uint64_t* d_rng, int32_t n_valid, int32_t size, const int32_t* d_index_to_key,
                                        int32_t capacity, int32_t* d_out_index, int32_t* d_out_key, int32_t* d_out_slot,
                                        void* d_workspace, int64_t workspace_bytes, void* stream) {
-  if (size < 8192 || n_valid == 1 || !d_workspace || workspace_bytes < (int64_t)sizeof(UniformWs))
+  if (size < 2048 || n_valid == 1 || !d_workspace || workspace_bytes < (int64_t)sizeof(UniformWs))
     return isdqn_sample_uniform(d_rng, n_valid, size, d_index_to_key, capacity, d_out_index, d_out_key, d_out_slot, stream);
   if (!d_rng || n_valid < 1 || (d_index_to_key && capacity < 1)) return ISDQN_E_INVALID;
   if (size > (1 << 20)) return ISDQN_E_TOO_LARGE;

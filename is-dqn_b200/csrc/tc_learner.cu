@@ -451,7 +451,10 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
     const char* e = getenv("ISDQN_TMA_STORE");
     return !(e && e[0] == '0');
   }();
-  const bool ts = ts_on && L.out_dim <= 64 && L.OW <= 256 && th <= 256;
+  // single-wave launches only: measured at batch 4096 the one-CTA-per-SM TMA-store shape loses to two staged-store CTAs per
+  // SM (torso forward 0.66 vs 0.58 ms: with one CTA the four epilogue warps are latency bound), at batch 32 it is neutral
+  // to slightly faster (129.7 vs 130.7 us per update)
+  const bool ts = ts_on && wide_launch(n_tiles) && L.out_dim <= 64 && L.OW <= 256 && th <= 256;
   CUtensorMap tm_out = tm_x, tm_xhat = tm_x;
   const int n_train_img = (xhat != nullptr && L.has_ln) ? m_train / L.pix : 0;
   if (ts) {
@@ -490,13 +493,15 @@ int launch_conv_fwd_tma(const Layer& L, const bf16* x, int n_img, const bf16* w,
     p.acc_scale = in_scale;                                                                            \
     return launch_tc(p, n_tiles, 1, 1, s, "tc_conv_fwd_tma");                                          \
   }
-#define ISDQN_CONV_FWD_TMA(BN, KB, TS)                                                                 \
-  if (wide_launch(n_tiles)) ISDQN_CONV_FWD_TMA_W(BN, true, KB, TS) else ISDQN_CONV_FWD_TMA_W(BN, false, KB, TS)
+#define ISDQN_CONV_FWD_TMA(BN, KB)                                                                     \
+  if (ts) ISDQN_CONV_FWD_TMA_W(BN, true, KB, true)                                                     \
+  else if (wide_launch(n_tiles)) ISDQN_CONV_FWD_TMA_W(BN, true, KB, false)                             \
+  else ISDQN_CONV_FWD_TMA_W(BN, false, KB, false)
   switch (L.out_dim) {
-    case 32: if (ts) ISDQN_CONV_FWD_TMA(32, true, true) else ISDQN_CONV_FWD_TMA(32, true, false)
-    case 64: if (ts) ISDQN_CONV_FWD_TMA(64, false, true) else ISDQN_CONV_FWD_TMA(64, false, false)
-    case 128: ISDQN_CONV_FWD_TMA(128, false, false)
-    case 256: ISDQN_CONV_FWD_TMA(256, false, false)
+    case 32: ISDQN_CONV_FWD_TMA(32, true)
+    case 64: ISDQN_CONV_FWD_TMA(64, false)
+    case 128: ISDQN_CONV_FWD_TMA(128, false)
+    case 256: ISDQN_CONV_FWD_TMA(256, false)
     default: return ISDQN_E_UNSUPPORTED;
   }
 #undef ISDQN_CONV_FWD_TMA_W

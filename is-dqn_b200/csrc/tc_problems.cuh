@@ -107,31 +107,6 @@ __device__ __forceinline__ void warp_store_block16(uint32_t* stg, const uint32_t
   }
 }
 
-// The reverse: every lane receives 16 consecutive words of ITS row, read with full-sector instructions (8 rows x 64
-// contiguous bytes each) through the same per-warp staging block.  Rows that are not valid read as zeros.  Warp-collective.
-__device__ __forceinline__ void warp_load_block16(uint32_t* stg, uint32_t (&w)[16], const void* row_ptr, bool valid) {
-  const int lane = threadIdx.x & 31;
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  const unsigned long long mine = (unsigned long long)(uintptr_t)row_ptr;
-  const int sub = lane >> 2, c4 = lane & 3;
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = 8 * it + sub;
-    const unsigned long long rp = __shfl_sync(0xffffffffu, mine, r);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if ((vmask >> r) & 1u) v = __ldg(reinterpret_cast<const uint4*>((uintptr_t)rp) + c4);
-    *reinterpret_cast<uint4*>(stg + r * kStagePitch + 4 * c4) = v;
-  }
-  __syncwarp();
-  const uint4* mine4 = reinterpret_cast<const uint4*>(stg + lane * kStagePitch);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 v = mine4[q];
-    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-  }
-}
-
 // fp32 store of the accumulator tile through warp_store_block16 (stg != nullptr) — thread t owns row t
 template <int BN>
 __device__ __forceinline__ void store_rows_f32_coalesced(uint32_t tmem_lane_base, float* __restrict__ dst, bool row_valid, int n0,
@@ -240,13 +215,16 @@ __device__ __forceinline__ void ln_bwd_tile(const LnBwdFuse& f, const LnBwdCtx& 
   float dy[BN];
   float xk[KEEP_XH ? BN : 1];
   float sg = 0.f, sgx = 0.f;
-  // the normalised values of this thread's row, 16 at a time through the warp's staging block (full-sector loads: a
-  // thread reading its own 128- or 256-byte row directly touches half a sector per instruction)
+  // the normalised values of this thread's row, 16 at a time
+  // (measured: staging these loads through shared memory for full-sector instructions — warp_load_block16 — made the
+  // batch-4096 input-gradient kernels 20 % SLOWER: they are bound by the L1 LSU data pipe, and the staging adds a
+  // st.shared + ld.shared per 16 bytes; direct 16-byte loads of the thread's own row it is)
   auto load_xhat16 = [&](int first, float (&x)[16]) {
-    uint32_t w[16];
-    warp_load_block16(stg, w, reinterpret_cast<const float*>(xr) + first, valid);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(w[i]);
+    for (int q = 0; q < 4; ++q) {
+      const float4 x4 = valid ? __ldg(xr + first / 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[4 * q] = x4.x; x[4 * q + 1] = x4.y; x[4 * q + 2] = x4.z; x[4 * q + 3] = x4.w;
+    }
   };
 #pragma unroll
   for (int cb = 0; cb < BN / 32; ++cb) {
