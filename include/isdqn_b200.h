@@ -353,6 +353,11 @@ int isdqn_act_wait(const int32_t* h_flag_pinned, int32_t seq, int64_t timeout_us
  * isdqn_threefry2x32: the Threefry-2x32 (20 rounds) block function, out2 = E_key(x0, x1). */
 void isdqn_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out2);
 int32_t isdqn_threefry_randint(uint32_t k0, uint32_t k1, int32_t minval, int32_t maxval);
+/* jax.random.split(key, num) -> out_keys[2 * num] raw key words (key i = out_keys[2i], out_keys[2i + 1]) and
+ * jax.random.uniform(key) (float32 in [0, 1)): the epsilon-greedy draws of select_action
+ * (slimdqn/sample_collection/utils.py:8-15), restated like isdqn_threefry_randint. */
+void isdqn_threefry_split(uint32_t k0, uint32_t k1, int32_t num, uint32_t* out_keys);
+float isdqn_threefry_uniform(uint32_t k0, uint32_t k1);
 
 /* Diagnostic: device-side timeline.  While d_buf (uint64[4001], zero-initialised device memory) is set, CTA (0,0,0) of
  * every learner-step kernel appends its start time in ns (%globaltimer) at d_buf[1 + d_buf[0]++].  NULL switches it off. */

@@ -166,6 +166,8 @@ PROTOTYPES = {
     "isdqn_act_wait": (C.c_int, [_P, _I32, _I64]),
     "isdqn_threefry2x32": (None, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
     "isdqn_threefry_randint": (_I32, [C.c_uint32, C.c_uint32, _I32, _I32]),
+    "isdqn_threefry_split": (None, [C.c_uint32, C.c_uint32, _I32, _P]),
+    "isdqn_threefry_uniform": (C.c_float, [C.c_uint32, C.c_uint32]),
     "isdqn_dp_unique_id": (C.c_int, [_P]),
     "isdqn_dp_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "isdqn_dp_allreduce_f32": (C.c_int, [_P, _P, _I64, _P]),

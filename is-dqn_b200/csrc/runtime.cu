@@ -199,6 +199,29 @@ extern "C" int32_t isdqn_threefry_randint(uint32_t k0, uint32_t k1, int32_t minv
   return (int32_t)((int64_t)minval + (int64_t)off);
 }
 
+// jax.random.split(key, num): out_keys[2 * num] (raw key words).  threefry_2x32(key, iota(2 * num)): the counts are split in
+// two halves that form the two lanes, the outputs of the lanes are concatenated and reshaped (num, 2).
+extern "C" void isdqn_threefry_split(uint32_t k0, uint32_t k1, int32_t num, uint32_t* out_keys) {
+  if (num < 1 || !out_keys) return;
+  const int half = num;  // 2 * num counts -> lanes x0 = [0, num), x1 = [num, 2 num)
+  for (int i = 0; i < half; ++i) {
+    uint32_t a = (uint32_t)i, b = (uint32_t)(half + i);
+    threefry2x32(k0, k1, a, b);
+    out_keys[i] = a;          // first half of the flat output
+    out_keys[half + i] = b;   // second half
+  }
+}
+
+// jax.random.uniform(key) (float32 in [0, 1)): 32 random bits -> mantissa of a float in [1, 2) minus 1
+extern "C" float isdqn_threefry_uniform(uint32_t k0, uint32_t k1) {
+  uint32_t x0 = 0, x1 = 0;
+  threefry2x32(k0, k1, x0, x1);
+  const uint32_t bits = (x0 >> 9) | 0x3F800000u;
+  float f;
+  memcpy(&f, &bits, sizeof(f));
+  return f - 1.0f;
+}
+
 extern "C" int isdqn_abi_version(void) { return ISDQN_ABI_VERSION; }
 
 extern "C" const char* isdqn_strerror(int code) {

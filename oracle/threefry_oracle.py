@@ -65,3 +65,11 @@ def randint(key, minval: int, maxval: int) -> int:
     mult = ((mult * mult) & M) % span
     off = ((((higher % span) * mult) & M) + (lower % span)) & M
     return minval + off % span
+
+
+def uniform(key) -> float:
+    """jax.random.uniform(key) for float32: (bits >> 9 | 0x3F800000) viewed as a float in [1, 2), minus 1."""
+    import struct
+
+    bits = (random_bits32(key) >> 9) | 0x3F800000
+    return struct.unpack("<f", struct.pack("<I", bits))[0] - 1.0

@@ -46,3 +46,38 @@ def test_raw_key_forms():
     assert _raw_key(np.array([[3, 4]], dtype=np.uint32)) == (3, 4)
     a, b = _raw_key("seed"), _raw_key("seed")
     assert a == b and a != _raw_key("other")
+
+
+def test_split_and_uniform_match_the_restatement():
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for _ in range(500):
+        k0, k1 = (int(x) for x in rng.integers(0, 2**32, 2, dtype=np.uint64))
+        for num in (2, 3, 5):
+            out = (C.c_uint32 * (2 * num))()
+            lib.isdqn_threefry_split(k0, k1, num, out)
+            assert [(out[2 * i], out[2 * i + 1]) for i in range(num)] == T.split((k0, k1), num)
+        u = lib.isdqn_threefry_uniform(k0, k1)
+        assert u == np.float32(T.uniform((k0, k1))) and 0.0 <= u < 1.0
+
+
+def test_select_action_follows_the_reference_control_flow():
+    """utils.py:8-15 on the host: explore iff uniform(k_u) <= eps, random action from k_a, greedy call with k_g."""
+    from isdqn_b200.sample_collection import utils as U
+
+    seen = []
+
+    def best_action(params, state, key):
+        seen.append(tuple(int(x) for x in key))
+        return np.int32(7)
+
+    for seed in range(200):
+        ku, ka, kg = T.split((0, seed), 3)
+        eps = 0.5
+        got = U.select_action(best_action, None, None, seed, 9, lambda n: eps, 0)
+        if T.uniform(ku) <= eps:
+            assert int(got) == T.randint(ka, 0, 9)
+        else:
+            assert int(got) == 7 and seen[-1] == kg
+    sched = U.linear_schedule(1.0, 0.01, 1000)
+    assert sched(0) == 1.0 and abs(sched(500) - 0.505) < 1e-12 and abs(sched(5000) - 0.01) < 1e-12
