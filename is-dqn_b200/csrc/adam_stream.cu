@@ -18,6 +18,8 @@
 //     tile, fp32 accumulation), then update the stage in place: conflict-free 16-byte shared-memory accesses, the Adam
 //     element update of learner_kernels.cuh, fence.proxy.async, arrive.
 // Tiles are dealt round-robin over the CTAs, so at any moment the whole GPU streams one contiguous window of each array.  Every other leaf of the flat vector is updated by the consumers after their last tile.
+#include <cstdlib>
+
 #include "learner_kernels.cuh"
 #include "tc_engine.cuh"
 
@@ -40,13 +42,28 @@ constexpr int kTpStageBytes = 3 * kTpTileBytes + kTpTileElems * 2;  // p, mu, nu
 constexpr int kTpLdA = 24;  // bf16 per staged act row (16 + 8: the 8 rows of an ldmatrix fall in 8 different banks)
 constexpr int kTpMaxStages = 3;
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// pol != 0: an L2 eviction-priority policy (createpolicy) rides on the copy.  The optimiser state of the Dense kernel
+// (p, mu, nu: 48 MB) and its bf16 shadow (8 MB) are written here and read again by the next step — 56 MB of the 126 MB
+// L2: marked evict_last they are still resident when the next update (and the next forward / input-gradient GEMM, for
+// the shadow) comes for them, so the pass streams from L2 instead of HBM (ISDQN_ADAM_L2=0: no hints).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  if (pol)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+  if (pol)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem),
+                 "r"(bytes), "l"(pol)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -63,7 +80,7 @@ dense_wgrad_adam_stream_kernel(float* __restrict__ p_all, const float* __restric
                                float* __restrict__ nu_all, const int32_t* __restrict__ count, float lr, float b1, float b2,
                                float eps, __nv_bfloat16* __restrict__ shadow_all, int64_t w_off, int64_t n_total4,
                                const __nv_bfloat16* __restrict__ act, int64_t lda, const __nv_bfloat16* __restrict__ dz, int B,
-                               int Kin, int N, int stages) {
+                               int Kin, int N, int stages, int l2_hint) {
   // Programmatic dependent launch: this kernel's predecessor is the partial reduction, which only produces `g_all` —
   // the gradients of the OTHER leaves.  p / mu / nu / shadow of the Dense kernel, dz, act and the step counter were all
   // written by grids that completed before the predecessor even started (every kernel of the chain waits for its own
@@ -102,6 +119,7 @@ dense_wgrad_adam_stream_kernel(float* __restrict__ p_all, const float* __restric
 
   if (warp == kTpConsumers / 32) {
     // ------------------------------------------------------------------------------------------ producer warp
+    const uint64_t pol = l2_hint ? l2_policy_evict_last() : 0ull;
     auto issue_loads = [&](int it) {
       const int s = it % stages;
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -109,9 +127,9 @@ dense_wgrad_adam_stream_kernel(float* __restrict__ p_all, const float* __restric
         mbar_arrive_expect_tx(full + s, 3u * kTpTileBytes);
         const int64_t off = w_off + tile * kTpTileElems;
         const uint32_t dst = smem_u32(stage0 + (size_t)s * kTpStageBytes);
-        bulk_g2s(dst, p_all + off, kTpTileBytes, full + s);
-        bulk_g2s(dst + kTpTileBytes, mu_all + off, kTpTileBytes, full + s);
-        bulk_g2s(dst + 2 * kTpTileBytes, nu_all + off, kTpTileBytes, full + s);
+        bulk_g2s(dst, p_all + off, kTpTileBytes, full + s, pol);
+        bulk_g2s(dst + kTpTileBytes, mu_all + off, kTpTileBytes, full + s, pol);
+        bulk_g2s(dst + 2 * kTpTileBytes, nu_all + off, kTpTileBytes, full + s, pol);
       }
       // act^T of these R rows: R / 8 16-byte pieces per batch row, asynchronous (the arrival is performed by the copy)
       const int64_t row0 = tile * R;
@@ -130,10 +148,10 @@ dense_wgrad_adam_stream_kernel(float* __restrict__ p_all, const float* __restric
       if (lane == 0) {
         const int64_t off = w_off + ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * kTpTileElems;
         const uint32_t src = smem_u32(stage0 + (size_t)s * kTpStageBytes);
-        bulk_s2g(p_all + off, src, kTpTileBytes);
-        bulk_s2g(mu_all + off, src + kTpTileBytes, kTpTileBytes);
-        bulk_s2g(nu_all + off, src + 2 * kTpTileBytes, kTpTileBytes);
-        if (shadow_all) bulk_s2g(shadow_all + off, src + 3 * kTpTileBytes, kTpTileElems * 2);
+        bulk_s2g(p_all + off, src, kTpTileBytes, pol);
+        bulk_s2g(mu_all + off, src + kTpTileBytes, kTpTileBytes, pol);
+        bulk_s2g(nu_all + off, src + 2 * kTpTileBytes, kTpTileBytes, pol);
+        if (shadow_all) bulk_s2g(shadow_all + off, src + 3 * kTpTileBytes, kTpTileElems * 2, pol);
         bulk_commit();
         // refill the stage whose stores were committed one tile ago: they have had a whole tile to leave shared memory
         if (j >= 1 && j - 1 + stages < n_my) bulk_wait_read_all_but_one();
@@ -268,11 +286,15 @@ int isdqn_dense_wgrad_adam_stream_launch(float* d_params, const float* d_grads, 
   if (attr_once.first()) {
     ISDQN_CUDA_CHECK(cudaFuncSetAttribute(dense_wgrad_adam_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
   }
+  static const bool l2_hint = [] {
+    const char* e = getenv("ISDQN_ADAM_L2");
+    return !(e && e[0] == '0');
+  }();
   ISDQN_PROF(as_stream(stream), "dense_wgrad_adam");
   ISDQN_CUDA_CHECK(launch_pdl(dense_wgrad_adam_stream_kernel, dim3((unsigned)kNumSMs), dim3(kTpThreads), smem, as_stream(stream), d_params,
                               d_grads, d_mu, d_nu, d_count, lr, b1, b2, eps, reinterpret_cast<__nv_bfloat16*>(d_shadow_bf16), w_off,
                               n_total / 4, reinterpret_cast<const __nv_bfloat16*>(d_act_bf16), lda,
-                              reinterpret_cast<const __nv_bfloat16*>(d_dz_bf16), B, Kin, N, stages));
+                              reinterpret_cast<const __nv_bfloat16*>(d_dz_bf16), B, Kin, N, stages, l2_hint ? 1 : 0));
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }
