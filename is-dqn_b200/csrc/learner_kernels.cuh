@@ -811,6 +811,172 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ wh, cons
   }
 }
 
+// heads_td_loss_kernel + head_bwd_kernel in ONE launch (small batches: the TD loss is a 6 us hop of the dependent chain for
+// 288 subtractions).  d(loss)/dq is non-zero only at the taken action of every online head, so it is K numbers per sample,
+// cheap enough for every CTA to recompute what it needs from the Q-values:
+//   [0, row_ctas)                 input gradient + LayerNorm / ReLU backward of the hidden layer (as head_bwd_kernel), the row's
+//                                 K TD errors computed on the spot
+//   [row_ctas, row_ctas + wg)     head kernel gradient; the CTA first computes the whole [B][K] TD matrix into shared memory
+//   last CTA                      per-head loss means (+ cumulated sums), head bias gradient, |TD| matrix, Adam step counter
+// Same arithmetic per element as the two kernels it replaces (isdqn.py:97-109); the sums run in a fixed order.
+constexpr int kTailMaxB = 256;
+constexpr int kHbTdMax = 4096;  // B * K values staged per CTA
+__device__ __forceinline__ float td_error(const float* __restrict__ q_all, int n_out, int B, int b, int k, int A, int a, float r,
+                                          float coef) {
+  const float* qn = q_all + (int64_t)(B + b) * n_out + k * A;  // Q_k(s', .)
+  float mx = qn[0];
+  for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
+  const float target = r + coef * mx;
+  return q_all[(int64_t)b * n_out + (k + 1) * A + a] - target;
+}
+
+static __global__ void __launch_bounds__(kRowThreads)
+head_bwd_td_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action, const double* __restrict__ reward,
+                   const uint8_t* __restrict__ terminal, float gamma_n, int B, int B_global, int K, int A,
+                   const float* __restrict__ is_weights, float* __restrict__ td_abs, float* __restrict__ losses,
+                   double* __restrict__ cumulated, float* __restrict__ dbias, int32_t* count, const float* __restrict__ wh,
+                   const float* __restrict__ act_in, int C, int NH, int row_ctas, int wg_ctas, const float* __restrict__ xhat,
+                   const float* __restrict__ rstd, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                   float* __restrict__ colpart, __nv_bfloat16* __restrict__ dz16, float* __restrict__ dwh) {
+  pdl_sync();
+  __shared__ float red[kRowThreads / 32];
+  __shared__ float s_val[kHbTdMax];  // row CTAs use the first K entries
+  __shared__ float s_sq[kHbTdMax];
+  __shared__ int s_act[kTailMaxB];
+  const int tid = threadIdx.x;
+  const float inv_b = 1.0f / (float)B_global;
+  if ((int)blockIdx.x >= row_ctas) {
+    // ---- the whole TD matrix: val[b][k] = d(loss)/dq at (b, head k + 1, a_b), sq[b][k] = w_b td^2
+    for (int i = tid; i < B; i += kRowThreads) s_act[i] = (int)action[i];
+    __syncthreads();
+    for (int i = tid; i < B * K; i += kRowThreads) {
+      const int b = i / K, k = i - b * K;
+      const float rw = (float)reward[b];
+      const float coef = (float)(1 - (int)terminal[b]) * gamma_n;
+      const float td = td_error(q_all, (1 + K) * A, B, b, k, A, s_act[b], rw, coef);
+      const float wb = is_weights ? is_weights[b] : 1.0f;
+      s_val[i] = 2.0f * td * inv_b * wb;
+      s_sq[i] = (wb * td) * td;
+      if ((int)blockIdx.x == row_ctas + wg_ctas && td_abs) td_abs[(int64_t)k * B + b] = fabsf(td);
+    }
+    __syncthreads();
+    if ((int)blockIdx.x == row_ctas + wg_ctas) {  // ---- cross-sample tail
+      if (tid < K) {
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t += s_sq[b * K + tid];
+        const float l = t * inv_b;
+        losses[tid] = l;
+        if (cumulated) cumulated[tid] += (double)l;
+      }
+      for (int c = tid; c < NH; c += kRowThreads) {
+        const int hd = c / A - 1, a = c - (hd + 1) * A;
+        float t = 0.f;
+        if (hd >= 0)
+          for (int b = 0; b < B; ++b)
+            if (s_act[b] == a) t += s_val[b * K + hd];
+        dbias[c] = t;
+      }
+      if (count && tid == 0) *count += 1;
+      return;
+    }
+    // ---- head kernel gradient: dWh[n][c] = sum_b act[b][n] dq[b][c]
+    const int o = ((int)blockIdx.x - row_ctas) * kRowThreads + tid;
+    if (o < C * NH) {
+      const int n = o / NH, c = o - n * NH;
+      const int hd = c / A - 1, a = c - (hd + 1) * A;
+      float acc = 0.f;
+      if (hd >= 0) {
+        for (int b = 0; b < B; ++b) {
+          if (s_act[b] != a) continue;
+          const float g = s_val[b * K + hd];
+          if (g != 0.f) acc = fmaf(act_in[(int64_t)b * C + n], g, acc);
+        }
+      }
+      dwh[o] = acc;
+    }
+    return;
+  }
+  // ---- row CTAs
+  float c0[kRowMaxPerThread], c1[kRowMaxPerThread], c2[kRowMaxPerThread], gam[kRowMaxPerThread], bet[kRowMaxPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    c0[j] = c1[j] = c2[j] = 0.f;
+    const int n = tid + j * kRowThreads;
+    gam[j] = (ln_g && n < C) ? ln_g[n] : 0.f;
+    bet[j] = (ln_g && n < C) ? ln_b[n] : 0.f;
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int r = blockIdx.x; r < B; r += row_ctas) {
+    __syncthreads();  // (the previous row's values are no longer read)
+    const int a_r = (int)action[r];
+    if (tid < K) {
+      const float rw = (float)reward[r];
+      const float coef = (float)(1 - (int)terminal[r]) * gamma_n;
+      const float td = td_error(q_all, (1 + K) * A, B, r, tid, A, a_r, rw, coef);
+      const float wb = is_weights ? is_weights[r] : 1.0f;
+      s_val[tid] = 2.0f * td * inv_b * wb;
+    }
+    __syncthreads();
+    float dy[kRowMaxPerThread], xh[kRowMaxPerThread];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = tid + j * kRowThreads;
+      dy[j] = xh[j] = 0.f;
+      if (n < C) {
+        float dv = 0.f;
+        const float* wrow = wh + (int64_t)n * NH + A + a_r;  // head kernel row n at the taken action of head 1, 2, ...
+        for (int i0 = 0; i0 < K; i0 += 8) {  // loads of 8 heads in flight; zero factors are skipped (x + 0 * w == x)
+          float wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = (i0 + u < K) ? __ldg(wrow + (i0 + u) * A) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float v = (i0 + u < K) ? s_val[i0 + u] : 0.f;
+            if (v != 0.f) dv = fmaf(v, wv[u], dv);
+          }
+        }
+        const int64_t idx = (int64_t)r * C + n;
+        if (ln_g) {
+          xh[j] = xhat[idx];
+          dy[j] = (xh[j] * gam[j] + bet[j] > 0.f) ? dv : 0.f;
+          const float g = dy[j] * gam[j];
+          sg += g;
+          sgx += g * xh[j];
+        } else {
+          dy[j] = act_in[idx] > 0.f ? dv : 0.f;
+        }
+      }
+    }
+    float rs = 0.f, mg = 0.f, mgx = 0.f;
+    if (ln_g) {
+      mg = block_sum_256(sg, red) * inv_c;
+      mgx = block_sum_256(sgx, red) * inv_c;
+      rs = rstd[r];
+    }
+#pragma unroll
+    for (int j = 0; j < kRowMaxPerThread; ++j) {
+      const int n = tid + j * kRowThreads;
+      if (n < C) {
+        const float dz = ln_g ? rs * (dy[j] * gam[j] - mg - xh[j] * mgx) : dy[j];
+        if (dz16) dz16[(int64_t)r * C + n] = __float2bfloat16_rn(dz);
+        c0[j] += dz;
+        c1[j] += dy[j] * xh[j];
+        c2[j] += dy[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kRowMaxPerThread; ++j) {
+    const int n = tid + j * kRowThreads;
+    if (n < C) {
+      colpart[((int64_t)blockIdx.x * 3 + 0) * C + n] = c0[j];
+      colpart[((int64_t)blockIdx.x * 3 + 1) * C + n] = c1[j];
+      colpart[((int64_t)blockIdx.x * 3 + 2) * C + n] = c2[j];
+    }
+  }
+}
+
 // --------------------------------------------------------------------------- deterministic partial reduce
 constexpr int kMaxSegments = 40;
 struct Segment {
@@ -848,7 +1014,6 @@ static inline int head_tail_ctas(int C, int NH) { return 1 + (C * NH + 255) / 25
 
 // (the per-sample values are staged in shared memory first: the sums below then run over shared memory in a fixed order
 // instead of over a chain of dependent global loads)
-constexpr int kTailMaxB = 256;
 __device__ __forceinline__ void head_tail_block(const HeadTail& h, int j) {
   const int tid = threadIdx.x;
   __shared__ float s_tdq[kTailMaxB * 2 * 16 > 4096 ? 4096 : kTailMaxB * 2 * 16];  // [B][2K] while it fits, else global

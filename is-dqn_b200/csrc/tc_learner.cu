@@ -1015,7 +1015,15 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   }
   const float* q_all = wsp(ws, w.act[nl - 1]);
   const Layer& last = p.L[nl - 1];
-  if (!mid_done) {
+  // small batch: the TD loss runs inside the head-backward launch (head_bwd_td_kernel) instead of as a hop of its own
+  static const bool td_fold_on = [] {
+    const char* e = getenv("ISDQN_TD_FOLD");
+    return !(e && e[0] == '0');
+  }();
+  const bool td_fold = td_fold_on && backward && !mid_done && !q_out && nl >= 2 && p.L[nl - 2].type == 1 && B <= 256 &&
+                       B <= kTailMaxB && B * net->n_heads <= kHbTdMax && w.wsplits[nl - 1] == 1 && last.out_dim <= 128 &&
+                       p.L[nl - 2].out_dim <= kRowThreads * kRowMaxPerThread;
+  if (!mid_done && !td_fold) {
   ISDQN_PROF(s, "heads_td_loss");
   ISDQN_CUDA_CHECK(launch_pdl(heads_td_loss_kernel, dim3(net->n_heads), dim3(kLossThreads), 0, s, q_all, b->d_action, b->d_reward, b->d_terminal, tr->gamma_n, B,
                                                   tr->batch_global, net->n_heads, net->n_actions, tr->d_losses,
@@ -1098,6 +1106,19 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
       float* dprev = wsp(ws, w.dbuf[l & 1]);
       const int row_ctas = w.col_ctas[l - 1];
       const int wg_ctas = ceil_div(P.out_dim * L.out_dim, kRowThreads);
+      if (td_fold) {
+        ISDQN_PROF(s, "head_bwd_td");
+        ISDQN_CUDA_CHECK(launch_pdl(head_bwd_td_kernel, dim3(row_ctas + wg_ctas + 1), dim3(kRowThreads), 0, s, q_all, b->d_action,
+                                    b->d_reward, b->d_terminal, tr->gamma_n, B, tr->batch_global, net->n_heads, net->n_actions,
+                                    tr->d_is_weights, tr->d_td_abs, tr->d_losses, update ? tr->d_cumulated : nullptr,
+                                    grads + L.b_off, update ? tr->d_count : nullptr, params + L.w_off, wsp(ws, w.act[l - 1]),
+                                    P.out_dim, L.out_dim, row_ctas, wg_ctas, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]),
+                                    P.has_ln ? params + P.g_off : nullptr, P.has_ln ? params + P.beta_off : nullptr,
+                                    wsp(ws, w.colpart[l - 1]), w16(wt, t.dz16[l - 1]), grads + L.w_off));
+        ISDQN_LAUNCH_CHECK();
+        dz32 = dprev;
+        continue;
+      }
       ISDQN_PROF(s, "head_bwd");
       ISDQN_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3(row_ctas + wg_ctas), dim3(kRowThreads), 0, s, dz32, params + L.w_off,
                                   wsp(ws, w.act[l - 1]), B, P.out_dim, L.out_dim, row_ctas, dprev, wsp(ws, w.xhat[l - 1]),
