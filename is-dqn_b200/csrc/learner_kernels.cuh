@@ -819,15 +819,22 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ wh, cons
 //   [row_ctas, row_ctas + wg)     head kernel gradient; the CTA first computes the whole [B][K] TD matrix into shared memory
 //   last CTA                      per-head loss means (+ cumulated sums), head bias gradient, |TD| matrix, Adam step counter
 // Same arithmetic per element as the two kernels it replaces (isdqn.py:97-109); the sums run in a fixed order.
+constexpr int kMaxActions = 32;
 constexpr int kTailMaxB = 256;
 constexpr int kHbTdMax = 4096;  // B * K values staged per CTA
 __device__ __forceinline__ float td_error(const float* __restrict__ q_all, int n_out, int B, int b, int k, int A, int a, float r,
                                           float coef) {
   const float* qn = q_all + (int64_t)(B + b) * n_out + k * A;  // Q_k(s', .)
-  float mx = qn[0];
-  for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
+  // every load is issued before the first comparison (a `mx = fmaxf(mx, qn[j])` loop is a chain of A dependent L2 round trips)
+  const float qa = q_all[(int64_t)b * n_out + (k + 1) * A + a];
+  float qv[kMaxActions];
+#pragma unroll
+  for (int j = 0; j < kMaxActions; ++j) qv[j] = j < A ? qn[j] : qn[0];
+  float mx = qv[0];
+#pragma unroll
+  for (int j = 1; j < kMaxActions; ++j) mx = fmaxf(mx, qv[j]);  // (same maximum: max is exact in any order)
   const float target = r + coef * mx;
-  return q_all[(int64_t)b * n_out + (k + 1) * A + a] - target;
+  return qa - target;
 }
 
 static __global__ void __launch_bounds__(kRowThreads)
@@ -1092,7 +1099,19 @@ static inline bool segments_vec4_ok(const SegmentList& l) {
 // are combined in a fixed order => deterministic, and identical for VEC = 1 and VEC = 4.
 template <int VEC>
 __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegmentList list, const HeadTail tail, int n_tiles) {
-  pdl_sync();
+  // Trigger BEFORE the wait: the successor is the streaming optimiser kernel, whose tile pipeline touches nothing this
+  // kernel or its predecessor (the last weight gradient) writes and which only waits for THIS grid before its rest-leaf
+  // phase (adam_stream.cu).  Launched now, its CTAs take the SMs as the weight-gradient CTAs leave them and stream the
+  // Dense kernel's state while the partial sums are still being folded (ISDQN_REDUCE_LATE_TRIGGER=1 at build time: the
+  // usual wait-then-trigger).
+  trace_kernel_start();
+#if defined(ISDQN_REDUCE_LATE_TRIGGER)
+  pdl_wait();
+  pdl_trigger();
+#else
+  pdl_trigger();
+  pdl_wait();
+#endif
   if ((int)blockIdx.x >= n_tiles) {
     head_tail_block(tail, (int)blockIdx.x - n_tiles);
     return;
@@ -1171,7 +1190,6 @@ static inline cudaError_t launch_reduce_segments(SegmentList& segs, cudaStream_t
 // CTA produces its head's slice of d(loss)/dq and of the head layer's bias gradient.
 constexpr int kLossThreads = 256;
 constexpr int kMaxHeads = 64;
-constexpr int kMaxActions = 32;
 
 static __global__ void __launch_bounds__(kLossThreads)
 heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict__ action,
@@ -1205,11 +1223,7 @@ heads_td_loss_kernel(const float* __restrict__ q_all, const int64_t* __restrict_
       a = (int)action[b];
       const float r = (float)reward[b];                             // f64 -> f32 at the jit boundary
       const float coef = (float)(1 - (int)terminal[b]) * gamma_n;   // ((1 - d) * gamma^n) in fp32
-      const float* qn = q_all + (int64_t)(B + b) * n_out + k * A;   // Q_k(s', .)
-      float mx = qn[0];
-      for (int j = 1; j < A; ++j) mx = fmaxf(mx, qn[j]);
-      const float target = r + coef * mx;
-      const float td = q_all[(int64_t)b * n_out + (k + 1) * A + a] - target;
+      const float td = td_error(q_all, n_out, B, b, k, A, a, r, coef);  // Q_{k+1}(s, a) - (r + coef max_a' Q_k(s', a'))
       // importance weight of a prioritized batch (1 without: both products are then exact, the reference's loss bit for bit)
       const float wb = is_weights ? is_weights[b] : 1.0f;
       part += (wb * td) * td;
