@@ -1016,9 +1016,11 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
   const float* q_all = wsp(ws, w.act[nl - 1]);
   const Layer& last = p.L[nl - 1];
   // small batch: the TD loss runs inside the head-backward launch (head_bwd_td_kernel) instead of as a hop of its own
+  // (opt-in: measured 131.3 us per update against 126.7 us with the separate loss kernel — the folded kernel's row CTAs
+  // gain two round trips on the critical path and every weight-gradient CTA recomputes the TD matrix; profiles/r02_summary.md)
   static const bool td_fold_on = [] {
     const char* e = getenv("ISDQN_TD_FOLD");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   const bool td_fold = td_fold_on && backward && !mid_done && !q_out && nl >= 2 && p.L[nl - 2].type == 1 && B <= 256 &&
                        B <= kTailMaxB && B * net->n_heads <= kHbTdMax && w.wsplits[nl - 1] == 1 && last.out_dim <= 128 &&

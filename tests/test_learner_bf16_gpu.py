@@ -151,9 +151,9 @@ def test_update_is_adam_of_the_reported_gradient_bf16(B):
         assert torch.equal(agent.params.shadow.float(), agent.params.flat.to(torch.bfloat16).float())
 
 
-@pytest.mark.parametrize("env", [{"ISDQN_MID": "1"}, {"ISDQN_PAIR": "0", "ISDQN_LNFUSE": "0", "ISDQN_TD_FOLD": "0"},
+@pytest.mark.parametrize("env", [{"ISDQN_MID": "1"}, {"ISDQN_PAIR": "0", "ISDQN_LNFUSE": "0", "ISDQN_TD_FOLD": "1"},
                                  {"ISDQN_PAIR_D1": "0", "ISDQN_TMA_STORE": "0", "ISDQN_ADAM_L2": "0"}],
-                         ids=["head_mid", "unfused_backward", "pair_proportional_staged_stores"])
+                         ids=["head_mid", "unfused_backward_td_fold", "pair_proportional_staged_stores"])
 def test_alternative_launch_plans_keep_parity(env):
     """The opt-in / fallback launch plans of the batch-32 chain (one-launch head step; separate weight-gradient,
     input-gradient and LayerNorm-backward launches) against the same oracle bars, in a fresh process (the switches are
