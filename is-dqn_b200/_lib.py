@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # (ISDQN_LIB: another build of the same library, e.g. an experiment variant next to the default one)
 LIB_PATH = os.environ.get("ISDQN_LIB") or os.path.join(_HERE, "lib", "libisdqn_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_FEATURES = 8
-MAX_LEAVES = 48
+MAX_LEAVES = 64
 SUMTREE_SET_MAX = 8192
 SUMTREE_OP_MAX = 1024
 
@@ -31,7 +31,7 @@ ST_KEY_MISSING = 64
 SUMTREE_TAG_MAX = -0.5
 
 OUT_RAW, OUT_F32, OUT_BF16 = 0, 1, 2
-ARCH_CNN, ARCH_FC = 0, 1
+ARCH_CNN, ARCH_FC, ARCH_IMPALA = 0, 1, 2
 COMPUTE_F32, COMPUTE_BF16 = 0, 1
 
 

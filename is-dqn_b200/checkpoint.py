@@ -19,6 +19,13 @@ from typing import Any, Dict
 
 import numpy as np
 
+
+def module_at(inner: dict, mod: str) -> dict:
+    """The module dict at the path `mod` ("Dense_0", or "Stack_1/Conv_2" for impala's nested sub-modules)."""
+    for part in mod.split("/"):
+        inner = inner[part]
+    return inner
+
 # what a parameter checkpoint legitimately refers to: NumPy's array / dtype / scalar reconstruction and plain containers
 _NUMPY_NAMES = {"_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"}
 _BUILTIN_NAMES = {"dict", "list", "tuple", "set", "frozenset", "int", "float", "complex", "bool", "str", "bytes", "bytearray",
@@ -76,7 +83,18 @@ def flax_leaves(model: Dict[str, Any]) -> Dict[str, Dict[str, np.ndarray]]:
             node = node["params"]
     if not isinstance(node, dict) or not all(isinstance(v, dict) for v in node.values()):
         raise ValueError("not a flax-shaped parameter tree: expected {module: {leaf: array}}")
-    return {mod: {leaf: np.asarray(v) for leaf, v in leaves.items()} for mod, leaves in node.items()}
+    out: Dict[str, Dict[str, np.ndarray]] = {}
+
+    def walk(prefix: str, mod: dict) -> None:
+        # a sub-module (impala's Stack_i) holds modules, a module holds array leaves; paths are joined with "/"
+        for name, v in mod.items():
+            if isinstance(v, dict):
+                walk(f"{prefix}/{name}" if prefix else name, v)
+            else:
+                out.setdefault(prefix, {})[name] = np.asarray(v)
+
+    walk("", node)
+    return out
 
 
 def check_against(specs, leaves: Dict[str, Dict[str, np.ndarray]]) -> None:
@@ -105,7 +123,7 @@ def load_model(agent, model_or_path) -> None:
     check_against(agent.params.specs, leaves)
     for mod, lv in leaves.items():
         for leaf, v in lv.items():
-            agent.params["params"][mod][leaf] = np.asarray(v, dtype=np.float32)
+            module_at(agent.params["params"], mod)[leaf] = np.asarray(v, dtype=np.float32)
 
 
 # ---------------------------------------------------------------------------------------------------- resume
@@ -122,15 +140,18 @@ def unpack_state(npz) -> Dict[str, Any]:
     trees: Dict[str, Any] = {"params": {}, "mu": {}, "nu": {}}
     for key in npz.files if hasattr(npz, "files") else npz.keys():
         parts = key.split("/")
-        if len(parts) == 3 and parts[0] in trees:
-            trees[parts[0]].setdefault(parts[1], {})[parts[2]] = np.asarray(npz[key])
+        if len(parts) >= 3 and parts[0] in trees:  # prefix / module path (may be nested) / leaf
+            trees[parts[0]].setdefault("/".join(parts[1:-1]), {})[parts[-1]] = np.asarray(npz[key])
     trees["count"] = int(np.asarray(npz["count"]))
     trees["cumulated_losses"] = np.asarray(npz["cumulated_losses"], dtype=np.float64)
     return trees
 
 
 def _host_tree(tree) -> Dict[str, Dict[str, np.ndarray]]:
-    return {mod: {leaf: v.detach().cpu().numpy() for leaf, v in lv.items()} for mod, lv in tree["params"].items()}
+    out: Dict[str, Dict[str, np.ndarray]] = {}
+    for mod, leaf, v in tree.leaves():
+        out.setdefault(mod, {})[leaf] = v.detach().cpu().numpy()
+    return out
 
 
 def save_agent_state(agent, path) -> None:
@@ -149,6 +170,6 @@ def load_agent_state(agent, path) -> None:
     for name, tree in (("params", agent.params), ("mu", agent.optimizer_state["mu"]), ("nu", agent.optimizer_state["nu"])):
         for mod, lv in st[name].items():
             for leaf, v in lv.items():
-                tree["params"][mod][leaf] = v
+                module_at(tree["params"], mod)[leaf] = v
     agent.optimizer_state["count"].fill_(st["count"])
     agent.cumulated_losses = st["cumulated_losses"]

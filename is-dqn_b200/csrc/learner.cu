@@ -2,6 +2,7 @@
 // in learner_kernels.cuh.  Replaces the jitted body of iSDQN.learn_on_batch / loss_on_batch / best_action
 // (slimdqn/networks/isdqn.py:82-135) and DQNNet.__call__ (slimdqn/networks/architectures/dqn.py:47-103).
 #include "learner_kernels.cuh"
+#include "impala_kernels.cuh"
 #include "plan.cuh"
 
 using namespace isdqn;
@@ -131,6 +132,43 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
   return ISDQN_OK;
 }
 
+// weight gradient of a convolution: deterministic partials over `splits` row ranges; returns the number of partials
+// written to `part` ([splits][K][Cout]) or -(error code)
+int launch_conv_wgrad_f32(const Layer& L, const void* in, int in_kind, int rows_l, const float* dz, float* part, int splits,
+                          cudaStream_t s) {
+  ConvWgradArgs a;
+  a.in = in;
+  a.H = L.H; a.W = L.W; a.Cin = L.Cin; a.OH = L.OH; a.OW = L.OW; a.Cout = L.out_dim;
+  a.ksz = L.ksz; a.stride = L.stride; a.pad_y = L.pad_y; a.pad_x = L.pad_x;
+  a.M = rows_l; a.K = L.in_dim; a.dz = dz; a.part = part;
+  a.rows_per_split = ceil_div(ceil_div(rows_l, splits), kBK) * kBK;
+  const int real_splits = ceil_div(rows_l, a.rows_per_split);
+  dim3 grid(ceil_div(L.in_dim, 64), ceil_div(L.out_dim, 64), real_splits);
+  ISDQN_PROF(s, "conv_wgrad");
+  if (in_kind == IN_U8_255) conv_wgrad_kernel<IN_U8_255><<<grid, kGemmThreads, 0, s>>>(a);
+  else if (in_kind == IN_F32_255) conv_wgrad_kernel<IN_F32_255><<<grid, kGemmThreads, 0, s>>>(a);
+  else conv_wgrad_kernel<IN_F32><<<grid, kGemmThreads, 0, s>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return -ISDQN_E_CUDA;
+  return real_splits;
+}
+
+// input gradient of a convolution: dx [n_img*H*W][Cin] from dz [n_img*OH*OW][Cout]
+int launch_conv_dgrad_f32(const Layer& L, int n_img, const float* dz, const float* w, float* dx, cudaStream_t s) {
+  ConvDgradArgs a;
+  a.H = L.H; a.W = L.W; a.Cin = L.Cin; a.OH = L.OH; a.OW = L.OW; a.Cout = L.out_dim;
+  a.ksz = L.ksz; a.stride = L.stride; a.pad_y = L.pad_y; a.pad_x = L.pad_x;
+  a.n_img = n_img;
+  a.taps = ceil_div(L.ksz, L.stride);
+  a.Kd = a.taps * a.taps * L.out_dim;
+  a.dz = dz; a.w = w; a.dx = dx;
+  const int rows_max = n_img * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
+  dim3 grid(ceil_div(rows_max, 64), ceil_div(L.Cin, 64), L.stride * L.stride);
+  ISDQN_PROF(s, "conv_dgrad");
+  conv_dgrad_kernel<<<grid, kGemmThreads, 0, s>>>(a);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
 int check_common(const isdqn_net* net, Plan* p) {
   if (!net) return ISDQN_E_INVALID;
   if (net->n_heads > kMaxHeads || net->n_actions > kMaxActions) return ISDQN_E_TOO_LARGE;
@@ -148,8 +186,9 @@ int run_loss(const Plan& p, const isdqn_net* net, const isdqn_train* tr, const i
   return ISDQN_OK;
 }
 
+// d_input (optional): receives dL/d(input of layer 0) [B][in_dim] (the impala torso continues the backward pass from it)
 int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train* tr, const isdqn_batch* b, int in_kind,
-                 cudaStream_t s) {
+                 cudaStream_t s, float* d_input = nullptr) {
   const int B = tr->batch;
   const float* params = tr->d_params;
   float* grads = tr->d_grads;
@@ -176,25 +215,11 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       int rc = launch_gemm(g, 1, s, "dense_wgrad_gemm");
       if (rc) return rc;
     } else {
-      ConvWgradArgs a;
-      a.in = first ? b->d_state : wsp(ws, w.act[l - 1]);
-      a.H = L.H; a.W = L.W; a.Cin = L.Cin; a.OH = L.OH; a.OW = L.OW; a.Cout = L.out_dim;
-      a.ksz = L.ksz; a.stride = L.stride; a.pad_y = L.pad_y; a.pad_x = L.pad_x;
-      a.M = rows_l; a.K = L.in_dim; a.dz = dz; a.part = wsp(ws, w.wpart[l]);
-      const int splits = w.wsplits[l];
-      a.rows_per_split = ceil_div(ceil_div(rows_l, splits), kBK) * kBK;
-      const int real_splits = ceil_div(rows_l, a.rows_per_split);
-      dim3 grid(ceil_div(L.in_dim, 64), ceil_div(L.out_dim, 64), real_splits);
-      ISDQN_PROF(s, "conv_wgrad");
-      if (first) {
-        if (in_kind == IN_U8_255) conv_wgrad_kernel<IN_U8_255><<<grid, kGemmThreads, 0, s>>>(a);
-        else if (in_kind == IN_F32_255) conv_wgrad_kernel<IN_F32_255><<<grid, kGemmThreads, 0, s>>>(a);
-        else conv_wgrad_kernel<IN_F32><<<grid, kGemmThreads, 0, s>>>(a);
-      } else {
-        conv_wgrad_kernel<IN_F32><<<grid, kGemmThreads, 0, s>>>(a);
-      }
-      ISDQN_LAUNCH_CHECK();
-      add_seg(a.part, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
+      const int real_splits = launch_conv_wgrad_f32(L, first ? b->d_state : wsp(ws, w.act[l - 1]), first ? in_kind : IN_F32, rows_l,
+                                                    dz, wsp(ws, w.wpart[l]), w.wsplits[l], s);
+      if (real_splits < 0) return -real_splits;
+      float* part_l = wsp(ws, w.wpart[l]);
+      add_seg(part_l, grads + L.w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, real_splits);
     }
     // ---- bias / LayerNorm parameter gradients come from the column partials of the kernel that produced dz
     if (L.relu) {
@@ -206,10 +231,10 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
         add_seg(cp + 2 * L.out_dim, grads + L.beta_off, st, L.out_dim, w.col_ctas[l]);
       }
     }  // the head layer's bias gradient was written by the loss kernel
-    if (first) break;
+    if (first && !d_input) break;
     // ---- input gradient = dL/d(out of layer l-1), then through that layer's ReLU + LayerNorm
-    const Layer& P = p.L[l - 1];
-    float* dprev = wsp(ws, w.dbuf[l & 1]);
+    const Layer& P = p.L[first ? 0 : l - 1];
+    float* dprev = first ? d_input : wsp(ws, w.dbuf[l & 1]);
     if (L.type == 1) {
       GemmArgs g;  // dX[b][in] = dz[b][out] W^T : B(k=out, n=in) = W[in*out_dim + out]
       g.A = dz; g.sam = L.out_dim; g.sak = 1;
@@ -220,19 +245,10 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       int rc = launch_gemm(g, 1, s, "dense_dgrad_gemm");
       if (rc) return rc;
     } else {
-      ConvDgradArgs a;
-      a.H = L.H; a.W = L.W; a.Cin = L.Cin; a.OH = L.OH; a.OW = L.OW; a.Cout = L.out_dim;
-      a.ksz = L.ksz; a.stride = L.stride; a.pad_y = L.pad_y; a.pad_x = L.pad_x;
-      a.n_img = B;
-      a.taps = ceil_div(L.ksz, L.stride);
-      a.Kd = a.taps * a.taps * L.out_dim;
-      a.dz = dz; a.w = params + L.w_off; a.dx = dprev;
-      const int rows_max = B * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
-      dim3 grid(ceil_div(rows_max, 64), ceil_div(L.Cin, 64), L.stride * L.stride);
-      ISDQN_PROF(s, "conv_dgrad");
-      conv_dgrad_kernel<<<grid, kGemmThreads, 0, s>>>(a);
-      ISDQN_LAUNCH_CHECK();
+      int rc = launch_conv_dgrad_f32(L, B, dz, params + L.w_off, dprev, s);
+      if (rc) return rc;
     }
+    if (first) break;
     {
       const int rows_p = B * P.pix;
       const float* g_ = P.has_ln ? params + P.g_off : nullptr;
@@ -257,8 +273,436 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
   return ISDQN_OK;
 }
 
+// ======================================================================================================= impala
+// architecture_type == "impala" (slimdqn/networks/architectures/dqn.py:7-36, 77-86), fp32 only:
+//   3 x Stack(features[s]):  x = Conv3x3(x); x = max_pool 3x3 / 2 SAME; 2 x { r = x; x = relu(LN(x)); x = relu(Conv3x3(x));
+//   x = Conv3x3(x) + r };  then relu(LN(x)), flatten (h, w, c), Dense tail as in the other architectures.
+// The torso is walked explicitly below; the Dense tail is an `fc` Plan over the flattened torso output, run by the
+// same run_forward / run_loss / run_backward as every other network.
+struct ImpalaStack {
+  int Cin, C, Hin, Win, H, W, pool_pad_y, pool_pad_x;
+  int64_t w[5], b[5], g[2], beta[2];  // Conv_0..4, LayerNorm_0..1 of the Stack (offsets into the flat vector)
+};
+struct ImpalaPlan {
+  ImpalaStack st[3];
+  int has_ln;
+  int64_t fin_g, fin_beta;  // DQNNet's own LayerNorm_0 behind the stacks
+  int64_t tail_base;        // first float of the Dense tail's leaves
+  int flat;                 // H*W*C of the last stack = input width of the tail
+  isdqn_net tail_net;
+  Plan tail;
+  isdqn_layout layout;
+};
+
+Layer impala_conv_layer(int H, int W, int Cin, int Cout) {
+  Layer L = {};
+  L.type = 0;
+  L.H = H; L.W = W; L.Cin = Cin; L.OH = H; L.OW = W; L.ksz = 3; L.stride = 1; L.pad_y = L.pad_x = 1;  // 'SAME'
+  L.in_dim = 9 * Cin; L.out_dim = Cout; L.pix = H * W;
+  return L;
+}
+
+int build_impala_plan(const isdqn_net* net, ImpalaPlan* ip) {
+  if (!net || net->arch != ISDQN_ARCH_IMPALA) return ISDQN_E_INVALID;
+  if (net->n_heads < 1 || net->n_actions < 1 || net->n_heads > kMaxHeads || net->n_actions > kMaxActions)
+    return net->n_heads < 1 || net->n_actions < 1 ? ISDQN_E_INVALID : ISDQN_E_TOO_LARGE;
+  if (net->n_features < 3 || net->n_features > ISDQN_MAX_FEATURES) return ISDQN_E_INVALID;
+  if (net->obs_h < 1 || net->obs_w < 1 || net->obs_c < 1) return ISDQN_E_INVALID;
+  for (int i = 0; i < net->n_features; ++i)
+    if (net->features[i] < 1) return ISDQN_E_INVALID;
+  isdqn_layout& lay = ip->layout;
+  lay.n_leaves = 0;
+  int64_t off = 0;
+  bool overflow = false;
+  auto leaf = [&](int64_t size) {
+    const int64_t o = off;
+    if (lay.n_leaves >= ISDQN_MAX_LEAVES) { overflow = true; return o; }
+    lay.offset[lay.n_leaves] = o;
+    lay.size[lay.n_leaves] = size;
+    lay.n_leaves++;
+    off = (off + size + 7) & ~(int64_t)7;
+    return o;
+  };
+  ip->has_ln = net->layer_norm ? 1 : 0;
+  int h = net->obs_h, w = net->obs_w, c = net->obs_c;
+  for (int s = 0; s < 3; ++s) {
+    ImpalaStack& S = ip->st[s];
+    S.Cin = c; S.C = net->features[s]; S.Hin = h; S.Win = w;
+    if (S.C > 256) return ISDQN_E_TOO_LARGE;  // one CTA covers all output channels of a convolution
+    same_pad(h, 3, 2, &S.H, &S.pool_pad_y);
+    same_pad(w, 3, 2, &S.W, &S.pool_pad_x);
+    S.w[0] = leaf((int64_t)9 * c * S.C);
+    S.b[0] = leaf(S.C);
+    for (int j = 0; j < 2; ++j) {
+      S.g[j] = ip->has_ln ? leaf(S.C) : -1;
+      S.beta[j] = ip->has_ln ? leaf(S.C) : -1;
+      for (int q = 1; q <= 2; ++q) {
+        S.w[q + 2 * j] = leaf((int64_t)9 * S.C * S.C);
+        S.b[q + 2 * j] = leaf(S.C);
+      }
+    }
+    h = S.H; w = S.W; c = S.C;
+  }
+  ip->fin_g = ip->has_ln ? leaf(c) : -1;
+  ip->fin_beta = ip->has_ln ? leaf(c) : -1;
+  ip->tail_base = off;
+  ip->flat = h * w * c;
+  isdqn_net& t = ip->tail_net;
+  t = *net;
+  t.arch = ISDQN_ARCH_FC;
+  t.obs_h = t.obs_w = 1;
+  t.obs_c = ip->flat;
+  t.n_features = net->n_features - 3;
+  for (int i = 0; i < ISDQN_MAX_FEATURES; ++i) t.features[i] = i < t.n_features ? net->features[i + 3] : 0;
+  int rc = build_plan(&t, &ip->tail);
+  if (rc) return rc;
+  for (int i = 0; i < ip->tail.layout.n_leaves; ++i) {
+    if (lay.n_leaves >= ISDQN_MAX_LEAVES) return ISDQN_E_TOO_LARGE;
+    lay.offset[lay.n_leaves] = ip->tail_base + ip->tail.layout.offset[i];
+    lay.size[lay.n_leaves] = ip->tail.layout.size[i];
+    lay.n_leaves++;
+  }
+  if (overflow) return ISDQN_E_TOO_LARGE;
+  lay.total = ip->tail_base + ip->tail.layout.total;
+  return ISDQN_OK;
+}
+
+// partial-sum scratch of one Stack's backward pass (offsets in floats); re-used stack after stack
+struct ImpalaPartials {
+  int64_t wpart[5];
+  int wsplits[5];
+  int64_t colsum[3];  // bias gradients of the convolutions without an activation: Conv_0, Conv_2, Conv_4
+  int colsum_ctas[3];
+  int64_t colpart[4];  // [ctas][3][C] of: relu behind Conv_1, LayerNorm_0, relu behind Conv_3, LayerNorm_1
+  int col_ctas;
+  int64_t total;
+};
+int colsum_ctas_for(int rows) {
+  int c = ceil_div(rows, 256);
+  if (c > 2 * kNumSMs) c = 2 * kNumSMs;
+  return c < 1 ? 1 : c;
+}
+void impala_partials(const ImpalaStack& S, int B, ImpalaPartials* o) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    const int64_t r = off;
+    off = align4(off + n);
+    return r;
+  };
+  const int rows_a = B * S.Hin * S.Win, rows = B * S.H * S.W;
+  for (int i = 0; i < 5; ++i) {
+    const int K = 9 * (i == 0 ? S.Cin : S.C);
+    o->wsplits[i] = conv_wgrad_splits(i == 0 ? rows_a : rows, K, S.C);
+    o->wpart[i] = take((int64_t)o->wsplits[i] * K * S.C);
+  }
+  for (int i = 0; i < 3; ++i) {
+    o->colsum_ctas[i] = colsum_ctas_for(i == 0 ? rows_a : rows);
+    o->colsum[i] = take((int64_t)o->colsum_ctas[i] * S.C);
+  }
+  o->col_ctas = ln_bwd_ctas(rows, S.C);
+  for (int i = 0; i < 4; ++i) o->colpart[i] = take((int64_t)o->col_ctas * 3 * S.C);
+  o->total = off;
+}
+
+struct ImpalaWs {  // offsets in floats; -1 = not allocated
+  int64_t x0;  // Conv_0 output of the stack being computed (dead after the pooling)
+  struct St {
+    int64_t widx;              // uint8 window index of the pooling maximum (training rows)
+    int64_t x[3];              // block inputs / outputs: x[0] = pooled, x[1] = after block 0, x[2] = stack output
+    int64_t t[2], u[2];        // relu(LN(x[j])), relu(Conv_{1+2j}(t[j]))
+    int64_t xhat[2], rstd[2];  // LayerNorm_j statistics of the training rows
+  } st[3];
+  int64_t tf, xhf, rsf;  // relu(LN_0(stack 2 output)) = tail input, and that LayerNorm's statistics
+  int64_t finpart;
+  int fin_ctas;
+  int64_t tail;  // the tail Plan's Workspace starts here
+  Workspace tailw;
+  int64_t G, T1, T2, G0, part;
+  int64_t total;
+};
+
+void carve_impala(const ImpalaPlan& ip, int rows, int B, ImpalaWs* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    const int64_t r = off;
+    off = align4(off + n);
+    return r;
+  };
+  int64_t max_x0 = 0, max_g = 0, max_g0 = 0, max_part = 0;
+  for (int s = 0; s < 3; ++s) {
+    const ImpalaStack& S = ip.st[s];
+    const int64_t a = (int64_t)S.Hin * S.Win * S.C, n = (int64_t)S.H * S.W * S.C;
+    if (rows * a > max_x0) max_x0 = rows * a;
+    if (B * n > max_g) max_g = B * n;
+    if (B * a > max_g0) max_g0 = B * a;
+    if (B > 0) {
+      ImpalaPartials P;
+      impala_partials(S, B, &P);
+      if (P.total > max_part) max_part = P.total;
+    }
+  }
+  w->x0 = take(max_x0);
+  for (int s = 0; s < 3; ++s) {
+    const ImpalaStack& S = ip.st[s];
+    const int64_t n = (int64_t)S.H * S.W * S.C;
+    ImpalaWs::St& O = w->st[s];
+    O.widx = B > 0 ? take((B * n + 3) / 4) : -1;
+    for (int j = 0; j < 3; ++j) O.x[j] = take(rows * n);
+    for (int j = 0; j < 2; ++j) {
+      O.t[j] = take(rows * n);
+      O.u[j] = take(rows * n);
+      O.xhat[j] = (B > 0 && ip.has_ln) ? take(B * n) : -1;
+      O.rstd[j] = (B > 0 && ip.has_ln) ? take((int64_t)B * S.H * S.W) : -1;
+    }
+  }
+  const ImpalaStack& L = ip.st[2];
+  w->tf = take((int64_t)rows * ip.flat);
+  w->xhf = (B > 0 && ip.has_ln) ? take((int64_t)B * ip.flat) : -1;
+  w->rsf = (B > 0 && ip.has_ln) ? take((int64_t)B * L.H * L.W) : -1;
+  carve_workspace(ip.tail, rows, B, &w->tailw);
+  w->tail = take(w->tailw.total);
+  if (B > 0) {
+    w->G = take(max_g);
+    w->T1 = take(max_g);
+    w->T2 = take(max_g);
+    w->G0 = take(max_g0);
+    w->part = take(max_part);
+    w->fin_ctas = ln_bwd_ctas(B * L.H * L.W, L.C);
+    w->finpart = take((int64_t)w->fin_ctas * 3 * L.C);
+  } else {
+    w->G = w->T1 = w->T2 = w->G0 = w->part = w->finpart = -1;
+    w->fin_ctas = 0;
+  }
+  w->total = off;
+}
+
+int impala_conv(const Layer& L, const void* in0, const void* in1, int n0, int rows, int kind, const float* w, const float* bias,
+                int relu, const float* residual, float* out, cudaStream_t s) {
+  ConvArgs a;
+  fill_conv_geom(L, &a);
+  a.in0 = in0; a.in1 = in1; a.n_img0 = n0;
+  a.M = rows * L.pix;
+  a.w = w; a.bias = bias; a.ln_g = nullptr; a.ln_b = nullptr; a.relu = relu;
+  a.out = out; a.xhat = nullptr; a.rstd = nullptr; a.m_train = 0;
+  a.residual = residual;
+  return launch_conv_fwd(a, kind, s);
+}
+
+int grid_for(int64_t n) {
+  int64_t g = ceil_div<int64_t>(n, 256);
+  if (g > 16 * kNumSMs) g = 16 * kNumSMs;
+  return g < 1 ? 1 : (int)g;
+}
+
+int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const float* params, const void* in0, const void* in1,
+                   int n0, int rows, int rows_train, int in_kind, cudaStream_t s) {
+  const float* prev = nullptr;
+  for (int si = 0; si < 3; ++si) {
+    const ImpalaStack& S = ip.st[si];
+    const ImpalaWs::St& O = w.st[si];
+    const Layer La = impala_conv_layer(S.Hin, S.Win, S.Cin, S.C);
+    const Layer Lb = impala_conv_layer(S.H, S.W, S.C, S.C);
+    float* x0 = wsp(ws, w.x0);
+    int rc = impala_conv(La, si == 0 ? in0 : prev, si == 0 ? in1 : nullptr, si == 0 ? n0 : rows, rows, si == 0 ? in_kind : IN_F32,
+                         params + S.w[0], params + S.b[0], 0, nullptr, x0, s);
+    if (rc) return rc;
+    ISDQN_PROF(s, "maxpool_fwd");
+    maxpool3s2_fwd_kernel<<<grid_for((int64_t)rows * S.H * S.W * S.C), 256, 0, s>>>(
+        x0, rows, S.Hin, S.Win, S.C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]),
+        reinterpret_cast<uint8_t*>(wsp(ws, O.widx)), rows_train > 0 ? rows_train : 0);
+    ISDQN_LAUNCH_CHECK();
+    const int prow = rows * S.H * S.W;
+    for (int j = 0; j < 2; ++j) {
+      ISDQN_PROF(s, "ln_relu_fwd");
+      ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, wsp(ws, O.x[j]), prow, S.C, ip.has_ln ? params + S.g[j] : nullptr,
+                                               ip.has_ln ? params + S.beta[j] : nullptr, wsp(ws, O.t[j]), wsp(ws, O.xhat[j]),
+                                               wsp(ws, O.rstd[j]), rows_train * S.H * S.W));
+      rc = impala_conv(Lb, wsp(ws, O.t[j]), nullptr, rows, rows, IN_F32, params + S.w[1 + 2 * j], params + S.b[1 + 2 * j], 1,
+                       nullptr, wsp(ws, O.u[j]), s);
+      if (rc) return rc;
+      rc = impala_conv(Lb, wsp(ws, O.u[j]), nullptr, rows, rows, IN_F32, params + S.w[2 + 2 * j], params + S.b[2 + 2 * j], 0,
+                       wsp(ws, O.x[j]), wsp(ws, O.x[j + 1]), s);
+      if (rc) return rc;
+    }
+    prev = wsp(ws, O.x[2]);
+  }
+  const ImpalaStack& L = ip.st[2];
+  ISDQN_PROF(s, "ln_relu_fwd");
+  ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, prev, rows * L.H * L.W, L.C, ip.has_ln ? params + ip.fin_g : nullptr,
+                                           ip.has_ln ? params + ip.fin_beta : nullptr, wsp(ws, w.tf), wsp(ws, w.xhf),
+                                           wsp(ws, w.rsf), rows_train * L.H * L.W));
+  return run_forward(ip.tail, w.tailw, wsp(ws, w.tail), params + ip.tail_base, wsp(ws, w.tf), nullptr, rows, rows, rows_train,
+                     IN_F32, s);
+}
+
+int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isdqn_train* tr, const isdqn_batch* b, int in_kind,
+                    cudaStream_t s) {
+  const int B = tr->batch;
+  const float* params = tr->d_params;
+  float* grads = tr->d_grads;
+  float *G = wsp(ws, w.G), *T1 = wsp(ws, w.T1), *T2 = wsp(ws, w.T2), *G0 = wsp(ws, w.G0), *pb = wsp(ws, w.part);
+  {  // Dense tail; its input gradient is dL/d relu(LN_0(x)) of the last stack
+    isdqn_train trt = *tr;
+    trt.d_params = tr->d_params + ip.tail_base;
+    trt.d_grads = tr->d_grads + ip.tail_base;
+    isdqn_batch bt = *b;
+    bt.d_state = wsp(ws, w.tf);
+    int rc = run_backward(ip.tail, w.tailw, wsp(ws, w.tail), &trt, &bt, IN_F32, s, G);
+    if (rc) return rc;
+  }
+  SegmentList segs;
+  segs.count = 0;
+  auto add_seg = [&](const float* src, float* dst, int64_t stride, int n, int parts) {
+    Segment& sg = segs.s[segs.count++];
+    sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts; sg.s2d_cout = 0;
+  };
+  // G (post-ReLU gradient) -> gradient of the LayerNorm input, in place; [1] / [2] of the column partials are the
+  // LayerNorm scale / bias gradients, [0] (sum of the result) the bias gradient of a convolution right below a ReLU
+  auto act_bwd = [&](float* d, const float* xhat, const float* rstd, int64_t g_off, int64_t beta_off, const float* act, int rows,
+                     int C, float* colpart, int ctas) -> int {
+    ISDQN_PROF(s, "ln_relu_bwd");
+    const bool ln = g_off >= 0;
+    ISDQN_CUDA_CHECK(launch_ln_relu_bwd_warp(ctas, s, d, ln ? xhat : nullptr, ln ? rstd : nullptr, ln ? params + g_off : nullptr,
+                                             ln ? params + beta_off : nullptr, act, rows, C, colpart, nullptr, nullptr));
+    if (ln) {
+      add_seg(colpart + C, grads + g_off, 3 * (int64_t)C, C, ctas);
+      add_seg(colpart + 2 * C, grads + beta_off, 3 * (int64_t)C, C, ctas);
+    }
+    return ISDQN_OK;
+  };
+  auto colsum = [&](const float* x, int rows, int C, float* part, int ctas, float* dst) -> int {
+    ISDQN_PROF(s, "colsum");
+    colsum_partials_kernel<<<ctas, 256, 0, s>>>(x, rows, C, part);
+    ISDQN_LAUNCH_CHECK();
+    add_seg(part, dst, C, C, ctas);
+    return ISDQN_OK;
+  };
+  {
+    const ImpalaStack& L = ip.st[2];
+    int rc = act_bwd(G, wsp(ws, w.xhf), wsp(ws, w.rsf), ip.fin_g, ip.fin_beta, wsp(ws, w.tf), B * L.H * L.W, L.C,
+                     wsp(ws, w.finpart), w.fin_ctas);
+    if (rc) return rc;
+  }
+  for (int si = 2; si >= 0; --si) {
+    const ImpalaStack& S = ip.st[si];
+    const ImpalaWs::St& O = w.st[si];
+    ImpalaPartials P;
+    impala_partials(S, B, &P);
+    const int rows = B * S.H * S.W, C = S.C;
+    const int64_t n = (int64_t)rows * C;
+    const Layer Lb = impala_conv_layer(S.H, S.W, C, C);
+    for (int j = 1; j >= 0; --j) {
+      const int cb = 1 + 2 * j, cc = 2 + 2 * j;
+      // G = dL/d(block output) = dL/d(Conv_cc output) (no activation) and, through the skip, part of dL/d(block input)
+      int rc = colsum(G, rows, C, pb + P.colsum[1 + j], P.colsum_ctas[1 + j], grads + S.b[cc]);
+      if (rc) return rc;
+      int sp = launch_conv_wgrad_f32(Lb, wsp(ws, O.u[j]), IN_F32, rows, G, pb + P.wpart[cc], P.wsplits[cc], s);
+      if (sp < 0) return -sp;
+      add_seg(pb + P.wpart[cc], grads + S.w[cc], (int64_t)9 * C * C, 9 * C * C, sp);
+      rc = launch_conv_dgrad_f32(Lb, B, G, params + S.w[cc], T1, s);
+      if (rc) return rc;
+      // through relu(Conv_cb(.)): T1 -> dL/d(Conv_cb output)
+      float* cp = pb + P.colpart[2 * j];
+      rc = act_bwd(T1, nullptr, nullptr, -1, -1, wsp(ws, O.u[j]), rows, C, cp, P.col_ctas);
+      if (rc) return rc;
+      add_seg(cp, grads + S.b[cb], 3 * (int64_t)C, C, P.col_ctas);
+      sp = launch_conv_wgrad_f32(Lb, wsp(ws, O.t[j]), IN_F32, rows, T1, pb + P.wpart[cb], P.wsplits[cb], s);
+      if (sp < 0) return -sp;
+      add_seg(pb + P.wpart[cb], grads + S.w[cb], (int64_t)9 * C * C, 9 * C * C, sp);
+      rc = launch_conv_dgrad_f32(Lb, B, T1, params + S.w[cb], T2, s);
+      if (rc) return rc;
+      // through relu(LN_j(.)): T2 -> dL/d(block input) along the convolution branch; the skip branch adds G
+      rc = act_bwd(T2, wsp(ws, O.xhat[j]), wsp(ws, O.rstd[j]), S.g[j], S.beta[j], wsp(ws, O.t[j]), rows, C,
+                   pb + P.colpart[2 * j + 1], P.col_ctas);
+      if (rc) return rc;
+      ISDQN_PROF(s, "residual_add");
+      add_inplace_kernel<<<grid_for(n), 256, 0, s>>>(G, T2, n);
+      ISDQN_LAUNCH_CHECK();
+    }
+    ISDQN_PROF(s, "maxpool_bwd");
+    maxpool3s2_bwd_kernel<<<grid_for((int64_t)B * S.Hin * S.Win * C), 256, 0, s>>>(
+        G, reinterpret_cast<const uint8_t*>(wsp(ws, O.widx)), B, S.Hin, S.Win, C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, G0);
+    ISDQN_LAUNCH_CHECK();
+    const Layer La = impala_conv_layer(S.Hin, S.Win, S.Cin, C);
+    const int rows_a = B * S.Hin * S.Win;
+    int rc = colsum(G0, rows_a, C, pb + P.colsum[0], P.colsum_ctas[0], grads + S.b[0]);
+    if (rc) return rc;
+    const void* in = si == 0 ? b->d_state : static_cast<const void*>(wsp(ws, w.st[si - 1].x[2]));
+    const int sp = launch_conv_wgrad_f32(La, in, si == 0 ? in_kind : IN_F32, rows_a, G0, pb + P.wpart[0], P.wsplits[0], s);
+    if (sp < 0) return -sp;
+    add_seg(pb + P.wpart[0], grads + S.w[0], (int64_t)9 * S.Cin * C, 9 * S.Cin * C, sp);
+    if (si > 0) {
+      rc = launch_conv_dgrad_f32(La, B, G0, params + S.w[0], G, s);
+      if (rc) return rc;
+    }
+    // this stack's partials are folded before the next stack re-uses the scratch
+    ISDQN_PROF(s, "reduce_segments");
+    ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s));
+    segs.count = 0;
+  }
+  return ISDQN_OK;
+}
+
+int impala_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update, float* q_out,
+                 void* stream) {
+  if (!tr || !b) return ISDQN_E_INVALID;
+  if (tr->compute_dtype != ISDQN_COMPUTE_F32) return ISDQN_E_UNSUPPORTED;  // the tensor-core path covers `cnn`
+  ImpalaPlan ip;
+  int rc = build_impala_plan(net, &ip);
+  if (rc) return rc;
+  if (!tr->d_params || !tr->d_losses || !tr->d_workspace || tr->batch < 1 || tr->batch_global < tr->batch) return ISDQN_E_INVALID;
+  if (!b->d_state || !b->d_next_state || !b->d_action || !b->d_reward || !b->d_terminal) return ISDQN_E_INVALID;
+  if (backward && !tr->d_grads) return ISDQN_E_INVALID;
+  if (update && (!tr->d_mu || !tr->d_nu || !tr->d_count)) return ISDQN_E_INVALID;
+  const int B = tr->batch;
+  ImpalaWs w;
+  carve_impala(ip, 2 * B, B, &w);
+  if (w.total * (int64_t)sizeof(float) > tr->workspace_bytes) return ISDQN_E_INVALID;
+  cudaStream_t s = as_stream(stream);
+  void* ws = tr->d_workspace;
+  rc = impala_forward(ip, w, ws, tr->d_params, b->d_state, b->d_next_state, B, 2 * B, backward ? B : 0, IN_U8_255, s);
+  if (rc) return rc;
+  void* tws = wsp(ws, w.tail);
+  const Layer& last = ip.tail.L[ip.tail.n_layers - 1];
+  const float* q_all = wsp(tws, w.tailw.act[ip.tail.n_layers - 1]);
+  rc = run_loss(ip.tail, net, tr, b, q_all, backward ? wsp(tws, w.tailw.dq) : nullptr,
+                backward ? tr->d_grads + ip.tail_base + last.b_off : nullptr, update ? tr->d_count : nullptr, s);
+  if (rc) return rc;
+  if (q_out)
+    ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * 2 * (size_t)B * ip.tail.n_out, cudaMemcpyDeviceToDevice, s));
+  if (!backward) return ISDQN_OK;
+  rc = impala_backward(ip, w, ws, tr, b, IN_U8_255, s);
+  if (rc) return rc;
+  if (!update) return ISDQN_OK;
+  if (tr->nccl_comm) {
+    ISDQN_PROF(s, "nccl_allreduce");
+    rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, ip.layout.total, stream);
+    if (rc) return rc;
+  }
+  return isdqn_adam_step_nocount(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
+                                 ip.layout.total, stream);
+}
+
+// forward only (isdqn_forward / isdqn_best_action); returns the device pointer of q [rows][n_out] through q_dev
+int impala_infer(const isdqn_net* net, const float* d_params, const void* d_input, int input_is_float, int rows, void* d_workspace,
+                 int64_t workspace_bytes, const float** q_dev, int* n_out, cudaStream_t s) {
+  ImpalaPlan ip;
+  int rc = build_impala_plan(net, &ip);
+  if (rc) return rc;
+  if (!d_params || !d_input || !d_workspace || rows < 1) return ISDQN_E_INVALID;
+  ImpalaWs w;
+  carve_impala(ip, rows, 0, &w);
+  if (w.total * (int64_t)sizeof(float) > workspace_bytes) return ISDQN_E_INVALID;
+  rc = impala_forward(ip, w, d_workspace, d_params, d_input, nullptr, rows, rows, 0, input_is_float ? IN_F32_255 : IN_U8_255, s);
+  if (rc) return rc;
+  *q_dev = wsp(wsp(d_workspace, w.tail), w.tailw.act[ip.tail.n_layers - 1]);
+  *n_out = ip.tail.n_out;
+  return ISDQN_OK;
+}
+
 int train_common(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update,
                  float* q_out, void* stream) {
+  if (net && net->arch == ISDQN_ARCH_IMPALA) return impala_train(net, tr, b, backward, update, q_out, stream);
   if (tr && tr->compute_dtype == ISDQN_COMPUTE_BF16) return isdqn_tc_train_dispatch(net, tr, b, backward, update, q_out, stream);
   Plan p;
   int rc = check_common(net, &p);
@@ -300,6 +744,13 @@ int train_common(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch*
 
 extern "C" int isdqn_net_layout(const isdqn_net* net, isdqn_layout* out) {
   if (!out) return ISDQN_E_INVALID;
+  if (net && net->arch == ISDQN_ARCH_IMPALA) {
+    ImpalaPlan ip;
+    const int rci = build_impala_plan(net, &ip);
+    if (rci) return rci;
+    *out = ip.layout;
+    return ISDQN_OK;
+  }
   Plan p;
   int rc = build_plan(net, &p);
   if (rc) return rc;
@@ -308,6 +759,13 @@ extern "C" int isdqn_net_layout(const isdqn_net* net, isdqn_layout* out) {
 }
 
 extern "C" int64_t isdqn_forward_workspace_bytes(const isdqn_net* net, int32_t n_rows) {
+  if (net && net->arch == ISDQN_ARCH_IMPALA) {
+    ImpalaPlan ip;
+    if (build_impala_plan(net, &ip) || n_rows < 1) return -1;
+    ImpalaWs w;
+    carve_impala(ip, n_rows, 0, &w);
+    return w.total * (int64_t)sizeof(float);
+  }
   Plan p;
   if (build_plan(net, &p) || n_rows < 1) return -1;
   Workspace w;
@@ -316,6 +774,13 @@ extern "C" int64_t isdqn_forward_workspace_bytes(const isdqn_net* net, int32_t n
 }
 
 extern "C" int64_t isdqn_learn_workspace_bytes(const isdqn_net* net, int32_t batch) {
+  if (net && net->arch == ISDQN_ARCH_IMPALA) {
+    ImpalaPlan ip;
+    if (build_impala_plan(net, &ip) || batch < 1) return -1;
+    ImpalaWs w;
+    carve_impala(ip, 2 * batch, batch, &w);
+    return w.total * (int64_t)sizeof(float);
+  }
   Plan p;
   if (build_plan(net, &p) || batch < 1) return -1;
   Workspace w;
@@ -325,6 +790,16 @@ extern "C" int64_t isdqn_learn_workspace_bytes(const isdqn_net* net, int32_t bat
 
 extern "C" int isdqn_forward(const isdqn_net* net, const float* d_params, const void* d_input, int32_t input_is_float,
                              int32_t n_rows, float* d_q, void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (net && net->arch == ISDQN_ARCH_IMPALA) {
+    if (!d_q) return ISDQN_E_INVALID;
+    const float* q = nullptr;
+    int n_out = 0;
+    const int rci = impala_infer(net, d_params, d_input, input_is_float, n_rows, d_workspace, workspace_bytes, &q, &n_out,
+                                 as_stream(stream));
+    if (rci) return rci;
+    ISDQN_CUDA_CHECK(cudaMemcpyAsync(d_q, q, sizeof(float) * (size_t)n_rows * n_out, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return ISDQN_OK;
+  }
   Plan p;
   int rc = check_common(net, &p);
   if (rc) return rc;
@@ -471,6 +946,16 @@ extern "C" int isdqn_learn_on_batch(const isdqn_net* net, const isdqn_train* tr,
 extern "C" int isdqn_best_action(const isdqn_net* net, const float* d_params, const void* d_state, int32_t input_is_float,
                                  int32_t idx_network, int32_t* d_action, void* d_workspace, int64_t workspace_bytes,
                                  void* stream) {
+  if (net && net->arch == ISDQN_ARCH_IMPALA) {
+    if (!d_action || idx_network < 0 || idx_network >= net->n_heads) return ISDQN_E_INVALID;
+    const float* q = nullptr;
+    int n_out = 0;
+    const int rci = impala_infer(net, d_params, d_state, input_is_float, 1, d_workspace, workspace_bytes, &q, &n_out, as_stream(stream));
+    if (rci) return rci;
+    argmax_head_kernel<<<1, 32, 0, as_stream(stream)>>>(q, net->n_actions, 1 + idx_network, d_action);
+    ISDQN_LAUNCH_CHECK();
+    return ISDQN_OK;
+  }
   Plan p;
   int rc = check_common(net, &p);
   if (rc) return rc;

@@ -74,6 +74,7 @@ struct ConvArgs {
   float* xhat;  // [m_train][Cout] or null
   float* rstd;  // [m_train] or null
   int m_train;
+  const float* residual = nullptr;  // [M][Cout] added to conv + bias (impala block output, dqn.py:34); only without LayerNorm
 };
 
 // ----------------------------------------------------------------------------------------------- conv fwd
@@ -185,6 +186,11 @@ __global__ void __launch_bounds__(kGemmThreads) conv_fwd_kernel(const ConvArgs a
     } else {
 #pragma unroll
       for (int j = 0; j < TN; ++j) y[j] = z[j];
+      if (a.residual != nullptr && m < a.M) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+          if (tx * TN + j < a.Cout) y[j] += a.residual[(int64_t)m * a.Cout + tx * TN + j];
+      }
     }
     if (m < a.M) {
       const bool save = a.xhat != nullptr && a.ln_g != nullptr && m < a.m_train;

@@ -1,10 +1,13 @@
-"""`DQNNet` on the device — mirrors `slimdqn/networks/architectures/dqn.py:39-103` (architecture_type `cnn` and
-`fc`, optional LayerNorm).  `impala` and `batch_norm` are out of scope and raise.
+"""`DQNNet` on the device — mirrors `slimdqn/networks/architectures/dqn.py:7-103` (architecture_type `cnn`, `fc`
+and `impala` — the latter on the fp32 path only —, optional LayerNorm).  `batch_norm` is out of scope
+and raises.
 
 Parameters live in ONE flat float32 CUDA vector (leaves packed in execution order, 16-byte aligned; layout from
 `isdqn_net_layout`); the flax-shaped pytree `{"params": {"Conv_0": {"kernel", "bias"}, "LayerNorm_0": {"scale",
 "bias"}, ..., "Dense_1": {...}}}` the reference exposes is a tree of VIEWS into that vector, so
-`params["params"]["Dense_1"]["kernel"]` reads and writes the memory the kernels use.
+`params["params"]["Dense_1"]["kernel"]` reads and writes the memory the kernels use.  impala nests one level more
+(`params["params"]["Stack_0"]["Conv_1"]["kernel"]`, flax's naming of the `Stack` sub-module); in the leaf list such a
+module is written as the path "Stack_0/Conv_1".
 """
 from __future__ import annotations
 
@@ -35,10 +38,27 @@ def leaf_specs(arch: str, obs_dim: Sequence[int], features: Sequence[int], n_out
                 ln += 1
             h, w, c = _same_out(h, s), _same_out(w, s), int(features[i])
         fan_in, start = h * w * c, 3
+    elif arch == "impala":
+        # Stack (dqn.py:7-36): Conv_0, max_pool, 2 x [LayerNorm_j, relu, Conv_{1+2j}, relu, Conv_{2+2j}, + skip]; the
+        # DQNNet's own LayerNorm_0 follows the three stacks (dqn.py:84-86)
+        h, w, c = obs_dim
+        for s in range(3):
+            f = int(features[s])
+            out += [(f"Stack_{s}/Conv_0", "kernel", (3, 3, c, f)), (f"Stack_{s}/Conv_0", "bias", (f,))]
+            for j in range(2):
+                if layer_norm:
+                    out += [(f"Stack_{s}/LayerNorm_{j}", "scale", (f,)), (f"Stack_{s}/LayerNorm_{j}", "bias", (f,))]
+                for q in (1 + 2 * j, 2 + 2 * j):
+                    out += [(f"Stack_{s}/Conv_{q}", "kernel", (3, 3, f, f)), (f"Stack_{s}/Conv_{q}", "bias", (f,))]
+            h, w, c = _same_out(h, 2), _same_out(w, 2), f
+        if layer_norm:
+            out += [("LayerNorm_0", "scale", (c,)), ("LayerNorm_0", "bias", (c,))]
+            ln = 1
+        fan_in, start = h * w * c, 3
     elif arch == "fc":
         fan_in, start = int(np.prod(obs_dim)), 0
     else:
-        raise NotImplementedError(f"architecture_type {arch!r} is out of scope for isdqn_b200 (cnn, fc only)")
+        raise NotImplementedError(f"architecture_type {arch!r} is not a DQNNet architecture (cnn, impala, fc)")
     d = 0
     for i in range(start, len(features)):
         f = int(features[i])
@@ -49,6 +69,20 @@ def leaf_specs(arch: str, obs_dim: Sequence[int], features: Sequence[int], n_out
         fan_in, d = f, d + 1
     out += [(f"Dense_{d}", "kernel", (fan_in, n_out)), (f"Dense_{d}", "bias", (n_out,))]
     return out
+
+
+def truncated_standard_normal(g: np.random.Generator, shape) -> np.ndarray:
+    """jax.random.truncated_normal(key, -2, 2): draws of N(0, 1) conditioned on |x| <= 2 (rejection sampling — clipping
+    would pile 4.6 % of the mass onto the two bounds)."""
+    n = int(np.prod(shape))
+    out = np.empty(n)
+    have = 0
+    while have < n:
+        v = g.standard_normal(max(int((n - have) * 1.1) + 16, 16))
+        v = v[np.abs(v) <= 2.0][: n - have]
+        out[have : have + v.size] = v
+        have += v.size
+    return out.reshape(shape)
 
 
 class _LeafDict(dict):
@@ -85,7 +119,14 @@ class ParamTree(dict):
 
     def leaves(self):
         for mod, leaf, _ in self.specs:
-            yield mod, leaf, self["params"][mod][leaf]
+            yield mod, leaf, module_at(self["params"], mod)[leaf]
+
+
+def module_at(inner: dict, mod: str) -> dict:
+    """The module dict at the path `mod` ("Dense_0", or "Stack_1/Conv_2" for a nested flax sub-module)."""
+    for part in mod.split("/"):
+        inner = inner[part]
+    return inner
 
 
 def build_tree(flat, specs, offsets) -> ParamTree:
@@ -93,7 +134,11 @@ def build_tree(flat, specs, offsets) -> ParamTree:
     inner = {}
     for (mod, leaf, shape), off in zip(specs, offsets):
         n = int(np.prod(shape))
-        d = inner.setdefault(mod, _LeafDict())
+        *parents, name = mod.split("/")
+        node = inner
+        for part in parents:
+            node = node.setdefault(part, {})
+        d = node.setdefault(name, _LeafDict())
         d.owner = tree
         dict.__setitem__(d, leaf, flat[off : off + n].view(shape))
     tree["params"] = inner
@@ -106,8 +151,8 @@ class DQNNet:
     def __init__(self, features: Sequence[int], architecture_type: str, final_feature: int, layer_norm: bool = False, batch_norm: bool = False):
         if batch_norm:
             raise NotImplementedError("batch_norm=True is out of scope for isdqn_b200 (SURVEY.md §2: needs cross-replica statistics)")
-        if architecture_type not in ("cnn", "fc"):
-            raise NotImplementedError(f"architecture_type {architecture_type!r} is out of scope for isdqn_b200 (cnn, fc only)")
+        if architecture_type not in ("cnn", "fc", "impala"):
+            raise NotImplementedError(f"architecture_type {architecture_type!r} is not a DQNNet architecture (cnn, impala, fc)")
         self.features = [int(f) for f in features]
         self.architecture_type = architecture_type
         self.final_feature = int(final_feature)
@@ -118,17 +163,22 @@ class DQNNet:
         self._specs = None
         self._ws = {}
 
+    @property
+    def image_input(self) -> bool:
+        """uint8 (H, W, C) frames, normalised by 255 inside the network (dqn.py:51, 80)"""
+        return self.architecture_type in ("cnn", "impala")
+
     # ------------------------------------------------------------------------------------------------ layout
     def configure(self, observation_dim, n_heads: int, n_actions: int) -> None:
         """Fixes the input shape (flax does this lazily in `init`) and queries the native parameter layout."""
         lib = _lib.load()
         obs = tuple(int(x) for x in observation_dim)
         net = _lib.Net()
-        net.arch = _lib.ARCH_CNN if self.architecture_type == "cnn" else _lib.ARCH_FC
+        net.arch = {"cnn": _lib.ARCH_CNN, "fc": _lib.ARCH_FC, "impala": _lib.ARCH_IMPALA}[self.architecture_type]
         net.layer_norm = 1 if self.layer_norm else 0
-        if self.architecture_type == "cnn":
+        if self.image_input:
             if len(obs) != 3:
-                raise ValueError(f"cnn expects (H, W, C) observations, got {obs}")
+                raise ValueError(f"{self.architecture_type} expects (H, W, C) observations, got {obs}")
             net.obs_h, net.obs_w, net.obs_c = obs
         else:
             net.obs_h, net.obs_w, net.obs_c = 1, 1, int(np.prod(obs))
@@ -157,9 +207,11 @@ class DQNNet:
         return build_tree(flat, self._specs, self._offsets)
 
     def init(self, key, x=None) -> ParamTree:
-        """Flax-equivalent initialisers (xavier_uniform for cnn incl. its Dense tail, lecun_normal for fc; zero
-        biases, unit LayerNorm scales — dqn.py:49,90).  The random stream is NumPy's, not JAX's threefry: initial
-        VALUES differ from the reference's for the same key (outside the parity contract)."""
+        """Flax-equivalent initialisers (xavier_uniform for cnn / impala incl. their Dense tails, lecun_normal — a
+        normal truncated at two standard deviations — for fc and for the convolutions inside an impala residual block,
+        which keep flax's default kernel_init, dqn.py:32-33; zero biases, unit LayerNorm scales — dqn.py:16,49,78,90).
+        The random stream is NumPy's, not JAX's threefry: initial VALUES differ from the reference's for the same key
+        (outside the parity contract)."""
         torch = _lib.require_cuda()
         seed = np.random.SeedSequence(np.frombuffer(np.asarray(key).tobytes(), dtype=np.uint8).tolist() or [0])
         g = np.random.default_rng(seed)
@@ -170,12 +222,13 @@ class DQNNet:
             if leaf == "kernel":
                 rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
                 fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
-                if self.architecture_type == "cnn":
+                block_conv = "/" in mod and mod.rsplit("/", 1)[1] != "Conv_0" and mod.rsplit("/", 1)[1].startswith("Conv_")
+                if self.architecture_type != "fc" and not block_conv:
                     lim = math.sqrt(6.0 / (fan_in + fan_out))
                     v = g.uniform(-lim, lim, shape)
                 else:
                     std = math.sqrt(1.0 / fan_in) / 0.87962566103423978
-                    v = np.clip(g.standard_normal(shape), -2.0, 2.0) * std
+                    v = truncated_standard_normal(g, shape) * std
             elif leaf == "scale":
                 v = np.ones(shape)
             else:
@@ -208,7 +261,7 @@ class DQNNet:
             t = t.unsqueeze(0)
         if tuple(t.shape[1:]) != tuple(self.observation_dim):
             raise ValueError(f"input shape {tuple(t.shape)} does not match observation_dim {self.observation_dim}")
-        if self.architecture_type == "cnn" and t.dtype == torch.uint8:
+        if self.image_input and t.dtype == torch.uint8:
             is_float = 0
         else:
             t = t.to(torch.float32)

@@ -163,7 +163,7 @@ class iSDQN:
         t = self._torch
         net = self.network
         ctx = {}
-        if net.architecture_type == "cnn":
+        if net.image_input:
             shape, dt = (B,) + tuple(net.observation_dim), t.uint8
         else:
             shape, dt = (B,) + tuple(net.observation_dim), t.float32
@@ -293,8 +293,8 @@ class iSDQN:
         slot = st["slot"]
         st["slot"] = slot ^ 1
         arrays = [np.asarray(fields[k]) for k in _lib.BATCH_FIELDS]
-        if self.network.architecture_type == "cnn" and (arrays[0].dtype != np.uint8 or arrays[1].dtype != np.uint8):
-            raise TypeError("cnn batches must be uint8 frames (float states: use loss_on_batch / apply)")
+        if self.network.image_input and (arrays[0].dtype != np.uint8 or arrays[1].dtype != np.uint8):
+            raise TypeError("cnn / impala batches must be uint8 frames (float states: use loss_on_batch / apply)")
         h_src = _lib.pinned_pack_base(arrays, ctx["pack_offs"])
         if h_src is None:
             # pageable (or differently laid out) arrays: through this slot's pinned block, once its last copy has left
@@ -367,7 +367,7 @@ class iSDQN:
     # ------------------------------------------------------------------------------------------------ update
     def update_online_params(self, step: int, replay_buffer):
         if step % self.data_to_update == 0:
-            device_rb = hasattr(replay_buffer, "sample_device") and self.network.architecture_type == "cnn"
+            device_rb = hasattr(replay_buffer, "sample_device") and self.network.image_input
             sd = getattr(replay_buffer, "_sampling_distribution", None)
             if device_rb and self.prioritized_beta is not None and hasattr(sd, "update_device"):
                 # prioritized training driver (new: the reference never wires its prioritized sampler to an agent,
@@ -572,7 +572,7 @@ class iSDQN:
         state, _, is_float = net.prepare_input(samples.state)
         next_state, _, _ = net.prepare_input(samples.next_state)
         B = int(state.shape[0])
-        if net.architecture_type == "cnn" and is_float:
+        if net.image_input and is_float:
             # float states (tests/utils.py generator): forward through the float entry point, then the loss kernel
             all_q, _ = net.apply_fn(params, t.cat((state, next_state)))
             all_q = all_q.reshape(2 * B, -1).contiguous()
@@ -773,7 +773,7 @@ class iSDQN:
         net = self.network
         if not isinstance(state, t.Tensor):
             obs = np.asarray(state)
-            want = np.uint8 if net.architecture_type == "cnn" else np.float32
+            want = np.uint8 if net.image_input else np.float32
             if obs.dtype == want and obs.size == int(np.prod(net.observation_dim)) and self._nccl_comm is None:
                 # host observation of the stored dtype: the graph-replayed path; a host int32 (`.item()` works on it)
                 return np.int32(self._greedy_actions_fast(params, obs)[1 + int(idx_network)])
@@ -799,11 +799,11 @@ class iSDQN:
 
     def get_model(self):
         """isdqn.py:137-138: `{"params": params}` with host numpy leaves (pickle-able, flax-shaped)."""
+        def host(node):
+            return {k: host(v) if isinstance(v, dict) else v.detach().cpu().numpy() for k, v in node.items()}
+
         return {
             "params": {
-                "params": {
-                    mod: {leaf: v.detach().cpu().numpy() for leaf, v in leaves.items()}
-                    for mod, leaves in self.params["params"].items()
-                }
+                "params": host(self.params["params"])
             }
         }

@@ -8,6 +8,9 @@ The restatement follows the published semantics of those pinned versions (SURVEY
   forward      slimdqn/networks/architectures/dqn.py:47-103  (cnn: x/255, Conv SAME + bias, LayerNorm over
                the channel axis eps=1e-6 with the fast variance E[x^2]-E[x]^2 clamped at 0, ReLU, HWC
                flatten, Dense+LN+ReLU, Dense; fc: Dense(+LN)+ReLU ..., Dense)
+               dqn.py:7-36, 77-86  (impala: 3 x Stack = Conv3x3, max_pool 3x3/2 SAME (-inf padding), 2 x residual
+               block [LN, ReLU, Conv3x3, ReLU, Conv3x3, + skip]; LN, ReLU, HWC flatten, Dense tail.  Modules of a
+               Stack are keyed by their path, "Stack_0/Conv_1")
   apply_fn     slimdqn/networks/isdqn.py:39-41   reshape to (N, 1+K, A)
   loss         isdqn.py:92-103   sum_k mean_b (Q_k(s,a) - stopgrad(r + (1-d) gamma^n max_a' Q_{k-1}(s',a')))^2
   target       isdqn.py:105-109  evaluation order r + (((1-d) * gamma^n) * max)
@@ -54,6 +57,21 @@ def param_shapes(arch: str, obs_dim: Sequence[int], features: Sequence[int], n_o
                 ln += 1
             h, w, c = same_padding(h, k, s)[0], same_padding(w, k, s)[0], features[i]
         fan_in, start = h * w * c, 3
+    elif arch == "impala":
+        h, w, c = obs_dim
+        for st in range(3):
+            f = features[st]
+            out += [(f"Stack_{st}/Conv_0", "kernel", (3, 3, c, f)), (f"Stack_{st}/Conv_0", "bias", (f,))]
+            for j in range(2):
+                if layer_norm:
+                    out += [(f"Stack_{st}/LayerNorm_{j}", "scale", (f,)), (f"Stack_{st}/LayerNorm_{j}", "bias", (f,))]
+                for q in (1 + 2 * j, 2 + 2 * j):
+                    out += [(f"Stack_{st}/Conv_{q}", "kernel", (3, 3, f, f)), (f"Stack_{st}/Conv_{q}", "bias", (f,))]
+            h, w, c = same_padding(h, 3, 2)[0], same_padding(w, 3, 2)[0], f
+        if layer_norm:
+            out += [("LayerNorm_0", "scale", (c,)), ("LayerNorm_0", "bias", (c,))]
+            ln = 1
+        fan_in, start = h * w * c, 3
     elif arch == "fc":
         fan_in, start = int(np.prod(obs_dim)), 0
     else:
@@ -78,7 +96,8 @@ def init_params(seed: int, arch: str, obs_dim, features, n_out: int, layer_norm:
         if leaf == "kernel":
             rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
             fi, fo = shape[-2] * rf, shape[-1] * rf
-            if arch == "cnn":
+            block_conv = "/" in mod and not mod.endswith("/Conv_0")  # flax's default lecun_normal (dqn.py:32-33)
+            if arch != "fc" and not block_conv:
                 lim = math.sqrt(6.0 / (fi + fo))
                 v = g.uniform(-lim, lim, shape)
             else:
@@ -157,6 +176,38 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
                 taps.append(x)
             x = rnd(torch.relu(x))
         x = x.reshape(x.shape[0], -1)
+    elif arch == "impala":
+        def conv3(x, mod):  # nn.Conv(features, (3, 3)): stride 1, padding SAME = 1 on every side
+            w = params[mod]["kernel"]
+            y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
+            return (y + params[mod]["bias"].view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+
+        x = x.to(dtype) / 255.0
+        for st in range(3):
+            x = conv3(x, f"Stack_{st}/Conv_0")
+            _, plo_h, phi_h = same_padding(x.shape[1], 3, 2)
+            _, plo_w, phi_w = same_padding(x.shape[2], 3, 2)
+            xp = F.pad(x.permute(0, 3, 1, 2), (plo_w, phi_w, plo_h, phi_h), value=float("-inf"))
+            x = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
+            for j in range(2):
+                block_input = x
+                if layer_norm:
+                    m = params[f"Stack_{st}/LayerNorm_{j}"]
+                    x = layer_norm_lastdim(x, m["scale"], m["bias"])
+                if taps is not None:
+                    taps.append(x)
+                x = torch.relu(x)
+                x = conv3(x, f"Stack_{st}/Conv_{1 + 2 * j}")
+                if taps is not None:
+                    taps.append(x)
+                x = torch.relu(x)
+                x = conv3(x, f"Stack_{st}/Conv_{2 + 2 * j}") + block_input
+        if layer_norm:
+            x = layer_norm_lastdim(x, params["LayerNorm_0"]["scale"], params["LayerNorm_0"]["bias"])
+            ln = 1
+        if taps is not None:
+            taps.append(x)
+        x = torch.relu(x).reshape(x.shape[0], -1)
     else:
         x = x.to(dtype)
     n_dense = sum(1 for m in params if m.startswith("Dense_"))
@@ -265,7 +316,7 @@ def relu_margin(params: Params, state: torch.Tensor, arch: str, layer_norm: bool
 def make_batch(seed: int, B: int, obs_dim, A: int, arch: str, p_terminal: float = 0.2):
     """Synthetic batch in the dtypes `rb.sample()` returns (u8 stacks, i64 action, f64 reward, bool terminal)."""
     g = np.random.default_rng(seed)
-    if arch == "cnn":
+    if arch in ("cnn", "impala"):
         s = g.integers(0, 256, (B,) + tuple(obs_dim), dtype=np.uint8)
         s2 = g.integers(0, 256, (B,) + tuple(obs_dim), dtype=np.uint8)
     else:

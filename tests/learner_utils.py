@@ -34,13 +34,19 @@ def oracle_params_for(agent, seed, randomize=True, dtype=torch.float64):
 
 def push_params(agent, oracle_params, tree=None):
     tree = tree if tree is not None else agent.params
+    from isdqn_b200.networks.architectures.dqn import module_at
+
     for mod, leaves in oracle_params.items():
         for leaf, v in leaves.items():
-            tree["params"][mod][leaf] = v.detach().to(torch.float32).numpy()
+            module_at(tree["params"], mod)[leaf] = v.detach().to(torch.float32).numpy()
 
 
 def tree_to_numpy(tree):
-    return {m: {k: v.detach().cpu().numpy().astype(np.float64) for k, v in lv.items()} for m, lv in tree["params"].items()}
+    """{module path: {leaf: float64 ndarray}} (impala's nested modules come back under "Stack_0/Conv_1")"""
+    out = {}
+    for mod, leaf, v in tree.leaves():
+        out.setdefault(mod, {})[leaf] = v.detach().cpu().numpy().astype(np.float64)
+    return out
 
 
 def batch_as_element(batch):

@@ -57,7 +57,27 @@ def test_out_of_scope_configurations_raise():
     with pytest.raises(NotImplementedError):
         DQNNet([32, 64, 64, 512], "cnn", 90, layer_norm=True, batch_norm=True)
     with pytest.raises(NotImplementedError):
-        DQNNet([32, 64, 64, 512], "impala", 90)
+        DQNNet([32, 64, 64, 512], "resnet", 90)
+
+
+@pytest.mark.parametrize("layer_norm", [True, False])
+def test_impala_layout_matches_the_flax_leaf_list(layer_norm):
+    """host-only: the native layout of `impala` (isdqn_net_layout) against the flax-named leaf list, Stack by Stack"""
+    from isdqn_b200.networks.architectures.dqn import DQNNet, leaf_specs
+
+    net = DQNNet([16, 32, 32, 256], "impala", 5 * 6, layer_norm=layer_norm)
+    net.configure((84, 84, 4), 4, 6)
+    specs = leaf_specs("impala", (84, 84, 4), [16, 32, 32, 256], 30, layer_norm)
+    assert net._layout.n_leaves == len(specs) == (50 if layer_norm else 34)
+    names = [m for m, _, _ in specs]
+    assert names[0] == "Stack_0/Conv_0" and "Stack_2/Conv_4" in names and names[-1] == "Dense_1"
+    assert ("LayerNorm_0" in names) == layer_norm and ("Stack_1/LayerNorm_1" in names) == layer_norm
+    # 84 -> 42 -> 21 -> 11 through the three poolings: the Dense tail sees 11 * 11 * 32 features
+    dense0 = [s for m, l, s in specs if m == "Dense_0" and l == "kernel"][0]
+    assert dense0 == (11 * 11 * 32, 256)
+    offs = [int(net._layout.offset[i]) for i in range(net._layout.n_leaves)]
+    assert offs == sorted(offs) and all(o % 8 == 0 for o in offs)
+    assert int(net._layout.total) >= offs[-1] + 30
 
 
 def test_no_cpu_fallback():

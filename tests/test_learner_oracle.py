@@ -210,3 +210,87 @@ def test_same_padded_conv_matches_an_unfold_matmul():
         assert z.shape == taps[i].shape
         assert torch.allclose(z, taps[i], rtol=1e-10, atol=1e-12), i
         act = torch.relu(z)
+
+
+# ------------------------------------------------------------------------------------------------------ impala
+def _impala_cfg():
+    return dict(obs_dim=(21, 18, 3), features=[5, 7, 6, 11], K=2, A=3)
+
+
+def test_impala_oracle_max_pool_is_same_padded_with_minus_infinity():
+    """the pooling of the impala oracle against a brute-force window maximum written with its own index arithmetic
+    (flax nn.max_pool padding='SAME': out = ceil(in / 2), pad_lo = total // 2, padded cells never win)"""
+    import torch.nn.functional as F
+
+    g = np.random.default_rng(3)
+    for H, W in ((84, 84), (42, 42), (21, 21), (37, 50), (5, 4)):
+        x = torch.from_numpy(g.standard_normal((2, H, W, 3))) - 5.0  # all negative: a zero-padded pooling would show
+        _, lo_h, hi_h = L.same_padding(H, 3, 2)
+        _, lo_w, hi_w = L.same_padding(W, 3, 2)
+        xp = F.pad(x.permute(0, 3, 1, 2), (lo_w, hi_w, lo_h, hi_h), value=float("-inf"))
+        got = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1).numpy()
+        OH, OW = -(-H // 2), -(-W // 2)
+        assert got.shape == (2, OH, OW, 3)
+        ph = max((OH - 1) * 2 + 3 - H, 0) // 2
+        pw = max((OW - 1) * 2 + 3 - W, 0) // 2
+        xn = x.numpy()
+        for oy in range(OH):
+            for ox in range(OW):
+                ys = [y for y in range(oy * 2 - ph, oy * 2 - ph + 3) if 0 <= y < H]
+                xs = [c for c in range(ox * 2 - pw, ox * 2 - pw + 3) if 0 <= c < W]
+                want = xn[:, ys][:, :, xs].max(axis=(1, 2))
+                np.testing.assert_array_equal(got[:, oy, ox], want)
+
+
+def test_impala_oracle_structure_and_gradient():
+    c = _impala_cfg()
+    shapes = L.param_shapes("impala", c["obs_dim"], c["features"], (1 + c["K"]) * c["A"], True)
+    names = [m for m, _, _ in shapes]
+    # flax auto-names: five convolutions and two LayerNorms per Stack, the DQNNet's LayerNorm_0, then the Dense tail
+    assert names.count("Stack_1/Conv_4") == 2 and names.count("Stack_2/LayerNorm_1") == 2 and "LayerNorm_0" in names
+    assert [s for m, l, s in shapes if m == "Dense_0" and l == "kernel"][0] == (3 * 3 * 6, 11)  # 21x18 -> 11x9 -> 6x5 -> 3x3
+    p = L.init_params(5, "impala", c["obs_dim"], c["features"], (1 + c["K"]) * c["A"], True)
+    L.randomize_small_leaves(p, 6)
+    g = np.random.default_rng(5)
+    x = torch.from_numpy(g.integers(0, 256, (2,) + c["obs_dim"], dtype=np.uint8))
+    q = L.forward(p, x, "impala", True, 1 + c["K"], c["A"])
+    assert q.shape == (2, 1 + c["K"], c["A"]) and torch.isfinite(q).all()
+    # a residual block whose second convolution is zero is the identity on its input: zeroing Conv_2 / Conv_4 of every
+    # Stack must give the same Q-values as a network whose blocks are skipped altogether
+    pz = L.clone_params(p)
+    for st in range(3):
+        for q_ in (2, 4):
+            pz[f"Stack_{st}/Conv_{q_}"]["kernel"].zero_()
+            pz[f"Stack_{st}/Conv_{q_}"]["bias"].zero_()
+    qz = L.forward(pz, x, "impala", True, 1 + c["K"], c["A"])
+    pw = L.clone_params(pz)
+    for st in range(3):  # garbage in the (now unused) first convolutions of the blocks must not matter either
+        pw[f"Stack_{st}/Conv_1"]["kernel"].add_(3.0)
+        pw[f"Stack_{st}/LayerNorm_0"]["scale"].mul_(-2.0)
+    assert torch.equal(L.forward(pw, x, "impala", True, 1 + c["K"], c["A"]), qz)
+    # autograd through pooling / skips against central differences on a few coordinates
+    batch = L.make_batch(9, 2, c["obs_dim"], c["A"], "impala")
+    pp = L.clone_params(p)
+    _, _, grads, _, _ = L.learn_on_batch(pp, L.zeros_like_params(p), L.zeros_like_params(p), 0, batch, "impala", True, c["K"],
+                                         c["A"], 0.99, 1, 0.0, 1.0)
+    s_, a_, _, s2_, _ = batch
+    targets = L.loss_on_batch(p, batch, "impala", True, c["K"], c["A"], 0.99, 1)[3]
+
+    def frozen_loss(pp):  # the targets carry a stop_gradient (isdqn.py:100): hold them fixed
+        all_q = L.forward(pp, torch.cat((s_, s2_)), "impala", True, 1 + c["K"], c["A"])
+        q_ = all_q[:2, 1:, :].gather(-1, a_.view(2, 1, 1).expand(2, c["K"], 1)).squeeze(-1)
+        return ((q_ - targets) ** 2).mean(0).sum()
+
+    for mod, leaf, idx in (("Stack_0/Conv_0", "kernel", (1, 2, 0, 3)), ("Stack_1/Conv_3", "kernel", (0, 1, 2, 4)),
+                           ("Stack_2/LayerNorm_1", "scale", (2,)), ("Stack_0/Conv_2", "bias", (1,)), ("LayerNorm_0", "bias", (4,)),
+                           ("Stack_2/Conv_0", "bias", (0,)), ("Stack_1/LayerNorm_0", "bias", (3,))):
+        h = 1e-6
+        vals = []
+        for sgn in (+1, -1):
+            q_ = L.clone_params(p)
+            q_[mod][leaf][idx] += sgn * h
+            with torch.no_grad():
+                vals.append(float(frozen_loss(q_)))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        an = float(grads[mod][leaf][idx])
+        assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)) + 1e-7, (mod, leaf, fd, an)
