@@ -421,6 +421,17 @@ def run_ours(args, rank, world, local_rank):
             ms32, ms32_e2e, _, _, _ = measure_agent(agent32, rb, n32, max(3, args.warmup // 4), barrier, stream, local_rank)
             fp32 = {"steps": n32, "ms": ms32, "ms_e2e": ms32_e2e}
             del agent32
+        # ---- architecture_type "impala" (launch_job/atari/launch_time.sh runs both torsos with these features): fp32 path
+        impala = None
+        if args.dtype == "bf16" and rank == 0:
+            agent_i = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "impala", LR, GAMMA, 1, 1, 8000,
+                            adam_eps=ADAM_EPS, compute_dtype="float32")
+            n_i = max(10, args.steps // 10)
+            ms_i, ms_i_e2e, _, _, _ = measure_agent(agent_i, rb, n_i, 3, lambda: torch.cuda.synchronize(), stream, local_rank)
+            impala = {"dtype": "f32", "features": list(FEATURES), "params": agent_i.network.n_params, "steps": n_i,
+                      "value": n_i / (ms_i / 1e3), "ms_per_step": ms_i / n_i, "e2e": n_i / (ms_i_e2e / 1e3), "unit": "updates/s",
+                      "scope": "rank 0 only; CUDA-core fp32 kernels (the tensor-core path covers the cnn torso)"}
+            del agent_i
         # ---- replay throughput shape: 2048 batches of 32 per launch (sampler + gather only)
         n_big = 2048 * BATCH
         for _ in range(3):
@@ -666,6 +677,7 @@ def run_ours(args, rank, world, local_rank):
         "fill": {"adds": n_fill, "seconds": t_fill, "us_per_add": t_fill / n_fill * 1e6, "path": "ReplayBuffer.add_batch (4096 per call)",
                  "per_transition_add_us": t_one / n_one * 1e6},
         "fp32": fp32,
+        "impala": impala,
         "torso": torso,
         "dp": dp,
     }

@@ -96,7 +96,10 @@ def main():
     ap.add_argument("--capacity", type=int, default=50_000)
     ap.add_argument("--prioritized", action="store_true")
     ap.add_argument("--dtype", default="bfloat16")
+    ap.add_argument("--architecture", default="cnn", choices=["cnn", "impala"])
     args = ap.parse_args()
+    if args.architecture == "impala":
+        args.dtype = "float32"  # the tensor-core path covers cnn
     from isdqn_b200.networks.isdqn import iSDQN
     from isdqn_b200.sample_collection.replay_buffer import ReplayBuffer
     from isdqn_b200.sample_collection.samplers import PrioritizedSamplingDistribution, UniformSamplingDistribution
@@ -107,7 +110,7 @@ def main():
     if args.prioritized:  # new transitions enter at the maximum recorded priority
         add = rb.add
         rb.add = lambda t, **kw: add(t, priority="max")
-    agent = iSDQN(0, (84, 84, 4), env.n_actions, 9, [32, 64, 64, 512], True, False, "cnn", 6.25e-5, 0.99, 1, 4, 1000,
+    agent = iSDQN(0, (84, 84, 4), env.n_actions, 9, [32, 64, 64, 512], True, False, args.architecture, 6.25e-5, 0.99, 1, 4, 1000,
                   adam_eps=1.5e-4, compute_dtype=args.dtype)
     if args.prioritized:
         agent.prioritized_beta = 0.4

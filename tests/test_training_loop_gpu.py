@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 
-@pytest.mark.parametrize("prioritized", [False, True])
-def test_reference_training_loop_runs_on_the_drop_in_classes(prioritized):
+@pytest.mark.parametrize("prioritized,arch", [(False, "cnn"), (True, "cnn"), (False, "impala"), (True, "impala")])
+def test_reference_training_loop_runs_on_the_drop_in_classes(prioritized, arch):
     import torch
     from train_synthetic import SyntheticAtari, train
 
@@ -23,7 +23,7 @@ def test_reference_training_loop_runs_on_the_drop_in_classes(prioritized):
     from oracle.replay_oracle import ReplayOracle
     from oracle.samplers_oracle import UniformSamplingOracle
 
-    cap, steps = 300, 700
+    cap, steps = 300, (700 if arch == "cnn" else 520)
     env = SyntheticAtari(3, p_terminal=0.02)
     sampler = PrioritizedSamplingDistribution(0, cap) if prioritized else UniformSamplingDistribution(0)
     rb = ReplayBuffer(sampler, 32, cap, stack_size=4, update_horizon=1, gamma=0.99, clipping=lambda x: np.clip(x, -1, 1))
@@ -35,8 +35,9 @@ def test_reference_training_loop_runs_on_the_drop_in_classes(prioritized):
         add(t, **({"priority": "max"} if prioritized else {}))
 
     rb.add = add_both
-    agent = iSDQN(0, (84, 84, 4), env.n_actions, 3, [32, 64, 64, 512], True, False, "cnn", 1e-4, 0.99, 1, 4, 200,
-                  adam_eps=1.5e-4, compute_dtype="bfloat16")
+    feats = [32, 64, 64, 512] if arch == "cnn" else [16, 32, 32, 256]
+    agent = iSDQN(0, (84, 84, 4), env.n_actions, 3, feats, True, False, arch, 1e-4, 0.99, 1, 4, 200,
+                  adam_eps=1.5e-4, compute_dtype="bfloat16" if arch == "cnn" else "float32")
     if prioritized:
         agent.prioritized_beta = 0.4
     p = {"epsilon_end": 0.05, "epsilon_duration": 300, "n_epochs": 1, "n_training_steps_per_epoch": steps,
@@ -46,7 +47,7 @@ def test_reference_training_loop_runs_on_the_drop_in_classes(prioritized):
     torch.cuda.synchronize()
     rb._sampling_distribution.check_status()
     # target updates every 200 steps after the first 100: at least 3 log records with the reference's keys, finite losses
-    assert len(logs) >= 3
+    assert len(logs) >= (3 if arch == "cnn" else 2)
     for rec in logs:
         assert {"loss", "networks/0_loss", "networks/2_loss", "n_training_steps"} <= set(rec)
         assert np.isfinite(rec["loss"]) and rec["loss"] >= 0
