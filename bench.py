@@ -424,14 +424,17 @@ def run_ours(args, rank, world, local_rank):
         # ---- architecture_type "impala" (launch_job/atari/launch_time.sh runs both torsos with these features): fp32 path
         impala = None
         if args.dtype == "bf16" and rank == 0:
-            agent_i = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "impala", LR, GAMMA, 1, 1, 8000,
-                            adam_eps=ADAM_EPS, compute_dtype="float32")
-            n_i = max(10, args.steps // 10)
-            ms_i, ms_i_e2e, _, _, _ = measure_agent(agent_i, rb, n_i, 3, lambda: torch.cuda.synchronize(), stream, local_rank)
-            impala = {"dtype": "f32", "features": list(FEATURES), "params": agent_i.network.n_params, "steps": n_i,
-                      "value": n_i / (ms_i / 1e3), "ms_per_step": ms_i / n_i, "e2e": n_i / (ms_i_e2e / 1e3), "unit": "updates/s",
-                      "scope": "rank 0 only; CUDA-core fp32 kernels (the tensor-core path covers the cnn torso)"}
-            del agent_i
+            impala = {"features": list(FEATURES), "unit": "updates/s",
+                      "scope": "rank 0 only; bf16: every convolution but Stack_0/Conv_0 on the tcgen05 tile engine (gather-fed "
+                               "problems), fp32 residual stream / LayerNorm / Dense tail; f32: CUDA-core kernels (1e-5 parity)"}
+            for name, cd in (("bf16", "bfloat16"), ("f32", "float32")):
+                agent_i = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "impala", LR, GAMMA, 1, 1, 8000,
+                                adam_eps=ADAM_EPS, compute_dtype=cd)
+                n_i = max(10, args.steps // (4 if name == "bf16" else 10))
+                ms_i, ms_i_e2e, _, _, _ = measure_agent(agent_i, rb, n_i, 3, lambda: torch.cuda.synchronize(), stream, local_rank)
+                impala["params"] = agent_i.network.n_params
+                impala[name] = {"steps": n_i, "value": n_i / (ms_i / 1e3), "ms_per_step": ms_i / n_i, "e2e": n_i / (ms_i_e2e / 1e3)}
+                del agent_i
         # ---- replay throughput shape: 2048 batches of 32 per launch (sampler + gather only)
         n_big = 2048 * BATCH
         for _ in range(3):

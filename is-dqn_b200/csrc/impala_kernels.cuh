@@ -11,8 +11,12 @@ namespace isdqn {
 // flax nn.max_pool(x, (3, 3), strides=(2, 2), padding="SAME") (dqn.py:23): -inf padding, out = ceil(in / 2).
 // widx[img][oy][ox][c] = ky*3 + kx of the FIRST maximum in row-major window order (XLA's select-and-scatter with a
 // `>=` select keeps the earlier element on ties), written for the images that get a backward pass.
-static __global__ void __launch_bounds__(256)
-maxpool3s2_fwd_kernel(const float* __restrict__ x, int n_img, int H, int W, int C, int OH, int OW, int pad_y, int pad_x,
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+maxpool3s2_fwd_kernel(const TIn* __restrict__ x, int n_img, int H, int W, int C, int OH, int OW, int pad_y, int pad_x,
                       float* __restrict__ y, uint8_t* __restrict__ widx, int n_img_train) {
   const int64_t total = (int64_t)n_img * OH * OW * C;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -32,7 +36,7 @@ maxpool3s2_fwd_kernel(const float* __restrict__ x, int n_img, int H, int W, int 
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * 2 - pad_x + kx;
         if ((unsigned)ix >= (unsigned)W) continue;
-        const float v = x[(((int64_t)img * H + iy) * W + ix) * C + c];
+        const float v = to_f32(x[(((int64_t)img * H + iy) * W + ix) * C + c]);
         if (bi < 0 || v > best) {
           best = v;
           bi = ky * 3 + kx;
@@ -48,7 +52,7 @@ maxpool3s2_fwd_kernel(const float* __restrict__ x, int n_img, int H, int W, int 
 // recorded maximum is this pixel, in a fixed order.
 static __global__ void __launch_bounds__(256)
 maxpool3s2_bwd_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ widx, int n_img, int H, int W, int C, int OH,
-                      int OW, int pad_y, int pad_x, float* __restrict__ gx) {
+                      int OW, int pad_y, int pad_x, float* __restrict__ gx, __nv_bfloat16* __restrict__ gx16) {
   const int64_t total = (int64_t)n_img * H * W * C;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int c = (int)(i % C);
@@ -75,6 +79,7 @@ maxpool3s2_bwd_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ 
       }
     }
     gx[i] = acc;
+    if (gx16) gx16[i] = __float2bfloat16_rn(acc);
   }
 }
 
@@ -84,8 +89,8 @@ maxpool3s2_bwd_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ 
 template <int MAXJ>
 __global__ void __launch_bounds__(256)
 ln_relu_fwd_warp_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ ln_g,
-                        const float* __restrict__ ln_b, float* __restrict__ t, float* __restrict__ xhat,
-                        float* __restrict__ rstd, int rows_train) {
+                        const float* __restrict__ ln_b, float* __restrict__ t, __nv_bfloat16* __restrict__ t16,
+                        float* __restrict__ xhat, float* __restrict__ rstd, int rows_train) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gam[MAXJ], bet[MAXJ];
 #pragma unroll
@@ -127,7 +132,9 @@ ln_relu_fwd_warp_kernel(const float* __restrict__ x, int rows, int C, const floa
           if (save) xhat[(int64_t)r * C + n] = xh;
           y = xh * gam[j] + bet[j];
         }
-        t[(int64_t)r * C + n] = fmaxf(y, 0.f);
+        y = fmaxf(y, 0.f);
+        if (t) t[(int64_t)r * C + n] = y;
+        if (t16) t16[(int64_t)r * C + n] = __float2bfloat16_rn(y);
       }
     }
     if (save && lane == 0) rstd[r] = rs;
@@ -135,13 +142,14 @@ ln_relu_fwd_warp_kernel(const float* __restrict__ x, int rows, int C, const floa
 }
 
 static inline cudaError_t launch_ln_relu_fwd_warp(cudaStream_t s, const float* x, int rows, int C, const float* ln_g,
-                                                  const float* ln_b, float* t, float* xhat, float* rstd, int rows_train) {
+                                                  const float* ln_b, float* t, __nv_bfloat16* t16, float* xhat, float* rstd,
+                                                  int rows_train) {
   int ctas = ceil_div(rows, 8);
   if (ctas > 16 * kNumSMs) ctas = 16 * kNumSMs;
-  if (C <= 32) ln_relu_fwd_warp_kernel<1><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, xhat, rstd, rows_train);
-  else if (C <= 64) ln_relu_fwd_warp_kernel<2><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, xhat, rstd, rows_train);
-  else if (C <= 128) ln_relu_fwd_warp_kernel<4><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, xhat, rstd, rows_train);
-  else ln_relu_fwd_warp_kernel<8><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, xhat, rstd, rows_train);
+  if (C <= 32) ln_relu_fwd_warp_kernel<1><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, t16, xhat, rstd, rows_train);
+  else if (C <= 64) ln_relu_fwd_warp_kernel<2><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, t16, xhat, rstd, rows_train);
+  else if (C <= 128) ln_relu_fwd_warp_kernel<4><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, t16, xhat, rstd, rows_train);
+  else ln_relu_fwd_warp_kernel<8><<<ctas, 256, 0, s>>>(x, rows, C, ln_g, ln_b, t, t16, xhat, rstd, rows_train);
   return cudaGetLastError();
 }
 
@@ -165,9 +173,25 @@ colsum_partials_kernel(const float* __restrict__ x, int rows, int C, float* __re
   }
 }
 
-// dst += src  (the two branches of a residual connection meet here in the backward pass)
-static __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] += src[i];
+// dst += src  (the two branches of a residual connection meet here in the backward pass); optional bf16 copy of the sum
+static __global__ void __launch_bounds__(256)
+add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ dst16) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float v = dst[i] + src[i];
+    dst[i] = v;
+    if (dst16) dst16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// tensor-core path, forward: out = x + c (c = bf16 output of the block's second convolution); optional bf16 copy
+static __global__ void __launch_bounds__(256)
+residual_add_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ c, float* __restrict__ out,
+                        __nv_bfloat16* __restrict__ out16, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float v = x[i] + __bfloat162float(c[i]);
+    out[i] = v;
+    if (out16) out16[i] = __float2bfloat16_rn(v);
+  }
 }
 
 }  // namespace isdqn

@@ -13,6 +13,17 @@ extern "C" int isdqn_adam_step_nocount(float* d_params, const float* d_grads, fl
 
 int isdqn_tc_train_dispatch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update,
                             float* q_out, void* stream);
+// building blocks of the tile engine (tc_learner.cu)
+bool isdqn_tc_conv_ok(const isdqn::Layer& L);
+int isdqn_tc_conv_fwd(const isdqn::Layer& L, const void* x16, int rows, const void* w16, const float* params, void* out16,
+                      cudaStream_t s);
+int isdqn_tc_conv_wgrad(const isdqn::Layer& L, const void* x16, const void* dz16, float* part, int rows_l, int splits,
+                        int* real_splits, cudaStream_t s);
+int isdqn_tc_conv_dgrad(const isdqn::Layer& L, const void* dz16, const void* w16, float* dx, int B, cudaStream_t s);
+int isdqn_cast_bf16_launch(const float* src, void* dst16, int64_t n, cudaStream_t s);
+int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
+                      float b1, float b2, float eps, int64_t n, void* d_shadow_bf16, void* stream, int64_t skip_begin,
+                      int64_t skip_len, int max_ctas);
 
 namespace {
 
@@ -476,6 +487,66 @@ void carve_impala(const ImpalaPlan& ip, int rows, int B, ImpalaWs* w) {
   w->total = off;
 }
 
+// bf16 buffers of the tensor-core mode (offsets in BYTES into isdqn_train.d_workspace_tc)
+struct ImpalaTc {
+  int64_t x0;  // Conv_0 output of stacks 1, 2 (scratch)
+  int64_t c;   // output of a block's second convolution (scratch)
+  struct St {
+    int64_t t[2], u[2];  // relu(LN(x[j])), relu(Conv_{1+2j}(t[j]))
+    int64_t x3;          // bf16 copy of the stack output (input of the next stack's Conv_0); -1 for the last stack
+  } st[3];
+  int64_t G, T, G0;  // bf16 copies of the gradients the weight / input gradient GEMMs consume
+  int64_t total;
+};
+void carve_impala_tc(const ImpalaPlan& ip, int rows, int B, ImpalaTc* t) {
+  int64_t off = 0;
+  auto take = [&](int64_t n_elems) {
+    const int64_t r = off;
+    off = (off + 2 * n_elems + 255) & ~(int64_t)255;
+    return r;
+  };
+  int64_t max_x0 = 0, max_c = 0, max_g = 0, max_g0 = 0;
+  for (int s = 0; s < 3; ++s) {
+    const ImpalaStack& S = ip.st[s];
+    const int64_t a = (int64_t)S.Hin * S.Win * S.C, n = (int64_t)S.H * S.W * S.C;
+    if (s > 0 && rows * a > max_x0) max_x0 = rows * a;
+    if (rows * n > max_c) max_c = rows * n;
+    if (B * n > max_g) max_g = B * n;
+    if (s > 0 && B * a > max_g0) max_g0 = B * a;
+  }
+  t->x0 = take(max_x0);
+  t->c = take(max_c);
+  for (int s = 0; s < 3; ++s) {
+    const ImpalaStack& S = ip.st[s];
+    const int64_t n = (int64_t)S.H * S.W * S.C;
+    for (int j = 0; j < 2; ++j) {
+      t->st[s].t[j] = take(rows * n);
+      t->st[s].u[j] = take(rows * n);
+    }
+    t->st[s].x3 = s < 2 ? take(rows * n) : -1;
+  }
+  if (B > 0) {
+    t->G = take(max_g);
+    t->T = take(max_g);
+    t->G0 = take(max_g0);
+  } else {
+    t->G = t->T = t->G0 = -1;
+  }
+  t->total = off;
+}
+inline __nv_bfloat16* w16(void* wt, int64_t off) {
+  return off < 0 ? nullptr : reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(wt) + off);
+}
+// every convolution but Conv_0 of the first stack (3 x 3 x 4 input channels: K = 36) goes to the tile engine
+bool impala_tc_eligible(const ImpalaPlan& ip) {
+  for (int s = 0; s < 3; ++s) {
+    const ImpalaStack& S = ip.st[s];
+    if (s > 0 && !isdqn_tc_conv_ok(impala_conv_layer(S.Hin, S.Win, S.Cin, S.C))) return false;
+    if (!isdqn_tc_conv_ok(impala_conv_layer(S.H, S.W, S.C, S.C))) return false;
+  }
+  return true;
+}
+
 int impala_conv(const Layer& L, const void* in0, const void* in1, int n0, int rows, int kind, const float* w, const float* bias,
                 int relu, const float* residual, float* out, cudaStream_t s) {
   ConvArgs a;
@@ -494,53 +565,85 @@ int grid_for(int64_t n) {
   return g < 1 ? 1 : (int)g;
 }
 
+// t / wt / shadow: tensor-core mode (bf16 activations in wt, bf16 kernels out of the parameter shadow); null = fp32 mode
 int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const float* params, const void* in0, const void* in1,
-                   int n0, int rows, int rows_train, int in_kind, cudaStream_t s) {
+                   int n0, int rows, int rows_train, int in_kind, cudaStream_t s, const ImpalaTc* t = nullptr, void* wt = nullptr,
+                   const __nv_bfloat16* shadow = nullptr) {
+  const bool tc = t != nullptr;
   const float* prev = nullptr;
   for (int si = 0; si < 3; ++si) {
     const ImpalaStack& S = ip.st[si];
     const ImpalaWs::St& O = w.st[si];
-    const Layer La = impala_conv_layer(S.Hin, S.Win, S.Cin, S.C);
-    const Layer Lb = impala_conv_layer(S.H, S.W, S.C, S.C);
+    Layer La = impala_conv_layer(S.Hin, S.Win, S.Cin, S.C);
+    Layer Lb = impala_conv_layer(S.H, S.W, S.C, S.C);
     float* x0 = wsp(ws, w.x0);
-    int rc = impala_conv(La, si == 0 ? in0 : prev, si == 0 ? in1 : nullptr, si == 0 ? n0 : rows, rows, si == 0 ? in_kind : IN_F32,
-                         params + S.w[0], params + S.b[0], 0, nullptr, x0, s);
-    if (rc) return rc;
-    ISDQN_PROF(s, "maxpool_fwd");
-    maxpool3s2_fwd_kernel<<<grid_for((int64_t)rows * S.H * S.W * S.C), 256, 0, s>>>(
-        x0, rows, S.Hin, S.Win, S.C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]),
-        reinterpret_cast<uint8_t*>(wsp(ws, O.widx)), rows_train > 0 ? rows_train : 0);
+    const int64_t n_out = (int64_t)rows * S.H * S.W * S.C;
+    uint8_t* widx = reinterpret_cast<uint8_t*>(wsp(ws, O.widx));
+    const int n_train = rows_train > 0 ? rows_train : 0;
+    int rc;
+    if (tc && si > 0) {
+      La.relu = 0; La.has_ln = 0; La.b_off = S.b[0];
+      rc = isdqn_tc_conv_fwd(La, w16(wt, t->st[si - 1].x3), rows, shadow + S.w[0], params, w16(wt, t->x0), s);
+      if (rc) return rc;
+      ISDQN_PROF(s, "maxpool_fwd");
+      maxpool3s2_fwd_kernel<__nv_bfloat16><<<grid_for(n_out), 256, 0, s>>>(w16(wt, t->x0), rows, S.Hin, S.Win, S.C, S.H, S.W,
+                                                                          S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]), widx, n_train);
+    } else {
+      rc = impala_conv(La, si == 0 ? in0 : prev, si == 0 ? in1 : nullptr, si == 0 ? n0 : rows, rows, si == 0 ? in_kind : IN_F32,
+                       params + S.w[0], params + S.b[0], 0, nullptr, x0, s);
+      if (rc) return rc;
+      ISDQN_PROF(s, "maxpool_fwd");
+      maxpool3s2_fwd_kernel<float><<<grid_for(n_out), 256, 0, s>>>(x0, rows, S.Hin, S.Win, S.C, S.H, S.W, S.pool_pad_y, S.pool_pad_x,
+                                                                 wsp(ws, O.x[0]), widx, n_train);
+    }
     ISDQN_LAUNCH_CHECK();
     const int prow = rows * S.H * S.W;
     for (int j = 0; j < 2; ++j) {
       ISDQN_PROF(s, "ln_relu_fwd");
       ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, wsp(ws, O.x[j]), prow, S.C, ip.has_ln ? params + S.g[j] : nullptr,
-                                               ip.has_ln ? params + S.beta[j] : nullptr, wsp(ws, O.t[j]), wsp(ws, O.xhat[j]),
-                                               wsp(ws, O.rstd[j]), rows_train * S.H * S.W));
-      rc = impala_conv(Lb, wsp(ws, O.t[j]), nullptr, rows, rows, IN_F32, params + S.w[1 + 2 * j], params + S.b[1 + 2 * j], 1,
-                       nullptr, wsp(ws, O.u[j]), s);
-      if (rc) return rc;
-      rc = impala_conv(Lb, wsp(ws, O.u[j]), nullptr, rows, rows, IN_F32, params + S.w[2 + 2 * j], params + S.b[2 + 2 * j], 0,
-                       wsp(ws, O.x[j]), wsp(ws, O.x[j + 1]), s);
-      if (rc) return rc;
+                                               ip.has_ln ? params + S.beta[j] : nullptr, tc ? nullptr : wsp(ws, O.t[j]),
+                                               tc ? w16(wt, t->st[si].t[j]) : nullptr, wsp(ws, O.xhat[j]), wsp(ws, O.rstd[j]),
+                                               rows_train * S.H * S.W));
+      if (tc) {
+        Lb.has_ln = 0;
+        Lb.relu = 1; Lb.b_off = S.b[1 + 2 * j];
+        rc = isdqn_tc_conv_fwd(Lb, w16(wt, t->st[si].t[j]), rows, shadow + S.w[1 + 2 * j], params, w16(wt, t->st[si].u[j]), s);
+        if (rc) return rc;
+        Lb.relu = 0; Lb.b_off = S.b[2 + 2 * j];
+        rc = isdqn_tc_conv_fwd(Lb, w16(wt, t->st[si].u[j]), rows, shadow + S.w[2 + 2 * j], params, w16(wt, t->c), s);
+        if (rc) return rc;
+        ISDQN_PROF(s, "residual_add");
+        residual_add_fwd_kernel<<<grid_for(n_out), 256, 0, s>>>(wsp(ws, O.x[j]), w16(wt, t->c), wsp(ws, O.x[j + 1]),
+                                                               j == 1 ? w16(wt, t->st[si].x3) : nullptr, n_out);
+        ISDQN_LAUNCH_CHECK();
+      } else {
+        rc = impala_conv(Lb, wsp(ws, O.t[j]), nullptr, rows, rows, IN_F32, params + S.w[1 + 2 * j], params + S.b[1 + 2 * j], 1,
+                         nullptr, wsp(ws, O.u[j]), s);
+        if (rc) return rc;
+        rc = impala_conv(Lb, wsp(ws, O.u[j]), nullptr, rows, rows, IN_F32, params + S.w[2 + 2 * j], params + S.b[2 + 2 * j], 0,
+                         wsp(ws, O.x[j]), wsp(ws, O.x[j + 1]), s);
+        if (rc) return rc;
+      }
     }
     prev = wsp(ws, O.x[2]);
   }
   const ImpalaStack& L = ip.st[2];
   ISDQN_PROF(s, "ln_relu_fwd");
   ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, prev, rows * L.H * L.W, L.C, ip.has_ln ? params + ip.fin_g : nullptr,
-                                           ip.has_ln ? params + ip.fin_beta : nullptr, wsp(ws, w.tf), wsp(ws, w.xhf),
+                                           ip.has_ln ? params + ip.fin_beta : nullptr, wsp(ws, w.tf), nullptr, wsp(ws, w.xhf),
                                            wsp(ws, w.rsf), rows_train * L.H * L.W));
   return run_forward(ip.tail, w.tailw, wsp(ws, w.tail), params + ip.tail_base, wsp(ws, w.tf), nullptr, rows, rows, rows_train,
                      IN_F32, s);
 }
 
 int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isdqn_train* tr, const isdqn_batch* b, int in_kind,
-                    cudaStream_t s) {
+                    cudaStream_t s, const ImpalaTc* t = nullptr, void* wt = nullptr, const __nv_bfloat16* shadow = nullptr) {
+  const bool tc = t != nullptr;
   const int B = tr->batch;
   const float* params = tr->d_params;
   float* grads = tr->d_grads;
   float *G = wsp(ws, w.G), *T1 = wsp(ws, w.T1), *T2 = wsp(ws, w.T2), *G0 = wsp(ws, w.G0), *pb = wsp(ws, w.part);
+  __nv_bfloat16 *G16 = tc ? w16(wt, t->G) : nullptr, *T16 = tc ? w16(wt, t->T) : nullptr, *G016 = tc ? w16(wt, t->G0) : nullptr;
   {  // Dense tail; its input gradient is dL/d relu(LN_0(x)) of the last stack
     isdqn_train trt = *tr;
     trt.d_params = tr->d_params + ip.tail_base;
@@ -556,14 +659,16 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     Segment& sg = segs.s[segs.count++];
     sg.src = src; sg.dst = dst; sg.stride = stride; sg.n = n; sg.parts = parts; sg.s2d_cout = 0;
   };
-  // G (post-ReLU gradient) -> gradient of the LayerNorm input, in place; [1] / [2] of the column partials are the
-  // LayerNorm scale / bias gradients, [0] (sum of the result) the bias gradient of a convolution right below a ReLU
-  auto act_bwd = [&](float* d, const float* xhat, const float* rstd, int64_t g_off, int64_t beta_off, const float* act, int rows,
-                     int C, float* colpart, int ctas) -> int {
+  // d (post-ReLU gradient) -> gradient of the LayerNorm input, in place (and / or as bf16); [1] / [2] of the column
+  // partials are the LayerNorm scale / bias gradients, [0] (sum of the result) the bias gradient of a convolution right
+  // below a ReLU
+  auto act_bwd = [&](float* d, const float* xhat, const float* rstd, int64_t g_off, int64_t beta_off, const float* act,
+                     const __nv_bfloat16* act16, int rows, int C, float* colpart, int ctas, __nv_bfloat16* dz16,
+                     bool store_d) -> int {
     ISDQN_PROF(s, "ln_relu_bwd");
     const bool ln = g_off >= 0;
     ISDQN_CUDA_CHECK(launch_ln_relu_bwd_warp(ctas, s, d, ln ? xhat : nullptr, ln ? rstd : nullptr, ln ? params + g_off : nullptr,
-                                             ln ? params + beta_off : nullptr, act, rows, C, colpart, nullptr, nullptr));
+                                             ln ? params + beta_off : nullptr, act, rows, C, colpart, dz16, act16, store_d));
     if (ln) {
       add_seg(colpart + C, grads + g_off, 3 * (int64_t)C, C, ctas);
       add_seg(colpart + 2 * C, grads + beta_off, 3 * (int64_t)C, C, ctas);
@@ -577,10 +682,26 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     add_seg(part, dst, C, C, ctas);
     return ISDQN_OK;
   };
+  // weight gradient partials + input gradient of one convolution (x / x16: its input, dz / dz16: gradient of its output)
+  auto conv_bwd = [&](const Layer& L, const void* x, int x_kind, const __nv_bfloat16* x16, const float* dz,
+                      const __nv_bfloat16* dz16, int rows_l, float* part, int splits, int64_t w_off, float* dx, bool on_tc) -> int {
+    int sp = 0;
+    if (on_tc) {
+      int rc = isdqn_tc_conv_wgrad(L, x16, dz16, part, rows_l, splits, &sp, s);
+      if (rc) return rc;
+    } else {
+      sp = launch_conv_wgrad_f32(L, x, x_kind, rows_l, dz, part, splits, s);
+      if (sp < 0) return -sp;
+    }
+    add_seg(part, grads + w_off, (int64_t)L.in_dim * L.out_dim, L.in_dim * L.out_dim, sp);
+    if (!dx) return ISDQN_OK;
+    if (on_tc) return isdqn_tc_conv_dgrad(L, dz16, shadow + w_off, dx, B, s);
+    return launch_conv_dgrad_f32(L, B, dz, params + w_off, dx, s);
+  };
   {
     const ImpalaStack& L = ip.st[2];
-    int rc = act_bwd(G, wsp(ws, w.xhf), wsp(ws, w.rsf), ip.fin_g, ip.fin_beta, wsp(ws, w.tf), B * L.H * L.W, L.C,
-                     wsp(ws, w.finpart), w.fin_ctas);
+    int rc = act_bwd(G, wsp(ws, w.xhf), wsp(ws, w.rsf), ip.fin_g, ip.fin_beta, wsp(ws, w.tf), nullptr, B * L.H * L.W, L.C,
+                     wsp(ws, w.finpart), w.fin_ctas, G16, true);
     if (rc) return rc;
   }
   for (int si = 2; si >= 0; --si) {
@@ -593,46 +714,45 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     const Layer Lb = impala_conv_layer(S.H, S.W, C, C);
     for (int j = 1; j >= 0; --j) {
       const int cb = 1 + 2 * j, cc = 2 + 2 * j;
+      const __nv_bfloat16* t16 = tc ? w16(wt, t->st[si].t[j]) : nullptr;
+      const __nv_bfloat16* u16 = tc ? w16(wt, t->st[si].u[j]) : nullptr;
       // G = dL/d(block output) = dL/d(Conv_cc output) (no activation) and, through the skip, part of dL/d(block input)
       int rc = colsum(G, rows, C, pb + P.colsum[1 + j], P.colsum_ctas[1 + j], grads + S.b[cc]);
       if (rc) return rc;
-      int sp = launch_conv_wgrad_f32(Lb, wsp(ws, O.u[j]), IN_F32, rows, G, pb + P.wpart[cc], P.wsplits[cc], s);
-      if (sp < 0) return -sp;
-      add_seg(pb + P.wpart[cc], grads + S.w[cc], (int64_t)9 * C * C, 9 * C * C, sp);
-      rc = launch_conv_dgrad_f32(Lb, B, G, params + S.w[cc], T1, s);
+      rc = conv_bwd(Lb, wsp(ws, O.u[j]), IN_F32, u16, G, G16, rows, pb + P.wpart[cc], P.wsplits[cc], S.w[cc], T1, tc);
       if (rc) return rc;
       // through relu(Conv_cb(.)): T1 -> dL/d(Conv_cb output)
       float* cp = pb + P.colpart[2 * j];
-      rc = act_bwd(T1, nullptr, nullptr, -1, -1, wsp(ws, O.u[j]), rows, C, cp, P.col_ctas);
+      rc = act_bwd(T1, nullptr, nullptr, -1, -1, wsp(ws, O.u[j]), u16, rows, C, cp, P.col_ctas, T16, !tc);
       if (rc) return rc;
       add_seg(cp, grads + S.b[cb], 3 * (int64_t)C, C, P.col_ctas);
-      sp = launch_conv_wgrad_f32(Lb, wsp(ws, O.t[j]), IN_F32, rows, T1, pb + P.wpart[cb], P.wsplits[cb], s);
-      if (sp < 0) return -sp;
-      add_seg(pb + P.wpart[cb], grads + S.w[cb], (int64_t)9 * C * C, 9 * C * C, sp);
-      rc = launch_conv_dgrad_f32(Lb, B, T1, params + S.w[cb], T2, s);
+      rc = conv_bwd(Lb, wsp(ws, O.t[j]), IN_F32, t16, T1, T16, rows, pb + P.wpart[cb], P.wsplits[cb], S.w[cb], T2, tc);
       if (rc) return rc;
       // through relu(LN_j(.)): T2 -> dL/d(block input) along the convolution branch; the skip branch adds G
-      rc = act_bwd(T2, wsp(ws, O.xhat[j]), wsp(ws, O.rstd[j]), S.g[j], S.beta[j], wsp(ws, O.t[j]), rows, C,
-                   pb + P.colpart[2 * j + 1], P.col_ctas);
+      rc = act_bwd(T2, wsp(ws, O.xhat[j]), wsp(ws, O.rstd[j]), S.g[j], S.beta[j], wsp(ws, O.t[j]), t16, rows, C,
+                   pb + P.colpart[2 * j + 1], P.col_ctas, nullptr, true);
       if (rc) return rc;
       ISDQN_PROF(s, "residual_add");
-      add_inplace_kernel<<<grid_for(n), 256, 0, s>>>(G, T2, n);
+      add_inplace_kernel<<<grid_for(n), 256, 0, s>>>(G, T2, n, G16);
       ISDQN_LAUNCH_CHECK();
     }
+    const bool a_tc = tc && si > 0;
     ISDQN_PROF(s, "maxpool_bwd");
     maxpool3s2_bwd_kernel<<<grid_for((int64_t)B * S.Hin * S.Win * C), 256, 0, s>>>(
-        G, reinterpret_cast<const uint8_t*>(wsp(ws, O.widx)), B, S.Hin, S.Win, C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, G0);
+        G, reinterpret_cast<const uint8_t*>(wsp(ws, O.widx)), B, S.Hin, S.Win, C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, G0,
+        a_tc ? G016 : nullptr);
     ISDQN_LAUNCH_CHECK();
     const Layer La = impala_conv_layer(S.Hin, S.Win, S.Cin, C);
     const int rows_a = B * S.Hin * S.Win;
     int rc = colsum(G0, rows_a, C, pb + P.colsum[0], P.colsum_ctas[0], grads + S.b[0]);
     if (rc) return rc;
     const void* in = si == 0 ? b->d_state : static_cast<const void*>(wsp(ws, w.st[si - 1].x[2]));
-    const int sp = launch_conv_wgrad_f32(La, in, si == 0 ? in_kind : IN_F32, rows_a, G0, pb + P.wpart[0], P.wsplits[0], s);
-    if (sp < 0) return -sp;
-    add_seg(pb + P.wpart[0], grads + S.w[0], (int64_t)9 * S.Cin * C, 9 * S.Cin * C, sp);
-    if (si > 0) {
-      rc = launch_conv_dgrad_f32(La, B, G0, params + S.w[0], G, s);
+    rc = conv_bwd(La, in, si == 0 ? in_kind : IN_F32, a_tc ? w16(wt, t->st[si - 1].x3) : nullptr, G0, G016, rows_a,
+                  pb + P.wpart[0], P.wsplits[0], S.w[0], si > 0 ? G : nullptr, a_tc);
+    if (rc) return rc;
+    if (a_tc) {  // the input gradient came out in fp32: the next stack's GEMMs want it in bf16 as well
+      const ImpalaStack& Pn = ip.st[si - 1];
+      rc = isdqn_cast_bf16_launch(G, G16, (int64_t)B * Pn.H * Pn.W * Pn.C, s);
       if (rc) return rc;
     }
     // this stack's partials are folded before the next stack re-uses the scratch
@@ -646,11 +766,13 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
 int impala_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update, float* q_out,
                  void* stream) {
   if (!tr || !b) return ISDQN_E_INVALID;
-  if (tr->compute_dtype != ISDQN_COMPUTE_F32) return ISDQN_E_UNSUPPORTED;  // the tensor-core path covers `cnn`
   ImpalaPlan ip;
   int rc = build_impala_plan(net, &ip);
   if (rc) return rc;
+  const bool tc = tr->compute_dtype == ISDQN_COMPUTE_BF16;
+  if (tc && !impala_tc_eligible(ip)) return ISDQN_E_UNSUPPORTED;
   if (!tr->d_params || !tr->d_losses || !tr->d_workspace || tr->batch < 1 || tr->batch_global < tr->batch) return ISDQN_E_INVALID;
+  if (tc && (!tr->d_workspace_tc || !tr->d_params_bf16)) return ISDQN_E_INVALID;
   if (!b->d_state || !b->d_next_state || !b->d_action || !b->d_reward || !b->d_terminal) return ISDQN_E_INVALID;
   if (backward && !tr->d_grads) return ISDQN_E_INVALID;
   if (update && (!tr->d_mu || !tr->d_nu || !tr->d_count)) return ISDQN_E_INVALID;
@@ -658,9 +780,21 @@ int impala_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch*
   ImpalaWs w;
   carve_impala(ip, 2 * B, B, &w);
   if (w.total * (int64_t)sizeof(float) > tr->workspace_bytes) return ISDQN_E_INVALID;
+  ImpalaTc t;
+  if (tc) {
+    carve_impala_tc(ip, 2 * B, B, &t);
+    if (t.total > tr->workspace_tc_bytes) return ISDQN_E_INVALID;
+  }
   cudaStream_t s = as_stream(stream);
   void* ws = tr->d_workspace;
-  rc = impala_forward(ip, w, ws, tr->d_params, b->d_state, b->d_next_state, B, 2 * B, backward ? B : 0, IN_U8_255, s);
+  void* wt = tc ? tr->d_workspace_tc : nullptr;
+  __nv_bfloat16* shadow = tc ? reinterpret_cast<__nv_bfloat16*>(tr->d_params_bf16) : nullptr;
+  if (tc && tr->refresh_shadow) {
+    rc = isdqn_cast_bf16_launch(tr->d_params, shadow, ip.layout.total, s);
+    if (rc) return rc;
+  }
+  rc = impala_forward(ip, w, ws, tr->d_params, b->d_state, b->d_next_state, B, 2 * B, backward ? B : 0, IN_U8_255, s,
+                      tc ? &t : nullptr, wt, shadow);
   if (rc) return rc;
   void* tws = wsp(ws, w.tail);
   const Layer& last = ip.tail.L[ip.tail.n_layers - 1];
@@ -671,7 +805,7 @@ int impala_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch*
   if (q_out)
     ISDQN_CUDA_CHECK(cudaMemcpyAsync(q_out, q_all, sizeof(float) * 2 * (size_t)B * ip.tail.n_out, cudaMemcpyDeviceToDevice, s));
   if (!backward) return ISDQN_OK;
-  rc = impala_backward(ip, w, ws, tr, b, IN_U8_255, s);
+  rc = impala_backward(ip, w, ws, tr, b, IN_U8_255, s, tc ? &t : nullptr, wt, shadow);
   if (rc) return rc;
   if (!update) return ISDQN_OK;
   if (tr->nccl_comm) {
@@ -679,8 +813,8 @@ int impala_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch*
     rc = isdqn_dp_allreduce_f32(tr->nccl_comm, tr->d_grads, ip.layout.total, stream);
     if (rc) return rc;
   }
-  return isdqn_adam_step_nocount(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
-                                 ip.layout.total, stream);
+  return isdqn_adam_launch(tr->d_params, tr->d_grads, tr->d_mu, tr->d_nu, tr->d_count, tr->lr, tr->b1, tr->b2, tr->eps,
+                           ip.layout.total, shadow, stream, 0, 0, 0);
 }
 
 // forward only (isdqn_forward / isdqn_best_action); returns the device pointer of q [rows][n_out] through q_dev
@@ -741,6 +875,16 @@ int train_common(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch*
 }
 
 }  // namespace
+
+// bytes of bf16 scratch of the impala torso in tensor-core mode (0: the network is not eligible)
+int64_t isdqn_impala_tc_bytes(const isdqn_net* net, int batch) {
+  ImpalaPlan ip;
+  if (build_impala_plan(net, &ip) || batch < 1) return -1;
+  if (!impala_tc_eligible(ip)) return 0;
+  ImpalaTc t;
+  carve_impala_tc(ip, 2 * batch, batch, &t);
+  return t.total;
+}
 
 extern "C" int isdqn_net_layout(const isdqn_net* net, isdqn_layout* out) {
   if (!out) return ISDQN_E_INVALID;

@@ -1386,12 +1386,49 @@ int tc_train(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, 
 }  // namespace
 
 // Entry used by the learner dispatch in learner.cu
+// ---- building blocks for callers outside this file (the impala torso in learner.cu): one convolution forward / weight
+// gradient / input gradient on the tile engine, bf16 NHWC activations, bf16 HWIO kernels out of the parameter shadow
+bool isdqn_tc_conv_ok(const Layer& L) {
+  if (L.type != 0 || L.Cin % 8 != 0) return false;
+  if (!(L.out_dim == 32 || L.out_dim == 64 || L.out_dim == 128 || L.out_dim == 256)) return false;
+  const int taps = ceil_div(L.ksz, L.stride);
+  if (ceil_div(L.in_dim, tc::kBM) * 16 > tc::kMaxChunks) return false;
+  if (L.stride * L.stride * ceil_div(taps * taps * L.out_dim, tc::kBK) * 8 > tc::kMaxChunks) return false;
+  return true;
+}
+// out16 = act(conv(x16) + bias) with L.relu / L.b_off (no LayerNorm in the epilogue: L.has_ln must be 0)
+int isdqn_tc_conv_fwd(const Layer& L, const void* x16, int rows, const void* w16_, const float* params, void* out16, cudaStream_t s) {
+  return launch_conv_fwd_tc<false>(L, x16, nullptr, rows, rows, reinterpret_cast<const bf16*>(w16_), params,
+                                   reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, s);
+}
+int isdqn_tc_conv_wgrad(const Layer& L, const void* x16, const void* dz16, float* part, int rows_l, int splits, int* real_splits,
+                        cudaStream_t s) {
+  return launch_conv_wgrad_tc<false>(L, x16, reinterpret_cast<const bf16*>(dz16), part, rows_l, splits, real_splits, s);
+}
+int isdqn_tc_conv_dgrad(const Layer& L, const void* dz16, const void* w16_, float* dx, int B, cudaStream_t s) {
+  return launch_conv_dgrad_tc(L, reinterpret_cast<const bf16*>(dz16), reinterpret_cast<const bf16*>(w16_), dx, B, s);
+}
+int isdqn_cast_bf16_launch(const float* src, void* dst16, int64_t n, cudaStream_t s) {
+  if (n & 3) return ISDQN_E_INVALID;
+  const int64_t n4 = n / 4;
+  if (n4 == 0) return ISDQN_OK;
+  int64_t grid = ceil_div<int64_t>(n4, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  ISDQN_PROF(s, "cast_bf16");
+  cast_f32_bf16_kernel<<<(unsigned)grid, 256, 0, s>>>(src, reinterpret_cast<bf16*>(dst16), n4);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+int64_t isdqn_impala_tc_bytes(const isdqn_net* net, int batch);  // learner.cu
+
 int isdqn_tc_train_dispatch(const isdqn_net* net, const isdqn_train* tr, const isdqn_batch* b, bool backward, bool update,
                             float* q_out, void* stream) {
   return tc_train(net, tr, b, backward, update, q_out, stream);
 }
 
 extern "C" int64_t isdqn_learn_workspace_tc_bytes(const isdqn_net* net, int32_t batch) {
+  if (net && net->arch == ISDQN_ARCH_IMPALA) return isdqn_impala_tc_bytes(net, batch);
   Plan p;
   if (build_plan(net, &p) || batch < 1) return -1;
   if (!tc_eligible(p, net)) return 0;

@@ -178,9 +178,17 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
         x = x.reshape(x.shape[0], -1)
     elif arch == "impala":
         def conv3(x, mod):  # nn.Conv(features, (3, 3)): stride 1, padding SAME = 1 on every side
+            # emulate_bf16: every convolution but the first (K = 36, CUDA cores) runs on the tensor cores with bf16 input,
+            # kernel and output gradient, and its epilogue emits bf16
+            on_tc = emulate_bf16 and mod != "Stack_0/Conv_0"
             w = params[mod]["kernel"]
+            if on_tc:
+                w, x = rnd(w), rnd(x)
             y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
-            return (y + params[mod]["bias"].view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+            if on_tc:
+                y = _RoundGradBf16.apply(y)
+            y = (y + params[mod]["bias"].view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+            return rnd(y) if on_tc else y
 
         x = x.to(dtype) / 255.0
         for st in range(3):
@@ -211,6 +219,8 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
     else:
         x = x.to(dtype)
     n_dense = sum(1 for m in params if m.startswith("Dense_"))
+    if arch == "impala":  # the Dense tail of the impala network stays in fp32
+        emulate_bf16, rnd = False, (lambda t: t)
     for d in range(n_dense - 1):
         y = x @ rnd(params[f"Dense_{d}"]["kernel"])
         if emulate_bf16:

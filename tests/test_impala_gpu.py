@@ -108,10 +108,36 @@ def test_impala_acting_checkpoint_and_shift(tmp_path):
     assert torch.linalg.norm(shifted[:-1] - qv[1:]).item() == 0
 
 
-def test_impala_rejects_the_tensor_core_dtype():
+def test_impala_bf16_tensor_core_convolutions():
+    """compute_dtype="bfloat16": every convolution but Stack_0/Conv_0 on the tcgen05 tile engine (bf16 operands, fp32
+    accumulation, fp32 residual stream / LayerNorm / Dense tail).  Bars of tests/test_learner_bf16_gpu.py: Q-values,
+    targets, losses 2e-2 against the float64 oracle, gradients 15 % in L2; tight against the bf16-emulating oracle."""
+    from tests.test_learner_bf16_gpu import check_bf16
+
+    check_bf16(dict(IMPALA_84, features=[32, 64, 64, 512]), 32, seed=92, n_steps=2)
+    check_bf16(dict(IMPALA_42, features=[32, 32, 64, 128], layer_norm=False), 5, seed=93, n_steps=1)
+
+
+def test_impala_bf16_learns_from_replay_batches_deterministically():
+    cfg = dict(IMPALA_84, features=[32, 64, 64, 512])
+    outs = []
+    for _ in range(2):
+        agent = make_agent(94, **cfg, compute_dtype="bfloat16")
+        batch = L.make_batch(9400, 32, cfg["obs_dim"], cfg["A"], "impala")
+        el = batch_as_element(batch)
+        for _ in range(4):
+            agent.params, agent.optimizer_state, losses = agent.learn_on_batch(agent.params, agent.optimizer_state, el)
+        assert torch.isfinite(losses).all()
+        outs.append(agent.params.flat.cpu().numpy().tobytes())
+        q = agent.network.apply(agent.params, batch[0][0].numpy())
+        assert torch.isfinite(q).all()
+    assert outs[0] == outs[1]
+
+
+def test_impala_ineligible_widths_refuse_the_tensor_core_dtype():
     from isdqn_b200 import _lib
 
-    agent = make_agent(91, **IMPALA_42, compute_dtype="bfloat16")
+    agent = make_agent(91, **IMPALA_42, compute_dtype="bfloat16")  # 16 channels: not a tile-engine width
     batch = L.make_batch(9100, 4, IMPALA_42["obs_dim"], IMPALA_42["A"], "impala")
     with pytest.raises(_lib.IsdqnNativeError):
         agent.learn_on_batch(agent.params, agent.optimizer_state, batch_as_element(batch))
