@@ -1397,12 +1397,25 @@ bool isdqn_tc_conv_ok(const Layer& L) {
   return true;
 }
 // out16 = act(conv(x16) + bias) with L.relu / L.b_off (no LayerNorm in the epilogue: L.has_ln must be 0)
+static bool blocks_tma_on() {  // TMA-fed problems where the shape allows (A/B: ISDQN_IMPALA_TMA=0 keeps the gathers)
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_IMPALA_TMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 int isdqn_tc_conv_fwd(const Layer& L, const void* x16, int rows, const void* w16_, const float* params, void* out16, cudaStream_t s) {
+  if (blocks_tma_on() && conv_fwd_tma_ok(L))
+    return launch_conv_fwd_tma(L, reinterpret_cast<const bf16*>(x16), rows, reinterpret_cast<const bf16*>(w16_), nullptr, params,
+                               reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, 1.0f, s);
   return launch_conv_fwd_tc<false>(L, x16, nullptr, rows, rows, reinterpret_cast<const bf16*>(w16_), params,
                                    reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, s);
 }
 int isdqn_tc_conv_wgrad(const Layer& L, const void* x16, const void* dz16, float* part, int rows_l, int splits, int* real_splits,
                         cudaStream_t s) {
+  if (blocks_tma_on() && conv_wgrad_tma_ok(L))
+    return launch_conv_wgrad_tma(L, reinterpret_cast<const bf16*>(x16), reinterpret_cast<const bf16*>(dz16), part, rows_l / L.pix,
+                                 splits, real_splits, s, 1.0f, L.ksz, 1);
   return launch_conv_wgrad_tc<false>(L, x16, reinterpret_cast<const bf16*>(dz16), part, rows_l, splits, real_splits, s);
 }
 int isdqn_tc_conv_dgrad(const Layer& L, const void* dz16, const void* w16_, float* dx, int B, cudaStream_t s) {

@@ -22,9 +22,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for dtype, tol in (("float32", 2e-5), ("bfloat16", 2e-2)):
-        Bg = 32 * world
-        mk = lambda: iSDQN(7, (84, 84, 4), 9, 9, [32, 64, 64, 512], True, False, "cnn", 6.25e-5, 0.99, 1, 1, 10**9,
+    for arch, dtype, tol in (("cnn", "float32", 2e-5), ("cnn", "bfloat16", 2e-2), ("impala", "float32", 2e-5),
+                             ("impala", "bfloat16", 2e-2)):
+        Bg = (32 if arch == "cnn" else 8) * world
+        mk = lambda: iSDQN(7, (84, 84, 4), 9, 9, [32, 64, 64, 512], True, False, arch, 6.25e-5, 0.99, 1, 1, 10**9,
                            adam_eps=1.5e-4, compute_dtype=dtype)
         dp = mk()
         init_data_parallel(dp)
@@ -39,14 +40,14 @@ def main():
             good = e_l <= tol and e_p <= tol
             ok &= good
             if rank == 0:
-                print(f"dp_check {dtype} world={world} step={step} losses rel err {e_l:.2e} params rel err {e_p:.2e} {'OK' if good else 'FAIL'}", flush=True)
+                print(f"dp_check {arch} {dtype} world={world} step={step} losses rel err {e_l:.2e} params rel err {e_p:.2e} {'OK' if good else 'FAIL'}", flush=True)
         # parameters must be bit-identical across ranks
         ref = dp.params.flat.clone()
         dist.broadcast(ref, src=0)
         same = bool(torch.equal(ref, dp.params.flat))
         ok &= same
         if rank == 0:
-            print(f"dp_check {dtype} replicas bit-identical: {same}", flush=True)
+            print(f"dp_check {arch} {dtype} replicas bit-identical: {same}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
