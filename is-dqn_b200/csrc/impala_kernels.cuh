@@ -162,8 +162,20 @@ colsum_partials_kernel(const float* __restrict__ x, int rows, int C, float* __re
   const int groups = 256 / cw;
   const int col = threadIdx.x % cw, grp = threadIdx.x / cw;
   float acc = 0.f;
-  if (col < C)
-    for (int r = blockIdx.x * groups + grp; r < rows; r += gridDim.x * groups) acc += x[(int64_t)r * C + col];
+  if (col < C) {
+    // four rows in flight per thread (the loop is a chain of L2 / HBM round trips otherwise); the order of the additions is
+    // fixed by (grid, rows) alone
+    const int step = gridDim.x * groups;
+    int r = blockIdx.x * groups + grp;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      const float v0 = x[(int64_t)r * C + col], v1 = x[(int64_t)(r + step) * C + col];
+      const float v2 = x[(int64_t)(r + 2 * step) * C + col], v3 = x[(int64_t)(r + 3 * step) * C + col];
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; r < rows; r += step) a0 += x[(int64_t)r * C + col];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   sm[threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x < C) {
@@ -171,6 +183,35 @@ colsum_partials_kernel(const float* __restrict__ x, int rows, int C, float* __re
     for (int g = 0; g < groups; ++g) t += sm[g * cw + threadIdx.x];
     part[(int64_t)blockIdx.x * C + threadIdx.x] = t;
   }
+}
+
+// First convolution of the first Stack on the tile engine: uint8 frames [n][H][W][C <= 8] of the two batch halves -> bf16
+// [n][H][W][8] holding the exact integers 0..255 (the 1/255 is applied to the fp32 accumulator), channels C..7 zero, so
+// that one pixel is one 16-byte chunk of the implicit-GEMM gather.
+static __global__ void __launch_bounds__(256)
+u8_frames_pad8_bf16_kernel(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, int64_t n_pix0, int64_t n_pix, int C,
+                           __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * 256) {
+    const uint8_t* src = i < n_pix0 ? in0 + i * C : in1 + (i - n_pix0) * C;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __float2bfloat16_rn(c < C ? (float)src[c] : 0.f);
+    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// bf16 kernel [3][3][C][Cout] -> [3][3][8][Cout] with zero rows for the padded channels
+static __global__ void pad_first_kernel_bf16(const __nv_bfloat16* __restrict__ w, int C, int Cout, __nv_bfloat16* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 72 * Cout) return;
+  const int co = i % Cout, r = i / Cout, c = r % 8, tap = r / 8;
+  wp[i] = c < C ? w[(tap * C + c) * Cout + co] : __float2bfloat16_rn(0.f);
+}
+// gradient of the padded kernel [3][3][8][Cout] (fp32) -> the real kernel's gradient [3][3][C][Cout]
+static __global__ void unpad_first_kernel_grad(const float* __restrict__ gp, int C, int Cout, float* __restrict__ g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * C * Cout) return;
+  const int co = i % Cout, r = i / Cout, c = r % C, tap = r / C;
+  g[i] = gp[(tap * 8 + c) * Cout + co];
 }
 
 // dst += src  (the two branches of a residual connection meet here in the backward pass); optional bf16 copy of the sum

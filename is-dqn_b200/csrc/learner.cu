@@ -16,9 +16,9 @@ int isdqn_tc_train_dispatch(const isdqn_net* net, const isdqn_train* tr, const i
 // building blocks of the tile engine (tc_learner.cu)
 bool isdqn_tc_conv_ok(const isdqn::Layer& L);
 int isdqn_tc_conv_fwd(const isdqn::Layer& L, const void* x16, int rows, const void* w16, const float* params, void* out16,
-                      cudaStream_t s);
+                      cudaStream_t s, float in_scale = 1.0f);
 int isdqn_tc_conv_wgrad(const isdqn::Layer& L, const void* x16, const void* dz16, float* part, int rows_l, int splits,
-                        int* real_splits, cudaStream_t s);
+                        int* real_splits, cudaStream_t s, float in_scale = 1.0f);
 int isdqn_tc_conv_dgrad(const isdqn::Layer& L, const void* dz16, const void* w16, float* dx, int B, cudaStream_t s);
 int isdqn_cast_bf16_launch(const float* src, void* dst16, int64_t n, cudaStream_t s);
 int isdqn_adam_launch(float* d_params, const float* d_grads, float* d_mu, float* d_nu, const int32_t* d_count, float lr,
@@ -74,9 +74,19 @@ void fill_conv_geom(const Layer& L, ConvArgs* a) {
   a->K = L.in_dim;
 }
 
+// Hidden Dense layers of an `fc` plan on the tile engine (the Dense tail of the impala network in tensor-core mode):
+// bf16 copies of the layer inputs, bf16 kernels out of the parameter shadow, fp32 partials / LayerNorm / head as always.
+struct DenseTc {
+  const __nv_bfloat16* in16;                        // bf16 copy of the plan's input [rows][in_dim of layer 0]
+  __nv_bfloat16* act16[ISDQN_MAX_FEATURES + 1];     // bf16 copy of the output of hidden layer l [rows][out_dim]
+  __nv_bfloat16* dz16;                              // [B][widest hidden layer]: gradient of the pre-activation output
+  const __nv_bfloat16* shadow;                      // bf16 parameters, same offsets as the plan's
+};
+bool dense_tc_ok(const Layer& L) { return L.type == 1 && L.in_dim % 8 == 0 && L.out_dim % 8 == 0; }
+
 // Forward through every layer.  in0/in1: the two halves of concat(s, s') (in1 may be null, n0 = rows then).
 int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params, const void* in0, const void* in1,
-                int n0, int rows, int rows_train, int in_kind, cudaStream_t s) {
+                int n0, int rows, int rows_train, int in_kind, cudaStream_t s, const DenseTc* dtc = nullptr) {
   for (int l = 0; l < p.n_layers; ++l) {
     const Layer& L = p.L[l];
     const bool first = l == 0;
@@ -109,10 +119,23 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
         ISDQN_CUDA_CHECK(launch_head_fwd(s, wsp(ws, w.act[l - 1]), params + L.w_off, params + L.b_off, L.in_dim, L.out_dim, out, rows));
         continue;
       }
-      const bool direct = real_splits == 1 && !L.has_ln && !L.relu;
+      const bool on_tc = dtc != nullptr && l + 1 < p.n_layers && dense_tc_ok(L) && (!first || in1 == nullptr);
+      const bool direct = !on_tc && real_splits == 1 && !L.has_ln && !L.relu;
       float* part = direct ? out : wsp(ws, w.fwd_part);
       const int64_t split_stride = (int64_t)rows * L.out_dim;
-      for (int half = 0; half < 2; ++half) {
+      int n_parts = real_splits;
+      if (on_tc) {
+        // the tile engine splits the K axis in 64-element chunks: ask for a split count that is a fixed point of its rule
+        // (chunks per split = ceil(chunks / splits), splits = ceil(chunks / chunks per split)), so that exactly n_parts
+        // partials are written
+        const int chunks = ceil_div(L.in_dim, 64);
+        n_parts = real_splits < chunks ? real_splits : chunks;
+        for (int it = 0; it < 8; ++it) n_parts = ceil_div(chunks, ceil_div(chunks, n_parts));
+        int rc = isdqn_tc_gemm_bf16(first ? dtc->in16 : dtc->act16[l - 1], L.in_dim, 0, dtc->shadow + L.w_off, L.out_dim, 1, part,
+                                    rows, L.out_dim, L.in_dim, n_parts, s);
+        if (rc) return rc;
+      }
+      for (int half = 0; half < 2 && !on_tc; ++half) {
         GemmArgs g;
         int m_begin, m_count;
         if (first) {
@@ -134,8 +157,9 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
       if (!direct) {
         ISDQN_PROF(s, "dense_finalize");
         dense_finalize_kernel<<<rows, kRowThreads, 0, s>>>(
-            part, real_splits, split_stride, rows, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu, out,
-            rows_train > 0 ? wsp(ws, w.xhat[l]) : nullptr, rows_train > 0 ? wsp(ws, w.rstd[l]) : nullptr, rows_train);
+            part, n_parts, split_stride, rows, L.out_dim, params + L.b_off, ln_g, ln_b, L.relu, out,
+            rows_train > 0 ? wsp(ws, w.xhat[l]) : nullptr, rows_train > 0 ? wsp(ws, w.rstd[l]) : nullptr, rows_train,
+            on_tc ? dtc->act16[l] : nullptr);
         ISDQN_LAUNCH_CHECK();
       }
     }
@@ -199,7 +223,7 @@ int run_loss(const Plan& p, const isdqn_net* net, const isdqn_train* tr, const i
 
 // d_input (optional): receives dL/d(input of layer 0) [B][in_dim] (the impala torso continues the backward pass from it)
 int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train* tr, const isdqn_batch* b, int in_kind,
-                 cudaStream_t s, float* d_input = nullptr) {
+                 cudaStream_t s, float* d_input = nullptr, const DenseTc* dtc = nullptr) {
   const int B = tr->batch;
   const float* params = tr->d_params;
   float* grads = tr->d_grads;
@@ -214,8 +238,14 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
     const Layer& L = p.L[l];
     const bool first = l == 0;
     const int rows_l = B * L.pix;
+    const bool on_tc = dtc != nullptr && l + 1 < p.n_layers && dense_tc_ok(L);  // (its dz16 was written by the step below)
     // ---- weight gradient
-    if (L.type == 1) {
+    if (on_tc) {
+      // dW[in][out] = X^T dz: both operands MN-major ([k = b][in], [k = b][out])
+      int rc = isdqn_tc_gemm_bf16(first ? dtc->in16 : dtc->act16[l - 1], L.in_dim, 1, dtc->dz16, L.out_dim, 1, grads + L.w_off,
+                                  L.in_dim, L.out_dim, B, 1, s);
+      if (rc) return rc;
+    } else if (L.type == 1) {
       GemmArgs g;  // dW[in][out] = X^T dz : A(m'=in, k'=b) = X[b*in_dim + in]
       g.A = first ? reinterpret_cast<const float*>(b->d_state) : wsp(ws, w.act[l - 1]);
       g.sam = 1; g.sak = L.in_dim;
@@ -246,7 +276,11 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
     // ---- input gradient = dL/d(out of layer l-1), then through that layer's ReLU + LayerNorm
     const Layer& P = p.L[first ? 0 : l - 1];
     float* dprev = first ? d_input : wsp(ws, w.dbuf[l & 1]);
-    if (L.type == 1) {
+    if (on_tc) {
+      // dX[b][in] = dz[b][out] W^T: A = dz16 [b][out] and B = W16 [in][out] are both K-major
+      int rc = isdqn_tc_gemm_bf16(dtc->dz16, L.out_dim, 0, dtc->shadow + L.w_off, L.out_dim, 0, dprev, B, L.in_dim, L.out_dim, 1, s);
+      if (rc) return rc;
+    } else if (L.type == 1) {
       GemmArgs g;  // dX[b][in] = dz[b][out] W^T : B(k=out, n=in) = W[in*out_dim + out]
       g.A = dz; g.sam = L.out_dim; g.sak = 1;
       g.B = params + L.w_off; g.sbk = 1; g.sbn = L.out_dim;
@@ -265,13 +299,14 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       const float* g_ = P.has_ln ? params + P.g_off : nullptr;
       const float* b_ = P.has_ln ? params + P.beta_off : nullptr;
       ISDQN_PROF(s, "ln_relu_bwd");
+      __nv_bfloat16* dz16_p = (dtc != nullptr && dense_tc_ok(P)) ? dtc->dz16 : nullptr;
       if (ln_bwd_use_warp(P.out_dim)) {
         ISDQN_CUDA_CHECK(launch_ln_relu_bwd_warp(w.col_ctas[l - 1], s, dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_,
-                                wsp(ws, w.act[l - 1]), rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]), nullptr, nullptr));
+                                wsp(ws, w.act[l - 1]), rows_p, P.out_dim, wsp(ws, w.colpart[l - 1]), dz16_p, nullptr));
       } else {
         ln_relu_bwd_block_kernel<<<w.col_ctas[l - 1], kRowThreads, 0, s>>>(
             dprev, wsp(ws, w.xhat[l - 1]), wsp(ws, w.rstd[l - 1]), g_, b_, wsp(ws, w.act[l - 1]), rows_p, P.out_dim,
-            wsp(ws, w.colpart[l - 1]));
+            wsp(ws, w.colpart[l - 1]), dz16_p);
       }
       ISDQN_LAUNCH_CHECK();
     }
@@ -390,7 +425,7 @@ struct ImpalaPartials {
 };
 int colsum_ctas_for(int rows) {
   int c = ceil_div(rows, 256);
-  if (c > 2 * kNumSMs) c = 2 * kNumSMs;
+  if (c > 4 * kNumSMs) c = 4 * kNumSMs;
   return c < 1 ? 1 : c;
 }
 void impala_partials(const ImpalaStack& S, int B, ImpalaPartials* o) {
@@ -496,8 +531,22 @@ struct ImpalaTc {
     int64_t x3;          // bf16 copy of the stack output (input of the next stack's Conv_0); -1 for the last stack
   } st[3];
   int64_t G, T, G0;  // bf16 copies of the gradients the weight / input gradient GEMMs consume
+  // first convolution (3 x 3 x obs_c <= 8 input channels) on the tile engine: frames as bf16 integers 0..255 with the
+  // channel axis zero-padded to 8 (one 16-byte chunk per pixel), the kernel padded alike, its gradient un-padded at the end
+  int first_tc;
+  int64_t xpad, wpad, gpad;  // bf16 [rows][H][W][8]; bf16 [3][3][8][C]; fp32 [3][3][8][C]
+  // Dense tail: bf16 copies of its input and of the hidden activations, bf16 dz of a hidden layer
+  int64_t tf, tact[ISDQN_MAX_FEATURES + 1], tdz;
   int64_t total;
 };
+Layer impala_first_layer_padded(const ImpalaStack& S) { return impala_conv_layer(S.Hin, S.Win, 8, S.C); }
+bool first_conv_tc_on() {  // A/B: ISDQN_IMPALA_FIRST_TC=0 keeps Stack_0/Conv_0 on the CUDA-core kernels
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_IMPALA_FIRST_TC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 void carve_impala_tc(const ImpalaPlan& ip, int rows, int B, ImpalaTc* t) {
   int64_t off = 0;
   auto take = [&](int64_t n_elems) {
@@ -506,13 +555,15 @@ void carve_impala_tc(const ImpalaPlan& ip, int rows, int B, ImpalaTc* t) {
     return r;
   };
   int64_t max_x0 = 0, max_c = 0, max_g = 0, max_g0 = 0;
+  t->first_tc = (ip.st[0].Cin <= 8 && isdqn_tc_conv_ok(impala_first_layer_padded(ip.st[0])) && first_conv_tc_on()) ? 1 : 0;
   for (int s = 0; s < 3; ++s) {
     const ImpalaStack& S = ip.st[s];
     const int64_t a = (int64_t)S.Hin * S.Win * S.C, n = (int64_t)S.H * S.W * S.C;
-    if (s > 0 && rows * a > max_x0) max_x0 = rows * a;
+    const bool a_tc = s > 0 || t->first_tc;
+    if (a_tc && rows * a > max_x0) max_x0 = rows * a;
     if (rows * n > max_c) max_c = rows * n;
     if (B * n > max_g) max_g = B * n;
-    if (s > 0 && B * a > max_g0) max_g0 = B * a;
+    if (a_tc && B * a > max_g0) max_g0 = B * a;
   }
   t->x0 = take(max_x0);
   t->c = take(max_c);
@@ -531,6 +582,24 @@ void carve_impala_tc(const ImpalaPlan& ip, int rows, int B, ImpalaTc* t) {
     t->G0 = take(max_g0);
   } else {
     t->G = t->T = t->G0 = -1;
+  }
+  {
+    t->tf = take((int64_t)rows * ip.flat);
+    int widest = 8;
+    for (int l = 0; l < ISDQN_MAX_FEATURES + 1; ++l) t->tact[l] = -1;
+    for (int l = 0; l + 1 < ip.tail.n_layers; ++l) {
+      t->tact[l] = take((int64_t)rows * ip.tail.L[l].out_dim);
+      if (ip.tail.L[l].out_dim > widest) widest = ip.tail.L[l].out_dim;
+    }
+    t->tdz = B > 0 ? take((int64_t)B * widest) : -1;
+  }
+  if (t->first_tc) {
+    const ImpalaStack& S = ip.st[0];
+    t->xpad = take((int64_t)rows * S.Hin * S.Win * 8);
+    t->wpad = take((int64_t)72 * S.C);
+    t->gpad = B > 0 ? take((int64_t)2 * 72 * S.C) : -1;  // fp32: twice the bf16 element size
+  } else {
+    t->xpad = t->wpad = t->gpad = -1;
   }
   t->total = off;
 }
@@ -565,6 +634,20 @@ int grid_for(int64_t n) {
   return g < 1 ? 1 : (int)g;
 }
 
+bool tail_tc_on() {  // A/B: ISDQN_IMPALA_TAIL_TC=0 keeps the Dense tail on the CUDA-core GEMMs
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_IMPALA_TAIL_TC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+void fill_dense_tc(const ImpalaPlan& ip, const ImpalaTc& t, void* wt, const __nv_bfloat16* shadow, DenseTc* d) {
+  d->in16 = w16(wt, t.tf);
+  for (int l = 0; l < ISDQN_MAX_FEATURES + 1; ++l) d->act16[l] = w16(wt, t.tact[l]);
+  d->dz16 = w16(wt, t.tdz);
+  d->shadow = shadow + ip.tail_base;
+}
+
 // t / wt / shadow: tensor-core mode (bf16 activations in wt, bf16 kernels out of the parameter shadow); null = fp32 mode
 int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const float* params, const void* in0, const void* in1,
                    int n0, int rows, int rows_train, int in_kind, cudaStream_t s, const ImpalaTc* t = nullptr, void* wt = nullptr,
@@ -581,9 +664,24 @@ int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const floa
     uint8_t* widx = reinterpret_cast<uint8_t*>(wsp(ws, O.widx));
     const int n_train = rows_train > 0 ? rows_train : 0;
     int rc;
-    if (tc && si > 0) {
+    if (tc && (si > 0 || t->first_tc)) {
       La.relu = 0; La.has_ln = 0; La.b_off = S.b[0];
-      rc = isdqn_tc_conv_fwd(La, w16(wt, t->st[si - 1].x3), rows, shadow + S.w[0], params, w16(wt, t->x0), s);
+      if (si == 0) {
+        Layer Lp = impala_first_layer_padded(S);
+        Lp.relu = 0; Lp.has_ln = 0; Lp.b_off = S.b[0];
+        const int64_t n_pix = (int64_t)rows * S.Hin * S.Win;
+        ISDQN_PROF(s, "frames_pad8_bf16");
+        u8_frames_pad8_bf16_kernel<<<grid_for(n_pix), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(in0),
+                                                                  reinterpret_cast<const uint8_t*>(in1),
+                                                                  (int64_t)n0 * S.Hin * S.Win, n_pix, S.Cin, w16(wt, t->xpad));
+        ISDQN_LAUNCH_CHECK();
+        pad_first_kernel_bf16<<<ceil_div(72 * S.C, 256), 256, 0, s>>>(shadow + S.w[0], S.Cin, S.C, w16(wt, t->wpad));
+        ISDQN_LAUNCH_CHECK();
+        rc = isdqn_tc_conv_fwd(Lp, w16(wt, t->xpad), rows, w16(wt, t->wpad), params, w16(wt, t->x0), s,
+                               in_kind == IN_F32 ? 1.0f : 1.0f / 255.0f);
+      } else {
+        rc = isdqn_tc_conv_fwd(La, w16(wt, t->st[si - 1].x3), rows, shadow + S.w[0], params, w16(wt, t->x0), s);
+      }
       if (rc) return rc;
       ISDQN_PROF(s, "maxpool_fwd");
       maxpool3s2_fwd_kernel<__nv_bfloat16><<<grid_for(n_out), 256, 0, s>>>(w16(wt, t->x0), rows, S.Hin, S.Win, S.C, S.H, S.W,
@@ -630,10 +728,12 @@ int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const floa
   const ImpalaStack& L = ip.st[2];
   ISDQN_PROF(s, "ln_relu_fwd");
   ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, prev, rows * L.H * L.W, L.C, ip.has_ln ? params + ip.fin_g : nullptr,
-                                           ip.has_ln ? params + ip.fin_beta : nullptr, wsp(ws, w.tf), nullptr, wsp(ws, w.xhf),
-                                           wsp(ws, w.rsf), rows_train * L.H * L.W));
+                                           ip.has_ln ? params + ip.fin_beta : nullptr, wsp(ws, w.tf), tc ? w16(wt, t->tf) : nullptr,
+                                           wsp(ws, w.xhf), wsp(ws, w.rsf), rows_train * L.H * L.W));
+  DenseTc dtc;
+  if (tc) fill_dense_tc(ip, *t, wt, shadow, &dtc);
   return run_forward(ip.tail, w.tailw, wsp(ws, w.tail), params + ip.tail_base, wsp(ws, w.tf), nullptr, rows, rows, rows_train,
-                     IN_F32, s);
+                     IN_F32, s, (tc && tail_tc_on()) ? &dtc : nullptr);
 }
 
 int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isdqn_train* tr, const isdqn_batch* b, int in_kind,
@@ -650,7 +750,9 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     trt.d_grads = tr->d_grads + ip.tail_base;
     isdqn_batch bt = *b;
     bt.d_state = wsp(ws, w.tf);
-    int rc = run_backward(ip.tail, w.tailw, wsp(ws, w.tail), &trt, &bt, IN_F32, s, G);
+    DenseTc dtc;
+    if (tc) fill_dense_tc(ip, *t, wt, shadow, &dtc);
+    int rc = run_backward(ip.tail, w.tailw, wsp(ws, w.tail), &trt, &bt, IN_F32, s, G, (tc && tail_tc_on()) ? &dtc : nullptr);
     if (rc) return rc;
   }
   SegmentList segs;
@@ -736,7 +838,7 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
       add_inplace_kernel<<<grid_for(n), 256, 0, s>>>(G, T2, n, G16);
       ISDQN_LAUNCH_CHECK();
     }
-    const bool a_tc = tc && si > 0;
+    const bool a_tc = tc && (si > 0 || t->first_tc);
     ISDQN_PROF(s, "maxpool_bwd");
     maxpool3s2_bwd_kernel<<<grid_for((int64_t)B * S.Hin * S.Win * C), 256, 0, s>>>(
         G, reinterpret_cast<const uint8_t*>(wsp(ws, O.widx)), B, S.Hin, S.Win, C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, G0,
@@ -747,10 +849,25 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     int rc = colsum(G0, rows_a, C, pb + P.colsum[0], P.colsum_ctas[0], grads + S.b[0]);
     if (rc) return rc;
     const void* in = si == 0 ? b->d_state : static_cast<const void*>(wsp(ws, w.st[si - 1].x[2]));
-    rc = conv_bwd(La, in, si == 0 ? in_kind : IN_F32, a_tc ? w16(wt, t->st[si - 1].x3) : nullptr, G0, G016, rows_a,
-                  pb + P.wpart[0], P.wsplits[0], S.w[0], si > 0 ? G : nullptr, a_tc);
-    if (rc) return rc;
-    if (a_tc) {  // the input gradient came out in fp32: the next stack's GEMMs want it in bf16 as well
+    float* gpad = nullptr;
+    if (a_tc && si == 0) {
+      // padded first convolution: partials [splits][3][3][8][C] -> gpad, un-padded into the gradient after the reduction.
+      // (The partial scratch was sized for 9 * Cin rows per split: the padded kernel has 72, so fewer splits fit.)
+      const Layer Lp = impala_first_layer_padded(S);
+      gpad = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wt) + t->gpad);
+      int splits = (int)(((int64_t)P.wsplits[0] * 9 * S.Cin) / 72);
+      if (splits < 1) splits = 1;
+      int sp = 0;
+      rc = isdqn_tc_conv_wgrad(Lp, w16(wt, t->xpad), G016, pb + P.wpart[0], rows_a, splits, &sp, s,
+                               in_kind == IN_F32 ? 1.0f : 1.0f / 255.0f);
+      if (rc) return rc;
+      add_seg(pb + P.wpart[0], gpad, (int64_t)72 * C, 72 * C, sp);
+    } else {
+      rc = conv_bwd(La, in, si == 0 ? in_kind : IN_F32, (a_tc && si > 0) ? w16(wt, t->st[si - 1].x3) : nullptr, G0, G016, rows_a,
+                    pb + P.wpart[0], P.wsplits[0], S.w[0], si > 0 ? G : nullptr, a_tc);
+      if (rc) return rc;
+    }
+    if (a_tc && si > 0) {  // the input gradient came out in fp32: the next stack's GEMMs want it in bf16 as well
       const ImpalaStack& Pn = ip.st[si - 1];
       rc = isdqn_cast_bf16_launch(G, G16, (int64_t)B * Pn.H * Pn.W * Pn.C, s);
       if (rc) return rc;
@@ -759,6 +876,10 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     ISDQN_PROF(s, "reduce_segments");
     ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s));
     segs.count = 0;
+    if (gpad) {
+      unpad_first_kernel_grad<<<ceil_div(9 * S.Cin * C, 256), 256, 0, s>>>(gpad, S.Cin, C, grads + S.w[0]);
+      ISDQN_LAUNCH_CHECK();
+    }
   }
   return ISDQN_OK;
 }

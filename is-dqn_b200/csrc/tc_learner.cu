@@ -1404,19 +1404,20 @@ static bool blocks_tma_on() {  // TMA-fed problems where the shape allows (A/B: 
   }();
   return on;
 }
-int isdqn_tc_conv_fwd(const Layer& L, const void* x16, int rows, const void* w16_, const float* params, void* out16, cudaStream_t s) {
+int isdqn_tc_conv_fwd(const Layer& L, const void* x16, int rows, const void* w16_, const float* params, void* out16, cudaStream_t s,
+                      float in_scale) {
   if (blocks_tma_on() && conv_fwd_tma_ok(L))
     return launch_conv_fwd_tma(L, reinterpret_cast<const bf16*>(x16), rows, reinterpret_cast<const bf16*>(w16_), nullptr, params,
-                               reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, 1.0f, s);
+                               reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, in_scale, s);
   return launch_conv_fwd_tc<false>(L, x16, nullptr, rows, rows, reinterpret_cast<const bf16*>(w16_), params,
-                                   reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, s);
+                                   reinterpret_cast<bf16*>(out16), nullptr, nullptr, 0, s, in_scale);
 }
 int isdqn_tc_conv_wgrad(const Layer& L, const void* x16, const void* dz16, float* part, int rows_l, int splits, int* real_splits,
-                        cudaStream_t s) {
+                        cudaStream_t s, float in_scale) {
   if (blocks_tma_on() && conv_wgrad_tma_ok(L))
     return launch_conv_wgrad_tma(L, reinterpret_cast<const bf16*>(x16), reinterpret_cast<const bf16*>(dz16), part, rows_l / L.pix,
-                                 splits, real_splits, s, 1.0f, L.ksz, 1);
-  return launch_conv_wgrad_tc<false>(L, x16, reinterpret_cast<const bf16*>(dz16), part, rows_l, splits, real_splits, s);
+                                 splits, real_splits, s, in_scale, L.ksz, 1);
+  return launch_conv_wgrad_tc<false>(L, x16, reinterpret_cast<const bf16*>(dz16), part, rows_l, splits, real_splits, s, in_scale);
 }
 int isdqn_tc_conv_dgrad(const Layer& L, const void* dz16, const void* w16_, float* dx, int B, cudaStream_t s) {
   return launch_conv_dgrad_tc(L, reinterpret_cast<const bf16*>(dz16), reinterpret_cast<const bf16*>(w16_), dx, B, s);

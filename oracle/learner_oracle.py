@@ -178,12 +178,14 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
         x = x.reshape(x.shape[0], -1)
     elif arch == "impala":
         def conv3(x, mod):  # nn.Conv(features, (3, 3)): stride 1, padding SAME = 1 on every side
-            # emulate_bf16: every convolution but the first (K = 36, CUDA cores) runs on the tensor cores with bf16 input,
-            # kernel and output gradient, and its epilogue emits bf16
-            on_tc = emulate_bf16 and mod != "Stack_0/Conv_0"
+            # emulate_bf16: the convolutions run on the tensor cores with bf16 input, kernel and output gradient, and their
+            # epilogues emit bf16 (the frames of the very first one are exact integers, the 1/255 meets the fp32 accumulator)
+            on_tc = emulate_bf16
             w = params[mod]["kernel"]
             if on_tc:
-                w, x = rnd(w), rnd(x)
+                w = rnd(w)
+                if mod != "Stack_0/Conv_0":
+                    x = rnd(x)
             y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
             if on_tc:
                 y = _RoundGradBf16.apply(y)
@@ -215,12 +217,10 @@ def forward(params: Params, x: torch.Tensor, arch: str, layer_norm: bool, n_head
             ln = 1
         if taps is not None:
             taps.append(x)
-        x = torch.relu(x).reshape(x.shape[0], -1)
+        x = rnd(torch.relu(x)).reshape(x.shape[0], -1)  # (the hidden Dense layers read a bf16 copy)
     else:
         x = x.to(dtype)
     n_dense = sum(1 for m in params if m.startswith("Dense_"))
-    if arch == "impala":  # the Dense tail of the impala network stays in fp32
-        emulate_bf16, rnd = False, (lambda t: t)
     for d in range(n_dense - 1):
         y = x @ rnd(params[f"Dense_{d}"]["kernel"])
         if emulate_bf16:
