@@ -671,12 +671,11 @@ int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const floa
         Lp.relu = 0; Lp.has_ln = 0; Lp.b_off = S.b[0];
         const int64_t n_pix = (int64_t)rows * S.Hin * S.Win;
         ISDQN_PROF(s, "frames_pad8_bf16");
-        u8_frames_pad8_bf16_kernel<<<grid_for(n_pix), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(in0),
-                                                                  reinterpret_cast<const uint8_t*>(in1),
-                                                                  (int64_t)n0 * S.Hin * S.Win, n_pix, S.Cin, w16(wt, t->xpad));
-        ISDQN_LAUNCH_CHECK();
-        pad_first_kernel_bf16<<<ceil_div(72 * S.C, 256), 256, 0, s>>>(shadow + S.w[0], S.Cin, S.C, w16(wt, t->wpad));
-        ISDQN_LAUNCH_CHECK();
+        ISDQN_CUDA_CHECK(launch_pdl(u8_frames_pad8_bf16_kernel, dim3(grid_for(n_pix)), dim3(256), 0, s,
+                                    reinterpret_cast<const uint8_t*>(in0), reinterpret_cast<const uint8_t*>(in1),
+                                    (int64_t)n0 * S.Hin * S.Win, n_pix, S.Cin, w16(wt, t->xpad)));
+        ISDQN_CUDA_CHECK(launch_pdl(pad_first_kernel_bf16, dim3(ceil_div(72 * S.C, 256)), dim3(256), 0, s, shadow + S.w[0], S.Cin, S.C,
+                                    w16(wt, t->wpad)));
         rc = isdqn_tc_conv_fwd(Lp, w16(wt, t->xpad), rows, w16(wt, t->wpad), params, w16(wt, t->x0), s,
                                in_kind == IN_F32 ? 1.0f : 1.0f / 255.0f);
       } else {
@@ -684,24 +683,33 @@ int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const floa
       }
       if (rc) return rc;
       ISDQN_PROF(s, "maxpool_fwd");
-      maxpool3s2_fwd_kernel<__nv_bfloat16><<<grid_for(n_out), 256, 0, s>>>(w16(wt, t->x0), rows, S.Hin, S.Win, S.C, S.H, S.W,
-                                                                          S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]), widx, n_train);
+      if (S.C % 8 == 0) {
+        ISDQN_CUDA_CHECK(launch_pdl(maxpool3s2_fwd_bf16x8_kernel, dim3(grid_for(n_out / 8)), dim3(256), 0, s, w16(wt, t->x0), rows,
+                                    S.Hin, S.Win, S.C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]), widx, n_train));
+      } else {
+        ISDQN_CUDA_CHECK(launch_pdl(maxpool3s2_fwd_kernel<__nv_bfloat16>, dim3(grid_for(n_out)), dim3(256), 0, s, w16(wt, t->x0),
+                                    rows, S.Hin, S.Win, S.C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]), widx, n_train));
+      }
     } else {
       rc = impala_conv(La, si == 0 ? in0 : prev, si == 0 ? in1 : nullptr, si == 0 ? n0 : rows, rows, si == 0 ? in_kind : IN_F32,
                        params + S.w[0], params + S.b[0], 0, nullptr, x0, s);
       if (rc) return rc;
       ISDQN_PROF(s, "maxpool_fwd");
-      maxpool3s2_fwd_kernel<float><<<grid_for(n_out), 256, 0, s>>>(x0, rows, S.Hin, S.Win, S.C, S.H, S.W, S.pool_pad_y, S.pool_pad_x,
-                                                                 wsp(ws, O.x[0]), widx, n_train);
+      ISDQN_CUDA_CHECK(launch_pdl(maxpool3s2_fwd_kernel<float>, dim3(grid_for(n_out)), dim3(256), 0, s, x0, rows, S.Hin, S.Win, S.C,
+                                  S.H, S.W, S.pool_pad_y, S.pool_pad_x, wsp(ws, O.x[0]), widx, n_train));
     }
     ISDQN_LAUNCH_CHECK();
     const int prow = rows * S.H * S.W;
     for (int j = 0; j < 2; ++j) {
       ISDQN_PROF(s, "ln_relu_fwd");
-      ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, wsp(ws, O.x[j]), prow, S.C, ip.has_ln ? params + S.g[j] : nullptr,
+      // tensor-core mode, j == 1: the skip connection of block 0 (x[1] = x[0] + bf16 output of Conv_2) is folded into this
+      // launch, which reads x[0] and the convolution output and writes x[1] next to its normalised form
+      const bool fold = tc && j == 1;
+      ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, wsp(ws, O.x[fold ? 0 : j]), prow, S.C, ip.has_ln ? params + S.g[j] : nullptr,
                                                ip.has_ln ? params + S.beta[j] : nullptr, tc ? nullptr : wsp(ws, O.t[j]),
                                                tc ? w16(wt, t->st[si].t[j]) : nullptr, wsp(ws, O.xhat[j]), wsp(ws, O.rstd[j]),
-                                               rows_train * S.H * S.W));
+                                               rows_train * S.H * S.W, fold ? w16(wt, t->c) : nullptr,
+                                               fold ? wsp(ws, O.x[1]) : nullptr));
       if (tc) {
         Lb.has_ln = 0;
         Lb.relu = 1; Lb.b_off = S.b[1 + 2 * j];
@@ -710,10 +718,11 @@ int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const floa
         Lb.relu = 0; Lb.b_off = S.b[2 + 2 * j];
         rc = isdqn_tc_conv_fwd(Lb, w16(wt, t->st[si].u[j]), rows, shadow + S.w[2 + 2 * j], params, w16(wt, t->c), s);
         if (rc) return rc;
-        ISDQN_PROF(s, "residual_add");
-        residual_add_fwd_kernel<<<grid_for(n_out), 256, 0, s>>>(wsp(ws, O.x[j]), w16(wt, t->c), wsp(ws, O.x[j + 1]),
-                                                               j == 1 ? w16(wt, t->st[si].x3) : nullptr, n_out);
-        ISDQN_LAUNCH_CHECK();
+        if (j == 1 && si < 2) {  // stack output: the next stack's first convolution reads the bf16 copy
+          ISDQN_PROF(s, "residual_add");
+          ISDQN_CUDA_CHECK(launch_pdl(residual_add_fwd_kernel, dim3(grid_for(n_out)), dim3(256), 0, s, wsp(ws, O.x[1]),
+                                      w16(wt, t->c), wsp(ws, O.x[2]), w16(wt, t->st[si].x3), n_out));
+        }
       } else {
         rc = impala_conv(Lb, wsp(ws, O.t[j]), nullptr, rows, rows, IN_F32, params + S.w[1 + 2 * j], params + S.b[1 + 2 * j], 1,
                          nullptr, wsp(ws, O.u[j]), s);
@@ -727,9 +736,11 @@ int impala_forward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const floa
   }
   const ImpalaStack& L = ip.st[2];
   ISDQN_PROF(s, "ln_relu_fwd");
-  ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, prev, rows * L.H * L.W, L.C, ip.has_ln ? params + ip.fin_g : nullptr,
-                                           ip.has_ln ? params + ip.fin_beta : nullptr, wsp(ws, w.tf), tc ? w16(wt, t->tf) : nullptr,
-                                           wsp(ws, w.xhf), wsp(ws, w.rsf), rows_train * L.H * L.W));
+  ISDQN_CUDA_CHECK(launch_ln_relu_fwd_warp(s, tc ? wsp(ws, w.st[2].x[1]) : prev, rows * L.H * L.W, L.C,
+                                           ip.has_ln ? params + ip.fin_g : nullptr, ip.has_ln ? params + ip.fin_beta : nullptr,
+                                           wsp(ws, w.tf), tc ? w16(wt, t->tf) : nullptr, wsp(ws, w.xhf), wsp(ws, w.rsf),
+                                           rows_train * L.H * L.W, tc ? w16(wt, t->c) : nullptr,
+                                           tc ? wsp(ws, w.st[2].x[2]) : nullptr));
   DenseTc dtc;
   if (tc) fill_dense_tc(ip, *t, wt, shadow, &dtc);
   return run_forward(ip.tail, w.tailw, wsp(ws, w.tail), params + ip.tail_base, wsp(ws, w.tf), nullptr, rows, rows, rows_train,
@@ -779,8 +790,7 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
   };
   auto colsum = [&](const float* x, int rows, int C, float* part, int ctas, float* dst) -> int {
     ISDQN_PROF(s, "colsum");
-    colsum_partials_kernel<<<ctas, 256, 0, s>>>(x, rows, C, part);
-    ISDQN_LAUNCH_CHECK();
+    ISDQN_CUDA_CHECK(launch_pdl(colsum_partials_kernel, dim3(ctas), dim3(256), 0, s, x, rows, C, part));
     add_seg(part, dst, C, C, ctas);
     return ISDQN_OK;
   };
@@ -819,8 +829,13 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
       const __nv_bfloat16* t16 = tc ? w16(wt, t->st[si].t[j]) : nullptr;
       const __nv_bfloat16* u16 = tc ? w16(wt, t->st[si].u[j]) : nullptr;
       // G = dL/d(block output) = dL/d(Conv_cc output) (no activation) and, through the skip, part of dL/d(block input)
-      int rc = colsum(G, rows, C, pb + P.colsum[1 + j], P.colsum_ctas[1 + j], grads + S.b[cc]);
-      if (rc) return rc;
+      int rc;
+      if (si == 2 && j == 1) {  // (the LayerNorm backward that produced this G left its column sums in finpart[.][0])
+        add_seg(wsp(ws, w.finpart), grads + S.b[cc], 3 * (int64_t)C, C, w.fin_ctas);
+      } else {
+        rc = colsum(G, rows, C, pb + P.colsum[1 + j], P.colsum_ctas[1 + j], grads + S.b[cc]);
+        if (rc) return rc;
+      }
       rc = conv_bwd(Lb, wsp(ws, O.u[j]), IN_F32, u16, G, G16, rows, pb + P.wpart[cc], P.wsplits[cc], S.w[cc], T1, tc);
       if (rc) return rc;
       // through relu(Conv_cb(.)): T1 -> dL/d(Conv_cb output)
@@ -835,15 +850,21 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
                    pb + P.colpart[2 * j + 1], P.col_ctas, nullptr, true);
       if (rc) return rc;
       ISDQN_PROF(s, "residual_add");
-      add_inplace_kernel<<<grid_for(n), 256, 0, s>>>(G, T2, n, G16);
-      ISDQN_LAUNCH_CHECK();
+      ISDQN_CUDA_CHECK(launch_pdl(add_inplace_kernel, dim3(grid_for(n)), dim3(256), 0, s, G, T2, n, G16));
     }
     const bool a_tc = tc && (si > 0 || t->first_tc);
     ISDQN_PROF(s, "maxpool_bwd");
-    maxpool3s2_bwd_kernel<<<grid_for((int64_t)B * S.Hin * S.Win * C), 256, 0, s>>>(
-        G, reinterpret_cast<const uint8_t*>(wsp(ws, O.widx)), B, S.Hin, S.Win, C, S.H, S.W, S.pool_pad_y, S.pool_pad_x, G0,
-        a_tc ? G016 : nullptr);
-    ISDQN_LAUNCH_CHECK();
+    {
+      const int64_t n_in = (int64_t)B * S.Hin * S.Win * C;
+      const uint8_t* widx = reinterpret_cast<const uint8_t*>(wsp(ws, O.widx));
+      if (C % 4 == 0) {
+        ISDQN_CUDA_CHECK(launch_pdl(maxpool3s2_bwd_x4_kernel, dim3(grid_for(n_in / 4)), dim3(256), 0, s, G, widx, B, S.Hin, S.Win, C,
+                                    S.H, S.W, S.pool_pad_y, S.pool_pad_x, G0, a_tc ? G016 : nullptr));
+      } else {
+        ISDQN_CUDA_CHECK(launch_pdl(maxpool3s2_bwd_kernel, dim3(grid_for(n_in)), dim3(256), 0, s, G, widx, B, S.Hin, S.Win, C, S.H,
+                                    S.W, S.pool_pad_y, S.pool_pad_x, G0, a_tc ? G016 : nullptr));
+      }
+    }
     const Layer La = impala_conv_layer(S.Hin, S.Win, S.Cin, C);
     const int rows_a = B * S.Hin * S.Win;
     int rc = colsum(G0, rows_a, C, pb + P.colsum[0], P.colsum_ctas[0], grads + S.b[0]);
@@ -877,8 +898,8 @@ int impala_backward(const ImpalaPlan& ip, const ImpalaWs& w, void* ws, const isd
     ISDQN_CUDA_CHECK(launch_reduce_segments(segs, s));
     segs.count = 0;
     if (gpad) {
-      unpad_first_kernel_grad<<<ceil_div(9 * S.Cin * C, 256), 256, 0, s>>>(gpad, S.Cin, C, grads + S.w[0]);
-      ISDQN_LAUNCH_CHECK();
+      ISDQN_CUDA_CHECK(launch_pdl(unpad_first_kernel_grad, dim3(ceil_div(9 * S.Cin * C, 256)), dim3(256), 0, s, gpad, S.Cin, C,
+                                  grads + S.w[0]));
     }
   }
   return ISDQN_OK;
