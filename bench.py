@@ -425,8 +425,8 @@ def run_ours(args, rank, world, local_rank):
         impala = None
         if args.dtype == "bf16" and rank == 0:
             impala = {"features": list(FEATURES), "unit": "updates/s",
-                      "scope": "rank 0 only; bf16: every convolution but Stack_0/Conv_0 on the tcgen05 tile engine (gather-fed "
-                               "problems), fp32 residual stream / LayerNorm / Dense tail; f32: CUDA-core kernels (1e-5 parity)"}
+                      "scope": "rank 0 only; bf16: all convolutions and the hidden Dense layer on the tcgen05 tile engine, fp32 "
+                               "residual stream / LayerNorm / head / Adam (2e-2 parity); f32: CUDA-core kernels (1e-5 parity)"}
             for name, cd in (("bf16", "bfloat16"), ("f32", "float32")):
                 agent_i = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "impala", LR, GAMMA, 1, 1, 8000,
                                 adam_eps=ADAM_EPS, compute_dtype=cd)

@@ -163,7 +163,7 @@ int isdqn_gather_stacks(const uint8_t* d_frames, int64_t frame_stride, int32_t f
  * Flat parameter vector: leaves packed in execution order, each leaf start aligned to 8 floats:
  *   cnn: Conv_i.kernel (HWIO), Conv_i.bias, [LayerNorm_i.scale, LayerNorm_i.bias] for i=0..2, then the Dense
  *        tail; fc: Dense tail only.  Dense kernels are (in, out) row-major; activations are NHWC.
- *   impala (dqn.py:7-36, 77-86; fp32 compute only): for each Stack_s, s = 0..2 (features[s] channels):
+ *   impala (dqn.py:7-36, 77-86): for each Stack_s, s = 0..2 (features[s] channels):
  *        Conv_0.kernel (3x3 HWIO), Conv_0.bias, then per residual block j = 0, 1:
  *        [LayerNorm_j.scale, LayerNorm_j.bias,] Conv_{1+2j}.kernel, .bias, Conv_{2+2j}.kernel, .bias;
  *        then [LayerNorm_0.scale, .bias] of the DQNNet itself, then the Dense tail (Dense_0 [, LayerNorm_1], ..., head).

@@ -1,5 +1,5 @@
 """`DQNNet` on the device — mirrors `slimdqn/networks/architectures/dqn.py:7-103` (architecture_type `cnn`, `fc`
-and `impala` — the latter on the fp32 path only —, optional LayerNorm).  `batch_norm` is out of scope
+and `impala`, optional LayerNorm).  `batch_norm` is out of scope
 and raises.
 
 Parameters live in ONE flat float32 CUDA vector (leaves packed in execution order, 16-byte aligned; layout from
