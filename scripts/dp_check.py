@@ -22,7 +22,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for arch, dtype, tol in (("cnn", "float32", 2e-5), ("cnn", "bfloat16", 2e-2), ("impala", "float32", 2e-5),
+    # impala / float32: the first update agrees to 2e-7; from the second on a handful of the ~1.5 M ReLU units per sample sit
+    # within the 1e-7 parameter difference of zero and take the other branch, which Adam's division by sqrt(v) + eps turns
+    # into 2e-5 .. 5e-5 of the largest parameter (the same 1e-4 bar as tests/test_learner_gpu.py TOL_PARAM)
+    for arch, dtype, tol in (("cnn", "float32", 2e-5), ("cnn", "bfloat16", 2e-2), ("impala", "float32", 1e-4),
                              ("impala", "bfloat16", 2e-2)):
         Bg = (32 if arch == "cnn" else 8) * world
         mk = lambda: iSDQN(7, (84, 84, 4), 9, 9, [32, 64, 64, 512], True, False, arch, 6.25e-5, 0.99, 1, 1, 10**9,
