@@ -277,8 +277,8 @@ def workload_config(capacity):
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the step
-# (profiles/r01_b32_step_ncu.md; cold caches: the fp32 reads all come from DRAM, most writes are still in L2 at the end)
-NCU_TRAFFIC_BYTES = {"adam": 67_726_848, "dense_wgrad_adam": 53_222_400}
+# (profiles/r02_b32_step_ncu.md, row 13; cold caches: the fp32 reads all come from DRAM, most writes are still in L2 at the end)
+NCU_TRAFFIC_BYTES = {"adam": 67_726_848, "dense_wgrad_adam": 51_260_160}
 
 
 DENSE0 = 7744 * 512  # the hidden Dense kernel (11*11*64 -> 512)
@@ -423,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
             del agent32
         # ---- architecture_type "impala" (launch_job/atari/launch_time.sh runs both torsos with these features): fp32 path
         impala = None
-        if args.dtype == "bf16" and rank == 0:
+        if args.dtype == "bf16" and rank == 0 and not args.no_impala:
             impala = {"features": list(FEATURES), "unit": "updates/s",
                       "scope": "rank 0 only; bf16: all convolutions and the hidden Dense layer on the tcgen05 tile engine, fp32 "
                                "residual stream / LayerNorm / head / Adam (2e-2 parity); f32: CUDA-core kernels (1e-5 parity)"}
@@ -842,6 +842,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="dp mode: global batch (default 4096)")
     ap.add_argument("--width", type=int, default=None, choices=[1, 2, 4], help="dp mode: CNN width multiplier (default 2)")
     ap.add_argument("--no-dp", action="store_true", help="agents mode: skip the data-parallel sub-records (configs[4])")
+    ap.add_argument("--no-impala", action="store_true", help="skip the impala sub-record (profiling runs)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"],
                     help="bf16: tcgen05 tensor-core path (fp32 accumulate/master weights); f32: CUDA-core fp32 parity path")
     args = ap.parse_args()
