@@ -514,6 +514,33 @@ def run_ours(args, rank, world, local_rank):
             ps.check_status()
             prio["update32_device_us"] = p0.elapsed_time(p1) / 50 * 1e3
             del ps
+            # BASELINE configs[2] as a training loop: prioritized buffer (capacity = the uniform one's, inserts at the maximum
+            # priority) -> draw with probabilities -> importance-weighted step -> |TD| written back as priorities, all on
+            # the device, one graph replay per update (iSDQN.update_online_params with prioritized_beta set)
+            if not args.no_impala:
+                rbp = ReplayBuffer(PrioritizedSamplingDistribution(rank, cap), BATCH, cap, stack_size=4, update_horizon=1,
+                                   gamma=GAMMA, clipping=lambda x: np.clip(x, -1, 1), frame_capacity=cap + cap // 8 + 64)
+                t_lfill = fill_replay(rbp, 3000 + rank, n_fill, priorities="max")
+                agent_p = iSDQN(rank, OBS, N_ACTIONS, K_HEADS, FEATURES, True, False, "cnn", LR, GAMMA, 1, 1, 8000,
+                                adam_eps=ADAM_EPS, compute_dtype="bfloat16")
+                agent_p.prioritized_beta = 0.4
+                n_p = max(50, args.steps // 2)
+                for i in range(10):
+                    agent_p.update_online_params(i + 1, rbp)
+                torch.cuda.synchronize()
+                p0.record()
+                for i in range(n_p):
+                    agent_p.update_online_params(i + 1, rbp)
+                p1.record()
+                torch.cuda.synchronize()
+                rbp._sampling_distribution.check_status()
+                ms_p = p0.elapsed_time(p1)
+                prio["learner"] = {"config": "BASELINE configs[2]: prioritized replay, capacity %d, K=9 cnn+LN, batch 32, beta 0.4" % cap,
+                                   "steps": n_p, "value": n_p / (ms_p / 1e3), "unit": "updates/s", "ms_per_step": ms_p / n_p,
+                                   "fill_us_per_add": t_lfill / n_fill * 1e6,
+                                   "losses_finite": bool(np.isfinite(np.asarray(agent_p.losses_to_host_async().get())).all())}
+                del agent_p, rbp
+                torch.cuda.empty_cache()
         # ---- acting path: one greedy action for one host observation stack, read back with .item()
         act_state = np.random.default_rng(3).integers(0, 256, OBS, dtype=np.uint8)
         for i in range(20):

@@ -133,6 +133,15 @@ int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, int depth, 
                              int32_t* d_out_key, int32_t* d_out_slot, double* d_out_target, double* d_out_prob,
                              uint32_t* d_status, void* stream);
 
+/* One training batch for a CAPTURED step (size <= 1024): the draw of isdqn_sample_prioritized with the live count read on
+ * the device (*d_n_valid), the importance weights (n_valid * P(i))^-beta / max over the batch as float32 (beta read from
+ * *d_beta, so that an annealed beta needs no re-capture; d_out_weight may be NULL) and the generator advance in one launch; nothing depends on host state, so the launch can live in the same CUDA
+ * graph as the learner step and isdqn_sumtree_set_keys (new functionality: the reference never trains from its
+ * prioritized sampler; draw = samplers.py:105-116). */
+int isdqn_sample_prioritized_train(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size, const int32_t* d_n_valid,
+                                   const int32_t* d_index_to_key, int32_t capacity, int32_t* d_out_key, int32_t* d_out_slot,
+                                   double* d_out_prob, const double* d_beta, float* d_out_weight, uint32_t* d_status, void* stream);
+
 /* Scatter of host-accumulated patches into a device int32 table (index_to_key, element metadata):
  * d_table[d_patch_index[i]*width + j] = d_patch_value[i*width + j].  Later patches win. */
 int isdqn_scatter_rows_i32(int32_t* d_table, int32_t width, const int32_t* d_patch_index,

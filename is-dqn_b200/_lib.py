@@ -116,6 +116,7 @@ PROTOTYPES = {
     "isdqn_sumtree_set_ops": (C.c_int, [_P, C.c_int, _P, _I32, _P, _P, _P, _P, _P]),
     "isdqn_sample_uniform": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P]),
     "isdqn_sample_prioritized": (C.c_int, [_P, _P, C.c_int, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "isdqn_sample_prioritized_train": (C.c_int, [_P, _P, C.c_int, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "isdqn_sumtree_set_keys_workspace_bytes": (_I64, [_I32]),
     "isdqn_sumtree_set_keys": (C.c_int, [_P, C.c_int, _P, _P, _I32, _I32, _I32, C.c_double, C.c_double, _P, _I32, _P, _I32, _P, _P, _P, _I64, _P]),
     "isdqn_scatter_rows_i32": (C.c_int, [_P, _I32, _P, _P, _I32, _P]),

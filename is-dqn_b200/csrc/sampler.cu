@@ -201,6 +201,77 @@ sample_prioritized_kernel(const uint64_t* __restrict__ rng, const double* __rest
   if (st && status) atomicOr(status, st);
 }
 
+// One training batch (size <= 1024, one CTA, thread i = draw i) for a captured step: the same draw as
+// sample_prioritized_kernel with the live count read from the device, plus the importance weights of the batch
+// (n_valid * P(i)) ** -beta / max_i(.) as float32 (Schaul et al. 2016) and the generator advance, in one launch.
+__global__ void __launch_bounds__(1024)
+sample_prioritized_train_kernel(uint64_t* __restrict__ rng, const double* __restrict__ nodes, int depth, int size,
+                                const int32_t* __restrict__ n_valid_dev, const int32_t* __restrict__ index_to_key, int capacity,
+                                int32_t* __restrict__ out_key, int32_t* __restrict__ out_slot, double* __restrict__ out_prob,
+                                const double* __restrict__ beta_dev, float* __restrict__ out_weight, uint32_t* status) {
+  __shared__ double red[32];
+  const double beta = beta_dev ? *beta_dev : 0.0;
+  const PcgMirror m0 = pcg_load(rng);
+  const int n_valid = *n_valid_dev;
+  const double root = nodes[0];
+  const int first_leaf = (1 << (depth - 1)) - 1;
+  const int i = threadIdx.x;
+  uint32_t st = 0;
+  double w = 0.0;
+  if (i == 0 && root == 0.0) st |= ISDQN_ST_EMPTY_TREE;
+  if (i < size) {
+    const uint64_t o = pcg_out64_at(m0.state, m0.inc, (uint64_t)i);
+    const double u = (double)(o >> 11) * (1.0 / 9007199254740992.0);
+    double t = __dadd_rn(0.0, __dmul_rn(root - 0.0, u));
+    if (!(t >= 0.0 && t < root)) st |= ISDQN_ST_TARGET_RANGE;
+    int node = 0;
+    for (int level = 0; level < depth - 1; ++level) {
+      const int left = 2 * node + 1;
+      const double ls = __ldg(nodes + left);
+      if (t < ls) {
+        node = left;
+      } else {
+        node = left + 1;
+        t = t - ls;
+        if (level + 1 < depth - 1 && !(t < __ldg(nodes + left + 1))) st |= ISDQN_ST_DESCENT_ASSERT;
+      }
+    }
+    const int32_t index = node - first_leaf;
+    const double prob = root > 0.0 ? __ldg(nodes + node) / root : 0.0;
+    if (out_prob) out_prob[i] = prob;
+    int32_t safe = index;
+    if (index >= n_valid) {
+      st |= ISDQN_ST_INDEX_RANGE;
+      safe = n_valid > 0 ? n_valid - 1 : 0;
+    }
+    const int32_t key = n_valid == 0 ? 0 : index_to_key[safe];
+    if (out_key) out_key[i] = key;
+    if (out_slot) out_slot[i] = (int32_t)(((int64_t)key % capacity + capacity) % capacity);
+    // (a zero-probability draw was flagged above — the reference raises there; its weight is 0, not inf)
+    w = (out_weight && prob > 0.0) ? pow(prob * (double)n_valid, -beta) : 0.0;
+  }
+  if (out_weight) {  // block maximum
+    double mx = w;
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      mx = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (threadIdx.x == 0) red[0] = mx;
+    }
+    __syncthreads();
+    if (i < size) out_weight[i] = red[0] > 0.0 ? (float)(w / red[0]) : 0.f;
+  }
+  if (st && status) atomicOr(status, st);
+  __syncthreads();  // every thread has read the generator state
+  if (threadIdx.x == 0) {
+    PcgMirror m = m0;
+    m.state = pcg_advance(m.state, m.inc, (uint64_t)size);
+    pcg_store(rng, m);
+  }
+}
+
 __global__ void pcg_advance64_kernel(uint64_t* rng, uint64_t steps) {
   PcgMirror m = pcg_load(rng);
   m.state = pcg_advance(m.state, m.inc, steps);
@@ -306,6 +377,23 @@ extern "C" int isdqn_sample_prioritized(uint64_t* d_rng, const double* d_nodes, 
   ISDQN_LAUNCH_CHECK();
   ISDQN_PROF(as_stream(stream), "pcg_advance");
   pcg_advance64_kernel<<<1, 1, 0, as_stream(stream)>>>(d_rng, (uint64_t)size);
+  ISDQN_LAUNCH_CHECK();
+  return ISDQN_OK;
+}
+
+extern "C" int isdqn_sample_prioritized_train(uint64_t* d_rng, const double* d_nodes, int depth, int32_t size,
+                                              const int32_t* d_n_valid, const int32_t* d_index_to_key, int32_t capacity,
+                                              int32_t* d_out_key, int32_t* d_out_slot, double* d_out_prob,
+                                              const double* d_beta, float* d_out_weight, uint32_t* d_status, void* stream) {
+  if (!d_rng || !d_nodes || !d_n_valid || !d_index_to_key || depth < 1 || depth > 31 || size < 1 || capacity < 1 ||
+      (d_out_weight && !d_beta))
+    return ISDQN_E_INVALID;
+  if (size > 1024) return ISDQN_E_TOO_LARGE;
+  ISDQN_PROF(as_stream(stream), "sample_prioritized");
+  const int threads = ceil_div(size, 32) * 32;
+  sample_prioritized_train_kernel<<<1, threads, 0, as_stream(stream)>>>(d_rng, d_nodes, depth, size, d_n_valid, d_index_to_key,
+                                                                        capacity, d_out_key, d_out_slot, d_out_prob, d_beta,
+                                                                        d_out_weight, d_status);
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

@@ -372,6 +372,9 @@ class iSDQN:
             if device_rb and self.prioritized_beta is not None and hasattr(sd, "update_device"):
                 # prioritized training driver (new: the reference never wires its prioritized sampler to an agent,
                 # SURVEY F10): draw with probabilities, learn with importance weights, write |TD| back — all on the device
+                if (self._dp_world == 1 and self._use_graph and os.environ.get("ISDQN_GRAPH_SAMPLE", "1") != "0"
+                        and self._learn_from_replay(replay_buffer, prioritized=True)):
+                    return
                 B = replay_buffer._batch_size
                 batch_samples, d_keys, d_w = replay_buffer.sample_device(out=self.batch_buffers(B), beta=self.prioritized_beta)
                 self.params, self.optimizer_state, losses = self.learn_on_batch(
@@ -436,18 +439,30 @@ class iSDQN:
 
         return False, {}
 
-    def _learn_from_replay(self, replay_buffer) -> bool:
-        """`rb.sample()` + `learn_on_batch` as ONE graph replay: draw -> gather -> step (uniform device replay only).  The
-        host pushes what it has pending (frames, records, key-map patches) before the replay.  False: not applicable."""
+    def _learn_from_replay(self, replay_buffer, prioritized: bool = False) -> bool:
+        """`rb.sample()` + `learn_on_batch` as ONE graph replay: draw -> gather -> step, and for the prioritized driver
+        draw with importance weights -> gather -> weighted step -> |TD| written back as priorities.  The host pushes what
+        it has pending (frames, records, key-map patches, sum-tree ops) before the replay.  False: not applicable."""
         B = replay_buffer._batch_size
         ctx = self._context(B)
-        plan = ctx.get("rb_plan")
+        name = "rb_plan_prio" if prioritized else "rb_plan"
+        plan = ctx.get(name)
         if plan is None or plan[0] is not replay_buffer:
-            made = replay_buffer.capturable_sample(self.batch_buffers(B)) if hasattr(replay_buffer, "capturable_sample") else None
+            if prioritized:
+                made = (replay_buffer.capturable_prioritized_step(self.batch_buffers(B), ctx["is_weights"])
+                        if hasattr(replay_buffer, "capturable_prioritized_step") else None)
+            else:
+                made = replay_buffer.capturable_sample(self.batch_buffers(B)) if hasattr(replay_buffer, "capturable_sample") else None
             if made is None:
                 return False
-            plan = ctx["rb_plan"] = (replay_buffer,) + tuple(made)
-        _, prepare, enqueue, token = plan
+            plan = ctx[name] = (replay_buffer,) + tuple(made)
+        post = None
+        if prioritized:
+            _, prepare, enqueue, update, set_beta, token = plan
+            td_abs, K, eps = ctx["td_abs"], self.n_bellman_iterations, float(self.prioritized_eps)
+            post = lambda stream_ptr: update(stream_ptr, td_abs, K, eps)
+        else:
+            _, prepare, enqueue, token = plan
         cur = self._torch.cuda.current_stream()
         side = None
         if cur.cuda_stream == 0:  # the legacy default stream cannot be captured
@@ -458,9 +473,11 @@ class iSDQN:
         run = side if side is not None else cur
         with self._torch.cuda.stream(run):
             prepare()
+            if prioritized:
+                set_beta(self.prioritized_beta)
         try:
-            out = self._learn_on_stream(ctx, self.params, self.optimizer_state, B, run.cuda_stream, True, False,
-                                        pre=enqueue, pre_token=token())
+            out = self._learn_on_stream(ctx, self.params, self.optimizer_state, B, run.cuda_stream, True, prioritized,
+                                        pre=enqueue, pre_token=(token(), eps) if prioritized else token(), post=post)
             self._last_step = (out[2], run)
         finally:
             if side is not None:
@@ -501,8 +518,9 @@ class iSDQN:
                 cur.wait_stream(side)
 
     def _learn_on_stream(self, ctx, params, optimizer_state, B, stream, accumulate=False, weighted=False, pre=None,
-                         pre_token=None, batch_slot=None):
-        """pre(stream): launches enqueued in front of the step (the replay draw + gather), captured with it.
+                         pre_token=None, batch_slot=None, post=None):
+        """pre(stream) / post(stream): launches enqueued in front of / behind the step (the replay draw + gather; the
+        priority write-back), captured with it.
         batch_slot: the step reads its batch from that host-batch staging slot instead of the persistent batch buffers."""
         batch = ctx["batch"] if batch_slot is None else ctx["stage"]["batch"][batch_slot]
         key = (params.flat.data_ptr(), optimizer_state["mu"].flat.data_ptr(), optimizer_state["nu"].flat.data_ptr(),
@@ -539,6 +557,11 @@ class iSDQN:
             except _lib.IsdqnNativeError as e:  # (the capture must be closed whatever happened inside it)
                 err = e
             rc = self._lib.isdqn_learn_on_batch(self.network._net, tr, batch, stream)
+            try:
+                if post is not None and err is None and rc == 0:
+                    post(stream)
+            except _lib.IsdqnNativeError as e:
+                err = e
             exec_ = _lib.C.c_void_p()
             rc2 = self._lib.isdqn_graph_end(stream, exec_)
             if err is not None:
@@ -552,6 +575,8 @@ class iSDQN:
             if pre is not None:
                 pre(stream)
             _lib.check(self._lib.isdqn_learn_on_batch(self.network._net, tr, batch, stream), "isdqn_learn_on_batch")
+            if post is not None:
+                post(stream)
             ctx["warm"] += 1
         return params, optimizer_state, ctx["losses"]
 

@@ -527,6 +527,47 @@ class ReplayBuffer:
 
         return prepare, enqueue, token
 
+    def capturable_prioritized_step(self, out: ReplayElement, d_weight, size=None):
+        """The prioritized counterpart of `capturable_sample` for a captured training step: returns
+        (prepare, enqueue, update, set_beta, token) or None.  enqueue(stream_ptr): draw (importance weights into
+        `d_weight`) -> gather into `out`; update(stream_ptr, d_td_abs, rows, offset): priorities of the drawn keys <- mean
+        |TD| (+ offset, ^ alpha); prepare(): pending frames / records / key maps / sum-tree ops; set_beta(beta)."""
+        from .samplers import PrioritizedSamplingDistribution
+
+        sd = self._sampling_distribution
+        if not isinstance(sd, PrioritizedSamplingDistribution) or not self._allocated:
+            return None
+        if size is None:
+            size = self._batch_size
+        if size > 1024:
+            return None
+        _, d_slot, draw, update, set_beta = sd.capturable_train_draw(size, self._slots, d_weight)
+        state, action, reward, nxt, terminal = out
+        lib, S = self._lib, self._stack_size
+
+        def prepare():
+            self._flush()
+            sd._flush_maps()
+            sd._sum_tree.flush()
+
+        def enqueue(stream_ptr: int) -> None:
+            draw(stream_ptr)
+            _lib.check(
+                lib.isdqn_gather_stacks(
+                    self._d_frames.data_ptr(), self._frame_stride, self._frame_elems, self._elem_size, S,
+                    self._d_elem_frames.data_ptr(), self._d_action.data_ptr(), self._d_reward.data_ptr(),
+                    self._d_terminal.data_ptr(), d_slot.data_ptr(), size, _lib.OUT_RAW, state.data_ptr(), nxt.data_ptr(),
+                    action.data_ptr(), reward.data_ptr(), terminal.data_ptr(), stream_ptr,
+                ),
+                "isdqn_gather_stacks",
+            )
+
+        def token():
+            return (id(self), sd._d_index_to_key.data_ptr(), self._d_frames.data_ptr(), size, "prioritized",
+                    sd._d_key_to_index.data_ptr(), sd._sum_tree._d_nodes.data_ptr())
+
+        return prepare, enqueue, update, set_beta, token
+
     def sample_device(self, size=None, out_dtype: int = _lib.OUT_RAW, out: Optional[ReplayElement] = None,
                       return_keys: bool = False, beta: Optional[float] = None):
         """Device-resident `sample`: draw -> key -> slot -> gather without leaving the GPU.  For uint8 stack-4

@@ -425,6 +425,51 @@ class PrioritizedSamplingDistribution(UniformSamplingDistribution):
         self._flush_maps()
         return self._draw_device(size, capacity, want_prob=want_prob)
 
+    def capturable_train_draw(self, size: int, capacity: int, d_weight):
+        """For a captured prioritized training step: (d_key, d_slot, draw, update, set_beta).  draw(stream_ptr) launches the
+        batch draw with the live count and beta read on the device and writes the importance weights into `d_weight`
+        (float32 [size]); update(stream_ptr, d_td_abs, rows, offset) writes the mean |TD| of the drawn keys back as their
+        priorities (isdqn_sumtree_set_keys).  Neither allocates nor reads host state: both can be captured in the learner's
+        CUDA graph.  The caller runs `_flush_maps()` and `self._sum_tree.flush()` before every launch / replay."""
+        t = self._torch
+        lib, tree, cap = self._lib, self._sum_tree, max(int(capacity), 1)
+        d_key = t.empty(size, dtype=t.int32, device=self._device)
+        d_slot = t.empty(size, dtype=t.int32, device=self._device)
+        d_prob = t.empty(size, dtype=t.float64, device=self._device)
+        d_beta = t.zeros(1, dtype=t.float64, device=self._device)
+        ws = t.empty(int(lib.isdqn_sumtree_set_keys_workspace_bytes(size)), dtype=t.uint8, device=self._device)
+        state = {"beta": None}
+
+        def set_beta(beta: float) -> None:
+            if state["beta"] != float(beta):
+                d_beta.fill_(float(beta))
+                state["beta"] = float(beta)
+
+        def draw(stream_ptr: int) -> None:
+            self._last_prob = d_prob
+            _lib.check(
+                lib.isdqn_sample_prioritized_train(
+                    self._d_rng.data_ptr(), tree._d_nodes.data_ptr(), tree._depth, size, self._d_n_valid.data_ptr(),
+                    self._d_index_to_key.data_ptr(), cap, d_key.data_ptr(), d_slot.data_ptr(), d_prob.data_ptr(),
+                    d_beta.data_ptr(), d_weight.data_ptr(), tree._d_status.data_ptr(), stream_ptr,
+                ),
+                "isdqn_sample_prioritized_train",
+            )
+
+        def update(stream_ptr: int, d_td_abs, rows: int, offset: float) -> None:
+            # (n_valid: the table length — a dead key is caught through its -1 entry in the key -> index mirror)
+            _lib.check(
+                lib.isdqn_sumtree_set_keys(
+                    tree._d_nodes.data_ptr(), tree._depth, d_key.data_ptr(), d_td_abs.data_ptr(), 2, int(rows), size, float(offset),
+                    float(self._priority_exponent), self._d_key_to_index.data_ptr(), self._n_slots,
+                    self._d_index_to_key.data_ptr(), int(self._d_index_to_key.numel()), tree._d_max.data_ptr(),
+                    tree._d_status.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr,
+                ),
+                "isdqn_sumtree_set_keys",
+            )
+
+        return d_key, d_slot, draw, update, set_beta
+
     def importance_weights(self, beta: float):
         """Importance-sampling weights of the latest `sample_device(..., want_prob=True)` draw, float32 CUDA tensor:
         (N * P(i)) ** -beta, normalised by the largest weight of the batch (Schaul et al. 2016; new functionality — the

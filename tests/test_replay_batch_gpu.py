@@ -264,3 +264,52 @@ def test_agent_prioritized_update_runs_on_device(mods):
     want = (torch.from_numpy(w).cuda()[None, :] * tdm * tdm).mean(dim=1)
     np.testing.assert_allclose(losses.cpu().numpy(), want.cpu().numpy(), rtol=1e-5)
     np.testing.assert_allclose((tdm * tdm).mean(dim=1).cpu().numpy(), l_plain.cpu().numpy(), rtol=1e-5)
+
+
+def test_captured_prioritized_step_equals_the_launch_by_launch_driver(mods):
+    """The prioritized training step as ONE graph replay (draw with importance weights -> gather -> weighted step -> priority
+    write-back, `isdqn_sample_prioritized_train`) against the same loop run launch by launch (`ISDQN_GRAPH_SAMPLE=0` path:
+    `sample_device(beta=)` + `learn_on_batch` + `update_device`): same draws, same weights, same trees, same parameters —
+    with adds and evictions between the updates and an annealed beta."""
+    import torch
+
+    from isdqn_b200.networks.isdqn import iSDQN
+
+    replay_buffer, samplers = mods
+    cap, B, K = 400, 32, 3
+    rng = np.random.default_rng(5)
+    N0, N1 = 380, 8
+    frames = rng.integers(0, 256, (N0 + 30 * N1, 84, 84), dtype=np.uint8)
+    acts, rews = rng.integers(0, 4, len(frames)), rng.integers(-1, 2, len(frames)).astype(np.float64)
+    terms = rng.random(len(frames)) < 0.01
+
+    def run(captured: bool):
+        rb = replay_buffer.ReplayBuffer(samplers.PrioritizedSamplingDistribution(3, cap), B, cap, stack_size=4, update_horizon=1,
+                                        gamma=0.99, compress=False)
+        rb.add_batch(frames[:N0], acts[:N0], rews[:N0], terms[:N0], priorities="max")
+        agent = iSDQN(0, (84, 84, 4), 4, K, [32, 64, 64, 512], True, False, "cnn", 1e-4, 0.99, 1, 1, 10**9, compute_dtype="bfloat16")
+        weights = []
+        for step in range(1, 31):
+            agent.prioritized_beta = 0.4 + 0.02 * step  # annealed: the captured step reads beta from device memory
+            if captured:
+                assert agent._learn_from_replay(rb, prioritized=True)
+            else:
+                batch, d_keys, d_w = rb.sample_device(out=agent.batch_buffers(B), beta=agent.prioritized_beta)
+                agent.params, agent.optimizer_state, _ = agent.learn_on_batch(agent.params, agent.optimizer_state, batch,
+                                                                              _accumulate=True, is_weights=d_w)
+                rb.update_device(d_keys, agent.td_abs(B), prio_rows=K, offset=agent.prioritized_eps)
+            weights.append(agent._context(B)["is_weights"].cpu().numpy().copy())
+            lo = N0 + (step - 1) * N1  # the buffer keeps moving: 8 adds (evictions from step 3 on) per update
+            rb.add_batch(frames[lo:lo + N1], acts[lo:lo + N1], rews[lo:lo + N1], terms[lo:lo + N1], priorities="max")
+        torch.cuda.synchronize()
+        sd = rb._sampling_distribution
+        sd.check_status()
+        return np.stack(weights), sd._sum_tree._nodes.copy(), agent.params.flat.cpu().numpy(), list(sd._index_to_key)
+
+    w_a, tree_a, p_a, keys_a = run(True)
+    w_b, tree_b, p_b, keys_b = run(False)
+    assert keys_a == keys_b
+    np.testing.assert_allclose(w_a, w_b, rtol=2e-6)
+    assert (w_a.max(axis=1) == 1.0).all() and (w_a > 0).all()
+    np.testing.assert_allclose(tree_a, tree_b, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(p_a, p_b, rtol=0, atol=1e-5 * np.abs(p_b).max())
