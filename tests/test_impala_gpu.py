@@ -166,6 +166,14 @@ def test_impala_bf16_tensor_core_convolutions():
     _check_impala_bf16(dict(IMPALA_84, features=[32, 64, 64, 512]), 32, seed=92)
     _check_impala_bf16(dict(IMPALA_42, features=[32, 32, 64, 128], layer_norm=False), 5, seed=93)
     _check_impala_bf16(dict(IMPALA_42, features=[64, 128, 256, 256]), 3, seed=95)
+    # two hidden Dense layers on the engine; 12 input channels: the first convolution stays on the CUDA cores (no padding
+    # to one 16-byte chunk) inside the tensor-core mode
+    _check_impala_bf16(dict(IMPALA_42, features=[32, 32, 64, 128, 64]), 4, seed=97)
+    agent = _check_impala_bf16(dict(IMPALA_42, obs_dim=(42, 42, 12), features=[32, 64, 64, 128]), 4, seed=98)
+    # acting goes through the same kernels on one observation (2 rows): it runs and returns a valid action
+    state = np.random.default_rng(98).integers(0, 256, (42, 42, 12), dtype=np.uint8)
+    for k in range(3):
+        assert 0 <= int(agent.best_action(agent.params, state, k).item()) < IMPALA_42["A"]
 
 
 def test_impala_bf16_gather_and_tma_problems_agree(monkeypatch):
