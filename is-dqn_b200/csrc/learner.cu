@@ -3,6 +3,7 @@
 // (slimdqn/networks/isdqn.py:82-135) and DQNNet.__call__ (slimdqn/networks/architectures/dqn.py:47-103).
 #include "learner_kernels.cuh"
 #include "impala_kernels.cuh"
+#include "dense_small.cuh"
 #include "plan.cuh"
 
 using namespace isdqn;
@@ -82,6 +83,13 @@ struct DenseTc {
   __nv_bfloat16* dz16;                              // [B][widest hidden layer]: gradient of the pre-activation output
   const __nv_bfloat16* shadow;                      // bf16 parameters, same offsets as the plan's
 };
+bool dense_small_on() {  // A/B: ISDQN_DENSE_SMALL=0 keeps the tiled GEMM for the small-batch Dense layers
+  static const bool on = [] {
+    const char* e = getenv("ISDQN_DENSE_SMALL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 bool dense_tc_ok(const Layer& L) { return L.type == 1 && L.in_dim % 8 == 0 && L.out_dim % 8 == 0; }
 
 // Forward through every layer.  in0/in1: the two halves of concat(s, s') (in1 may be null, n0 = rows then).
@@ -135,7 +143,17 @@ int run_forward(const Plan& p, const Workspace& w, void* ws, const float* params
                                     rows, L.out_dim, L.in_dim, n_parts, s);
         if (rc) return rc;
       }
-      for (int half = 0; half < 2 && !on_tc; ++half) {
+      // few rows: the memory-shaped kernel (dense_small.cuh) instead of the tiled GEMM; same partial layout
+      const bool small_fwd = !on_tc && !direct && rows <= 64 && L.out_dim % 4 == 0 && dense_small_on();
+      if (small_fwd) {
+        ISDQN_PROF(s, "dense_fwd_small");
+        dense_fwd_small_kernel<<<dim3(ceil_div(L.out_dim, 128), real_splits), 256, 0, s>>>(
+            reinterpret_cast<const float*>(first ? in0 : wsp(ws, w.act[l - 1])),
+            reinterpret_cast<const float*>(first ? in1 : nullptr), first ? n0 : rows, rows, L.in_dim, L.out_dim, params + L.w_off,
+            part, split_stride, kps);
+        ISDQN_LAUNCH_CHECK();
+      }
+      for (int half = 0; half < 2 && !on_tc && !small_fwd; ++half) {
         GemmArgs g;
         int m_begin, m_count;
         if (first) {
@@ -245,6 +263,11 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       int rc = isdqn_tc_gemm_bf16(first ? dtc->in16 : dtc->act16[l - 1], L.in_dim, 1, dtc->dz16, L.out_dim, 1, grads + L.w_off,
                                   L.in_dim, L.out_dim, B, 1, s);
       if (rc) return rc;
+    } else if (L.type == 1 && B <= 64 && L.out_dim % 4 == 0 && dense_small_on()) {
+      ISDQN_PROF(s, "dense_wgrad_small");
+      dense_wgrad_small_kernel<<<dim3(ceil_div(L.in_dim, 16), ceil_div(L.out_dim, 512)), 128, 0, s>>>(
+          first ? reinterpret_cast<const float*>(b->d_state) : wsp(ws, w.act[l - 1]), dz, grads + L.w_off, B, L.in_dim, L.out_dim);
+      ISDQN_LAUNCH_CHECK();
     } else if (L.type == 1) {
       GemmArgs g;  // dW[in][out] = X^T dz : A(m'=in, k'=b) = X[b*in_dim + in]
       g.A = first ? reinterpret_cast<const float*>(b->d_state) : wsp(ws, w.act[l - 1]);
@@ -280,6 +303,10 @@ int run_backward(const Plan& p, const Workspace& w, void* ws, const isdqn_train*
       // dX[b][in] = dz[b][out] W^T: A = dz16 [b][out] and B = W16 [in][out] are both K-major
       int rc = isdqn_tc_gemm_bf16(dtc->dz16, L.out_dim, 0, dtc->shadow + L.w_off, L.out_dim, 0, dprev, B, L.in_dim, L.out_dim, 1, s);
       if (rc) return rc;
+    } else if (L.type == 1 && B <= 32 && dense_small_on()) {
+      ISDQN_PROF(s, "dense_dgrad_small");
+      dense_dgrad_small_kernel<<<ceil_div(L.in_dim, 32), 256, 0, s>>>(dz, params + L.w_off, dprev, B, L.in_dim, L.out_dim);
+      ISDQN_LAUNCH_CHECK();
     } else if (L.type == 1) {
       GemmArgs g;  // dX[b][in] = dz[b][out] W^T : B(k=out, n=in) = W[in*out_dim + out]
       g.A = dz; g.sam = L.out_dim; g.sak = 1;
