@@ -210,10 +210,18 @@ sample_prioritized_train_kernel(uint64_t* __restrict__ rng, const double* __rest
                                 int32_t* __restrict__ out_key, int32_t* __restrict__ out_slot, double* __restrict__ out_prob,
                                 const double* __restrict__ beta_dev, float* __restrict__ out_weight, uint32_t* status) {
   __shared__ double red[32];
+  // the top kTopLevels levels of the heap, loaded in one cooperative round trip: a draw is a chain of (depth - 1) dependent
+  // 8-byte reads, and with one CTA there is nothing to hide their latency behind — 11 of the 20 come out of shared memory
+  constexpr int kTopLevels = 11;
+  __shared__ double top[(1 << kTopLevels) - 1];
+  const int cached_levels = depth - 1 < kTopLevels ? depth - 1 : kTopLevels;
+  const int n_top = (1 << cached_levels) - 1;
+  for (int j = threadIdx.x; j < n_top; j += blockDim.x) top[j] = __ldg(nodes + j);
   const double beta = beta_dev ? *beta_dev : 0.0;
   const PcgMirror m0 = pcg_load(rng);
   const int n_valid = *n_valid_dev;
-  const double root = nodes[0];
+  __syncthreads();
+  const double root = n_top > 0 ? top[0] : nodes[0];
   const int first_leaf = (1 << (depth - 1)) - 1;
   const int i = threadIdx.x;
   uint32_t st = 0;
@@ -227,13 +235,14 @@ sample_prioritized_train_kernel(uint64_t* __restrict__ rng, const double* __rest
     int node = 0;
     for (int level = 0; level < depth - 1; ++level) {
       const int left = 2 * node + 1;
-      const double ls = __ldg(nodes + left);
+      const bool in_top = left + 1 < n_top;
+      const double ls = in_top ? top[left] : __ldg(nodes + left);
       if (t < ls) {
         node = left;
       } else {
         node = left + 1;
         t = t - ls;
-        if (level + 1 < depth - 1 && !(t < __ldg(nodes + left + 1))) st |= ISDQN_ST_DESCENT_ASSERT;
+        if (level + 1 < depth - 1 && !(t < (in_top ? top[left + 1] : __ldg(nodes + left + 1)))) st |= ISDQN_ST_DESCENT_ASSERT;
       }
     }
     const int32_t index = node - first_leaf;
@@ -390,7 +399,7 @@ extern "C" int isdqn_sample_prioritized_train(uint64_t* d_rng, const double* d_n
     return ISDQN_E_INVALID;
   if (size > 1024) return ISDQN_E_TOO_LARGE;
   ISDQN_PROF(as_stream(stream), "sample_prioritized");
-  const int threads = ceil_div(size, 32) * 32;
+  const int threads = size <= 256 ? 256 : ceil_div(size, 32) * 32;  // (idle threads still help load the top of the heap)
   sample_prioritized_train_kernel<<<1, threads, 0, as_stream(stream)>>>(d_rng, d_nodes, depth, size, d_n_valid, d_index_to_key,
                                                                         capacity, d_out_key, d_out_slot, d_out_prob, d_beta,
                                                                         d_out_weight, d_status);

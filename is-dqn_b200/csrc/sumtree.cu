@@ -452,21 +452,15 @@ sumtree_set_ops_kernel(double* nodes, int depth, const int32_t* __restrict__ op_
 // PRIO: 0 = float64 [n], 1 = float32 [n], 2 = float32 [prio_rows][n] averaged over the rows in ascending order (the per-head
 // |TD| matrix the loss kernel writes).  A key that is not live sets ISDQN_ST_KEY_MISSING and the abort flag (the
 // reference raises KeyError before it touches the tree).
-__global__ void __launch_bounds__(256)
-sumtree_keys_to_set_kernel(const int32_t* __restrict__ keys, const void* __restrict__ prio, int prio_kind, int prio_rows, int n,
-                           double prio_offset, double alpha, const int32_t* __restrict__ key_slot_to_index, int n_slots,
-                           const int32_t* __restrict__ index_to_key, int n_valid, int32_t* __restrict__ out_idx,
-                           double* __restrict__ out_val, int32_t* abort_flag, uint32_t* status) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// one entry of that translation: (dense index, priority ** alpha) of keys[i]; returns false for a key that is not live
+__device__ __forceinline__ bool key_to_entry(int i, const int32_t* __restrict__ keys, const void* __restrict__ prio, int prio_kind,
+                                             int prio_rows, int n, double prio_offset, double alpha,
+                                             const int32_t* __restrict__ key_slot_to_index, int n_slots,
+                                             const int32_t* __restrict__ index_to_key, int n_valid, int32_t* idx_out, double* p_out) {
   const int32_t key = keys[i];
   const int slot = (int)((((int64_t)key % n_slots) + n_slots) % n_slots);
   const int32_t idx = key_slot_to_index[slot];
   const bool live = idx >= 0 && idx < n_valid && index_to_key[idx] == key;
-  if (!live) {
-    if (status) atomicOr(status, ISDQN_ST_KEY_MISSING);
-    atomicExch(abort_flag, 1);
-  }
   double p;
   if (prio_kind == 0) {
     p = reinterpret_cast<const double*>(prio)[i];
@@ -479,8 +473,45 @@ sumtree_keys_to_set_kernel(const int32_t* __restrict__ keys, const void* __restr
   }
   p += prio_offset;
   if (!(alpha == 1.0)) p = p == 0.0 ? 0.0 : pow(p, alpha);
-  out_idx[i] = live ? idx : 0;
+  *idx_out = live ? idx : 0;
+  *p_out = p;
+  return live;
+}
+
+__global__ void __launch_bounds__(256)
+sumtree_keys_to_set_kernel(const int32_t* __restrict__ keys, const void* __restrict__ prio, int prio_kind, int prio_rows, int n,
+                           double prio_offset, double alpha, const int32_t* __restrict__ key_slot_to_index, int n_slots,
+                           const int32_t* __restrict__ index_to_key, int n_valid, int32_t* __restrict__ out_idx,
+                           double* __restrict__ out_val, int32_t* abort_flag, uint32_t* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t idx;
+  double p;
+  if (!key_to_entry(i, keys, prio, prio_kind, prio_rows, n, prio_offset, alpha, key_slot_to_index, n_slots, index_to_key, n_valid,
+                    &idx, &p)) {
+    if (status) atomicOr(status, ISDQN_ST_KEY_MISSING);
+    atomicExch(abort_flag, 1);
+  }
+  out_idx[i] = idx;
   out_val[i] = p;
+}
+
+// n <= 32 (the priority update of one training batch): translation and set in ONE warp-sized launch — lane = entry
+__global__ void __launch_bounds__(32)
+sumtree_keys_set_warp_kernel(double* nodes, int depth, const int32_t* __restrict__ keys, const void* __restrict__ prio,
+                             int prio_kind, int prio_rows, int n, double prio_offset, double alpha,
+                             const int32_t* __restrict__ key_slot_to_index, int n_slots,
+                             const int32_t* __restrict__ index_to_key, int n_valid, double* max_prio, uint32_t* status) {
+  const int lane = threadIdx.x;
+  int32_t idx = 0;
+  double p = 0.0;
+  bool dead = false;
+  if (lane < n)
+    dead = !key_to_entry(lane, keys, prio, prio_kind, prio_rows, n, prio_offset, alpha, key_slot_to_index, n_slots, index_to_key,
+                         n_valid, &idx, &p);
+  if (dead && status) atomicOr(status, ISDQN_ST_KEY_MISSING);
+  if (__any_sync(0xffffffffu, dead)) return;  // the reference raises KeyError before it touches the tree
+  sumtree_set_warp<false>(nodes, depth, n, idx, p, max_prio, status);
 }
 
 __global__ void clear_flag_kernel(int32_t* flag) { *flag = 0; }
@@ -567,6 +598,13 @@ extern "C" int isdqn_sumtree_set_keys(double* d_nodes, int depth, const int32_t*
   if (n > 1024) return ISDQN_E_TOO_LARGE;
   if (workspace_bytes < isdqn_sumtree_set_keys_workspace_bytes(n)) return ISDQN_E_INVALID;
   cudaStream_t s = as_stream(stream);
+  if (n <= 32 && warp_set_enabled()) {
+    ISDQN_PROF(s, "sumtree_keys_set");
+    sumtree_keys_set_warp_kernel<<<1, 32, 0, s>>>(d_nodes, depth, d_keys, d_priorities, prio_kind, prio_rows, n, prio_offset, alpha,
+                                                  d_key_slot_to_index, n_slots, d_index_to_key, n_valid, d_max_priority, d_status);
+    ISDQN_LAUNCH_CHECK();
+    return ISDQN_OK;
+  }
   int32_t* flag = reinterpret_cast<int32_t*>(d_workspace);
   int32_t* idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + 16);
   double* val = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(d_workspace) + 16 + ((int64_t)n * 4 + 15) / 16 * 16);
