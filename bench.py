@@ -434,6 +434,13 @@ def run_ours(args, rank, world, local_rank):
                 ms_i, ms_i_e2e, _, _, _ = measure_agent(agent_i, rb, n_i, 3, lambda: torch.cuda.synchronize(), stream, local_rank)
                 impala["params"] = agent_i.network.n_params
                 impala[name] = {"steps": n_i, "value": n_i / (ms_i / 1e3), "ms_per_step": ms_i / n_i, "e2e": n_i / (ms_i_e2e / 1e3)}
+                obs_i = np.random.default_rng(5).integers(0, 256, OBS, dtype=np.uint8)
+                for i in range(10):
+                    agent_i.best_action(agent_i.params, obs_i, i).item()
+                t_i = time.perf_counter()
+                for i in range(50):
+                    agent_i.best_action(agent_i.params, obs_i, i).item()
+                impala[name]["acting_us_per_action"] = (time.perf_counter() - t_i) / 50 * 1e6
                 del agent_i
         # ---- replay throughput shape: 2048 batches of 32 per launch (sampler + gather only)
         n_big = 2048 * BATCH
