@@ -15,7 +15,7 @@ build/%.o: $(PKG)/csrc/%.cu $(HDRS)
 
 $(LIB): $(OBJS)
 	@mkdir -p $(PKG)/lib
-	$(NVCC) -shared -o $@ $(OBJS) -ldl -Xlinker --version-script=$(PKG)/csrc/exports.map
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -ldl -Xlinker --version-script=$(PKG)/csrc/exports.map
 
 # optional: the XLA FFI handlers (needs xla/ffi/api/ffi.h, e.g. XLA_FFI_INCLUDE=$$(python -c "import jaxlib,os;print(os.path.join(jaxlib.__path__[0],'include'))"))
 ffi: $(LIB)
