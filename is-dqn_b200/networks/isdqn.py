@@ -199,7 +199,8 @@ class iSDQN:
             if nb <= 0:
                 raise _lib.IsdqnNativeError(
                     "compute_dtype='bfloat16' needs a cnn with 32/64/128/256-channel convolutions and hidden Dense "
-                    "widths that are multiples of 64; use compute_dtype='float32' for this network"
+                    "widths that are multiples of 64, or an impala network with 32/64/128/256-channel stacks; use "
+                    "compute_dtype='float32' for this network"
                 )
             ctx["ws_tc"] = t.empty(nb, dtype=t.uint8, device="cuda")
         # double-buffered pinned + device staging for host batches (the reference's implicit device_put at the jit
