@@ -112,7 +112,11 @@ __global__ void __launch_bounds__(kGemmThreads) conv_fwd_kernel(const ConvArgs a
 
   const int a_kk = tid % kBK, a_r0 = tid / kBK;
   constexpr int A_ROWS_PER_PASS = kGemmThreads / kBK;
-  for (int k0 = 0; k0 < a.K; k0 += kBK) {
+  constexpr int NA = BM / A_ROWS_PER_PASS, NB = kBK * BN / kGemmThreads;
+  // software pipeline: the global loads of chunk k0 + kBK are in registers while chunk k0 is multiplied (at batch 32 the
+  // grids are 1-3 CTAs per SM: nothing else hides the load latency).  Same loads, same order of additions.
+  float ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
     {  // A tile: im2col gather, k (= ky,kx,c with c fastest: contiguous in NHWC) fastest across lanes
       const int k = k0 + a_kk;
       const bool kvalid = k < a.K;
@@ -120,7 +124,8 @@ __global__ void __launch_bounds__(kGemmThreads) conv_fwd_kernel(const ConvArgs a
       const int t = k / a.Cin;
       const int kx = t % a.ksz, ky = t / a.ksz;
 #pragma unroll
-      for (int r = a_r0; r < BM; r += A_ROWS_PER_PASS) {
+      for (int q = 0; q < NA; ++q) {
+        const int r = a_r0 + q * A_ROWS_PER_PASS;
         float v = 0.f;
         const int img = ri_img[r];
         const int iy = ri_iy0[r] + ky, ix = ri_ix0[r] + kx;
@@ -130,15 +135,28 @@ __global__ void __launch_bounds__(kGemmThreads) conv_fwd_kernel(const ConvArgs a
           const int li = second ? img - a.n_img0 : img;
           v = read_in<KIND>(src, (((int64_t)li * a.H + iy) * a.W + ix) * a.Cin + c);
         }
-        As[a_kk][r] = v;
+        ra[q] = v;
       }
     }
-    for (int i = tid; i < kBK * BN; i += kGemmThreads) {  // B tile: weights, n fastest
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {  // B tile: weights, n fastest
+      const int i = tid + q * kGemmThreads;
       const int nn = i % BN, kk = i / BN;
       const int k = k0 + kk;
-      Bs[kk][nn] = (k < a.K && nn < a.Cout) ? __ldg(a.w + (int64_t)k * a.Cout + nn) : 0.f;
+      rb[q] = (k < a.K && nn < a.Cout) ? __ldg(a.w + (int64_t)k * a.Cout + nn) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < a.K; k0 += kBK) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) As[a_kk][a_r0 + q * A_ROWS_PER_PASS] = ra[q];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int i = tid + q * kGemmThreads;
+      Bs[i / BN][i % BN] = rb[q];
     }
     __syncthreads();
+    if (k0 + kBK < a.K) fetch(k0 + kBK);
     tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
     __syncthreads();
   }
@@ -348,7 +366,10 @@ static __global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const C
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   const int a_kk = tid % kBK, a_r0 = tid / kBK;
-  for (int k0 = 0; k0 < a.Kd; k0 += kBK) {
+  constexpr int PASS = kGemmThreads / kBK, NA = BM / PASS, NB = BN / PASS;
+  // software pipeline (as in conv_fwd_kernel): the next chunk's global loads are in registers while this one is multiplied
+  float ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
     const int k = k0 + a_kk;
     const int co = k % a.Cout;
     const int t = k / a.Cout;
@@ -356,20 +377,29 @@ static __global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const C
     const int ky = ry + s * ty_, kx = rx + s * tx_;
     const bool tapvalid = k < a.Kd && ky < a.ksz && kx < a.ksz;
 #pragma unroll
-    for (int r = a_r0; r < BM; r += kGemmThreads / kBK) {
+    for (int q = 0; q < NA; ++q) {
+      const int r = a_r0 + q * PASS;
       float v = 0.f;
       const int img = ri_img[r];
       const int oy = ri_oy[r] - ty_, ox = ri_ox[r] - tx_;
       if (tapvalid && img >= 0 && (unsigned)oy < (unsigned)a.OH && (unsigned)ox < (unsigned)a.OW)
         v = a.dz[(((int64_t)img * a.OH + oy) * a.OW + ox) * a.Cout + co];
-      As[a_kk][r] = v;
+      ra[q] = v;
     }
 #pragma unroll
-    for (int nn = a_r0; nn < BN; nn += kGemmThreads / kBK) {  // B tile: W[ky][kx][c][co], co (= k) fastest
-      const int cc = n0 + nn;
-      Bs[a_kk][nn] = (tapvalid && cc < a.Cin) ? __ldg(a.w + (((int64_t)ky * a.ksz + kx) * a.Cin + cc) * a.Cout + co) : 0.f;
+    for (int q = 0; q < NB; ++q) {  // B tile: W[ky][kx][c][co], co (= k) fastest
+      const int cc = n0 + a_r0 + q * PASS;
+      rb[q] = (tapvalid && cc < a.Cin) ? __ldg(a.w + (((int64_t)ky * a.ksz + kx) * a.Cin + cc) * a.Cout + co) : 0.f;
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < a.Kd; k0 += kBK) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) As[a_kk][a_r0 + q * PASS] = ra[q];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) Bs[a_kk][a_r0 + q * PASS] = rb[q];
     __syncthreads();
+    if (k0 + kBK < a.Kd) fetch(k0 + kBK);
     tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
     __syncthreads();
   }
