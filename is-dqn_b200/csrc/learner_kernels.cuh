@@ -241,7 +241,6 @@ __global__ void __launch_bounds__(kGemmThreads) conv_wgrad_kernel(const ConvWgra
   typedef TileCfg<BM, BN, TN> Cfg;
   __shared__ __align__(16) float As[kBK][BM + 4];
   __shared__ __align__(16) float Bs[kBK][BN + 4];
-  __shared__ int ri_img[kBK], ri_iy0[kBK], ri_ix0[kBK];
   const int tid = threadIdx.x;
   const int kc0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int tx = tid % Cfg::LANES_N, ty = tid / Cfg::LANES_N;
@@ -263,38 +262,52 @@ __global__ void __launch_bounds__(kGemmThreads) conv_wgrad_kernel(const ConvWgra
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int mb = m_begin; mb < m_end; mb += kBK) {
-    if (tid < kBK) {
-      const int m = mb + tid;
-      if (m < m_end) {
-        const int img = m / (a.OH * a.OW);
-        const int rem = m - img * (a.OH * a.OW);
-        const int oy = rem / a.OW, ox = rem - oy * a.OW;
-        ri_img[tid] = img;
-        ri_iy0[tid] = oy * a.stride - a.pad_y;
-        ri_ix0[tid] = ox * a.stride - a.pad_x;
-      } else {
-        ri_img[tid] = -1;
-        ri_iy0[tid] = ri_ix0[tid] = 0;
+  // software pipeline (as in conv_fwd_kernel): the next chunk's global loads are in registers while this one is multiplied.
+  // Every thread tracks the output pixel (image, oy, ox) of the NA im2col rows it gathers and steps them by kBK per chunk.
+  constexpr int PA = kGemmThreads / BM, NA = kBK / PA, PB = kGemmThreads / BN, NB = kBK / PB;
+  int p_img[NA], p_oy[NA], p_ox[NA];
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    const int m = m_begin + a_kk0 + q * PA;
+    p_img[q] = m / (a.OH * a.OW);
+    const int rem = m - p_img[q] * (a.OH * a.OW);
+    p_oy[q] = rem / a.OW;
+    p_ox[q] = rem - p_oy[q] * a.OW;
+  }
+  float ra[NA], rb[NB];
+  auto fetch = [&](int mb) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int m = mb + a_kk0 + q * PA;
+      float v = 0.f;
+      const int iy = p_oy[q] * a.stride - a.pad_y + ky, ix = p_ox[q] * a.stride - a.pad_x + kx;
+      if (kcvalid && m < m_end && (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
+        v = read_in<KIND>(a.in, (((int64_t)p_img[q] * a.H + iy) * a.W + ix) * a.Cin + c);
+      ra[q] = v;
+      p_ox[q] += kBK;  // the row this slot gathers in the next chunk
+      while (p_ox[q] >= a.OW) {
+        p_ox[q] -= a.OW;
+        if (++p_oy[q] == a.OH) {
+          p_oy[q] = 0;
+          ++p_img[q];
+        }
       }
     }
-    __syncthreads();
 #pragma unroll
-    for (int kk = a_kk0; kk < kBK; kk += kGemmThreads / BM) {
-      float v = 0.f;
-      const int img = ri_img[kk];
-      const int iy = ri_iy0[kk] + ky, ix = ri_ix0[kk] + kx;
-      if (kcvalid && img >= 0 && (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
-        v = read_in<KIND>(a.in, (((int64_t)img * a.H + iy) * a.W + ix) * a.Cin + c);
-      As[kk][a_mm] = v;
-    }
-#pragma unroll
-    for (int kk = b_kk0; kk < kBK; kk += kGemmThreads / BN) {
-      const int m = mb + kk;
+    for (int q = 0; q < NB; ++q) {
+      const int m = mb + b_kk0 + q * PB;
       const int n = n0 + b_nn;
-      Bs[kk][b_nn] = (m < m_end && n < a.Cout) ? a.dz[(int64_t)m * a.Cout + n] : 0.f;
+      rb[q] = (m < m_end && n < a.Cout) ? a.dz[(int64_t)m * a.Cout + n] : 0.f;
     }
+  };
+  if (m_begin < m_end) fetch(m_begin);
+  for (int mb = m_begin; mb < m_end; mb += kBK) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) As[a_kk0 + q * PA][a_mm] = ra[q];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) Bs[b_kk0 + q * PB][b_nn] = rb[q];
     __syncthreads();
+    if (mb + kBK < m_end) fetch(mb + kBK);
     tile_fma<BM, BN, TN>(As, Bs, acc, ty, tx);
     __syncthreads();
   }
