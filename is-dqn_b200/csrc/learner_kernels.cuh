@@ -817,7 +817,16 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ wh, cons
       dy[j] = xh[j] = 0.f;
       if (n < C) {
         float dv = 0.f;
-        for (int i = 0; i < nnz; ++i) dv = fmaf(nzv[i], __ldg(wh + (int64_t)n * NH + nzk[i]), dv);
+        // four head-kernel loads in flight at a time (nnz is ~K: one dependent L2 round trip per entry otherwise); the
+        // additions keep their order
+        for (int i0 = 0; i0 < nnz; i0 += 4) {
+          float w4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w4[u] = i0 + u < nnz ? __ldg(wh + (int64_t)n * NH + nzk[i0 + u]) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u < nnz) dv = fmaf(nzv[i0 + u], w4[u], dv);
+        }
         const int64_t idx = (int64_t)r * C + n;
         if (ln_g) {
           xh[j] = xhat[idx];
