@@ -215,9 +215,13 @@ int launch_conv_dgrad_f32(const Layer& L, int n_img, const float* dz, const floa
   a.Kd = a.taps * a.taps * L.out_dim;
   a.dz = dz; a.w = w; a.dx = dx;
   const int rows_max = n_img * ceil_div(L.H, L.stride) * ceil_div(L.W, L.stride);
-  dim3 grid(ceil_div(rows_max, 64), ceil_div(L.Cin, 64), L.stride * L.stride);
+  const int cy = ceil_div(L.Cin, 64), cz = L.stride * L.stride;
   ISDQN_PROF(s, "conv_dgrad");
-  conv_dgrad_kernel<<<grid, kGemmThreads, 0, s>>>(a);
+  if (ceil_div(rows_max, 64) * cy * cz < 2 * kNumSMs) {  // small grid: 32-row tiles
+    conv_dgrad_kernel<32, 4><<<dim3(ceil_div(rows_max, 32), cy, cz), kGemmThreads, 0, s>>>(a);
+  } else {
+    conv_dgrad_kernel<64, 8><<<dim3(ceil_div(rows_max, 64), cy, cz), kGemmThreads, 0, s>>>(a);
+  }
   ISDQN_LAUNCH_CHECK();
   return ISDQN_OK;
 }

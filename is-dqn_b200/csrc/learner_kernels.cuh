@@ -335,8 +335,10 @@ struct ConvDgradArgs {
   float* dx;        // [n_img*H*W][Cin]
 };
 
-static __global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const ConvDgradArgs a) {
-  constexpr int BM = 64, BN = 64, TN = 8;
+// <64, 8>: 64 x 64 tiles; <32, 4>: 32 x 64 tiles — twice the CTAs for the small grids of a batch-32 step
+template <int BM, int TN>
+__global__ void __launch_bounds__(kGemmThreads) conv_dgrad_kernel(const ConvDgradArgs a) {
+  constexpr int BN = 64;
   typedef TileCfg<BM, BN, TN> Cfg;
   __shared__ __align__(16) float As[kBK][BM + 4];
   __shared__ __align__(16) float Bs[kBK][BN + 4];
