@@ -27,13 +27,21 @@ dense_fwd_small_kernel(const float* __restrict__ in0, const float* __restrict__ 
   for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k0 = k_begin; k0 < k_end; k0 += kDsK) {
     // stage x[0..64)[k0 .. k0 + kDsK) transposed: k fastest across the lanes, so the global reads are coalesced
-#pragma unroll 7
-    for (int idx = threadIdx.x; idx < 64 * kDsK; idx += 256) {
+    // (all 28 loads of a thread are issued before the first store: one exposed round trip per pass, not four)
+    float sv[64 * kDsK / 256];
+#pragma unroll
+    for (int j = 0; j < 64 * kDsK / 256; ++j) {
+      const int idx = threadIdx.x + j * 256;
       const int kk = idx % kDsK, r = idx / kDsK;
       const int k = k0 + kk;
       float v = 0.f;
-      if (r < rows && k < k_end) v = r < n0 ? in0[(int64_t)r * K + k] : in1[(int64_t)(r - n0) * K + k];
-      reinterpret_cast<float*>(&As[kk][0])[r] = v;
+      if (r < rows && k < k_end) v = r < n0 ? __ldg(in0 + (int64_t)r * K + k) : __ldg(in1 + (int64_t)(r - n0) * K + k);
+      sv[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < 64 * kDsK / 256; ++j) {
+      const int idx = threadIdx.x + j * 256;
+      reinterpret_cast<float*>(&As[idx % kDsK][0])[idx / kDsK] = sv[j];
     }
     __syncthreads();
     const int kmax = min(kDsK, k_end - k0);
